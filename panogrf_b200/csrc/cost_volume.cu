@@ -1,0 +1,433 @@
+// K1 — fused 360° spherical-sweep cost volume for sm_100a.
+//
+// Replaces the reference's per-depth python loop
+//   models/spherical_cost_volume.py:231-341 (calculate_cost_volume_erp), :135-230 (get_cv_per_depth)
+//   models/spherical_cost_volume_mv.py:219-347 (multi-view mean)
+//   helpers/my_torch_helpers.py:12-120 (spherical <-> cartesian)
+//   network/omni_mvsnet/pipeline3_model.py:849-853 (group-wise mean, fused as an epilogue)
+// with ONE launch that never materialises the warped (B,D,C,H,W) source volume.
+//
+// Work decomposition (HBM-write bound: 4*C bytes/voxel out, features stay L2/L1 resident):
+//   CTA  = 4 warps = one ERP row segment of 128 pixels x a chunk of depth hypotheses
+//   warp = 32 consecutive pixels, loops over the depth chunk
+//   phase A (lane <-> pixel): ray * depth -> rigid transform -> (theta,phi) -> uv -> tap record in smem
+//   phase B (lane <-> (pixel, float4 channel group)): 4 x 128-bit gathers per source view (each
+//            bilinear tap of a pixel is one contiguous C*4-byte line of the channels-last map),
+//            cost vs. the reference feature held in registers, accumulation over source views
+//   epilogue: channels-last -> direct 128-bit streaming stores (512 B contiguous per warp store);
+//             planar (B,D,C,H,W)/(B,C,D,H,W)/group-mean -> conflict-free smem transpose, 128-B row stores
+#include "common.cuh"
+
+namespace pgrf {
+
+constexpr int kCvWarps = 4;
+constexpr int kCvThreads = kCvWarps * 32;
+constexpr int kMaxSrc = 8;
+
+struct CvParams {
+  const float* images;
+  const float* depths;
+  const float* depth_volume;
+  const float* rots;
+  const float* trans;
+  float* out;
+  int* err;
+  int B, S, H, W, D;
+  int ref_idx, n_src;
+  int src_views[kMaxSrc];
+  float divisor;
+  int dataset, cost_type, groups, OC;
+  int d_chunk;
+  long long sB, sD, sC;  // planar strides in elements
+  float ang0, ang1, ang2, ang3;  // per-dataset pixel->angle constants (see host side)
+};
+
+struct __align__(16) TapRec {
+  float tx, ty;   // fractional offsets inside the 2x2 footprint
+  int off4;       // float4 index of the (y0,x0) texel inside one (H,W,C) view
+  unsigned mask;  // bit0 nw, bit1 ne, bit2 sw, bit3 se: tap inside the map (zeros padding)
+};
+
+// ---- pixel -> unit ray, per dataset (spherical_cost_volume.py:272-301, my_torch_helpers.py:33-58) ----
+__device__ __forceinline__ void pixel_ray(const CvParams& p, int x, int y, float& rx, float& ry, float& rz) {
+  const float fx = (float)x, fy = (float)y;
+  float theta, phi;
+  switch (p.dataset) {
+    case PGRF_DS_M3D:
+      phi = (fy + 0.5f) * p.ang0;                       // (phi+0.5)*(pi/H)
+      theta = (fx + 0.5f) * p.ang1 - PGRF_HALF_PI_F;    // (theta+0.5)*(2pi/W) - pi/2
+      break;
+    case PGRF_DS_REPLICA_TEST:
+      theta = p.ang1 * (fx + 0.5f) - PGRF_PI_F;
+      phi = (-(fy + 0.5f) * PGRF_PI_F) / p.ang0 + PGRF_HALF_PI_F;   // ang0 = H
+      break;
+    case PGRF_DS_RESIDENTIAL:
+      theta = PGRF_PI_F * ((2.f * fx) / p.ang1 - 1.5f);             // ang1 = W-1
+      phi = PGRF_PI_F * (0.5f - fy / p.ang0);                       // ang0 = H-1
+      break;
+    default:  // CoffeeArea
+      theta = p.ang1 * fx + PGRF_TWO_PI_F;                          // ang1 = -2pi/(W-1)
+      phi = p.ang0 * fy;                                            // ang0 = pi/(H-1)
+      break;
+  }
+  float st, ct, sp, cp;
+  sincosf(theta, &st, &ct);
+  sincosf(phi, &sp, &cp);
+  switch (p.dataset) {
+    case PGRF_DS_M3D:          rx = sp * ct; ry = cp;  rz = sp * st; break;
+    case PGRF_DS_REPLICA_TEST: rx = st * cp; ry = -sp; rz = ct * cp; break;
+    case PGRF_DS_RESIDENTIAL:  rx = ct * cp; ry = sp;  rz = st * cp; break;
+    default:                   rx = sp * ct; ry = sp * st; rz = cp;  break;
+  }
+}
+
+// ---- camera-frame point -> normalised (u,v) (my_torch_helpers.py:62-120 + spherical_cost_volume.py:153-190) ----
+__device__ __forceinline__ void point_uv(int dataset, float cx, float cy, float cz, float& u, float& v) {
+  const float kLin = 0.17453292519943295f;       // deg2rad(10)
+  const float kCosDeg = 0.984807753012208f;      // cos(10 deg)
+  const float kOneMinusCos = 0.015192246987791981f;
+  const float radius = sqrtf(cx * cx + cy * cy + cz * cz);
+  float uu, vv;
+  switch (dataset) {
+    case PGRF_DS_M3D: {
+      const float theta = atan2f(cz, cx);
+      const float yr = cy / radius;
+      float phi;
+      if (fabsf(yr) < kCosDeg) phi = acosf(yr);
+      else if (cy >= 0.f) phi = kLin * (1.f - yr) / kOneMinusCos;       // acos linearised near the poles
+      else phi = PGRF_PI_F - kLin * (yr + 1.f) / kOneMinusCos;
+      uu = fmod_two_pi(theta + PGRF_HALF_PI_F + PGRF_TWO_PI_F);
+      vv = phi;
+      break;
+    }
+    case PGRF_DS_REPLICA_TEST: {
+      const float theta = atan2f(cx, cz);
+      const float phi = -asinf(cz / radius);      // sic (reference :99 uses z)
+      uu = fmod_two_pi(theta + PGRF_PI_F + PGRF_TWO_PI_F);
+      vv = -phi + PGRF_HALF_PI_F;
+      break;
+    }
+    case PGRF_DS_RESIDENTIAL: {
+      float theta = -atan2f(-cz, cx);
+      const float phi = asinf(cy / radius);
+      if (theta > PGRF_HALF_PI_F && theta <= PGRF_TWO_PI_F) theta -= PGRF_TWO_PI_F;
+      uu = fmod_two_pi(theta + 4.71238898038468985769f);   // 3/4 * 2pi
+      vv = PGRF_HALF_PI_F - phi;
+      break;
+    }
+    default: {
+      float theta = atan2f(cy, cx);
+      const float phi = acosf(cz / radius);
+      if (theta < 0.f) theta += PGRF_TWO_PI_F;
+      uu = PGRF_TWO_PI_F - theta;
+      vv = phi;
+      break;
+    }
+  }
+  u = uu / PGRF_PI_F - 1.f;
+  v = 2.f * vv / PGRF_PI_F - 1.f;
+}
+
+template <int C, bool PLANAR>
+__global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams p) {
+  constexpr int CG = C / 4;      // lanes (float4 channel groups) per pixel
+  constexpr int PPS = 32 / CG;   // pixels per sub-iteration of phase B
+  constexpr int NSUB = 32 / PPS; // sub-iterations to cover the warp's 32 pixels
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float s_A[kMaxSrc][12];  // per source view: A = R_s * R_ref^-1 (row-major 3x3), b = t_s - A t_ref
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = (p.W + kCvThreads - 1) / kCvThreads;
+  const int y = blockIdx.x / tiles_x;
+  const int x_warp = (blockIdx.x % tiles_x) * kCvThreads + warp * 32;
+  const int b = blockIdx.z;
+  const int d_begin = blockIdx.y * p.d_chunk;
+  const int d_end = min(p.D, d_begin + p.d_chunk);
+
+  TapRec* rec = reinterpret_cast<TapRec*>(smem_raw) + warp * (p.n_src * 32);
+  float* tile = reinterpret_cast<float*>(smem_raw + (size_t)kCvWarps * p.n_src * 32 * sizeof(TapRec)) +
+                warp * (C * 33);
+
+  // Relative pose of every swept view w.r.t. the reference view, in fp64, rounded once to fp32.
+  if (threadIdx.x < p.n_src) {
+    const int s = p.src_views[threadIdx.x];
+    const float* Rr = p.rots + ((size_t)b * p.S + p.ref_idx) * 9;
+    const float* tr = p.trans + ((size_t)b * p.S + p.ref_idx) * 3;
+    const float* Rs = p.rots + ((size_t)b * p.S + s) * 9;
+    const float* ts = p.trans + ((size_t)b * p.S + s) * 3;
+    double r[9], inv[9];
+    for (int i = 0; i < 9; ++i) r[i] = Rr[i];
+    const double det = r[0] * (r[4] * r[8] - r[5] * r[7]) - r[1] * (r[3] * r[8] - r[5] * r[6]) +
+                       r[2] * (r[3] * r[7] - r[4] * r[6]);
+    const double id = 1.0 / det;
+    inv[0] = (r[4] * r[8] - r[5] * r[7]) * id; inv[1] = (r[2] * r[7] - r[1] * r[8]) * id; inv[2] = (r[1] * r[5] - r[2] * r[4]) * id;
+    inv[3] = (r[5] * r[6] - r[3] * r[8]) * id; inv[4] = (r[0] * r[8] - r[2] * r[6]) * id; inv[5] = (r[2] * r[3] - r[0] * r[5]) * id;
+    inv[6] = (r[3] * r[7] - r[4] * r[6]) * id; inv[7] = (r[1] * r[6] - r[0] * r[7]) * id; inv[8] = (r[0] * r[4] - r[1] * r[3]) * id;
+    double A[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        A[i * 3 + j] = (double)Rs[i * 3 + 0] * inv[0 * 3 + j] + (double)Rs[i * 3 + 1] * inv[1 * 3 + j] +
+                       (double)Rs[i * 3 + 2] * inv[2 * 3 + j];
+    for (int i = 0; i < 9; ++i) s_A[threadIdx.x][i] = (float)A[i];
+    for (int i = 0; i < 3; ++i)
+      s_A[threadIdx.x][9 + i] =
+          (float)((double)ts[i] - (A[i * 3] * (double)tr[0] + A[i * 3 + 1] * (double)tr[1] + A[i * 3 + 2] * (double)tr[2]));
+  }
+  __syncthreads();
+
+  const int x = x_warp + lane;
+  float rx, ry, rz;
+  pixel_ray(p, min(x, p.W - 1), y, rx, ry, rz);
+
+  // phase-B coordinates of this lane
+  const int pp = lane / CG, cg = lane % CG;
+  const size_t view_f4 = (size_t)p.H * p.W * CG;  // float4 per (H,W,C) view
+  const float4* img4 = reinterpret_cast<const float4*>(p.images) + (size_t)b * p.S * view_f4;
+
+  // reference features of the warp's 32 pixels stay in registers for the whole depth chunk
+  float4 ref[NSUB];
+#pragma unroll
+  for (int j = 0; j < NSUB; ++j) {
+    const int px = x_warp + j * PPS + pp;
+    ref[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (px < p.W) ref[j] = ldg4(img4 + (size_t)p.ref_idx * view_f4 + ((size_t)y * p.W + px) * CG + cg);
+  }
+
+  const bool use_div = p.divisor != 0.f;
+  const size_t plane = (size_t)p.H * p.W;
+  bool bad = false;
+
+  for (int d = d_begin; d < d_end; ++d) {
+    // ---------------- phase A: one lane per pixel ----------------
+    float depth;
+    if (p.depth_volume) depth = (x < p.W) ? __ldg(p.depth_volume + ((size_t)b * p.D + d) * plane + (size_t)y * p.W + x) : 1.f;
+    else depth = __ldg(p.depths + d);
+    for (int s = 0; s < p.n_src; ++s) {
+      const float* A = s_A[s];
+      const float ax = A[0] * rx + A[1] * ry + A[2] * rz;
+      const float ay = A[3] * rx + A[4] * ry + A[5] * rz;
+      const float az = A[6] * rx + A[7] * ry + A[8] * rz;
+      const float cx = fmaf(depth, ax, A[9]), cy = fmaf(depth, ay, A[10]), cz = fmaf(depth, az, A[11]);
+      float u, v;
+      point_uv(p.dataset, cx, cy, cz, u, v);
+      if (!(u >= -1.f && u <= 1.f && v >= -1.f && v <= 1.f) && x < p.W) bad = true;
+      // grid_sample(align_corners=True) un-normalisation, ATen grid_sampler_unnormalize
+      const float ix = ((u + 1.f) / 2.f) * (float)(p.W - 1);
+      const float iy = ((v + 1.f) / 2.f) * (float)(p.H - 1);
+      const float x0f = floorf(ix), y0f = floorf(iy);
+      // clamp before the int conversion so a flagged (NaN / out-of-range) voxel cannot index wildly
+      const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)p.W);
+      const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)p.H);
+      TapRec r;
+      r.tx = ix - x0f;
+      r.ty = iy - y0f;
+      r.off4 = (y0 * p.W + x0) * CG;
+      const bool xl = x0 >= 0 && x0 < p.W, xr = x0 + 1 >= 0 && x0 + 1 < p.W;
+      const bool yt = y0 >= 0 && y0 < p.H, yb = y0 + 1 >= 0 && y0 + 1 < p.H;
+      const bool fin = (ix == ix) && (iy == iy);
+      r.mask = fin ? ((xl && yt) | ((xr && yt) << 1) | ((xl && yb) << 2) | ((xr && yb) << 3)) : 0u;
+      rec[s * 32 + lane] = r;
+    }
+    __syncwarp();
+
+    // ---------------- phase B: one lane per (pixel, float4 of channels) ----------------
+#pragma unroll
+    for (int j = 0; j < NSUB; ++j) {
+      const int pi = j * PPS + pp;
+      const int px = x_warp + pi;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < p.n_src; ++s) {
+        const TapRec r = rec[s * 32 + pi];
+        const float4* base = img4 + (size_t)p.src_views[s] * view_f4 + r.off4 + cg;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 nw = (r.mask & 1u) ? ldg4(base) : z4;
+        const float4 ne = (r.mask & 2u) ? ldg4(base + CG) : z4;
+        const float4 sw = (r.mask & 4u) ? ldg4(base + (size_t)p.W * CG) : z4;
+        const float4 se = (r.mask & 8u) ? ldg4(base + (size_t)p.W * CG + CG) : z4;
+        const float tx1 = 1.f - r.tx, ty1 = 1.f - r.ty;   // exact: == (x0+1)-ix, (y0+1)-iy
+        const float wnw = tx1 * ty1, wne = r.tx * ty1, wsw = tx1 * r.ty, wse = r.tx * r.ty;
+        float4 val;
+        val.x = nw.x * wnw; val.y = nw.y * wnw; val.z = nw.z * wnw; val.w = nw.w * wnw;
+        val.x = fmaf(ne.x, wne, val.x); val.y = fmaf(ne.y, wne, val.y); val.z = fmaf(ne.z, wne, val.z); val.w = fmaf(ne.w, wne, val.w);
+        val.x = fmaf(sw.x, wsw, val.x); val.y = fmaf(sw.y, wsw, val.y); val.z = fmaf(sw.z, wsw, val.z); val.w = fmaf(sw.w, wsw, val.w);
+        val.x = fmaf(se.x, wse, val.x); val.y = fmaf(se.y, wse, val.y); val.z = fmaf(se.z, wse, val.z); val.w = fmaf(se.w, wse, val.w);
+        if (p.cost_type == PGRF_COST_ABS_DIFF) {
+          val.x = fabsf(val.x - ref[j].x); val.y = fabsf(val.y - ref[j].y);
+          val.z = fabsf(val.z - ref[j].z); val.w = fabsf(val.w - ref[j].w);
+        } else if (p.cost_type == PGRF_COST_DOT) {
+          val.x *= ref[j].x; val.y *= ref[j].y; val.z *= ref[j].z; val.w *= ref[j].w;
+        }
+        if (use_div) { val.x = val.x / p.divisor; val.y = val.y / p.divisor; val.z = val.z / p.divisor; val.w = val.w / p.divisor; }
+        acc.x += val.x; acc.y += val.y; acc.z += val.z; acc.w += val.w;
+      }
+      if (!PLANAR) {
+        if (px < p.W) {
+          float4* dst = reinterpret_cast<float4*>(p.out) +
+                        ((((size_t)b * p.D + d) * p.H + y) * p.W + px) * CG + cg;
+          stcs4(dst, acc);
+        }
+      } else {
+        // tile[c][pixel] with row pitch 33: bank = (4cg + k + 4j + pp) mod 32 -> conflict-free
+        tile[(cg * 4 + 0) * 33 + pi] = acc.x;
+        tile[(cg * 4 + 1) * 33 + pi] = acc.y;
+        tile[(cg * 4 + 2) * 33 + pi] = acc.z;
+        tile[(cg * 4 + 3) * 33 + pi] = acc.w;
+      }
+    }
+    if (PLANAR) {
+      __syncwarp();
+      if (x < p.W) {
+        float* dst = p.out + (size_t)b * p.sB + (size_t)d * p.sD + (size_t)y * p.W + x;
+        if (p.groups > 0) {
+          const int cpg = C / p.groups;
+          const float inv_n = (float)cpg;
+          for (int g = 0; g < p.groups; ++g) {
+            float sum = 0.f;
+            for (int k = 0; k < cpg; ++k) sum += tile[(g * cpg + k) * 33 + lane];
+            __stcs(dst + (size_t)g * p.sC, sum / inv_n);
+          }
+        } else {
+#pragma unroll 8
+          for (int c = 0; c < C; ++c) __stcs(dst + (size_t)c * p.sC, tile[c * 33 + lane]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (bad) atomicOr(p.err, 1);
+}
+
+template <int C>
+static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
+  const int tiles_x = (p.W + kCvThreads - 1) / kCvThreads;
+  const int n_chunks = (p.D + p.d_chunk - 1) / p.d_chunk;
+  dim3 grid((unsigned)(tiles_x * p.H), (unsigned)n_chunks, (unsigned)p.B);
+  const bool planar = layout != PGRF_CV_BDHWC;
+  size_t smem = (size_t)kCvWarps * p.n_src * 32 * sizeof(TapRec);
+  if (planar) smem += (size_t)kCvWarps * C * 33 * sizeof(float);
+  if (planar) {
+    PGRF_CUDA(cudaFuncSetAttribute(cost_volume_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cost_volume_kernel<C, true><<<grid, kCvThreads, smem, st>>>(p);
+  } else {
+    PGRF_CUDA(cudaFuncSetAttribute(cost_volume_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cost_volume_kernel<C, false><<<grid, kCvThreads, smem, st>>>(p);
+  }
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+}  // namespace pgrf
+
+using namespace pgrf;
+
+extern "C" int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, int W, int C,
+                                    const float* depths, const float* depth_volume, int D,
+                                    const float* rots, const float* trans,
+                                    int ref_idx, const int* src_views, int n_src, float divisor,
+                                    int dataset, int cost_type, int layout, int groups,
+                                    float* out, int* err_flag, void* stream) {
+  PGRF_REQUIRE(images && rots && trans && out && err_flag, "cost_volume: null pointer argument");
+  PGRF_REQUIRE(depths || depth_volume, "cost_volume: need depths or depth_volume");
+  PGRF_REQUIRE(B > 0 && S > 0 && H > 1 && W > 1 && D > 0, "cost_volume: bad shape B=%d S=%d H=%d W=%d D=%d", B, S, H, W, D);
+  PGRF_REQUIRE(B <= 65535, "cost_volume: B=%d exceeds grid.z", B);
+  PGRF_REQUIRE(C == 4 || C == 8 || C == 16 || C == 32 || C == 64, "cost_volume: C=%d unsupported (need 4,8,16,32,64)", C);
+  PGRF_REQUIRE(n_src >= 1 && n_src <= kMaxSrc, "cost_volume: n_src=%d out of [1,%d]", n_src, kMaxSrc);
+  PGRF_REQUIRE(ref_idx >= 0 && ref_idx < S, "cost_volume: ref_idx=%d out of range", ref_idx);
+  PGRF_REQUIRE(dataset >= 0 && dataset <= 3, "cost_volume: unknown dataset id %d", dataset);
+  PGRF_REQUIRE(cost_type >= 0 && cost_type <= 2, "Unknown cost type");
+  PGRF_REQUIRE(layout >= 0 && layout <= 2, "cost_volume: unknown layout %d", layout);
+  PGRF_REQUIRE(groups == 0 || (layout == PGRF_CV_BCDHW && groups > 0 && C % groups == 0),
+               "cost_volume: groups=%d needs layout BCDHW and C %% groups == 0", groups);
+  PGRF_REQUIRE((size_t)H * W * C < (1ull << 31), "cost_volume: one view exceeds 2^31 elements");
+  PGRF_REQUIRE((((uintptr_t)images | (uintptr_t)out) & 15) == 0, "cost_volume: images/out must be 16-byte aligned");
+
+  CvParams p;
+  memset(&p, 0, sizeof(p));
+  p.images = images; p.depths = depths; p.depth_volume = depth_volume; p.rots = rots; p.trans = trans;
+  p.out = out; p.err = err_flag;
+  p.B = B; p.S = S; p.H = H; p.W = W; p.D = D;
+  p.ref_idx = ref_idx; p.n_src = n_src;
+  for (int i = 0; i < n_src; ++i) {
+    PGRF_REQUIRE(src_views[i] >= 0 && src_views[i] < S, "cost_volume: src view %d out of range", src_views[i]);
+    p.src_views[i] = src_views[i];
+  }
+  p.divisor = divisor; p.dataset = dataset; p.cost_type = cost_type; p.groups = groups;
+  p.OC = groups > 0 ? groups : C;
+  const long long HW = (long long)H * W;
+  if (layout == PGRF_CV_BDCHW) { p.sC = HW; p.sD = HW * p.OC; p.sB = p.sD * D; }
+  else { p.sD = HW; p.sC = HW * D; p.sB = p.sC * p.OC; }
+  switch (dataset) {
+    case PGRF_DS_M3D: p.ang0 = (float)(PGRF_PI_D / H); p.ang1 = (float)(2 * PGRF_PI_D / W); break;
+    case PGRF_DS_REPLICA_TEST: p.ang0 = (float)H; p.ang1 = (float)(2 * PGRF_PI_D / W); break;
+    case PGRF_DS_RESIDENTIAL: p.ang0 = (float)(H - 1); p.ang1 = (float)(W - 1); break;
+    default: p.ang0 = (float)(PGRF_PI_D / (H - 1)); p.ang1 = (float)(-2 * PGRF_PI_D / (W - 1)); break;
+  }
+  // depth chunking: enough CTAs for >= ~4 waves of 148 SMs x 8 resident CTAs, chunks of >= 4 depths
+  const long long ctas_per_chunk = (long long)((W + kCvThreads - 1) / kCvThreads) * H * B;
+  int n_chunks = (int)((148LL * 8 * 4 + ctas_per_chunk - 1) / ctas_per_chunk);
+  if (n_chunks < 1) n_chunks = 1;
+  int d_chunk = (D + n_chunks - 1) / n_chunks;
+  if (d_chunk < 4) d_chunk = D < 4 ? D : 4;
+  p.d_chunk = d_chunk;
+  PGRF_REQUIRE((D + d_chunk - 1) / d_chunk <= 65535, "cost_volume: too many depth chunks");
+
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 4: return launch_c<4>(p, layout, st);
+    case 8: return launch_c<8>(p, layout, st);
+    case 16: return launch_c<16>(p, layout, st);
+    case 32: return launch_c<32>(p, layout, st);
+    default: return launch_c<64>(p, layout, st);
+  }
+}
+
+extern "C" int pgrf_cost_volume_host(const float* images, int B, int S, int H, int W, int C,
+                                     const float* depths, const float* depth_volume, int D,
+                                     const float* rots, const float* trans,
+                                     int ref_idx, const int* src_views, int n_src, float divisor,
+                                     int dataset, int cost_type, int layout, int groups, float* out) {
+  PGRF_REQUIRE(images && rots && trans && out, "cost_volume_host: null pointer argument");
+  PGRF_REQUIRE(groups >= 0 && (groups == 0 || C % groups == 0), "cost_volume_host: bad groups");
+  const size_t n_img = (size_t)B * S * H * W * C, n_dv = (size_t)B * D * H * W;
+  const size_t n_out = (size_t)B * D * H * W * (groups > 0 ? groups : C);
+  float *d_img = nullptr, *d_depth = nullptr, *d_rots = nullptr, *d_trans = nullptr, *d_out = nullptr;
+  int* d_err = nullptr;
+  cudaStream_t st;
+  PGRF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = PGRF_OK;
+  int h_err = 0;
+  auto body = [&]() -> int {
+    PGRF_CUDA(cudaMallocAsync(&d_img, n_img * 4, st));
+    PGRF_CUDA(cudaMallocAsync(&d_depth, (depth_volume ? n_dv : (size_t)D) * 4, st));
+    PGRF_CUDA(cudaMallocAsync(&d_rots, (size_t)B * S * 9 * 4, st));
+    PGRF_CUDA(cudaMallocAsync(&d_trans, (size_t)B * S * 3 * 4, st));
+    PGRF_CUDA(cudaMallocAsync(&d_out, n_out * 4, st));
+    PGRF_CUDA(cudaMallocAsync(&d_err, 4, st));
+    PGRF_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
+    PGRF_CUDA(cudaMemcpyAsync(d_img, images, n_img * 4, cudaMemcpyHostToDevice, st));
+    PGRF_CUDA(cudaMemcpyAsync(d_depth, depth_volume ? depth_volume : depths, (depth_volume ? n_dv : (size_t)D) * 4,
+                              cudaMemcpyHostToDevice, st));
+    PGRF_CUDA(cudaMemcpyAsync(d_rots, rots, (size_t)B * S * 9 * 4, cudaMemcpyHostToDevice, st));
+    PGRF_CUDA(cudaMemcpyAsync(d_trans, trans, (size_t)B * S * 3 * 4, cudaMemcpyHostToDevice, st));
+    int r = pgrf_cost_volume_fwd(d_img, B, S, H, W, C, depth_volume ? nullptr : d_depth, depth_volume ? d_depth : nullptr, D,
+                                 d_rots, d_trans, ref_idx, src_views, n_src, divisor, dataset, cost_type, layout, groups,
+                                 d_out, d_err, st);
+    if (r != PGRF_OK) return r;
+    PGRF_CUDA(cudaMemcpyAsync(out, d_out, n_out * 4, cudaMemcpyDeviceToHost, st));
+    PGRF_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+    PGRF_CUDA(cudaStreamSynchronize(st));
+    return PGRF_OK;
+  };
+  rc = body();
+  cudaFreeAsync(d_img, st); cudaFreeAsync(d_depth, st); cudaFreeAsync(d_rots, st);
+  cudaFreeAsync(d_trans, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_err, st);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == PGRF_OK && h_err) {
+    set_error("Wrong UV mapping, UV must be in [-1, 1]!");
+    return PGRF_ERANGE;
+  }
+  return rc;
+}

@@ -1,0 +1,105 @@
+"""Drop-in for the reference's `models/spherical_cost_volume.py` / `models/spherical_cost_volume_mv.py`.
+
+Same function names, argument meaning and error behaviour
+(`calculate_cost_volume_erp` models/spherical_cost_volume.py:231-341,
+ `calculate_cost_volume_erp_multiview` models/spherical_cost_volume_mv.py:219-347), but the D
+(x views) python iterations, each a chain of ~25 elementwise launches + grid_sample + a host sync,
+run as ONE fused sm_100a kernel (csrc/cost_volume.cu) through the C ABI.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_CHECK_UV = True   # the reference asserts uv in [-1,1] after every depth (:191); we check one flag per call
+
+
+def _sweep(args, images, depths, trans, rots, depth_volume, cost_type, ref_idx, src_views, divisor,
+           out_layout="bdchw", groups=0):
+    name = args["dataset_name"]
+    if name not in _lib.DATASET_IDS:
+        raise Exception(f"unknown dataset_name {name!r}")          # reference: bare `raise Exception` (:189,:294)
+    if cost_type not in _lib.COST_IDS:
+        raise ValueError("Unknown cost type")                      # reference :217
+    if out_layout not in _lib.CV_LAYOUT_IDS:
+        raise ValueError(f"unknown out_layout {out_layout!r}")
+    _lib.require_cuda(images, trans, rots)
+    if images.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("panogrf_b200 cost volume: backward is not implemented yet "
+                                  "(the render path runs the MVS net under no_grad, init_net.py:255)")
+    lib = _lib.load()
+    B, S, H, W, C = images.shape
+    images = images.contiguous().float()
+    rots = rots.reshape(B, S, 3, 3).contiguous().float()
+    trans = trans.reshape(B, S, 3).contiguous().float()
+    dev = images.device
+    use_volume = bool(args["contain_dnet"])
+    d_ptr = v_ptr = None
+    if use_volume:
+        depth_volume = depth_volume.to(device=dev, dtype=torch.float32).contiguous()
+        D = depth_volume.shape[1]
+        assert depth_volume.shape == (B, D, H, W), "depth_volume must be (B,D,H,W)"
+        v_ptr = _lib.ptr(depth_volume)
+    else:
+        depths = torch.as_tensor(depths, dtype=torch.float32, device=dev).reshape(-1).contiguous()
+        D = depths.numel()
+        d_ptr = _lib.ptr(depths)
+    OC = groups if groups > 0 else C
+    if out_layout == "bdchw":
+        store = torch.empty((B, D, OC, H, W), device=dev, dtype=torch.float32)
+    elif out_layout == "bdhwc":
+        store = torch.empty((B, D, H, W, OC), device=dev, dtype=torch.float32)
+    else:
+        store = torch.empty((B, OC, D, H, W), device=dev, dtype=torch.float32)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    views = (ctypes.c_int * len(src_views))(*src_views)
+    with torch.cuda.device(dev):
+        rc = lib.pgrf_cost_volume_fwd(
+            _lib.ptr(images), B, S, H, W, C, d_ptr, v_ptr, D, _lib.ptr(rots), _lib.ptr(trans),
+            ref_idx, views, len(src_views), float(divisor),
+            _lib.DATASET_IDS[name], _lib.COST_IDS[cost_type], _lib.CV_LAYOUT_IDS[out_layout], groups,
+            _lib.ptr(store), _lib.ptr(err), _lib.stream_ptr())
+    _lib.check(rc, "pgrf_cost_volume_fwd")
+    if _CHECK_UV and int(err.item()) != 0:
+        raise AssertionError("Wrong UV mapping, UV must be in [-1, 1]!")
+    if groups > 0:
+        return store                                               # (B,G,D,H,W)
+    if out_layout == "bdchw":
+        return store.permute(0, 1, 3, 4, 2)                        # same strides as the reference's :340
+    if out_layout == "bcdhw":
+        return store.permute(0, 2, 3, 4, 1)
+    return store
+
+
+def calculate_cost_volume_erp(args, images, depths, trans, rots, depth_volume=None, cost_type="abs_diff",
+                              ref_gmms=None, nghbr_gmms=None, thres=None, direction="up",
+                              out_layout="bdchw", groups=0):
+    """(B,2,H,W,C) channels-last features [0]=source,[1]=reference -> (B,D,H,W,C) cost volume.
+
+    `ref_gmms`, `nghbr_gmms`, `thres`, `direction` are accepted and ignored exactly like the
+    reference.  Extensions (keyword-only in spirit): `out_layout` picks the physical layout
+    ("bdchw" = the reference's strides, "bdhwc" channels-last, "bcdhw" the regulariser's), and
+    `groups>0` fuses the group-wise mean of pipeline3_model.py:849-853, returning (B,G,D,H,W).
+    """
+    if groups > 0:
+        out_layout = "bcdhw"
+    return _sweep(args, images, depths, trans, rots, depth_volume, cost_type, 1, [0], 0.0, out_layout, groups)
+
+
+def calculate_cost_volume_erp_multiview(args, images, depths, trans, rots, depth_volume=None,
+                                        cost_type="abs_diff", ref_gmms=None, nghbr_gmms=None, thres=None,
+                                        direction="up", curr_idx=0, out_layout="bdhwc", groups=0):
+    """(B,S,H,W,C) -> mean over views {0..S-2}\\{curr_idx} of the 2-view volume, each /(S-2).
+
+    The LAST view is skipped on purpose, like the reference (:312 "exclude the last").  The
+    reference returns a contiguous (B,D,H,W,C) tensor here (sum of permuted views), hence the
+    channels-last default.
+    """
+    S = images.shape[1]
+    assert S > 2
+    views = [v for v in range(S - 1) if v != curr_idx]
+    if groups > 0:
+        out_layout = "bcdhw"
+    return _sweep(args, images, depths, trans, rots, depth_volume, cost_type, curr_idx, views, float(S - 2),
+                  out_layout, groups)

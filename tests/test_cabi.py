@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/panogrf_b200.h declares."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from panogrf_b200 import build as b
+    b.build()
+    from panogrf_b200 import _lib
+    return _lib.load()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "panogrf_b200.h")).read()
+    return sorted(set(re.findall(r"PGRF_API[^;(]*?\b(pgrf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    from panogrf_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 5
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.SIGNATURES"
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_version_and_error_string(lib):
+    assert lib.pgrf_version() >= 100
+    assert isinstance(lib.pgrf_last_error(), bytes)
+
+
+def test_argument_validation_without_gpu(lib):
+    """Shape validation happens before any CUDA call, so it is checkable on a CPU-only box."""
+    import ctypes
+    from panogrf_b200 import _lib
+    views = (ctypes.c_int * 1)(0)
+    dummy = ctypes.c_void_p(256)
+    rc = lib.pgrf_cost_volume_fwd(dummy, 1, 2, 8, 16, 5, dummy, None, 4, dummy, dummy, 1, views, 1, 0.0,
+                                  0, 0, 0, 0, dummy, dummy, None)
+    assert rc == _lib.PGRF_EINVAL and b"C=5" in lib.pgrf_last_error()
+    rc = lib.pgrf_cost_volume_fwd(dummy, 1, 2, 8, 16, 8, dummy, None, 4, dummy, dummy, 1, views, 1, 0.0,
+                                  0, 7, 0, 0, dummy, dummy, None)
+    assert rc == _lib.PGRF_EINVAL and lib.pgrf_last_error() == b"Unknown cost type"
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from panogrf_b200 import calculate_cost_volume_erp
+    from panogrf_b200._lib import PanoGRFError
+    with pytest.raises(PanoGRFError):
+        calculate_cost_volume_erp({"dataset_name": "m3d", "contain_dnet": False}, torch.zeros(1, 2, 8, 16, 8),
+                                  torch.ones(3), torch.zeros(1, 2, 3), torch.eye(3).expand(1, 2, 3, 3))

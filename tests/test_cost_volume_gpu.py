@@ -1,0 +1,155 @@
+"""GPU parity: fused sm_100a cost-volume kernel (through the C ABI) vs the CPU oracle and the
+reference's golden outputs (HOT 1)."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import cases  # noqa: E402
+from util import assert_close, load_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cost_volume as ocv  # noqa: E402
+
+
+def _dev(x):
+    return None if x is None else x.cuda()
+
+
+def _run_kernel(c, g, **kw):
+    import panogrf_b200 as pg
+    args = {"dataset_name": c["dataset"], "contain_dnet": c["per_pixel"], "mono_uncertainty": False}
+    dv = _dev(g["depth_volume"]) if c["per_pixel"] else None
+    if c.get("mv"):
+        return pg.calculate_cost_volume_erp_multiview(args, _dev(g["images"]), _dev(g["depths"]), _dev(g["trans"]),
+                                                      _dev(g["rots"]), depth_volume=dv, cost_type=c["cost_type"],
+                                                      curr_idx=c["curr_idx"], **kw)
+    return pg.calculate_cost_volume_erp(args, _dev(g["images"]), _dev(g["depths"]), _dev(g["trans"]),
+                                        _dev(g["rots"]), depth_volume=dv, cost_type=c["cost_type"], **kw)
+
+
+@pytest.mark.parametrize("name", list(cases.CV_CASES))
+@pytest.mark.parametrize("layout", ["bdchw", "bdhwc", "bcdhw"])
+def test_kernel_matches_reference_golden(name, layout):
+    c = cases.CV_CASES[name]
+    g = load_golden(name)
+    out = _run_kernel(c, g, out_layout=layout)
+    assert tuple(out.shape) == tuple(g["out"].shape)
+    if layout == "bdchw" and not c.get("mv"):
+        B, D, H, W, C = out.shape
+        assert out.stride() == (D * C * H * W, C * H * W, W, 1, H * W)   # reference's permuted view (:340)
+    assert_close(out, g["out"], atol=2e-4, max_bad_frac=2e-4, what=f"{name}/{layout}")
+
+
+@pytest.mark.parametrize("name", ["cv_m3d_volume", "cv_mv5_volume"])
+def test_group_wise_epilogue(name):
+    c = cases.CV_CASES[name]
+    g = load_golden(name)
+    out = _run_kernel(c, g, groups=8)
+    expect = ocv.group_mean(g["out"], 8)
+    assert_close(out, expect, atol=1e-4, max_bad_frac=2e-4, what=name + "/groups")
+
+
+def test_smooth_features_tight_tolerance():
+    """Low-pass features: bilinear error no longer dominated by white noise -> pure rtol 1e-4 (+1e-5)."""
+    name = "cv_m3d_volume"
+    c = cases.CV_CASES[name]
+    inp = cases.make_cv_inputs(name, seed=3, smooth_feats=True)
+    expect = ocv.calculate_cost_volume_erp(inp["args"], inp["images"], inp["depths"], inp["trans"], inp["rots"],
+                                           depth_volume=inp["depth_volume"])
+    g = dict(images=inp["images"], depths=inp["depths"], trans=inp["trans"], rots=inp["rots"],
+             depth_volume=inp["depth_volume"])
+    out = _run_kernel(c, g)
+    assert_close(out, expect, atol=1e-5, max_bad_frac=2e-4, what="smooth")
+
+
+def test_config1_size_vs_oracle():
+    """BASELINE config 1 shape (256x512, C32, D64, 2 views): full comparison against the CPU oracle."""
+    import panogrf_b200 as pg
+    gen = torch.Generator().manual_seed(0)
+    B, H, W, C, D = 1, 256, 512, 32, 64
+    images = cases.smooth(torch.randn(B, 2, H, W, C, generator=gen), passes=1)
+    rots = torch.eye(3).expand(B, 2, 3, 3).contiguous()
+    trans = torch.tensor([[[0., 0., 0.5], [0., 0., -0.5]]])
+    depths = torch.linspace(0.1, 10.0, D)
+    args = {"dataset_name": "m3d", "contain_dnet": False, "mono_uncertainty": False}
+    expect = ocv.calculate_cost_volume_erp(args, images, depths, trans, rots)
+    out = pg.calculate_cost_volume_erp(args, images.cuda(), depths.cuda(), trans.cuda(), rots.cuda())
+    assert_close(out, expect, atol=1e-4, max_bad_frac=1e-5, what="config1")
+    out_cl = pg.calculate_cost_volume_erp(args, images.cuda(), depths.cuda(), trans.cuda(), rots.cuda(),
+                                          out_layout="bdhwc")
+    assert torch.equal(out_cl, out.contiguous())          # layouts are bit-identical
+
+
+def test_full_size_properties():
+    """512x1024, D128 (config 3 per-GPU shape): size-independent properties instead of an oracle run."""
+    import panogrf_b200 as pg
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    B, H, W, C, D = 1, 512, 1024, 32, 128
+    args = {"dataset_name": "m3d", "contain_dnet": False, "mono_uncertainty": False}
+    rots = torch.eye(3, device="cuda").expand(B, 2, 3, 3).contiguous()
+    depths = torch.linspace(0.1, 10.0, D, device="cuda")
+    # (1) constant image, any pose -> abs_diff cost is exactly zero, 'none' returns the constant
+    const = torch.full((B, 2, H, W, C), 0.625, device="cuda")
+    trans = torch.tensor([[[0., 0., 0.5], [0., 0., -0.5]]], device="cuda")
+    out = pg.calculate_cost_volume_erp(args, const, depths, trans, rots, out_layout="bdhwc")
+    assert float(out.abs().max()) <= 1e-6
+    del out
+    # (2) linearity of the warp in the source features: cv_none(a*x + y) == a*cv_none(x) + cv_none(y)
+    D2 = 16
+    x = torch.randn(B, 2, H, W, C, device="cuda", generator=gen)
+    y = torch.randn(B, 2, H, W, C, device="cuda", generator=gen)
+    f = lambda im: pg.calculate_cost_volume_erp(args, im, depths[:D2], trans, rots, cost_type="none",
+                                                out_layout="bdhwc")
+    lhs = f(2.0 * x + y)
+    rhs = 2.0 * f(x) + f(y)
+    assert float((lhs - rhs).abs().max()) < 1e-4
+    # (3) multi-view with identical source views equals the 2-view volume
+    img3 = torch.stack([x[:, 0], x[:, 1], x[:, 0], x[:, 0]], 1).contiguous()
+    rots4 = torch.eye(3, device="cuda").expand(B, 4, 3, 3).contiguous()
+    trans4 = torch.stack([trans[:, 0], trans[:, 1], trans[:, 0], trans[:, 0]], 1).contiguous()
+    mv = pg.calculate_cost_volume_erp_multiview(args, img3, depths[:D2], trans4, rots4, curr_idx=1)
+    two = pg.calculate_cost_volume_erp(args, x, depths[:D2], trans, rots, out_layout="bdhwc")
+    assert float((mv - two).abs().max()) < 1e-5
+
+
+def test_uv_range_assert_and_errors():
+    import panogrf_b200 as pg
+    args = {"dataset_name": "m3d", "contain_dnet": False, "mono_uncertainty": False}
+    images = torch.randn(1, 2, 8, 32, 8, device="cuda")
+    rots = torch.eye(3, device="cuda").expand(1, 2, 3, 3).contiguous()
+    trans = torch.zeros(1, 2, 3, device="cuda")
+    # depth 0 with identical poses -> radius 0 -> NaN uv -> the reference's assert (:191) fires
+    with pytest.raises(AssertionError, match="Wrong UV mapping"):
+        pg.calculate_cost_volume_erp(args, images, torch.zeros(2, device="cuda"), trans, rots)
+    with pytest.raises(ValueError):
+        pg.calculate_cost_volume_erp(args, images, torch.ones(2, device="cuda"), trans, rots, cost_type="ssd")
+    with pytest.raises(Exception):
+        pg.calculate_cost_volume_erp({"dataset_name": "nope", "contain_dnet": False}, images,
+                                     torch.ones(2, device="cuda"), trans, rots)
+
+
+def test_host_entry_point_matches_device_path():
+    """The *_host C-ABI call (H2D + kernel + D2H) returns the same bits as the device-pointer call."""
+    import ctypes
+    import numpy as np
+    import panogrf_b200 as pg
+    from panogrf_b200 import _lib
+    name = "cv_m3d_scalar"
+    c = cases.CV_CASES[name]
+    g = load_golden(name)
+    dev_out = _run_kernel(c, g, out_layout="bdhwc").cpu().numpy()
+    lib = _lib.load()
+    B, S, H, W, C = g["images"].shape
+    D = g["depths"].numel()
+    out = np.empty((B, D, H, W, C), np.float32)
+    arr = lambda t: np.ascontiguousarray(t.numpy(), np.float32)
+    im, dp, ro, tr = arr(g["images"]), arr(g["depths"]), arr(g["rots"]), arr(g["trans"])
+    views = (ctypes.c_int * 1)(0)
+    rc = lib.pgrf_cost_volume_host(im.ctypes.data, B, S, H, W, C, dp.ctypes.data, None, D, ro.ctypes.data,
+                                   tr.ctypes.data, 1, views, 1, 0.0, 0, 0, 1, 0, out.ctypes.data)
+    assert rc == 0, _lib.last_error()
+    assert np.array_equal(out, dev_out)
