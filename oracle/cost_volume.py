@@ -147,7 +147,7 @@ def _depth_tensor(depths, depth_volume, B, H, W):
     return d.expand(B, d.shape[1], H, W)
 
 
-def sweep_uv(dataset_name, depth, rot_ref, tran_ref, rot_src, tran_src):
+def sweep_uv(dataset_name, depth, rot_ref, tran_ref, rot_src, tran_src, return_radius=False):
     """(u,v) of every (b,d,y,x) voxel in the source panorama; get_cv_per_depth :137-159."""
     B, D, H, W = depth.shape
     xyz = unit_rays(dataset_name, H, W)                             # (H,W,3)
@@ -155,6 +155,8 @@ def sweep_uv(dataset_name, depth, rot_ref, tran_ref, rot_src, tran_src):
     inv_ref = torch.inverse(rot_ref)                                # (B,3,3)
     w = torch.einsum("bij,bdhwj->bdhwi", inv_ref, m - tran_ref[:, None, None, None, :])
     c = torch.einsum("bij,bdhwj->bdhwi", rot_src, w) + tran_src[:, None, None, None, :]
+    if return_radius:
+        return cartesian_to_uv(dataset_name, c) + (torch.linalg.norm(c, dim=-1),)
     return cartesian_to_uv(dataset_name, c)
 
 

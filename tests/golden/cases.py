@@ -56,3 +56,80 @@ def make_cv_inputs(name, seed=0, smooth_feats=False):
     args = {"dataset_name": c["dataset"], "contain_dnet": c["per_pixel"], "mono_uncertainty": False}
     return dict(args=args, images=images, depths=depths, trans=trans, rots=rots, depth_volume=depth_volume,
                 cost_type=c["cost_type"], mv=c.get("mv", False), curr_idx=c.get("curr_idx", 0))
+
+
+# ------------------------------------------------------------------------------------------------
+# render path
+# ------------------------------------------------------------------------------------------------
+
+def render_cfg(height=32, width=64, dataset="m3d", sample_num=16, use_vis=False, use_disp=True,
+               hierarchical=True, fine_use_all=False, ray_batch_num=128, **extra):
+    """Config dict with every key the reference renderer reads (render.py:102-124 defaults + yaml)."""
+    cfg = {
+        "dataset_name": dataset, "batch_size": 1, "height": height, "width": width,
+        "min_depth": 0.5, "max_depth": 15.0, "use_disp": use_disp,
+        "use_wrap_padding": True, "autoencoder": False, "debug": False,
+        "use_hierarchical_sampling": hierarchical, "fine_depth_use_all": fine_use_all,
+        "depth_sample_num": sample_num, "fine_depth_sample_num": sample_num, "sample_num": sample_num,
+        "ray_batch_num": ray_batch_num, "render_depth": True, "render_uncert": False,
+        "use_polar_weighted_loss": False, "use_ray_mask": True,
+        "dist_decoder_cfg": {"use_vis": use_vis}, "fine_dist_decoder_cfg": {"use_vis": use_vis},
+        "agg_net_cfg": {}, "fine_agg_net_cfg": {},
+        "local_feature_type": "ERP",
+        # render.py:102-124 defaults read by the (out-of-scope) encoders' constructors
+        "handle_distort": False, "handle_distort_all": False, "handle_distort_input_all": False,
+        "with_sin": False, "wo_mono_feat": False, "uncert_tune": False, "use_depth": False,
+    }
+    cfg.update(extra)
+    return cfg
+
+
+RENDER_CASES = {
+    # name: (cfg kwargs, rfn, n_rays, feature-map scales)
+    "render_m3d_2src": dict(cfg=dict(), rfn=2, n_rays=96),
+    "render_m3d_vis_nodisp": dict(cfg=dict(use_vis=True, use_disp=False), rfn=2, n_rays=64),
+    "render_m3d_4src_all": dict(cfg=dict(fine_use_all=True, sample_num=32, hierarchical=True), rfn=4, n_rays=48,
+                                fine_sample_num=16),
+    "render_residential": dict(cfg=dict(dataset="residential"), rfn=2, n_rays=64),
+    "render_replica": dict(cfg=dict(dataset="replica_test"), rfn=3, n_rays=64),
+    "render_coffee": dict(cfg=dict(dataset="CoffeeArea", hierarchical=False), rfn=2, n_rays=64),
+}
+
+
+def make_render_inputs(name, seed=0):
+    c = RENDER_CASES[name]
+    kw = dict(c["cfg"])
+    if "fine_sample_num" in c:
+        # fine_depth_use_all: coarse dn + fine fdn must equal the fine agg net's sample_num
+        kw["depth_sample_num"] = kw["sample_num"] - c["fine_sample_num"]
+        kw["fine_depth_sample_num"] = c["fine_sample_num"]
+    cfg = render_cfg(**{k: v for k, v in kw.items() if k not in ("depth_sample_num", "fine_depth_sample_num")})
+    for k in ("depth_sample_num", "fine_depth_sample_num"):
+        if k in kw:
+            cfg[k] = kw[k]
+    if "fine_sample_num" in c:
+        # coarse net sees depth_sample_num samples, the fine net depth_sample_num + fine_depth_sample_num.
+        # A top-level "sample_num" would override both (renderer.py:67-69), so it is dropped here.
+        total = cfg.pop("sample_num")
+        cfg["agg_net_cfg"] = {"sample_num": cfg["depth_sample_num"]}
+        cfg["fine_agg_net_cfg"] = {"sample_num": total}
+    gen = torch.Generator().manual_seed(seed + sum(map(ord, name)))
+    h, w, rfn = cfg["height"], cfg["width"], c["rfn"]
+    imgs = smooth(torch.rand(rfn, h, w, 3, generator=gen), 1).permute(0, 3, 1, 2).contiguous()
+    img_feats = torch.randn(rfn, 32, h // 2, w // 2, generator=gen)
+    ray_feats = torch.randn(rfn, 32, h // 4, w // 4, generator=gen)
+    rots = small_rotations(gen, 1, rfn + 1, 8.0)[0]
+    trans = torch.randn(rfn + 1, 3, generator=gen) * 0.4
+    w2c = torch.cat([rots, trans[:, :, None]], -1)                       # (rfn+1,3,4)
+    que_w2c = w2c[-1]
+    R, t = que_w2c[:, :3], que_w2c[:, 3]
+    c2w = torch.cat([R.t(), (-R.t() @ t)[:, None]], -1)[None]
+    perm = torch.randperm(h * w, generator=gen)[:c["n_rays"]]
+    coords = torch.stack([(perm % w).float(), (perm // w).float()], -1)[None]
+    que = {"coords": coords, "c2w": c2w, "w2c": que_w2c[None], "depth_range": torch.tensor([[0.5, 15.0]])}
+    ref = {"imgs": imgs, "w2c": w2c[:rfn].contiguous(), "depth_range": torch.tensor([[0.5, 15.0]]).repeat(rfn, 1),
+           "ray_feats": ray_feats, "img_feats": img_feats}
+    return cfg, que, ref
+
+
+RENDER_WEIGHT_PREFIXES = ("dist_decoder.", "fine_dist_decoder.", "agg_net.", "fine_agg_net.")
