@@ -88,6 +88,98 @@ PGRF_API int pgrf_cost_volume_host(const float* images, int B, int S, int H, int
                           int dataset, int cost_type, int layout, int groups,
                           float* out);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 + K3 + K4 — one render pass (coarse or fine) over a batch of rays.
+ * Replaces, per ray batch, network/renderer.py:223-317 (render_by_depth) and everything it calls:
+ *   render_ops.py:76-106 (depth2points_spherical), :110-122 (depth2inv_dists), :158-257
+ *   (project_points_dict), ops.py:32-52 (interpolate_feats), renderer.py:120-136
+ *   (predict_proj_ray_prob) + dist_decoder.py:99-140, renderer.py:180-188 (get_img_feats),
+ *   aggregate_net.py:41-89 + ibrnet.py:315-373, renderer.py:210-219 (network_rendering),
+ *   render_ops.py:145-153 (alpha_values2hit_prob), renderer.py:302-304 (render_depth) and, when
+ *   `fine_depth` is set, render_ops.py:413-473 (sample_fine_depth) + the sort of renderer.py:470-472.
+ * All pointers are DEVICE pointers to contiguous fp32 unless stated.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pgrf_render_args {
+  int dataset;                 /* PGRF_DS_* (cfg["dataset_name"]) */
+  int H, W;                    /* ERP size of the spherical convention (cfg["height"], cfg["width"]) */
+  int rfn;                     /* source views, 1..4 */
+  int rn;                      /* rays in this batch */
+  int dn;                      /* samples per ray, 3..128 */
+  int use_vis;                 /* dist_decoder_cfg.use_vis of the COARSE decoder (renderer.py:129) */
+  float bias_val;              /* dist_decoder_cfg.bias_val (0.05) */
+  const float* coords;         /* (rn,2) query pixel (x,y); truncated like .long() */
+  const float* depth;          /* (rn,dn) sample depths, or (dn) shared by all rays when depth_ray_stride==0 */
+  int depth_ray_stride;        /* dn or 0 */
+  const float* que_c2w;        /* (3,4) query camera-to-world */
+  float que_near, que_far;     /* que_imgs_info["depth_range"] */
+  const float* ref_w2c;        /* (rfn,3,4) */
+  const float* ref_depth_range;/* (rfn,2) */
+  const float* imgs_cl;        /* (rfn,img_h,img_w,4) channels-last rgb, 4th channel padding */
+  int img_h, img_w;
+  const float* img_feats_cl;   /* (rfn,if_h,if_w,32) channels-last */
+  int if_h, if_w;
+  const float* ray_feats_cl;   /* (rfn,rf_h,rf_w,32) channels-last */
+  int rf_h, rf_w;
+  const float* weights;        /* packed blob, pgrf_weight_blob_floats() floats, see pgrf_weight_layer_info */
+  float* f1;                   /* workspace, sizes from pgrf_render_workspace */
+  float* f2;
+  float* pixel_colors;         /* (rn,3)  out */
+  float* render_depth;         /* (rn)    out, optional */
+  float* hit_prob;             /* (rn,dn) out, optional */
+  float* density;              /* (rn,dn) out, optional */
+  float* colors;               /* (rn,dn,3) out, optional */
+  float* fine_depth;           /* (rn, fine_dn [+ dn]) out, optional: sorted fine samples */
+  int fine_dn;
+  const float* fine_u;         /* (fine_dn) the deterministic u table of render_ops.py:442-445 */
+  int fine_use_all;            /* cfg["fine_depth_use_all"] */
+  int use_disp;                /* cfg["use_disp"] (inv_mode of sample_fine_depth) */
+  int* fine_inds;              /* (rn,fine_dn) searchsorted bin indices, optional (parity tests) */
+  float* prob_dbg;             /* (rfn,rn*dn,3) alpha, vis, hit_prob of prj_dict, optional */
+  float* prj_dbg;              /* (rfn,rn*dn,6) pts(2), depth, dir(3) of prj_dict, optional */
+  float* feat_dbg;             /* (rfn,rn*dn,67) ray_feats(32), rgb(3), img_feats(32) of prj_dict, optional */
+} pgrf_render_args;
+
+PGRF_API int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream);
+/* workspace sizes (floats) for `n_samples` = rn*dn samples and rfn views */
+PGRF_API int pgrf_render_workspace(int rfn, long long n_samples, long long* f1_floats, long long* f2_floats);
+
+/* Whole view = the reference's ray-batch loop (network/renderer.py:647-683) + coarse->fine hand-off
+ * (renderer.py:600-631, 435-524).  `pass` describes the COARSE pass over ALL rays of the view
+ * (depth = the shared (dn) table, depth_ray_stride = 0, outputs sized for pass.rn rays, f1/f2 sized
+ * for rays_per_launch rays of max(dn, fine_total) samples); rays are processed rays_per_launch at a time. */
+typedef struct pgrf_render_view_args {
+  pgrf_render_args pass;
+  int hierarchical;            /* cfg["use_hierarchical_sampling"] */
+  const float* weights_fine;   /* blob of fine_dist_decoder + fine_agg_net (== pass.weights for cfg["one_mlp"]) */
+  float bias_val_fine;
+  int rays_per_launch;
+  float* fine_depth_ws;        /* (rays_per_launch, fine_total) workspace, used when que_depth_fine == NULL */
+  float* pixel_colors_fine;    /* (rn,3) */
+  float* render_depth_fine;    /* (rn) optional */
+  float* hit_prob_fine;        /* (rn,fine_total) optional */
+  float* density_fine;         /* (rn,fine_total) optional */
+  float* colors_fine;          /* (rn,fine_total,3) optional */
+  float* que_depth_fine;       /* (rn,fine_total) optional: the sorted fine sample depths */
+} pgrf_render_view_args;
+
+PGRF_API int pgrf_render_view_fwd(const pgrf_render_view_args* args, void* stream);
+/* HOST-pointer variant: all pointers are host memory, the three maps are NCHW like the reference's
+ * ref_imgs_info (imgs: 3 channels); does H2D, layout conversion, all passes, D2H and synchronises. */
+PGRF_API int pgrf_render_view_host(const pgrf_render_view_args* args);
+/* (N,C,H,W) -> channels-last (N,H,W,Cpad), zero padded */
+PGRF_API int pgrf_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int Cpad, void* stream);
+
+/* Weight blob layout: one entry per (slice of a) Linear layer of [fine_]dist_decoder / [fine_]agg_net.
+ * name uses "{dd}" / "{agg}" placeholders; the weight slice [N, k_begin:k_begin+K] is stored
+ * transposed (k-major) with rows padded to Npad at w_offset, the bias (Npad) at b_offset. */
+PGRF_API int pgrf_weight_blob_floats(void);
+PGRF_API int pgrf_weight_num_layers(void);
+PGRF_API int pgrf_weight_layer_info(int i, char* name, int name_cap, int* K, int* N, int* Npad, int* has_bias,
+                                    int* k_begin, int* w_offset, int* b_offset);
+/* layer-norm (weight 16, bias 16) offset, positional table offset ([max_samples][16]) */
+PGRF_API int pgrf_weight_aux_offsets(int* layer_norm_offset, int* posenc_offset, int* max_samples);
+
 #ifdef __cplusplus
 }
 #endif

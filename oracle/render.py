@@ -132,6 +132,28 @@ def depth2inv_dists(depth, depth_range):
     return torch.cat([dists, torch.full([*depth.shape[:-1], 1], 1e6, dtype=torch.float32)], -1)
 
 
+def seq_cumsum(x):
+    """Sequential left-to-right fp32 cumulative sum over the last dim — the STATED accumulation order
+    of this build.  torch.cumsum accumulates in fp64 on the CPU and with a parallel scan
+    on CUDA, so neither is a fixed fp32 order; the CUDA kernels reproduce exactly this loop."""
+    out = torch.empty_like(x)
+    acc = torch.zeros_like(x[..., 0])
+    for i in range(x.shape[-1]):
+        acc = acc + x[..., i]
+        out[..., i] = acc
+    return out
+
+
+def seq_cumprod(x):
+    """Sequential left-to-right fp32 cumulative product over the last dim (see seq_cumsum)."""
+    out = torch.empty_like(x)
+    acc = torch.ones_like(x[..., 0])
+    for i in range(x.shape[-1]):
+        acc = acc * x[..., i]
+        out[..., i] = acc
+    return out
+
+
 def fine_sample_u(fdn):
     """The deterministic u-table of sample_fine_depth (render_ops.py:442-445)."""
     interval = 1 / fdn
@@ -148,8 +170,9 @@ def sample_fine_depth(depth, hit_prob, depth_range, sample_num, use_disp=True, r
     center = (depth[..., 1:] + depth[..., :-1]) / 2
     center = torch.cat([depth[..., 0:1], center, depth[..., -1:]], -1)
     hp = hit_prob + 1e-5
-    pdf = hp / torch.sum(hp, -1, keepdim=True)
-    cdf = torch.cumsum(pdf, -1)
+    # stated accumulation order: sequential left-to-right fp32 for the normaliser as well as the cdf
+    pdf = hp / seq_cumsum(hp)[..., -1:]
+    cdf = seq_cumsum(pdf)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
     u = fine_sample_u(sample_num).expand(list(cdf.shape[:-1]) + [sample_num]).contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
@@ -371,7 +394,7 @@ def agg_net_forward(W, p, prj, que_dir, n_samples):
 def alpha_values2hit_prob(alpha):
     """render_ops.py:145-153."""
     no_hit = torch.cat([torch.ones((*alpha.shape[:-1], 1)), 1. - alpha + 1e-10], -1)
-    return alpha * torch.cumprod(no_hit, -1)[..., :-1]
+    return alpha * seq_cumprod(no_hit)[..., :-1]
 
 
 def composite(density, colors, depth):

@@ -88,3 +88,52 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise PanoGRFError("panogrf_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+class RenderArgs(ctypes.Structure):
+    """Mirror of `pgrf_render_args` (include/panogrf_b200.h) — field order and types must match."""
+    _fields_ = [
+        ("dataset", _I), ("H", _I), ("W", _I), ("rfn", _I), ("rn", _I), ("dn", _I), ("use_vis", _I),
+        ("bias_val", _F),
+        ("coords", _P), ("depth", _P), ("depth_ray_stride", _I),
+        ("que_c2w", _P), ("que_near", _F), ("que_far", _F),
+        ("ref_w2c", _P), ("ref_depth_range", _P),
+        ("imgs_cl", _P), ("img_h", _I), ("img_w", _I),
+        ("img_feats_cl", _P), ("if_h", _I), ("if_w", _I),
+        ("ray_feats_cl", _P), ("rf_h", _I), ("rf_w", _I),
+        ("weights", _P), ("f1", _P), ("f2", _P),
+        ("pixel_colors", _P), ("render_depth", _P), ("hit_prob", _P), ("density", _P), ("colors", _P),
+        ("fine_depth", _P), ("fine_dn", _I), ("fine_u", _P), ("fine_use_all", _I), ("use_disp", _I),
+        ("fine_inds", _P), ("prob_dbg", _P), ("prj_dbg", _P), ("feat_dbg", _P),
+    ]
+
+
+_PI = ctypes.POINTER(_I)
+_PLL = ctypes.POINTER(ctypes.c_longlong)
+SIGNATURES.update({
+    "pgrf_render_pass_fwd": (_I, [ctypes.POINTER(RenderArgs), _P]),
+    "pgrf_render_workspace": (_I, [_I, ctypes.c_longlong, _PLL, _PLL]),
+    "pgrf_weight_blob_floats": (_I, []),
+    "pgrf_weight_num_layers": (_I, []),
+    "pgrf_weight_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI, _PI]),
+    "pgrf_weight_aux_offsets": (_I, [_PI, _PI, _PI]),
+})
+
+
+def weight_layers():
+    """[(name, K, N, Npad, has_bias, k_begin, w_offset, b_offset)] straight from the C side."""
+    lib = load()
+    out = []
+    for i in range(lib.pgrf_weight_num_layers()):
+        name = ctypes.create_string_buffer(128)
+        vals = [_I() for _ in range(7)]
+        check(lib.pgrf_weight_layer_info(i, name, 128, *[ctypes.byref(v) for v in vals]), "pgrf_weight_layer_info")
+        out.append((name.value.decode(),) + tuple(v.value for v in vals))
+    return out
+
+
+def weight_aux_offsets():
+    lib = load()
+    a, b, c = _I(), _I(), _I()
+    check(lib.pgrf_weight_aux_offsets(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "pgrf_weight_aux_offsets")
+    return a.value, b.value, c.value

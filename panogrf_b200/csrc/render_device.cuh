@@ -1,0 +1,288 @@
+// Device building blocks of the render-path kernels: activations, the shared-memory SIMT GEMM used
+// for every Linear layer of the fp32 parity path, TMA (cp.async.bulk) helpers, and the ERP geometry
+// of the renderer (network/spt_utils.py, network/render_ops.py).
+#pragma once
+#include "common.cuh"
+#include "render_layout.cuh"
+
+namespace pgrf {
+
+enum : int { ACT_NONE = 0, ACT_ELU = 1, ACT_RELU = 2 };
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float softplusf(float x) { return x > 20.f ? x : log1pf(__expf(x)); }
+template <int ACT>
+__device__ __forceinline__ float activate(float x) {
+  if (ACT == ACT_ELU) return elu1(x);
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  return x;
+}
+
+// -------------------------------------------------------------------------------------------------
+// C[n][m] = ACT( rs[m] * sum_k A[k][m] * Wt[k][n] + bias[n] + add[n][m % T] )        (all in smem)
+//   A  : [K][lda]  feature-major activations (m contiguous)
+//   Wt : [K][ldw]  k-major weights (n contiguous)
+//   C  : [N][ldc]
+// Work is cut into warp tiles of 32 rows x (4*TN) columns; lane = (g = lane>>3 : column group,
+// rg = lane&7 : group of 4 consecutive rows) owns a 4 x TN register tile.  Per k step a lane issues
+// one 128-bit load of A (8 distinct addresses per warp, broadcast over g) and TN/4 128-bit loads of
+// Wt (4 distinct addresses, broadcast over rg): 4*TN FMAs per 1+TN/4 shared-memory wavefronts.
+// -------------------------------------------------------------------------------------------------
+template <int TN, int ACT, bool ROW_SCALE, bool SAMPLE_ADD>
+__device__ __forceinline__ void gemm_smem(const float* __restrict__ A, int lda, int K,
+                                          const float* __restrict__ Wt, int ldw,
+                                          const float* __restrict__ bias,
+                                          float* __restrict__ C, int ldc, int M, int N,
+                                          const float* __restrict__ row_scale,
+                                          const float* __restrict__ sample_add, int T, int ld_add,
+                                          int warp, int lane, int nwarps) {
+  constexpr int CT = 4 * TN;  // columns per warp tile
+  const int ntm = M >> 5, ntn = (N + CT - 1) / CT;
+  const int rg = lane & 7, g = lane >> 3;
+  for (int t = warp; t < ntm * ntn; t += nwarps) {
+    const int m0 = (t % ntm) * 32 + 4 * rg;
+    const int n0 = (t / ntm) * CT + TN * g;
+    if (n0 >= N) continue;  // ragged last column tile (N multiple of TN but not of CT)
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    const float* a_ptr = A + m0;
+    const float* w_ptr = Wt + n0;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(a_ptr + k * lda);
+      float w[TN];
+#pragma unroll
+      for (int j4 = 0; j4 < TN / 4; ++j4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w_ptr + k * ldw + 4 * j4);
+        w[4 * j4] = wv.x; w[4 * j4 + 1] = wv.y; w[4 * j4 + 2] = wv.z; w[4 * j4 + 3] = wv.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        acc[0][j] = fmaf(a.x, w[j], acc[0][j]);
+        acc[1][j] = fmaf(a.y, w[j], acc[1][j]);
+        acc[2][j] = fmaf(a.z, w[j], acc[2][j]);
+        acc[3][j] = fmaf(a.w, w[j], acc[3][j]);
+      }
+    }
+    float rs[4] = {1.f, 1.f, 1.f, 1.f};
+    if (ROW_SCALE) {
+      const float4 r = *reinterpret_cast<const float4*>(row_scale + m0);
+      rs[0] = r.x; rs[1] = r.y; rs[2] = r.z; rs[3] = r.w;
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + j;
+      const float b = bias ? bias[n] : 0.f;
+      float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (SAMPLE_ADD) add = *reinterpret_cast<const float4*>(sample_add + n * ld_add + (m0 % T));
+      float4 o;
+      o.x = activate<ACT>(fmaf(rs[0], acc[0][j], b) + add.x);
+      o.y = activate<ACT>(fmaf(rs[1], acc[1][j], b) + add.y);
+      o.z = activate<ACT>(fmaf(rs[2], acc[2][j], b) + add.z);
+      o.w = activate<ACT>(fmaf(rs[3], acc[3][j], b) + add.w);
+      *reinterpret_cast<float4*>(C + n * ldc + m0) = o;
+    }
+  }
+}
+
+// Small layers: one thread per row, outputs in registers.  Wt[k][NP] k-major, read as broadcast float4.
+template <int K, int N, int NP>
+__device__ __forceinline__ void row_layer(const float* __restrict__ A, int lda, int m,
+                                          const float* __restrict__ Wt, const float* __restrict__ bias,
+                                          float (&out)[NP]) {
+#pragma unroll
+  for (int n = 0; n < NP; ++n) out[n] = bias ? bias[n] : 0.f;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float a = A[k * lda + m];
+#pragma unroll
+    for (int n4 = 0; n4 < NP / 4; ++n4) {
+      const float4 w = *reinterpret_cast<const float4*>(Wt + k * NP + 4 * n4);
+      out[4 * n4] = fmaf(a, w.x, out[4 * n4]);
+      out[4 * n4 + 1] = fmaf(a, w.y, out[4 * n4 + 1]);
+      out[4 * n4 + 2] = fmaf(a, w.z, out[4 * n4 + 2]);
+      out[4 * n4 + 3] = fmaf(a, w.w, out[4 * n4 + 3]);
+    }
+  }
+}
+// same, input vector already in registers
+template <int K, int N, int NP>
+__device__ __forceinline__ void reg_layer(const float (&in)[K], const float* __restrict__ Wt,
+                                          const float* __restrict__ bias, float (&out)[NP]) {
+#pragma unroll
+  for (int n = 0; n < NP; ++n) out[n] = bias ? bias[n] : 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int n4 = 0; n4 < NP / 4; ++n4) {
+      const float4 w = *reinterpret_cast<const float4*>(Wt + k * NP + 4 * n4);
+      out[4 * n4] = fmaf(in[k], w.x, out[4 * n4]);
+      out[4 * n4 + 1] = fmaf(in[k], w.y, out[4 * n4 + 1]);
+      out[4 * n4 + 2] = fmaf(in[k], w.z, out[4 * n4 + 2]);
+      out[4 * n4 + 3] = fmaf(in[k], w.w, out[4 * n4 + 3]);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// TMA 1-D bulk copies + mbarrier (PTX; SASS: UBLKCP / SYNCS)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// global -> shared, completion signalled on the mbarrier (bytes multiple of 16, 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global (bulk async group)
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// -------------------------------------------------------------------------------------------------
+// ERP geometry of the renderer — (W-1),(H-1) pixel convention (network/spt_utils.py)
+// -------------------------------------------------------------------------------------------------
+
+// pixel (x,y) -> unit direction in the camera frame (ray_utils.py:4-16, spt_utils.py:37-127)
+__device__ __forceinline__ void equi_unit_dir(int dataset, float x, float y, int H, int W, float& dx, float& dy, float& dz) {
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  float theta, phi;
+  switch (dataset) {
+    case PGRF_DS_M3D:
+      x = fminf(fmaxf(x, 0.f), wm1); y = fminf(fmaxf(y, 0.f), hm1);
+      theta = x / wm1 * 2.f * PGRF_PI_F - PGRF_HALF_PI_F;
+      phi = y / hm1 * PGRF_PI_F;
+      break;
+    case PGRF_DS_REPLICA_TEST:
+      theta = x * 2.f * PGRF_PI_F / wm1 - PGRF_PI_F;
+      phi = -y * PGRF_PI_F / hm1 + PGRF_HALF_PI_F;
+      break;
+    case PGRF_DS_RESIDENTIAL:
+      x = fminf(fmaxf(x, 0.f), wm1); y = fminf(fmaxf(y, 0.f), hm1);
+      theta = PGRF_PI_F * (2.f * x / wm1 - 1.5f);
+      phi = PGRF_PI_F * (0.5f - y / hm1);
+      break;
+    default:
+      x = fminf(fmaxf(x, 0.f), wm1); y = fminf(fmaxf(y, 0.f), hm1);
+      theta = (float)(-2.0 * PGRF_PI_D / (double)(W - 1)) * x + PGRF_TWO_PI_F;
+      phi = (float)(PGRF_PI_D / (double)(H - 1)) * y;
+      break;
+  }
+  float st, ct, sp, cp;
+  sincosf(theta, &st, &ct);
+  sincosf(phi, &sp, &cp);
+  switch (dataset) {
+    case PGRF_DS_M3D:          dx = sp * ct; dy = cp;  dz = sp * st; break;
+    case PGRF_DS_REPLICA_TEST: dx = st * cp; dy = -sp; dz = ct * cp; break;
+    case PGRF_DS_RESIDENTIAL:  dx = ct * cp; dy = sp;  dz = st * cp; break;
+    default:                   dx = sp * ct; dy = sp * st; dz = cp;  break;
+  }
+  const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+  dx /= n; dy /= n; dz /= n;
+}
+
+// torch.remainder(a, b) for b > 0
+__device__ __forceinline__ float py_mod(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.f && m < 0.f) m += b;
+  return m;
+}
+
+// camera-frame point -> (radius, pixel x, pixel y) (ray_utils.py:18-22, spt_utils.py:129-199)
+__device__ __forceinline__ void cam_to_equi(int dataset, float cx, float cy, float cz, int H, int W, float& radius, float& px, float& py) {
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  radius = sqrtf(cx * cx + cy * cy + cz * cz);
+  switch (dataset) {
+    case PGRF_DS_M3D: {
+      float theta = atan2f(cz, cx);
+      const float phi = acosf(cy / (radius + 1e-5f));
+      theta = py_mod(theta + PGRF_HALF_PI_F, PGRF_TWO_PI_F);
+      px = theta / PGRF_TWO_PI_F * wm1;
+      py = phi / PGRF_PI_F * hm1;
+      break;
+    }
+    case PGRF_DS_REPLICA_TEST: {
+      const float theta = atan2f(cx, cz);
+      const float phi = -asinf(cy / radius);
+      px = (float)((double)(W - 1) / (2.0 * PGRF_PI_D)) * (theta + PGRF_PI_F);
+      py = (float)((double)(H - 1) / PGRF_PI_D) * (-phi + PGRF_HALF_PI_F);
+      break;
+    }
+    case PGRF_DS_RESIDENTIAL: {
+      float theta = -atan2f(-cz, cx);
+      const float phi = asinf(cy / radius);
+      if (theta > PGRF_HALF_PI_F && theta <= PGRF_TWO_PI_F) theta -= PGRF_TWO_PI_F;
+      px = ((float)(1.0 / (2.0 * PGRF_PI_D)) * theta + 0.75f) * wm1;
+      py = (0.5f - phi / PGRF_PI_F) * hm1;
+      break;
+    }
+    default: {
+      float theta = atan2f(cy, cx);
+      const float phi = acosf(cz / radius);
+      if (theta < 0.f) theta += PGRF_TWO_PI_F;
+      px = wm1 * (1.f - theta / PGRF_TWO_PI_F);
+      py = phi * hm1 / PGRF_PI_F;
+      break;
+    }
+  }
+}
+
+// Bilinear footprint of F.grid_sample(padding_mode='border') as called by interpolate_feats
+// (network/ops.py:32-52): full-res pixel -> normalised -> map coordinates, clipped to the border.
+struct Footprint {
+  int off;        // texel index (y0*fw + x0) of the north-west tap
+  int dx, dy;     // 1 when the east / south neighbour is inside the map, else 0 (weight is 0 there)
+  float tx, ty;
+};
+__device__ __forceinline__ Footprint border_footprint(float px, float py, int h, int w, int fh, int fw) {
+  const bool align = (fh == h && fw == w);
+  const float xn = px / (float)(w - 1) * 2.f - 1.f;
+  const float yn = py / (float)(h - 1) * 2.f - 1.f;
+  float ix, iy;
+  if (align) {
+    ix = ((xn + 1.f) / 2.f) * (float)(fw - 1);
+    iy = ((yn + 1.f) / 2.f) * (float)(fh - 1);
+  } else {
+    ix = ((xn + 1.f) * (float)fw - 1.f) / 2.f;
+    iy = ((yn + 1.f) * (float)fh - 1.f) / 2.f;
+  }
+  ix = fminf(fmaxf(ix, 0.f), (float)(fw - 1));
+  iy = fminf(fmaxf(iy, 0.f), (float)(fh - 1));
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  Footprint f;
+  const int xi = (int)x0, yi = (int)y0;
+  f.tx = ix - x0;
+  f.ty = iy - y0;
+  f.dx = (xi + 1 < fw) ? 1 : 0;
+  f.dy = (yi + 1 < fh) ? 1 : 0;
+  f.off = yi * fw + xi;
+  return f;
+}
+
+}  // namespace pgrf

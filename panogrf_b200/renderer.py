@@ -1,0 +1,389 @@
+"""Drop-in for the render-time hot path of the reference's `network/renderer.py`.
+
+`NeuralRayBaseRenderer(cfg)` keeps the reference's constructor signature, config keys, method names
+(`render`, `render_impl`, `render_by_depth`) and the `state_dict()` names of the hot-path
+parameters (`[fine_]dist_decoder.*`, `[fine_]agg_net.*`), so a reference checkpoint loads with
+`load_state_dict(..., strict=False)`.  The per-ray-batch python/ATen pipeline
+(network/renderer.py:223-317, 435-524, 567-633, 635-686) is replaced by three persistent sm_100a
+kernels per pass (csrc/render_kernels.cu) reached through the C ABI.
+
+Out of scope here (SURVEY.md §8f "next"): the per-call CNN encoders (`image_encoder`,
+`vis_encoder`, `init_net`).  `render()` therefore takes `ref_imgs_info['img_feats']` and the already
+vis-encoded `ref_imgs_info['ray_feats']`, or runs user-supplied encoder callables if attached.
+Only the eval path (`is_train=False`, deterministic sampling, no autograd) is implemented.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .weights import pack_blob
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers with the reference's names / shapes / default initialisation
+# ------------------------------------------------------------------------------------------------
+
+def _seq(dims, act_slots=True):
+    """Linear layers at even indices (0,2,4,...) like the reference's nn.Sequential stacks."""
+    mods = []
+    for i in range(len(dims) - 1):
+        mods.append(nn.Linear(dims[i], dims[i + 1]))
+        mods.append(nn.Identity())
+    return nn.Sequential(*mods)
+
+
+def _kaiming(module):
+    for m in module.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.kaiming_normal_(m.weight.data)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias.data)
+
+
+class MixtureLogisticsDistDecoder(nn.Module):
+    """Parameters of network/dist_decoder.py:53-97."""
+    default_cfg = {"feats_dim": 32, "bias_val": 0.05, "use_vis": True}
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        d = self.cfg["feats_dim"]
+        if d != 32:
+            raise _lib.PanoGRFError("panogrf_b200 kernels are built for feats_dim == 32")
+        self.mean_decoder = _seq([d, d, d, 2])
+        self.var_decoder = _seq([d, d, d, 2])
+        self.aw_decoder = _seq([d, d, d, 1])
+        if self.cfg["use_vis"]:
+            self.vis_decoder = _seq([d, d, d, 1])
+
+
+class _RayAttention(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w_qs = nn.Linear(16, 16, bias=False)
+        self.w_ks = nn.Linear(16, 16, bias=False)
+        self.w_vs = nn.Linear(16, 16, bias=False)
+        self.fc = nn.Linear(16, 16, bias=False)
+        self.layer_norm = nn.LayerNorm(16, eps=1e-6)
+
+
+class IBRNetWithNeuRay(nn.Module):
+    """Parameters of network/ibrnet.py:239-300."""
+
+    def __init__(self, neuray_in_dim=32, in_feat_ch=32, n_samples=64):
+        super().__init__()
+        if neuray_in_dim != 32 or in_feat_ch != 32:
+            raise _lib.PanoGRFError("panogrf_b200 kernels are built for neuray_dim == in_feat_ch == 32")
+        self.n_samples = n_samples
+        self.ray_dir_fc = _seq([4, 16, in_feat_ch + 3])
+        self.base_fc = _seq([(in_feat_ch + 3) * 5 + neuray_in_dim, 64, 32])
+        self.vis_fc = _seq([32, 32, 33])
+        self.vis_fc2 = _seq([32, 32, 1])
+        self.geometry_fc = _seq([32 * 2 + 1, 64, 16])
+        self.ray_attention = _RayAttention()
+        self.out_geometry_fc = _seq([16, 16, 1])
+        self.rgb_fc = _seq([32 + 1 + 4, 16, 8, 1])
+        self.neuray_fc = _seq([neuray_in_dim, 8, 1])
+        for m in (self.base_fc, self.vis_fc2, self.vis_fc, self.geometry_fc, self.rgb_fc, self.neuray_fc):
+            _kaiming(m)
+
+
+class DefaultAggregationNet(nn.Module):
+    """Parameters of network/aggregate_net.py:16-39."""
+    default_cfg = {"sample_num": 64, "neuray_dim": 32, "use_img_feats": False}
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        if self.cfg.get("level") in [-1]:
+            raise _lib.PanoGRFError("level=-1 (16-channel image features) is not supported")
+        for k in ("wo_geometry", "wo_appearance"):
+            if self.cfg.get(k):
+                raise _lib.PanoGRFError(f"ablation switch {k} is not supported by the fused kernels")
+        dim = self.cfg["neuray_dim"]
+        self.agg_impl = IBRNetWithNeuRay(dim, in_feat_ch=32, n_samples=self.cfg["sample_num"])
+        self.prob_embed = nn.Sequential(nn.Linear(2 + 32, dim), nn.Identity(), nn.Linear(dim, dim))
+
+
+name2dist_decoder = {"mixture_logistics": MixtureLogisticsDistDecoder}
+name2agg_net = {"default": DefaultAggregationNet}
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side tables that must be bit-identical to the reference's (tiny, computed once on the CPU)
+# ------------------------------------------------------------------------------------------------
+
+def coarse_depth_table(cfg, sample_num, use_disp):
+    """sample_depth with random_sample=False (network/render_ops.py:292-339): one (dn,) table —
+    the deterministic samples are identical for every ray."""
+    near = torch.ones(1) * cfg["min_depth"]
+    far = torch.ones(1) * cfg["max_depth"]
+    dn = sample_num
+    assert dn > 2
+    val = torch.arange(1, dn - 1, dtype=torch.float32)[None, None, :] + torch.zeros(1, 1, dn - 2)
+    if not use_disp:
+        interval = (far - near) / (dn - 1)
+        ticks = interval[:, None, None] * val
+        diff = far - near
+        ticks = torch.cat([torch.zeros(1, 1, 1), ticks, diff[:, None, None]], -1)
+        return (near[:, None, None] + ticks).reshape(-1)
+    interval = (1 / far - 1 / near) / (dn - 1)
+    ticks = interval[:, None, None] * val
+    diff = 1 / far - 1 / near
+    ticks = torch.cat([torch.zeros(1, 1, 1), ticks, diff[:, None, None]], -1)
+    return (1 / (1 / near[:, None, None] + ticks)).reshape(-1)
+
+
+def fine_u_table(fdn):
+    """render_ops.py:442-445."""
+    interval = 1 / fdn
+    return (0.5 * interval + torch.arange(fdn) * interval).float()
+
+
+def to_channels_last(x, pad_to=None):
+    """(N,C,H,W) -> contiguous (N,H,W,C[+pad])."""
+    x = x.float().permute(0, 2, 3, 1)
+    if pad_to is not None and x.shape[-1] < pad_to:
+        x = torch.cat([x, x.new_zeros(*x.shape[:-1], pad_to - x.shape[-1])], -1)
+    return x.contiguous()
+
+
+class NeuralRayBaseRenderer(nn.Module):
+    base_cfg = {
+        "dist_decoder_type": "mixture_logistics", "dist_decoder_cfg": {},
+        "agg_net_type": "default", "agg_net_cfg": {},
+        "use_hierarchical_sampling": False, "fine_agg_net_cfg": {}, "fine_dist_decoder_cfg": {},
+        "fine_depth_sample_num": 64, "fine_depth_use_all": False,
+        "ray_batch_num": 2048, "depth_sample_num": 64,
+        "use_ray_mask": True, "ray_mask_view_num": 1, "ray_mask_point_num": 8,
+        "render_depth": False, "render_uncert": False, "debug": False, "use_disp": True,
+    }
+    #: rays per kernel launch (the reference's ray_batch_num only bounds ITS activation memory;
+    #: here it bounds the F1/F2 workspaces, sized to stay L2 resident)
+    rays_per_launch = 4096
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.base_cfg, **cfg}
+        for k in ("agg_net_cfg", "fine_agg_net_cfg", "dist_decoder_cfg", "fine_dist_decoder_cfg"):
+            self.cfg[k] = dict(self.cfg.get(k) or {})
+        for key in ("sample_num", "level", "wo_geometry", "wo_appearance"):      # renderer.py:67-78
+            if key in cfg:
+                self.cfg["agg_net_cfg"][key] = self.cfg[key]
+                self.cfg["fine_agg_net_cfg"][key] = self.cfg[key]
+        if self.cfg["dataset_name"] not in _lib.DATASET_IDS:
+            raise Exception(f"unknown dataset_name {self.cfg['dataset_name']!r}")
+        if self.cfg.get("debug"):
+            raise _lib.PanoGRFError("cfg['debug'] (network bypass) is not part of the hot path")
+        if self.cfg.get("diner_depth_guided_sampling"):
+            raise _lib.PanoGRFError("diner_depth_guided_sampling is not implemented (SURVEY.md §8f rank 3)")
+        self.dist_decoder = name2dist_decoder[self.cfg["dist_decoder_type"]](self.cfg["dist_decoder_cfg"])
+        self.agg_net = name2agg_net[self.cfg["agg_net_type"]](self.cfg["agg_net_cfg"])
+        if self.cfg["use_hierarchical_sampling"] and not self.cfg.get("one_mlp"):
+            self.fine_dist_decoder = name2dist_decoder[self.cfg["dist_decoder_type"]](self.cfg["fine_dist_decoder_cfg"])
+            self.fine_agg_net = name2agg_net[self.cfg["agg_net_type"]](self.cfg["fine_agg_net_cfg"])
+        self.image_encoder = None    # optional user-supplied encoders (out of scope, see module docstring)
+        self.vis_encoder = None
+        self._blob_cache = {}
+
+    # ---- weights --------------------------------------------------------------------------------
+    def _blob(self, fine, device):
+        params = [p for n, p in self.named_parameters()
+                  if n.startswith(("fine_dist_decoder.", "fine_agg_net.") if fine else ("dist_decoder.", "agg_net."))]
+        key = (fine, str(device), tuple((p.data_ptr(), p._version) for p in params))
+        hit = self._blob_cache.get(fine)
+        if hit is None or hit[0] != key:
+            agg = self.fine_agg_net if fine else self.agg_net
+            blob = pack_blob(self.state_dict(), fine, agg.cfg["sample_num"], device)
+            self._blob_cache[fine] = (key, blob)
+        return self._blob_cache[fine][1]
+
+    # ---- one pass -------------------------------------------------------------------------------
+    def _pass(self, ctx, coords, depth, depth_stride, fine_net, want_fine, outs, r0, keep_hit):
+        """Launch rows/samples/rays kernels for `coords` (rn,2) with sample depths `depth`."""
+        cfg, lib = self.cfg, _lib.load()
+        rn = coords.shape[0]
+        dn = depth.shape[-1]
+        dev = coords.device
+        agg = self.fine_agg_net if fine_net else self.agg_net
+        if agg.cfg["sample_num"] != dn:
+            raise RuntimeError(f"The size of tensor a ({dn}) must match the size of tensor b "
+                               f"({agg.cfg['sample_num']}) at non-singleton dimension 1")   # ibrnet.py:358
+        a = _lib.RenderArgs()
+        a.dataset = _lib.DATASET_IDS[cfg["dataset_name"]]
+        a.H, a.W = int(cfg["height"]), int(cfg["width"])
+        a.rfn, a.rn, a.dn = ctx["rfn"], rn, dn
+        a.use_vis = int(bool(self.dist_decoder.cfg["use_vis"]))
+        a.bias_val = float((self.fine_dist_decoder if fine_net else self.dist_decoder).cfg["bias_val"])
+        a.coords, a.depth, a.depth_ray_stride = _lib.ptr(coords), _lib.ptr(depth), depth_stride
+        a.que_c2w, a.que_near, a.que_far = _lib.ptr(ctx["c2w"]), ctx["que_near"], ctx["que_far"]
+        a.ref_w2c, a.ref_depth_range = _lib.ptr(ctx["w2c"]), _lib.ptr(ctx["ref_range"])
+        a.imgs_cl, a.img_h, a.img_w = _lib.ptr(ctx["imgs"]), ctx["imgs"].shape[1], ctx["imgs"].shape[2]
+        a.img_feats_cl, a.if_h, a.if_w = _lib.ptr(ctx["img_feats"]), ctx["img_feats"].shape[1], ctx["img_feats"].shape[2]
+        a.ray_feats_cl, a.rf_h, a.rf_w = _lib.ptr(ctx["ray_feats"]), ctx["ray_feats"].shape[1], ctx["ray_feats"].shape[2]
+        a.weights = _lib.ptr(self._blob(fine_net, dev))
+        f1n, f2n = ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(lib.pgrf_render_workspace(a.rfn, rn * dn, ctypes.byref(f1n), ctypes.byref(f2n)), "pgrf_render_workspace")
+        ws = ctx["ws"]
+        if ws.get("f1") is None or ws["f1"].numel() < f1n.value:
+            ws["f1"] = torch.empty(f1n.value, device=dev, dtype=torch.float32)
+        if ws.get("f2") is None or ws["f2"].numel() < f2n.value:
+            ws["f2"] = torch.empty(f2n.value, device=dev, dtype=torch.float32)
+        a.f1, a.f2 = _lib.ptr(ws["f1"]), _lib.ptr(ws["f2"])
+        sl = slice(r0, r0 + rn)
+        a.pixel_colors = _lib.ptr(outs["pixel_colors_nr"][0, sl])
+        a.render_depth = _lib.ptr(outs["render_depth"][0, sl]) if "render_depth" in outs else None
+        a.density = _lib.ptr(outs["density_nr"][0, sl])
+        a.colors = _lib.ptr(outs["colors_nr"][0, sl])
+        hit = None
+        if keep_hit:
+            a.hit_prob = _lib.ptr(outs["hit_prob_nr"][0, sl])
+        fine_depth = None
+        if want_fine:
+            fdn = int(cfg["fine_depth_sample_num"])
+            use_all = bool(cfg["fine_depth_use_all"])
+            fine_depth = torch.empty(rn, fdn + (dn if use_all else 0), device=dev, dtype=torch.float32)
+            a.fine_depth, a.fine_dn, a.fine_u = _lib.ptr(fine_depth), fdn, _lib.ptr(ctx["fine_u"])
+            a.fine_use_all, a.use_disp = int(use_all), int(bool(cfg["use_disp"]))
+        for k in ("prob_dbg", "prj_dbg", "feat_dbg", "fine_inds"):
+            if ctx.get(k) is not None:
+                setattr(a, k, _lib.ptr(ctx[k]))
+        with torch.cuda.device(dev):
+            rc = lib.pgrf_render_pass_fwd(ctypes.byref(a), _lib.stream_ptr())
+        _lib.check(rc, "pgrf_render_pass_fwd")
+        return fine_depth
+
+    def _context(self, que_imgs_info, ref_imgs_info):
+        imgs = ref_imgs_info["imgs"]
+        _lib.require_cuda(imgs, ref_imgs_info["ray_feats"], ref_imgs_info["img_feats"], que_imgs_info["coords"])
+        dev = imgs.device
+        c2w = que_imgs_info["c2w"]
+        assert c2w.shape[0] == 1, "que_imgs_info c2w.shape[0]=1"                 # render_ops.py:89
+        if ref_imgs_info["ray_feats"].shape[1] != 32 or ref_imgs_info["img_feats"].shape[1] != 32:
+            raise _lib.PanoGRFError("ray_feats / img_feats must have 32 channels")
+        dr = que_imgs_info["depth_range"].float().cpu()
+        return {
+            "rfn": imgs.shape[0],
+            "imgs": to_channels_last(imgs, 4),
+            "img_feats": to_channels_last(ref_imgs_info["img_feats"]),
+            "ray_feats": to_channels_last(ref_imgs_info["ray_feats"]),
+            "w2c": ref_imgs_info["w2c"].float().contiguous().to(dev),
+            "ref_range": ref_imgs_info["depth_range"].float().contiguous().to(dev),
+            "c2w": c2w.float().reshape(3, 4).contiguous().to(dev),
+            "que_near": float(dr[0, 0]), "que_far": float(dr[0, 1]),
+            "fine_u": fine_u_table(int(self.cfg["fine_depth_sample_num"])).to(dev),
+            "ws": {},
+        }
+
+    # ---- reference API --------------------------------------------------------------------------
+    def render_impl(self, que_imgs_info, ref_imgs_info, is_train, is_perspec=False, _ctx=None, _outs=None, _r0=0,
+                    keep_hit_prob=False):
+        """network/renderer.py:567-633 (default, non-diner branch) for the rays in que_imgs_info['coords']."""
+        if is_train:
+            raise NotImplementedError("panogrf_b200 renderer: only the eval path (is_train=False) is implemented")
+        if is_perspec:
+            raise NotImplementedError("perspective (cube) query rays are outside the ERP hot path")
+        cfg = self.cfg
+        ctx = _ctx or self._context(que_imgs_info, ref_imgs_info)
+        coords = que_imgs_info["coords"]
+        assert coords.shape[0] == 1
+        coords2 = coords[0].float().contiguous()
+        rn = coords2.shape[0]
+        dev = coords2.device
+        dn = int(cfg["depth_sample_num"])
+        hier = bool(cfg["use_hierarchical_sampling"])
+        if _outs is None:
+            _outs = self._alloc_outputs(rn, dev, keep_hit_prob or hier, ctx['rfn'])
+            _r0 = 0
+        depth_table = coarse_depth_table(cfg, dn, cfg["use_disp"]).to(dev)
+        coarse = {k: v for k, v in _outs.items() if not k.endswith("_fine")}
+        fine_depth = self._pass(ctx, coords2, depth_table, 0, False, hier, coarse, _r0, "hit_prob_nr" in coarse)
+        if hier:
+            fine = {k[:-5]: v for k, v in _outs.items() if k.endswith("_fine")}
+            self._pass(ctx, coords2, fine_depth, fine_depth.shape[1], not cfg.get("one_mlp", False), False, fine, _r0,
+                       "hit_prob_nr" in fine)
+            if "que_depth_fine" in _outs:
+                _outs["que_depth_fine"][0, _r0:_r0 + rn] = fine_depth
+        return _outs
+
+    def _alloc_outputs(self, rn, dev, keep_hit_prob, rfn):
+        cfg = self.cfg
+        dn = int(cfg["depth_sample_num"])
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        outs = {"pixel_colors_nr": e(1, rn, 3), "colors_nr": e(1, rn, dn, 3), "density_nr": e(1, rn, dn)}
+        if keep_hit_prob:
+            outs["hit_prob_nr"] = e(1, rn, dn)
+        if cfg["use_ray_mask"]:
+            # every projection is "valid" in the ERP path: mask of ones (renderer.py:289-293)
+            views_ok = rfn >= cfg["ray_mask_view_num"]
+            outs["ray_mask"] = torch.full((1, rn), bool(views_ok and dn > cfg["ray_mask_point_num"]), device=dev)
+        if cfg["render_depth"]:
+            outs["render_depth"] = e(1, rn)
+        if cfg["use_hierarchical_sampling"]:
+            fdn = int(cfg["fine_depth_sample_num"]) + (dn if cfg["fine_depth_use_all"] else 0)
+            outs.update({"pixel_colors_nr_fine": e(1, rn, 3), "colors_nr_fine": e(1, rn, fdn, 3),
+                         "density_nr_fine": e(1, rn, fdn)})
+            if keep_hit_prob:
+                outs["hit_prob_nr_fine"] = e(1, rn, fdn)
+                outs["que_depth_fine"] = e(1, rn, fdn)
+            if cfg["use_ray_mask"]:
+                outs["ray_mask_fine"] = torch.full((1, rn), bool(views_ok and fdn > cfg["ray_mask_point_num"]), device=dev)
+            if cfg["render_depth"]:
+                outs["render_depth_fine"] = e(1, rn)
+        return outs
+
+    def render(self, que_imgs_info, ref_imgs_info, is_train, is_perspec=False, keep_hit_prob=False):
+        """network/renderer.py:635-686: all rays of the query view; returns the reference's output dict."""
+        if is_train:
+            raise NotImplementedError("panogrf_b200 renderer: only the eval path (is_train=False) is implemented")
+        ref_imgs_info = dict(ref_imgs_info)
+        if "img_feats" not in ref_imgs_info:
+            if self.image_encoder is None or self.vis_encoder is None:
+                raise _lib.PanoGRFError(
+                    "ref_imgs_info has no 'img_feats': attach image_encoder/vis_encoder callables or pass "
+                    "pre-encoded maps (the CNN encoders are outside the hot path)")
+            feats = self.image_encoder(ref_imgs_info["imgs"])
+            ref_imgs_info["img_feats"] = feats
+            ref_imgs_info["ray_feats"] = self.vis_encoder(ref_imgs_info["ray_feats"], feats)
+        ctx = self._context(que_imgs_info, ref_imgs_info)
+        coords = que_imgs_info["coords"]
+        rn = coords.shape[1]
+        outs = self._alloc_outputs(rn, coords.device, keep_hit_prob, ctx['rfn'])
+        step = int(self.rays_per_launch)
+        for r0 in range(0, rn, step):
+            q = dict(que_imgs_info)
+            q["coords"] = coords[:, r0:r0 + step]
+            self.render_impl(q, ref_imgs_info, False, is_perspec, _ctx=ctx, _outs=outs, _r0=r0)
+        if not is_train and not keep_hit_prob:
+            outs = {k: v for k, v in outs.items() if not k.startswith("hit_prob")}
+        return outs
+
+    def render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, is_fine, is_perspec=False):
+        """network/renderer.py:223-317 for explicit per-ray sample depths (qn=1,rn,dn)."""
+        if is_train or is_perspec:
+            raise NotImplementedError("only the eval ERP path is implemented")
+        ctx = self._context(que_imgs_info, ref_imgs_info)
+        coords2 = que_imgs_info["coords"][0].float().contiguous()
+        rn, dn = coords2.shape[0], que_depth.shape[-1]
+        dev = coords2.device
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        outs = {"pixel_colors_nr": e(1, rn, 3), "hit_prob_nr": e(1, rn, dn), "colors_nr": e(1, rn, dn, 3),
+                "density_nr": e(1, rn, dn), "render_depth": e(1, rn)}
+        depth = que_depth.reshape(rn, dn).float().contiguous()
+        self._pass(ctx, coords2, depth, dn, bool(is_fine), False, outs, 0, True)
+        if self.cfg["use_ray_mask"]:
+            ok = ctx["rfn"] >= self.cfg["ray_mask_view_num"] and dn > self.cfg["ray_mask_point_num"]
+            outs["ray_mask"] = torch.full((1, rn), bool(ok), device=dev)
+        if not self.cfg["render_depth"]:
+            outs.pop("render_depth")
+        return outs
+
+    def forward(self, data, is_perspec=False):
+        que = dict(data["que_imgs_info"])
+        ref = dict(data["ref_imgs_info"])
+        return self.render(que, ref, "eval" not in data, is_perspec)
+
+
+name2network = {"neuray_base": NeuralRayBaseRenderer}

@@ -1,0 +1,62 @@
+"""Packing of the hot-path parameters into the blob layout of csrc/render_layout.cuh.
+
+Parameters keep the reference's `state_dict()` names (SURVEY.md §5 "Checkpoint / resume"):
+`[fine_]dist_decoder.{mean,var,aw,vis}_decoder.{0,2,4}`, `[fine_]agg_net.prob_embed.{0,2}`,
+`[fine_]agg_net.agg_impl.*` — so a reference `model.pth` loads unchanged.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def posenc_table(d_hid, n_samples):
+    """Sinusoid table of IBRNetWithNeuRay.posenc (network/ibrnet.py:305-313), fp64 -> fp32."""
+    pos = np.arange(n_samples)[:, None].astype(np.float64)
+    j = np.arange(d_hid)[None, :]
+    table = pos / np.power(10000, 2 * (j // 2) / d_hid)
+    table[:, 0::2] = np.sin(table[:, 0::2])
+    table[:, 1::2] = np.cos(table[:, 1::2])
+    return torch.from_numpy(table).float()
+
+
+def pack_blob(state, fine, n_samples, device):
+    """state: mapping name -> tensor (a state_dict). Returns a (blob_floats,) fp32 tensor on `device`.
+
+    `n_samples` is the length of the aggregation net's positional table (its cfg `sample_num`).
+    """
+    lib = _lib.load()
+    dd = "fine_dist_decoder" if fine else "dist_decoder"
+    agg = "fine_agg_net" if fine else "agg_net"
+    blob = torch.zeros(lib.pgrf_weight_blob_floats(), dtype=torch.float32)
+    for name, K, N, Npad, has_bias, k_begin, w_off, b_off in _lib.weight_layers():
+        key = name.replace("{dd}", dd).replace("{agg}", agg)
+        if key.endswith("ray_attention.qkv"):
+            base = key[:-len(".qkv")]
+            w = torch.cat([state[base + ".w_qs.weight"], state[base + ".w_ks.weight"], state[base + ".w_vs.weight"]], 0)
+            b = None
+        elif key.endswith("ray_attention.fc"):
+            w, b = state[key + ".weight"], None
+        else:
+            if key + ".weight" not in state:
+                if ".vis_decoder." in key:           # use_vis == False: decoder absent, slots stay zero
+                    continue
+                raise KeyError(f"missing parameter {key}.weight")
+            w = state[key + ".weight"]
+            b = state.get(key + ".bias")
+        w = w.detach().float().cpu()
+        assert w.shape[0] == N and w.shape[1] >= k_begin + K, (key, tuple(w.shape), K, N)
+        wt = torch.zeros(K, Npad)
+        wt[:, :N] = w[:, k_begin:k_begin + K].t()
+        blob[w_off:w_off + K * Npad] = wt.reshape(-1)
+        if has_bias:
+            assert b is not None, key
+            blob[b_off:b_off + N] = b.detach().float().cpu()
+    ln_off, pe_off, max_samples = _lib.weight_aux_offsets()
+    lnk = agg + ".agg_impl.ray_attention.layer_norm"
+    blob[ln_off:ln_off + 16] = state[lnk + ".weight"].detach().float().cpu()
+    blob[ln_off + 16:ln_off + 32] = state[lnk + ".bias"].detach().float().cpu()
+    if n_samples > max_samples:
+        raise _lib.PanoGRFError(f"sample_num={n_samples} exceeds the kernel limit {max_samples}")
+    blob[pe_off:pe_off + n_samples * 16] = posenc_table(16, n_samples).reshape(-1)
+    return blob.to(device)
