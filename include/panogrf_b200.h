@@ -138,6 +138,7 @@ typedef struct pgrf_render_args {
   float* prob_dbg;             /* (rfn,rn*dn,3) alpha, vis, hit_prob of prj_dict, optional */
   float* prj_dbg;              /* (rfn,rn*dn,6) pts(2), depth, dir(3) of prj_dict, optional */
   float* feat_dbg;             /* (rfn,rn*dn,67) ray_feats(32), rgb(3), img_feats(32) of prj_dict, optional */
+  int stage_mask;              /* 0 = all three kernels; else bit0 rows, bit1 samples, bit2 rays (profiling) */
 } pgrf_render_args;
 
 PGRF_API int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream);

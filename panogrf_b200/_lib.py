@@ -105,6 +105,17 @@ class RenderArgs(ctypes.Structure):
         ("pixel_colors", _P), ("render_depth", _P), ("hit_prob", _P), ("density", _P), ("colors", _P),
         ("fine_depth", _P), ("fine_dn", _I), ("fine_u", _P), ("fine_use_all", _I), ("use_disp", _I),
         ("fine_inds", _P), ("prob_dbg", _P), ("prj_dbg", _P), ("feat_dbg", _P),
+        ("stage_mask", _I),
+    ]
+
+
+class RenderViewArgs(ctypes.Structure):
+    """Mirror of `pgrf_render_view_args`."""
+    _fields_ = [
+        ("pass_", RenderArgs), ("hierarchical", _I), ("weights_fine", _P), ("bias_val_fine", _F),
+        ("rays_per_launch", _I), ("fine_depth_ws", _P),
+        ("pixel_colors_fine", _P), ("render_depth_fine", _P), ("hit_prob_fine", _P), ("density_fine", _P),
+        ("colors_fine", _P), ("que_depth_fine", _P),
     ]
 
 
@@ -113,6 +124,9 @@ _PLL = ctypes.POINTER(ctypes.c_longlong)
 SIGNATURES.update({
     "pgrf_render_pass_fwd": (_I, [ctypes.POINTER(RenderArgs), _P]),
     "pgrf_render_workspace": (_I, [_I, ctypes.c_longlong, _PLL, _PLL]),
+    "pgrf_render_view_fwd": (_I, [ctypes.POINTER(RenderViewArgs), _P]),
+    "pgrf_render_view_host": (_I, [ctypes.POINTER(RenderViewArgs)]),
+    "pgrf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "pgrf_weight_blob_floats": (_I, []),
     "pgrf_weight_num_layers": (_I, []),
     "pgrf_weight_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI, _PI]),

@@ -784,10 +784,10 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
     PGRF_CUDA(cudaFuncSetAttribute(render_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
     attr_done = true;
   }
-  render_rows_kernel<<<min(p.n_tiles, sms), kThreads, s1, st>>>(p);
-  render_samples_kernel<<<min(p.n_tiles, sms), kThreads, s2, st>>>(p);
-  render_rays_kernel<<<min(p.n_tiles3, sms), kThreads, s3, st>>>(p);
-  count_launch(3);
+  const int mask = a.stage_mask ? a.stage_mask : 7;
+  if (mask & 1) { render_rows_kernel<<<min(p.n_tiles, sms), kThreads, s1, st>>>(p); count_launch(); }
+  if (mask & 2) { render_samples_kernel<<<min(p.n_tiles, sms), kThreads, s2, st>>>(p); count_launch(); }
+  if (mask & 4) { render_rays_kernel<<<min(p.n_tiles3, sms), kThreads, s3, st>>>(p); count_launch(); }
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
 }

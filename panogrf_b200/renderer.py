@@ -187,6 +187,7 @@ class NeuralRayBaseRenderer(nn.Module):
         self.image_encoder = None    # optional user-supplied encoders (out of scope, see module docstring)
         self.vis_encoder = None
         self._blob_cache = {}
+        self._ws = {}
 
     # ---- weights --------------------------------------------------------------------------------
     def _blob(self, fine, device):
@@ -250,6 +251,7 @@ class NeuralRayBaseRenderer(nn.Module):
         for k in ("prob_dbg", "prj_dbg", "feat_dbg", "fine_inds"):
             if ctx.get(k) is not None:
                 setattr(a, k, _lib.ptr(ctx[k]))
+        a.stage_mask = int(ctx.get("stage_mask", 0))
         with torch.cuda.device(dev):
             rc = lib.pgrf_render_pass_fwd(ctypes.byref(a), _lib.stream_ptr())
         _lib.check(rc, "pgrf_render_pass_fwd")
@@ -349,16 +351,75 @@ class NeuralRayBaseRenderer(nn.Module):
             ref_imgs_info["ray_feats"] = self.vis_encoder(ref_imgs_info["ray_feats"], feats)
         ctx = self._context(que_imgs_info, ref_imgs_info)
         coords = que_imgs_info["coords"]
+        assert coords.shape[0] == 1
         rn = coords.shape[1]
         outs = self._alloc_outputs(rn, coords.device, keep_hit_prob, ctx['rfn'])
-        step = int(self.rays_per_launch)
-        for r0 in range(0, rn, step):
-            q = dict(que_imgs_info)
-            q["coords"] = coords[:, r0:r0 + step]
-            self.render_impl(q, ref_imgs_info, False, is_perspec, _ctx=ctx, _outs=outs, _r0=r0)
-        if not is_train and not keep_hit_prob:
-            outs = {k: v for k, v in outs.items() if not k.startswith("hit_prob")}
+        self._render_view(ctx, coords[0].float().contiguous(), outs)
         return outs
+
+    def _render_view(self, ctx, coords2, outs):
+        """One C-ABI call for the whole view: pgrf_render_view_fwd runs the ray-batch loop and the
+        coarse -> fine hand-off (network/renderer.py:647-683, 600-631) on the current stream."""
+        cfg, lib = self.cfg, _lib.load()
+        dev = coords2.device
+        rn = coords2.shape[0]
+        dn = int(cfg["depth_sample_num"])
+        hier = bool(cfg["use_hierarchical_sampling"])
+        fdn = int(cfg["fine_depth_sample_num"])
+        fine_total = fdn + (dn if cfg["fine_depth_use_all"] else 0) if hier else 0
+        one_mlp = bool(cfg.get("one_mlp", False))
+        for is_fine, n in ((False, dn), (True, fine_total)):
+            if is_fine and not hier:
+                continue
+            agg = self.fine_agg_net if (is_fine and not one_mlp) else self.agg_net
+            if agg.cfg["sample_num"] != n:
+                raise RuntimeError(f"The size of tensor a ({n}) must match the size of tensor b "
+                                   f"({agg.cfg['sample_num']}) at non-singleton dimension 1")   # ibrnet.py:358
+        chunk = max(1, min(int(self.rays_per_launch), rn))
+        va = _lib.RenderViewArgs()
+        a = va.pass_
+        a.dataset = _lib.DATASET_IDS[cfg["dataset_name"]]
+        a.H, a.W = int(cfg["height"]), int(cfg["width"])
+        a.rfn, a.rn, a.dn = ctx["rfn"], rn, dn
+        a.use_vis = int(bool(self.dist_decoder.cfg["use_vis"]))
+        a.bias_val = float(self.dist_decoder.cfg["bias_val"])
+        depth_table = coarse_depth_table(cfg, dn, cfg["use_disp"]).to(dev)
+        a.coords, a.depth, a.depth_ray_stride = _lib.ptr(coords2), _lib.ptr(depth_table), 0
+        a.que_c2w, a.que_near, a.que_far = _lib.ptr(ctx["c2w"]), ctx["que_near"], ctx["que_far"]
+        a.ref_w2c, a.ref_depth_range = _lib.ptr(ctx["w2c"]), _lib.ptr(ctx["ref_range"])
+        a.imgs_cl, a.img_h, a.img_w = _lib.ptr(ctx["imgs"]), ctx["imgs"].shape[1], ctx["imgs"].shape[2]
+        a.img_feats_cl, a.if_h, a.if_w = _lib.ptr(ctx["img_feats"]), ctx["img_feats"].shape[1], ctx["img_feats"].shape[2]
+        a.ray_feats_cl, a.rf_h, a.rf_w = _lib.ptr(ctx["ray_feats"]), ctx["ray_feats"].shape[1], ctx["ray_feats"].shape[2]
+        a.weights = _lib.ptr(self._blob(False, dev))
+        f1n, f2n = ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(lib.pgrf_render_workspace(a.rfn, chunk * max(dn, fine_total), ctypes.byref(f1n), ctypes.byref(f2n)),
+                   "pgrf_render_workspace")
+        ws = self._ws.setdefault(str(dev), {})
+        for key, n in (("f1", f1n.value), ("f2", f2n.value), ("fine", chunk * max(fine_total, 1))):
+            if ws.get(key) is None or ws[key].numel() < n:
+                ws[key] = torch.empty(n, device=dev, dtype=torch.float32)
+        a.f1, a.f2 = _lib.ptr(ws["f1"]), _lib.ptr(ws["f2"])
+        opt = lambda k: _lib.ptr(outs[k][0]) if k in outs else None
+        a.pixel_colors = _lib.ptr(outs["pixel_colors_nr"][0])
+        a.render_depth, a.hit_prob = opt("render_depth"), opt("hit_prob_nr")
+        a.density, a.colors = opt("density_nr"), opt("colors_nr")
+        va.hierarchical = int(hier)
+        va.rays_per_launch = chunk
+        keep = [depth_table]
+        if hier:
+            a.fine_dn, a.fine_u = fdn, _lib.ptr(ctx["fine_u"])
+            a.fine_use_all, a.use_disp = int(bool(cfg["fine_depth_use_all"])), int(bool(cfg["use_disp"]))
+            va.weights_fine = _lib.ptr(self._blob(not one_mlp, dev))
+            va.bias_val_fine = float((self.dist_decoder if one_mlp else self.fine_dist_decoder).cfg["bias_val"])
+            va.fine_depth_ws = _lib.ptr(ws["fine"])
+            va.pixel_colors_fine = _lib.ptr(outs["pixel_colors_nr_fine"][0])
+            va.render_depth_fine, va.hit_prob_fine = opt("render_depth_fine"), opt("hit_prob_nr_fine")
+            va.density_fine, va.colors_fine = opt("density_nr_fine"), opt("colors_nr_fine")
+            va.que_depth_fine = opt("que_depth_fine")
+        with torch.cuda.device(dev):
+            rc = lib.pgrf_render_view_fwd(ctypes.byref(va), _lib.stream_ptr())
+        _lib.check(rc, "pgrf_render_view_fwd")
+        del keep
 
     def render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, is_fine, is_perspec=False):
         """network/renderer.py:223-317 for explicit per-ray sample depths (qn=1,rn,dn)."""
