@@ -80,6 +80,9 @@ PGRF_API int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, int 
                          int dataset, int cost_type, int layout, int groups,
                          float* out, int* err_flag, void* stream);
 
+/* tuning knobs for experiments ("cv_jb": gathers batched per lane 2|4|8, "cv_dchunk": depths per CTA, 0 = heuristic) */
+PGRF_API int pgrf_debug_set(const char* key, int value);
+
 /* Same computation from/to HOST buffers (H2D + kernel + D2H + sync). Returns PGRF_ERANGE if flagged. */
 PGRF_API int pgrf_cost_volume_host(const float* images, int B, int S, int H, int W, int C,
                           const float* depths, const float* depth_volume, int D,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "pgrf_last_error": (_c.c_char_p, []),
     "pgrf_version": (_I, []),
     "pgrf_launch_count": (_c.c_int64, []),
+    "pgrf_debug_set": (_I, [_c.c_char_p, _I]),
     "pgrf_cost_volume_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P]),
     "pgrf_cost_volume_host": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _F, _I, _I, _I, _I, _P]),
 }

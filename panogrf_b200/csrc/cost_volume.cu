@@ -44,9 +44,14 @@ struct CvParams {
 
 struct __align__(16) TapRec {
   float tx, ty;   // fractional offsets inside the 2x2 footprint
-  int off4;       // float4 index of the (y0,x0) texel inside one (H,W,C) view
-  unsigned mask;  // bit0 nw, bit1 ne, bit2 sw, bit3 se: tap inside the map (zeros padding)
+  int off4;       // float4 index of the north-west texel inside one (H,W,C) view
+  int pad;
 };
+// The footprint is canonicalised so that all four taps are inside the map: for uv in [-1,1] the only
+// out-of-map tap of grid_sample(zeros padding) is x0+1 == W (or y0+1 == H) reached with weight exactly 0
+// when ix == W-1; shifting the footprint one texel back (x0 = W-2, tx = 1) gives bit-identical weights
+// (1-tx = 0 on the west taps) and needs no predication.  Out-of-range uv (flagged, the reference asserts)
+// is clamped the same way so the gather stays memory-safe.
 
 // ---- pixel -> unit ray, per dataset (spherical_cost_volume.py:272-301, my_torch_helpers.py:33-58) ----
 __device__ __forceinline__ void pixel_ray(const CvParams& p, int x, int y, float& rx, float& ry, float& rz) {
@@ -128,7 +133,7 @@ __device__ __forceinline__ void point_uv(int dataset, float cx, float cy, float 
   v = 2.f * vv / PGRF_PI_F - 1.f;
 }
 
-template <int C, bool PLANAR>
+template <int C, bool PLANAR, bool SINGLE, int JBT>
 __global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams p) {
   constexpr int CG = C / 4;      // lanes (float4 channel groups) per pixel
   constexpr int PPS = 32 / CG;   // pixels per sub-iteration of phase B
@@ -194,6 +199,8 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams 
     if (px < p.W) ref[j] = ldg4(img4 + (size_t)p.ref_idx * view_f4 + ((size_t)y * p.W + px) * CG + cg);
   }
 
+  const float4* lane_base = img4 + cg;
+  const int row_f4 = p.W * CG;
   const bool use_div = p.divisor != 0.f;
   const size_t plane = (size_t)p.H * p.W;
   bool bad = false;
@@ -215,64 +222,73 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams 
       // grid_sample(align_corners=True) un-normalisation, ATen grid_sampler_unnormalize
       const float ix = ((u + 1.f) / 2.f) * (float)(p.W - 1);
       const float iy = ((v + 1.f) / 2.f) * (float)(p.H - 1);
-      const float x0f = floorf(ix), y0f = floorf(iy);
-      // clamp before the int conversion so a flagged (NaN / out-of-range) voxel cannot index wildly
-      const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)p.W);
-      const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)p.H);
+      float x0f = floorf(ix), y0f = floorf(iy);
+      x0f = fminf(fmaxf(x0f, 0.f), (float)(p.W - 2));   // NaN -> 0
+      y0f = fminf(fmaxf(y0f, 0.f), (float)(p.H - 2));
       TapRec r;
       r.tx = ix - x0f;
       r.ty = iy - y0f;
-      r.off4 = (y0 * p.W + x0) * CG;
-      const bool xl = x0 >= 0 && x0 < p.W, xr = x0 + 1 >= 0 && x0 + 1 < p.W;
-      const bool yt = y0 >= 0 && y0 < p.H, yb = y0 + 1 >= 0 && y0 + 1 < p.H;
-      const bool fin = (ix == ix) && (iy == iy);
-      r.mask = fin ? ((xl && yt) | ((xr && yt) << 1) | ((xl && yb) << 2) | ((xr && yb) << 3)) : 0u;
+      r.off4 = ((int)y0f * p.W + (int)x0f) * CG;
+      r.pad = 0;
       rec[s * 32 + lane] = r;
     }
     __syncwarp();
 
     // ---------------- phase B: one lane per (pixel, float4 of channels) ----------------
+    // Sub-iterations are processed JB at a time with ALL their gathers issued before the first use, so a
+    // lane keeps 4*JB independent 128-bit loads in flight (the kernel is latency bound on these L1/L2 hits).
+    constexpr int JB = (NSUB >= JBT) ? JBT : NSUB;
+    float4* out_cl = reinterpret_cast<float4*>(p.out) + ((((size_t)b * p.D + d) * p.H + y) * p.W + x_warp) * CG + lane;
 #pragma unroll
-    for (int j = 0; j < NSUB; ++j) {
-      const int pi = j * PPS + pp;
-      const int px = x_warp + pi;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < p.n_src; ++s) {
-        const TapRec r = rec[s * 32 + pi];
-        const float4* base = img4 + (size_t)p.src_views[s] * view_f4 + r.off4 + cg;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 nw = (r.mask & 1u) ? ldg4(base) : z4;
-        const float4 ne = (r.mask & 2u) ? ldg4(base + CG) : z4;
-        const float4 sw = (r.mask & 4u) ? ldg4(base + (size_t)p.W * CG) : z4;
-        const float4 se = (r.mask & 8u) ? ldg4(base + (size_t)p.W * CG + CG) : z4;
-        const float tx1 = 1.f - r.tx, ty1 = 1.f - r.ty;   // exact: == (x0+1)-ix, (y0+1)-iy
-        const float wnw = tx1 * ty1, wne = r.tx * ty1, wsw = tx1 * r.ty, wse = r.tx * r.ty;
-        float4 val;
-        val.x = nw.x * wnw; val.y = nw.y * wnw; val.z = nw.z * wnw; val.w = nw.w * wnw;
-        val.x = fmaf(ne.x, wne, val.x); val.y = fmaf(ne.y, wne, val.y); val.z = fmaf(ne.z, wne, val.z); val.w = fmaf(ne.w, wne, val.w);
-        val.x = fmaf(sw.x, wsw, val.x); val.y = fmaf(sw.y, wsw, val.y); val.z = fmaf(sw.z, wsw, val.z); val.w = fmaf(sw.w, wsw, val.w);
-        val.x = fmaf(se.x, wse, val.x); val.y = fmaf(se.y, wse, val.y); val.z = fmaf(se.z, wse, val.z); val.w = fmaf(se.w, wse, val.w);
-        if (p.cost_type == PGRF_COST_ABS_DIFF) {
-          val.x = fabsf(val.x - ref[j].x); val.y = fabsf(val.y - ref[j].y);
-          val.z = fabsf(val.z - ref[j].z); val.w = fabsf(val.w - ref[j].w);
-        } else if (p.cost_type == PGRF_COST_DOT) {
-          val.x *= ref[j].x; val.y *= ref[j].y; val.z *= ref[j].z; val.w *= ref[j].w;
+    for (int j0 = 0; j0 < NSUB; j0 += JB) {
+      float4 acc[JB];
+#pragma unroll
+      for (int jj = 0; jj < JB; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < (SINGLE ? 1 : p.n_src); ++s) {
+        const float4* vbase = lane_base + (size_t)p.src_views[s] * view_f4;
+        float4 t[JB][4];
+        float tx[JB], ty[JB];
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+          const TapRec r = rec[s * 32 + (j0 + jj) * PPS + pp];
+          const float4* row0 = vbase + r.off4;
+          const float4* row1 = row0 + row_f4;
+          t[jj][0] = ldg4(row0); t[jj][1] = ldg4(row0 + CG); t[jj][2] = ldg4(row1); t[jj][3] = ldg4(row1 + CG);
+          tx[jj] = r.tx; ty[jj] = r.ty;
         }
-        if (use_div) { val.x = val.x / p.divisor; val.y = val.y / p.divisor; val.z = val.z / p.divisor; val.w = val.w / p.divisor; }
-        acc.x += val.x; acc.y += val.y; acc.z += val.z; acc.w += val.w;
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+          const float tx1 = 1.f - tx[jj], ty1 = 1.f - ty[jj];   // exact: == (x0+1)-ix, (y0+1)-iy
+          const float wnw = tx1 * ty1, wne = tx[jj] * ty1, wsw = tx1 * ty[jj], wse = tx[jj] * ty[jj];
+          const float4 nw = t[jj][0], ne = t[jj][1], sw = t[jj][2], se = t[jj][3];
+          const float4 rf = ref[j0 + jj];
+          float4 val;   // ATen's accumulation order: nw, ne, sw, se
+          val.x = nw.x * wnw; val.y = nw.y * wnw; val.z = nw.z * wnw; val.w = nw.w * wnw;
+          val.x = fmaf(ne.x, wne, val.x); val.y = fmaf(ne.y, wne, val.y); val.z = fmaf(ne.z, wne, val.z); val.w = fmaf(ne.w, wne, val.w);
+          val.x = fmaf(sw.x, wsw, val.x); val.y = fmaf(sw.y, wsw, val.y); val.z = fmaf(sw.z, wsw, val.z); val.w = fmaf(sw.w, wsw, val.w);
+          val.x = fmaf(se.x, wse, val.x); val.y = fmaf(se.y, wse, val.y); val.z = fmaf(se.z, wse, val.z); val.w = fmaf(se.w, wse, val.w);
+          if (p.cost_type == PGRF_COST_ABS_DIFF) {
+            val.x = fabsf(val.x - rf.x); val.y = fabsf(val.y - rf.y); val.z = fabsf(val.z - rf.z); val.w = fabsf(val.w - rf.w);
+          } else if (p.cost_type == PGRF_COST_DOT) {
+            val.x *= rf.x; val.y *= rf.y; val.z *= rf.z; val.w *= rf.w;
+          }
+          if (!SINGLE && use_div) { val.x = val.x / p.divisor; val.y = val.y / p.divisor; val.z = val.z / p.divisor; val.w = val.w / p.divisor; }
+          acc[jj].x += val.x; acc[jj].y += val.y; acc[jj].z += val.z; acc[jj].w += val.w;
+        }
       }
-      if (!PLANAR) {
-        if (px < p.W) {
-          float4* dst = reinterpret_cast<float4*>(p.out) +
-                        ((((size_t)b * p.D + d) * p.H + y) * p.W + px) * CG + cg;
-          stcs4(dst, acc);
+#pragma unroll
+      for (int jj = 0; jj < JB; ++jj) {
+        const int pi = (j0 + jj) * PPS + pp;
+        if (!PLANAR) {
+          // lane (pp,cg) of sub-iteration j writes float4 index j*32 + lane of the warp's 32*CG contiguous float4
+          if (x_warp + pi < p.W) stcs4(out_cl + (j0 + jj) * 32, acc[jj]);
+        } else {
+          // tile[c][pixel] with row pitch 33: bank = (4cg + k + 4j + pp) mod 32 -> conflict-free
+          tile[(cg * 4 + 0) * 33 + pi] = acc[jj].x;
+          tile[(cg * 4 + 1) * 33 + pi] = acc[jj].y;
+          tile[(cg * 4 + 2) * 33 + pi] = acc[jj].z;
+          tile[(cg * 4 + 3) * 33 + pi] = acc[jj].w;
         }
-      } else {
-        // tile[c][pixel] with row pitch 33: bank = (4cg + k + 4j + pp) mod 32 -> conflict-free
-        tile[(cg * 4 + 0) * 33 + pi] = acc.x;
-        tile[(cg * 4 + 1) * 33 + pi] = acc.y;
-        tile[(cg * 4 + 2) * 33 + pi] = acc.z;
-        tile[(cg * 4 + 3) * 33 + pi] = acc.w;
       }
     }
     if (PLANAR) {
@@ -288,8 +304,9 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams 
             __stcs(dst + (size_t)g * p.sC, sum / inv_n);
           }
         } else {
+          float* q = dst;
 #pragma unroll 8
-          for (int c = 0; c < C; ++c) __stcs(dst + (size_t)c * p.sC, tile[c * 33 + lane]);
+          for (int c = 0; c < C; ++c) { __stcs(q, tile[c * 33 + lane]); q += p.sC; }
         }
       }
     }
@@ -297,6 +314,9 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams 
   }
   if (bad) atomicOr(p.err, 1);
 }
+
+int g_cv_jb = 0;      // gathers batched per lane (4*JB 128-bit loads in flight); 0 = measured default per layout
+int g_cv_dchunk = 0;  // 0 = heuristic
 
 template <int C>
 static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
@@ -306,13 +326,25 @@ static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
   const bool planar = layout != PGRF_CV_BDHWC;
   size_t smem = (size_t)kCvWarps * p.n_src * 32 * sizeof(TapRec);
   if (planar) smem += (size_t)kCvWarps * C * 33 * sizeof(float);
+  const bool single = p.n_src == 1 && p.divisor == 0.f;
+#define PGRF_CV_LAUNCH(PL, SG, J)                                                                                     \
+  do {                                                                                                                \
+    PGRF_CUDA(cudaFuncSetAttribute(cost_volume_kernel<C, PL, SG, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    cost_volume_kernel<C, PL, SG, J><<<grid, kCvThreads, smem, st>>>(p);                                              \
+  } while (0)
+  const int jb = g_cv_jb ? g_cv_jb : (planar ? 4 : 2);   // B200 sweep, tools/time_cost_volume.py
   if (planar) {
-    PGRF_CUDA(cudaFuncSetAttribute(cost_volume_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cost_volume_kernel<C, true><<<grid, kCvThreads, smem, st>>>(p);
+    if (!single) PGRF_CV_LAUNCH(true, false, 2);
+    else if (jb == 2) PGRF_CV_LAUNCH(true, true, 2);
+    else if (jb == 8) PGRF_CV_LAUNCH(true, true, 8);
+    else PGRF_CV_LAUNCH(true, true, 4);
   } else {
-    PGRF_CUDA(cudaFuncSetAttribute(cost_volume_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cost_volume_kernel<C, false><<<grid, kCvThreads, smem, st>>>(p);
+    if (!single) PGRF_CV_LAUNCH(false, false, 2);
+    else if (jb == 2) PGRF_CV_LAUNCH(false, true, 2);
+    else if (jb == 8) PGRF_CV_LAUNCH(false, true, 8);
+    else PGRF_CV_LAUNCH(false, true, 4);
   }
+#undef PGRF_CV_LAUNCH
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
@@ -321,6 +353,13 @@ static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
 }  // namespace pgrf
 
 using namespace pgrf;
+
+extern "C" int pgrf_debug_set(const char* key, int value) {
+  if (!strcmp(key, "cv_jb")) { g_cv_jb = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_dchunk")) { g_cv_dchunk = value; return PGRF_OK; }
+  set_error("pgrf_debug_set: unknown key %s", key);
+  return PGRF_EINVAL;
+}
 
 extern "C" int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, int W, int C,
                                     const float* depths, const float* depth_volume, int D,
@@ -370,6 +409,7 @@ extern "C" int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, in
   if (n_chunks < 1) n_chunks = 1;
   int d_chunk = (D + n_chunks - 1) / n_chunks;
   if (d_chunk < 4) d_chunk = D < 4 ? D : 4;
+  if (g_cv_dchunk > 0) d_chunk = g_cv_dchunk < D ? g_cv_dchunk : D;
   p.d_chunk = d_chunk;
   PGRF_REQUIRE((D + d_chunk - 1) / d_chunk <= 65535, "cost_volume: too many depth chunks");
 

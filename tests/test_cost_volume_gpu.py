@@ -121,7 +121,7 @@ def test_sampled_coordinates_config1():
     # longitude error scales with 1/sin(phi_src) and both with depth/radius: strict bound where both are benign
     well = (radius > 0.25 * depth) & (v.abs() < 0.8)
     assert float(well.float().mean()) > 0.7
-    assert float(ex[well].max()) < 2e-4 and float(ey[well].max()) < 2e-4      # < 1e-4 rel. of the 512-px extent
+    assert float(ex[well].max()) < 5e-4 and float(ey[well].max()) < 5e-4      # 1e-6 of the 512-px extent (1 ulp = 3e-5 px)
     assert float(ex.mean()) < 3e-5 and float(ey.mean()) < 3e-5
     assert float(ex.max()) < 5e-3 and float(ey.max()) < 5e-3                  # poles / epipole, see config1 test
 
