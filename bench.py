@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays-per-launch", type=int, default=0)
+    ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: tcgen05 tensor-core MLP (rtol 1e-2); fp32: SIMT parity path (rtol 1e-4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -212,6 +214,7 @@ def main():
     rows = (rank * H // world, (rank + 1) * H // world)
     torch.manual_seed(0)
     cfg = cfg_dict()
+    cfg["mlp_dtype"] = args.mlp_dtype
     net = pg.NeuralRayBaseRenderer(cfg).to(dev).eval()           # same seed on every rank -> identical weights
     if args.rays_per_launch:
         net.rays_per_launch = args.rays_per_launch
@@ -275,8 +278,8 @@ def main():
         line = {
             "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "views_per_s": 1e3 / ms_per_step, "rays_per_launch": net.rays_per_launch,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.mlp_dtype == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "mlp": args.mlp_dtype + (" tcgen05 (fp32 accumulate, rtol 1e-2)" if args.mlp_dtype == "bf16" else " SIMT (rtol 1e-4)"), "views_per_s": 1e3 / ms_per_step, "rays_per_launch": net.rays_per_launch,
                        "l2": "256 MiB flush buffer written between timed iterations", "sharding": f"{H // world} rows/rank",
                        "collective": "all_gather(rgb, depth)" if world > 1 else "none"},
             "clocks": sampler.summary(),
@@ -311,6 +314,8 @@ def time_stages(torch, net, que_d, ref_d, flush):
             "colors_nr": torch.empty(1, rn, DN, 3, device=dev), "render_depth": torch.empty(1, rn, device=dev)}
     res = {}
     names = {1: "render_rows_kernel", 2: "render_samples_kernel", 4: "render_rays_kernel"}
+    if net.mlp_dtype == "bf16":
+        names = {3: "render_mlp_bf16_kernel", 4: "render_rays_kernel"}
     net._pass(ctx, coords, depth, 0, False, False, outs, 0, False)      # populate workspaces
     torch.cuda.synchronize()
     for mask, name in names.items():
@@ -331,6 +336,7 @@ def time_stages(torch, net, que_d, ref_d, flush):
     flops = {
         "render_rows_kernel": 2.0 * rows * MAC_ROW_R1,
         "render_samples_kernel": 2.0 * (rows * MAC_ROW_R2 + samples * MAC_SAMPLE_R2),
+        "render_mlp_bf16_kernel": 2.0 * (rows * (MAC_ROW_R1 + MAC_ROW_R2) + samples * MAC_SAMPLE_R2),
         "render_rays_kernel": 2.0 * samples * MAC_SAMPLE_R3,
     }
     peaks = measured_peaks()
@@ -339,8 +345,9 @@ def time_stages(torch, net, que_d, ref_d, flush):
     peak = peaks["bf16_sustained"] or peaks["bf16_tflops"]
     roof = {"kernel": top, "bound": "tensor", "achieved": flops[top] / res[top] / 1e9, "peak": peak, "unit": "TFLOP/s",
             "frac": flops[top] / res[top] / 1e9 / peak, "traffic": None,
-            "note": f"fp32 SIMT parity path measured against the {peaks['src']} bf16 tensor peak (sustained); "
-                    "fp32 FMA peak of B200 is ~74 TFLOP/s"}
+            "note": (f"algorithmic (unpadded) MLP FLOPs of the kernel / its CUDA-event time, against the {peaks['src']} bf16 "
+                     "tensor peak (sustained); " + ("tcgen05 bf16 path" if net.mlp_dtype == "bf16" else
+                                                   "fp32 SIMT parity path, fp32 FMA peak of B200 is ~74 TFLOP/s"))}
     return {"kernels": kernels, "roofline_objects": {"roofline": roof}}
 
 
@@ -357,6 +364,9 @@ def time_e2e(torch, net, que, ref, cfg, steps):
     depth, fine_u = pin(coarse_depth_table(cfg, DN, True)), pin(fine_u_table(DN))
     dev = next(net.parameters()).device
     wc, wf = pin(net._blob(False, dev).cpu()), pin(net._blob(True, dev).cpu())
+    w16c = w16f = None
+    if net.mlp_dtype == "bf16":
+        w16c, w16f = net._blob16(False, dev).cpu().pin_memory(), net._blob16(True, dev).cpu().pin_memory()
     rgb_c = torch.empty(rn, 3).pin_memory()
     rgb = torch.empty(rn, 3).pin_memory()
     dep = torch.empty(rn).pin_memory()
@@ -370,12 +380,16 @@ def time_e2e(torch, net, que, ref, cfg, steps):
     a.img_feats_cl, a.if_h, a.if_w = _lib.ptr(imf), imf.shape[2], imf.shape[3]
     a.ray_feats_cl, a.rf_h, a.rf_w = _lib.ptr(rf), rf.shape[2], rf.shape[3]
     a.weights = _lib.ptr(wc)
+    if w16c is not None:
+        a.mlp_bf16, a.weights16, va.weights16_fine = 1, _lib.ptr(w16c), _lib.ptr(w16f)
     a.pixel_colors = _lib.ptr(rgb_c)
     a.fine_dn, a.fine_u, a.fine_use_all, a.use_disp = DN, _lib.ptr(fine_u), 0, 1
     va.hierarchical, va.weights_fine, va.bias_val_fine = 1, _lib.ptr(wf), 0.05
     va.rays_per_launch = int(net.rays_per_launch)
     va.pixel_colors_fine, va.render_depth_fine = _lib.ptr(rgb), _lib.ptr(dep)
     h2d = sum(t.numel() * 4 for t in (coords, imgs, imf, rf, w2c, rng, c2w, depth, fine_u, wc, wf))
+    if w16c is not None:
+        h2d += w16c.numel() + w16f.numel()
     d2h = sum(t.numel() * 4 for t in (rgb_c, rgb, dep))
     times = []
     for i in range(2 + steps):

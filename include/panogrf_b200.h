@@ -80,6 +80,9 @@ PGRF_API int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, int 
                          int dataset, int cost_type, int layout, int groups,
                          float* out, int* err_flag, void* stream);
 
+/* tcgen05/TMEM self-test: out[128,N] = bf16(A[128,K]) * bf16(W[N,K])^T, fp32 accumulate (device pointers) */
+PGRF_API int pgrf_umma_selftest(const float* A, const float* W, float* out, int K, int N, int variant, void* stream);
+
 /* tuning knobs for experiments ("cv_jb": gathers batched per lane 2|4|8, "cv_dchunk": depths per CTA, 0 = heuristic) */
 PGRF_API int pgrf_debug_set(const char* key, int value);
 
@@ -141,7 +144,9 @@ typedef struct pgrf_render_args {
   float* prob_dbg;             /* (rfn,rn*dn,3) alpha, vis, hit_prob of prj_dict, optional */
   float* prj_dbg;              /* (rfn,rn*dn,6) pts(2), depth, dir(3) of prj_dict, optional */
   float* feat_dbg;             /* (rfn,rn*dn,67) ray_feats(32), rgb(3), img_feats(32) of prj_dict, optional */
-  int stage_mask;              /* 0 = all three kernels; else bit0 rows, bit1 samples, bit2 rays (profiling) */
+  int stage_mask;              /* 0 = all kernels; else bit0 rows, bit1 samples, bit2 rays (profiling; bf16: bit0|bit1 = fused MLP kernel) */
+  int mlp_bf16;                /* 1 = bf16 tcgen05 MLP path (rtol 1e-2), 0 = fp32 SIMT parity path (rtol 1e-4) */
+  const void* weights16;       /* bf16 blob (pgrf_w16_blob_bytes bytes, layout from pgrf_w16_layer_info); needed when mlp_bf16 */
 } pgrf_render_args;
 
 PGRF_API int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream);
@@ -156,6 +161,7 @@ typedef struct pgrf_render_view_args {
   pgrf_render_args pass;
   int hierarchical;            /* cfg["use_hierarchical_sampling"] */
   const float* weights_fine;   /* blob of fine_dist_decoder + fine_agg_net (== pass.weights for cfg["one_mlp"]) */
+  const void* weights16_fine;  /* bf16 blob of the fine nets (when pass.mlp_bf16) */
   float bias_val_fine;
   int rays_per_launch;
   float* fine_depth_ws;        /* (rays_per_launch, fine_total) workspace, used when que_depth_fine == NULL */
@@ -181,6 +187,12 @@ PGRF_API int pgrf_weight_blob_floats(void);
 PGRF_API int pgrf_weight_num_layers(void);
 PGRF_API int pgrf_weight_layer_info(int i, char* name, int name_cap, int* K, int* N, int* Npad, int* has_bias,
                                     int* k_begin, int* w_offset, int* b_offset);
+/* bf16 tensor-core blob: layer i stored as [Kpad/8][Npad][8] bf16 at w_offset_bytes, fp32 bias [Npad] at b_offset_bytes;
+ * kmap[Kpad] / nmap[Npad] give the reference input / output feature of every padded slot (-1 = zero) */
+PGRF_API int pgrf_w16_blob_bytes(void);
+PGRF_API int pgrf_w16_num_layers(void);
+PGRF_API int pgrf_w16_layer_info(int i, char* name, int name_cap, int* Kpad, int* Npad, int* w_offset_bytes, int* b_offset_bytes,
+                                 int* kmap, int* nmap);
 /* layer-norm (weight 16, bias 16) offset, positional table offset ([max_samples][16]) */
 PGRF_API int pgrf_weight_aux_offsets(int* layer_norm_offset, int* posenc_offset, int* max_samples);
 

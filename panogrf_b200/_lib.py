@@ -27,6 +27,7 @@ SIGNATURES = {
     "pgrf_version": (_I, []),
     "pgrf_launch_count": (_c.c_int64, []),
     "pgrf_debug_set": (_I, [_c.c_char_p, _I]),
+    "pgrf_umma_selftest": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "pgrf_cost_volume_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P]),
     "pgrf_cost_volume_host": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _F, _I, _I, _I, _I, _P]),
 }
@@ -106,14 +107,14 @@ class RenderArgs(ctypes.Structure):
         ("pixel_colors", _P), ("render_depth", _P), ("hit_prob", _P), ("density", _P), ("colors", _P),
         ("fine_depth", _P), ("fine_dn", _I), ("fine_u", _P), ("fine_use_all", _I), ("use_disp", _I),
         ("fine_inds", _P), ("prob_dbg", _P), ("prj_dbg", _P), ("feat_dbg", _P),
-        ("stage_mask", _I),
+        ("stage_mask", _I), ("mlp_bf16", _I), ("weights16", _P),
     ]
 
 
 class RenderViewArgs(ctypes.Structure):
     """Mirror of `pgrf_render_view_args`."""
     _fields_ = [
-        ("pass_", RenderArgs), ("hierarchical", _I), ("weights_fine", _P), ("bias_val_fine", _F),
+        ("pass_", RenderArgs), ("hierarchical", _I), ("weights_fine", _P), ("weights16_fine", _P), ("bias_val_fine", _F),
         ("rays_per_launch", _I), ("fine_depth_ws", _P),
         ("pixel_colors_fine", _P), ("render_depth_fine", _P), ("hit_prob_fine", _P), ("density_fine", _P),
         ("colors_fine", _P), ("que_depth_fine", _P),
@@ -132,6 +133,9 @@ SIGNATURES.update({
     "pgrf_weight_num_layers": (_I, []),
     "pgrf_weight_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI, _PI]),
     "pgrf_weight_aux_offsets": (_I, [_PI, _PI, _PI]),
+    "pgrf_w16_blob_bytes": (_I, []),
+    "pgrf_w16_num_layers": (_I, []),
+    "pgrf_w16_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI]),
 })
 
 
@@ -152,3 +156,18 @@ def weight_aux_offsets():
     a, b, c = _I(), _I(), _I()
     check(lib.pgrf_weight_aux_offsets(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "pgrf_weight_aux_offsets")
     return a.value, b.value, c.value
+
+
+def w16_layers():
+    """[(name, Kpad, Npad, w_offset_bytes, b_offset_bytes, kmap, nmap)] of the bf16 tensor-core blob."""
+    lib = load()
+    out = []
+    for i in range(lib.pgrf_w16_num_layers()):
+        name = ctypes.create_string_buffer(128)
+        kp, np_, wo, bo = _I(), _I(), _I(), _I()
+        kmap = (_I * 256)()
+        nmap = (_I * 64)()
+        check(lib.pgrf_w16_layer_info(i, name, 128, ctypes.byref(kp), ctypes.byref(np_), ctypes.byref(wo), ctypes.byref(bo),
+                                      kmap, nmap), "pgrf_w16_layer_info")
+        out.append((name.value.decode(), kp.value, np_.value, wo.value, bo.value, list(kmap[:kp.value]), list(nmap[:np_.value])))
+    return out

@@ -1,0 +1,499 @@
+// bf16 tensor-core variant of the per-(view,sample) and per-sample stages of the render path:
+// rows kernel + samples kernel of render_kernels.cu fused into ONE persistent tcgen05 kernel.
+//
+//   * CTA = 2 independent warpgroups (128 threads each); a warpgroup owns one tile of 128 (view,sample) rows at a
+//     time: thread <-> row for geometry, every epilogue and all element-wise math (state stays in registers);
+//   * every Linear layer is a tcgen05.mma (kind::f16, bf16 operands in shared memory, fp32 accumulators in TMEM,
+//     M = 128 rows, N = 16..64, K = 16..240) issued by one thread of the warpgroup and completed through
+//     tcgen05.commit -> mbarrier; the epilogue reads its row with tcgen05.ld (32x32b) and writes the next layer's
+//     A operand with one conflict-free 128-bit store per 8 features (k-chunk-major layout, umma.cuh);
+//   * all 27 layers' bf16 weights (76 KB) stay resident in shared memory; the F1 inter-kernel tiles of the fp32
+//     path never exist; only the pooled per-sample features (F2: 68 floats / sample) go to HBM for the rays kernel.
+// Reference semantics: same as render_rows_kernel + render_samples_kernel (see render_kernels.cu header).
+// Numerics: operands rounded to bf16, accumulation and all non-GEMM math in fp32 (north star: rtol 1e-2).
+#include <type_traits>
+
+#include "render_device.cuh"
+#include "render_layout16.cuh"
+#include "umma.cuh"
+
+#define W16(L) (std::integral_constant<int, pgrf::w16_offset(L)>::value)
+#define B16(L) (std::integral_constant<int, pgrf::b16_offset(L)>::value)
+
+namespace pgrf {
+
+constexpr int kWG = 2;                      // warpgroups per CTA
+constexpr int kThreads16 = 128 * kWG;
+constexpr int ROWS = 128;                   // rows per tile == operand row pitch
+constexpr int CH = ROWS * 16;               // bytes per k-chunk of an A operand
+
+// ---- per-warpgroup shared memory map (bytes) ----
+constexpr int E_BYTES = 20 * CH;            // pooled blocks of XB (20 chunks); early: RF + HD0..2; late: H64, HV, HV2, XF32, RG, R1
+constexpr int P_BYTES = 10 * CH;            // tail of XB: rgb_feat' (5 chunks) + neuray (4) + zero chunk (1)
+constexpr int S_OFF = E_BYTES + P_BYTES;    // DD (2 chunks), RDH (2 chunks), 8 float vectors
+constexpr int S_BYTES = 4 * CH + 8 * ROWS * 4;
+constexpr int WG_BYTES = S_OFF + S_BYTES;
+// early E
+constexpr int E_RF = 0;                     // 6 chunks: ray_feats (4) + [hit',vis',0..] + zero chunk
+constexpr int E_HD0 = 6 * CH, E_HD1 = 10 * CH, E_HD2 = 14 * CH;   // 4 chunks each
+// late E
+constexpr int E_H64 = 0;                    // 8 chunks
+constexpr int E_HV = 8 * CH, E_HV2 = 12 * CH;                     // 4 chunks each
+constexpr int E_XF32 = 8 * CH;              // fp32 [32][128] = 8 chunks worth (aliases HV, HV2 once they are dead)
+constexpr int E_RG = 0;                     // 6 chunks: x (4) + [vis2, dirdiff, 0] + zero chunk
+constexpr int E_R1 = 16 * CH;               // 2 chunks
+// P
+constexpr int P_IMG = 0;                    // 4 chunks img_feats(+dir feat)
+constexpr int P_RGB = 4 * CH;               // 1 chunk  [rgb(+dir feat) 3, 0 x5]
+constexpr int P_NEU = 5 * CH;               // 4 chunks prob_embedding
+constexpr int P_ZERO = 9 * CH;              // 1 zero chunk
+// S
+constexpr int S_DD = 0, S_RDH = 2 * CH, S_F = 4 * CH;
+enum { SF_PX = 0, SF_PY, SF_W0, SF_VIS2, SF_LOGIT, SF_R, SF_G, SF_B };
+
+constexpr int SM16_W = 0;
+constexpr int SM16_WG = (kW16Bytes + 127) & ~127;
+constexpr int SM16_BAR = SM16_WG + kWG * WG_BYTES;
+constexpr int SM16_BYTES = SM16_BAR + 64;
+
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+// ---- epilogues (thread = row m).  Kept out of line and rolled: the kernel is a long straight-line sequence of
+// stages executed once per tile by only 8 warps, so instruction-cache footprint matters more than unrolling. ----
+// dst chunks [0,nchunks) = bf16( act(acc + bias) )
+static __device__ __noinline__ void epi_act_store(uint32_t taddr, const float* __restrict__ bias, unsigned char* dst, int m,
+                                                  int nchunks, int act) {
+  // two chunks (16 accumulator columns) per TMEM round trip; nchunks is even for every caller
+#pragma unroll 1
+  for (int c = 0; c < nchunks; c += 2) {
+    float v[16];
+    umma::ld16(taddr + 8 * c, v);
+    const float4* b4 = reinterpret_cast<const float4*>(bias + 8 * c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = b4[i];
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+    if (act == ACT_ELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = elu1(v[i]);
+    } else if (act == ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    umma::store_chunk(dst, ROWS, c, m, v);
+    umma::store_chunk(dst, ROWS, c + 1, m, v + 8);
+  }
+}
+// first accumulator column (+bias) of a padded N=16 output layer
+__device__ __forceinline__ float epi_scalar(uint32_t taddr, const float* __restrict__ bias) {
+  float a, b;
+  umma::ld2(taddr, a, b);
+  return a + bias[0];
+}
+__device__ __forceinline__ void zero_chunk(unsigned char* dst, int chunk, int m) {
+  *reinterpret_cast<uint4*>(dst + ((size_t)chunk * ROWS + m) * 16) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// one MMA stage: publish the operand writes, sync the warpgroup, let one thread issue, wait for completion
+#define STAGE_BEGIN()                                                       \
+  umma::fence_smem_to_async(); umma::fence_before_sync(); wg_sync(wg);      \
+  if (m == 0) { umma::fence_after_sync();
+#define STAGE_END()                                                         \
+    umma::commit(bar); }                                                    \
+  mbar_wait(bar, phase); phase ^= 1; umma::fence_after_sync();
+
+struct Render16Params {
+  pgrf_render_args a;
+  int V, T, M;
+  long long total;
+  int n_tiles;
+};
+
+__global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Render16Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  const pgrf_render_args& a = p.a;
+  const int tid = threadIdx.x;
+  const int wg = tid >> 7;            // warpgroup
+  const int m = tid & 127;            // row inside the warpgroup's tile
+  const int wq = (tid >> 5) & 3;      // warp inside the warpgroup -> TMEM lane quadrant
+  unsigned char* Wb = smem + SM16_W;
+  const float* Bias = reinterpret_cast<const float*>(Wb + kW16WeightBytes);
+  unsigned char* E = smem + SM16_WG + wg * WG_BYTES;
+  unsigned char* P = E + E_BYTES;
+  unsigned char* S = E + S_OFF;
+  float* SF = reinterpret_cast<float*>(S + S_F);
+  float* XF = reinterpret_cast<float*>(P);        // x in fp32 [32][128]; P is dead once base_fc.0 has consumed it
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM16_BAR) + wg;
+
+  // one-time setup: weights -> smem, TMEM allocation (512 columns: 256 per warpgroup), mbarriers
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.weights16);
+    uint4* dst = reinterpret_cast<uint4*>(Wb);
+    for (int i = tid; i < kW16Bytes / 16; i += kThreads16) dst[i] = __ldg(src + i);
+  }
+  if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
+  if (m == 0) mbar_init(bar, 1);
+  umma::fence_smem_to_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = tmem_base_s + wg * 256;                 // this warpgroup's TMEM columns
+  const uint32_t tq = tb + ((uint32_t)(wq * 32) << 16);       // + this warp's lane quadrant
+  uint32_t phase = 0;
+
+  const int T = p.T, V = p.V, M = p.M;
+  const int v = min(m / T, V - 1), t = m % T;
+  const float wgt = 1.f / ((float)V + 1e-8f);
+
+#pragma unroll 1
+  for (int tile = blockIdx.x * kWG + wg; tile < p.n_tiles; tile += gridDim.x * kWG) {
+    long long g = (long long)tile * T + t;
+    const bool row_valid = (m < M) && (g < p.total);
+    if (g >= p.total) g = p.total - 1;
+    const int ray = (int)(g / a.dn), s = (int)(g % a.dn);
+
+    // ------------------------------------------------------------ geometry (thread = row)
+    const RowGeom rg = row_geometry(a, v, g);
+    SF[SF_PX * ROWS + m] = rg.px;
+    SF[SF_PY * ROWS + m] = rg.py;
+    {
+      float dd8[8] = {rg.dirdiff[0], rg.dirdiff[1], rg.dirdiff[2], rg.dirdiff[3], 0.f, 0.f, 0.f, 0.f};
+      umma::store_chunk(S + S_DD, ROWS, 0, m, dd8);
+      zero_chunk(S + S_DD, 1, m);
+    }
+    // own-row colour taps (fp32, kept in registers for the final blend)
+    float rgb_in[3];
+    {
+      const Footprint f = border_footprint(rg.px, rg.py, a.img_h, a.img_w, a.img_h, a.img_w);
+      const float4 c = tap4(reinterpret_cast<const float4*>(a.imgs_cl) + (size_t)v * a.img_h * a.img_w + f.off, f, 1, a.img_w);
+      rgb_in[0] = c.x; rgb_in[1] = c.y; rgb_in[2] = c.z;
+    }
+    // sampling interval of this sample along its ray (depth2inv_dists) and the view's normalised depth
+    float d_prev, d_s, dv;
+    {
+      const float* dp = a.depth + (size_t)ray * a.depth_ray_stride;
+      const float i_s = inv_norm(__ldg(dp + s), a.que_near, a.que_far);
+      d_s = (s + 1 < a.dn) ? inv_norm(__ldg(dp + s + 1), a.que_near, a.que_far) - i_s : 1e6f;
+      d_prev = d_s;
+      if (s > 0) d_prev = i_s - inv_norm(__ldg(dp + s - 1), a.que_near, a.que_far);
+      const float rnear = __ldg(a.ref_depth_range + 2 * v), rfar = __ldg(a.ref_depth_range + 2 * v + 1);
+      dv = inv_norm(fmaxf(rg.pdepth, 1e-5f), rnear, rfar);
+    }
+    wg_sync(wg);
+
+    // ------------------------------------------------------------ cooperative gathers (lane = (row, float4 group))
+#pragma unroll 1
+    for (int it = m; it < ROWS * 8; it += 128) {
+      const int r = it >> 3, cg = it & 7;
+      const int rv = min(r / T, V - 1);
+      const float px = SF[SF_PX * ROWS + r], py = SF[SF_PY * ROWS + r];
+      const Footprint f1 = border_footprint(px, py, a.img_h, a.img_w, a.rf_h, a.rf_w);
+      const float4 rf = tap4(reinterpret_cast<const float4*>(a.ray_feats_cl) + ((size_t)rv * a.rf_h * a.rf_w + f1.off) * 8 + cg,
+                             f1, 8, a.rf_w * 8);
+      const Footprint f2 = border_footprint(px, py, a.img_h, a.img_w, a.if_h, a.if_w);
+      const float4 imf = tap4(reinterpret_cast<const float4*>(a.img_feats_cl) + ((size_t)rv * a.if_h * a.if_w + f2.off) * 8 + cg,
+                              f2, 8, a.if_w * 8);
+      // 4 channels = half a chunk: chunk cg/2, 8-byte half cg%2
+      uint2 q;
+      q.x = umma::pack2(rf.x, rf.y); q.y = umma::pack2(rf.z, rf.w);
+      *reinterpret_cast<uint2*>(E + E_RF + ((size_t)(cg >> 1) * ROWS + r) * 16 + (cg & 1) * 8) = q;
+      q.x = umma::pack2(imf.x, imf.y); q.y = umma::pack2(imf.z, imf.w);
+      *reinterpret_cast<uint2*>(P + P_IMG + ((size_t)(cg >> 1) * ROWS + r) * 16 + (cg & 1) * 8) = q;
+    }
+    zero_chunk(E + E_RF, 4, m);
+    zero_chunk(E + E_RF, 5, m);
+    zero_chunk(P, 9, m);
+
+    // ------------------------------------------------------------ stage 1: decoder layer 0 (x3) + ray_dir_fc.0
+    STAGE_BEGIN()
+      umma::gemm_issue(tb + 0, E + E_RF, ROWS, Wb + W16(M_MEAN0), 32, 32, 32);
+      umma::gemm_issue(tb + 32, E + E_RF, ROWS, Wb + W16(M_VAR0), 32, 32, 32);
+      umma::gemm_issue(tb + 64, E + E_RF, ROWS, Wb + W16(M_AW0), 32, 32, 32);
+      umma::gemm_issue(tb + 128, S + S_DD, ROWS, Wb + W16(M_RD0), 16, 16, 16);
+    STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_MEAN0), E + E_HD0, m, 4, ACT_ELU);
+    epi_act_store(tq + 32, Bias + B16(M_VAR0), E + E_HD1, m, 4, ACT_ELU);
+    epi_act_store(tq + 64, Bias + B16(M_AW0), E + E_HD2, m, 4, ACT_ELU);
+    epi_act_store(tq + 128, Bias + B16(M_RD0), S + S_RDH, m, 2, ACT_ELU);
+
+    // ------------------------------------------------------------ stage 2: decoder layer 1 (x3) + ray_dir_fc.2
+    STAGE_BEGIN()
+      umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_MEAN1), 32, 32, 32);
+      umma::gemm_issue(tb + 32, E + E_HD1, ROWS, Wb + W16(M_VAR1), 32, 32, 32);
+      umma::gemm_issue(tb + 64, E + E_HD2, ROWS, Wb + W16(M_AW1), 32, 32, 32);
+      umma::gemm_issue(tb + 128, S + S_RDH, ROWS, Wb + W16(M_RD1), 48, 48, 16);
+    STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_MEAN1), E + E_HD0, m, 4, ACT_ELU);   // in place: the MMAs reading HD* are complete
+    epi_act_store(tq + 32, Bias + B16(M_VAR1), E + E_HD1, m, 4, ACT_ELU);
+    epi_act_store(tq + 64, Bias + B16(M_AW1), E + E_HD2, m, 4, ACT_ELU);
+    // direction feature (f' order: img_feats 0..31, rgb 32..34): rgb_feat = [img_feats, rgb] + ELU(ray_dir_fc)
+#pragma unroll 1
+    for (int c = 0; c < 5; ++c) {
+      float df[8], x[8];
+      umma::ld8(tq + 128 + 8 * c, df);
+      if (c < 4) {
+        umma::load_chunk(P + P_IMG, ROWS, c, m, x);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = i < 3 ? rgb_in[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = elu1(df[i] + Bias[B16(M_RD1) + 8 * c + i]);
+        x[i] = (c < 4 || i < 3) ? x[i] + d : 0.f;
+      }
+      umma::store_chunk(P, ROWS, c, m, x);     // P_IMG chunks 0..3, P_RGB = chunk 4
+    }
+
+    // ------------------------------------------------------------ stage 3: decoder output layers
+    STAGE_BEGIN()
+      umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_MEAN2), 16, 16, 32);
+      umma::gemm_issue(tb + 16, E + E_HD1, ROWS, Wb + W16(M_VAR2), 16, 16, 32);
+      umma::gemm_issue(tb + 32, E + E_HD2, ROWS, Wb + W16(M_AW2), 16, 16, 32);
+    STAGE_END()
+    float mean[2], var[2], aw, visd = 1.f;
+    {
+      float o0, o1;
+      umma::ld2(tq + 0, o0, o1);
+      mean[0] = softplusf(o0 + Bias[B16(M_MEAN2)]); mean[1] = softplusf(o1 + Bias[B16(M_MEAN2) + 1]);
+      umma::ld2(tq + 16, o0, o1);
+      var[0] = softplusf(o0 + Bias[B16(M_VAR2)]) + a.bias_val; var[1] = softplusf(o1 + Bias[B16(M_VAR2) + 1]) + a.bias_val;
+      aw = sigmoidf(epi_scalar(tq + 32, Bias + B16(M_AW2)));
+    }
+    if (a.use_vis) {   // 4th decoder, three more sequential stages through HD0
+      STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_RF, ROWS, Wb + W16(M_VIS0), 32, 32, 32); STAGE_END()
+      epi_act_store(tq + 0, Bias + B16(M_VIS0), E + E_HD0, m, 4, ACT_ELU);
+      STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_VIS1), 32, 32, 32); STAGE_END()
+      epi_act_store(tq + 0, Bias + B16(M_VIS1), E + E_HD0, m, 4, ACT_ELU);
+      STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_VIS2), 16, 16, 32); STAGE_END()
+      visd = sigmoidf(epi_scalar(tq + 0, Bias + B16(M_VIS2)));
+    }
+
+    // ------------------------------------------------------------ logistic-mixture probabilities (dist_decoder.compute_prob)
+    {
+      const float nearp = dv - d_prev / 2.f, farp = dv + d_s / 2.f;
+      const float mix[2] = {aw, 1.f - aw};
+      float visibility = 0.f, hp = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float cdf0 = 0.5f + 0.5f * tanhf((nearp - mean[j]) * var[j]);
+        float cdf1 = 0.5f + 0.5f * tanhf((farp - mean[j]) * var[j]);
+        if (a.use_vis) { cdf0 *= visd; cdf1 *= visd; }
+        visibility += (1.f - cdf0) * mix[j];
+        hp += (cdf1 - cdf0) * mix[j];
+      }
+      if (a.prob_dbg && row_valid) {
+        float* d = a.prob_dbg + ((size_t)v * p.total + g) * 3;
+        d[0] = logf(hp / (visibility - hp + 1e-5f) + 1e-5f); d[1] = visibility; d[2] = hp;
+      }
+      float hv8[8] = {(hp - 0.5f) * 2.f, (visibility - 0.5f) * 2.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      umma::store_chunk(E + E_RF, ROWS, 4, m, hv8);
+    }
+
+    // ------------------------------------------------------------ stage 4/5: prob_embed 34 -> 32 (ReLU) -> 32
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_RF, ROWS, Wb + W16(M_PE0), 32, 32, 48); STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_PE0), E + E_HD0, m, 4, ACT_RELU);
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_PE1), 32, 32, 32); STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_PE1), P + P_NEU, m, 4, ACT_NONE);
+
+    // ------------------------------------------------------------ stage 6/7: neuray_fc 32 -> 8 -> 1 (sigmoid)
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, P + P_NEU, ROWS, Wb + W16(M_NF0), 16, 16, 32); STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_NF0), E + E_HD1, m, 2, ACT_ELU);   // padded outputs 8..15: ELU(0 + 0) = 0
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD1, ROWS, Wb + W16(M_NF1), 16, 16, 16); STAGE_END()
+    SF[SF_W0 * ROWS + m] = sigmoidf(epi_scalar(tq + 0, Bias + B16(M_NF1)));
+    umma::fence_before_sync();
+    wg_sync(wg);
+
+    // ------------------------------------------------------------ view pooling #1 (fused_mean_variance x2) -> XB blocks
+    {
+      float w0n[4];
+#pragma unroll
+      for (int vv = 0; vv < 4; ++vv) w0n[vv] = (vv < V) ? SF[SF_W0 * ROWS + vv * T + t] * wgt : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 5; ++c) {
+        float x[4][8];
+#pragma unroll
+        for (int vv = 0; vv < 4; ++vv)
+          if (vv < V) umma::load_chunk(P, ROWS, c, vv * T + t, x[vv]);
+        float m0[8], v0[8], m1[8], v1[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int vv = 0; vv < 4; ++vv)
+            if (vv < V) { a0 += x[vv][i] * w0n[vv]; a1 += x[vv][i] * wgt; }
+          float b0 = 0.f, b1 = 0.f;
+#pragma unroll
+          for (int vv = 0; vv < 4; ++vv)
+            if (vv < V) {
+              b0 += w0n[vv] * ((x[vv][i] - a0) * (x[vv][i] - a0));
+              b1 += wgt * ((x[vv][i] - a1) * (x[vv][i] - a1));
+            }
+          m0[i] = a0; v0[i] = b0; m1[i] = a1; v1[i] = b1;
+        }
+        umma::store_chunk(E, ROWS, 0 + c, m, m0);
+        umma::store_chunk(E, ROWS, 5 + c, m, v0);
+        umma::store_chunk(E, ROWS, 10 + c, m, m1);
+        umma::store_chunk(E, ROWS, 15 + c, m, v1);
+      }
+    }
+
+    // ------------------------------------------------------------ stage 8: base_fc.0 (K = 240: pooled | rgb_feat | neuray)
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E, ROWS, Wb + W16(M_BASE0), 64, 64, 240); STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_BASE0), E + E_H64, m, 8, ACT_ELU);
+
+    // ------------------------------------------------------------ stage 9: base_fc.2 -> x (fp32, column m of XF)
+    STAGE_BEGIN() umma::gemm_issue(tb + 64, E + E_H64, ROWS, Wb + W16(M_BASE1), 32, 32, 64); STAGE_END()
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float r[8], sx[8];
+      umma::ld8(tq + 64 + 8 * c, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xv = elu1(r[i] + Bias[B16(M_BASE1) + 8 * c + i]);
+        XF[(8 * c + i) * ROWS + m] = xv;
+        sx[i] = xv * wgt;
+      }
+      umma::store_chunk(E + E_HV, ROWS, c, m, sx);
+    }
+    // ------------------------------------------------------------ stage 10/11: vis_fc(x * weight) 32 -> 32 -> 33
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV, ROWS, Wb + W16(M_VFC0), 32, 32, 32); STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_VFC0), E + E_HV2, m, 4, ACT_ELU);
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV2, ROWS, Wb + W16(M_VFC1), 48, 48, 32); STAGE_END()
+    {
+      const float vis1 = sigmoidf(elu1(epi_scalar(tq + 32, Bias + B16(M_VFC1) + 32)));   // vis = sigmoid(vis) * mask
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float r[8], sx[8];
+        umma::ld8(tq + 8 * c, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xv = XF[(8 * c + i) * ROWS + m] + elu1(r[i] + Bias[B16(M_VFC1) + 8 * c + i]);   // x = x + x_res
+          XF[(8 * c + i) * ROWS + m] = xv;
+          sx[i] = xv * vis1;
+        }
+        umma::store_chunk(E + E_HV, ROWS, c, m, sx);
+      }
+    }
+    // ------------------------------------------------------------ stage 12/13: vis_fc2(x * vis) 32 -> 32 -> 1
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV, ROWS, Wb + W16(M_V2_0), 32, 32, 32); STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_V2_0), E + E_HV2, m, 4, ACT_ELU);
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV2, ROWS, Wb + W16(M_V2_1), 16, 16, 32); STAGE_END()
+    {
+      const float vis2 = sigmoidf(epi_scalar(tq + 0, Bias + B16(M_V2_1)));
+      SF[SF_VIS2 * ROWS + m] = vis2;
+      // rgb_fc input [x(32), vis, ray_diff(4)] -> K = 48
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float xx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xx[i] = XF[(8 * c + i) * ROWS + m];
+        umma::store_chunk(E + E_RG, ROWS, c, m, xx);
+      }
+      float tail[8] = {vis2, rg.dirdiff[0], rg.dirdiff[1], rg.dirdiff[2], rg.dirdiff[3], 0.f, 0.f, 0.f};
+      umma::store_chunk(E + E_RG, ROWS, 4, m, tail);
+      zero_chunk(E + E_RG, 5, m);
+    }
+    // ------------------------------------------------------------ stage 14: rgb_fc.0, overlapped with view pooling #2
+    umma::fence_smem_to_async(); umma::fence_before_sync(); wg_sync(wg);
+    if (m == 0) { umma::fence_after_sync(); umma::gemm_issue(tb + 0, E + E_RG, ROWS, Wb + W16(M_RGB0), 16, 16, 48); umma::commit(bar); }
+    if (m < T) {   // weights = vis / (sum + 1e-8), mean / var of x over views, mean of weights -> F2
+      const long long gs = (long long)tile * T + m;
+      float* f2 = a.f2 + (size_t)tile * kF2 * T + m;
+      float sum = 0.f;
+#pragma unroll
+      for (int vv = 0; vv < 4; ++vv) if (vv < V) sum += SF[SF_VIS2 * ROWS + vv * T + m];
+      float wv[4], ws = 0.f;
+#pragma unroll
+      for (int vv = 0; vv < 4; ++vv) { wv[vv] = (vv < V) ? SF[SF_VIS2 * ROWS + vv * T + m] / (sum + 1e-8f) : 0.f; ws += wv[vv]; }
+      if (gs < p.total) {
+#pragma unroll 2
+        for (int c = 0; c < 32; ++c) {
+          float mean_c = 0.f;
+#pragma unroll
+          for (int vv = 0; vv < 4; ++vv) if (vv < V) mean_c += XF[c * ROWS + vv * T + m] * wv[vv];
+          float var_c = 0.f;
+#pragma unroll
+          for (int vv = 0; vv < 4; ++vv)
+            if (vv < V) { const float d = XF[c * ROWS + vv * T + m] - mean_c; var_c += wv[vv] * (d * d); }
+          f2[(size_t)c * T] = mean_c;
+          f2[(size_t)(32 + c) * T] = var_c;
+        }
+        f2[(size_t)64 * T] = ws / (float)V;
+      }
+    }
+    mbar_wait(bar, phase); phase ^= 1; umma::fence_after_sync();
+    epi_act_store(tq + 0, Bias + B16(M_RGB0), E + E_R1, m, 2, ACT_ELU);
+    // ------------------------------------------------------------ stage 15/16: rgb_fc.2, rgb_fc.4
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_R1, ROWS, Wb + W16(M_RGB1), 16, 16, 16); STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_RGB1), S + S_DD, m, 2, ACT_ELU);       // DD is dead since stage 1
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, S + S_DD, ROWS, Wb + W16(M_RGB2), 16, 16, 16); STAGE_END()
+    SF[SF_LOGIT * ROWS + m] = epi_scalar(tq + 0, Bias + B16(M_RGB2));
+    SF[SF_R * ROWS + m] = rgb_in[0]; SF[SF_G * ROWS + m] = rgb_in[1]; SF[SF_B * ROWS + m] = rgb_in[2];
+    umma::fence_before_sync();
+    wg_sync(wg);
+    // ------------------------------------------------------------ softmax over views, blend the raw colours -> F2
+    if (m < T) {
+      const long long gs = (long long)tile * T + m;
+      if (gs < p.total) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int vv = 0; vv < 4; ++vv) if (vv < V) mx = fmaxf(mx, SF[SF_LOGIT * ROWS + vv * T + m]);
+        float den = 0.f, r = 0.f, gg = 0.f, b = 0.f;
+#pragma unroll
+        for (int vv = 0; vv < 4; ++vv)
+          if (vv < V) {
+            const float e = expf(SF[SF_LOGIT * ROWS + vv * T + m] - mx);
+            den += e;
+            r += SF[SF_R * ROWS + vv * T + m] * e; gg += SF[SF_G * ROWS + vv * T + m] * e; b += SF[SF_B * ROWS + vv * T + m] * e;
+          }
+        float* f2 = a.f2 + (size_t)tile * kF2 * T + m;
+        f2[(size_t)(F2_RGB + 0) * T] = r / den; f2[(size_t)(F2_RGB + 1) * T] = gg / den; f2[(size_t)(F2_RGB + 2) * T] = b / den;
+      }
+    }
+    wg_sync(wg);   // SF / E / P are rewritten by the next tile
+  }
+
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tmem_base_s, 512);
+}
+
+}  // namespace pgrf
+
+using namespace pgrf;
+
+extern "C" int pgrf_w16_blob_bytes(void) { return kW16Bytes; }
+extern "C" int pgrf_w16_num_layers(void) { return kNumLayers16; }
+extern "C" int pgrf_w16_layer_info(int i, char* name, int name_cap, int* Kpad, int* Npad, int* w_offset_bytes, int* b_offset_bytes,
+                                   int* kmap, int* nmap) {
+  PGRF_REQUIRE(i >= 0 && i < kNumLayers16, "w16 layer index %d out of range", i);
+  snprintf(name, name_cap, "%s", kLayers16[i].name);
+  *Kpad = kLayers16[i].Kpad; *Npad = kLayers16[i].Npad;
+  *w_offset_bytes = w16_offset(i);
+  *b_offset_bytes = kW16WeightBytes + 4 * b16_offset(i);
+  for (int k = 0; k < kLayers16[i].Kpad; ++k) kmap[k] = w16_kmap(i, k);
+  for (int n = 0; n < kLayers16[i].Npad; ++n) nmap[n] = w16_nmap(i, n);
+  return PGRF_OK;
+}
+
+namespace pgrf {
+int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long total, int n_tiles, int sms, cudaStream_t st) {
+  PGRF_REQUIRE(a.weights16 != nullptr, "render: bf16 path needs weights16");
+  PGRF_REQUIRE(((uintptr_t)a.weights16 & 15) == 0, "render: weights16 must be 16-byte aligned");
+  Render16Params p;
+  p.a = a; p.V = V; p.T = T; p.M = V * T; p.total = total; p.n_tiles = n_tiles;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PGRF_CUDA(cudaFuncSetAttribute(render_mlp_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM16_BYTES));
+    attr_done = true;
+  }
+  const int grid = min((n_tiles + kWG - 1) / kWG, sms);
+  render_mlp_bf16_kernel<<<grid, kThreads16, SM16_BYTES, st>>>(p);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+}  // namespace pgrf

@@ -58,67 +58,6 @@ constexpr int R1_SC = R1_OUT + kF1 * LD;       // per-row scalars, 10 x [LD]
 constexpr int R1_FLOATS = R1_SC + 10 * LD;
 enum { SC_PX = 0, SC_PY, SC_PDEPTH, SC_MEAN0, SC_MEAN1, SC_VAR0, SC_VAR1, SC_AW, SC_VIS, SC_SPARE };
 
-__device__ __forceinline__ float4 tap4(const float4* __restrict__ base, const Footprint& f, int stride_x, int stride_y) {
-  // ATen order: nw, ne, sw, se
-  const float4 nw = ldg4(base);
-  const float4 ne = ldg4(base + f.dx * stride_x);
-  const float4 sw = ldg4(base + f.dy * stride_y);
-  const float4 se = ldg4(base + f.dy * stride_y + f.dx * stride_x);
-  const float tx1 = 1.f - f.tx, ty1 = 1.f - f.ty;
-  const float wnw = tx1 * ty1, wne = f.tx * ty1, wsw = tx1 * f.ty, wse = f.tx * f.ty;
-  float4 o;
-  o.x = nw.x * wnw; o.y = nw.y * wnw; o.z = nw.z * wnw; o.w = nw.w * wnw;
-  o.x = fmaf(ne.x, wne, o.x); o.y = fmaf(ne.y, wne, o.y); o.z = fmaf(ne.z, wne, o.z); o.w = fmaf(ne.w, wne, o.w);
-  o.x = fmaf(sw.x, wsw, o.x); o.y = fmaf(sw.y, wsw, o.y); o.z = fmaf(sw.z, wsw, o.z); o.w = fmaf(sw.w, wsw, o.w);
-  o.x = fmaf(se.x, wse, o.x); o.y = fmaf(se.y, wse, o.y); o.z = fmaf(se.z, wse, o.z); o.w = fmaf(se.w, wse, o.w);
-  return o;
-}
-
-// Geometry of one (view, sample) row. Outputs projected pixel/depth, projection direction and the
-// (dir - que_dir, dot) feature of aggregate_net.get_dir_diff.
-struct RowGeom {
-  float px, py, pdepth;
-  float dir[3];
-  float dirdiff[4];
-};
-__device__ __forceinline__ RowGeom row_geometry(const pgrf_render_args& a, int v, long long g) {
-  const int ray = (int)(g / a.dn), s = (int)(g % a.dn);
-  const float cx = __ldg(a.coords + 2 * (size_t)ray), cy = __ldg(a.coords + 2 * (size_t)ray + 1);
-  const float depth = __ldg(a.depth + (size_t)ray * a.depth_ray_stride + s);
-  float dx, dy, dz;
-  // `.long()` truncation of the pixel coordinate (render_ops.py:96-97)
-  equi_unit_dir(a.dataset, (float)(long long)cx, (float)(long long)cy, a.H, a.W, dx, dy, dz);
-  const float* c = a.que_c2w;  // (3,4) row-major
-  const float rdx = c[0] * dx + c[1] * dy + c[2] * dz;
-  const float rdy = c[4] * dx + c[5] * dy + c[6] * dz;
-  const float rdz = c[8] * dx + c[9] * dy + c[10] * dz;
-  const float p0 = c[3] + rdx * depth, p1 = c[7] + rdy * depth, p2 = c[11] + rdz * depth;
-  const float rn = sqrtf(rdx * rdx + rdy * rdy + rdz * rdz);
-  const float q0 = -rdx / rn, q1 = -rdy / rn, q2 = -rdz / rn;   // que_dir
-  const float* w = a.ref_w2c + 12 * v;
-  const float pc0 = w[0] * p0 + w[1] * p1 + w[2] * p2 + w[3];
-  const float pc1 = w[4] * p0 + w[5] * p1 + w[6] * p2 + w[7];
-  const float pc2 = w[8] * p0 + w[9] * p1 + w[10] * p2 + w[11];
-  RowGeom r;
-  cam_to_equi(a.dataset, pc0, pc1, pc2, a.H, a.W, r.pdepth, r.px, r.py);
-  // camera centre -R^T t (render_ops.py:204), direction from the point to the source camera
-  const float cam0 = -(w[0] * w[3] + w[4] * w[7] + w[8] * w[11]);
-  const float cam1 = -(w[1] * w[3] + w[5] * w[7] + w[9] * w[11]);
-  const float cam2 = -(w[2] * w[3] + w[6] * w[7] + w[10] * w[11]);
-  const float e0 = p0 - cam0, e1 = p1 - cam1, e2 = p2 - cam2;
-  const float en = fmaxf(sqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e-5f);
-  r.dir[0] = -e0 / en; r.dir[1] = -e1 / en; r.dir[2] = -e2 / en;
-  r.dirdiff[0] = r.dir[0] - q0; r.dirdiff[1] = r.dir[1] - q1; r.dirdiff[2] = r.dir[2] - q2;
-  r.dirdiff[3] = r.dir[0] * q0 + r.dir[1] * q1 + r.dir[2] * q2;
-  return r;
-}
-
-// normalised inverse depth of dist_decoder.get_near_far_points / render_ops.depth2inv_dists
-__device__ __forceinline__ float inv_norm(float depth, float near, float far) {
-  const float nn = -1.f / near, ff = -1.f / far;
-  return (-1.f / depth - nn) / (ff - nn);
-}
-
 // One decoder of MixtureLogisticsDistDecoder (dist_decoder.py:64-97): D = 0 mean, 1 var, 2 aw, 3 vis.
 template <int D>
 __device__ __forceinline__ void decoder_stage(const float* W, const float* IN, float* H1, float* H2, float* SC, int Mp,
@@ -719,6 +658,9 @@ static int num_sms() {
 
 }  // namespace pgrf
 
+namespace pgrf {
+int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long total, int n_tiles, int sms, cudaStream_t st);
+}
 using namespace pgrf;
 
 extern "C" int pgrf_weight_blob_floats(void) { return kBlobFloats; }
@@ -757,7 +699,7 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
   PGRF_REQUIRE(a.H > 1 && a.W > 1 && a.img_h > 1 && a.img_w > 1 && a.if_h > 0 && a.if_w > 0 && a.rf_h > 0 && a.rf_w > 0,
                "render: bad map sizes");
   PGRF_REQUIRE(a.coords && a.depth && a.que_c2w && a.ref_w2c && a.ref_depth_range && a.imgs_cl && a.img_feats_cl &&
-                   a.ray_feats_cl && a.weights && a.f1 && a.f2 && a.pixel_colors,
+                   a.ray_feats_cl && a.weights && (a.f1 || a.mlp_bf16) && a.f2 && a.pixel_colors,
                "render: null pointer argument");
   PGRF_REQUIRE(a.depth_ray_stride == 0 || a.depth_ray_stride == a.dn, "render: depth_ray_stride must be 0 or dn");
   PGRF_REQUIRE(!a.fine_depth || (a.fine_u && a.fine_dn >= 1 && a.fine_dn + (a.fine_use_all ? a.dn : 0) <= 2 * kMaxSamplesPerRay - 2),
@@ -785,6 +727,15 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
     attr_done = true;
   }
   const int mask = a.stage_mask ? a.stage_mask : 7;
+  if (a.mlp_bf16) {
+    if (mask & 3) {
+      const int rc = launch_render_mlp_bf16(a, p.V, p.T, p.total, p.n_tiles, sms, st);
+      if (rc != PGRF_OK) return rc;
+    }
+    if (mask & 4) { render_rays_kernel<<<min(p.n_tiles3, sms), kThreads, s3, st>>>(p); count_launch(); }
+    PGRF_CUDA(cudaGetLastError());
+    return PGRF_OK;
+  }
   if (mask & 1) { render_rows_kernel<<<min(p.n_tiles, sms), kThreads, s1, st>>>(p); count_launch(); }
   if (mask & 2) { render_samples_kernel<<<min(p.n_tiles, sms), kThreads, s2, st>>>(p); count_launch(); }
   if (mask & 4) { render_rays_kernel<<<min(p.n_tiles3, sms), kThreads, s3, st>>>(p); count_launch(); }

@@ -50,6 +50,7 @@ extern "C" int pgrf_render_view_fwd(const pgrf_render_view_args* va, void* strea
   const int dn = base.dn;
   const int fine_total = va->hierarchical ? base.fine_dn + (base.fine_use_all ? dn : 0) : 0;
   if (va->hierarchical) {
+    PGRF_REQUIRE(!base.mlp_bf16 || va->weights16_fine, "render_view: bf16 fine pass needs weights16_fine");
     PGRF_REQUIRE(va->weights_fine && va->pixel_colors_fine && base.fine_u, "render_view: fine pass needs weights_fine, "
                  "pixel_colors_fine and fine_u");
     PGRF_REQUIRE(va->que_depth_fine || va->fine_depth_ws, "render_view: need que_depth_fine or fine_depth_ws");
@@ -77,6 +78,7 @@ extern "C" int pgrf_render_view_fwd(const pgrf_render_view_args* va, void* strea
     f.depth = fine_depth;
     f.depth_ray_stride = fine_total;
     f.weights = va->weights_fine;
+    f.weights16 = va->weights16_fine;
     f.bias_val = va->bias_val_fine;
     f.fine_depth = nullptr;
     f.pixel_colors = va->pixel_colors_fine + 3 * (size_t)r0;
@@ -113,6 +115,14 @@ extern "C" int pgrf_render_view_host(const pgrf_render_view_args* hv) {
   }
   cudaStream_t st;
   PGRF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  {  // keep freed blocks in the stream-ordered pool between calls (default threshold 0 returns them to the OS at every sync)
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   std::vector<void*> allocs;
   auto dalloc = [&](size_t bytes) -> void* {
     void* p = nullptr;
@@ -137,6 +147,7 @@ extern "C" int pgrf_render_view_host(const pgrf_render_view_args* hv) {
     p.ref_w2c = up(h.ref_w2c, (size_t)rfn * 12 * 4);
     p.ref_depth_range = up(h.ref_depth_range, (size_t)rfn * 2 * 4);
     p.weights = up(h.weights, (size_t)blob * 4);
+    if (h.mlp_bf16) p.weights16 = up(h.weights16, (size_t)pgrf_w16_blob_bytes());
     float* imgs_nchw = up(h.imgs_cl, n_img * 4);
     float* if_nchw = up(h.img_feats_cl, n_if * 4);
     float* rf_nchw = up(h.ray_feats_cl, n_rf * 4);
@@ -145,11 +156,12 @@ extern "C" int pgrf_render_view_host(const pgrf_render_view_args* hv) {
     float* rf_cl = (float*)dalloc(n_rf * 4);
     if (hv->hierarchical) {
       d.weights_fine = up(hv->weights_fine, (size_t)blob * 4);
+      if (h.mlp_bf16) d.weights16_fine = up(hv->weights16_fine, (size_t)pgrf_w16_blob_bytes());
       p.fine_u = up(h.fine_u, (size_t)h.fine_dn * 4);
       d.fine_depth_ws = (float*)dalloc((size_t)chunk * fine_total * 4);
       d.que_depth_fine = nullptr;
     }
-    p.f1 = (float*)dalloc((size_t)f1n * 4);
+    p.f1 = h.mlp_bf16 ? nullptr : (float*)dalloc((size_t)f1n * 4);
     p.f2 = (float*)dalloc((size_t)f2n * 4);
     // device outputs for whatever the caller asked for
     struct Out { float** dev; float* host; size_t n; };
@@ -168,7 +180,7 @@ extern "C" int pgrf_render_view_host(const pgrf_render_view_args* hv) {
     want(&d.hit_prob_fine, hv->hit_prob_fine, (size_t)rn * fine_total);
     want(&d.density_fine, hv->density_fine, (size_t)rn * fine_total);
     want(&d.colors_fine, hv->colors_fine, (size_t)rn * fine_total * 3);
-    for (void* a : allocs) PGRF_REQUIRE(a != nullptr, "render_view_host: device allocation / upload failed");
+    for (void* al : allocs) PGRF_REQUIRE(al != nullptr, "render_view_host: device allocation / upload failed");
     p.imgs_cl = imgs_cl; p.img_feats_cl = if_cl; p.ray_feats_cl = rf_cl;
     p.prob_dbg = nullptr; p.prj_dbg = nullptr; p.feat_dbg = nullptr; p.fine_inds = nullptr; p.fine_depth = nullptr;
     int r = pgrf_nchw_to_nhwc(imgs_nchw, imgs_cl, rfn, 3, h.img_h, h.img_w, 4, st);

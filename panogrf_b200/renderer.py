@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .weights import pack_blob
+from .weights import pack_blob, pack_blob16
 
 
 # ------------------------------------------------------------------------------------------------
@@ -188,6 +188,10 @@ class NeuralRayBaseRenderer(nn.Module):
         self.vis_encoder = None
         self._blob_cache = {}
         self._ws = {}
+        #: "fp32": SIMT parity path (rtol 1e-4); "bf16": tcgen05 tensor-core MLP (bf16 operands, fp32 accumulate, rtol 1e-2)
+        self.mlp_dtype = str(self.cfg.get("mlp_dtype", "fp32"))
+        if self.mlp_dtype not in ("fp32", "bf16"):
+            raise _lib.PanoGRFError(f"mlp_dtype must be 'fp32' or 'bf16', got {self.mlp_dtype!r}")
 
     # ---- weights --------------------------------------------------------------------------------
     def _blob(self, fine, device):
@@ -200,6 +204,15 @@ class NeuralRayBaseRenderer(nn.Module):
             blob = pack_blob(self.state_dict(), fine, agg.cfg["sample_num"], device)
             self._blob_cache[fine] = (key, blob)
         return self._blob_cache[fine][1]
+
+    def _blob16(self, fine, device):
+        params = [p for n, p in self.named_parameters()
+                  if n.startswith(("fine_dist_decoder.", "fine_agg_net.") if fine else ("dist_decoder.", "agg_net."))]
+        key = (fine, str(device), tuple((p.data_ptr(), p._version) for p in params))
+        hit = self._blob_cache.get(("w16", fine))
+        if hit is None or hit[0] != key:
+            self._blob_cache[("w16", fine)] = (key, pack_blob16(self.state_dict(), fine, device))
+        return self._blob_cache[("w16", fine)][1]
 
     # ---- one pass -------------------------------------------------------------------------------
     def _pass(self, ctx, coords, depth, depth_stride, fine_net, want_fine, outs, r0, keep_hit):
@@ -225,6 +238,8 @@ class NeuralRayBaseRenderer(nn.Module):
         a.img_feats_cl, a.if_h, a.if_w = _lib.ptr(ctx["img_feats"]), ctx["img_feats"].shape[1], ctx["img_feats"].shape[2]
         a.ray_feats_cl, a.rf_h, a.rf_w = _lib.ptr(ctx["ray_feats"]), ctx["ray_feats"].shape[1], ctx["ray_feats"].shape[2]
         a.weights = _lib.ptr(self._blob(fine_net, dev))
+        if self.mlp_dtype == "bf16":
+            a.mlp_bf16, a.weights16 = 1, _lib.ptr(self._blob16(fine_net, dev))
         f1n, f2n = ctypes.c_longlong(), ctypes.c_longlong()
         _lib.check(lib.pgrf_render_workspace(a.rfn, rn * dn, ctypes.byref(f1n), ctypes.byref(f2n)), "pgrf_render_workspace")
         ws = ctx["ws"]
@@ -391,10 +406,14 @@ class NeuralRayBaseRenderer(nn.Module):
         a.img_feats_cl, a.if_h, a.if_w = _lib.ptr(ctx["img_feats"]), ctx["img_feats"].shape[1], ctx["img_feats"].shape[2]
         a.ray_feats_cl, a.rf_h, a.rf_w = _lib.ptr(ctx["ray_feats"]), ctx["ray_feats"].shape[1], ctx["ray_feats"].shape[2]
         a.weights = _lib.ptr(self._blob(False, dev))
+        if self.mlp_dtype == "bf16":
+            a.mlp_bf16, a.weights16 = 1, _lib.ptr(self._blob16(False, dev))
         f1n, f2n = ctypes.c_longlong(), ctypes.c_longlong()
         _lib.check(lib.pgrf_render_workspace(a.rfn, chunk * max(dn, fine_total), ctypes.byref(f1n), ctypes.byref(f2n)),
                    "pgrf_render_workspace")
         ws = self._ws.setdefault(str(dev), {})
+        if self.mlp_dtype == "bf16":
+            f1n.value = 4                      # the fused tensor-core kernel has no F1 inter-kernel tiles
         for key, n in (("f1", f1n.value), ("f2", f2n.value), ("fine", chunk * max(fine_total, 1))):
             if ws.get(key) is None or ws[key].numel() < n:
                 ws[key] = torch.empty(n, device=dev, dtype=torch.float32)
@@ -410,6 +429,8 @@ class NeuralRayBaseRenderer(nn.Module):
             a.fine_dn, a.fine_u = fdn, _lib.ptr(ctx["fine_u"])
             a.fine_use_all, a.use_disp = int(bool(cfg["fine_depth_use_all"])), int(bool(cfg["use_disp"]))
             va.weights_fine = _lib.ptr(self._blob(not one_mlp, dev))
+            if self.mlp_dtype == "bf16":
+                va.weights16_fine = _lib.ptr(self._blob16(not one_mlp, dev))
             va.bias_val_fine = float((self.dist_decoder if one_mlp else self.fine_dist_decoder).cfg["bias_val"])
             va.fine_depth_ws = _lib.ptr(ws["fine"])
             va.pixel_colors_fine = _lib.ptr(outs["pixel_colors_nr_fine"][0])

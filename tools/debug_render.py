@@ -7,6 +7,7 @@ from util import load_golden
 import panogrf_b200 as pg
 name = sys.argv[1] if len(sys.argv) > 1 else "render_m3d_2src"
 cfg, _, _ = cases.make_render_inputs(name)
+cfg["mlp_dtype"] = sys.argv[2] if len(sys.argv) > 2 else "fp32"
 que, ref, W, gold = split_golden(load_golden(name))
 net = pg.NeuralRayBaseRenderer(cfg).cuda().eval()
 net.load_state_dict(W, strict=False)
@@ -16,4 +17,4 @@ torch.cuda.synchronize()
 for k, v in gold.items():
     if k.startswith("ray_mask"): continue
     d = (out[k].cpu() - v.float()).abs()
-    print(k, "max abs err", float(d.max()), "max ref", float(v.abs().max()))
+    print(k, "max abs err", float(d.max()), "max ref", float(v.abs().max()), "rel-to-max", float(d.max() / v.abs().max()))

@@ -9,6 +9,7 @@ import panogrf_b200 as pg
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
 cfg = bench.cfg_dict()
+cfg["mlp_dtype"] = os.environ.get("PGRF_MLP", "bf16")
 net = pg.NeuralRayBaseRenderer(cfg).to(dev).eval()
 que, ref = bench.make_inputs(torch, rows=(250, 250 + 2 * net.rays_per_launch // bench.W))
 que_d = {k: v.to(dev) for k, v in que.items()}
