@@ -315,20 +315,22 @@ def time_stages(torch, net, que_d, ref_d, flush):
     res = {}
     names = {1: "render_rows_kernel", 2: "render_samples_kernel", 4: "render_rays_kernel"}
     if net.mlp_dtype == "bf16":
-        names = {3: "render_mlp_bf16_kernel", 4: "render_rays_kernel"}
+        names = {3: "render_mlp_bf16_kernel", 4: "render_rays_bf16_kernel"}
     net._pass(ctx, coords, depth, 0, False, False, outs, 0, False)      # populate workspaces
     torch.cuda.synchronize()
     for mask, name in names.items():
         ts = []
-        for i in range(6):
+        reps = 20                      # back-to-back launches inside one event pair: amortises the host launch path
+        for i in range(4):
             ctx["stage_mask"] = mask
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            net._pass(ctx, coords, depth, 0, False, False, outs, 0, False)
+            for _ in range(reps):
+                net._pass(ctx, coords, depth, 0, False, False, outs, 0, False)
             e1.record()
             torch.cuda.synchronize()
-            if i >= 2:
-                ts.append(e0.elapsed_time(e1))
+            if i >= 1:
+                ts.append(e0.elapsed_time(e1) / reps)
         res[name] = sum(ts) / len(ts)
     ctx["stage_mask"] = 0
     samples = rn * DN
@@ -338,6 +340,7 @@ def time_stages(torch, net, que_d, ref_d, flush):
         "render_samples_kernel": 2.0 * (rows * MAC_ROW_R2 + samples * MAC_SAMPLE_R2),
         "render_mlp_bf16_kernel": 2.0 * (rows * (MAC_ROW_R1 + MAC_ROW_R2) + samples * MAC_SAMPLE_R2),
         "render_rays_kernel": 2.0 * samples * MAC_SAMPLE_R3,
+        "render_rays_bf16_kernel": 2.0 * samples * MAC_SAMPLE_R3,
     }
     peaks = measured_peaks()
     kernels = {k: {"ms": round(v, 4), "tflops": round(flops[k] / v / 1e9, 2), "rays": rn} for k, v in res.items()}

@@ -52,7 +52,7 @@ constexpr int S_DD = 0, S_RDH = 2 * CH, S_F = 4 * CH;
 enum { SF_PX = 0, SF_PY, SF_W0, SF_VIS2, SF_LOGIT, SF_R, SF_G, SF_B };
 
 constexpr int SM16_W = 0;
-constexpr int SM16_WG = (kW16Bytes + 127) & ~127;
+constexpr int SM16_WG = (kW16Sec0Bytes + 127) & ~127;
 constexpr int SM16_BAR = SM16_WG + kWG * WG_BYTES;
 constexpr int SM16_BYTES = SM16_BAR + 64;
 
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.weights16);
     uint4* dst = reinterpret_cast<uint4*>(Wb);
-    for (int i = tid; i < kW16Bytes / 16; i += kThreads16) dst[i] = __ldg(src + i);
+    for (int i = tid; i < kW16Sec0Bytes / 16; i += kThreads16) dst[i] = __ldg(src + i);
   }
   if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
   if (m == 0) mbar_init(bar, 1);
@@ -472,14 +472,16 @@ extern "C" int pgrf_w16_layer_info(int i, char* name, int name_cap, int* Kpad, i
   PGRF_REQUIRE(i >= 0 && i < kNumLayers16, "w16 layer index %d out of range", i);
   snprintf(name, name_cap, "%s", kLayers16[i].name);
   *Kpad = kLayers16[i].Kpad; *Npad = kLayers16[i].Npad;
-  *w_offset_bytes = w16_offset(i);
-  *b_offset_bytes = kW16WeightBytes + 4 * b16_offset(i);
+  const int sec = kLayers16[i].section;
+  *w_offset_bytes = sec16_begin(sec) + w16_offset(i);
+  *b_offset_bytes = sec16_begin(sec) + sec16_w_bytes(sec) + 4 * b16_offset(i);
   for (int k = 0; k < kLayers16[i].Kpad; ++k) kmap[k] = w16_kmap(i, k);
   for (int n = 0; n < kLayers16[i].Npad; ++n) nmap[n] = w16_nmap(i, n);
   return PGRF_OK;
 }
 
 namespace pgrf {
+static_assert(SM16_BYTES + 1024 <= 227 * 1024, "fused MLP kernel shared memory");
 int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long total, int n_tiles, int sms, cudaStream_t st) {
   PGRF_REQUIRE(a.weights16 != nullptr, "render: bf16 path needs weights16");
   PGRF_REQUIRE(((uintptr_t)a.weights16 & 15) == 0, "render: weights16 must be 16-byte aligned");

@@ -660,6 +660,7 @@ static int num_sms() {
 
 namespace pgrf {
 int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long total, int n_tiles, int sms, cudaStream_t st);
+int launch_render_rays_bf16(const pgrf_render_args& a, int V, int T, long long total, int sms, cudaStream_t st);
 }
 using namespace pgrf;
 
@@ -732,8 +733,10 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
       const int rc = launch_render_mlp_bf16(a, p.V, p.T, p.total, p.n_tiles, sms, st);
       if (rc != PGRF_OK) return rc;
     }
-    if (mask & 4) { render_rays_kernel<<<min(p.n_tiles3, sms), kThreads, s3, st>>>(p); count_launch(); }
-    PGRF_CUDA(cudaGetLastError());
+    if (mask & 4) {
+      const int rc = launch_render_rays_bf16(a, p.V, p.T, p.total, sms, st);
+      if (rc != PGRF_OK) return rc;
+    }
     return PGRF_OK;
   }
   if (mask & 1) { render_rows_kernel<<<min(p.n_tiles, sms), kThreads, s1, st>>>(p); count_launch(); }

@@ -24,57 +24,75 @@ struct Layer16 {
   int K, N;          // reference in/out features (of the whole torch weight)
   int Kpad, Npad;
   int kind;
+  int section;       // 0 = fused rows+samples kernel, 1 = rays kernel; blob = [W sec0 | bias sec0 | W sec1 | bias sec1]
 };
 
-constexpr int kNumLayers16 = 27;
+constexpr int kNumLayers16 = 30;
 constexpr Layer16 kLayers16[kNumLayers16] = {
-    {"{dd}.mean_decoder.0", 32, 32, 32, 32, W16_PLAIN}, {"{dd}.mean_decoder.2", 32, 32, 32, 32, W16_PLAIN},
-    {"{dd}.mean_decoder.4", 32, 2, 32, 16, W16_PLAIN},
-    {"{dd}.var_decoder.0", 32, 32, 32, 32, W16_PLAIN},  {"{dd}.var_decoder.2", 32, 32, 32, 32, W16_PLAIN},
-    {"{dd}.var_decoder.4", 32, 2, 32, 16, W16_PLAIN},
-    {"{dd}.aw_decoder.0", 32, 32, 32, 32, W16_PLAIN},   {"{dd}.aw_decoder.2", 32, 32, 32, 32, W16_PLAIN},
-    {"{dd}.aw_decoder.4", 32, 1, 32, 16, W16_PLAIN},
-    {"{dd}.vis_decoder.0", 32, 32, 32, 32, W16_PLAIN},  {"{dd}.vis_decoder.2", 32, 32, 32, 32, W16_PLAIN},
-    {"{dd}.vis_decoder.4", 32, 1, 32, 16, W16_PLAIN},
-    {"{agg}.prob_embed.0", 34, 32, 48, 32, W16_PLAIN},  {"{agg}.prob_embed.2", 32, 32, 32, 32, W16_PLAIN},
-    {"{agg}.agg_impl.ray_dir_fc.0", 4, 16, 16, 16, W16_PLAIN},
-    {"{agg}.agg_impl.ray_dir_fc.2", 16, 35, 16, 48, W16_RD2},
-    {"{agg}.agg_impl.neuray_fc.0", 32, 8, 32, 16, W16_PLAIN},
-    {"{agg}.agg_impl.neuray_fc.2", 8, 1, 16, 16, W16_PLAIN},
-    {"{agg}.agg_impl.base_fc.0", 207, 64, 240, 64, W16_BASE0},
-    {"{agg}.agg_impl.base_fc.2", 64, 32, 64, 32, W16_PLAIN},
-    {"{agg}.agg_impl.vis_fc.0", 32, 32, 32, 32, W16_PLAIN},
-    {"{agg}.agg_impl.vis_fc.2", 32, 33, 32, 48, W16_PLAIN},
-    {"{agg}.agg_impl.vis_fc2.0", 32, 32, 32, 32, W16_PLAIN},
-    {"{agg}.agg_impl.vis_fc2.2", 32, 1, 32, 16, W16_PLAIN},
-    {"{agg}.agg_impl.rgb_fc.0", 37, 16, 48, 16, W16_PLAIN},
-    {"{agg}.agg_impl.rgb_fc.2", 16, 8, 16, 16, W16_PLAIN},
-    {"{agg}.agg_impl.rgb_fc.4", 8, 1, 16, 16, W16_PLAIN},
+    {"{dd}.mean_decoder.0", 32, 32, 32, 32, W16_PLAIN, 0}, {"{dd}.mean_decoder.2", 32, 32, 32, 32, W16_PLAIN, 0},
+    {"{dd}.mean_decoder.4", 32, 2, 32, 16, W16_PLAIN, 0},
+    {"{dd}.var_decoder.0", 32, 32, 32, 32, W16_PLAIN, 0},  {"{dd}.var_decoder.2", 32, 32, 32, 32, W16_PLAIN, 0},
+    {"{dd}.var_decoder.4", 32, 2, 32, 16, W16_PLAIN, 0},
+    {"{dd}.aw_decoder.0", 32, 32, 32, 32, W16_PLAIN, 0},   {"{dd}.aw_decoder.2", 32, 32, 32, 32, W16_PLAIN, 0},
+    {"{dd}.aw_decoder.4", 32, 1, 32, 16, W16_PLAIN, 0},
+    {"{dd}.vis_decoder.0", 32, 32, 32, 32, W16_PLAIN, 0},  {"{dd}.vis_decoder.2", 32, 32, 32, 32, W16_PLAIN, 0},
+    {"{dd}.vis_decoder.4", 32, 1, 32, 16, W16_PLAIN, 0},
+    {"{agg}.prob_embed.0", 34, 32, 48, 32, W16_PLAIN, 0},  {"{agg}.prob_embed.2", 32, 32, 32, 32, W16_PLAIN, 0},
+    {"{agg}.agg_impl.ray_dir_fc.0", 4, 16, 16, 16, W16_PLAIN, 0},
+    {"{agg}.agg_impl.ray_dir_fc.2", 16, 35, 16, 48, W16_RD2, 0},
+    {"{agg}.agg_impl.neuray_fc.0", 32, 8, 32, 16, W16_PLAIN, 0},
+    {"{agg}.agg_impl.neuray_fc.2", 8, 1, 16, 16, W16_PLAIN, 0},
+    {"{agg}.agg_impl.base_fc.0", 207, 64, 240, 64, W16_BASE0, 0},
+    {"{agg}.agg_impl.base_fc.2", 64, 32, 64, 32, W16_PLAIN, 0},
+    {"{agg}.agg_impl.vis_fc.0", 32, 32, 32, 32, W16_PLAIN, 0},
+    {"{agg}.agg_impl.vis_fc.2", 32, 33, 32, 48, W16_PLAIN, 0},
+    {"{agg}.agg_impl.vis_fc2.0", 32, 32, 32, 32, W16_PLAIN, 0},
+    {"{agg}.agg_impl.vis_fc2.2", 32, 1, 32, 16, W16_PLAIN, 0},
+    {"{agg}.agg_impl.rgb_fc.0", 37, 16, 48, 16, W16_PLAIN, 0},
+    {"{agg}.agg_impl.rgb_fc.2", 16, 8, 16, 16, W16_PLAIN, 0},
+    {"{agg}.agg_impl.rgb_fc.4", 8, 1, 16, 16, W16_PLAIN, 0},
+    // ---- rays kernel ----
+    {"{agg}.agg_impl.geometry_fc.0", 65, 64, 80, 64, W16_PLAIN, 1},
+    {"{agg}.agg_impl.geometry_fc.2", 64, 16, 64, 16, W16_PLAIN, 1},
+    {"{agg}.agg_impl.ray_attention.qkv", 16, 48, 16, 48, W16_PLAIN, 1},   // [w_qs | w_ks | w_vs] stacked along n, no bias
 };
 enum : int {
   M_MEAN0 = 0, M_MEAN1, M_MEAN2, M_VAR0, M_VAR1, M_VAR2, M_AW0, M_AW1, M_AW2, M_VIS0, M_VIS1, M_VIS2,
   M_PE0, M_PE1, M_RD0, M_RD1, M_NF0, M_NF1, M_BASE0, M_BASE1, M_VFC0, M_VFC1, M_V2_0, M_V2_1, M_RGB0, M_RGB1, M_RGB2,
+  M_GEO0, M_GEO1, M_QKV,
 };
 
 // feature order f' -> reference order of a 35-vector [rgb(3), img_feats(32)]
 __host__ __device__ constexpr int fprime_to_ref(int f) { return f < 32 ? f + 3 : f - 32; }
 
-// byte offset of layer i's bf16 weights inside the blob
+constexpr int sec16_w_bytes(int sec) {
+  int o = 0;
+  for (int j = 0; j < kNumLayers16; ++j) if (kLayers16[j].section == sec) o += kLayers16[j].Kpad * kLayers16[j].Npad * 2;
+  return o;
+}
+constexpr int sec16_b_floats(int sec) {
+  int o = 0;
+  for (int j = 0; j < kNumLayers16; ++j) if (kLayers16[j].section == sec) o += kLayers16[j].Npad;
+  return o;
+}
+constexpr int sec16_bytes(int sec) { return sec16_w_bytes(sec) + 4 * sec16_b_floats(sec); }
+constexpr int sec16_begin(int sec) { return sec == 0 ? 0 : sec16_bytes(0); }
+// byte offset of layer i's bf16 weights RELATIVE TO ITS SECTION (what the kernels index their smem copy with)
 constexpr int w16_offset(int i) {
   int o = 0;
-  for (int j = 0; j < i; ++j) o += kLayers16[j].Kpad * kLayers16[j].Npad * 2;
+  for (int j = 0; j < i; ++j) if (kLayers16[j].section == kLayers16[i].section) o += kLayers16[j].Kpad * kLayers16[j].Npad * 2;
   return o;
 }
-constexpr int kW16WeightBytes = w16_offset(kNumLayers16);
-// float index of layer i's bias inside the bias region (which starts at kW16WeightBytes)
+// float index of layer i's bias inside its section's bias array (which follows the section's weights)
 constexpr int b16_offset(int i) {
   int o = 0;
-  for (int j = 0; j < i; ++j) o += kLayers16[j].Npad;
+  for (int j = 0; j < i; ++j) if (kLayers16[j].section == kLayers16[i].section) o += kLayers16[j].Npad;
   return o;
 }
-constexpr int kW16BiasFloats = b16_offset(kNumLayers16);
-constexpr int kW16Bytes = kW16WeightBytes + kW16BiasFloats * 4;
-static_assert(kW16WeightBytes % 16 == 0, "bias region must stay 16-byte aligned");
+constexpr int kW16Sec0Bytes = sec16_bytes(0);
+constexpr int kW16WeightBytes = sec16_w_bytes(0);   // section 0: weights then biases
+constexpr int kW16Bytes = sec16_bytes(0) + sec16_bytes(1);
+static_assert(sec16_w_bytes(0) % 16 == 0 && sec16_bytes(0) % 16 == 0 && sec16_w_bytes(1) % 16 == 0, "16-byte aligned regions");
 
 inline int w16_kmap(int layer, int k) {
   const Layer16& L = kLayers16[layer];

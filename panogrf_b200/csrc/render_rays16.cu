@@ -1,0 +1,350 @@
+// bf16 tensor-core variant of the per-ray stage (geometry_fc, ray transformer, compositing, fine resampling).
+//
+// Same decomposition as render_bf16.cu: CTA = 4 independent warpgroups, a warpgroup owns one tile of up to 128
+// samples (whole rays), thread <-> sample.  geometry_fc.0/.2 and the fused q|k|v projection are tcgen05 MMAs
+// (bf16 operands, fp32 TMEM accumulators); the 4-head attention over the samples of a ray runs per thread on fp32
+// K/V tiles kept in shared memory as float4 per (head, token); fc + LayerNorm + out_geometry_fc are 16-wide
+// register GEMVs; compositing and the inverse-CDF fine resampling are one warp per ray with the stated sequential
+// fp32 accumulation order.  Reference: ibrnet.py:352-364,15-27,72-102; render_ops.py:145-153,413-473;
+// renderer.py:210-219,302-304,472.
+#include <type_traits>
+
+#include "render_device.cuh"
+#include "render_layout16.cuh"
+#include "umma.cuh"
+
+#define W16(L) (std::integral_constant<int, pgrf::w16_offset(L)>::value)
+#define B16(L) (std::integral_constant<int, pgrf::b16_offset(L)>::value)
+#define WOFF(L) (std::integral_constant<int, pgrf::sec_off(L) - pgrf::sec_off(pgrf::L_AFC)>::value)
+#define BOFF(L) (std::integral_constant<int, pgrf::bias_off(L) - pgrf::sec_off(pgrf::L_AFC)>::value)
+
+namespace pgrf {
+
+constexpr int kWGr = 4;
+constexpr int kThreadsR = 128 * kWGr;
+constexpr int RROWS = 128;
+constexpr int RCH = RROWS * 16;
+
+// per-warpgroup shared memory (bytes)
+constexpr int R_A = 0;                       // 10 chunks: [mean 32 | var 32 | wmean, 0 x15]; later H64 (8 chunks)
+constexpr int R_G16 = 10 * RCH;              // 2 chunks
+constexpr int R_K4 = R_G16 + 2 * RCH;        // float4 [4 heads][128 tokens]
+constexpr int R_V4 = R_K4 + 4 * RROWS * 16;
+constexpr int R_RV = R_V4 + 4 * RROWS * 16;  // 6 x [256] floats
+constexpr int R_RGB = R_RV + 6 * 256 * 4;    // 3 x [128] floats
+constexpr int R_WG_BYTES = R_RGB + 3 * RROWS * 4;
+enum { RV2_SIGMA = 0, RV2_ALPHA, RV2_HIT, RV2_CDF, RV2_CENTER, RV2_FINE };
+
+constexpr int kSec1Bytes = sec16_bytes(1);
+constexpr int kR3W32Begin = sec_off(L_AFC);                            // only fc, out_geometry_fc and layer norm stay fp32
+constexpr int kR3W32 = section_floats(2) + 32 - kR3W32Begin;
+constexpr int SMR_W16 = 0;
+constexpr int SMR_W32 = (kSec1Bytes + 15) & ~15;
+constexpr int SMR_PE = SMR_W32 + ((kR3W32 * 4 + 15) & ~15);
+constexpr int SMR_WG = (SMR_PE + kMaxSamplesPerRay * 16 * 4 + 127) & ~127;
+constexpr int SMR_BAR = SMR_WG + kWGr * R_WG_BYTES;
+constexpr int SMR_BYTES = SMR_BAR + 64;
+
+__device__ __forceinline__ void wgr_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ float warp_sum16(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static __device__ __noinline__ void epi_elu_store(uint32_t taddr, const float* __restrict__ bias, unsigned char* dst, int m, int nchunks) {
+#pragma unroll 1
+  for (int c = 0; c < nchunks; c += 2) {
+    float v[16];
+    umma::ld16(taddr + 8 * c, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = elu1(v[i] + bias[8 * c + i]);
+    umma::store_chunk(dst, RROWS, c, m, v);
+    umma::store_chunk(dst, RROWS, c + 1, m, v + 8);
+  }
+}
+
+struct Rays16Params {
+  pgrf_render_args a;
+  int V, T, log2T;
+  long long total;
+  int rays_per_tile, n_tiles;
+};
+
+#define RSTAGE_BEGIN()                                                      \
+  umma::fence_smem_to_async(); umma::fence_before_sync(); wgr_sync(wg);     \
+  if (m == 0) { umma::fence_after_sync();
+#define RSTAGE_END()                                                        \
+    umma::commit(bar); }                                                    \
+  mbar_wait(bar, phase); phase ^= 1; umma::fence_after_sync();
+
+__global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Rays16Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  const pgrf_render_args& a = p.a;
+  const int tid = threadIdx.x;
+  const int wg = tid >> 7, m = tid & 127, wq = (tid >> 5) & 3, lane = tid & 31;
+  unsigned char* Wb = smem + SMR_W16;
+  const float* Bias = reinterpret_cast<const float*>(Wb + sec16_w_bytes(1));
+  float* W32 = reinterpret_cast<float*>(smem + SMR_W32);
+  float* PE = reinterpret_cast<float*>(smem + SMR_PE);
+  unsigned char* G = smem + SMR_WG + wg * R_WG_BYTES;
+  float4* K4 = reinterpret_cast<float4*>(G + R_K4);
+  float4* V4 = reinterpret_cast<float4*>(G + R_V4);
+  float* RV = reinterpret_cast<float*>(G + R_RV);
+  float* RGB = reinterpret_cast<float*>(G + R_RGB);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMR_BAR) + wg;
+
+  {
+    constexpr int sec1 = sec16_begin(1);
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.weights16) + sec1);
+    uint4* dst = reinterpret_cast<uint4*>(Wb);
+    for (int i = tid; i < kSec1Bytes / 16; i += kThreadsR) dst[i] = __ldg(src + i);
+    constexpr int sec2 = section_begin(2);
+    for (int i = tid; i < kR3W32; i += kThreadsR) W32[i] = __ldg(a.weights + sec2 + kR3W32Begin + i);
+    for (int i = tid; i < a.dn * 16; i += kThreadsR) PE[i] = __ldg(a.weights + kPosencOffset + i);
+  }
+  if (tid < 32) umma::tmem_alloc(&tmem_base_s, 256);
+  if (m == 0) mbar_init(bar, 1);
+  umma::fence_smem_to_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = tmem_base_s + wg * 64;
+  const uint32_t tq = tb + ((uint32_t)(wq * 32) << 16);
+  uint32_t phase = 0;
+  constexpr int ln_rel = section_floats(2) - kR3W32Begin;
+  const float* LNW = W32 + ln_rel;
+  const float* LNB = LNW + 16;
+
+  const int dn = a.dn, V = p.V, T = p.T;
+  const int rpt = p.rays_per_tile;
+  const int Mv = rpt * dn;
+
+#pragma unroll 1
+  for (int tile = blockIdx.x * kWGr + wg; tile < p.n_tiles; tile += gridDim.x * kWGr) {
+    const long long g0 = (long long)tile * Mv;
+    long long g = g0 + min(m, Mv - 1);
+    if (g >= p.total) g = p.total - 1;
+    const int sidx = (int)(g % dn);                       // sample index inside its ray
+    // ---- pooled features of this sample (F2 tile [kF2][T]) -> A operand (bf16), colours -> smem
+    {
+      const float* f2 = a.f2 + (size_t)(g >> p.log2T) * kF2 * T + (g & (T - 1));
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(f2 + (size_t)(8 * c + i) * T);
+        umma::store_chunk(G + R_A, RROWS, c, m, v);
+      }
+      float tail[8] = {__ldg(f2 + (size_t)64 * T), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      umma::store_chunk(G + R_A, RROWS, 8, m, tail);
+      *reinterpret_cast<uint4*>(G + R_A + ((size_t)9 * RROWS + m) * 16) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) RGB[i * RROWS + m] = __ldg(f2 + (size_t)(F2_RGB + i) * T);
+    }
+    // ---- geometry_fc 65 -> 64 -> 16 (+ positional code)
+    RSTAGE_BEGIN() umma::gemm_issue(tb, G + R_A, RROWS, Wb + W16(M_GEO0), 64, 64, 80); RSTAGE_END()
+    epi_elu_store(tq, Bias + B16(M_GEO0), G + R_A, m, 8);       // H64 overwrites A: its MMA is complete
+    RSTAGE_BEGIN() umma::gemm_issue(tb, G + R_A, RROWS, Wb + W16(M_GEO1), 16, 16, 64); RSTAGE_END()
+    float g16[16];
+    {
+      umma::ld16(tq, g16);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g16[i] = elu1(g16[i] + Bias[B16(M_GEO1) + i]) + PE[sidx * 16 + i];
+      umma::store_chunk(G + R_G16, RROWS, 0, m, g16);
+      umma::store_chunk(G + R_G16, RROWS, 1, m, g16 + 8);
+    }
+    // ---- q | k | v projections
+    RSTAGE_BEGIN() umma::gemm_issue(tb, G + R_G16, RROWS, Wb + W16(M_QKV), 48, 48, 16); RSTAGE_END()
+    float q[16];
+    {
+      umma::ld16(tq, q);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) q[i] *= 0.5f;            // q / temperature, temperature = sqrt(d_k) = 2
+      float kv[16];
+      umma::ld16(tq + 16, kv);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) K4[h * RROWS + m] = make_float4(kv[4 * h], kv[4 * h + 1], kv[4 * h + 2], kv[4 * h + 3]);
+      umma::ld16(tq + 32, kv);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) V4[h * RROWS + m] = make_float4(kv[4 * h], kv[4 * h + 1], kv[4 * h + 2], kv[4 * h + 3]);
+    }
+    umma::fence_before_sync();
+    wgr_sync(wg);
+    // ---- 4-head attention over the samples of this token's ray (mask rule ibrnet.py:359-360: < 2 views -> uniform)
+    float ao[16];
+    {
+      const int r0 = (min(m, Mv - 1) / dn) * dn;
+      const bool masked = !(V > 1);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float q0 = q[4 * h], q1 = q[4 * h + 1], q2 = q[4 * h + 2], q3 = q[4 * h + 3];
+        const float4* Kh = K4 + h * RROWS + r0;
+        const float4* Vh = V4 + h * RROWS + r0;
+        float mx = -INFINITY;
+#pragma unroll 4
+        for (int j = 0; j < dn; ++j) {
+          const float4 k = Kh[j];
+          mx = fmaxf(mx, masked ? -1e9f : q0 * k.x + q1 * k.y + q2 * k.z + q3 * k.w);
+        }
+        float den = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < dn; ++j) {
+          const float4 k = Kh[j];
+          const float4 vv = Vh[j];
+          const float sc = masked ? -1e9f : q0 * k.x + q1 * k.y + q2 * k.z + q3 * k.w;
+          const float e = fast_exp(sc - mx);
+          den += e;
+          o0 = fmaf(e, vv.x, o0); o1 = fmaf(e, vv.y, o1); o2 = fmaf(e, vv.z, o2); o3 = fmaf(e, vv.w, o3);
+        }
+        const float inv = 1.f / den;
+        ao[4 * h] = o0 * inv; ao[4 * h + 1] = o1 * inv; ao[4 * h + 2] = o2 * inv; ao[4 * h + 3] = o3 * inv;
+      }
+    }
+    // ---- fc + residual + LayerNorm(1e-6) + out_geometry_fc 16 -> 16 -> 1 (ReLU), fp32 register GEMVs
+    {
+      float o[16], x[16];
+      reg_layer<16, 16, 16>(ao, W32 + WOFF(L_AFC), nullptr, o);
+      float mean = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { x[i] = o[i] + g16[i]; mean += x[i]; }
+      mean *= (1.f / 16.f);
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) var += (x[i] - mean) * (x[i] - mean);
+      var *= (1.f / 16.f);
+      const float rstd = rsqrtf(var + 1e-6f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = (x[i] - mean) * rstd * LNW[i] + LNB[i];
+      float h1[16], s4[4];
+      reg_layer<16, 16, 16>(x, W32 + WOFF(L_OG0), W32 + BOFF(L_OG0), h1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h1[i] = elu1(h1[i]);
+      reg_layer<16, 1, 4>(h1, W32 + WOFF(L_OG1), W32 + BOFF(L_OG1), s4);
+      RV[RV2_SIGMA * 256 + m] = fmaxf(s4[0], 0.f);
+    }
+    wgr_sync(wg);
+    // ---- per ray: alpha compositing (+ fine resampling), one warp per ray
+    for (int r = wq; r < rpt; r += 4) {
+      const long long ray = (long long)tile * rpt + r;
+      if (ray >= a.rn) continue;
+      const int m0 = r * dn;
+      float* alpha = RV + RV2_ALPHA * 256 + m0;
+      float* hit = RV + RV2_HIT * 256 + m0;
+      const float* sigma = RV + RV2_SIGMA * 256 + m0;
+      const float* dp = a.depth + (size_t)ray * a.depth_ray_stride;
+      for (int s = lane; s < dn; s += 32) alpha[s] = 1.f - fast_exp(-sigma[s]);
+      __syncwarp();
+      if (lane == 0) {  // sequential fp32 cumprod (stated accumulation order)
+        float trans = 1.f;
+        for (int s = 0; s < dn; ++s) {
+          hit[s] = alpha[s] * trans;
+          trans = trans * (1.f - alpha[s] + 1e-10f);
+        }
+      }
+      __syncwarp();
+      float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
+      for (int s = lane; s < dn; s += 32) {
+        const float hs = hit[s];
+        const float r_ = RGB[0 * RROWS + m0 + s], g_ = RGB[1 * RROWS + m0 + s], b_ = RGB[2 * RROWS + m0 + s];
+        cr = fmaf(hs, r_, cr); cg = fmaf(hs, g_, cg); cb = fmaf(hs, b_, cb);
+        cd = fmaf(hs, __ldg(dp + s), cd);
+        if (a.hit_prob) a.hit_prob[(size_t)ray * dn + s] = hs;
+        if (a.density) a.density[(size_t)ray * dn + s] = sigma[s];
+        if (a.colors) {
+          float* c = a.colors + ((size_t)ray * dn + s) * 3;
+          c[0] = r_; c[1] = g_; c[2] = b_;
+        }
+      }
+      cr = warp_sum16(cr); cg = warp_sum16(cg); cb = warp_sum16(cb); cd = warp_sum16(cd);
+      if (lane == 0) {
+        a.pixel_colors[(size_t)ray * 3 + 0] = cr; a.pixel_colors[(size_t)ray * 3 + 1] = cg; a.pixel_colors[(size_t)ray * 3 + 2] = cb;
+        if (a.render_depth) a.render_depth[ray] = cd;
+      }
+      if (a.fine_depth) {
+        // ---- sample_fine_depth (render_ops.py:413-473), deterministic u-table ----
+        float* cdf = RV + RV2_CDF * 256 + 2 * m0;
+        float* center = RV + RV2_CENTER * 256 + 2 * m0;
+        float* fine = RV + RV2_FINE * 256 + 2 * m0;
+        const bool inv = a.use_disp != 0;
+        const float nn = -1.f / a.que_near, ff = -1.f / a.que_far;
+        for (int s = lane; s <= dn; s += 32) {
+          float d1 = __ldg(dp + min(s, dn - 1));
+          float d0 = __ldg(dp + max(s - 1, 0));
+          if (inv) { d1 = (-1.f / d1 - nn) / (ff - nn); d0 = (-1.f / d0 - nn) / (ff - nn); }
+          center[s] = (s == 0 || s == dn) ? d1 : (d1 + d0) / 2.f;
+        }
+        float tot = 0.f;
+        if (lane == 0) for (int s = 0; s < dn; ++s) tot += hit[s] + 1e-5f;     // sequential normaliser
+        tot = __shfl_sync(0xffffffffu, tot, 0);
+        for (int s = lane; s < dn; s += 32) cdf[s + 1] = (hit[s] + 1e-5f) / tot; // pdf, in parallel (IEEE division)
+        __syncwarp();
+        if (lane == 0) {                                                         // sequential cumsum
+          float c = 0.f;
+          cdf[0] = 0.f;
+          for (int s = 0; s < dn; ++s) { c += cdf[s + 1]; cdf[s + 1] = c; }
+        }
+        __syncwarp();
+        const int fdn = a.fine_dn;
+        for (int k = lane; k < fdn; k += 32) {
+          const float u = __ldg(a.fine_u + k);
+          int lo = 0, hi = dn + 1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+          const int inds = lo;
+          if (a.fine_inds) a.fine_inds[(size_t)ray * fdn + k] = inds;
+          const int below = max(inds - 1, 0), above = min(dn, inds);
+          const float cb_ = cdf[below], ca_ = cdf[above];
+          float denom = ca_ - cb_;
+          if (denom < 1e-5f) denom = 1.f;
+          const float t = (u - cb_) / denom;
+          float fd = __fadd_rn(center[below], __fmul_rn(t, center[above] - center[below]));
+          if (inv) { fd = __fadd_rn(__fmul_rn(fd, ff - nn), nn); fd = -1.f / fd; }
+          fine[k] = fd;
+        }
+        int total_out = fdn;
+        if (a.fine_use_all) {
+          for (int s = lane; s < dn; s += 32) fine[fdn + s] = __ldg(dp + s);
+          total_out = fdn + dn;
+        }
+        __syncwarp();
+        for (int k = lane; k < total_out; k += 32) {   // rank sort (value-only result == torch.sort)
+          const float x = fine[k];
+          int rank = 0;
+          for (int j = 0; j < total_out; ++j) {
+            const float y = fine[j];
+            rank += (y < x || (y == x && j < k)) ? 1 : 0;
+          }
+          a.fine_depth[(size_t)ray * total_out + rank] = x;
+        }
+      }
+    }
+    wgr_sync(wg);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tmem_base_s, 256);
+}
+
+static_assert(SMR_BYTES <= 227 * 1024, "rays kernel shared memory");
+
+int launch_render_rays_bf16(const pgrf_render_args& a, int V, int T, long long total, int sms, cudaStream_t st) {
+  Rays16Params p;
+  p.a = a; p.V = V; p.T = T; p.total = total;
+  p.log2T = 0;
+  while ((1 << p.log2T) < T) ++p.log2T;
+  p.rays_per_tile = a.dn >= RROWS ? 1 : RROWS / a.dn;
+  p.n_tiles = (a.rn + p.rays_per_tile - 1) / p.rays_per_tile;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PGRF_CUDA(cudaFuncSetAttribute(render_rays_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMR_BYTES));
+    attr_done = true;
+  }
+  const int grid = min((p.n_tiles + kWGr - 1) / kWGr, sms);
+  render_rays_bf16_kernel<<<grid, kThreadsR, SMR_BYTES, st>>>(p);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+}  // namespace pgrf

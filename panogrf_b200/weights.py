@@ -71,12 +71,17 @@ def pack_blob16(state, fine, device):
     blob = torch.zeros(lib.pgrf_w16_blob_bytes(), dtype=torch.uint8)
     for name, Kpad, Npad, w_off, b_off, kmap, nmap in _lib.w16_layers():
         key = name.replace("{dd}", dd).replace("{agg}", agg)
-        if key + ".weight" not in state:
-            if ".vis_decoder." in key:
-                continue
-            raise KeyError(f"missing parameter {key}.weight")
-        w = state[key + ".weight"].detach().float().cpu()
-        b = state.get(key + ".bias")
+        if key.endswith("ray_attention.qkv"):
+            base = key[:-len(".qkv")]
+            w = torch.cat([state[base + ".w_qs.weight"], state[base + ".w_ks.weight"], state[base + ".w_vs.weight"]], 0)
+            w, b = w.detach().float().cpu(), None
+        else:
+            if key + ".weight" not in state:
+                if ".vis_decoder." in key:
+                    continue
+                raise KeyError(f"missing parameter {key}.weight")
+            w = state[key + ".weight"].detach().float().cpu()
+            b = state.get(key + ".bias")
         km = torch.tensor(kmap)
         nm = torch.tensor(nmap)
         wp = torch.zeros(Npad, Kpad)
