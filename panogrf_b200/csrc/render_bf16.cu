@@ -31,7 +31,7 @@ constexpr int CH = ROWS * 16;               // bytes per k-chunk of an A operand
 constexpr int E_BYTES = 20 * CH;            // pooled blocks of XB (20 chunks); early: RF + HD0..2; late: H64, HV, HV2, XF32, RG, R1
 constexpr int P_BYTES = 10 * CH;            // tail of XB: rgb_feat' (5 chunks) + neuray (4) + zero chunk (1)
 constexpr int S_OFF = E_BYTES + P_BYTES;    // DD (2 chunks), RDH (2 chunks), 8 float vectors
-constexpr int S_BYTES = 4 * CH + 8 * ROWS * 4;
+constexpr int S_BYTES = 4 * CH + 8 * ROWS * 4;   // SF vectors 0/1 (+2,3 early) double as the footprint records
 constexpr int WG_BYTES = S_OFF + S_BYTES;
 // early E
 constexpr int E_RF = 0;                     // 6 chunks: ray_feats (4) + [hit',vis',0..] + zero chunk
@@ -76,7 +76,7 @@ static __device__ __noinline__ void epi_act_store(uint32_t taddr, const float* _
     }
     if (act == ACT_ELU) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = elu1(v[i]);
+      for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : fast_exp(v[i]) - 1.f;   // FSETP + FSEL, no branch
     } else if (act == ACT_RELU) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -95,6 +95,24 @@ __device__ __forceinline__ void zero_chunk(unsigned char* dst, int chunk, int m)
   *reinterpret_cast<uint4*>(dst + ((size_t)chunk * ROWS + m) * 16) = make_uint4(0u, 0u, 0u, 0u);
 }
 
+struct __align__(16) FootRec {
+  int off;      // texel index of the north-west tap inside the stacked (rfn*h*w) map
+  int dxy;      // bit0: east neighbour inside the map, bit1: south neighbour inside the map
+  float tx, ty;
+};
+__device__ __forceinline__ float4 tap4_rec(const float4* __restrict__ base, const FootRec& f, int stride_x, int stride_y) {
+  const int sx = (f.dxy & 1) ? stride_x : 0, sy = (f.dxy & 2) ? stride_y : 0;
+  const float4 nw = ldg4(base), ne = ldg4(base + sx), sw = ldg4(base + sy), se = ldg4(base + sy + sx);
+  const float tx1 = 1.f - f.tx, ty1 = 1.f - f.ty;
+  const float wnw = tx1 * ty1, wne = f.tx * ty1, wsw = tx1 * f.ty, wse = f.tx * f.ty;
+  float4 o;
+  o.x = nw.x * wnw; o.y = nw.y * wnw; o.z = nw.z * wnw; o.w = nw.w * wnw;
+  o.x = fmaf(ne.x, wne, o.x); o.y = fmaf(ne.y, wne, o.y); o.z = fmaf(ne.z, wne, o.z); o.w = fmaf(ne.w, wne, o.w);
+  o.x = fmaf(sw.x, wsw, o.x); o.y = fmaf(sw.y, wsw, o.y); o.z = fmaf(sw.z, wsw, o.z); o.w = fmaf(sw.w, wsw, o.w);
+  o.x = fmaf(se.x, wse, o.x); o.y = fmaf(se.y, wse, o.y); o.z = fmaf(se.z, wse, o.z); o.w = fmaf(se.w, wse, o.w);
+  return o;
+}
+
 // one MMA stage: publish the operand writes, sync the warpgroup, let one thread issue, wait for completion
 #define STAGE_BEGIN()                                                       \
   umma::fence_smem_to_async(); umma::fence_before_sync(); wg_sync(wg);      \
@@ -110,6 +128,7 @@ struct Render16Params {
   int n_tiles;
 };
 
+template <int V>
 __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Render16Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
@@ -124,6 +143,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
   unsigned char* P = E + E_BYTES;
   unsigned char* S = E + S_OFF;
   float* SF = reinterpret_cast<float*>(S + S_F);
+  FootRec* FP = reinterpret_cast<FootRec*>(SF);   // [2][128] records = SF vectors 0..7 (all dead during geometry/gather)
   float* XF = reinterpret_cast<float*>(P);        // x in fp32 [32][128]; P is dead once base_fc.0 has consumed it
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM16_BAR) + wg;
 
@@ -143,7 +163,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
   const uint32_t tq = tb + ((uint32_t)(wq * 32) << 16);       // + this warp's lane quadrant
   uint32_t phase = 0;
 
-  const int T = p.T, V = p.V, M = p.M;
+  const int T = p.T, M = p.M;
   const int v = min(m / T, V - 1), t = m % T;
   const float wgt = 1.f / ((float)V + 1e-8f);
 
@@ -156,8 +176,14 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
 
     // ------------------------------------------------------------ geometry (thread = row)
     const RowGeom rg = row_geometry(a, v, g);
-    SF[SF_PX * ROWS + m] = rg.px;
-    SF[SF_PY * ROWS + m] = rg.py;
+    {
+      Footprint f = border_footprint(rg.px, rg.py, a.img_h, a.img_w, a.rf_h, a.rf_w);
+      FootRec r1; r1.off = v * a.rf_h * a.rf_w + f.off; r1.dxy = f.dx | (f.dy << 1); r1.tx = f.tx; r1.ty = f.ty;
+      FP[m] = r1;
+      f = border_footprint(rg.px, rg.py, a.img_h, a.img_w, a.if_h, a.if_w);
+      r1.off = v * a.if_h * a.if_w + f.off; r1.dxy = f.dx | (f.dy << 1); r1.tx = f.tx; r1.ty = f.ty;
+      FP[ROWS + m] = r1;
+    }
     {
       float dd8[8] = {rg.dirdiff[0], rg.dirdiff[1], rg.dirdiff[2], rg.dirdiff[3], 0.f, 0.f, 0.f, 0.f};
       umma::store_chunk(S + S_DD, ROWS, 0, m, dd8);
@@ -184,17 +210,16 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     wg_sync(wg);
 
     // ------------------------------------------------------------ cooperative gathers (lane = (row, float4 group))
-#pragma unroll 1
+    // each row's two bilinear footprints were computed once by its own thread (FP records in smem); here 8 lanes
+    // per row fetch the 4 x 128-byte taps of both feature maps and blend
+#pragma unroll 2
     for (int it = m; it < ROWS * 8; it += 128) {
       const int r = it >> 3, cg = it & 7;
-      const int rv = min(r / T, V - 1);
-      const float px = SF[SF_PX * ROWS + r], py = SF[SF_PY * ROWS + r];
-      const Footprint f1 = border_footprint(px, py, a.img_h, a.img_w, a.rf_h, a.rf_w);
-      const float4 rf = tap4(reinterpret_cast<const float4*>(a.ray_feats_cl) + ((size_t)rv * a.rf_h * a.rf_w + f1.off) * 8 + cg,
-                             f1, 8, a.rf_w * 8);
-      const Footprint f2 = border_footprint(px, py, a.img_h, a.img_w, a.if_h, a.if_w);
-      const float4 imf = tap4(reinterpret_cast<const float4*>(a.img_feats_cl) + ((size_t)rv * a.if_h * a.if_w + f2.off) * 8 + cg,
-                              f2, 8, a.if_w * 8);
+      const FootRec f1 = FP[r], f2 = FP[ROWS + r];
+      const float4* b1 = reinterpret_cast<const float4*>(a.ray_feats_cl) + (size_t)f1.off * 8 + cg;
+      const float4* b2 = reinterpret_cast<const float4*>(a.img_feats_cl) + (size_t)f2.off * 8 + cg;
+      const float4 rf = tap4_rec(b1, f1, 8, a.rf_w * 8);
+      const float4 imf = tap4_rec(b2, f2, 8, a.if_w * 8);
       // 4 channels = half a chunk: chunk cg/2, 8-byte half cg%2
       uint2 q;
       q.x = umma::pack2(rf.x, rf.y); q.y = umma::pack2(rf.z, rf.w);
@@ -308,26 +333,23 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
 
     // ------------------------------------------------------------ view pooling #1 (fused_mean_variance x2) -> XB blocks
     {
-      float w0n[4];
+      float w0n[V];
 #pragma unroll
-      for (int vv = 0; vv < 4; ++vv) w0n[vv] = (vv < V) ? SF[SF_W0 * ROWS + vv * T + t] * wgt : 0.f;
+      for (int vv = 0; vv < V; ++vv) w0n[vv] = SF[SF_W0 * ROWS + vv * T + t] * wgt;
 #pragma unroll 1
       for (int c = 0; c < 5; ++c) {
-        float x[4][8];
+        float x[V][8];
 #pragma unroll
-        for (int vv = 0; vv < 4; ++vv)
-          if (vv < V) umma::load_chunk(P, ROWS, c, vv * T + t, x[vv]);
+        for (int vv = 0; vv < V; ++vv) umma::load_chunk(P, ROWS, c, vv * T + t, x[vv]);
         float m0[8], v0[8], m1[8], v1[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-          for (int vv = 0; vv < 4; ++vv)
-            if (vv < V) { a0 += x[vv][i] * w0n[vv]; a1 += x[vv][i] * wgt; }
+          for (int vv = 0; vv < V; ++vv) { a0 += x[vv][i] * w0n[vv]; a1 += x[vv][i] * wgt; }
           float b0 = 0.f, b1 = 0.f;
 #pragma unroll
-          for (int vv = 0; vv < 4; ++vv)
-            if (vv < V) {
+          for (int vv = 0; vv < V; ++vv) {
               b0 += w0n[vv] * ((x[vv][i] - a0) * (x[vv][i] - a0));
               b1 += wgt * ((x[vv][i] - a1) * (x[vv][i] - a1));
             }
@@ -404,20 +426,19 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       float* f2 = a.f2 + (size_t)tile * kF2 * T + m;
       float sum = 0.f;
 #pragma unroll
-      for (int vv = 0; vv < 4; ++vv) if (vv < V) sum += SF[SF_VIS2 * ROWS + vv * T + m];
-      float wv[4], ws = 0.f;
+      for (int vv = 0; vv < V; ++vv) sum += SF[SF_VIS2 * ROWS + vv * T + m];
+      float wv[V], ws = 0.f;
 #pragma unroll
-      for (int vv = 0; vv < 4; ++vv) { wv[vv] = (vv < V) ? SF[SF_VIS2 * ROWS + vv * T + m] / (sum + 1e-8f) : 0.f; ws += wv[vv]; }
+      for (int vv = 0; vv < V; ++vv) { wv[vv] = SF[SF_VIS2 * ROWS + vv * T + m] / (sum + 1e-8f); ws += wv[vv]; }
       if (gs < p.total) {
 #pragma unroll 2
         for (int c = 0; c < 32; ++c) {
           float mean_c = 0.f;
 #pragma unroll
-          for (int vv = 0; vv < 4; ++vv) if (vv < V) mean_c += XF[c * ROWS + vv * T + m] * wv[vv];
+          for (int vv = 0; vv < V; ++vv) mean_c += XF[c * ROWS + vv * T + m] * wv[vv];
           float var_c = 0.f;
 #pragma unroll
-          for (int vv = 0; vv < 4; ++vv)
-            if (vv < V) { const float d = XF[c * ROWS + vv * T + m] - mean_c; var_c += wv[vv] * (d * d); }
+          for (int vv = 0; vv < V; ++vv) { const float d = XF[c * ROWS + vv * T + m] - mean_c; var_c += wv[vv] * (d * d); }
           f2[(size_t)c * T] = mean_c;
           f2[(size_t)(32 + c) * T] = var_c;
         }
@@ -440,11 +461,10 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       if (gs < p.total) {
         float mx = -INFINITY;
 #pragma unroll
-        for (int vv = 0; vv < 4; ++vv) if (vv < V) mx = fmaxf(mx, SF[SF_LOGIT * ROWS + vv * T + m]);
+        for (int vv = 0; vv < V; ++vv) mx = fmaxf(mx, SF[SF_LOGIT * ROWS + vv * T + m]);
         float den = 0.f, r = 0.f, gg = 0.f, b = 0.f;
 #pragma unroll
-        for (int vv = 0; vv < 4; ++vv)
-          if (vv < V) {
+        for (int vv = 0; vv < V; ++vv) {
             const float e = expf(SF[SF_LOGIT * ROWS + vv * T + m] - mx);
             den += e;
             r += SF[SF_R * ROWS + vv * T + m] * e; gg += SF[SF_G * ROWS + vv * T + m] * e; b += SF[SF_B * ROWS + vv * T + m] * e;
@@ -487,13 +507,21 @@ int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long to
   PGRF_REQUIRE(((uintptr_t)a.weights16 & 15) == 0, "render: weights16 must be 16-byte aligned");
   Render16Params p;
   p.a = a; p.V = V; p.T = T; p.M = V * T; p.total = total; p.n_tiles = n_tiles;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PGRF_CUDA(cudaFuncSetAttribute(render_mlp_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM16_BYTES));
-    attr_done = true;
-  }
   const int grid = min((n_tiles + kWG - 1) / kWG, sms);
-  render_mlp_bf16_kernel<<<grid, kThreads16, SM16_BYTES, st>>>(p);
+#define PGRF_LAUNCH_V(VV)                                                                                              \
+  case VV: {                                                                                                           \
+    static bool done = false;                                                                                          \
+    if (!done) {                                                                                                       \
+      PGRF_CUDA(cudaFuncSetAttribute(render_mlp_bf16_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM16_BYTES)); \
+      done = true;                                                                                                     \
+    }                                                                                                                  \
+    render_mlp_bf16_kernel<VV><<<grid, kThreads16, SM16_BYTES, st>>>(p);                                               \
+  } break;
+  switch (V) {
+    PGRF_LAUNCH_V(1) PGRF_LAUNCH_V(2) PGRF_LAUNCH_V(3) PGRF_LAUNCH_V(4)
+    default: PGRF_REQUIRE(false, "render: rfn=%d source views unsupported (1..4)", V);
+  }
+#undef PGRF_LAUNCH_V
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
