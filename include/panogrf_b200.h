@@ -192,7 +192,8 @@ PGRF_API int pgrf_weight_layer_info(int i, char* name, int name_cap, int* K, int
 PGRF_API int pgrf_w16_blob_bytes(void);
 PGRF_API int pgrf_w16_num_layers(void);
 PGRF_API int pgrf_w16_layer_info(int i, char* name, int name_cap, int* Kpad, int* Npad, int* w_offset_bytes, int* b_offset_bytes,
-                                 int* kmap, int* nmap);
+                                 int* kmap, int* nmap, int* is_small);
+/* is_small = 1: tiny output layer kept as fp32 W[N][K] row-major at w_offset_bytes and bias[N] at b_offset_bytes (Kpad = K, Npad = N) */
 /* layer-norm (weight 16, bias 16) offset, positional table offset ([max_samples][16]) */
 PGRF_API int pgrf_weight_aux_offsets(int* layer_norm_offset, int* posenc_offset, int* max_samples);
 

@@ -135,7 +135,7 @@ SIGNATURES.update({
     "pgrf_weight_aux_offsets": (_I, [_PI, _PI, _PI]),
     "pgrf_w16_blob_bytes": (_I, []),
     "pgrf_w16_num_layers": (_I, []),
-    "pgrf_w16_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI]),
+    "pgrf_w16_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI, _PI]),
 })
 
 
@@ -159,15 +159,16 @@ def weight_aux_offsets():
 
 
 def w16_layers():
-    """[(name, Kpad, Npad, w_offset_bytes, b_offset_bytes, kmap, nmap)] of the bf16 tensor-core blob."""
+    """[(name, Kpad, Npad, w_offset_bytes, b_offset_bytes, kmap, nmap, is_small)] of the bf16 tensor-core blob."""
     lib = load()
     out = []
     for i in range(lib.pgrf_w16_num_layers()):
         name = ctypes.create_string_buffer(128)
-        kp, np_, wo, bo = _I(), _I(), _I(), _I()
+        kp, np_, wo, bo, small = _I(), _I(), _I(), _I(), _I()
         kmap = (_I * 256)()
         nmap = (_I * 64)()
         check(lib.pgrf_w16_layer_info(i, name, 128, ctypes.byref(kp), ctypes.byref(np_), ctypes.byref(wo), ctypes.byref(bo),
-                                      kmap, nmap), "pgrf_w16_layer_info")
-        out.append((name.value.decode(), kp.value, np_.value, wo.value, bo.value, list(kmap[:kp.value]), list(nmap[:np_.value])))
+                                      kmap, nmap, ctypes.byref(small)), "pgrf_w16_layer_info")
+        out.append((name.value.decode(), kp.value, np_.value, wo.value, bo.value, list(kmap[:kp.value]), list(nmap[:np_.value]),
+                    bool(small.value)))
     return out

@@ -19,6 +19,8 @@
 
 #define W16(L) (std::integral_constant<int, pgrf::w16_offset(L)>::value)
 #define B16(L) (std::integral_constant<int, pgrf::b16_offset(L)>::value)
+#define SMW(L) (std::integral_constant<int, pgrf::small16_offset(L)>::value)
+#define SMB(L) (std::integral_constant<int, pgrf::small16_bias_offset(L)>::value)
 
 namespace pgrf {
 
@@ -85,6 +87,46 @@ static __device__ __noinline__ void epi_act_store(uint32_t taddr, const float* _
     umma::store_chunk(dst, ROWS, c + 1, m, v + 8);
   }
 }
+// dst chunks (optional) = bf16(h), h = act(acc + bias); out[j] = sum_k h[k] * Wsm[j][k]  (tiny fp32 output layer fused
+// into the epilogue of the layer that feeds it: saves one MMA stage and keeps its input in fp32)
+template <int NOUT>
+static __device__ __noinline__ void epi_act_gemv(uint32_t taddr, const float* __restrict__ bias, unsigned char* dst, int m,
+                                                 int nchunks, int act, const float* __restrict__ Wsm, int K, float (&out)[NOUT]) {
+#pragma unroll
+  for (int j = 0; j < NOUT; ++j) out[j] = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; c += 2) {
+    float v[16];
+    umma::ld16(taddr + 8 * c, v);
+    const float4* b4 = reinterpret_cast<const float4*>(bias + 8 * c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = b4[i];
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+    if (act == ACT_ELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : fast_exp(v[i]) - 1.f;
+    } else if (act == ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (dst) {
+      umma::store_chunk(dst, ROWS, c, m, v);
+      umma::store_chunk(dst, ROWS, c + 1, m, v + 8);
+    }
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) {
+      const float4* w4 = reinterpret_cast<const float4*>(Wsm + j * K + 8 * c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w = w4[i];
+        out[j] = fmaf(v[4 * i], w.x, out[j]); out[j] = fmaf(v[4 * i + 1], w.y, out[j]);
+        out[j] = fmaf(v[4 * i + 2], w.z, out[j]); out[j] = fmaf(v[4 * i + 3], w.w, out[j]);
+      }
+    }
+  }
+}
 // first accumulator column (+bias) of a padded N=16 output layer
 __device__ __forceinline__ float epi_scalar(uint32_t taddr, const float* __restrict__ bias) {
   float a, b;
@@ -139,6 +181,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
   const int wq = (tid >> 5) & 3;      // warp inside the warpgroup -> TMEM lane quadrant
   unsigned char* Wb = smem + SM16_W;
   const float* Bias = reinterpret_cast<const float*>(Wb + kW16WeightBytes);
+  const float* Wsm = reinterpret_cast<const float*>(Wb + kW16SmallBegin0);     // fp32 tiny output layers
   unsigned char* E = smem + SM16_WG + wg * WG_BYTES;
   unsigned char* P = E + E_BYTES;
   unsigned char* S = E + S_OFF;
@@ -250,9 +293,17 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       umma::gemm_issue(tb + 64, E + E_HD2, ROWS, Wb + W16(M_AW1), 32, 32, 32);
       umma::gemm_issue(tb + 128, S + S_RDH, ROWS, Wb + W16(M_RD1), 48, 48, 16);
     STAGE_END()
-    epi_act_store(tq + 0, Bias + B16(M_MEAN1), E + E_HD0, m, 4, ACT_ELU);   // in place: the MMAs reading HD* are complete
-    epi_act_store(tq + 32, Bias + B16(M_VAR1), E + E_HD1, m, 4, ACT_ELU);
-    epi_act_store(tq + 64, Bias + B16(M_AW1), E + E_HD2, m, 4, ACT_ELU);
+    // decoder output layers (32 -> 2, 2, 1) fused into these epilogues as fp32 register GEMVs
+    float mean[2], var[2], aw, visd = 1.f;
+    {
+      float o2[2], o1[1];
+      epi_act_gemv<2>(tq + 0, Bias + B16(M_MEAN1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_MEAN2), 32, o2);
+      mean[0] = softplusf(o2[0] + Wsm[SMB(M_MEAN2)]); mean[1] = softplusf(o2[1] + Wsm[SMB(M_MEAN2) + 1]);
+      epi_act_gemv<2>(tq + 32, Bias + B16(M_VAR1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_VAR2), 32, o2);
+      var[0] = softplusf(o2[0] + Wsm[SMB(M_VAR2)]) + a.bias_val; var[1] = softplusf(o2[1] + Wsm[SMB(M_VAR2) + 1]) + a.bias_val;
+      epi_act_gemv<1>(tq + 64, Bias + B16(M_AW1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_AW2), 32, o1);
+      aw = sigmoidf(o1[0] + Wsm[SMB(M_AW2)]);
+    }
     // direction feature (f' order: img_feats 0..31, rgb 32..34): rgb_feat = [img_feats, rgb] + ELU(ray_dir_fc)
 #pragma unroll 1
     for (int c = 0; c < 5; ++c) {
@@ -272,28 +323,13 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       umma::store_chunk(P, ROWS, c, m, x);     // P_IMG chunks 0..3, P_RGB = chunk 4
     }
 
-    // ------------------------------------------------------------ stage 3: decoder output layers
-    STAGE_BEGIN()
-      umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_MEAN2), 16, 16, 32);
-      umma::gemm_issue(tb + 16, E + E_HD1, ROWS, Wb + W16(M_VAR2), 16, 16, 32);
-      umma::gemm_issue(tb + 32, E + E_HD2, ROWS, Wb + W16(M_AW2), 16, 16, 32);
-    STAGE_END()
-    float mean[2], var[2], aw, visd = 1.f;
-    {
-      float o0, o1;
-      umma::ld2(tq + 0, o0, o1);
-      mean[0] = softplusf(o0 + Bias[B16(M_MEAN2)]); mean[1] = softplusf(o1 + Bias[B16(M_MEAN2) + 1]);
-      umma::ld2(tq + 16, o0, o1);
-      var[0] = softplusf(o0 + Bias[B16(M_VAR2)]) + a.bias_val; var[1] = softplusf(o1 + Bias[B16(M_VAR2) + 1]) + a.bias_val;
-      aw = sigmoidf(epi_scalar(tq + 32, Bias + B16(M_AW2)));
-    }
-    if (a.use_vis) {   // 4th decoder, three more sequential stages through HD0
+    if (a.use_vis) {   // 4th decoder: two more sequential stages through HD0, output layer fused
       STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_RF, ROWS, Wb + W16(M_VIS0), 32, 32, 32); STAGE_END()
       epi_act_store(tq + 0, Bias + B16(M_VIS0), E + E_HD0, m, 4, ACT_ELU);
       STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_VIS1), 32, 32, 32); STAGE_END()
-      epi_act_store(tq + 0, Bias + B16(M_VIS1), E + E_HD0, m, 4, ACT_ELU);
-      STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_VIS2), 16, 16, 32); STAGE_END()
-      visd = sigmoidf(epi_scalar(tq + 0, Bias + B16(M_VIS2)));
+      float o1[1];
+      epi_act_gemv<1>(tq + 0, Bias + B16(M_VIS1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_VIS2), 32, o1);
+      visd = sigmoidf(o1[0] + Wsm[SMB(M_VIS2)]);
     }
 
     // ------------------------------------------------------------ logistic-mixture probabilities (dist_decoder.compute_prob)
@@ -321,13 +357,14 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_RF, ROWS, Wb + W16(M_PE0), 32, 32, 48); STAGE_END()
     epi_act_store(tq + 0, Bias + B16(M_PE0), E + E_HD0, m, 4, ACT_RELU);
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_PE1), 32, 32, 32); STAGE_END()
-    epi_act_store(tq + 0, Bias + B16(M_PE1), P + P_NEU, m, 4, ACT_NONE);
-
-    // ------------------------------------------------------------ stage 6/7: neuray_fc 32 -> 8 -> 1 (sigmoid)
-    STAGE_BEGIN() umma::gemm_issue(tb + 0, P + P_NEU, ROWS, Wb + W16(M_NF0), 16, 16, 32); STAGE_END()
-    epi_act_store(tq + 0, Bias + B16(M_NF0), E + E_HD1, m, 2, ACT_ELU);   // padded outputs 8..15: ELU(0 + 0) = 0
-    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD1, ROWS, Wb + W16(M_NF1), 16, 16, 16); STAGE_END()
-    SF[SF_W0 * ROWS + m] = sigmoidf(epi_scalar(tq + 0, Bias + B16(M_NF1)));
+    {   // prob_embedding -> P (bf16 operand of base_fc.0) and, fused, neuray_fc 32 -> 8 (ELU) -> 1 (sigmoid) in fp32
+      float h8[8];
+      epi_act_gemv<8>(tq + 0, Bias + B16(M_PE1), P + P_NEU, m, 4, ACT_NONE, Wsm + SMW(M_NF0), 32, h8);
+      float o = Wsm[SMB(M_NF1)];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o = fmaf(elu1(h8[i] + Wsm[SMB(M_NF0) + i]), Wsm[SMW(M_NF1) + i], o);
+      SF[SF_W0 * ROWS + m] = sigmoidf(o);
+    }
     umma::fence_before_sync();
     wg_sync(wg);
 
@@ -401,10 +438,10 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     }
     // ------------------------------------------------------------ stage 12/13: vis_fc2(x * vis) 32 -> 32 -> 1
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV, ROWS, Wb + W16(M_V2_0), 32, 32, 32); STAGE_END()
-    epi_act_store(tq + 0, Bias + B16(M_V2_0), E + E_HV2, m, 4, ACT_ELU);
-    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV2, ROWS, Wb + W16(M_V2_1), 16, 16, 32); STAGE_END()
     {
-      const float vis2 = sigmoidf(epi_scalar(tq + 0, Bias + B16(M_V2_1)));
+      float o1[1];
+      epi_act_gemv<1>(tq + 0, Bias + B16(M_V2_0), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_V2_1), 32, o1);   // vis_fc2.2 fused
+      const float vis2 = sigmoidf(o1[0] + Wsm[SMB(M_V2_1)]);
       SF[SF_VIS2 * ROWS + m] = vis2;
       // rgb_fc input [x(32), vis, ray_diff(4)] -> K = 48
 #pragma unroll 1
@@ -446,12 +483,14 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       }
     }
     mbar_wait(bar, phase); phase ^= 1; umma::fence_after_sync();
-    epi_act_store(tq + 0, Bias + B16(M_RGB0), E + E_R1, m, 2, ACT_ELU);
-    // ------------------------------------------------------------ stage 15/16: rgb_fc.2, rgb_fc.4
-    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_R1, ROWS, Wb + W16(M_RGB1), 16, 16, 16); STAGE_END()
-    epi_act_store(tq + 0, Bias + B16(M_RGB1), S + S_DD, m, 2, ACT_ELU);       // DD is dead since stage 1
-    STAGE_BEGIN() umma::gemm_issue(tb + 0, S + S_DD, ROWS, Wb + W16(M_RGB2), 16, 16, 16); STAGE_END()
-    SF[SF_LOGIT * ROWS + m] = epi_scalar(tq + 0, Bias + B16(M_RGB2));
+    {   // rgb_fc.2 (16 -> 8, ELU) and rgb_fc.4 (8 -> 1) fused as fp32 register GEMVs
+      float h8[8];
+      epi_act_gemv<8>(tq + 0, Bias + B16(M_RGB0), nullptr, m, 2, ACT_ELU, Wsm + SMW(M_RGB1), 16, h8);
+      float o = Wsm[SMB(M_RGB2)];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o = fmaf(elu1(h8[i] + Wsm[SMB(M_RGB1) + i]), Wsm[SMW(M_RGB2) + i], o);
+      SF[SF_LOGIT * ROWS + m] = o;
+    }
     SF[SF_R * ROWS + m] = rgb_in[0]; SF[SF_G * ROWS + m] = rgb_in[1]; SF[SF_B * ROWS + m] = rgb_in[2];
     umma::fence_before_sync();
     wg_sync(wg);
@@ -488,13 +527,20 @@ using namespace pgrf;
 extern "C" int pgrf_w16_blob_bytes(void) { return kW16Bytes; }
 extern "C" int pgrf_w16_num_layers(void) { return kNumLayers16; }
 extern "C" int pgrf_w16_layer_info(int i, char* name, int name_cap, int* Kpad, int* Npad, int* w_offset_bytes, int* b_offset_bytes,
-                                   int* kmap, int* nmap) {
+                                   int* kmap, int* nmap, int* is_small) {
   PGRF_REQUIRE(i >= 0 && i < kNumLayers16, "w16 layer index %d out of range", i);
   snprintf(name, name_cap, "%s", kLayers16[i].name);
   *Kpad = kLayers16[i].Kpad; *Npad = kLayers16[i].Npad;
   const int sec = kLayers16[i].section;
-  *w_offset_bytes = sec16_begin(sec) + w16_offset(i);
-  *b_offset_bytes = sec16_begin(sec) + sec16_w_bytes(sec) + 4 * b16_offset(i);
+  *is_small = is_small16(i) ? 1 : 0;
+  if (is_small16(i)) {   // fp32 W[N][K] row-major, then bias[N]
+    const int small_begin = sec16_begin(sec) + sec16_w_bytes(sec) + 4 * sec16_b_floats(sec);
+    *w_offset_bytes = small_begin + 4 * small16_offset(i);
+    *b_offset_bytes = small_begin + 4 * small16_bias_offset(i);
+  } else {
+    *w_offset_bytes = sec16_begin(sec) + w16_offset(i);
+    *b_offset_bytes = sec16_begin(sec) + sec16_w_bytes(sec) + 4 * b16_offset(i);
+  }
   for (int k = 0; k < kLayers16[i].Kpad; ++k) kmap[k] = w16_kmap(i, k);
   for (int n = 0; n < kLayers16[i].Npad; ++n) nmap[n] = w16_nmap(i, n);
   return PGRF_OK;

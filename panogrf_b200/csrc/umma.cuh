@@ -69,12 +69,14 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 static __device__ __noinline__ void gemm_issue(uint32_t d_tmem, const void* A, int a_rows, const void* Wt, int w_rows, int N, int K,
                                         bool accumulate_first = false) {
   const uint32_t idesc = instr_desc_bf16(128, N);
-  const uint32_t a0 = smem_addr(A), w0 = smem_addr(Wt);
   const uint32_t a_lbo = a_rows * 16, w_lbo = w_rows * 16;
+  uint64_t ad = smem_desc(smem_addr(A), a_lbo, 128);
+  uint64_t bd = smem_desc(smem_addr(Wt), w_lbo, 128);
+  const uint64_t a_step = (uint64_t)((2 * a_lbo) >> 4), w_step = (uint64_t)((2 * w_lbo) >> 4);   // two k-chunks per K=16 MMA
   for (int k = 0; k < K; k += 16) {
-    const uint64_t ad = smem_desc(a0 + (k >> 3) * a_lbo, a_lbo, 128);
-    const uint64_t bd = smem_desc(w0 + (k >> 3) * w_lbo, w_lbo, 128);
     mma_bf16(d_tmem, ad, bd, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+    ad += a_step;     // start-address field (bits 0..13, 16-byte units); operands never cross the 256 KB field range
+    bd += w_step;
   }
 }
 

@@ -69,7 +69,7 @@ def pack_blob16(state, fine, device):
     dd = "fine_dist_decoder" if fine else "dist_decoder"
     agg = "fine_agg_net" if fine else "agg_net"
     blob = torch.zeros(lib.pgrf_w16_blob_bytes(), dtype=torch.uint8)
-    for name, Kpad, Npad, w_off, b_off, kmap, nmap in _lib.w16_layers():
+    for name, Kpad, Npad, w_off, b_off, kmap, nmap, is_small in _lib.w16_layers():
         key = name.replace("{dd}", dd).replace("{agg}", agg)
         if key.endswith("ray_attention.qkv"):
             base = key[:-len(".qkv")]
@@ -82,6 +82,11 @@ def pack_blob16(state, fine, device):
                 raise KeyError(f"missing parameter {key}.weight")
             w = state[key + ".weight"].detach().float().cpu()
             b = state.get(key + ".bias")
+        if is_small:      # fp32 W[N][K] row-major + bias[N], evaluated as a register GEMV in the previous epilogue
+            blob[w_off:w_off + Kpad * Npad * 4] = w[:Npad, :Kpad].contiguous().view(torch.uint8).reshape(-1)
+            if b is not None:
+                blob[b_off:b_off + Npad * 4] = b.detach().float().cpu().contiguous().view(torch.uint8).reshape(-1)
+            continue
         km = torch.tensor(kmap)
         nm = torch.tensor(nmap)
         wp = torch.zeros(Npad, Kpad)
