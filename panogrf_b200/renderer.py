@@ -188,6 +188,7 @@ class NeuralRayBaseRenderer(nn.Module):
         self.vis_encoder = None
         self._blob_cache = {}
         self._ws = {}
+        self._cl_cache = {}
         #: "fp32": SIMT parity path (rtol 1e-4); "bf16": tcgen05 tensor-core MLP (bf16 operands, fp32 accumulate, rtol 1e-2)
         self.mlp_dtype = str(self.cfg.get("mlp_dtype", "fp32"))
         if self.mlp_dtype not in ("fp32", "bf16"):
@@ -283,9 +284,9 @@ class NeuralRayBaseRenderer(nn.Module):
         dr = que_imgs_info["depth_range"].float().cpu()
         return {
             "rfn": imgs.shape[0],
-            "imgs": to_channels_last(imgs, 4),
-            "img_feats": to_channels_last(ref_imgs_info["img_feats"]),
-            "ray_feats": to_channels_last(ref_imgs_info["ray_feats"]),
+            "imgs": self._cached_cl("imgs", imgs, 4),
+            "img_feats": self._cached_cl("img_feats", ref_imgs_info["img_feats"], None),
+            "ray_feats": self._cached_cl("ray_feats", ref_imgs_info["ray_feats"], None),
             "w2c": ref_imgs_info["w2c"].float().contiguous().to(dev),
             "ref_range": ref_imgs_info["depth_range"].float().contiguous().to(dev),
             "c2w": c2w.float().reshape(3, 4).contiguous().to(dev),
@@ -293,6 +294,15 @@ class NeuralRayBaseRenderer(nn.Module):
             "fine_u": fine_u_table(int(self.cfg["fine_depth_sample_num"])).to(dev),
             "ws": {},
         }
+
+    def _cached_cl(self, name, t, pad_to):
+        """Channels-last copy of a source map, reused while the caller keeps passing the same (unmodified) tensor —
+        the source panoramas do not change between the query poses of a video render (render.py:249-291)."""
+        key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+        hit = self._cl_cache.get(name)
+        if hit is None or hit[0] != key:
+            self._cl_cache[name] = (key, to_channels_last(t, pad_to), t)      # keep `t` alive so data_ptr stays unique
+        return self._cl_cache[name][1]
 
     # ---- reference API --------------------------------------------------------------------------
     def render_impl(self, que_imgs_info, ref_imgs_info, is_train, is_perspec=False, _ctx=None, _outs=None, _r0=0,
