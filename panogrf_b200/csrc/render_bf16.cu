@@ -24,34 +24,30 @@
 
 namespace pgrf {
 
-constexpr int kWG = 2;                      // warpgroups per CTA
+constexpr int kWG = 3;                      // warpgroups per CTA (12 warps; shared memory: 72 KB weights + 3 x 44 KB)
 constexpr int kThreads16 = 128 * kWG;
 constexpr int ROWS = 128;                   // rows per tile == operand row pitch
 constexpr int CH = ROWS * 16;               // bytes per k-chunk of an A operand
 
-// ---- per-warpgroup shared memory map (bytes) ----
-constexpr int E_BYTES = 20 * CH;            // pooled blocks of XB (20 chunks); early: RF + HD0..2; late: H64, HV, HV2, XF32, RG, R1
-constexpr int P_BYTES = 10 * CH;            // tail of XB: rgb_feat' (5 chunks) + neuray (4) + zero chunk (1)
-constexpr int S_OFF = E_BYTES + P_BYTES;    // DD (2 chunks), RDH (2 chunks), 8 float vectors
-constexpr int S_BYTES = 4 * CH + 8 * ROWS * 4;   // SF vectors 0/1 (+2,3 early) double as the footprint records
+// ---- per-warpgroup shared memory map (bytes): two 10-chunk operand regions + 8 float vectors ----
+//  E early : RF = chunks 0..5 (ray_feats 4 | [hit',vis',0..] | zero; chunks 4,5 hold ray_dir_fc.0's output until compute_prob)
+//            HDA = chunks 6..9 (decoder / prob_embed hidden)
+//  E mid   : pooled view statistics, 10 chunks at a time (mean0|var0, then mean1|var1) -> base_fc.0 K-slices
+//  E late  : H64 = 0..7 ; HV = 0..3 ; HV2 = 4..7 ; RG = 4..9
+//  P early : img_feats 0..3 | rgb 4 | HDB 5..8 (second decoder hidden buffer) | zero 9
+//  P mid   : rgb_feat' 0..4 | prob_embedding 5..8 | zero 9   == last 80 K-columns of base_fc.0
+//  P late  : x in fp32 [32][128] (chunks 0..7)
+constexpr int E_BYTES = 10 * CH;
+constexpr int P_BYTES = 10 * CH;
+constexpr int S_OFF = E_BYTES + P_BYTES;
+constexpr int S_BYTES = 8 * ROWS * 4;       // SF vectors; all 8 double as the 2 x 128 footprint records during geometry/gather
 constexpr int WG_BYTES = S_OFF + S_BYTES;
-// early E
-constexpr int E_RF = 0;                     // 6 chunks: ray_feats (4) + [hit',vis',0..] + zero chunk
-constexpr int E_HD0 = 6 * CH, E_HD1 = 10 * CH, E_HD2 = 14 * CH;   // 4 chunks each
-// late E
-constexpr int E_H64 = 0;                    // 8 chunks
-constexpr int E_HV = 8 * CH, E_HV2 = 12 * CH;                     // 4 chunks each
-constexpr int E_XF32 = 8 * CH;              // fp32 [32][128] = 8 chunks worth (aliases HV, HV2 once they are dead)
-constexpr int E_RG = 0;                     // 6 chunks: x (4) + [vis2, dirdiff, 0] + zero chunk
-constexpr int E_R1 = 16 * CH;               // 2 chunks
-// P
-constexpr int P_IMG = 0;                    // 4 chunks img_feats(+dir feat)
-constexpr int P_RGB = 4 * CH;               // 1 chunk  [rgb(+dir feat) 3, 0 x5]
-constexpr int P_NEU = 5 * CH;               // 4 chunks prob_embedding
-constexpr int P_ZERO = 9 * CH;              // 1 zero chunk
-// S
-constexpr int S_DD = 0, S_RDH = 2 * CH, S_F = 4 * CH;
+constexpr int E_RF = 0, E_RDH = 4 * CH, E_HDA = 6 * CH;
+constexpr int E_H64 = 0, E_HV = 0, E_HV2 = 4 * CH, E_RG = 4 * CH;
+constexpr int P_IMG = 0, P_RGB = 4 * CH, P_NEU = 5 * CH, P_HDB = 5 * CH, P_ZERO = 9 * CH;
+constexpr int S_F = 0;
 enum { SF_PX = 0, SF_PY, SF_W0, SF_VIS2, SF_LOGIT, SF_R, SF_G, SF_B };
+constexpr int kTmemPerWG = 128;
 
 constexpr int SM16_W = 0;
 constexpr int SM16_WG = (kW16Sec0Bytes + 127) & ~127;
@@ -163,6 +159,31 @@ __device__ __forceinline__ float4 tap4_rec(const float4* __restrict__ base, cons
     umma::commit(bar); }                                                    \
   mbar_wait(bar, phase); phase ^= 1; umma::fence_after_sync();
 
+// weighted mean / variance over the V views of sample t (fused_mean_variance, ibrnet.py:112-116) of the 40-wide
+// rgb_feat' block in P (chunks 0..4) -> E chunks 0..4 (mean) and 5..9 (variance), written to row m
+template <int V>
+__device__ __forceinline__ void pool_views(const unsigned char* P, unsigned char* E, int t, int T, int m, const float (&w)[V]) {
+#pragma unroll 1
+  for (int c = 0; c < 5; ++c) {
+    float x[V][8];
+#pragma unroll
+    for (int vv = 0; vv < V; ++vv) umma::load_chunk(P, ROWS, c, vv * T + t, x[vv]);
+    float mu[8], var[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a0 = 0.f;
+#pragma unroll
+      for (int vv = 0; vv < V; ++vv) a0 += x[vv][i] * w[vv];
+      float b0 = 0.f;
+#pragma unroll
+      for (int vv = 0; vv < V; ++vv) b0 += w[vv] * ((x[vv][i] - a0) * (x[vv][i] - a0));
+      mu[i] = a0; var[i] = b0;
+    }
+    umma::store_chunk(E, ROWS, c, m, mu);
+    umma::store_chunk(E, ROWS, 5 + c, m, var);
+  }
+}
+
 struct Render16Params {
   pgrf_render_args a;
   int V, T, M;
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  const uint32_t tb = tmem_base_s + wg * 256;                 // this warpgroup's TMEM columns
+  const uint32_t tb = tmem_base_s + wg * kTmemPerWG;          // this warpgroup's TMEM columns
   const uint32_t tq = tb + ((uint32_t)(wq * 32) << 16);       // + this warp's lane quadrant
   uint32_t phase = 0;
 
@@ -227,10 +248,15 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       r1.off = v * a.if_h * a.if_w + f.off; r1.dxy = f.dx | (f.dy << 1); r1.tx = f.tx; r1.ty = f.ty;
       FP[ROWS + m] = r1;
     }
-    {
-      float dd8[8] = {rg.dirdiff[0], rg.dirdiff[1], rg.dirdiff[2], rg.dirdiff[3], 0.f, 0.f, 0.f, 0.f};
-      umma::store_chunk(S + S_DD, ROWS, 0, m, dd8);
-      zero_chunk(S + S_DD, 1, m);
+    {   // ray_dir_fc.0 (4 -> 16, ELU) as an fp32 register GEMV; its output is the K = 16 operand of ray_dir_fc.2
+      float h[16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        const float4 w = *reinterpret_cast<const float4*>(Wsm + SMW(M_RD0) + 4 * n);
+        h[n] = elu1(Wsm[SMB(M_RD0) + n] + rg.dirdiff[0] * w.x + rg.dirdiff[1] * w.y + rg.dirdiff[2] * w.z + rg.dirdiff[3] * w.w);
+      }
+      umma::store_chunk(E + E_RDH, ROWS, 0, m, h);
+      umma::store_chunk(E + E_RDH, ROWS, 1, m, h + 8);
     }
     // own-row colour taps (fp32, kept in registers for the final blend)
     float rgb_in[3];
@@ -263,52 +289,25 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       const float4* b2 = reinterpret_cast<const float4*>(a.img_feats_cl) + (size_t)f2.off * 8 + cg;
       const float4 rf = tap4_rec(b1, f1, 8, a.rf_w * 8);
       const float4 imf = tap4_rec(b2, f2, 8, a.if_w * 8);
-      // 4 channels = half a chunk: chunk cg/2, 8-byte half cg%2
-      uint2 q;
+      uint2 q;   // 4 channels = half a chunk: chunk cg/2, 8-byte half cg%2
       q.x = umma::pack2(rf.x, rf.y); q.y = umma::pack2(rf.z, rf.w);
       *reinterpret_cast<uint2*>(E + E_RF + ((size_t)(cg >> 1) * ROWS + r) * 16 + (cg & 1) * 8) = q;
       q.x = umma::pack2(imf.x, imf.y); q.y = umma::pack2(imf.z, imf.w);
       *reinterpret_cast<uint2*>(P + P_IMG + ((size_t)(cg >> 1) * ROWS + r) * 16 + (cg & 1) * 8) = q;
     }
-    zero_chunk(E + E_RF, 4, m);
-    zero_chunk(E + E_RF, 5, m);
     zero_chunk(P, 9, m);
 
-    // ------------------------------------------------------------ stage 1: decoder layer 0 (x3) + ray_dir_fc.0
+    // ------------------------------------------------------------ stage A: mean_decoder.0 + ray_dir_fc.2
     STAGE_BEGIN()
       umma::gemm_issue(tb + 0, E + E_RF, ROWS, Wb + W16(M_MEAN0), 32, 32, 32);
-      umma::gemm_issue(tb + 32, E + E_RF, ROWS, Wb + W16(M_VAR0), 32, 32, 32);
-      umma::gemm_issue(tb + 64, E + E_RF, ROWS, Wb + W16(M_AW0), 32, 32, 32);
-      umma::gemm_issue(tb + 128, S + S_DD, ROWS, Wb + W16(M_RD0), 16, 16, 16);
+      umma::gemm_issue(tb + 64, E + E_RDH, ROWS, Wb + W16(M_RD1), 48, 48, 16);
     STAGE_END()
-    epi_act_store(tq + 0, Bias + B16(M_MEAN0), E + E_HD0, m, 4, ACT_ELU);
-    epi_act_store(tq + 32, Bias + B16(M_VAR0), E + E_HD1, m, 4, ACT_ELU);
-    epi_act_store(tq + 64, Bias + B16(M_AW0), E + E_HD2, m, 4, ACT_ELU);
-    epi_act_store(tq + 128, Bias + B16(M_RD0), S + S_RDH, m, 2, ACT_ELU);
-
-    // ------------------------------------------------------------ stage 2: decoder layer 1 (x3) + ray_dir_fc.2
-    STAGE_BEGIN()
-      umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_MEAN1), 32, 32, 32);
-      umma::gemm_issue(tb + 32, E + E_HD1, ROWS, Wb + W16(M_VAR1), 32, 32, 32);
-      umma::gemm_issue(tb + 64, E + E_HD2, ROWS, Wb + W16(M_AW1), 32, 32, 32);
-      umma::gemm_issue(tb + 128, S + S_RDH, ROWS, Wb + W16(M_RD1), 48, 48, 16);
-    STAGE_END()
-    // decoder output layers (32 -> 2, 2, 1) fused into these epilogues as fp32 register GEMVs
-    float mean[2], var[2], aw, visd = 1.f;
-    {
-      float o2[2], o1[1];
-      epi_act_gemv<2>(tq + 0, Bias + B16(M_MEAN1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_MEAN2), 32, o2);
-      mean[0] = softplusf(o2[0] + Wsm[SMB(M_MEAN2)]); mean[1] = softplusf(o2[1] + Wsm[SMB(M_MEAN2) + 1]);
-      epi_act_gemv<2>(tq + 32, Bias + B16(M_VAR1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_VAR2), 32, o2);
-      var[0] = softplusf(o2[0] + Wsm[SMB(M_VAR2)]) + a.bias_val; var[1] = softplusf(o2[1] + Wsm[SMB(M_VAR2) + 1]) + a.bias_val;
-      epi_act_gemv<1>(tq + 64, Bias + B16(M_AW1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_AW2), 32, o1);
-      aw = sigmoidf(o1[0] + Wsm[SMB(M_AW2)]);
-    }
+    epi_act_store(tq + 0, Bias + B16(M_MEAN0), E + E_HDA, m, 4, ACT_ELU);
     // direction feature (f' order: img_feats 0..31, rgb 32..34): rgb_feat = [img_feats, rgb] + ELU(ray_dir_fc)
 #pragma unroll 1
     for (int c = 0; c < 5; ++c) {
       float df[8], x[8];
-      umma::ld8(tq + 128 + 8 * c, df);
+      umma::ld8(tq + 64 + 8 * c, df);
       if (c < 4) {
         umma::load_chunk(P + P_IMG, ROWS, c, m, x);
       } else {
@@ -322,11 +321,41 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       }
       umma::store_chunk(P, ROWS, c, m, x);     // P_IMG chunks 0..3, P_RGB = chunk 4
     }
-
-    if (a.use_vis) {   // 4th decoder: two more sequential stages through HD0, output layer fused
-      STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_RF, ROWS, Wb + W16(M_VIS0), 32, 32, 32); STAGE_END()
-      epi_act_store(tq + 0, Bias + B16(M_VIS0), E + E_HD0, m, 4, ACT_ELU);
-      STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_VIS1), 32, 32, 32); STAGE_END()
+    // ------------------------------------------------------------ stages B, C, D: the decoders, software-pipelined over two
+    // hidden buffers (HDA in E, HDB in P); each output layer (32 -> 2, 2, 1) is an fp32 register GEMV fused into the epilogue
+    float mean[2], var[2], aw, visd = 1.f;
+    STAGE_BEGIN()
+      umma::gemm_issue(tb + 0, E + E_HDA, ROWS, Wb + W16(M_MEAN1), 32, 32, 32);
+      umma::gemm_issue(tb + 32, E + E_RF, ROWS, Wb + W16(M_VAR0), 32, 32, 32);
+    STAGE_END()
+    {
+      float o2[2];
+      epi_act_gemv<2>(tq + 0, Bias + B16(M_MEAN1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_MEAN2), 32, o2);
+      mean[0] = softplusf(o2[0] + Wsm[SMB(M_MEAN2)]); mean[1] = softplusf(o2[1] + Wsm[SMB(M_MEAN2) + 1]);
+      epi_act_store(tq + 32, Bias + B16(M_VAR0), P + P_HDB, m, 4, ACT_ELU);
+    }
+    STAGE_BEGIN()
+      umma::gemm_issue(tb + 0, P + P_HDB, ROWS, Wb + W16(M_VAR1), 32, 32, 32);
+      umma::gemm_issue(tb + 32, E + E_RF, ROWS, Wb + W16(M_AW0), 32, 32, 32);
+    STAGE_END()
+    {
+      float o2[2];
+      epi_act_gemv<2>(tq + 0, Bias + B16(M_VAR1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_VAR2), 32, o2);
+      var[0] = softplusf(o2[0] + Wsm[SMB(M_VAR2)]) + a.bias_val; var[1] = softplusf(o2[1] + Wsm[SMB(M_VAR2) + 1]) + a.bias_val;
+      epi_act_store(tq + 32, Bias + B16(M_AW0), E + E_HDA, m, 4, ACT_ELU);
+    }
+    STAGE_BEGIN()
+      umma::gemm_issue(tb + 0, E + E_HDA, ROWS, Wb + W16(M_AW1), 32, 32, 32);
+      if (a.use_vis) umma::gemm_issue(tb + 32, E + E_RF, ROWS, Wb + W16(M_VIS0), 32, 32, 32);
+    STAGE_END()
+    {
+      float o1[1];
+      epi_act_gemv<1>(tq + 0, Bias + B16(M_AW1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_AW2), 32, o1);
+      aw = sigmoidf(o1[0] + Wsm[SMB(M_AW2)]);
+    }
+    if (a.use_vis) {   // 4th decoder
+      epi_act_store(tq + 32, Bias + B16(M_VIS0), P + P_HDB, m, 4, ACT_ELU);
+      STAGE_BEGIN() umma::gemm_issue(tb + 0, P + P_HDB, ROWS, Wb + W16(M_VIS1), 32, 32, 32); STAGE_END()
       float o1[1];
       epi_act_gemv<1>(tq + 0, Bias + B16(M_VIS1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_VIS2), 32, o1);
       visd = sigmoidf(o1[0] + Wsm[SMB(M_VIS2)]);
@@ -350,13 +379,14 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
         d[0] = logf(hp / (visibility - hp + 1e-5f) + 1e-5f); d[1] = visibility; d[2] = hp;
       }
       float hv8[8] = {(hp - 0.5f) * 2.f, (visibility - 0.5f) * 2.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      umma::store_chunk(E + E_RF, ROWS, 4, m, hv8);
+      umma::store_chunk(E + E_RF, ROWS, 4, m, hv8);     // overwrites ray_dir_fc.0's output (its MMA completed in stage A)
+      zero_chunk(E + E_RF, 5, m);
     }
 
-    // ------------------------------------------------------------ stage 4/5: prob_embed 34 -> 32 (ReLU) -> 32
+    // ------------------------------------------------------------ prob_embed 34 -> 32 (ReLU) -> 32, neuray_fc fused
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_RF, ROWS, Wb + W16(M_PE0), 32, 32, 48); STAGE_END()
-    epi_act_store(tq + 0, Bias + B16(M_PE0), E + E_HD0, m, 4, ACT_RELU);
-    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HD0, ROWS, Wb + W16(M_PE1), 32, 32, 32); STAGE_END()
+    epi_act_store(tq + 0, Bias + B16(M_PE0), E + E_HDA, m, 4, ACT_RELU);
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HDA, ROWS, Wb + W16(M_PE1), 32, 32, 32); STAGE_END()
     {   // prob_embedding -> P (bf16 operand of base_fc.0) and, fused, neuray_fc 32 -> 8 (ELU) -> 1 (sigmoid) in fp32
       float h8[8];
       epi_act_gemv<8>(tq + 0, Bias + B16(M_PE1), P + P_NEU, m, 4, ACT_NONE, Wsm + SMW(M_NF0), 32, h8);
@@ -365,45 +395,26 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       for (int i = 0; i < 8; ++i) o = fmaf(elu1(h8[i] + Wsm[SMB(M_NF0) + i]), Wsm[SMW(M_NF1) + i], o);
       SF[SF_W0 * ROWS + m] = sigmoidf(o);
     }
-    umma::fence_before_sync();
-    wg_sync(wg);
-
-    // ------------------------------------------------------------ view pooling #1 (fused_mean_variance x2) -> XB blocks
-    {
-      float w0n[V];
-#pragma unroll
-      for (int vv = 0; vv < V; ++vv) w0n[vv] = SF[SF_W0 * ROWS + vv * T + t] * wgt;
-#pragma unroll 1
-      for (int c = 0; c < 5; ++c) {
-        float x[V][8];
-#pragma unroll
-        for (int vv = 0; vv < V; ++vv) umma::load_chunk(P, ROWS, c, vv * T + t, x[vv]);
-        float m0[8], v0[8], m1[8], v1[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int vv = 0; vv < V; ++vv) { a0 += x[vv][i] * w0n[vv]; a1 += x[vv][i] * wgt; }
-          float b0 = 0.f, b1 = 0.f;
-#pragma unroll
-          for (int vv = 0; vv < V; ++vv) {
-              b0 += w0n[vv] * ((x[vv][i] - a0) * (x[vv][i] - a0));
-              b1 += wgt * ((x[vv][i] - a1) * (x[vv][i] - a1));
-            }
-          m0[i] = a0; v0[i] = b0; m1[i] = a1; v1[i] = b1;
-        }
-        umma::store_chunk(E, ROWS, 0 + c, m, m0);
-        umma::store_chunk(E, ROWS, 5 + c, m, v0);
-        umma::store_chunk(E, ROWS, 10 + c, m, m1);
-        umma::store_chunk(E, ROWS, 15 + c, m, v1);
-      }
+    // ------------------------------------------------------------ base_fc.0 in three accumulating K-slices:
+    //   (a) per-row slice [rgb_feat' | prob_embedding | 0] = P (K = 80), issued now;
+    //   (b1) pooled [mean0 | var0], (b2) pooled [mean1 | var1] (K = 80 each) through the 10-chunk E region
+    umma::fence_smem_to_async(); umma::fence_before_sync(); wg_sync(wg);
+    if (m == 0) {
+      umma::fence_after_sync();
+      umma::gemm_issue(tb + 0, P, ROWS, Wb + W16(M_BASE0) + 20 * 64 * 16, 64, 64, 80);
     }
-
-    // ------------------------------------------------------------ stage 8: base_fc.0 (K = 240: pooled | rgb_feat | neuray)
-    STAGE_BEGIN() umma::gemm_issue(tb + 0, E, ROWS, Wb + W16(M_BASE0), 64, 64, 240); STAGE_END()
+    float w0n[V];
+#pragma unroll
+    for (int vv = 0; vv < V; ++vv) w0n[vv] = SF[SF_W0 * ROWS + vv * T + t] * wgt;
+    pool_views<V>(P, E, t, T, m, w0n);
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E, ROWS, Wb + W16(M_BASE0), 64, 64, 80, true); STAGE_END()
+#pragma unroll
+    for (int vv = 0; vv < V; ++vv) w0n[vv] = wgt;
+    pool_views<V>(P, E, t, T, m, w0n);
+    STAGE_BEGIN() umma::gemm_issue(tb + 0, E, ROWS, Wb + W16(M_BASE0) + 10 * 64 * 16, 64, 64, 80, true); STAGE_END()
     epi_act_store(tq + 0, Bias + B16(M_BASE0), E + E_H64, m, 8, ACT_ELU);
 
-    // ------------------------------------------------------------ stage 9: base_fc.2 -> x (fp32, column m of XF)
+    // ------------------------------------------------------------ base_fc.2 -> x (fp32, column m of XF = P region)
     STAGE_BEGIN() umma::gemm_issue(tb + 64, E + E_H64, ROWS, Wb + W16(M_BASE1), 32, 32, 64); STAGE_END()
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -415,9 +426,9 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
         XF[(8 * c + i) * ROWS + m] = xv;
         sx[i] = xv * wgt;
       }
-      umma::store_chunk(E + E_HV, ROWS, c, m, sx);
+      umma::store_chunk(E + E_HV, ROWS, c, m, sx);      // H64 is dead: its MMA completed
     }
-    // ------------------------------------------------------------ stage 10/11: vis_fc(x * weight) 32 -> 32 -> 33
+    // ------------------------------------------------------------ vis_fc(x * weight) 32 -> 32 -> 33
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV, ROWS, Wb + W16(M_VFC0), 32, 32, 32); STAGE_END()
     epi_act_store(tq + 0, Bias + B16(M_VFC0), E + E_HV2, m, 4, ACT_ELU);
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV2, ROWS, Wb + W16(M_VFC1), 48, 48, 32); STAGE_END()
@@ -436,14 +447,14 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
         umma::store_chunk(E + E_HV, ROWS, c, m, sx);
       }
     }
-    // ------------------------------------------------------------ stage 12/13: vis_fc2(x * vis) 32 -> 32 -> 1
+    // ------------------------------------------------------------ vis_fc2(x * vis) 32 -> 32 -> 1 (output layer fused)
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E + E_HV, ROWS, Wb + W16(M_V2_0), 32, 32, 32); STAGE_END()
     {
       float o1[1];
-      epi_act_gemv<1>(tq + 0, Bias + B16(M_V2_0), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_V2_1), 32, o1);   // vis_fc2.2 fused
+      epi_act_gemv<1>(tq + 0, Bias + B16(M_V2_0), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_V2_1), 32, o1);
       const float vis2 = sigmoidf(o1[0] + Wsm[SMB(M_V2_1)]);
       SF[SF_VIS2 * ROWS + m] = vis2;
-      // rgb_fc input [x(32), vis, ray_diff(4)] -> K = 48
+      // rgb_fc input [x(32), vis, ray_diff(4)] -> K = 48 in E chunks 4..9 (HV2 is dead)
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float xx[8];
@@ -455,7 +466,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       umma::store_chunk(E + E_RG, ROWS, 4, m, tail);
       zero_chunk(E + E_RG, 5, m);
     }
-    // ------------------------------------------------------------ stage 14: rgb_fc.0, overlapped with view pooling #2
+    // ------------------------------------------------------------ rgb_fc.0, overlapped with view pooling #2
     umma::fence_smem_to_async(); umma::fence_before_sync(); wg_sync(wg);
     if (m == 0) { umma::fence_after_sync(); umma::gemm_issue(tb + 0, E + E_RG, ROWS, Wb + W16(M_RGB0), 16, 16, 48); umma::commit(bar); }
     if (m < T) {   // weights = vis / (sum + 1e-8), mean / var of x over views, mean of weights -> F2
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
             const float e = expf(SF[SF_LOGIT * ROWS + vv * T + m] - mx);
             den += e;
             r += SF[SF_R * ROWS + vv * T + m] * e; gg += SF[SF_G * ROWS + vv * T + m] * e; b += SF[SF_B * ROWS + vv * T + m] * e;
-          }
+        }
         float* f2 = a.f2 + (size_t)tile * kF2 * T + m;
         f2[(size_t)(F2_RGB + 0) * T] = r / den; f2[(size_t)(F2_RGB + 1) * T] = gg / den; f2[(size_t)(F2_RGB + 2) * T] = b / den;
       }

@@ -40,7 +40,7 @@ constexpr Layer16 kLayers16[kNumLayers16] = {
     {"{dd}.vis_decoder.0", 32, 32, 32, 32, W16_PLAIN, 0},  {"{dd}.vis_decoder.2", 32, 32, 32, 32, W16_PLAIN, 0},
     {"{dd}.vis_decoder.4", 32, 1, 32, 1, W16_SMALL, 0},
     {"{agg}.prob_embed.0", 34, 32, 48, 32, W16_PLAIN, 0},  {"{agg}.prob_embed.2", 32, 32, 32, 32, W16_PLAIN, 0},
-    {"{agg}.agg_impl.ray_dir_fc.0", 4, 16, 16, 16, W16_PLAIN, 0},
+    {"{agg}.agg_impl.ray_dir_fc.0", 4, 16, 4, 16, W16_SMALL, 0},
     {"{agg}.agg_impl.ray_dir_fc.2", 16, 35, 16, 48, W16_RD2, 0},
     {"{agg}.agg_impl.neuray_fc.0", 32, 8, 32, 8, W16_SMALL, 0},
     {"{agg}.agg_impl.neuray_fc.2", 8, 1, 8, 1, W16_SMALL, 0},
