@@ -279,7 +279,7 @@ def main():
             "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.mlp_dtype == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "mlp": args.mlp_dtype + (" tcgen05 (fp32 accumulate, rtol 1e-2)" if args.mlp_dtype == "bf16" else " SIMT (rtol 1e-4)"), "views_per_s": 1e3 / ms_per_step, "rays_per_launch": net.rays_per_launch,
+            "config": {"workload": WORKLOAD, "mlp": args.mlp_dtype + (" tcgen05 (fp32 accumulate, rtol 1e-2)" if args.mlp_dtype == "bf16" else " SIMT (rtol 1e-4)"), "views_per_s": 1e3 / ms_per_step, "rays_per_launch": rays_per_launch(net),
                        "l2": "256 MiB flush buffer written between timed iterations", "sharding": f"{H // world} rows/rank",
                        "collective": "all_gather(rgb, depth)" if world > 1 else "none"},
             "clocks": sampler.summary(),
@@ -299,6 +299,10 @@ def main():
         dist.destroy_process_group()
 
 
+def rays_per_launch(net):
+    return int(net.rays_per_launch or (32768 if net.mlp_dtype == "bf16" else 4096))
+
+
 def time_stages(torch, net, que_d, ref_d, flush):
     """Device time of each of the three kernels of the coarse pass on one chunk of rays_per_launch rays."""
     from panogrf_b200 import _lib
@@ -306,7 +310,7 @@ def time_stages(torch, net, que_d, ref_d, flush):
     lib = _lib.load()
     cfg = net.cfg
     ctx = net._context(que_d, ref_d)
-    rn = min(int(net.rays_per_launch), que_d["coords"].shape[1])
+    rn = min(rays_per_launch(net), que_d["coords"].shape[1])
     coords = que_d["coords"][0, :rn].float().contiguous()
     dev = coords.device
     depth = coarse_depth_table(cfg, DN, cfg["use_disp"]).to(dev)
@@ -320,7 +324,7 @@ def time_stages(torch, net, que_d, ref_d, flush):
     torch.cuda.synchronize()
     for mask, name in names.items():
         ts = []
-        reps = 20                      # back-to-back launches inside one event pair: amortises the host launch path
+        reps = 5                       # back-to-back launches inside one event pair: amortises the host launch path
         for i in range(4):
             ctx["stage_mask"] = mask
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -388,7 +392,7 @@ def time_e2e(torch, net, que, ref, cfg, steps):
     a.pixel_colors = _lib.ptr(rgb_c)
     a.fine_dn, a.fine_u, a.fine_use_all, a.use_disp = DN, _lib.ptr(fine_u), 0, 1
     va.hierarchical, va.weights_fine, va.bias_val_fine = 1, _lib.ptr(wf), 0.05
-    va.rays_per_launch = int(net.rays_per_launch)
+    va.rays_per_launch = rays_per_launch(net)
     va.pixel_colors_fine, va.render_depth_fine = _lib.ptr(rgb), _lib.ptr(dep)
     h2d = sum(t.numel() * 4 for t in (coords, imgs, imf, rf, w2c, rng, c2w, depth, fine_u, wc, wf))
     if w16c is not None:

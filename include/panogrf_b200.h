@@ -146,6 +146,7 @@ typedef struct pgrf_render_args {
   float* feat_dbg;             /* (rfn,rn*dn,67) ray_feats(32), rgb(3), img_feats(32) of prj_dict, optional */
   int stage_mask;              /* 0 = all kernels; else bit0 rows, bit1 samples, bit2 rays (profiling; bf16: bit0|bit1 = fused MLP kernel) */
   int mlp_bf16;                /* 1 = bf16 tcgen05 MLP path (rtol 1e-2), 0 = fp32 SIMT parity path (rtol 1e-4) */
+  int* sched;                  /* optional device int[2]: dynamic tile counters of the bf16 kernels (zeroed by the call) */
   const void* weights16;       /* bf16 blob (pgrf_w16_blob_bytes bytes, layout from pgrf_w16_layer_info); needed when mlp_bf16 */
 } pgrf_render_args;
 

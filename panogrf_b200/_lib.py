@@ -107,7 +107,7 @@ class RenderArgs(ctypes.Structure):
         ("pixel_colors", _P), ("render_depth", _P), ("hit_prob", _P), ("density", _P), ("colors", _P),
         ("fine_depth", _P), ("fine_dn", _I), ("fine_u", _P), ("fine_use_all", _I), ("use_disp", _I),
         ("fine_inds", _P), ("prob_dbg", _P), ("prj_dbg", _P), ("feat_dbg", _P),
-        ("stage_mask", _I), ("mlp_bf16", _I), ("weights16", _P),
+        ("stage_mask", _I), ("mlp_bf16", _I), ("sched", _P), ("weights16", _P),
     ]
 
 

@@ -231,8 +231,21 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
   const int v = min(m / T, V - 1), t = m % T;
   const float wgt = 1.f / ((float)V + 1e-8f);
 
+  __shared__ int s_tile[kWG];
+  int static_tile = blockIdx.x * kWG + wg;
 #pragma unroll 1
-  for (int tile = blockIdx.x * kWG + wg; tile < p.n_tiles; tile += gridDim.x * kWG) {
+  while (true) {
+    // dynamic tile scheduler (one atomic per 128-row tile) when the caller provides a counter, else static striding
+    int tile;
+    if (a.sched) {
+      if (m == 0) s_tile[wg] = atomicAdd(a.sched + 0, 1);
+      wg_sync(wg);
+      tile = s_tile[wg];
+    } else {
+      tile = static_tile;
+      static_tile += gridDim.x * kWG;
+    }
+    if (tile >= p.n_tiles) break;
     long long g = (long long)tile * T + t;
     const bool row_valid = (m < M) && (g < p.total);
     if (g >= p.total) g = p.total - 1;

@@ -729,6 +729,7 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
   }
   const int mask = a.stage_mask ? a.stage_mask : 7;
   if (a.mlp_bf16) {
+    if (a.sched) PGRF_CUDA(cudaMemsetAsync(a.sched, 0, 2 * sizeof(int), st));
     if (mask & 3) {
       const int rc = launch_render_mlp_bf16(a, p.V, p.T, p.total, p.n_tiles, sms, st);
       if (rc != PGRF_OK) return rc;

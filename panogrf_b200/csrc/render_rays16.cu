@@ -121,8 +121,20 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
   const int rpt = p.rays_per_tile;
   const int Mv = rpt * dn;
 
+  __shared__ int s_tile[kWGr];
+  int static_tile = blockIdx.x * kWGr + wg;
 #pragma unroll 1
-  for (int tile = blockIdx.x * kWGr + wg; tile < p.n_tiles; tile += gridDim.x * kWGr) {
+  while (true) {
+    int tile;
+    if (a.sched) {   // dynamic tile scheduler
+      if (m == 0) s_tile[wg] = atomicAdd(a.sched + 1, 1);
+      wgr_sync(wg);
+      tile = s_tile[wg];
+    } else {
+      tile = static_tile;
+      static_tile += gridDim.x * kWGr;
+    }
+    if (tile >= p.n_tiles) break;
     const long long g0 = (long long)tile * Mv;
     long long g = g0 + min(m, Mv - 1);
     if (g >= p.total) g = p.total - 1;

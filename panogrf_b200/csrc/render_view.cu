@@ -162,6 +162,7 @@ extern "C" int pgrf_render_view_host(const pgrf_render_view_args* hv) {
       d.que_depth_fine = nullptr;
     }
     p.f1 = h.mlp_bf16 ? nullptr : (float*)dalloc((size_t)f1n * 4);
+    p.sched = h.mlp_bf16 ? (int*)dalloc(16) : nullptr;
     p.f2 = (float*)dalloc((size_t)f2n * 4);
     // device outputs for whatever the caller asked for
     struct Out { float** dev; float* host; size_t n; };

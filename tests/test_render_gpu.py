@@ -124,7 +124,7 @@ def test_render_full_view_chunking_and_properties():
     net = build_renderer(cfg, W)
     net.rays_per_launch = 1000          # ragged chunks
     a = net.render(cuda_dict(que), cuda_dict(ref2), False, keep_hit_prob=True)
-    net.rays_per_launch = 1 << 20
+    net.rays_per_launch = None
     b = net.render(cuda_dict(que), cuda_dict(ref2), False, keep_hit_prob=True)
     torch.cuda.synchronize()
     for k in a:
