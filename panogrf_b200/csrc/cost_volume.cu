@@ -129,12 +129,14 @@ __device__ __forceinline__ void point_uv(int dataset, float cx, float cy, float 
       break;
     }
   }
-  u = uu / PGRF_PI_F - 1.f;
-  v = 2.f * vv / PGRF_PI_F - 1.f;
+  // tensor / python-scalar is a multiplication by the fp32 reciprocal in torch's CUDA kernels; do the same
+  constexpr float kInvPi = 0.31830988618379067154f;
+  u = uu * kInvPi - 1.f;
+  v = 2.f * vv * kInvPi - 1.f;
 }
 
-template <int C, bool PLANAR, bool SINGLE, int JBT>
-__global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams p) {
+template <int C, bool PLANAR, bool SINGLE, int JBT, int MINB>
+__global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_kernel(const CvParams p) {
   constexpr int CG = C / 4;      // lanes (float4 channel groups) per pixel
   constexpr int PPS = 32 / CG;   // pixels per sub-iteration of phase B
   constexpr int NSUB = 32 / PPS; // sub-iterations to cover the warp's 32 pixels
@@ -202,6 +204,11 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams 
   const float4* lane_base = img4 + cg;
   const int row_f4 = p.W * CG;
   const bool use_div = p.divisor != 0.f;
+  // single swept view: the rotated ray is depth-invariant
+  const float hax = s_A[0][0] * rx + s_A[0][1] * ry + s_A[0][2] * rz;
+  const float hay = s_A[0][3] * rx + s_A[0][4] * ry + s_A[0][5] * rz;
+  const float haz = s_A[0][6] * rx + s_A[0][7] * ry + s_A[0][8] * rz;
+  const float hbx = s_A[0][9], hby = s_A[0][10], hbz = s_A[0][11];
   const size_t plane = (size_t)p.H * p.W;
   bool bad = false;
 
@@ -210,12 +217,17 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams 
     float depth;
     if (p.depth_volume) depth = (x < p.W) ? __ldg(p.depth_volume + ((size_t)b * p.D + d) * plane + (size_t)y * p.W + x) : 1.f;
     else depth = __ldg(p.depths + d);
-    for (int s = 0; s < p.n_src; ++s) {
-      const float* A = s_A[s];
-      const float ax = A[0] * rx + A[1] * ry + A[2] * rz;
-      const float ay = A[3] * rx + A[4] * ry + A[5] * rz;
-      const float az = A[6] * rx + A[7] * ry + A[8] * rz;
-      const float cx = fmaf(depth, ax, A[9]), cy = fmaf(depth, ay, A[10]), cz = fmaf(depth, az, A[11]);
+    for (int s = 0; s < (SINGLE ? 1 : p.n_src); ++s) {
+      float cx, cy, cz;
+      if (SINGLE) {
+        cx = fmaf(depth, hax, hbx); cy = fmaf(depth, hay, hby); cz = fmaf(depth, haz, hbz);
+      } else {
+        const float* A = s_A[s];
+        const float ax = A[0] * rx + A[1] * ry + A[2] * rz;
+        const float ay = A[3] * rx + A[4] * ry + A[5] * rz;
+        const float az = A[6] * rx + A[7] * ry + A[8] * rz;
+        cx = fmaf(depth, ax, A[9]); cy = fmaf(depth, ay, A[10]); cz = fmaf(depth, az, A[11]);
+      }
       float u, v;
       point_uv(p.dataset, cx, cy, cz, u, v);
       if (!(u >= -1.f && u <= 1.f && v >= -1.f && v <= 1.f) && x < p.W) bad = true;
@@ -317,6 +329,7 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(const CvParams 
 
 int g_cv_jb = 0;      // gathers batched per lane (4*JB 128-bit loads in flight); 0 = measured default per layout
 int g_cv_dchunk = 0;  // 0 = heuristic
+int g_cv_minb = 0;    // __launch_bounds__ min blocks per SM: 0 = default (5 blocks = 20 warps/SM), 1 = uncapped registers
 
 template <int C>
 static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
@@ -327,24 +340,28 @@ static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
   size_t smem = (size_t)kCvWarps * p.n_src * 32 * sizeof(TapRec);
   if (planar) smem += (size_t)kCvWarps * C * 33 * sizeof(float);
   const bool single = p.n_src == 1 && p.divisor == 0.f;
+#define PGRF_CV_LAUNCH1(PL, SG, J, MB)                                                                                \
+  do {                                                                                                                \
+    PGRF_CUDA(cudaFuncSetAttribute(cost_volume_kernel<C, PL, SG, J, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    cost_volume_kernel<C, PL, SG, J, MB><<<grid, kCvThreads, smem, st>>>(p);                                          \
+  } while (0)
 #define PGRF_CV_LAUNCH(PL, SG, J)                                                                                     \
   do {                                                                                                                \
-    PGRF_CUDA(cudaFuncSetAttribute(cost_volume_kernel<C, PL, SG, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    cost_volume_kernel<C, PL, SG, J><<<grid, kCvThreads, smem, st>>>(p);                                              \
+    if (g_cv_minb == 1) PGRF_CV_LAUNCH1(PL, SG, J, 1);                                                                \
+    else PGRF_CV_LAUNCH1(PL, SG, J, 5);                                                                               \
   } while (0)
-  const int jb = g_cv_jb ? g_cv_jb : (planar ? 4 : 2);   // B200 sweep, tools/time_cost_volume.py
+  const int jb = g_cv_jb ? g_cv_jb : 2;   // B200 sweep (tools/time_cost_volume.py): 8 gathers in flight per lane, <= 102 registers
   if (planar) {
     if (!single) PGRF_CV_LAUNCH(true, false, 2);
-    else if (jb == 2) PGRF_CV_LAUNCH(true, true, 2);
-    else if (jb == 8) PGRF_CV_LAUNCH(true, true, 8);
-    else PGRF_CV_LAUNCH(true, true, 4);
+    else if (jb == 4) PGRF_CV_LAUNCH(true, true, 4);
+    else PGRF_CV_LAUNCH(true, true, 2);
   } else {
     if (!single) PGRF_CV_LAUNCH(false, false, 2);
-    else if (jb == 2) PGRF_CV_LAUNCH(false, true, 2);
-    else if (jb == 8) PGRF_CV_LAUNCH(false, true, 8);
-    else PGRF_CV_LAUNCH(false, true, 4);
+    else if (jb == 4) PGRF_CV_LAUNCH(false, true, 4);
+    else PGRF_CV_LAUNCH(false, true, 2);
   }
 #undef PGRF_CV_LAUNCH
+#undef PGRF_CV_LAUNCH1
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
@@ -357,6 +374,7 @@ using namespace pgrf;
 extern "C" int pgrf_debug_set(const char* key, int value) {
   if (!strcmp(key, "cv_jb")) { g_cv_jb = value; return PGRF_OK; }
   if (!strcmp(key, "cv_dchunk")) { g_cv_dchunk = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_minb")) { g_cv_minb = value; return PGRF_OK; }
   set_error("pgrf_debug_set: unknown key %s", key);
   return PGRF_EINVAL;
 }

@@ -32,12 +32,12 @@ def run(B, H, W, C, D, layout, per_pixel=False, groups=0, S=2, iters=10):
 if __name__ == "__main__":
     from panogrf_b200 import _lib
     lib = _lib.load()
-    for jb in (2, 4, 8):
-        for dc in (0, 4, 8, 16, 32):
-            lib.pgrf_debug_set(b"cv_jb", jb); lib.pgrf_debug_set(b"cv_dchunk", dc)
-            print("jb", jb, "dchunk", dc)
+    for jb in (2, 4):
+        for mb in (0, 1):
+            lib.pgrf_debug_set(b"cv_jb", jb); lib.pgrf_debug_set(b"cv_minb", mb)
+            print("jb", jb, "minb", mb)
             run(1, 256, 512, 32, 64, "bdhwc"); run(1, 256, 512, 32, 64, "bdchw")
-    lib.pgrf_debug_set(b"cv_jb", 4); lib.pgrf_debug_set(b"cv_dchunk", 0)
+    lib.pgrf_debug_set(b"cv_jb", 0); lib.pgrf_debug_set(b"cv_minb", 0)
     for layout in ["bdhwc", "bdchw", "bcdhw"]:
         run(1, 256, 512, 32, 64, layout)
     run(1, 256, 512, 32, 64, "bdhwc", per_pixel=True)
