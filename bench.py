@@ -293,6 +293,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"8192 random rays of the view, oracle/render.py torch-CPU fp32, {t:.1f} s"}
         line["cost_volume"] = time_cost_volume(torch, pg, flush, peaks)
+        line["project_gather"] = time_project_gather(torch, que_d, ref_d, flush, peaks)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -408,6 +409,39 @@ def time_e2e(torch, net, que, ref, cfg, steps):
             times.append(dt)
     assert torch.isfinite(rgb).all() and float(rgb.abs().sum()) > 0
     return 1e3 * sum(times) / len(times), h2d, d2h
+
+
+def time_project_gather(torch, que_d, ref_d, flush, peaks):
+    """Stand-alone K2 (project_points_dict + get_img_feats): 65536 rays x 64 samples x 2 views, HBM roofline on its outputs."""
+    import types
+    from panogrf_b200 import render_ops as rops
+    dev = flush.device
+    rn, dn = 65536, DN
+    g = torch.Generator(device=dev).manual_seed(0)
+    dirs = torch.nn.functional.normalize(torch.randn(1, rn, 1, 3, device=dev, generator=g), dim=-1)
+    depth = torch.linspace(0.5, 15.0, dn, device=dev).view(1, 1, dn, 1)
+    pts = (dirs * depth).contiguous()                                   # (1,rn,dn,3) world points around the origin
+    spt = types.SimpleNamespace(dataset="m3d", height=H, width=W)
+    f = lambda: rops.project_points_dict(ref_d, pts, spt)
+    for _ in range(3):
+        out = f()
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = f()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    rows = rn * dn * RFN
+    alg = rows * (2 + 1 + 3 + 32 + 3 + 32) * 4 + rn * dn * 12
+    return {"workload": f"{rn} rays x {dn} samples x {RFN} views -> pts,depth,dir,ray_feats,rgb,img_feats (292 B/row); includes the "
+                        "NCHW->NHWC conversion of the three source maps done by the functional wrapper",
+            "rows_per_s": rows / ms * 1e3, "ms": ms,
+            "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "bytes_per_row": 292}}
 
 
 def time_cost_volume(torch, pg, flush, peaks):

@@ -181,6 +181,32 @@ PGRF_API int pgrf_render_view_host(const pgrf_render_view_args* args);
 /* (N,C,H,W) -> channels-last (N,H,W,Cpad), zero padded */
 PGRF_API int pgrf_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int Cpad, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone operators (the reference's functional API, network/render_ops.py); device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+/* project_points_dict (render_ops.py:234-257) + get_img_feats (renderer.py:180-188): pts (pn,3) world points ->
+ * per view: pixel (rfn,pn,2), depth (rfn,pn), dir (rfn,pn,3), ray_feats (rfn,pn,32), rgb (rfn,pn,3), img_feats (rfn,pn,32, optional).
+ * Maps channels-last like pgrf_render_args. */
+PGRF_API int pgrf_project_gather_fwd(const float* pts, long long pn, const float* w2c, int rfn, int dataset, int H, int W,
+                                     const float* imgs_cl, int img_h, int img_w, const float* img_feats_cl, int if_h, int if_w,
+                                     const float* ray_feats_cl, int rf_h, int rf_w, float* out_pix, float* out_depth,
+                                     float* out_dir, float* out_ray_feats, float* out_rgb, float* out_img_feats, void* stream);
+/* alpha_values2hit_prob (render_ops.py:145-153) [+ renderer.py:214-218,302-304]: pass `alpha` (rn,dn), or `density` (rn,dn) for
+ * alpha = 1-exp(-relu(density)); optional colors (rn,dn,3) -> pixel_colors (rn,3); optional depth -> render_depth (rn). */
+PGRF_API int pgrf_composite_fwd(const float* density, const float* alpha, const float* colors, const float* depth,
+                                int depth_ray_stride, int rn, int dn, float* hit_prob, float* pixel_colors, float* render_depth,
+                                void* stream);
+/* sample_fine_depth (render_ops.py:413-473) with the deterministic u table; fine_out (rn, fine_dn [+dn if use_all]);
+ * sort_out = 1 also applies the sort of renderer.py:470-472; inds_out (rn,fine_dn) optional searchsorted indices. */
+PGRF_API int pgrf_fine_sample_fwd(const float* depth, int depth_ray_stride, const float* hit_prob, const float* u_table,
+                                  float near_depth, float far_depth, int inv_mode, int rn, int dn, int fine_dn, int sort_out,
+                                  int use_all, float* fine_out, int* inds_out, void* stream);
+/* depth hypotheses of the MVS net (pipeline3_model.py:723-733,774-815): out (B,n_mono+n_linear,h,w) = per-pixel sorted
+ * [clamp(ref_mu + k_sigma[i], min, max)] ++ linear[]; k_sigma and linear ascending (device arrays, computed by the host
+ * with the reference's own ops so they are bit-identical). */
+PGRF_API int pgrf_depth_hypotheses_fwd(const float* ref_mu, int B, int h, int w, const float* k_sigma, int n_mono,
+                                       const float* linear, int n_linear, float min_depth, float max_depth, float* out, void* stream);
+
 /* Weight blob layout: one entry per (slice of a) Linear layer of [fine_]dist_decoder / [fine_]agg_net.
  * name uses "{dd}" / "{agg}" placeholders; the weight slice [N, k_begin:k_begin+K] is stored
  * transposed (k-major) with rows padded to Npad at w_offset, the bias (Npad) at b_offset. */

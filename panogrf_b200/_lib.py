@@ -129,6 +129,11 @@ SIGNATURES.update({
     "pgrf_render_view_fwd": (_I, [ctypes.POINTER(RenderViewArgs), _P]),
     "pgrf_render_view_host": (_I, [ctypes.POINTER(RenderViewArgs)]),
     "pgrf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "pgrf_project_gather_fwd": (_I, [_P, ctypes.c_longlong, _P, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I,
+                                      _P, _P, _P, _P, _P, _P, _P]),
+    "pgrf_composite_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "pgrf_fine_sample_fwd": (_I, [_P, _I, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "pgrf_depth_hypotheses_fwd": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _F, _F, _P, _P]),
     "pgrf_weight_blob_floats": (_I, []),
     "pgrf_weight_num_layers": (_I, []),
     "pgrf_weight_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI, _PI]),

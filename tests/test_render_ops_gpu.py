@@ -1,0 +1,88 @@
+"""GPU parity of the stand-alone operators (reference functional API, network/render_ops.py) against the oracle."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import cases  # noqa: E402
+from test_oracle_render import split_golden  # noqa: E402
+from util import assert_close, load_golden  # noqa: E402
+
+from oracle import cost_volume as ocv  # noqa: E402
+from oracle import render as orender  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["render_m3d_2src", "render_replica", "render_residential", "render_coffee", "render_m3d_4src_all"])
+def test_project_points_dict(name):
+    from panogrf_b200 import render_ops as rops
+    cfg, _, _ = cases.make_render_inputs(name)
+    que, ref, W, _ = split_golden(load_golden(name))
+    rn, dn = que["coords"].shape[1], cfg["depth_sample_num"]
+    depth = orender.sample_depth(cfg["min_depth"], cfg["max_depth"], rn, dn, cfg["use_disp"])
+    pts, _ = orender.depth2points_spherical(cfg["dataset_name"], cfg["height"], cfg["width"], que["c2w"], que["coords"], depth)
+    o = orender.render_by_depth(cfg, W, que, ref, depth, False, return_prj=True)["prj"]
+    spt = types.SimpleNamespace(dataset=cfg["dataset_name"], height=cfg["height"], width=cfg["width"])
+    refc = {k: v.cuda() for k, v in ref.items()}
+    got = rops.project_points_dict(refc, pts.cuda(), spt)
+    torch.cuda.synchronize()
+    tol = {"pts": 2e-3, "depth": 1e-5, "dir": 1e-5, "ray_feats": 2e-4, "rgb": 2e-5, "img_feats": 2e-4}
+    for k, atol in tol.items():
+        assert got[k].shape == o[k].shape, k
+        assert_close(got[k], o[k], rtol=1e-4, atol=atol, what=f"{name}/{k}")
+
+
+def test_alpha_compositing_and_fine_sampling_bit_exact_bins():
+    from panogrf_b200 import render_ops as rops
+    gen = torch.Generator().manual_seed(7)
+    rn, dn = 333, 64
+    alpha = torch.rand(1, rn, dn, generator=gen) ** 3
+    hit = rops.alpha_values2hit_prob(alpha.cuda()).cpu()
+    assert torch.equal(hit, orender.alpha_values2hit_prob(alpha))          # same sequential fp32 order -> identical bits
+    density = torch.randn(1, rn, dn, generator=gen)
+    colors = torch.rand(1, rn, dn, 3, generator=gen)
+    depth = orender.sample_depth(0.5, 15.0, rn, dn, True)
+    h, pix, rd = rops.composite(density.cuda(), colors.cuda(), depth.cuda())
+    eh, ep, ed = orender.composite(density, colors, depth)
+    assert_close(h, eh, rtol=1e-5, atol=1e-7, what="hit")
+    assert_close(pix, ep, rtol=1e-4, atol=1e-6, what="pixel")
+    assert_close(rd, ed, rtol=1e-4, atol=1e-5, what="depth")
+    args = {"use_disp": True}
+    rng = torch.tensor([[0.5, 15.0]])
+    hit2 = eh.clone()
+    hit2[:, :10] = 0                                                        # uniform pdf rows
+    hit2[:, 10:20, 5] = 40.0                                                # dominant bin (denom < 1e-5 branch)
+    fine, inds = rops.sample_fine_depth(args, depth.cuda(), hit2.cuda(), rng, 64, False, return_indices=True)
+    efine, einds = orender.sample_fine_depth(depth, hit2, rng, 64, True, return_indices=True)
+    assert torch.equal(inds.cpu(), einds), "searchsorted bin indices differ"
+    assert_close(fine, efine, rtol=1e-5, atol=0.0, what="fine depths")
+    fine_lin = rops.sample_fine_depth({"use_disp": False}, depth.cuda(), hit2.cuda(), rng, 32, False)
+    assert_close(fine_lin, orender.sample_fine_depth(depth, hit2, rng, 32, False), rtol=1e-5, atol=0.0, what="fine/no-disp")
+
+
+def test_sample_depth_and_inv_dists():
+    from panogrf_b200 import render_ops as rops
+    args = {"min_depth": 0.5, "max_depth": 15.0}
+    coords = torch.zeros(1, 7, 2, device="cuda")
+    for use_disp in (True, False):
+        d, dist = rops.sample_depth(args, coords, 64, False, use_disp)
+        assert torch.equal(d.cpu(), orender.sample_depth(0.5, 15.0, 7, 64, use_disp))
+        assert float(dist[0, 0, -1]) > 9e5
+    rng = torch.tensor([[0.5, 15.0]])
+    inv = rops.depth2inv_dists(d, rng.cuda())
+    assert_close(inv, orender.depth2inv_dists(d.cpu(), rng), rtol=1e-6, atol=1e-7, what="inv dists")
+
+
+def test_depth_hypotheses_bit_exact():
+    from panogrf_b200 import render_ops as rops
+    gen = torch.Generator().manual_seed(3)
+    mu = torch.rand(2, 1, 24, 40, generator=gen) * 11 - 0.5        # also outside [min,max] -> clamps
+    ks = ocv.magnet_k_list(5, 3)
+    got = rops.mono_guided_hypotheses(mu.cuda(), ks, 0.5, 0.1, 10.0, 59).cpu()
+    expect = ocv.mono_guided_hypotheses(mu, ks, 0.5, 0.1, 10.0, 59)
+    assert got.shape == (2, 64, 24, 40)
+    assert torch.equal(got, expect), "hypothesis values / order differ"
