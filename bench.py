@@ -437,8 +437,7 @@ def time_project_gather(torch, que_d, ref_d, flush, peaks):
     ms = sorted(ts)[len(ts) // 2]
     rows = rn * dn * RFN
     alg = rows * (2 + 1 + 3 + 32 + 3 + 32) * 4 + rn * dn * 12
-    return {"workload": f"{rn} rays x {dn} samples x {RFN} views -> pts,depth,dir,ray_feats,rgb,img_feats (292 B/row); includes the "
-                        "NCHW->NHWC conversion of the three source maps done by the functional wrapper",
+    return {"workload": f"{rn} rays x {dn} samples x {RFN} views -> pts,depth,dir,ray_feats,rgb,img_feats (292 B/row)",
             "rows_per_s": rows / ms * 1e3, "ms": ms,
             "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "bytes_per_row": 292}}

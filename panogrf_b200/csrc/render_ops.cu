@@ -13,7 +13,7 @@ namespace pgrf {
 // K2: projection + gathers.  CTA = 256 threads = 64 points x up to 4 views per tile.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPgThreads = 256;
-constexpr int kPgPoints = 64;   // points per tile
+constexpr int kPgMaxViews = 4;
 
 struct PgRec {
   int off_rf, off_if, off_im;   // north-west texel index inside the stacked (rfn*h*w) map
@@ -50,7 +50,8 @@ __device__ __forceinline__ float4 blend4(const float4* __restrict__ base, int sx
 __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgParams p) {
   __shared__ PgRec rec[kPgThreads];
   const int tid = threadIdx.x;
-  const int rows = kPgPoints * p.rfn;                      // (view, point) rows of this tile, <= 256
+  const int kPgPoints = kPgThreads / p.rfn;                // points per tile: all 256 threads own a (view, point) row
+  const int rows = kPgPoints * p.rfn;
   for (long long tile = blockIdx.x; tile * kPgPoints < p.pn; tile += gridDim.x) {
     const long long p0 = tile * kPgPoints;
     // ---- phase 1: thread = (view, point): w2c, spherical, pixel, direction, three footprints
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgPara
     __syncthreads();
     // ---- phase 2: lane = (row, float4 channel group): 8 lanes fetch one 128-byte texel line per tap and write one
     //      128-byte output row (coalesced both ways)
+#pragma unroll 2
     for (int it = tid; it < rows * 8; it += kPgThreads) {
       const int rrow = it >> 3, cg = it & 7;
       const int v = rrow / kPgPoints;
@@ -265,8 +267,9 @@ extern "C" int pgrf_project_gather_fwd(const float* pts, long long pn, const flo
   p.out_if = out_img_feats;
   p.pn = pn; p.rfn = rfn; p.dataset = dataset; p.H = H; p.W = W; p.img_h = img_h; p.img_w = img_w;
   p.if_h = if_h; p.if_w = if_w; p.rf_h = rf_h; p.rf_w = rf_w;
-  const long long tiles = (pn + kPgPoints - 1) / kPgPoints;
-  const int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+  const int pts_per_tile = kPgThreads / rfn;
+  const long long tiles = (pn + pts_per_tile - 1) / pts_per_tile;
+  const int grid = (int)(tiles < 148 * 16 ? tiles : 148 * 16);
   project_gather_kernel<<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p);
   count_launch();
   PGRF_CUDA(cudaGetLastError());

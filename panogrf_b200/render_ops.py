@@ -14,6 +14,18 @@ def _f32(t):
     return t.contiguous().float()
 
 
+_CL_CACHE = {}
+
+
+def _channels_last_cached(name, t, pad_to=None):
+    """NCHW -> channels-last copy, reused while the caller keeps passing the same unmodified tensor."""
+    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+    hit = _CL_CACHE.get(name)
+    if hit is None or hit[0] != key:
+        _CL_CACHE[name] = (key, to_channels_last(t, pad_to), t)
+    return _CL_CACHE[name][1]
+
+
 def sample_depth(args, coords, sample_num, random_sample, use_disp=True):
     """render_ops.py:292-339 (deterministic branch): (qn,rn,dn) depths and the (qn,rn,dn) forward differences."""
     if random_sample:
@@ -98,10 +110,10 @@ def project_points_dict(ref_imgs_info, que_pts, spt_utils, with_img_feats=True):
     imgs = ref_imgs_info["imgs"]
     rfn, _, ih, iw = imgs.shape
     dev = pts.device
-    imgs_cl = to_channels_last(imgs, 4)
-    rf_cl = to_channels_last(ref_imgs_info["ray_feats"])
+    imgs_cl = _channels_last_cached("imgs", imgs, 4)
+    rf_cl = _channels_last_cached("ray_feats", ref_imgs_info["ray_feats"])
     has_if = with_img_feats and "img_feats" in ref_imgs_info
-    if_cl = to_channels_last(ref_imgs_info["img_feats"]) if has_if else None
+    if_cl = _channels_last_cached("img_feats", ref_imgs_info["img_feats"]) if has_if else None
     w2c = _f32(ref_imgs_info["w2c"]).to(dev)
     e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
     pix, dep, dr, rf, rgb = e(rfn, pn, 2), e(rfn, pn, 1), e(rfn, pn, 3), e(rfn, pn, 32), e(rfn, pn, 3)
