@@ -190,6 +190,7 @@ class NeuralRayBaseRenderer(nn.Module):
         self._blob_cache = {}
         self._ws = {}
         self._cl_cache = {}
+        self._tables = {}
         #: "fp32": SIMT parity path (rtol 1e-4); "bf16": tcgen05 tensor-core MLP (bf16 operands, fp32 accumulate, rtol 1e-2)
         self.mlp_dtype = str(self.cfg.get("mlp_dtype", "fp32"))
         if self.mlp_dtype not in ("fp32", "bf16"):
@@ -283,7 +284,7 @@ class NeuralRayBaseRenderer(nn.Module):
         assert c2w.shape[0] == 1, "que_imgs_info c2w.shape[0]=1"                 # render_ops.py:89
         if ref_imgs_info["ray_feats"].shape[1] != 32 or ref_imgs_info["img_feats"].shape[1] != 32:
             raise _lib.PanoGRFError("ray_feats / img_feats must have 32 channels")
-        dr = que_imgs_info["depth_range"].float().cpu()
+        dr = self._cached_scalars("que_range", que_imgs_info["depth_range"])
         return {
             "rfn": imgs.shape[0],
             "imgs": self._cached_cl("imgs", imgs, 4),
@@ -292,10 +293,26 @@ class NeuralRayBaseRenderer(nn.Module):
             "w2c": ref_imgs_info["w2c"].float().contiguous().to(dev),
             "ref_range": ref_imgs_info["depth_range"].float().contiguous().to(dev),
             "c2w": c2w.float().reshape(3, 4).contiguous().to(dev),
-            "que_near": float(dr[0, 0]), "que_far": float(dr[0, 1]),
-            "fine_u": fine_u_table(int(self.cfg["fine_depth_sample_num"])).to(dev),
+            "que_near": dr[0], "que_far": dr[1],
+            "fine_u": self._cached_table(("fine_u", int(self.cfg["fine_depth_sample_num"])), dev,
+                                         lambda: fine_u_table(int(self.cfg["fine_depth_sample_num"]))),
             "ws": {},
         }
+
+    def _cached_scalars(self, name, t):
+        """(near, far) of a (1,2) depth_range tensor as python floats without a device sync on every call."""
+        key = (t.data_ptr(), t._version, str(t.device))
+        hit = self._cl_cache.get(name)
+        if hit is None or hit[0] != key:
+            v = t.detach().float().cpu()
+            self._cl_cache[name] = (key, (float(v[0, 0]), float(v[0, 1])), t)
+        return self._cl_cache[name][1]
+
+    def _cached_table(self, key, dev, make):
+        k = (key, str(dev))
+        if k not in self._tables:
+            self._tables[k] = make().to(dev)
+        return self._tables[k]
 
     def _sched(self, dev):
         ws = self._ws.setdefault(str(dev), {})
@@ -417,7 +434,8 @@ class NeuralRayBaseRenderer(nn.Module):
         a.rfn, a.rn, a.dn = ctx["rfn"], rn, dn
         a.use_vis = int(bool(self.dist_decoder.cfg["use_vis"]))
         a.bias_val = float(self.dist_decoder.cfg["bias_val"])
-        depth_table = coarse_depth_table(cfg, dn, cfg["use_disp"]).to(dev)
+        depth_table = self._cached_table(("coarse", dn, bool(cfg["use_disp"]), float(cfg["min_depth"]), float(cfg["max_depth"])),
+                                         dev, lambda: coarse_depth_table(cfg, dn, cfg["use_disp"]))
         a.coords, a.depth, a.depth_ray_stride = _lib.ptr(coords2), _lib.ptr(depth_table), 0
         a.que_c2w, a.que_near, a.que_far = _lib.ptr(ctx["c2w"]), ctx["que_near"], ctx["que_far"]
         a.ref_w2c, a.ref_depth_range = _lib.ptr(ctx["w2c"]), _lib.ptr(ctx["ref_range"])
