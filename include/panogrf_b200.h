@@ -207,6 +207,56 @@ PGRF_API int pgrf_fine_sample_fwd(const float* depth, int depth_ray_stride, cons
 PGRF_API int pgrf_depth_hypotheses_fwd(const float* ref_mu, int B, int h, int w, const float* k_sigma, int n_mono,
                                        const float* linear, int n_linear, float min_depth, float max_depth, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Depth-prior sample placement ("diner" branch of render_impl, network/renderer.py:570-600, :318-355):
+ *   sample_depth(n_candidates, linear)            network/render_ops.py:292-339
+ *   project_points_dict_diner                     network/render_ops.py:260-290
+ *   sample_depthguided / fill_up_uniform_samples  network/original_depth_guided_sample.py:45-297 / 333-366
+ * fused into one kernel: every candidate depth of a ray is projected into every source panorama, the MVS depth /
+ * variance / normal priors are gathered (bilinear, border), the surface likelihood is taken as the max over views, the
+ * n_samples - n_gaussian most likely candidates are kept (ties: lower candidate first), n_gaussian samples are drawn
+ * around the occlusion-aware mean, empty slots are filled uniformly, the optional uniform samples are appended, and the
+ * result is sorted.  The reference's two random draws are explicit inputs (fill_rand, gauss).  Device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pgrf_diner_args {
+  int dataset, H, W;             /* ERP convention, cfg height / width */
+  int rfn;
+  long long rn;
+  int n_candidates, n_samples, n_gaussian, n_uniform;
+  int include_norm;              /* cfg backface_culling: keep candidates with dot(R_v * ray, normal) <= 0 only */
+  int sigma_is_var;              /* 1: sigma = sqrt(uncert) (reference default var=True), 0: sigma = uncert */
+  float diner_sigma;             /* > 0: constant sigma (cfg diner_sigma) */
+  float cand_step;               /* fp32((max_depth - min_depth) / n_candidates), computed by the host */
+  float min_depth, max_depth, depth_diff_max;
+  const float* coords;           /* (rn,2) pixel (x,y) */
+  const float* cand_depth;       /* (n_candidates) shared by all rays (cand_ray_stride = 0) or (rn,n_candidates) */
+  long long cand_ray_stride;
+  const float* que_c2w;          /* (3,4) */
+  const float* ref_w2c;          /* (rfn,3,4) */
+  const float* mvs_depth;        /* (rfn,1,map_h,map_w) NCHW, as ref_imgs_info['mvs_depth'] */
+  const float* mvs_uncert;       /* (rfn,1,map_h,map_w) */
+  const float* mvs_normal;       /* (rfn,3,map_h,map_w) or NULL when include_norm = 0 */
+  int map_h, map_w, img_h, img_w;
+  const float* fill_rand;        /* (rn,n_samples) U[0,1) */
+  const float* gauss;            /* (rn,n_gaussian) N(0,1), NULL when n_gaussian = 0 */
+  const float* uniform_depth;    /* (n_uniform) appended to every ray (cfg contain_uniform), NULL when n_uniform = 0 */
+  float* out_depth;              /* (rn, n_samples + n_uniform), ascending */
+  float* likelihood;             /* optional (rn,n_candidates): max-over-views likelihood of every candidate */
+  /* dict variant (sample_depthguided called on a precomputed project_points_dict_diner result); all NULL for the fused path */
+  const float* prj_mu;           /* (rfn,rn,n_candidates) */
+  const float* prj_uncert;       /* (rfn,rn,n_candidates) */
+  const float* prj_depth;        /* (rfn,rn,n_candidates) */
+  const float* prj_normal;       /* (rfn,rn,n_candidates,3) */
+  const float* que_dir;          /* (rn,n_candidates,3) */
+} pgrf_diner_args;
+PGRF_API int pgrf_depth_guided_sample_fwd(const pgrf_diner_args* args, void* stream);
+/* project_points_dict_diner (render_ops.py:260-290): pts (pn,3) -> pixel (rfn,pn,2), depth (rfn,pn), gathered mvs depth
+ * (rfn,pn), variance (rfn,pn), normal (rfn,pn,3; optional) */
+PGRF_API int pgrf_project_gather_diner_fwd(const float* pts, long long pn, const float* w2c, int rfn, int dataset, int H, int W,
+                                           const float* mvs_depth, const float* mvs_uncert, const float* mvs_normal, int map_h,
+                                           int map_w, int img_h, int img_w, float* out_pix, float* out_depth, float* out_mu,
+                                           float* out_uncert, float* out_normal, void* stream);
+
 /* Weight blob layout: one entry per (slice of a) Linear layer of [fine_]dist_decoder / [fine_]agg_net.
  * name uses "{dd}" / "{agg}" placeholders; the weight slice [N, k_begin:k_begin+K] is stored
  * transposed (k-major) with rows padded to Npad at w_offset, the bias (Npad) at b_offset. */

@@ -121,9 +121,27 @@ class RenderViewArgs(ctypes.Structure):
     ]
 
 
+class DinerArgs(ctypes.Structure):
+    """Mirror of `pgrf_diner_args` (depth-prior sample placement)."""
+    _fields_ = [
+        ("dataset", _I), ("H", _I), ("W", _I), ("rfn", _I), ("rn", ctypes.c_longlong),
+        ("n_candidates", _I), ("n_samples", _I), ("n_gaussian", _I), ("n_uniform", _I),
+        ("include_norm", _I), ("sigma_is_var", _I), ("diner_sigma", _F), ("cand_step", _F),
+        ("min_depth", _F), ("max_depth", _F), ("depth_diff_max", _F),
+        ("coords", _P), ("cand_depth", _P), ("cand_ray_stride", ctypes.c_longlong),
+        ("que_c2w", _P), ("ref_w2c", _P), ("mvs_depth", _P), ("mvs_uncert", _P), ("mvs_normal", _P),
+        ("map_h", _I), ("map_w", _I), ("img_h", _I), ("img_w", _I),
+        ("fill_rand", _P), ("gauss", _P), ("uniform_depth", _P), ("out_depth", _P), ("likelihood", _P),
+        ("prj_mu", _P), ("prj_uncert", _P), ("prj_depth", _P), ("prj_normal", _P), ("que_dir", _P),
+    ]
+
+
 _PI = ctypes.POINTER(_I)
 _PLL = ctypes.POINTER(ctypes.c_longlong)
 SIGNATURES.update({
+    "pgrf_depth_guided_sample_fwd": (_I, [ctypes.POINTER(DinerArgs), _P]),
+    "pgrf_project_gather_diner_fwd": (_I, [_P, ctypes.c_longlong, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I,
+                                           _P, _P, _P, _P, _P, _P]),
     "pgrf_render_pass_fwd": (_I, [ctypes.POINTER(RenderArgs), _P]),
     "pgrf_render_workspace": (_I, [_I, ctypes.c_longlong, _PLL, _PLL]),
     "pgrf_render_view_fwd": (_I, [ctypes.POINTER(RenderViewArgs), _P]),

@@ -1,0 +1,327 @@
+// Depth-prior sample placement of the render path ("diner" branch, network/renderer.py:570-600 and :318-355):
+//   project_points_dict_diner                     network/render_ops.py:260-290
+//   sample_depthguided / fill_up_uniform_samples  network/original_depth_guided_sample.py:45-297 / 333-366
+// One CTA per ray walks the ray's candidate depths (typically 1000): project into every source panorama, gather the
+// MVS depth / variance / normal priors (bilinear, border padding), surface likelihood = max over views, compact the
+// few candidates with non-zero likelihood, keep the most likely ones (shared-memory bitonic sort only when more survive
+// than there are slots), draw the Gaussian samples, fill empty slots, append the uniform samples, sort, write.
+// Nothing but the (rn, n_samples) result reaches HBM; the reference materialises (rfn, rn, n_candidates, 7) floats.
+#include "render_device.cuh"
+
+namespace pgrf {
+
+constexpr int kDgThreads = 128;
+constexpr int kDgMaxCand = 4096;
+constexpr int kDgMaxOut = 512;
+
+__device__ __forceinline__ float tap1(const float* __restrict__ m, const Footprint& f, int fw) {
+  const float nw = __ldg(m + f.off), ne = __ldg(m + f.off + f.dx);
+  const float sw = __ldg(m + f.off + f.dy * fw), se = __ldg(m + f.off + f.dy * fw + f.dx);
+  const float tx1 = 1.f - f.tx, ty1 = 1.f - f.ty;
+  float o = nw * (tx1 * ty1);
+  o = fmaf(ne, f.tx * ty1, o);
+  o = fmaf(sw, tx1 * f.ty, o);
+  o = fmaf(se, f.tx * f.ty, o);
+  return o;
+}
+
+// original_depth_guided_sample.py:80-90,180-196 for one (view, candidate)
+__device__ __forceinline__ float surface_likelihood(const pgrf_diner_args& a, float mu, float uncert, float pd, float cosv) {
+  const bool ok = fabsf(mu - pd) < a.depth_diff_max && (!a.include_norm || cosv <= 0.f);
+  if (!ok) return 0.f;
+  const float sigma = a.diner_sigma > 0.f ? a.diner_sigma : (a.sigma_is_var ? sqrtf(uncert) : uncert);
+  const float half = a.cand_step / 2.f;
+  const float s2 = __fmul_rn(sigma, 1.41421356237309504880f);
+  const float x1 = (pd + half - mu) / s2;
+  const float x0 = (pd - half - mu) / s2;
+  return 0.5f * fabsf(erff(x1) - erff(x0));
+}
+
+template <typename T, typename Less>
+__device__ __forceinline__ void bitonic_sort(T* a, int n, Less less) {   // n = power of two, all threads of the CTA
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const T x = a[i], y = a[ixj];
+          if (less(y, x) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {   // scratch: 4 floats
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return scratch[0] + scratch[1] + scratch[2] + scratch[3];
+}
+
+__device__ __forceinline__ int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+__global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_diner_args a, int nc_pad, int nc_pow2) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm);                 // [nc_pow2]
+  float* lik = reinterpret_cast<float*>(keys + nc_pow2);                                 // [nc_pad]
+  float* opq = lik + nc_pad;                                                             // [nc_pad] (n_gaussian > 0)
+  float* z = opq + nc_pad;                                                               // [out_pow2]
+  __shared__ int s_count;
+  __shared__ float s_red[4];
+  const int tid = threadIdx.x;
+  const int nc = a.n_candidates, ns = a.n_samples, ng = a.n_gaussian, nu = a.n_uniform;
+  const int keep = ns - ng;
+  const int n_out = ns + nu;
+  const int out_pow2 = next_pow2(n_out), ns_pow2 = next_pow2(ns);
+  const bool from_dict = a.prj_mu != nullptr;
+
+  for (long long ray = blockIdx.x; ray < a.rn; ray += gridDim.x) {
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const float* cand = a.cand_depth + ray * a.cand_ray_stride;
+    // ---- ray in world space (render_ops.py:76-106)
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
+    if (!from_dict) {
+      const float cx = __ldg(a.coords + 2 * ray), cy = __ldg(a.coords + 2 * ray + 1);
+      float dx, dy, dz;
+      equi_unit_dir(a.dataset, (float)(long long)cx, (float)(long long)cy, a.H, a.W, dx, dy, dz);
+      const float* c = a.que_c2w;
+      r0 = c[0] * dx + c[1] * dy + c[2] * dz;
+      r1 = c[4] * dx + c[5] * dy + c[6] * dz;
+      r2 = c[8] * dx + c[9] * dy + c[10] * dz;
+      o0 = c[3]; o1 = c[7]; o2 = c[11];
+      const float rn = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+      u0 = r0 / rn; u1 = r1 / rn; u2 = r2 / rn;             // = -que_dir (original_depth_guided_sample.py:112-114)
+    }
+    const size_t map_px = (size_t)a.map_h * a.map_w;
+    // ---- phase 1: likelihood of every candidate, max over views; survivors are compacted as sortable keys
+    for (int i = tid; i < nc; i += kDgThreads) {
+      float best = 0.f;
+      if (from_dict) {
+        const float* qd = a.que_dir + ((size_t)ray * nc + i) * 3;
+        const float q0 = -__ldg(qd), q1 = -__ldg(qd + 1), q2 = -__ldg(qd + 2);
+        for (int v = 0; v < a.rfn; ++v) {
+          const size_t row = ((size_t)v * a.rn + ray) * nc + i;
+          float cosv = 0.f;
+          if (a.include_norm) {
+            const float* w = a.ref_w2c + 12 * v;
+            const float d0 = w[0] * q0 + w[1] * q1 + w[2] * q2;
+            const float d1 = w[4] * q0 + w[5] * q1 + w[6] * q2;
+            const float d2 = w[8] * q0 + w[9] * q1 + w[10] * q2;
+            const float* n = a.prj_normal + 3 * row;
+            cosv = d0 * __ldg(n) + d1 * __ldg(n + 1) + d2 * __ldg(n + 2);
+          }
+          best = fmaxf(best, surface_likelihood(a, __ldg(a.prj_mu + row), __ldg(a.prj_uncert + row), __ldg(a.prj_depth + row), cosv));
+        }
+      } else {
+        const float t = __ldg(cand + i);
+        const float p0 = o0 + r0 * t, p1 = o1 + r1 * t, p2 = o2 + r2 * t;
+        for (int v = 0; v < a.rfn; ++v) {
+          const float* w = a.ref_w2c + 12 * v;
+          const float pc0 = w[0] * p0 + w[1] * p1 + w[2] * p2 + w[3];
+          const float pc1 = w[4] * p0 + w[5] * p1 + w[6] * p2 + w[7];
+          const float pc2 = w[8] * p0 + w[9] * p1 + w[10] * p2 + w[11];
+          float pd, px, py;
+          cam_to_equi(a.dataset, pc0, pc1, pc2, a.H, a.W, pd, px, py);
+          const Footprint f = border_footprint(px, py, a.img_h, a.img_w, a.map_h, a.map_w);
+          const float mu = tap1(a.mvs_depth + v * map_px, f, a.map_w);
+          if (!(fabsf(mu - pd) < a.depth_diff_max)) continue;            // the common case: far from the prior surface
+          const float uncert = tap1(a.mvs_uncert + v * map_px, f, a.map_w);
+          float cosv = 0.f;
+          if (a.include_norm) {
+            const float d0 = w[0] * u0 + w[1] * u1 + w[2] * u2;
+            const float d1 = w[4] * u0 + w[5] * u1 + w[6] * u2;
+            const float d2 = w[8] * u0 + w[9] * u1 + w[10] * u2;
+            const float* nm = a.mvs_normal + (size_t)v * 3 * map_px;
+            cosv = d0 * tap1(nm, f, a.map_w) + d1 * tap1(nm + map_px, f, a.map_w) + d2 * tap1(nm + 2 * map_px, f, a.map_w);
+          }
+          best = fmaxf(best, surface_likelihood(a, mu, uncert, pd, cosv));
+        }
+      }
+      lik[i] = best;
+      if (a.likelihood) a.likelihood[(size_t)ray * nc + i] = best;
+      if (best > 0.f) {
+        // descending key order = descending likelihood, ties: lower candidate index first (stable descending sort)
+        const int pos = atomicAdd(&s_count, 1);
+        keys[pos] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)i);
+      }
+    }
+    __syncthreads();
+    const int count = s_count;
+    // ---- phase 2: more survivors than slots -> order them
+    if (count > keep) {
+      const int P = next_pow2(count);
+      for (int i = count + tid; i < P; i += kDgThreads) keys[i] = 0ull;
+      __syncthreads();
+      bitonic_sort(keys, P, [](unsigned long long x, unsigned long long y) { return x > y; });
+    }
+    // ---- phase 3: Gaussian samples around the occlusion-aware mean (original_depth_guided_sample.py:199-202,257-275)
+    float g_mean = 0.f, g_std = 0.f;
+    bool g_on = false;
+    if (ng > 0) {
+      if (tid < 32) {
+        float T = 1.f;                                                    // prod_{j<i} (1 - lik_j), sequential fp32
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          const int i = c0 + tid;
+          const float l = i < nc ? lik[i] : 0.f;
+          unsigned m = __ballot_sync(0xffffffffu, l > 0.f);
+          float mine = 0.f;
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const float lb = __shfl_sync(0xffffffffu, l, b);
+            if (tid == b) mine = lb * T;
+            T = T * (1.f - lb);
+          }
+          if (i < nc) opq[i] = mine;
+        }
+      }
+      __syncthreads();
+      float part = 0.f;
+      for (int i = tid; i < nc; i += kDgThreads) part += opq[i];
+      const float S = block_sum(part, s_red);
+      g_on = S != 0.f;
+      if (g_on) {
+        part = 0.f;
+        for (int i = tid; i < nc; i += kDgThreads) part += __ldg(cand + i) * (opq[i] / S);
+        g_mean = block_sum(part, s_red);
+        part = 0.f;
+        for (int i = tid; i < nc; i += kDgThreads) {
+          const float d = __ldg(cand + i) - g_mean;
+          part += d * d * (opq[i] / S);
+        }
+        g_std = sqrtf(block_sum(part, s_red));
+      }
+    }
+    // ---- phase 4: slots = [most likely candidates | Gaussian samples], 0 = empty
+    const int n_sel = count < keep ? count : keep;
+    for (int s = tid; s < ns_pow2; s += kDgThreads) {
+      float v = __int_as_float(0x7f800000);
+      if (s < n_sel) {
+        const unsigned idx = 0xFFFFFFFFu - (unsigned)(keys[s] & 0xFFFFFFFFull);
+        v = __ldg(cand + idx);
+      } else if (s < keep) {
+        v = 0.f;
+      } else if (s < ns) {
+        v = g_on ? __fadd_rn(__fmul_rn(__ldg(a.gauss + ray * ng + (s - keep)), g_std), g_mean) : 0.f;
+      }
+      z[s] = v;
+    }
+    __syncthreads();
+    bitonic_sort(z, ns_pow2, [](float x, float y) { return x < y; });
+    // ---- fill_up_uniform_samples (original_depth_guided_sample.py:333-366)
+    int mine = 0;
+    for (int s = tid; s < ns; s += kDgThreads) mine += (z[s] == 0.f) ? 1 : 0;
+    const float n_miss_f = block_sum((float)mine, s_red);
+    if (n_miss_f > 0.f) {
+      const float step = (a.max_depth - a.min_depth) / n_miss_f;
+      for (int s = tid; s < ns; s += kDgThreads)
+        if (z[s] == 0.f) {
+          float zf = __fadd_rn(a.min_depth, __fmul_rn((float)s, step));
+          zf = __fadd_rn(zf, __fmul_rn(__ldg(a.fill_rand + ray * ns + s), step));
+          z[s] = zf;
+        }
+    }
+    __syncthreads();
+    // ---- optional uniform samples (renderer.py:346-349), final sort
+    for (int s = ns + tid; s < out_pow2; s += kDgThreads) z[s] = (s < n_out) ? __ldg(a.uniform_depth + (s - ns)) : __int_as_float(0x7f800000);
+    __syncthreads();
+    bitonic_sort(z, out_pow2, [](float x, float y) { return x < y; });
+    for (int s = tid; s < n_out; s += kDgThreads) a.out_depth[ray * n_out + s] = z[s];
+    __syncthreads();
+  }
+}
+
+// project_points_dict_diner: thread = (view, point)
+__global__ void __launch_bounds__(256) project_gather_diner_kernel(const float* __restrict__ pts, long long pn, const float* __restrict__ w2c,
+                                                                   int rfn, int dataset, int H, int W, const float* __restrict__ mvs_depth,
+                                                                   const float* __restrict__ mvs_uncert, const float* __restrict__ mvs_normal,
+                                                                   int map_h, int map_w, int img_h, int img_w, float* __restrict__ out_pix,
+                                                                   float* __restrict__ out_depth, float* __restrict__ out_mu,
+                                                                   float* __restrict__ out_uncert, float* __restrict__ out_normal) {
+  const size_t map_px = (size_t)map_h * map_w;
+  const long long total = pn * rfn;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(g / pn);
+    const long long pi = g % pn;
+    const float x = __ldg(pts + 3 * pi), y = __ldg(pts + 3 * pi + 1), zc = __ldg(pts + 3 * pi + 2);
+    const float* w = w2c + 12 * v;
+    const float c0 = w[0] * x + w[1] * y + w[2] * zc + w[3];
+    const float c1 = w[4] * x + w[5] * y + w[6] * zc + w[7];
+    const float c2 = w[8] * x + w[9] * y + w[10] * zc + w[11];
+    float radius, px, py;
+    cam_to_equi(dataset, c0, c1, c2, H, W, radius, px, py);
+    const Footprint f = border_footprint(px, py, img_h, img_w, map_h, map_w);
+    out_pix[2 * g] = px; out_pix[2 * g + 1] = py;
+    out_depth[g] = radius;
+    out_mu[g] = tap1(mvs_depth + v * map_px, f, map_w);
+    out_uncert[g] = tap1(mvs_uncert + v * map_px, f, map_w);
+    if (out_normal) {
+      const float* nm = mvs_normal + (size_t)v * 3 * map_px;
+      out_normal[3 * g] = tap1(nm, f, map_w);
+      out_normal[3 * g + 1] = tap1(nm + map_px, f, map_w);
+      out_normal[3 * g + 2] = tap1(nm + 2 * map_px, f, map_w);
+    }
+  }
+}
+
+}  // namespace pgrf
+
+using namespace pgrf;
+
+extern "C" int pgrf_depth_guided_sample_fwd(const pgrf_diner_args* args, void* stream) {
+  PGRF_REQUIRE(args != nullptr, "depth_guided_sample: null args");
+  const pgrf_diner_args& a = *args;
+  PGRF_REQUIRE(a.rfn >= 1 && a.rn >= 1, "depth_guided_sample: rfn=%d rn=%lld", a.rfn, a.rn);
+  PGRF_REQUIRE(a.n_candidates >= 2 && a.n_candidates <= kDgMaxCand, "depth_guided_sample: n_candidates=%d not in [2,%d]",
+               a.n_candidates, kDgMaxCand);
+  PGRF_REQUIRE(a.n_samples >= 1 && a.n_uniform >= 0 && a.n_samples + a.n_uniform <= kDgMaxOut,
+               "depth_guided_sample: n_samples=%d n_uniform=%d (at most %d together)", a.n_samples, a.n_uniform, kDgMaxOut);
+  PGRF_REQUIRE(a.n_gaussian >= 0 && a.n_samples >= a.n_gaussian, "depth_guided_sample: n_samples >= n_gaussian required");
+  PGRF_REQUIRE(a.n_samples <= a.n_candidates, "depth_guided_sample: n_samples > n_candidates");
+  PGRF_REQUIRE(a.cand_depth && a.ref_w2c && a.fill_rand && a.out_depth, "depth_guided_sample: null pointer argument");
+  PGRF_REQUIRE(a.n_gaussian == 0 || a.gauss, "depth_guided_sample: n_gaussian > 0 needs the gauss table");
+  PGRF_REQUIRE(a.n_uniform == 0 || a.uniform_depth, "depth_guided_sample: n_uniform > 0 needs uniform_depth");
+  if (a.prj_mu) {
+    PGRF_REQUIRE(a.prj_uncert && a.prj_depth && a.que_dir && (!a.include_norm || a.prj_normal),
+                 "depth_guided_sample: dict variant needs prj_uncert, prj_depth, que_dir (and prj_normal with include_norm)");
+  } else {
+    PGRF_REQUIRE(a.dataset >= 0 && a.dataset <= 3, "Unknown dataset id %d", a.dataset);
+    PGRF_REQUIRE(a.coords && a.que_c2w && a.mvs_depth && a.mvs_uncert && (!a.include_norm || a.mvs_normal),
+                 "depth_guided_sample: fused variant needs coords, que_c2w, mvs_depth, mvs_uncert (and mvs_normal with include_norm)");
+    PGRF_REQUIRE(a.H >= 2 && a.W >= 2 && a.map_h >= 1 && a.map_w >= 1 && a.img_h >= 2 && a.img_w >= 2, "depth_guided_sample: bad map sizes");
+  }
+  const int nc_pad = (a.n_candidates + 3) & ~3;
+  int nc_pow2 = 1; while (nc_pow2 < a.n_candidates) nc_pow2 <<= 1;
+  int out_pow2 = 1; while (out_pow2 < a.n_samples + a.n_uniform) out_pow2 <<= 1;
+  const size_t smem = (size_t)nc_pow2 * 8 + (size_t)nc_pad * 8 + (size_t)out_pow2 * 4;
+  if (smem > 48 * 1024) PGRF_CUDA(cudaFuncSetAttribute(depth_guided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long max_grid = 148LL * 12;
+  const int grid = (int)(a.rn < max_grid ? a.rn : max_grid);
+  depth_guided_kernel<<<grid, kDgThreads, smem, (cudaStream_t)stream>>>(a, nc_pad, nc_pow2);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_project_gather_diner_fwd(const float* pts, long long pn, const float* w2c, int rfn, int dataset, int H, int W,
+                                             const float* mvs_depth, const float* mvs_uncert, const float* mvs_normal, int map_h,
+                                             int map_w, int img_h, int img_w, float* out_pix, float* out_depth, float* out_mu,
+                                             float* out_uncert, float* out_normal, void* stream) {
+  PGRF_REQUIRE(pts && w2c && mvs_depth && mvs_uncert && out_pix && out_depth && out_mu && out_uncert, "project_gather_diner: null pointer argument");
+  PGRF_REQUIRE((out_normal == nullptr) || mvs_normal, "project_gather_diner: out_normal needs mvs_normal");
+  PGRF_REQUIRE(pn >= 1 && rfn >= 1, "project_gather_diner: pn=%lld rfn=%d", pn, rfn);
+  PGRF_REQUIRE(dataset >= 0 && dataset <= 3, "Unknown dataset id %d", dataset);
+  const long long total = pn * rfn;
+  const long long blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < 148LL * 8 ? blocks : 148LL * 8);
+  project_gather_diner_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pts, pn, w2c, rfn, dataset, H, W, mvs_depth, mvs_uncert, mvs_normal,
+                                                                    map_h, map_w, img_h, img_w, out_pix, out_depth, out_mu, out_uncert,
+                                                                    out_normal);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}

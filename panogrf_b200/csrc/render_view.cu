@@ -46,7 +46,7 @@ extern "C" int pgrf_render_view_fwd(const pgrf_render_view_args* va, void* strea
   PGRF_REQUIRE(va != nullptr, "render_view: null args");
   const pgrf_render_args& base = va->pass;
   PGRF_REQUIRE(va->rays_per_launch >= 1, "render_view: rays_per_launch=%d", va->rays_per_launch);
-  PGRF_REQUIRE(base.depth_ray_stride == 0, "render_view: the coarse pass takes the shared (dn) depth table");
+  PGRF_REQUIRE(base.depth_ray_stride == 0 || base.depth_ray_stride == base.dn, "render_view: depth_ray_stride must be 0 or dn");
   const int dn = base.dn;
   const int fine_total = va->hierarchical ? base.fine_dn + (base.fine_use_all ? dn : 0) : 0;
   if (va->hierarchical) {
@@ -60,6 +60,7 @@ extern "C" int pgrf_render_view_fwd(const pgrf_render_view_args* va, void* strea
     pgrf_render_args c = base;
     c.rn = n;
     c.coords = base.coords + 2 * (size_t)r0;
+    c.depth = base.depth + (size_t)r0 * base.depth_ray_stride;
     c.pixel_colors = base.pixel_colors + 3 * (size_t)r0;
     if (base.render_depth) c.render_depth = base.render_depth + r0;
     if (base.hit_prob) c.hit_prob = base.hit_prob + (size_t)r0 * dn;
@@ -142,7 +143,7 @@ extern "C" int pgrf_render_view_host(const pgrf_render_view_args* hv) {
     const size_t n_img = (size_t)rfn * 3 * h.img_h * h.img_w, n_if = (size_t)rfn * 32 * h.if_h * h.if_w,
                  n_rf = (size_t)rfn * 32 * h.rf_h * h.rf_w;
     p.coords = up(h.coords, (size_t)rn * 2 * 4);
-    p.depth = up(h.depth, (size_t)dn * 4);
+    p.depth = up(h.depth, (h.depth_ray_stride ? (size_t)rn * dn : (size_t)dn) * 4);
     p.que_c2w = up(h.que_c2w, 12 * 4);
     p.ref_w2c = up(h.ref_w2c, (size_t)rfn * 12 * 4);
     p.ref_depth_range = up(h.ref_depth_range, (size_t)rfn * 2 * 4);

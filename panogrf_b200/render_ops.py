@@ -149,3 +149,145 @@ def mono_guided_hypotheses(ref_mu, k_list, fixed_sigma, min_depth, max_depth, n_
                                            float(min_depth), float(max_depth), _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "pgrf_depth_hypotheses_fwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# depth-prior sample placement (the "diner" branch of render_impl)
+# ------------------------------------------------------------------------------------------------
+
+def _cand_step(cfg, n_candidates):
+    """(max_depth - min_depth) / n_candidates exactly as the reference's fp32 tensor arithmetic evaluates it
+    (original_depth_guided_sample.py:131)."""
+    return float((torch.ones(1) * (cfg["max_depth"] - cfg["min_depth"]) / n_candidates)[0])
+
+
+def _random_tables(rn, n_samples, n_gaussian, dev, fill_rand, gauss, generator=None):
+    """The reference draws these with torch.rand_like / torch.randn_like inside the op; here they are arguments (drawn
+    on the device when not given) so that a run is reproducible and checkable."""
+    if fill_rand is None:
+        fill_rand = torch.rand(rn, n_samples, device=dev, generator=generator)
+    if n_gaussian > 0 and gauss is None:
+        gauss = torch.randn(rn, n_gaussian, device=dev, generator=generator)
+    fill_rand = _f32(fill_rand).to(dev).reshape(rn, n_samples)
+    gauss = _f32(gauss).to(dev).reshape(rn, n_gaussian) if n_gaussian > 0 else None
+    return fill_rand, gauss
+
+
+def project_points_dict_diner(ref_imgs_info, diner_que_pts, spt_utils, include_norm=False):
+    """render_ops.py:260-290: candidates (qn,rn,dn,3) -> {'ref_mvs_depths','ref_mvs_uncert','pts','depth'[,'ref_mvs_normal']}
+    of (rfn,qn,rn,dn,*)."""
+    _lib.require_cuda(diner_que_pts, ref_imgs_info["mvs_depth"], ref_imgs_info["mvs_uncert"])
+    lib = _lib.load()
+    qn, rn, dn, _ = diner_que_pts.shape
+    pts = _f32(diner_que_pts).reshape(-1, 3)
+    pn = pts.shape[0]
+    rfn, _, ih, iw = ref_imgs_info["imgs"].shape
+    dev = pts.device
+    md, mu_ = _f32(ref_imgs_info["mvs_depth"]), _f32(ref_imgs_info["mvs_uncert"])
+    mn = _f32(ref_imgs_info["mvs_normal"]) if include_norm else None
+    mh, mw = md.shape[-2:]
+    w2c = _f32(ref_imgs_info["w2c"]).to(dev)
+    e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    pix, dep, mu, unc = e(rfn, pn, 2), e(rfn, pn, 1), e(rfn, pn, 1), e(rfn, pn, 1)
+    nrm = e(rfn, pn, 3) if include_norm else None
+    name = spt_utils.dataset
+    if name not in _lib.DATASET_IDS:
+        raise Exception(f"unknown dataset {name!r}")
+    with torch.cuda.device(dev):
+        rc = lib.pgrf_project_gather_diner_fwd(
+            _lib.ptr(pts), pn, _lib.ptr(w2c), rfn, _lib.DATASET_IDS[name], int(spt_utils.height), int(spt_utils.width),
+            _lib.ptr(md), _lib.ptr(mu_), _lib.ptr(mn), mh, mw, ih, iw, _lib.ptr(pix), _lib.ptr(dep), _lib.ptr(mu), _lib.ptr(unc),
+            _lib.ptr(nrm), _lib.stream_ptr())
+    _lib.check(rc, "pgrf_project_gather_diner_fwd")
+    out = {"ref_mvs_depths": mu, "ref_mvs_uncert": unc, "pts": pix, "depth": dep}
+    if include_norm:
+        out["ref_mvs_normal"] = nrm
+    return {k: v.reshape(rfn, qn, rn, dn, -1) for k, v in out.items()}
+
+
+def sample_depthguided(cfg, ref_imgs_info, prj_depth_info_dict, que_depth, que_dir, n_samples, n_candidates, n_gaussian,
+                       depth_diff_max=0.05, include_norm=False, var=True, fill_rand=None, gauss=None, generator=None):
+    """original_depth_guided_sample.py:45-297 on a precomputed project_points_dict_diner result: (1,rn,n_candidates)
+    candidate depths -> (1,rn,n_samples) sorted sample depths.  `fill_rand` (rn,n_samples) / `gauss` (rn,n_gaussian)
+    replace the reference's in-op random draws."""
+    assert n_samples >= n_gaussian
+    _lib.require_cuda(que_depth, que_dir, prj_depth_info_dict["depth"])
+    lib = _lib.load()
+    dev = que_depth.device
+    rn = que_depth.shape[1]
+    rfn = prj_depth_info_dict["depth"].shape[0]
+    fill_rand, gauss = _random_tables(rn, n_samples, n_gaussian, dev, fill_rand, gauss, generator)
+    a = _lib.DinerArgs()
+    a.rfn, a.rn = rfn, rn
+    a.n_candidates, a.n_samples, a.n_gaussian, a.n_uniform = n_candidates, n_samples, n_gaussian, 0
+    a.include_norm, a.sigma_is_var = int(bool(include_norm)), int(bool(var))
+    a.diner_sigma = float(cfg["diner_sigma"]) if cfg.get("diner_sigma", 0) > 0 else 0.0
+    a.cand_step = _cand_step(cfg, n_candidates)
+    a.min_depth, a.max_depth, a.depth_diff_max = float(cfg["min_depth"]), float(cfg["max_depth"]), float(depth_diff_max)
+    cand = _f32(que_depth).reshape(rn, n_candidates)
+    w2c = _f32(ref_imgs_info["w2c"]).to(dev)
+    keep = [cand, w2c, fill_rand, gauss]
+    mu = _f32(prj_depth_info_dict["ref_mvs_depths"]).reshape(rfn, rn, n_candidates)
+    unc = _f32(prj_depth_info_dict["ref_mvs_uncert"]).reshape(rfn, rn, n_candidates)
+    pd = _f32(prj_depth_info_dict["depth"]).reshape(rfn, rn, n_candidates)
+    nrm = _f32(prj_depth_info_dict["ref_mvs_normal"]).reshape(rfn, rn, n_candidates, 3) if include_norm else None
+    qd = _f32(que_dir).reshape(rn, n_candidates, 3)
+    keep += [mu, unc, pd, nrm, qd]
+    a.cand_depth, a.cand_ray_stride, a.ref_w2c = _lib.ptr(cand), n_candidates, _lib.ptr(w2c)
+    a.fill_rand, a.gauss = _lib.ptr(fill_rand), _lib.ptr(gauss)
+    a.prj_mu, a.prj_uncert, a.prj_depth, a.prj_normal, a.que_dir = (_lib.ptr(mu), _lib.ptr(unc), _lib.ptr(pd), _lib.ptr(nrm),
+                                                                    _lib.ptr(qd))
+    out = torch.empty(1, rn, n_samples, device=dev, dtype=torch.float32)
+    a.out_depth = _lib.ptr(out)
+    with torch.cuda.device(dev):
+        rc = lib.pgrf_depth_guided_sample_fwd(a, _lib.stream_ptr())
+    _lib.check(rc, "pgrf_depth_guided_sample_fwd")
+    del keep
+    return out
+
+
+def depth_guided_placement(cfg, que_imgs_info, ref_imgs_info, fill_rand=None, gauss=None, generator=None,
+                           return_likelihood=False):
+    """The sample placement of `diner_render_by_depth` (renderer.py:318-349) fused into ONE kernel: linear candidates
+    (`n_candidates`), projection into the source panoramas, MVS-prior gathers, likelihood, selection of `n_samples`,
+    Gaussian samples, fill-up, optional `n_uniform` uniform samples (cfg contain_uniform / inv_uniform), sort.
+    Returns (1,rn,n_samples[+n_uniform]) depths (and the (rn,n_candidates) likelihood when asked for)."""
+    coords = que_imgs_info["coords"]
+    _lib.require_cuda(coords, ref_imgs_info["mvs_depth"], ref_imgs_info["mvs_uncert"])
+    lib = _lib.load()
+    dev = coords.device
+    rn = coords.shape[1]
+    nc, ns, ng = int(cfg["n_candidates"]), int(cfg["n_samples"]), int(cfg["n_gaussian"])
+    include_norm = bool(cfg.get("backface_culling", False))
+    name = cfg["dataset_name"]
+    if name not in _lib.DATASET_IDS:
+        raise Exception(f"unknown dataset {name!r}")
+    fill_rand, gauss = _random_tables(rn, ns, ng, dev, fill_rand, gauss, generator)
+    nu = int(cfg["n_uniform"]) if cfg.get("contain_uniform", False) else 0
+    uni = coarse_depth_table(cfg, nu, bool(cfg.get("inv_uniform", False))).to(dev) if nu > 0 else None
+    cand = coarse_depth_table(cfg, nc, False).to(dev)
+    rfn, _, ih, iw = ref_imgs_info["imgs"].shape
+    md, mu_ = _f32(ref_imgs_info["mvs_depth"]), _f32(ref_imgs_info["mvs_uncert"])
+    mn = _f32(ref_imgs_info["mvs_normal"]) if include_norm else None
+    c2w = _f32(que_imgs_info["c2w"]).to(dev).reshape(3, 4)
+    w2c = _f32(ref_imgs_info["w2c"]).to(dev)
+    xy = _f32(coords).reshape(rn, 2)
+    a = _lib.DinerArgs()
+    a.dataset, a.H, a.W, a.rfn, a.rn = _lib.DATASET_IDS[name], int(cfg["height"]), int(cfg["width"]), rfn, rn
+    a.n_candidates, a.n_samples, a.n_gaussian, a.n_uniform = nc, ns, ng, nu
+    a.include_norm, a.sigma_is_var = int(include_norm), 1
+    a.diner_sigma = float(cfg["diner_sigma"]) if cfg.get("diner_sigma", 0) > 0 else 0.0
+    a.cand_step = _cand_step(cfg, nc)
+    a.min_depth, a.max_depth, a.depth_diff_max = float(cfg["min_depth"]), float(cfg["max_depth"]), 0.05
+    a.coords, a.cand_depth, a.cand_ray_stride = _lib.ptr(xy), _lib.ptr(cand), 0
+    a.que_c2w, a.ref_w2c = _lib.ptr(c2w), _lib.ptr(w2c)
+    a.mvs_depth, a.mvs_uncert, a.mvs_normal = _lib.ptr(md), _lib.ptr(mu_), _lib.ptr(mn)
+    a.map_h, a.map_w, a.img_h, a.img_w = md.shape[-2], md.shape[-1], ih, iw
+    a.fill_rand, a.gauss, a.uniform_depth = _lib.ptr(fill_rand), _lib.ptr(gauss), _lib.ptr(uni)
+    out = torch.empty(1, rn, ns + nu, device=dev, dtype=torch.float32)
+    lik = torch.empty(rn, nc, device=dev, dtype=torch.float32) if return_likelihood else None
+    a.out_depth, a.likelihood = _lib.ptr(out), _lib.ptr(lik)
+    with torch.cuda.device(dev):
+        rc = lib.pgrf_depth_guided_sample_fwd(a, _lib.stream_ptr())
+    _lib.check(rc, "pgrf_depth_guided_sample_fwd")
+    return (out, lik) if return_likelihood else out

@@ -178,8 +178,6 @@ class NeuralRayBaseRenderer(nn.Module):
             raise Exception(f"unknown dataset_name {self.cfg['dataset_name']!r}")
         if self.cfg.get("debug"):
             raise _lib.PanoGRFError("cfg['debug'] (network bypass) is not part of the hot path")
-        if self.cfg.get("diner_depth_guided_sampling"):
-            raise _lib.PanoGRFError("diner_depth_guided_sampling is not implemented (SURVEY.md §8f rank 3)")
         self.dist_decoder = name2dist_decoder[self.cfg["dist_decoder_type"]](self.cfg["dist_decoder_cfg"])
         self.agg_net = name2agg_net[self.cfg["agg_net_type"]](self.cfg["agg_net_cfg"])
         if self.cfg["use_hierarchical_sampling"] and not self.cfg.get("one_mlp"):
@@ -338,6 +336,8 @@ class NeuralRayBaseRenderer(nn.Module):
         if is_perspec:
             raise NotImplementedError("perspective (cube) query rays are outside the ERP hot path")
         cfg = self.cfg
+        if cfg.get("diner_depth_guided_sampling", False):
+            return self._render_diner(que_imgs_info, ref_imgs_info, keep_hit_prob=True)
         ctx = _ctx or self._context(que_imgs_info, ref_imgs_info)
         coords = que_imgs_info["coords"]
         assert coords.shape[0] == 1
@@ -399,6 +399,8 @@ class NeuralRayBaseRenderer(nn.Module):
             feats = self.image_encoder(ref_imgs_info["imgs"])
             ref_imgs_info["img_feats"] = feats
             ref_imgs_info["ray_feats"] = self.vis_encoder(ref_imgs_info["ray_feats"], feats)
+        if self.cfg.get("diner_depth_guided_sampling", False):
+            return self._render_diner(que_imgs_info, ref_imgs_info, keep_hit_prob)
         ctx = self._context(que_imgs_info, ref_imgs_info)
         coords = que_imgs_info["coords"]
         assert coords.shape[0] == 1
@@ -406,6 +408,66 @@ class NeuralRayBaseRenderer(nn.Module):
         outs = self._alloc_outputs(rn, coords.device, keep_hit_prob, ctx['rfn'])
         self._render_view(ctx, coords[0].float().contiguous(), outs)
         return outs
+
+    def _render_diner(self, que_imgs_info, ref_imgs_info, keep_hit_prob=False):
+        """Depth-prior sample placement branch of render_impl (network/renderer.py:570-600) with
+        diner_render_by_depth (:318-436): one fused placement kernel (candidates -> likelihood -> selection -> fill-up
+        -> sort), then the usual pass on the per-ray depths with the COARSE networks; `c2f` adds the hierarchical fine
+        pass.  Without `c2f` every output carries the `_fine` suffix, as in the reference.  The reference's in-op
+        random draws are taken from que_imgs_info['diner_fill_rand'] (rn,n_samples) / ['diner_gauss'] (rn,n_gaussian)
+        when present, else drawn on the device."""
+        from .render_ops import depth_guided_placement
+        cfg = self.cfg
+        if cfg.get("N_uniform", 0) > 0:
+            raise NotImplementedError("merge_uniform_diner (cfg N_uniform > 0) is not part of the accelerated path")
+        for k in ("mvs_depth", "mvs_uncert"):
+            if k not in ref_imgs_info:
+                raise _lib.PanoGRFError(f"diner_depth_guided_sampling needs ref_imgs_info[{k!r}]")
+        ctx = self._context(que_imgs_info, ref_imgs_info)
+        coords = que_imgs_info["coords"]
+        assert coords.shape[0] == 1
+        coords2 = coords[0].float().contiguous()
+        rn, dev = coords2.shape[0], coords2.device
+        depth = depth_guided_placement(cfg, que_imgs_info, ref_imgs_info, que_imgs_info.get("diner_fill_rand"),
+                                       que_imgs_info.get("diner_gauss"))                     # (1,rn,N)
+        N = depth.shape[-1]
+        c2f = bool(cfg.get("c2f", False))
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        rfn = ctx["rfn"]
+
+        def alloc(n):
+            o = {"pixel_colors_nr": e(1, rn, 3), "colors_nr": e(1, rn, n, 3), "density_nr": e(1, rn, n)}
+            if keep_hit_prob or c2f:
+                o["hit_prob_nr"] = e(1, rn, n)
+            if cfg["use_ray_mask"]:
+                ok = rfn >= cfg["ray_mask_view_num"] and n > cfg["ray_mask_point_num"]
+                o["ray_mask"] = torch.full((1, rn), bool(ok), device=dev)
+            if cfg["render_depth"]:
+                o["render_depth"] = e(1, rn)
+            return o
+
+        coarse = alloc(N)
+        fdn = int(cfg["fine_depth_sample_num"])
+        fine_total = fdn + (N if cfg["fine_depth_use_all"] else 0)
+        fine = alloc(fine_total) if c2f else None
+        rpl = self.rays_per_launch or (32768 if self.mlp_dtype == "bf16" else 4096)
+        d2 = depth[0]
+        for r0 in range(0, rn, int(rpl)):
+            n = min(int(rpl), rn - r0)
+            fd = self._pass(ctx, coords2[r0:r0 + n], d2[r0:r0 + n], N, False, c2f, coarse, r0, "hit_prob_nr" in coarse)
+            if c2f:
+                self._pass(ctx, coords2[r0:r0 + n], fd, fine_total, not cfg.get("one_mlp", False), False, fine, r0,
+                           "hit_prob_nr" in fine)
+                if keep_hit_prob:
+                    fine.setdefault("que_depth", e(1, rn, fine_total))[0, r0:r0 + n] = fd
+        coarse["que_depth"] = depth
+        if not (keep_hit_prob or not c2f):
+            coarse.pop("hit_prob_nr", None)
+        if c2f:
+            outs = dict(coarse)
+            outs.update({k + "_fine": v for k, v in fine.items()})
+            return outs
+        return {k + "_fine": v for k, v in coarse.items()}
 
     def _render_view(self, ctx, coords2, outs):
         """One C-ABI call for the whole view: pgrf_render_view_fwd runs the ray-batch loop and the

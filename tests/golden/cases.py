@@ -133,3 +133,68 @@ def make_render_inputs(name, seed=0):
 
 
 RENDER_WEIGHT_PREFIXES = ("dist_decoder.", "fine_dist_decoder.", "agg_net.", "fine_agg_net.")
+
+
+# ------------------------------------------------------------------------------------------------
+# depth-prior sample placement ("diner" branch of render_impl, renderer.py:570-600)
+# ------------------------------------------------------------------------------------------------
+
+DINER_CASES = {
+    # few candidates survive |mu - depth| < 0.05: most slots are filled up uniformly
+    "diner_sparse": dict(cfg=dict(n_candidates=400, n_samples=16, n_gaussian=4, contain_uniform=True, n_uniform=8,
+                                  inv_uniform=True, sample_num=24), rfn=2, n_rays=64, map_scale=1, radius=3.0),
+    # small depth range: more surviving candidates than slots -> the top-k cut is exercised; with a real fine pass
+    "diner_dense_c2f": dict(cfg=dict(n_candidates=600, n_samples=16, n_gaussian=0, contain_uniform=False, c2f=True,
+                                     max_depth=4.0, sample_num=16, diner_sigma=0.03, hierarchical=True), rfn=3, n_rays=48, map_scale=2,
+                            radius=2.0),
+}
+
+
+def make_diner_inputs(name, seed=0):
+    """Inputs of the depth-guided branch: the usual render inputs + per-source MVS depth / variance / normal maps of
+    a synthetic sphere around the origin (so candidates near the surface agree with the depth prior)."""
+    from oracle import render as R
+    c = DINER_CASES[name]
+    kw = dict(c["cfg"])
+    kw.setdefault("hierarchical", False)
+    cfg = render_cfg(diner_depth_guided_sampling=True, backface_culling=True, **kw)
+    gen = torch.Generator().manual_seed(seed + sum(map(ord, name)))
+    h, w, rfn = cfg["height"], cfg["width"], c["rfn"]
+    imgs = smooth(torch.rand(rfn, h, w, 3, generator=gen), 1).permute(0, 3, 1, 2).contiguous()
+    img_feats = torch.randn(rfn, 32, h // 2, w // 2, generator=gen)
+    ray_feats = torch.randn(rfn, 32, h // 4, w // 4, generator=gen)
+    rots = small_rotations(gen, 1, rfn + 1, 8.0)[0]
+    trans = torch.randn(rfn + 1, 3, generator=gen) * 0.25
+    w2c = torch.cat([rots, trans[:, :, None]], -1)
+    que_w2c = w2c[-1]
+    Rq, tq = que_w2c[:, :3], que_w2c[:, 3]
+    c2w = torch.cat([Rq.t(), (-Rq.t() @ tq)[:, None]], -1)[None]
+    perm = torch.randperm(h * w, generator=gen)[:c["n_rays"]]
+    coords = torch.stack([(perm % w).float(), (perm // w).float()], -1)[None]
+    # sphere |p| = radius seen from every source camera
+    mh, mw = h // c["map_scale"], w // c["map_scale"]
+    dirs = R.equi_to_unit_dirs(cfg["dataset_name"], mh, mw).reshape(-1, 3)          # camera-frame unit rays
+    depth_maps, normal_maps = [], []
+    for v in range(rfn):
+        Rv, tv = w2c[v, :, :3], w2c[v, :, 3]
+        cam = -Rv.t() @ tv
+        dw = dirs @ Rv                                                              # world rays (R^T d)
+        b = dw @ cam
+        t = -b + torch.sqrt(b * b - cam.dot(cam) + c["radius"] ** 2)
+        p = cam[None] + t[:, None] * dw
+        n_cam = (p / p.norm(dim=1, keepdim=True)) @ Rv.t()                          # outward normal in the camera frame
+        depth_maps.append(t.reshape(1, mh, mw))
+        normal_maps.append(n_cam.reshape(mh, mw, 3).permute(2, 0, 1))
+    mvs_depth = torch.stack(depth_maps) + 0.01 * smooth(torch.randn(rfn, mh, mw, 1, generator=gen), 2).permute(0, 3, 1, 2)
+    flip = torch.sign(smooth(torch.randn(rfn, mh, mw, 1, generator=gen), 3).permute(0, 3, 1, 2) + 0.05)
+    mvs_normal = torch.stack(normal_maps) * flip + 0.05 * torch.randn(rfn, 3, mh, mw, generator=gen)
+    mvs_uncert = 0.0004 + 0.01 * torch.rand(rfn, 1, mh, mw, generator=gen)
+    que = {"coords": coords, "c2w": c2w, "w2c": que_w2c[None], "depth_range": torch.tensor([[cfg["min_depth"], cfg["max_depth"]]])}
+    ref = {"imgs": imgs, "w2c": w2c[:rfn].contiguous(),
+           "depth_range": torch.tensor([[cfg["min_depth"], cfg["max_depth"]]]).repeat(rfn, 1),
+           "ray_feats": ray_feats, "img_feats": img_feats,
+           "mvs_depth": mvs_depth.contiguous(), "mvs_uncert": mvs_uncert, "mvs_normal": mvs_normal.contiguous()}
+    rn = c["n_rays"]
+    fill_rand = torch.rand(rn, cfg["n_samples"], generator=gen)
+    gauss = torch.randn(rn, max(cfg["n_gaussian"], 1), generator=gen)[:, :cfg["n_gaussian"]]
+    return cfg, que, ref, fill_rand, gauss

@@ -1,0 +1,50 @@
+"""CPU: the depth-prior sample placement oracle reproduces the reference's diner branch (tests/golden/diner_*.npz)."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import cases  # noqa: E402
+from util import assert_close, load_golden  # noqa: E402
+from test_oracle_render import split_golden  # noqa: E402
+
+from oracle import depth_guided as odg  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(cases.DINER_CASES))
+def test_oracle_matches_reference_golden(name):
+    cfg, que_s, ref_s, fill_s, gauss_s = cases.make_diner_inputs(name)
+    g = load_golden(name)
+    que, ref, W, gold = split_golden(g)
+    assert torch.equal(que_s["coords"], que["coords"]) and torch.equal(ref_s["mvs_depth"], ref["mvs_depth"])
+    assert torch.equal(fill_s, g["fill_rand"])
+    out = odg.render_rays_diner(cfg, W, que, ref, g["fill_rand"], g["gauss"])
+    key = "que_depth" if cfg.get("c2f") else "que_depth_fine"
+    # sample placement: same candidates selected, same slots filled
+    assert_close(out[key], gold[key].float(), rtol=1e-5, atol=1e-6, what=f"{name}/{key}")
+    for k, v in gold.items():
+        if k.startswith("ray_mask"):
+            continue
+        assert_close(out[k], v.float(), rtol=1e-4, atol=2e-5, what=f"{name}/{k}")
+
+
+def test_fill_up_semantics():
+    cfg = {"min_depth": 1.0, "max_depth": 5.0}
+    z = torch.tensor([[0.0, 3.0, 0.0, 2.0], [0.0, 0.0, 0.0, 0.0], [1.5, 2.5, 3.5, 4.5]])
+    r = torch.full((3, 4), 0.5)
+    out = odg.fill_up_uniform_samples(cfg, z, r)
+    assert torch.allclose(out[0], torch.tensor([2.0, 2.0, 3.0, 4.0]))      # slots 0,1 of 2 missing: 1+[0.5,1.5]*2
+    assert torch.allclose(out[1], torch.tensor([1.5, 2.5, 3.5, 4.5]))
+    assert torch.equal(out[2], z[2])
+
+
+def test_placement_statistics():
+    """The synthetic sphere makes candidates near the surface likely: selected samples cluster around it."""
+    name = "diner_dense_c2f"
+    cfg, que, ref, fill_rand, gauss = cases.make_diner_inputs(name)
+    z = odg.diner_sample_placement(cfg, que, ref, fill_rand, gauss)
+    assert z.shape == (1, que["coords"].shape[1], cfg["n_samples"])
+    assert bool((z[..., 1:] >= z[..., :-1]).all())
+    assert float(z.min()) >= cfg["min_depth"] and float(z.max()) <= cfg["max_depth"]
