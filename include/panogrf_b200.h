@@ -94,6 +94,16 @@ PGRF_API int pgrf_cost_volume_host(const float* images, int B, int S, int H, int
                           int dataset, int cost_type, int layout, int groups,
                           float* out);
 
+/* K1 backward: gradient w.r.t. the feature maps (the reference: autograd through grid_sample + abs / mul,
+ * models/spherical_cost_volume.py:135-230; hypotheses and poses carry no gradient, pipeline3_model.py:647,671).
+ *   grad_out     (B,D,H,W,C) contiguous upstream gradient of the cost volume
+ *   grad_images  (B,S,H,W,C) ACCUMULATED into with vector atomics: zero it before the call
+ * Other arguments as pgrf_cost_volume_fwd. */
+PGRF_API int pgrf_cost_volume_bwd(const float* grad_out, const float* images, int B, int S, int H, int W, int C,
+                                  const float* depths, const float* depth_volume, int D, const float* rots, const float* trans,
+                                  int ref_idx, const int* src_views, int n_src, float divisor, int dataset, int cost_type,
+                                  float* grad_images, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------
  * K2 + K3 + K4 — one render pass (coarse or fine) over a batch of rays.

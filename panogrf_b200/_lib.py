@@ -30,6 +30,7 @@ SIGNATURES = {
     "pgrf_umma_selftest": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "pgrf_cost_volume_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P]),
     "pgrf_cost_volume_host": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _F, _I, _I, _I, _I, _P]),
+    "pgrf_cost_volume_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _F, _I, _I, _P, _P]),
 }
 
 _lib = None

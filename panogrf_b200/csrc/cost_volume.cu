@@ -16,124 +16,9 @@
 //            cost vs. the reference feature held in registers, accumulation over source views
 //   epilogue: channels-last -> direct 128-bit streaming stores (512 B contiguous per warp store);
 //             planar (B,D,C,H,W)/(B,C,D,H,W)/group-mean -> conflict-free smem transpose, 128-B row stores
-#include "common.cuh"
+#include "cost_volume.cuh"
 
 namespace pgrf {
-
-constexpr int kCvWarps = 4;
-constexpr int kCvThreads = kCvWarps * 32;
-constexpr int kMaxSrc = 8;
-
-struct CvParams {
-  const float* images;
-  const float* depths;
-  const float* depth_volume;
-  const float* rots;
-  const float* trans;
-  float* out;
-  int* err;
-  int B, S, H, W, D;
-  int ref_idx, n_src;
-  int src_views[kMaxSrc];
-  float divisor;
-  int dataset, cost_type, groups, OC;
-  int d_chunk;
-  long long sB, sD, sC;  // planar strides in elements
-  float ang0, ang1, ang2, ang3;  // per-dataset pixel->angle constants (see host side)
-};
-
-struct __align__(16) TapRec {
-  float tx, ty;   // fractional offsets inside the 2x2 footprint
-  int off4;       // float4 index of the north-west texel inside one (H,W,C) view
-  int pad;
-};
-// The footprint is canonicalised so that all four taps are inside the map: for uv in [-1,1] the only
-// out-of-map tap of grid_sample(zeros padding) is x0+1 == W (or y0+1 == H) reached with weight exactly 0
-// when ix == W-1; shifting the footprint one texel back (x0 = W-2, tx = 1) gives bit-identical weights
-// (1-tx = 0 on the west taps) and needs no predication.  Out-of-range uv (flagged, the reference asserts)
-// is clamped the same way so the gather stays memory-safe.
-
-// ---- pixel -> unit ray, per dataset (spherical_cost_volume.py:272-301, my_torch_helpers.py:33-58) ----
-__device__ __forceinline__ void pixel_ray(const CvParams& p, int x, int y, float& rx, float& ry, float& rz) {
-  const float fx = (float)x, fy = (float)y;
-  float theta, phi;
-  switch (p.dataset) {
-    case PGRF_DS_M3D:
-      phi = (fy + 0.5f) * p.ang0;                       // (phi+0.5)*(pi/H)
-      theta = (fx + 0.5f) * p.ang1 - PGRF_HALF_PI_F;    // (theta+0.5)*(2pi/W) - pi/2
-      break;
-    case PGRF_DS_REPLICA_TEST:
-      theta = p.ang1 * (fx + 0.5f) - PGRF_PI_F;
-      phi = (-(fy + 0.5f) * PGRF_PI_F) / p.ang0 + PGRF_HALF_PI_F;   // ang0 = H
-      break;
-    case PGRF_DS_RESIDENTIAL:
-      theta = PGRF_PI_F * ((2.f * fx) / p.ang1 - 1.5f);             // ang1 = W-1
-      phi = PGRF_PI_F * (0.5f - fy / p.ang0);                       // ang0 = H-1
-      break;
-    default:  // CoffeeArea
-      theta = p.ang1 * fx + PGRF_TWO_PI_F;                          // ang1 = -2pi/(W-1)
-      phi = p.ang0 * fy;                                            // ang0 = pi/(H-1)
-      break;
-  }
-  float st, ct, sp, cp;
-  sincosf(theta, &st, &ct);
-  sincosf(phi, &sp, &cp);
-  switch (p.dataset) {
-    case PGRF_DS_M3D:          rx = sp * ct; ry = cp;  rz = sp * st; break;
-    case PGRF_DS_REPLICA_TEST: rx = st * cp; ry = -sp; rz = ct * cp; break;
-    case PGRF_DS_RESIDENTIAL:  rx = ct * cp; ry = sp;  rz = st * cp; break;
-    default:                   rx = sp * ct; ry = sp * st; rz = cp;  break;
-  }
-}
-
-// ---- camera-frame point -> normalised (u,v) (my_torch_helpers.py:62-120 + spherical_cost_volume.py:153-190) ----
-__device__ __forceinline__ void point_uv(int dataset, float cx, float cy, float cz, float& u, float& v) {
-  const float kLin = 0.17453292519943295f;       // deg2rad(10)
-  const float kCosDeg = 0.984807753012208f;      // cos(10 deg)
-  const float kOneMinusCos = 0.015192246987791981f;
-  const float radius = sqrtf(cx * cx + cy * cy + cz * cz);
-  float uu, vv;
-  switch (dataset) {
-    case PGRF_DS_M3D: {
-      const float theta = atan2f(cz, cx);
-      const float yr = cy / radius;
-      float phi;
-      if (fabsf(yr) < kCosDeg) phi = acosf(yr);
-      else if (cy >= 0.f) phi = kLin * (1.f - yr) / kOneMinusCos;       // acos linearised near the poles
-      else phi = PGRF_PI_F - kLin * (yr + 1.f) / kOneMinusCos;
-      uu = fmod_two_pi(theta + PGRF_HALF_PI_F + PGRF_TWO_PI_F);
-      vv = phi;
-      break;
-    }
-    case PGRF_DS_REPLICA_TEST: {
-      const float theta = atan2f(cx, cz);
-      const float phi = -asinf(cz / radius);      // sic (reference :99 uses z)
-      uu = fmod_two_pi(theta + PGRF_PI_F + PGRF_TWO_PI_F);
-      vv = -phi + PGRF_HALF_PI_F;
-      break;
-    }
-    case PGRF_DS_RESIDENTIAL: {
-      float theta = -atan2f(-cz, cx);
-      const float phi = asinf(cy / radius);
-      if (theta > PGRF_HALF_PI_F && theta <= PGRF_TWO_PI_F) theta -= PGRF_TWO_PI_F;
-      uu = fmod_two_pi(theta + 4.71238898038468985769f);   // 3/4 * 2pi
-      vv = PGRF_HALF_PI_F - phi;
-      break;
-    }
-    default: {
-      float theta = atan2f(cy, cx);
-      const float phi = acosf(cz / radius);
-      if (theta < 0.f) theta += PGRF_TWO_PI_F;
-      uu = PGRF_TWO_PI_F - theta;
-      vv = phi;
-      break;
-    }
-  }
-  // tensor / python-scalar is a multiplication by the fp32 reciprocal in torch's CUDA kernels; do the same
-  constexpr float kInvPi = 0.31830988618379067154f;
-  u = uu * kInvPi - 1.f;
-  v = 2.f * vv * kInvPi - 1.f;
-}
 
 template <int C, bool PLANAR, bool SINGLE, int JBT, int MINB>
 __global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_kernel(const CvParams p) {
@@ -156,31 +41,7 @@ __global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_kernel(const CvP
   float* tile = reinterpret_cast<float*>(smem_raw + (size_t)kCvWarps * p.n_src * 32 * sizeof(TapRec)) +
                 warp * (C * 33);
 
-  // Relative pose of every swept view w.r.t. the reference view, in fp64, rounded once to fp32.
-  if (threadIdx.x < p.n_src) {
-    const int s = p.src_views[threadIdx.x];
-    const float* Rr = p.rots + ((size_t)b * p.S + p.ref_idx) * 9;
-    const float* tr = p.trans + ((size_t)b * p.S + p.ref_idx) * 3;
-    const float* Rs = p.rots + ((size_t)b * p.S + s) * 9;
-    const float* ts = p.trans + ((size_t)b * p.S + s) * 3;
-    double r[9], inv[9];
-    for (int i = 0; i < 9; ++i) r[i] = Rr[i];
-    const double det = r[0] * (r[4] * r[8] - r[5] * r[7]) - r[1] * (r[3] * r[8] - r[5] * r[6]) +
-                       r[2] * (r[3] * r[7] - r[4] * r[6]);
-    const double id = 1.0 / det;
-    inv[0] = (r[4] * r[8] - r[5] * r[7]) * id; inv[1] = (r[2] * r[7] - r[1] * r[8]) * id; inv[2] = (r[1] * r[5] - r[2] * r[4]) * id;
-    inv[3] = (r[5] * r[6] - r[3] * r[8]) * id; inv[4] = (r[0] * r[8] - r[2] * r[6]) * id; inv[5] = (r[2] * r[3] - r[0] * r[5]) * id;
-    inv[6] = (r[3] * r[7] - r[4] * r[6]) * id; inv[7] = (r[1] * r[6] - r[0] * r[7]) * id; inv[8] = (r[0] * r[4] - r[1] * r[3]) * id;
-    double A[9];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j)
-        A[i * 3 + j] = (double)Rs[i * 3 + 0] * inv[0 * 3 + j] + (double)Rs[i * 3 + 1] * inv[1 * 3 + j] +
-                       (double)Rs[i * 3 + 2] * inv[2 * 3 + j];
-    for (int i = 0; i < 9; ++i) s_A[threadIdx.x][i] = (float)A[i];
-    for (int i = 0; i < 3; ++i)
-      s_A[threadIdx.x][9 + i] =
-          (float)((double)ts[i] - (A[i * 3] * (double)tr[0] + A[i * 3 + 1] * (double)tr[1] + A[i * 3 + 2] * (double)tr[2]));
-  }
+  if (threadIdx.x < p.n_src) relative_pose(p, b, threadIdx.x, s_A[threadIdx.x]);
   __syncthreads();
 
   const int x = x_warp + lane;
@@ -379,13 +240,11 @@ extern "C" int pgrf_debug_set(const char* key, int value) {
   return PGRF_EINVAL;
 }
 
-extern "C" int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, int W, int C,
-                                    const float* depths, const float* depth_volume, int D,
-                                    const float* rots, const float* trans,
-                                    int ref_idx, const int* src_views, int n_src, float divisor,
-                                    int dataset, int cost_type, int layout, int groups,
-                                    float* out, int* err_flag, void* stream) {
-  PGRF_REQUIRE(images && rots && trans && out && err_flag, "cost_volume: null pointer argument");
+namespace pgrf {
+int cv_fill_params(CvParams& p, const float* images, int B, int S, int H, int W, int C, const float* depths, const float* depth_volume,
+                   int D, const float* rots, const float* trans, int ref_idx, const int* src_views, int n_src, float divisor,
+                   int dataset, int cost_type) {
+  PGRF_REQUIRE(images && rots && trans && src_views, "cost_volume: null pointer argument");
   PGRF_REQUIRE(depths || depth_volume, "cost_volume: need depths or depth_volume");
   PGRF_REQUIRE(B > 0 && S > 0 && H > 1 && W > 1 && D > 0, "cost_volume: bad shape B=%d S=%d H=%d W=%d D=%d", B, S, H, W, D);
   PGRF_REQUIRE(B <= 65535, "cost_volume: B=%d exceeds grid.z", B);
@@ -394,33 +253,48 @@ extern "C" int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, in
   PGRF_REQUIRE(ref_idx >= 0 && ref_idx < S, "cost_volume: ref_idx=%d out of range", ref_idx);
   PGRF_REQUIRE(dataset >= 0 && dataset <= 3, "cost_volume: unknown dataset id %d", dataset);
   PGRF_REQUIRE(cost_type >= 0 && cost_type <= 2, "Unknown cost type");
-  PGRF_REQUIRE(layout >= 0 && layout <= 2, "cost_volume: unknown layout %d", layout);
-  PGRF_REQUIRE(groups == 0 || (layout == PGRF_CV_BCDHW && groups > 0 && C % groups == 0),
-               "cost_volume: groups=%d needs layout BCDHW and C %% groups == 0", groups);
   PGRF_REQUIRE((size_t)H * W * C < (1ull << 31), "cost_volume: one view exceeds 2^31 elements");
-  PGRF_REQUIRE((((uintptr_t)images | (uintptr_t)out) & 15) == 0, "cost_volume: images/out must be 16-byte aligned");
-
-  CvParams p;
+  PGRF_REQUIRE(((uintptr_t)images & 15) == 0, "cost_volume: images/out must be 16-byte aligned");
   memset(&p, 0, sizeof(p));
   p.images = images; p.depths = depths; p.depth_volume = depth_volume; p.rots = rots; p.trans = trans;
-  p.out = out; p.err = err_flag;
   p.B = B; p.S = S; p.H = H; p.W = W; p.D = D;
   p.ref_idx = ref_idx; p.n_src = n_src;
   for (int i = 0; i < n_src; ++i) {
     PGRF_REQUIRE(src_views[i] >= 0 && src_views[i] < S, "cost_volume: src view %d out of range", src_views[i]);
     p.src_views[i] = src_views[i];
   }
-  p.divisor = divisor; p.dataset = dataset; p.cost_type = cost_type; p.groups = groups;
-  p.OC = groups > 0 ? groups : C;
-  const long long HW = (long long)H * W;
-  if (layout == PGRF_CV_BDCHW) { p.sC = HW; p.sD = HW * p.OC; p.sB = p.sD * D; }
-  else { p.sD = HW; p.sC = HW * D; p.sB = p.sC * p.OC; }
+  p.divisor = divisor; p.dataset = dataset; p.cost_type = cost_type;
   switch (dataset) {
     case PGRF_DS_M3D: p.ang0 = (float)(PGRF_PI_D / H); p.ang1 = (float)(2 * PGRF_PI_D / W); break;
     case PGRF_DS_REPLICA_TEST: p.ang0 = (float)H; p.ang1 = (float)(2 * PGRF_PI_D / W); break;
     case PGRF_DS_RESIDENTIAL: p.ang0 = (float)(H - 1); p.ang1 = (float)(W - 1); break;
     default: p.ang0 = (float)(PGRF_PI_D / (H - 1)); p.ang1 = (float)(-2 * PGRF_PI_D / (W - 1)); break;
   }
+  return PGRF_OK;
+}
+}  // namespace pgrf
+
+extern "C" int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, int W, int C,
+                                    const float* depths, const float* depth_volume, int D,
+                                    const float* rots, const float* trans,
+                                    int ref_idx, const int* src_views, int n_src, float divisor,
+                                    int dataset, int cost_type, int layout, int groups,
+                                    float* out, int* err_flag, void* stream) {
+  PGRF_REQUIRE(out && err_flag, "cost_volume: null pointer argument");
+  PGRF_REQUIRE(layout >= 0 && layout <= 2, "cost_volume: unknown layout %d", layout);
+  PGRF_REQUIRE(groups == 0 || (layout == PGRF_CV_BCDHW && groups > 0 && C % groups == 0),
+               "cost_volume: groups=%d needs layout BCDHW and C %% groups == 0", groups);
+  PGRF_REQUIRE(((uintptr_t)out & 15) == 0, "cost_volume: images/out must be 16-byte aligned");
+  CvParams p;
+  const int frc = cv_fill_params(p, images, B, S, H, W, C, depths, depth_volume, D, rots, trans, ref_idx, src_views, n_src, divisor,
+                                 dataset, cost_type);
+  if (frc != PGRF_OK) return frc;
+  p.out = out; p.err = err_flag;
+  p.groups = groups;
+  p.OC = groups > 0 ? groups : C;
+  const long long HW = (long long)H * W;
+  if (layout == PGRF_CV_BDCHW) { p.sC = HW; p.sD = HW * p.OC; p.sB = p.sD * D; }
+  else { p.sD = HW; p.sC = HW * D; p.sB = p.sC * p.OC; }
   // depth chunking: enough CTAs for >= ~4 waves of 148 SMs x 8 resident CTAs, chunks of >= 4 depths
   const long long ctas_per_chunk = (long long)((W + kCvThreads - 1) / kCvThreads) * H * B;
   int n_chunks = (int)((148LL * 8 * 4 + ctas_per_chunk - 1) / ctas_per_chunk);

@@ -15,6 +15,67 @@ from . import _lib
 _CHECK_UV = True   # the reference asserts uv in [-1,1] after every depth (:191); we check one flag per call
 
 
+class _SweepFn(torch.autograd.Function):
+    """torch.autograd.Function around the two C-ABI kernels (forward sweep, feature-map gradient)."""
+
+    @staticmethod
+    def forward(ctx, images, depth_t, rots, trans, meta):
+        lib = _lib.load()
+        B, S, H, W, C = images.shape
+        dev = images.device
+        use_volume, D = meta["use_volume"], meta["D"]
+        groups, out_layout = meta["groups"], meta["out_layout"]
+        OC = groups if groups > 0 else C
+        if out_layout == "bdchw":
+            store = torch.empty((B, D, OC, H, W), device=dev, dtype=torch.float32)
+        elif out_layout == "bdhwc":
+            store = torch.empty((B, D, H, W, OC), device=dev, dtype=torch.float32)
+        else:
+            store = torch.empty((B, OC, D, H, W), device=dev, dtype=torch.float32)
+        err = torch.zeros(1, device=dev, dtype=torch.int32)
+        views = (ctypes.c_int * len(meta["src_views"]))(*meta["src_views"])
+        with torch.cuda.device(dev):
+            rc = lib.pgrf_cost_volume_fwd(
+                _lib.ptr(images), B, S, H, W, C, None if use_volume else _lib.ptr(depth_t), _lib.ptr(depth_t) if use_volume else None,
+                D, _lib.ptr(rots), _lib.ptr(trans), meta["ref_idx"], views, len(meta["src_views"]), float(meta["divisor"]),
+                meta["dataset"], meta["cost"], _lib.CV_LAYOUT_IDS[out_layout], groups,
+                _lib.ptr(store), _lib.ptr(err), _lib.stream_ptr())
+        _lib.check(rc, "pgrf_cost_volume_fwd")
+        if _CHECK_UV and int(err.item()) != 0:
+            raise AssertionError("Wrong UV mapping, UV must be in [-1, 1]!")
+        ctx.meta = meta
+        ctx.save_for_backward(images, depth_t, rots, trans)
+        return store
+
+    @staticmethod
+    def backward(ctx, grad_store):
+        images, depth_t, rots, trans = ctx.saved_tensors
+        meta = ctx.meta
+        lib = _lib.load()
+        B, S, H, W, C = images.shape
+        groups, out_layout, D = meta["groups"], meta["out_layout"], meta["D"]
+        g = grad_store.float()
+        if groups > 0:                                             # (B,G,D,H,W): mean over C/G channels
+            cpg = C // groups
+            g = (g / cpg).repeat_interleave(cpg, dim=1)
+        if out_layout == "bdchw":
+            g = g.permute(0, 1, 3, 4, 2)
+        elif out_layout == "bcdhw":
+            g = g.permute(0, 2, 3, 4, 1)
+        g = g.contiguous()                                         # (B,D,H,W,C)
+        grad_images = torch.zeros_like(images)
+        views = (ctypes.c_int * len(meta["src_views"]))(*meta["src_views"])
+        use_volume = meta["use_volume"]
+        with torch.cuda.device(images.device):
+            rc = lib.pgrf_cost_volume_bwd(
+                _lib.ptr(g), _lib.ptr(images), B, S, H, W, C, None if use_volume else _lib.ptr(depth_t),
+                _lib.ptr(depth_t) if use_volume else None, D, _lib.ptr(rots), _lib.ptr(trans), meta["ref_idx"], views,
+                len(meta["src_views"]), float(meta["divisor"]), meta["dataset"], meta["cost"], _lib.ptr(grad_images),
+                _lib.stream_ptr())
+        _lib.check(rc, "pgrf_cost_volume_bwd")
+        return grad_images, None, None, None, None
+
+
 def _sweep(args, images, depths, trans, rots, depth_volume, cost_type, ref_idx, src_views, divisor,
            out_layout="bdchw", groups=0):
     name = args["dataset_name"]
@@ -25,44 +86,23 @@ def _sweep(args, images, depths, trans, rots, depth_volume, cost_type, ref_idx, 
     if out_layout not in _lib.CV_LAYOUT_IDS:
         raise ValueError(f"unknown out_layout {out_layout!r}")
     _lib.require_cuda(images, trans, rots)
-    if images.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError("panogrf_b200 cost volume: backward is not implemented yet "
-                                  "(the render path runs the MVS net under no_grad, init_net.py:255)")
-    lib = _lib.load()
     B, S, H, W, C = images.shape
     images = images.contiguous().float()
-    rots = rots.reshape(B, S, 3, 3).contiguous().float()
-    trans = trans.reshape(B, S, 3).contiguous().float()
+    rots = rots.reshape(B, S, 3, 3).contiguous().float().detach()
+    trans = trans.reshape(B, S, 3).contiguous().float().detach()
     dev = images.device
     use_volume = bool(args["contain_dnet"])
-    d_ptr = v_ptr = None
     if use_volume:
-        depth_volume = depth_volume.to(device=dev, dtype=torch.float32).contiguous()
-        D = depth_volume.shape[1]
-        assert depth_volume.shape == (B, D, H, W), "depth_volume must be (B,D,H,W)"
-        v_ptr = _lib.ptr(depth_volume)
+        # hypotheses carry no gradient (built under no_grad / detached, pipeline3_model.py:647,671)
+        depth_t = depth_volume.detach().to(device=dev, dtype=torch.float32).contiguous()
+        D = depth_t.shape[1]
+        assert depth_t.shape == (B, D, H, W), "depth_volume must be (B,D,H,W)"
     else:
-        depths = torch.as_tensor(depths, dtype=torch.float32, device=dev).reshape(-1).contiguous()
-        D = depths.numel()
-        d_ptr = _lib.ptr(depths)
-    OC = groups if groups > 0 else C
-    if out_layout == "bdchw":
-        store = torch.empty((B, D, OC, H, W), device=dev, dtype=torch.float32)
-    elif out_layout == "bdhwc":
-        store = torch.empty((B, D, H, W, OC), device=dev, dtype=torch.float32)
-    else:
-        store = torch.empty((B, OC, D, H, W), device=dev, dtype=torch.float32)
-    err = torch.zeros(1, device=dev, dtype=torch.int32)
-    views = (ctypes.c_int * len(src_views))(*src_views)
-    with torch.cuda.device(dev):
-        rc = lib.pgrf_cost_volume_fwd(
-            _lib.ptr(images), B, S, H, W, C, d_ptr, v_ptr, D, _lib.ptr(rots), _lib.ptr(trans),
-            ref_idx, views, len(src_views), float(divisor),
-            _lib.DATASET_IDS[name], _lib.COST_IDS[cost_type], _lib.CV_LAYOUT_IDS[out_layout], groups,
-            _lib.ptr(store), _lib.ptr(err), _lib.stream_ptr())
-    _lib.check(rc, "pgrf_cost_volume_fwd")
-    if _CHECK_UV and int(err.item()) != 0:
-        raise AssertionError("Wrong UV mapping, UV must be in [-1, 1]!")
+        depth_t = torch.as_tensor(depths, dtype=torch.float32, device=dev).detach().reshape(-1).contiguous()
+        D = depth_t.numel()
+    meta = dict(use_volume=use_volume, D=D, groups=groups, out_layout=out_layout, src_views=list(src_views), ref_idx=ref_idx,
+                divisor=divisor, dataset=_lib.DATASET_IDS[name], cost=_lib.COST_IDS[cost_type])
+    store = _SweepFn.apply(images, depth_t, rots, trans, meta)
     if groups > 0:
         return store                                               # (B,G,D,H,W)
     if out_layout == "bdchw":

@@ -58,6 +58,15 @@ def make_cv_inputs(name, seed=0, smooth_feats=False):
                 cost_type=c["cost_type"], mv=c.get("mv", False), curr_idx=c.get("curr_idx", 0))
 
 
+CV_BWD_CASES = ["cv_m3d_scalar", "cv_m3d_volume", "cv_m3d_dot", "cv_m3d_none", "cv_mv4_scalar", "cv_residential_vol"]
+
+
+def cv_bwd_weight(name, shape):
+    """Upstream gradient of the backward parity cases: d(loss)/d(out) with loss = sum(out * weight)."""
+    gen = torch.Generator().manual_seed(1000 + sum(map(ord, name)))
+    return torch.randn(*shape, generator=gen)
+
+
 # ------------------------------------------------------------------------------------------------
 # render path
 # ------------------------------------------------------------------------------------------------

@@ -195,3 +195,77 @@ def test_host_entry_point_matches_device_path():
                                    tr.ctypes.data, 1, views, 1, 0.0, 0, 0, 1, 0, out.ctypes.data)
     assert rc == 0, _lib.last_error()
     assert np.array_equal(out, dev_out)
+
+
+# ---- backward (torch.autograd.Function around pgrf_cost_volume_bwd) -------------------------------------------
+
+@pytest.mark.parametrize("name", cases.CV_BWD_CASES)
+@pytest.mark.parametrize("layout", ["bdchw", "bdhwc"])
+def test_backward_matches_reference_autograd(name, layout):
+    """d(sum(out*w))/d(images) against the gradient the reference's own autograd graph produced (tests/golden/*_bwd)."""
+    from panogrf_b200 import spherical_cost_volume as scv
+    inp = cases.make_cv_inputs(name)
+    images = inp["images"].cuda().requires_grad_(True)
+    kw = dict(depth_volume=None if inp["depth_volume"] is None else inp["depth_volume"].cuda(), cost_type=inp["cost_type"],
+              out_layout=layout)
+    if inp["mv"]:
+        out = scv.calculate_cost_volume_erp_multiview(inp["args"], images, inp["depths"], inp["trans"].cuda(), inp["rots"].cuda(),
+                                                      curr_idx=inp["curr_idx"], **kw)
+    else:
+        out = scv.calculate_cost_volume_erp(inp["args"], images, inp["depths"], inp["trans"].cuda(), inp["rots"].cuda(), **kw)
+    w = cases.cv_bwd_weight(name, out.shape).cuda()
+    (out * w).sum().backward()
+    gold = load_golden(name + "_bwd")["grad_images"]
+    assert images.grad.shape == gold.shape
+    # white-noise features: a 1-ulp footprint difference flips sign(warp - ref) for a few taps near ties
+    assert_close(images.grad, gold, rtol=1e-4, atol=2e-4, max_bad_frac=3e-3, what=f"{name}/{layout}")
+
+
+def test_backward_group_mean_and_linearity():
+    """groups>0 (fused group-wise mean) backward == backward of the explicit mean; gradient is linear in grad_out."""
+    from panogrf_b200 import spherical_cost_volume as scv
+    name = "cv_m3d_volume"
+    inp = cases.make_cv_inputs(name)
+    dv = inp["depth_volume"].cuda()
+    t, r = inp["trans"].cuda(), inp["rots"].cuda()
+
+    def grad_of(groups, scale):
+        images = inp["images"].cuda().requires_grad_(True)
+        out = scv.calculate_cost_volume_erp(inp["args"], images, inp["depths"], t, r, depth_volume=dv, groups=groups)
+        if groups == 0:
+            B, D, H, W, C = out.shape
+            out = out.reshape(B, D, H, W, 8, C // 8).mean(-1).permute(0, 4, 1, 2, 3)     # (B,G,D,H,W)
+        gen = torch.Generator().manual_seed(7)
+        w = torch.randn(out.shape, generator=gen).cuda() * scale
+        (out * w).sum().backward()
+        return images.grad
+
+    g_fused, g_explicit = grad_of(8, 1.0), grad_of(0, 1.0)
+    assert_close(g_fused, g_explicit, rtol=1e-4, atol=1e-5, what="group-mean backward")
+    assert_close(grad_of(8, 3.0), 3.0 * g_fused, rtol=1e-4, atol=1e-5, what="linearity")
+
+
+def test_backward_full_size_properties():
+    """configs[0] size: 'none' cost -> every source texel receives exactly the sum of bilinear weights that the forward
+    reads it with, so sum(grad_src) == sum(grad_out) (partition of unity), and the reference view gets no gradient."""
+    from panogrf_b200 import spherical_cost_volume as scv
+    B, H, W, C, D = 1, 256, 512, 32, 64
+    gen = torch.Generator().manual_seed(0)
+    images = torch.randn(B, 2, H, W, C, generator=gen).cuda().requires_grad_(True)
+    rots = torch.eye(3).repeat(B, 2, 1, 1).cuda()
+    trans = torch.tensor([[[0.0, 0.0, -0.5], [0.0, 0.0, 0.5]]]).cuda()
+    args = {"dataset_name": "m3d", "contain_dnet": False, "mono_uncertainty": False}
+    out = scv.calculate_cost_volume_erp(args, images, torch.linspace(0.5, 10, D), trans, rots, cost_type="none", out_layout="bdhwc")
+    w = torch.rand(out.shape, device="cuda")
+    (out * w).sum().backward()
+    g = images.grad
+    assert float(g[:, 1].abs().max()) == 0.0
+    total_in, total_out = float(w.double().sum()), float(g[:, 0].double().sum())
+    assert abs(total_in - total_out) <= 1e-4 * total_in
+    # abs_diff: ref gradient = -(sum over d of the warped-side gradient signs): antisymmetry of the two sides
+    images2 = images.detach().clone().requires_grad_(True)
+    out2 = scv.calculate_cost_volume_erp(args, images2, torch.linspace(0.5, 10, D), trans, rots, cost_type="abs_diff",
+                                         out_layout="bdhwc")
+    out2.sum().backward()
+    g2 = images2.grad
+    assert abs(float(g2[:, 0].double().sum()) + float(g2[:, 1].double().sum())) <= 1e-3 * float(g2[:, 1].double().abs().sum())

@@ -65,3 +65,20 @@ def test_group_mean_and_hypotheses():
     mu = torch.rand(1, 1, 4, 4) * 8 + 1
     vol = ocv.mono_guided_hypotheses(mu, ks, 0.5, 0.1, 10.0, 59)
     assert vol.shape == (1, 64, 4, 4) and bool((vol[:, 1:] >= vol[:, :-1]).all())
+
+
+@pytest.mark.parametrize("name", cases.CV_BWD_CASES)
+def test_oracle_gradient_matches_reference_autograd(name):
+    """d(sum(out*w))/d(images) of the oracle (torch autograd through its gather restatement) == the reference's."""
+    inp = cases.make_cv_inputs(name)
+    images = inp["images"].clone().requires_grad_(True)
+    fn = ocv.calculate_cost_volume_erp_multiview if inp["mv"] else ocv.calculate_cost_volume_erp
+    kw = dict(depth_volume=inp["depth_volume"], cost_type=inp["cost_type"])
+    if inp["mv"]:
+        kw["curr_idx"] = inp["curr_idx"]
+    out = fn(inp["args"], images, inp["depths"], inp["trans"], inp["rots"], **kw)
+    w = cases.cv_bwd_weight(name, out.shape)
+    (out * w).sum().backward()
+    gold = load_golden(name + "_bwd")
+    assert abs(float(w.double().sum()) - float(gold["weight_sum"])) < 1e-6
+    assert_close(images.grad, gold["grad_images"], rtol=1e-4, atol=1e-4, max_bad_frac=2e-3, what=name)
