@@ -294,6 +294,7 @@ def main():
                                     "sample": f"8192 random rays of the view, oracle/render.py torch-CPU fp32, {t:.1f} s"}
         line["cost_volume"] = time_cost_volume(torch, pg, flush, peaks)
         line["project_gather"] = time_project_gather(torch, que_d, ref_d, flush, peaks)
+        line["depth_guided"] = time_depth_guided(torch, que_d, ref_d)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -301,7 +302,7 @@ def main():
 
 
 def rays_per_launch(net):
-    return int(net.rays_per_launch or (32768 if net.mlp_dtype == "bf16" else 4096))
+    return int(net.rays_per_launch or (131072 if net.mlp_dtype == "bf16" else 4096))
 
 
 def time_stages(torch, net, que_d, ref_d, flush):
@@ -312,7 +313,13 @@ def time_stages(torch, net, que_d, ref_d, flush):
     cfg = net.cfg
     ctx = net._context(que_d, ref_d)
     rn = min(rays_per_launch(net), que_d["coords"].shape[1])
-    coords = que_d["coords"][0, :rn].float().contiguous()
+    # whole ERP rows spread evenly over the latitudes (the first rows alone are all next to a pole, where the source
+    # footprints scatter and the pass is ~1.5x slower than the view average)
+    n_rows = max(1, rn // W)
+    rn = n_rows * W
+    total_rows = que_d["coords"].shape[1] // W
+    row_ids = ((torch.arange(n_rows, dtype=torch.float64) + 0.5) * total_rows / n_rows).long().clamp(max=total_rows - 1)
+    coords = que_d["coords"][0].reshape(total_rows, W, 2)[row_ids.to(que_d["coords"].device)].reshape(rn, 2).float().contiguous()
     dev = coords.device
     depth = coarse_depth_table(cfg, DN, cfg["use_disp"]).to(dev)
     outs = {"pixel_colors_nr": torch.empty(1, rn, 3, device=dev), "density_nr": torch.empty(1, rn, DN, device=dev),
@@ -469,11 +476,64 @@ def time_cost_volume(torch, pg, flush, peaks):
     ms = sorted(ts)[len(ts) // 2]
     vox = B * D * Hc * Wc
     alg = vox * C * 4 + B * 2 * Hc * Wc * C * 4 + D * 4
+
+    def median_ms(fn, n=7):
+        for _ in range(2):
+            fn()
+        t = []
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1))
+        return sorted(t)[len(t) // 2]
+
+    ms_cl = median_ms(lambda: pg.calculate_cost_volume_erp(args, images, depths, trans, rots, out_layout="bdhwc"))
+    # backward: d/d(images) of the same volume (reads the 1.07 GB upstream gradient once, vector atomics into 2 maps)
+    img_g = images.clone().requires_grad_(True)
+    out = pg.calculate_cost_volume_erp(args, img_g, depths, trans, rots, out_layout="bdhwc")
+    gout = torch.ones_like(out)
+    ms_bwd = median_ms(lambda: torch.autograd.grad(out, img_g, gout, retain_graph=True), n=5)
+    del out, gout
     return {"workload": "configs[0]: 2 views 256x512 C32 D64 abs_diff, reference layout (B,D,C,H,W)",
             "voxels_per_s": vox / ms * 1e3, "ms": ms,
             "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": None,
-                         "bytes_per_voxel": alg / vox, "peak_src": peaks["src"]}}
+                         "bytes_per_voxel": alg / vox, "peak_src": peaks["src"]},
+            "channels_last": {"ms": ms_cl, "voxels_per_s": vox / ms_cl * 1e3, "frac": alg / ms_cl / 1e6 / peaks["hbm_gbs"]},
+            "backward": {"ms": ms_bwd, "voxels_per_s": vox / ms_bwd * 1e3, "frac": alg / ms_bwd / 1e6 / peaks["hbm_gbs"],
+                         "note": "grad w.r.t. feature maps through torch.autograd.Function (includes the zero-fill of grad_images)"}}
+
+
+def time_depth_guided(torch, que_d, ref_d):
+    """Depth-prior sample placement (diner branch): every ray x 1000 linear candidates x RFN views -> 64 samples, one kernel."""
+    from panogrf_b200.render_ops import depth_guided_placement
+    dev = que_d["coords"].device
+    rn = que_d["coords"].shape[1]
+    g = torch.Generator(device=dev).manual_seed(0)
+    cfg = {"dataset_name": "m3d", "height": H, "width": W, "min_depth": 0.5, "max_depth": 15.0, "n_candidates": 1000,
+           "n_samples": 64, "n_gaussian": 15, "backface_culling": True, "contain_uniform": False}
+    ref = dict(ref_d)
+    ref["mvs_depth"] = 3.0 + torch.rand(RFN, 1, H, W, device=dev, generator=g)
+    ref["mvs_uncert"] = torch.full((RFN, 1, H, W), 0.01, device=dev)
+    ref["mvs_normal"] = torch.randn(RFN, 3, H, W, device=dev, generator=g)
+    fill, ga = torch.rand(rn, 64, device=dev, generator=g), torch.randn(rn, 15, device=dev, generator=g)
+    f = lambda: depth_guided_placement(cfg, que_d, ref, fill, ga)
+    f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    return {"workload": f"{rn} rays x 1000 candidates x {RFN} views -> 64 samples/ray (49 likelihood + 15 gaussian, fill-up, sort)",
+            "ms": ms, "candidate_views_per_s": rn * 1000.0 * RFN / ms * 1e3,
+            "note": "compute bound (atan2/acos/erf per candidate-view); writes only (rn,64) floats"}
 
 
 if __name__ == "__main__":

@@ -78,6 +78,24 @@ struct Rays16Params {
     umma::commit(bar); }                                                    \
   mbar_wait(bar, phase); phase ^= 1; umma::fence_after_sync();
 
+// two-pass softmax(q.k) V with the exact running maximum (fallback of the bounded single pass below)
+static __device__ __noinline__ void attention_exact(float q0, float q1, float q2, float q3, const float4* Kh, const float4* Vh, int dn,
+                                                    float& den, float& o0, float& o1, float& o2, float& o3) {
+  float mx = -INFINITY;
+  for (int j = 0; j < dn; ++j) {
+    const float4 k = Kh[j];
+    mx = fmaxf(mx, q0 * k.x + q1 * k.y + q2 * k.z + q3 * k.w);
+  }
+  den = 0.f; o0 = 0.f; o1 = 0.f; o2 = 0.f; o3 = 0.f;
+  for (int j = 0; j < dn; ++j) {
+    const float4 k = Kh[j];
+    const float4 vv = Vh[j];
+    const float e = fast_exp(q0 * k.x + q1 * k.y + q2 * k.z + q3 * k.w - mx);
+    den += e;
+    o0 = fmaf(e, vv.x, o0); o1 = fmaf(e, vv.y, o1); o2 = fmaf(e, vv.z, o2); o3 = fmaf(e, vv.w, o3);
+  }
+}
+
 __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Rays16Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
@@ -122,6 +140,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
   const int Mv = rpt * dn;
 
   __shared__ int s_tile[kWGr];
+  __shared__ float4 s_kn[kWGr][4];
   int static_tile = blockIdx.x * kWGr + wg;
 #pragma unroll 1
   while (true) {
@@ -176,8 +195,19 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
       for (int i = 0; i < 16; ++i) q[i] *= 0.5f;            // q / temperature, temperature = sqrt(d_k) = 2
       float kv[16];
       umma::ld16(tq + 16, kv);
+      float kn2[4];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) K4[h * RROWS + m] = make_float4(kv[4 * h], kv[4 * h + 1], kv[4 * h + 2], kv[4 * h + 3]);
+      for (int h = 0; h < 4; ++h) {
+        K4[h * RROWS + m] = make_float4(kv[4 * h], kv[4 * h + 1], kv[4 * h + 2], kv[4 * h + 3]);
+        kn2[h] = kv[4 * h] * kv[4 * h] + kv[4 * h + 1] * kv[4 * h + 1] + kv[4 * h + 2] * kv[4 * h + 2] + kv[4 * h + 3] * kv[4 * h + 3];
+      }
+      // largest key norm of the tile, per head: |q||k|max bounds every score, so the softmax needs no separate max pass
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kn2[h] = fmaxf(kn2[h], __shfl_xor_sync(0xffffffffu, kn2[h], o));
+      }
+      if (lane == 0) s_kn[wg][wq] = make_float4(kn2[0], kn2[1], kn2[2], kn2[3]);
       umma::ld16(tq + 32, kv);
 #pragma unroll
       for (int h = 0; h < 4; ++h) V4[h * RROWS + m] = make_float4(kv[4 * h], kv[4 * h + 1], kv[4 * h + 2], kv[4 * h + 3]);
@@ -189,26 +219,44 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
     {
       const int r0 = (min(m, Mv - 1) / dn) * dn;
       const bool masked = !(V > 1);
+      float kmax[4];
+      {
+        const float4 a0 = s_kn[wg][0], a1 = s_kn[wg][1], a2 = s_kn[wg][2], a3 = s_kn[wg][3];
+        kmax[0] = sqrtf(fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)));
+        kmax[1] = sqrtf(fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y)));
+        kmax[2] = sqrtf(fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z)));
+        kmax[3] = sqrtf(fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w)));
+      }
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
         const float q0 = q[4 * h], q1 = q[4 * h + 1], q2 = q[4 * h + 2], q3 = q[4 * h + 3];
         const float4* Kh = K4 + h * RROWS + r0;
         const float4* Vh = V4 + h * RROWS + r0;
-        float mx = -INFINITY;
-#pragma unroll 4
-        for (int j = 0; j < dn; ++j) {
-          const float4 k = Kh[j];
-          mx = fmaxf(mx, masked ? -1e9f : q0 * k.x + q1 * k.y + q2 * k.z + q3 * k.w);
-        }
         float den = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+        if (masked) {                                   // all scores equal -> uniform weights
 #pragma unroll 4
-        for (int j = 0; j < dn; ++j) {
-          const float4 k = Kh[j];
-          const float4 vv = Vh[j];
-          const float sc = masked ? -1e9f : q0 * k.x + q1 * k.y + q2 * k.z + q3 * k.w;
-          const float e = fast_exp(sc - mx);
-          den += e;
-          o0 = fmaf(e, vv.x, o0); o1 = fmaf(e, vv.y, o1); o2 = fmaf(e, vv.z, o2); o3 = fmaf(e, vv.w, o3);
+          for (int j = 0; j < dn; ++j) { const float4 vv = Vh[j]; o0 += vv.x; o1 += vv.y; o2 += vv.z; o3 += vv.w; }
+          den = (float)dn;
+        } else {
+          // softmax(s) == softmax(s - c) for any c; c = |q||k|max >= max_j s_j (Cauchy-Schwarz) keeps exp() <= 1
+          const float bound = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3) * kmax[h];
+          const float2 qa = make_float2(q0, q1), qb = make_float2(q2, q3), c0 = make_float2(-bound, 0.f);
+          float2 oa = make_float2(0.f, 0.f), ob = make_float2(0.f, 0.f);
+#pragma unroll 4
+          for (int j = 0; j < dn; ++j) {
+            const float4 k = Kh[j];
+            const float4 vv = Vh[j];
+            float2 t = ffma2(qa, make_float2(k.x, k.y), c0);
+            t = ffma2(qb, make_float2(k.z, k.w), t);
+            const float e = fast_exp(t.x + t.y);
+            den += e;
+            const float2 ee = make_float2(e, e);
+            oa = ffma2(ee, make_float2(vv.x, vv.y), oa);
+            ob = ffma2(ee, make_float2(vv.z, vv.w), ob);
+          }
+          o0 = oa.x; o1 = oa.y; o2 = ob.x; o3 = ob.y;
+          // the bound was more than ~46 above the true maximum (huge, misaligned q/k): small terms were flushed -> exact path
+          if (!(den >= 1e-20f)) attention_exact(q0, q1, q2, q3, Kh, Vh, dn, den, o0, o1, o2, o3);
         }
         const float inv = 1.f / den;
         ao[4 * h] = o0 * inv; ao[4 * h + 1] = o1 * inv; ao[4 * h + 2] = o2 * inv; ao[4 * h + 3] = o3 * inv;

@@ -161,7 +161,7 @@ class NeuralRayBaseRenderer(nn.Module):
         "render_depth": False, "render_uncert": False, "debug": False, "use_disp": True,
     }
     #: rays per kernel launch (the reference's ray_batch_num only bounds ITS activation memory; here it bounds the
-    #: inter-kernel workspaces).  None = 32768 for the bf16 path (only the 272 B/sample F2 tiles exist; larger launches
+    #: inter-kernel workspaces).  None = 131072 for the bf16 path (only the 272 B/sample F2 tiles exist; larger launches
     #: amortise the per-CTA weight load and the tail), 4096 for the fp32 path (F1 tiles: 38.9 KB per 64 samples).
     rays_per_launch = None
 
@@ -450,7 +450,7 @@ class NeuralRayBaseRenderer(nn.Module):
         fdn = int(cfg["fine_depth_sample_num"])
         fine_total = fdn + (N if cfg["fine_depth_use_all"] else 0)
         fine = alloc(fine_total) if c2f else None
-        rpl = self.rays_per_launch or (32768 if self.mlp_dtype == "bf16" else 4096)
+        rpl = self.rays_per_launch or (131072 if self.mlp_dtype == "bf16" else 4096)
         d2 = depth[0]
         for r0 in range(0, rn, int(rpl)):
             n = min(int(rpl), rn - r0)
@@ -487,7 +487,7 @@ class NeuralRayBaseRenderer(nn.Module):
             if agg.cfg["sample_num"] != n:
                 raise RuntimeError(f"The size of tensor a ({n}) must match the size of tensor b "
                                    f"({agg.cfg['sample_num']}) at non-singleton dimension 1")   # ibrnet.py:358
-        rpl = self.rays_per_launch or (32768 if self.mlp_dtype == "bf16" else 4096)
+        rpl = self.rays_per_launch or (131072 if self.mlp_dtype == "bf16" else 4096)
         chunk = max(1, min(int(rpl), rn))
         va = _lib.RenderViewArgs()
         a = va.pass_
