@@ -59,6 +59,27 @@ __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128
 // ---- epilogues (thread = row m).  Kept out of line and rolled: the kernel is a long straight-line sequence of
 // stages executed once per tile by only 8 warps, so instruction-cache footprint matters more than unrolling. ----
 // dst chunks [0,nchunks) = bf16( act(acc + bias) )
+// acc[16] (+bias) -> activation, as 8 packed fp32 pairs (FADD2 / FMUL2: one issue slot per two elements)
+__device__ __forceinline__ void act_pairs(float (&v)[16], const float* __restrict__ bias, int act) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b = b4[i];
+    const float2 lo = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
+    const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+    v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
+  }
+  if (act == ACT_ELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 r = elu_pair(make_float2(v[2 * i], v[2 * i + 1]));
+      v[2 * i] = r.x; v[2 * i + 1] = r.y;
+    }
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+}
 static __device__ __noinline__ void epi_act_store(uint32_t taddr, const float* __restrict__ bias, unsigned char* dst, int m,
                                                   int nchunks, int act) {
   // two chunks (16 accumulator columns) per TMEM round trip; nchunks is even for every caller
@@ -66,19 +87,7 @@ static __device__ __noinline__ void epi_act_store(uint32_t taddr, const float* _
   for (int c = 0; c < nchunks; c += 2) {
     float v[16];
     umma::ld16(taddr + 8 * c, v);
-    const float4* b4 = reinterpret_cast<const float4*>(bias + 8 * c);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 b = b4[i];
-      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
-    if (act == ACT_ELU) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : fast_exp(v[i]) - 1.f;   // FSETP + FSEL, no branch
-    } else if (act == ACT_RELU) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-    }
+    act_pairs(v, bias + 8 * c, act);
     umma::store_chunk(dst, ROWS, c, m, v);
     umma::store_chunk(dst, ROWS, c + 1, m, v + 8);
   }
@@ -88,25 +97,14 @@ static __device__ __noinline__ void epi_act_store(uint32_t taddr, const float* _
 template <int NOUT>
 static __device__ __noinline__ void epi_act_gemv(uint32_t taddr, const float* __restrict__ bias, unsigned char* dst, int m,
                                                  int nchunks, int act, const float* __restrict__ Wsm, int K, float (&out)[NOUT]) {
+  float2 acc[NOUT];                      // even / odd k partial sums (FFMA2)
 #pragma unroll
-  for (int j = 0; j < NOUT; ++j) out[j] = 0.f;
+  for (int j = 0; j < NOUT; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int c = 0; c < nchunks; c += 2) {
     float v[16];
     umma::ld16(taddr + 8 * c, v);
-    const float4* b4 = reinterpret_cast<const float4*>(bias + 8 * c);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 b = b4[i];
-      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
-    if (act == ACT_ELU) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : fast_exp(v[i]) - 1.f;
-    } else if (act == ACT_RELU) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-    }
+    act_pairs(v, bias + 8 * c, act);
     if (dst) {
       umma::store_chunk(dst, ROWS, c, m, v);
       umma::store_chunk(dst, ROWS, c + 1, m, v + 8);
@@ -117,11 +115,13 @@ static __device__ __noinline__ void epi_act_gemv(uint32_t taddr, const float* __
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 w = w4[i];
-        out[j] = fmaf(v[4 * i], w.x, out[j]); out[j] = fmaf(v[4 * i + 1], w.y, out[j]);
-        out[j] = fmaf(v[4 * i + 2], w.z, out[j]); out[j] = fmaf(v[4 * i + 3], w.w, out[j]);
+        acc[j] = ffma2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(w.x, w.y), acc[j]);
+        acc[j] = ffma2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(w.z, w.w), acc[j]);
       }
     }
   }
+#pragma unroll
+  for (int j = 0; j < NOUT; ++j) out[j] = acc[j].x + acc[j].y;
 }
 // first accumulator column (+bias) of a padded N=16 output layer
 __device__ __forceinline__ float epi_scalar(uint32_t taddr, const float* __restrict__ bias) {
@@ -162,25 +162,35 @@ __device__ __forceinline__ float4 tap4_rec(const float4* __restrict__ base, cons
 // weighted mean / variance over the V views of sample t (fused_mean_variance, ibrnet.py:112-116) of the 40-wide
 // rgb_feat' block in P (chunks 0..4) -> E chunks 0..4 (mean) and 5..9 (variance), written to row m
 template <int V>
-__device__ __forceinline__ void pool_views(const unsigned char* P, unsigned char* E, int t, int T, int m, const float (&w)[V]) {
+__device__ __forceinline__ void pool_views(const unsigned char* P, unsigned char* E, int t, int T, int v, const float (&w)[V]) {
+  // the V threads of a sample split the five 8-channel chunks between them and each writes its results to all V rows
+  // (every (view, sample) row of base_fc.0 sees the same pooled statistics); packed fp32 pairs (FFMA2)
+  if (v >= V) return;
 #pragma unroll 1
-  for (int c = 0; c < 5; ++c) {
+  for (int c = v; c < 5; c += V) {
     float x[V][8];
 #pragma unroll
     for (int vv = 0; vv < V; ++vv) umma::load_chunk(P, ROWS, c, vv * T + t, x[vv]);
     float mu[8], var[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float a0 = 0.f;
+    for (int i = 0; i < 8; i += 2) {
+      float2 a0 = fmul2(make_float2(x[0][i], x[0][i + 1]), make_float2(w[0], w[0]));
 #pragma unroll
-      for (int vv = 0; vv < V; ++vv) a0 += x[vv][i] * w[vv];
-      float b0 = 0.f;
+      for (int vv = 1; vv < V; ++vv) a0 = ffma2(make_float2(x[vv][i], x[vv][i + 1]), make_float2(w[vv], w[vv]), a0);
+      const float2 na = make_float2(-a0.x, -a0.y);
+      float2 b0 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int vv = 0; vv < V; ++vv) b0 += w[vv] * ((x[vv][i] - a0) * (x[vv][i] - a0));
-      mu[i] = a0; var[i] = b0;
+      for (int vv = 0; vv < V; ++vv) {
+        const float2 d = fadd2(make_float2(x[vv][i], x[vv][i + 1]), na);
+        b0 = ffma2(make_float2(w[vv], w[vv]), fmul2(d, d), b0);
+      }
+      mu[i] = a0.x; mu[i + 1] = a0.y; var[i] = b0.x; var[i + 1] = b0.y;
     }
-    umma::store_chunk(E, ROWS, c, m, mu);
-    umma::store_chunk(E, ROWS, 5 + c, m, var);
+#pragma unroll
+    for (int vv = 0; vv < V; ++vv) {
+      umma::store_chunk(E, ROWS, c, vv * T + t, mu);
+      umma::store_chunk(E, ROWS, 5 + c, vv * T + t, var);
+    }
   }
 }
 
@@ -229,6 +239,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
 
   const int T = p.T, M = p.M;
   const int v = min(m / T, V - 1), t = m % T;
+  const int vrow = m / T;             // unclamped: rows beyond the V*T valid ones take no share of the pooling work
   const float wgt = 1.f / ((float)V + 1e-8f);
 
   __shared__ int s_tile[kWG];
@@ -419,11 +430,11 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     float w0n[V];
 #pragma unroll
     for (int vv = 0; vv < V; ++vv) w0n[vv] = SF[SF_W0 * ROWS + vv * T + t] * wgt;
-    pool_views<V>(P, E, t, T, m, w0n);
+    pool_views<V>(P, E, t, T, vrow, w0n);
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E, ROWS, Wb + W16(M_BASE0), 64, 64, 80, true); STAGE_END()
 #pragma unroll
     for (int vv = 0; vv < V; ++vv) w0n[vv] = wgt;
-    pool_views<V>(P, E, t, T, m, w0n);
+    pool_views<V>(P, E, t, T, vrow, w0n);
     STAGE_BEGIN() umma::gemm_issue(tb + 0, E, ROWS, Wb + W16(M_BASE0) + 10 * 64 * 16, 64, 64, 80, true); STAGE_END()
     epi_act_store(tq + 0, Bias + B16(M_BASE0), E + E_H64, m, 8, ACT_ELU);
 

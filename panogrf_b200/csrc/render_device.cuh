@@ -31,6 +31,31 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return d;
 }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// ELU(alpha=1) of two values with packed arithmetic: FMUL2 + 2 MUFU + FADD2 + 2 (FSETP+FSEL)
+__device__ __forceinline__ float2 elu_pair(float2 v) {
+  const float2 t = fmul2(v, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 r = fadd2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(-1.f, -1.f));
+  return make_float2(v.x > 0.f ? v.x : r.x, v.y > 0.f ? v.y : r.y);
+}
 __device__ __forceinline__ float elu1(float x) { return fmaxf(x, 0.f) + fminf(fast_exp(x) - 1.f, 0.f); }
 __device__ __forceinline__ float sigmoidf(float x) { return fast_rcp(1.f + fast_exp(-x)); }
 __device__ __forceinline__ float softplusf(float x) { return x > 20.f ? x : log1pf(fast_exp(x)); }
