@@ -163,33 +163,39 @@ __device__ __forceinline__ float4 tap4_rec(const float4* __restrict__ base, cons
 // rgb_feat' block in P (chunks 0..4) -> E chunks 0..4 (mean) and 5..9 (variance), written to row m
 template <int V>
 __device__ __forceinline__ void pool_views(const unsigned char* P, unsigned char* E, int t, int T, int v, const float (&w)[V]) {
-  // the V threads of a sample split the five 8-channel chunks between them and each writes its results to all V rows
-  // (every (view, sample) row of base_fc.0 sees the same pooled statistics); packed fp32 pairs (FFMA2)
+  // the V threads of a sample split the 40 channels in units of 4 (half a k-chunk) and each writes its results to all
+  // V rows (every (view, sample) row of base_fc.0 sees the same pooled statistics); packed fp32 pairs (FFMA2)
   if (v >= V) return;
 #pragma unroll 1
-  for (int c = v; c < 5; c += V) {
-    float x[V][8];
+  for (int u = v; u < 10; u += V) {
+    const int c = u >> 1, hb = (u & 1) * 8;                      // chunk, byte offset of the half inside the 16-byte row
+    float2 x[V][2];
 #pragma unroll
-    for (int vv = 0; vv < V; ++vv) umma::load_chunk(P, ROWS, c, vv * T + t, x[vv]);
-    float mu[8], var[8];
+    for (int vv = 0; vv < V; ++vv) {
+      const uint2 q = *reinterpret_cast<const uint2*>(P + ((size_t)c * ROWS + vv * T + t) * 16 + hb);
+      x[vv][0] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+      x[vv][1] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+    }
+    uint2 mu, var;
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      float2 a0 = fmul2(make_float2(x[0][i], x[0][i + 1]), make_float2(w[0], w[0]));
+    for (int i = 0; i < 2; ++i) {
+      float2 a0 = fmul2(x[0][i], make_float2(w[0], w[0]));
 #pragma unroll
-      for (int vv = 1; vv < V; ++vv) a0 = ffma2(make_float2(x[vv][i], x[vv][i + 1]), make_float2(w[vv], w[vv]), a0);
+      for (int vv = 1; vv < V; ++vv) a0 = ffma2(x[vv][i], make_float2(w[vv], w[vv]), a0);
       const float2 na = make_float2(-a0.x, -a0.y);
       float2 b0 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int vv = 0; vv < V; ++vv) {
-        const float2 d = fadd2(make_float2(x[vv][i], x[vv][i + 1]), na);
+        const float2 d = fadd2(x[vv][i], na);
         b0 = ffma2(make_float2(w[vv], w[vv]), fmul2(d, d), b0);
       }
-      mu[i] = a0.x; mu[i + 1] = a0.y; var[i] = b0.x; var[i + 1] = b0.y;
+      (i == 0 ? mu.x : mu.y) = umma::pack2(a0.x, a0.y);
+      (i == 0 ? var.x : var.y) = umma::pack2(b0.x, b0.y);
     }
 #pragma unroll
     for (int vv = 0; vv < V; ++vv) {
-      umma::store_chunk(E, ROWS, c, vv * T + t, mu);
-      umma::store_chunk(E, ROWS, 5 + c, vv * T + t, var);
+      *reinterpret_cast<uint2*>(E + ((size_t)c * ROWS + vv * T + t) * 16 + hb) = mu;
+      *reinterpret_cast<uint2*>(E + ((size_t)(5 + c) * ROWS + vv * T + t) * 16 + hb) = var;
     }
   }
 }
@@ -339,9 +345,12 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
         for (int i = 0; i < 8; ++i) x[i] = i < 3 ? rgb_in[i] : 0.f;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = elu1(df[i] + Bias[B16(M_RD1) + 8 * c + i]);
-        x[i] = (c < 4 || i < 3) ? x[i] + d : 0.f;
+      for (int i = 0; i < 8; i += 2) {
+        const float2 bb = *reinterpret_cast<const float2*>(Bias + B16(M_RD1) + 8 * c + i);
+        const float2 d = elu_pair(fadd2(make_float2(df[i], df[i + 1]), bb));
+        const float2 xs = fadd2(make_float2(x[i], x[i + 1]), d);
+        x[i] = (c < 4 || i < 3) ? xs.x : 0.f;
+        x[i + 1] = (c < 4 || i + 1 < 3) ? xs.y : 0.f;
       }
       umma::store_chunk(P, ROWS, c, m, x);     // P_IMG chunks 0..3, P_RGB = chunk 4
     }
@@ -445,10 +454,13 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       float r[8], sx[8];
       umma::ld8(tq + 64 + 8 * c, r);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xv = elu1(r[i] + Bias[B16(M_BASE1) + 8 * c + i]);
-        XF[(8 * c + i) * ROWS + m] = xv;
-        sx[i] = xv * wgt;
+      for (int i = 0; i < 8; i += 2) {
+        const float2 bb = *reinterpret_cast<const float2*>(Bias + B16(M_BASE1) + 8 * c + i);
+        const float2 xv = elu_pair(fadd2(make_float2(r[i], r[i + 1]), bb));
+        XF[(8 * c + i) * ROWS + m] = xv.x;
+        XF[(8 * c + i + 1) * ROWS + m] = xv.y;
+        const float2 sv = fmul2(xv, make_float2(wgt, wgt));
+        sx[i] = sv.x; sx[i + 1] = sv.y;
       }
       umma::store_chunk(E + E_HV, ROWS, c, m, sx);      // H64 is dead: its MMA completed
     }
@@ -463,10 +475,14 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
         float r[8], sx[8];
         umma::ld8(tq + 8 * c, r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xv = XF[(8 * c + i) * ROWS + m] + elu1(r[i] + Bias[B16(M_VFC1) + 8 * c + i]);   // x = x + x_res
-          XF[(8 * c + i) * ROWS + m] = xv;
-          sx[i] = xv * vis1;
+        for (int i = 0; i < 8; i += 2) {
+          const float2 bb = *reinterpret_cast<const float2*>(Bias + B16(M_VFC1) + 8 * c + i);
+          const float2 xo = make_float2(XF[(8 * c + i) * ROWS + m], XF[(8 * c + i + 1) * ROWS + m]);
+          const float2 xv = fadd2(xo, elu_pair(fadd2(make_float2(r[i], r[i + 1]), bb)));   // x = x + x_res
+          XF[(8 * c + i) * ROWS + m] = xv.x;
+          XF[(8 * c + i + 1) * ROWS + m] = xv.y;
+          const float2 sv = fmul2(xv, make_float2(vis1, vis1));
+          sx[i] = sv.x; sx[i + 1] = sv.y;
         }
         umma::store_chunk(E + E_HV, ROWS, c, m, sx);
       }

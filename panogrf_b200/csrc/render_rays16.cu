@@ -58,7 +58,10 @@ static __device__ __noinline__ void epi_elu_store(uint32_t taddr, const float* _
     float v[16];
     umma::ld16(taddr + 8 * c, v);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = elu1(v[i] + bias[8 * c + i]);
+    for (int i = 0; i < 16; i += 2) {
+      const float2 r = elu_pair(fadd2(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2*>(bias + 8 * c + i)));
+      v[i] = r.x; v[i + 1] = r.y;
+    }
     umma::store_chunk(dst, RROWS, c, m, v);
     umma::store_chunk(dst, RROWS, c + 1, m, v + 8);
   }
@@ -182,7 +185,11 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
     {
       umma::ld16(tq, g16);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) g16[i] = elu1(g16[i] + Bias[B16(M_GEO1) + i]) + PE[sidx * 16 + i];
+      for (int i = 0; i < 16; i += 2) {
+        const float2 r = fadd2(elu_pair(fadd2(make_float2(g16[i], g16[i + 1]), *reinterpret_cast<const float2*>(Bias + B16(M_GEO1) + i))),
+                               *reinterpret_cast<const float2*>(PE + sidx * 16 + i));
+        g16[i] = r.x; g16[i + 1] = r.y;
+      }
       umma::store_chunk(G + R_G16, RROWS, 0, m, g16);
       umma::store_chunk(G + R_G16, RROWS, 1, m, g16 + 8);
     }
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
       float h1[16], s4[4];
       reg_layer<16, 16, 16>(x, W32 + WOFF(L_OG0), W32 + BOFF(L_OG0), h1);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) h1[i] = elu1(h1[i]);
+      for (int i = 0; i < 16; i += 2) { const float2 r = elu_pair(make_float2(h1[i], h1[i + 1])); h1[i] = r.x; h1[i + 1] = r.y; }
       reg_layer<16, 1, 4>(h1, W32 + WOFF(L_OG1), W32 + BOFF(L_OG1), s4);
       RV[RV2_SIGMA * 256 + m] = fmaxf(s4[0], 0.f);
     }

@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 cfg = bench.cfg_dict()
 cfg["mlp_dtype"] = os.environ.get("PGRF_MLP", "bf16")
 net = pg.NeuralRayBaseRenderer(cfg).to(dev).eval()
-net.rays_per_launch = 4096
+net.rays_per_launch = int(os.environ.get("PGRF_RPL", "4096"))
 que, ref = bench.make_inputs(torch, rows=(250, 250 + 2 * net.rays_per_launch // bench.W))
 que_d = {k: v.to(dev) for k, v in que.items()}
 ref_d = {k: v.to(dev) for k, v in ref.items()}
