@@ -143,11 +143,13 @@ __device__ __forceinline__ float4 tap4_rec(const float4* __restrict__ base, cons
   const float4 nw = ldg4(base), ne = ldg4(base + sx), sw = ldg4(base + sy), se = ldg4(base + sy + sx);
   const float tx1 = 1.f - f.tx, ty1 = 1.f - f.ty;
   const float wnw = tx1 * ty1, wne = f.tx * ty1, wsw = tx1 * f.ty, wse = f.tx * f.ty;
-  float4 o;
-  o.x = nw.x * wnw; o.y = nw.y * wnw; o.z = nw.z * wnw; o.w = nw.w * wnw;
-  o.x = fmaf(ne.x, wne, o.x); o.y = fmaf(ne.y, wne, o.y); o.z = fmaf(ne.z, wne, o.z); o.w = fmaf(ne.w, wne, o.w);
-  o.x = fmaf(sw.x, wsw, o.x); o.y = fmaf(sw.y, wsw, o.y); o.z = fmaf(sw.z, wsw, o.z); o.w = fmaf(sw.w, wsw, o.w);
-  o.x = fmaf(se.x, wse, o.x); o.y = fmaf(se.y, wse, o.y); o.z = fmaf(se.z, wse, o.z); o.w = fmaf(se.w, wse, o.w);
+  // same products and accumulation order (nw, ne, sw, se) as the scalar form, two channels per instruction
+  const float2 w0 = make_float2(wnw, wnw), w1 = make_float2(wne, wne), w2 = make_float2(wsw, wsw), w3 = make_float2(wse, wse);
+  float2 lo = fmul2(make_float2(nw.x, nw.y), w0), hi = fmul2(make_float2(nw.z, nw.w), w0);
+  lo = ffma2(make_float2(ne.x, ne.y), w1, lo); hi = ffma2(make_float2(ne.z, ne.w), w1, hi);
+  lo = ffma2(make_float2(sw.x, sw.y), w2, lo); hi = ffma2(make_float2(sw.z, sw.w), w2, hi);
+  lo = ffma2(make_float2(se.x, se.y), w3, lo); hi = ffma2(make_float2(se.z, se.w), w3, hi);
+  const float4 o = make_float4(lo.x, lo.y, hi.x, hi.y);
   return o;
 }
 
@@ -509,28 +511,33 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // ------------------------------------------------------------ rgb_fc.0, overlapped with view pooling #2
     umma::fence_smem_to_async(); umma::fence_before_sync(); wg_sync(wg);
     if (m == 0) { umma::fence_after_sync(); umma::gemm_issue(tb + 0, E + E_RG, ROWS, Wb + W16(M_RGB0), 16, 16, 48); umma::commit(bar); }
-    if (m < T) {   // weights = vis / (sum + 1e-8), mean / var of x over views, mean of weights -> F2
-      const long long gs = (long long)tile * T + m;
-      float* f2 = a.f2 + (size_t)tile * kF2 * T + m;
+    if (vrow < V) {   // weights = vis / (sum + 1e-8), mean / var of x over views, mean of weights -> F2
+      // the V threads of sample t take every V-th PAIR of channels (packed fp32 pairs); stores stay coalesced over t
+      const long long gs = (long long)tile * T + t;
+      float* f2 = a.f2 + (size_t)tile * kF2 * T + t;
       float sum = 0.f;
 #pragma unroll
-      for (int vv = 0; vv < V; ++vv) sum += SF[SF_VIS2 * ROWS + vv * T + m];
+      for (int vv = 0; vv < V; ++vv) sum += SF[SF_VIS2 * ROWS + vv * T + t];
       float wv[V], ws = 0.f;
 #pragma unroll
-      for (int vv = 0; vv < V; ++vv) { wv[vv] = SF[SF_VIS2 * ROWS + vv * T + m] / (sum + 1e-8f); ws += wv[vv]; }
+      for (int vv = 0; vv < V; ++vv) { wv[vv] = SF[SF_VIS2 * ROWS + vv * T + t] / (sum + 1e-8f); ws += wv[vv]; }
       if (gs < p.total) {
 #pragma unroll 2
-        for (int c = 0; c < 32; ++c) {
-          float mean_c = 0.f;
+        for (int c = 2 * vrow; c < 32; c += 2 * V) {
+          float2 x[V];
 #pragma unroll
-          for (int vv = 0; vv < V; ++vv) mean_c += XF[c * ROWS + vv * T + m] * wv[vv];
-          float var_c = 0.f;
+          for (int vv = 0; vv < V; ++vv) x[vv] = make_float2(XF[c * ROWS + vv * T + t], XF[(c + 1) * ROWS + vv * T + t]);
+          float2 mean_c = fmul2(x[0], make_float2(wv[0], wv[0]));
 #pragma unroll
-          for (int vv = 0; vv < V; ++vv) { const float d = XF[c * ROWS + vv * T + m] - mean_c; var_c += wv[vv] * (d * d); }
-          f2[(size_t)c * T] = mean_c;
-          f2[(size_t)(32 + c) * T] = var_c;
+          for (int vv = 1; vv < V; ++vv) mean_c = ffma2(x[vv], make_float2(wv[vv], wv[vv]), mean_c);
+          const float2 nm = make_float2(-mean_c.x, -mean_c.y);
+          float2 var_c = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int vv = 0; vv < V; ++vv) { const float2 d = fadd2(x[vv], nm); var_c = ffma2(make_float2(wv[vv], wv[vv]), fmul2(d, d), var_c); }
+          f2[(size_t)c * T] = mean_c.x; f2[(size_t)(c + 1) * T] = mean_c.y;
+          f2[(size_t)(32 + c) * T] = var_c.x; f2[(size_t)(33 + c) * T] = var_c.y;
         }
-        f2[(size_t)64 * T] = ws / (float)V;
+        if (vrow == 0) f2[(size_t)64 * T] = ws / (float)V;
       }
     }
     mbar_wait(bar, phase); phase ^= 1; umma::fence_after_sync();
