@@ -164,18 +164,18 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
     // ---- pooled features of this sample (F2 tile [kF2][T]) -> A operand (bf16), colours -> smem
     {
       const float* f2 = a.f2 + (size_t)(g >> p.log2T) * kF2 * T + (g & (T - 1));
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        float v[8];
+      // all 68 loads of this sample are issued before the first use (HBM-streamed tile: the pass is latency bound on them)
+      float v[64];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __ldg(f2 + (size_t)(8 * c + i) * T);
-        umma::store_chunk(G + R_A, RROWS, c, m, v);
-      }
-      float tail[8] = {__ldg(f2 + (size_t)64 * T), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < 64; ++i) v[i] = __ldcs(f2 + (size_t)i * T);
+      const float wm = __ldcs(f2 + (size_t)64 * T);
+      const float c0 = __ldcs(f2 + (size_t)F2_RGB * T), c1 = __ldcs(f2 + (size_t)(F2_RGB + 1) * T), c2 = __ldcs(f2 + (size_t)(F2_RGB + 2) * T);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) umma::store_chunk(G + R_A, RROWS, c, m, v + 8 * c);
+      float tail[8] = {wm, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       umma::store_chunk(G + R_A, RROWS, 8, m, tail);
       *reinterpret_cast<uint4*>(G + R_A + ((size_t)9 * RROWS + m) * 16) = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) RGB[i * RROWS + m] = __ldg(f2 + (size_t)(F2_RGB + i) * T);
+      RGB[m] = c0; RGB[RROWS + m] = c1; RGB[2 * RROWS + m] = c2;
     }
     // ---- geometry_fc 65 -> 64 -> 16 (+ positional code)
     RSTAGE_BEGIN() umma::gemm_issue(tb, G + R_A, RROWS, Wb + W16(M_GEO0), 64, 64, 80); RSTAGE_END()
