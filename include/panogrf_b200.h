@@ -158,7 +158,21 @@ typedef struct pgrf_render_args {
   int mlp_bf16;                /* 1 = bf16 tcgen05 MLP path (rtol 1e-2), 0 = fp32 SIMT parity path (rtol 1e-4) */
   int* sched;                  /* optional device int[2]: dynamic tile counters of the bf16 kernels (zeroed by the call) */
   const void* weights16;       /* bf16 blob (pgrf_w16_blob_bytes bytes, layout from pgrf_w16_layer_info); needed when mlp_bf16 */
+  /* ---- optional per-row INPUTS replacing the fused producers (fp32 path only; for callers of the reference's module-level
+   * API: predict_proj_ray_prob renderer.py:120-136, DefaultAggregationNet.forward aggregate_net.py:41-89, network_rendering
+   * renderer.py:210-219).  Same record layouts as the *_dbg outputs above, (rfn, rn*dn, .) ---- */
+  const float* prj_in;         /* px,py,depth,dir[3]: skips ray construction + projection; needs que_dir_in and interval_in;
+                                  coords / que_c2w / ref_w2c may then be NULL */
+  const float* feat_in;        /* ray_feats[32] rgb[3] img_feats[32]: skips the three gathers; the maps may then be NULL */
+  const float* prob_in;        /* alpha, vis, hit_prob: skips the dist decoder + compute_prob */
+  const float* que_dir_in;     /* (rn*dn,3) unit query ray directions */
+  const float* interval_in;    /* (rn*dn) que_dists of depth2inv_dists (render_ops.py:110-122); `depth` may then be NULL
+                                  (no render_depth / fine sampling) */
+  float* dec_dbg;              /* optional OUTPUT (rfn, rn*dn, 6): mean[2], var[2], vis, aw of the dist decoder */
 } pgrf_render_args;
+/* Module-level entry ("agg_mlp_fwd"): the aggregation network + ray transformer + compositing on
+ * caller-provided per-row inputs (prj_in, feat_in, prob_in, que_dir_in required).  fp32. */
+PGRF_API int pgrf_agg_mlp_fwd(const pgrf_render_args* args, void* stream);
 
 PGRF_API int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream);
 /* workspace sizes (floats) for `n_samples` = rn*dn samples and rfn views */
@@ -266,6 +280,21 @@ PGRF_API int pgrf_project_gather_diner_fwd(const float* pts, long long pn, const
                                            const float* mvs_depth, const float* mvs_uncert, const float* mvs_normal, int map_h,
                                            int map_w, int img_h, int img_w, float* out_pix, float* out_depth, float* out_mu,
                                            float* out_uncert, float* out_normal, void* stream);
+
+/* MixtureLogisticsDistDecoder.compute_prob (dist_decoder.py:113-140) with get_near_far_points(is_ref=True) (:6-51):
+ * depth (rfn,n), interval (n) shared by all views or (rfn,n) when interval_per_view, mean/var (rfn,n,2), vis (rfn,n) or NULL
+ * (use_vis=False), aw (rfn,n), depth_range (rfn,2); n = rays*dn -> alpha, visibility, hit_prob (rfn,n) */
+PGRF_API int pgrf_compute_prob_fwd(const float* depth, const float* interval, int interval_per_view, const float* mean,
+                                   const float* var, const float* vis, const float* aw, const float* depth_range, int rfn,
+                                   long long n, int dn, float* alpha, float* visibility, float* hit_prob, void* stream);
+/* interpolate_feature_map (render_ops.py:126-143 -> ops.py:32-52): feats (rfn,C,fh,fw) NCHW, pix (rfn,pn,2) in full-res
+ * (h,w) pixel units -> out (rfn,pn,C); bilinear, padding 'border', align_corners = (fh==h && fw==w) */
+PGRF_API int pgrf_interpolate_feature_map_fwd(const float* feats, int rfn, int C, int fh, int fw, const float* pix, long long pn,
+                                              int h, int w, float* out, void* stream);
+/* depth2points_spherical (render_ops.py:76-106): coords (rn,2), depth (rn,dn) or (dn) shared (stride 0), c2w (3,4) ->
+ * pts (rn,dn,3) world points, dir (rn,dn,3) = -ray/|ray| */
+PGRF_API int pgrf_depth2points_fwd(const float* coords, const float* depth, int depth_ray_stride, const float* c2w, int dataset,
+                                   int H, int W, long long rn, int dn, float* pts, float* dir, void* stream);
 
 /* Weight blob layout: one entry per (slice of a) Linear layer of [fine_]dist_decoder / [fine_]agg_net.
  * name uses "{dd}" / "{agg}" placeholders; the weight slice [N, k_begin:k_begin+K] is stored

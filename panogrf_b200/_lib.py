@@ -109,6 +109,7 @@ class RenderArgs(ctypes.Structure):
         ("fine_depth", _P), ("fine_dn", _I), ("fine_u", _P), ("fine_use_all", _I), ("use_disp", _I),
         ("fine_inds", _P), ("prob_dbg", _P), ("prj_dbg", _P), ("feat_dbg", _P),
         ("stage_mask", _I), ("mlp_bf16", _I), ("sched", _P), ("weights16", _P),
+        ("prj_in", _P), ("feat_in", _P), ("prob_in", _P), ("que_dir_in", _P), ("interval_in", _P), ("dec_dbg", _P),
     ]
 
 
@@ -144,6 +145,10 @@ SIGNATURES.update({
     "pgrf_project_gather_diner_fwd": (_I, [_P, ctypes.c_longlong, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I,
                                            _P, _P, _P, _P, _P, _P]),
     "pgrf_render_pass_fwd": (_I, [ctypes.POINTER(RenderArgs), _P]),
+    "pgrf_agg_mlp_fwd": (_I, [ctypes.POINTER(RenderArgs), _P]),
+    "pgrf_compute_prob_fwd": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, ctypes.c_longlong, _I, _P, _P, _P, _P]),
+    "pgrf_interpolate_feature_map_fwd": (_I, [_P, _I, _I, _I, _I, _P, ctypes.c_longlong, _I, _I, _P, _P]),
+    "pgrf_depth2points_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, ctypes.c_longlong, _I, _P, _P, _P]),
     "pgrf_render_workspace": (_I, [_I, ctypes.c_longlong, _PLL, _PLL]),
     "pgrf_render_view_fwd": (_I, [ctypes.POINTER(RenderViewArgs), _P]),
     "pgrf_render_view_host": (_I, [ctypes.POINTER(RenderViewArgs)]),

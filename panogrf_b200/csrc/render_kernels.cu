@@ -103,7 +103,18 @@ __global__ void __launch_bounds__(kThreads, 1) render_rows_kernel(const RenderPa
         const int v = m / T, t = m % T;
         long long g = (long long)tile * T + t;
         if (g >= p.total) g = p.total - 1;   // padded rows replicate the last sample (never read back)
-        const RowGeom r = row_geometry(a, v, g);
+        RowGeom r;
+        if (a.prj_in) {   // the reference's prj_dict rows: pixel, depth and direction are given
+          const float* d = a.prj_in + ((size_t)v * p.total + g) * 6;
+          const float* q = a.que_dir_in + (size_t)g * 3;
+          r.px = __ldg(d); r.py = __ldg(d + 1); r.pdepth = __ldg(d + 2);
+          r.dir[0] = __ldg(d + 3); r.dir[1] = __ldg(d + 4); r.dir[2] = __ldg(d + 5);
+          const float q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+          r.dirdiff[0] = r.dir[0] - q0; r.dirdiff[1] = r.dir[1] - q1; r.dirdiff[2] = r.dir[2] - q2;
+          r.dirdiff[3] = r.dir[0] * q0 + r.dir[1] * q1 + r.dir[2] * q2;
+        } else {
+          r = row_geometry(a, v, g);
+        }
         SC[SC_PX * LD + m] = r.px; SC[SC_PY * LD + m] = r.py; SC[SC_PDEPTH * LD + m] = r.pdepth;
 #pragma unroll
         for (int i = 0; i < 4; ++i) OUT[(F1_DIRDIFF + i) * LD + m] = r.dirdiff[i];
@@ -123,6 +134,22 @@ __global__ void __launch_bounds__(kThreads, 1) render_rows_kernel(const RenderPa
     __syncthreads();
 
     // ---------------- gathers: lane <-> (row, float4 channel group) ----------------
+    if (a.feat_in) {   // gathered features are given (prj_dict['ray_feats'], ['rgb'], ['img_feats'])
+      for (int it = tid; it < LD * 67; it += kThreads) {
+        const int m = it / 67, c = it % 67;
+        float val = 0.f;
+        if (m < M) {
+          const int v = m / T, t = m % T;
+          long long g = (long long)tile * T + t;
+          if (g >= p.total) g = p.total - 1;
+          val = __ldg(a.feat_in + ((size_t)v * p.total + g) * 67 + c);
+        }
+        if (c < 32) IN[c * LD + m] = val;
+        else if (c < 35) { OUT[(c - 32) * LD + m] = val; OUT[(F1_RGBRAW + c - 32) * LD + m] = val; }
+        else OUT[(3 + c - 35) * LD + m] = val;
+      }
+      if (tid < LD) OUT[(F1_RGBRAW + 3) * LD + tid] = 0.f;
+    } else {
     for (int it = tid; it < LD * 8; it += kThreads) {
       const int m = it >> 3, cg = it & 7;
       float4 rf = make_float4(0.f, 0.f, 0.f, 0.f), imf = rf;
@@ -153,6 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rows_kernel(const RenderPa
       OUT[(F1_RGBRAW + 0) * LD + m] = c.x; OUT[(F1_RGBRAW + 1) * LD + m] = c.y; OUT[(F1_RGBRAW + 2) * LD + m] = c.z;
       OUT[(F1_RGBRAW + 3) * LD + m] = 0.f;
     }
+    }
     __syncthreads();
     if (a.feat_dbg) {  // optional prj_dict dump of the gathered features: ray_feats(32) rgb(3) img_feats(32)
       for (int it = tid; it < M * 67; it += kThreads) {
@@ -167,10 +195,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_rows_kernel(const RenderPa
     }
 
     // ---------------- dist decoder: 3 (4) MLPs 32 -> 32 -> 32 -> {2,2,1,1} ----------------
-    decoder_stage<0>(W, IN, H1, H2, SC, Mp, a.bias_val, tid, warp, lane);
-    decoder_stage<1>(W, IN, H1, H2, SC, Mp, a.bias_val, tid, warp, lane);
-    decoder_stage<2>(W, IN, H1, H2, SC, Mp, a.bias_val, tid, warp, lane);
-    if (a.use_vis) decoder_stage<3>(W, IN, H1, H2, SC, Mp, a.bias_val, tid, warp, lane);
+    if (!a.prob_in) {
+      decoder_stage<0>(W, IN, H1, H2, SC, Mp, a.bias_val, tid, warp, lane);
+      decoder_stage<1>(W, IN, H1, H2, SC, Mp, a.bias_val, tid, warp, lane);
+      decoder_stage<2>(W, IN, H1, H2, SC, Mp, a.bias_val, tid, warp, lane);
+      if (a.use_vis) decoder_stage<3>(W, IN, H1, H2, SC, Mp, a.bias_val, tid, warp, lane);
+    }
     __syncthreads();
 
     // ---------------- logistic-mixture probabilities (dist_decoder.compute_prob, is_ref=True) ----------------
@@ -182,30 +212,49 @@ __global__ void __launch_bounds__(kThreads, 1) render_rows_kernel(const RenderPa
         long long g = (long long)tile * T + t;
         if (g >= p.total) g = p.total - 1;
         const int ray = (int)(g / a.dn), s = (int)(g % a.dn);
-        const float* dp = a.depth + (size_t)ray * a.depth_ray_stride;
-        // que_dists = depth2inv_dists(que_depth, que depth_range): interval s = inv[s+1]-inv[s], last 1e6
-        const float i_s = inv_norm(__ldg(dp + s), a.que_near, a.que_far);
-        const float d_s = (s + 1 < a.dn) ? inv_norm(__ldg(dp + s + 1), a.que_near, a.que_far) - i_s : 1e6f;
-        float d_prev = d_s;  // interval_ext[0] = interval_half[0]
-        if (s > 0) d_prev = i_s - inv_norm(__ldg(dp + s - 1), a.que_near, a.que_far);
-        const float rnear = __ldg(a.ref_depth_range + 2 * v), rfar = __ldg(a.ref_depth_range + 2 * v + 1);
-        const float dv = inv_norm(fmaxf(SC[SC_PDEPTH * LD + m], 1e-5f), rnear, rfar);
-        const float nearp = dv - d_prev / 2.f, farp = dv + d_s / 2.f;
-        const float aw = SC[SC_AW * LD + m];
-        const float mix[2] = {aw, 1.f - aw};
-        const float mean[2] = {SC[SC_MEAN0 * LD + m], SC[SC_MEAN1 * LD + m]};
-        const float var[2] = {SC[SC_VAR0 * LD + m], SC[SC_VAR1 * LD + m]};
-        float visibility = 0.f, hp = 0.f;
+        if (a.prob_in) {   // prj_dict['alpha' | 'vis' | 'hit_prob'] are given: the dist decoder did not run
+          const float* d = a.prob_in + ((size_t)v * p.total + g) * 3;
+          alpha = __ldg(d); vis = __ldg(d + 1); hit = __ldg(d + 2);
+        } else {
+          float d_s, d_prev;
+          if (a.interval_in) {   // que_dists given (get_near_far_points, dist_decoder.py:6-51, is_ref=True)
+            d_s = __ldg(a.interval_in + g);
+            d_prev = s > 0 ? __ldg(a.interval_in + g - 1) : d_s;
+          } else {
+            const float* dp = a.depth + (size_t)ray * a.depth_ray_stride;
+            // que_dists = depth2inv_dists(que_depth, que depth_range): interval s = inv[s+1]-inv[s], last 1e6
+            const float i_s = inv_norm(__ldg(dp + s), a.que_near, a.que_far);
+            d_s = (s + 1 < a.dn) ? inv_norm(__ldg(dp + s + 1), a.que_near, a.que_far) - i_s : 1e6f;
+            d_prev = d_s;  // interval_ext[0] = interval_half[0]
+            if (s > 0) d_prev = i_s - inv_norm(__ldg(dp + s - 1), a.que_near, a.que_far);
+          }
+          const float rnear = __ldg(a.ref_depth_range + 2 * v), rfar = __ldg(a.ref_depth_range + 2 * v + 1);
+          const float dv = inv_norm(fmaxf(SC[SC_PDEPTH * LD + m], 1e-5f), rnear, rfar);
+          const float nearp = dv - d_prev / 2.f, farp = dv + d_s / 2.f;
+          const float aw = SC[SC_AW * LD + m];
+          const float mix[2] = {aw, 1.f - aw};
+          const float mean[2] = {SC[SC_MEAN0 * LD + m], SC[SC_MEAN1 * LD + m]};
+          const float var[2] = {SC[SC_VAR0 * LD + m], SC[SC_VAR1 * LD + m]};
+          float visibility = 0.f, hp = 0.f;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float cdf0 = 0.5f + 0.5f * tanhf((nearp - mean[j]) * var[j]);
-          float cdf1 = 0.5f + 0.5f * tanhf((farp - mean[j]) * var[j]);
-          if (a.use_vis) { cdf0 *= SC[SC_VIS * LD + m]; cdf1 *= SC[SC_VIS * LD + m]; }
-          visibility += (1.f - cdf0) * mix[j];
-          hp += (cdf1 - cdf0) * mix[j];
+          for (int j = 0; j < 2; ++j) {
+            float cdf0 = 0.5f + 0.5f * tanhf((nearp - mean[j]) * var[j]);
+            float cdf1 = 0.5f + 0.5f * tanhf((farp - mean[j]) * var[j]);
+            if (a.use_vis) { cdf0 *= SC[SC_VIS * LD + m]; cdf1 *= SC[SC_VIS * LD + m]; }
+            visibility += (1.f - cdf0) * mix[j];
+            hp += (cdf1 - cdf0) * mix[j];
+          }
+          hit = hp; vis = visibility;
+          alpha = logf(hp / (visibility - hp + 1e-5f) + 1e-5f);
+          if (a.dec_dbg) {
+            const long long gg = (long long)tile * T + t;
+            if (gg < p.total) {
+              float* d = a.dec_dbg + ((size_t)v * p.total + gg) * 6;
+              d[0] = mean[0]; d[1] = mean[1]; d[2] = var[0]; d[3] = var[1];
+              d[4] = a.use_vis ? SC[SC_VIS * LD + m] : 1.f; d[5] = aw;
+            }
+          }
         }
-        hit = hp; vis = visibility;
-        alpha = logf(hp / (visibility - hp + 1e-5f) + 1e-5f);
         if (a.prob_dbg) {
           const long long gg = (long long)tile * T + t;
           if (gg < p.total) {
@@ -557,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
       const int m0 = r * dn;
       float* alpha = RV + RV_ALPHA * 2 * LD + m0;
       float* hit = RV + RV_HIT * 2 * LD + m0;
-      const float* dp = a.depth + (size_t)ray * a.depth_ray_stride;
+      const float* dp = a.depth ? a.depth + (size_t)ray * a.depth_ray_stride : nullptr;   // NULL only in the module-level agg mode
       for (int s = lane; s < dn; s += 32) alpha[s] = 1.f - expf(-RV[RV_SIGMA * 2 * LD + m0 + s]);
       __syncwarp();
       if (lane == 0) {  // sequential fp32 cumprod, the order torch uses on the CPU (render_ops.py:150-152)
@@ -573,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         const float hs = hit[s];
         const float r_ = A[(F2_RGB + 0) * LD + m0 + s], g_ = A[(F2_RGB + 1) * LD + m0 + s], b_ = A[(F2_RGB + 2) * LD + m0 + s];
         cr = fmaf(hs, r_, cr); cg = fmaf(hs, g_, cg); cb = fmaf(hs, b_, cb);
-        cd = fmaf(hs, __ldg(dp + s), cd);
+        if (dp) cd = fmaf(hs, __ldg(dp + s), cd);
         if (a.hit_prob) a.hit_prob[(size_t)ray * dn + s] = hs;
         if (a.density) a.density[(size_t)ray * dn + s] = RV[RV_SIGMA * 2 * LD + m0 + s];
         if (a.colors) {
@@ -699,9 +748,16 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
   PGRF_REQUIRE(a.rn >= 1, "render: rn=%d", a.rn);
   PGRF_REQUIRE(a.H > 1 && a.W > 1 && a.img_h > 1 && a.img_w > 1 && a.if_h > 0 && a.if_w > 0 && a.rf_h > 0 && a.rf_w > 0,
                "render: bad map sizes");
-  PGRF_REQUIRE(a.coords && a.depth && a.que_c2w && a.ref_w2c && a.ref_depth_range && a.imgs_cl && a.img_feats_cl &&
-                   a.ray_feats_cl && a.weights && (a.f1 || a.mlp_bf16) && a.f2 && a.pixel_colors,
-               "render: null pointer argument");
+  const bool dict_in = a.prj_in || a.feat_in || a.prob_in;
+  PGRF_REQUIRE(!(dict_in || a.dec_dbg) || !a.mlp_bf16, "render: prj_in / feat_in / prob_in / dec_dbg exist on the fp32 path only");
+  PGRF_REQUIRE(!a.prj_in || (a.que_dir_in && (a.interval_in || a.prob_in || a.depth)),
+               "render: prj_in needs que_dir_in and interval_in (or depth, or prob_in)");
+  PGRF_REQUIRE(a.prj_in || (a.coords && a.que_c2w && a.ref_w2c), "render: null pointer argument (coords / que_c2w / ref_w2c)");
+  PGRF_REQUIRE(a.feat_in || (a.imgs_cl && a.img_feats_cl && a.ray_feats_cl), "render: null pointer argument (source maps)");
+  PGRF_REQUIRE(a.depth || (a.prj_in && (a.interval_in || a.prob_in) && !a.render_depth && !a.fine_depth),
+               "render: depth may only be omitted with prj_in + interval_in/prob_in and without render_depth / fine sampling");
+  PGRF_REQUIRE(a.prob_in || a.ref_depth_range, "render: null pointer argument (ref_depth_range)");
+  PGRF_REQUIRE(a.weights && (a.f1 || a.mlp_bf16) && a.f2 && a.pixel_colors, "render: null pointer argument");
   PGRF_REQUIRE(a.depth_ray_stride == 0 || a.depth_ray_stride == a.dn, "render: depth_ray_stride must be 0 or dn");
   PGRF_REQUIRE(!a.fine_depth || (a.fine_u && a.fine_dn >= 1 && a.fine_dn + (a.fine_use_all ? a.dn : 0) <= 2 * kMaxSamplesPerRay - 2),
                "render: bad fine sampling arguments");
@@ -745,4 +801,11 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
   if (mask & 4) { render_rays_kernel<<<min(p.n_tiles3, sms), kThreads, s3, st>>>(p); count_launch(); }
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
+}
+
+extern "C" int pgrf_agg_mlp_fwd(const pgrf_render_args* args, void* stream) {
+  PGRF_REQUIRE(args != nullptr, "agg_mlp: null args");
+  PGRF_REQUIRE(args->prj_in && args->feat_in && args->prob_in && args->que_dir_in,
+               "agg_mlp: prj_in, feat_in, prob_in and que_dir_in are required");
+  return pgrf_render_pass_fwd(args, stream);
 }

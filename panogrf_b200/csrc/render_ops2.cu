@@ -1,0 +1,129 @@
+// More stand-alone operators of the reference's functional / module API (not used by the fused renderer):
+//   compute_prob            — MixtureLogisticsDistDecoder.compute_prob (dist_decoder.py:113-140) with
+//                             get_near_far_points(is_ref=True) (:6-51)
+//   interpolate_feature_map — render_ops.py:126-143 -> ops.py:32-52: bilinear, border padding, any channel count, NCHW maps
+//   depth2points_spherical  — render_ops.py:76-106 (+ ray_utils.py:4-16): pixel -> unit ray -> world points and directions
+#include "render_device.cuh"
+
+namespace pgrf {
+
+__global__ void __launch_bounds__(256) compute_prob_kernel(const float* __restrict__ depth, const float* __restrict__ interval,
+                                                           long long interval_view_stride, const float* __restrict__ mean,
+                                                           const float* __restrict__ var, const float* __restrict__ vis,
+                                                           const float* __restrict__ aw, const float* __restrict__ depth_range,
+                                                           int rfn, long long n, int dn, float* __restrict__ alpha,
+                                                           float* __restrict__ visibility, float* __restrict__ hit_prob) {
+  const long long total = (long long)rfn * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i / n);
+    const long long g = i % n;
+    const int s = (int)(g % dn);
+    const float* iv = interval + (size_t)v * interval_view_stride;
+    const float d_s = __ldg(iv + g);
+    const float d_prev = s > 0 ? __ldg(iv + g - 1) : d_s;
+    const float rnear = __ldg(depth_range + 2 * v), rfar = __ldg(depth_range + 2 * v + 1);
+    const float dv = inv_norm(fmaxf(__ldg(depth + i), 1e-5f), rnear, rfar);
+    const float nearp = dv - d_prev / 2.f, farp = dv + d_s / 2.f;
+    const float a = __ldg(aw + i);
+    const float mix[2] = {a, 1.f - a};
+    float vsum = 0.f, hp = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float mu = __ldg(mean + 2 * i + j), va = __ldg(var + 2 * i + j);
+      float cdf0 = 0.5f + 0.5f * tanhf((nearp - mu) * va);
+      float cdf1 = 0.5f + 0.5f * tanhf((farp - mu) * va);
+      if (vis) { const float vv = __ldg(vis + i); cdf0 *= vv; cdf1 *= vv; }
+      vsum += (1.f - cdf0) * mix[j];
+      hp += (cdf1 - cdf0) * mix[j];
+    }
+    alpha[i] = logf(hp / (vsum - hp + 1e-5f) + 1e-5f);
+    visibility[i] = vsum;
+    hit_prob[i] = hp;
+  }
+}
+
+// thread = (view, point); channels looped (planar NCHW taps: 4 scalar loads per channel, L1/L2 resident maps)
+__global__ void __launch_bounds__(256) interpolate_kernel(const float* __restrict__ feats, int rfn, int C, int fh, int fw,
+                                                          const float* __restrict__ pix, long long pn, int h, int w,
+                                                          float* __restrict__ out) {
+  const size_t plane = (size_t)fh * fw;
+  const long long total = (long long)rfn * pn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i / pn);
+    const Footprint f = border_footprint(__ldg(pix + 2 * i), __ldg(pix + 2 * i + 1), h, w, fh, fw);
+    const float tx1 = 1.f - f.tx, ty1 = 1.f - f.ty;
+    const float wnw = tx1 * ty1, wne = f.tx * ty1, wsw = tx1 * f.ty, wse = f.tx * f.ty;
+    const float* base = feats + (size_t)v * C * plane + f.off;
+    for (int c = 0; c < C; ++c) {
+      const float* m = base + c * plane;
+      float o = __ldg(m) * wnw;
+      o = fmaf(__ldg(m + f.dx), wne, o);
+      o = fmaf(__ldg(m + f.dy * fw), wsw, o);
+      o = fmaf(__ldg(m + f.dy * fw + f.dx), wse, o);
+      out[(size_t)i * C + c] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) depth2points_kernel(const float* __restrict__ coords, const float* __restrict__ depth,
+                                                           long long depth_ray_stride, const float* __restrict__ c2w, int dataset,
+                                                           int H, int W, long long rn, int dn, float* __restrict__ pts,
+                                                           float* __restrict__ dir) {
+  const long long total = rn * dn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long ray = i / dn;
+    const int s = (int)(i % dn);
+    const float cx = __ldg(coords + 2 * ray), cy = __ldg(coords + 2 * ray + 1);
+    float dx, dy, dz;
+    equi_unit_dir(dataset, (float)(long long)cx, (float)(long long)cy, H, W, dx, dy, dz);
+    const float r0 = c2w[0] * dx + c2w[1] * dy + c2w[2] * dz;
+    const float r1 = c2w[4] * dx + c2w[5] * dy + c2w[6] * dz;
+    const float r2 = c2w[8] * dx + c2w[9] * dy + c2w[10] * dz;
+    const float t = __ldg(depth + ray * depth_ray_stride + s);
+    pts[3 * i] = c2w[3] + r0 * t; pts[3 * i + 1] = c2w[7] + r1 * t; pts[3 * i + 2] = c2w[11] + r2 * t;
+    const float nrm = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+    dir[3 * i] = -r0 / nrm; dir[3 * i + 1] = -r1 / nrm; dir[3 * i + 2] = -r2 / nrm;
+  }
+}
+
+static int grid_for(long long total) {
+  const long long b = (total + 255) / 256;
+  return (int)(b < 148LL * 16 ? b : 148LL * 16);
+}
+
+}  // namespace pgrf
+
+using namespace pgrf;
+
+extern "C" int pgrf_compute_prob_fwd(const float* depth, const float* interval, int interval_per_view, const float* mean,
+                                     const float* var, const float* vis, const float* aw, const float* depth_range, int rfn,
+                                     long long n, int dn, float* alpha, float* visibility, float* hit_prob, void* stream) {
+  PGRF_REQUIRE(depth && interval && mean && var && aw && depth_range && alpha && visibility && hit_prob, "compute_prob: null pointer argument");
+  PGRF_REQUIRE(rfn >= 1 && n >= 1 && dn >= 1 && n % dn == 0, "compute_prob: rfn=%d n=%lld dn=%d (n must be a multiple of dn)", rfn, n, dn);
+  compute_prob_kernel<<<grid_for((long long)rfn * n), 256, 0, (cudaStream_t)stream>>>(depth, interval, interval_per_view ? n : 0, mean, var, vis,
+                                                                                    aw, depth_range, rfn, n, dn, alpha, visibility, hit_prob);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_interpolate_feature_map_fwd(const float* feats, int rfn, int C, int fh, int fw, const float* pix, long long pn, int h,
+                                                int w, float* out, void* stream) {
+  PGRF_REQUIRE(feats && pix && out, "interpolate_feature_map: null pointer argument");
+  PGRF_REQUIRE(rfn >= 1 && C >= 1 && fh >= 1 && fw >= 1 && pn >= 1 && h >= 2 && w >= 2, "interpolate_feature_map: bad sizes");
+  interpolate_kernel<<<grid_for((long long)rfn * pn), 256, 0, (cudaStream_t)stream>>>(feats, rfn, C, fh, fw, pix, pn, h, w, out);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_depth2points_fwd(const float* coords, const float* depth, int depth_ray_stride, const float* c2w, int dataset, int H,
+                                     int W, long long rn, int dn, float* pts, float* dir, void* stream) {
+  PGRF_REQUIRE(coords && depth && c2w && pts && dir, "depth2points: null pointer argument");
+  PGRF_REQUIRE(dataset >= 0 && dataset <= 3, "depth2points: unknown dataset id %d", dataset);
+  PGRF_REQUIRE(rn >= 1 && dn >= 1 && H >= 2 && W >= 2 && (depth_ray_stride == 0 || depth_ray_stride == dn), "depth2points: bad sizes");
+  depth2points_kernel<<<grid_for(rn * dn), 256, 0, (cudaStream_t)stream>>>(coords, depth, depth_ray_stride, c2w, dataset, H, W, rn, dn, pts, dir);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}

@@ -134,6 +134,48 @@ def project_points_dict(ref_imgs_info, que_pts, spt_utils, with_img_feats=True):
     return {k: v.reshape(rfn, qn, rn, dn, -1) for k, v in out.items()}
 
 
+def interpolate_feature_map(ray_feats, coords, h, w, border_type="border"):
+    """render_ops.py:126-143: ray_feats (rfn,f,fh,fw), coords (rfn,pn,2) in (h,w) pixel units -> (rfn,pn,f); bilinear,
+    border padding, align_corners only when the map is at full resolution."""
+    if border_type != "border":
+        raise NotImplementedError("only border padding is used on the render path")
+    _lib.require_cuda(ray_feats, coords)
+    lib = _lib.load()
+    rfn, f, fh, fw = ray_feats.shape
+    pn = coords.shape[1]
+    feats, pix = _f32(ray_feats), _f32(coords).reshape(rfn, pn, 2)
+    out = torch.empty(rfn, pn, f, device=feats.device, dtype=torch.float32)
+    with torch.cuda.device(feats.device):
+        rc = lib.pgrf_interpolate_feature_map_fwd(_lib.ptr(feats), rfn, f, fh, fw, _lib.ptr(pix), pn, int(h), int(w), _lib.ptr(out),
+                                                  _lib.stream_ptr())
+    _lib.check(rc, "pgrf_interpolate_feature_map_fwd")
+    return out
+
+
+def depth2points_spherical(que_imgs_info, que_depth, spt_utils):
+    """render_ops.py:76-106: que_depth (qn=1,rn,dn) -> que_pts (1,rn,dn,3), que_dir (1,rn,dn,3)."""
+    c2w = que_imgs_info["c2w"]
+    assert c2w.shape[0] == 1, "que_imgs_info c2w.shape[0]=1"
+    _lib.require_cuda(que_depth, que_imgs_info["coords"])
+    lib = _lib.load()
+    qn, rn, dn = que_depth.shape
+    assert qn == 1
+    dev = que_depth.device
+    name = spt_utils.dataset
+    if name not in _lib.DATASET_IDS:
+        raise Exception(f"unknown dataset {name!r}")
+    depth = _f32(que_depth).reshape(rn, dn)
+    coords = _f32(que_imgs_info["coords"]).reshape(rn, 2)
+    c = _f32(c2w).reshape(3, 4).to(dev)
+    pts, dirs = torch.empty(1, rn, dn, 3, device=dev), torch.empty(1, rn, dn, 3, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pgrf_depth2points_fwd(_lib.ptr(coords), _lib.ptr(depth), dn, _lib.ptr(c), _lib.DATASET_IDS[name],
+                                       int(spt_utils.height), int(spt_utils.width), rn, dn, _lib.ptr(pts), _lib.ptr(dirs),
+                                       _lib.stream_ptr())
+    _lib.check(rc, "pgrf_depth2points_fwd")
+    return pts, dirs
+
+
 def mono_guided_hypotheses(ref_mu, k_list, fixed_sigma, min_depth, max_depth, n_linear):
     """Depth hypotheses of the MVS net (pipeline3_model.py:723-733, 774-815): clamp(ref_mu + k*sigma) for k in k_list,
     concatenated with linspace(min,max,n_linear) and sorted per pixel.  ref_mu (B,1,h,w) -> (B,len(k_list)+n_linear,h,w)."""

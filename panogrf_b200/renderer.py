@@ -58,6 +58,47 @@ class MixtureLogisticsDistDecoder(nn.Module):
         if self.cfg["use_vis"]:
             self.vis_decoder = _seq([d, d, d, 1])
 
+    def forward(self, feats):
+        """dist_decoder.py:99-107: feats (...,32) -> prj_mean (...,2), prj_var (...,2), prj_vis (...,1) | None, prj_aw (...,1)."""
+        lead = feats.shape[:-1]
+        x = feats.detach().float().reshape(-1, 32)
+        n0 = x.shape[0]
+        n = (n0 + 3) // 4 * 4                                     # rows are independent here: any (rn, dn=4) factorisation
+        feat = torch.zeros(1, n, 67, device=x.device)
+        feat[0, :n0, :32] = x
+        prj = torch.zeros(1, n, 6, device=x.device)
+        prj[..., 2] = 1.0
+        out = _module_pass(_module_blob(self, "dist_decoder.", self), 1, n // 4, 4, self.cfg["use_vis"], self.cfg["bias_val"],
+                           prj=prj, feat=feat, stage_mask=1, want_dec=True)["dec"][0, :n0]
+        mean, var = out[:, 0:2].reshape(*lead, 2), out[:, 2:4].reshape(*lead, 2)
+        vis = out[:, 4:5].reshape(*lead, 1) if self.cfg["use_vis"] else None
+        return mean, var, vis, out[:, 5:6].reshape(*lead, 1)
+
+    def compute_prob(self, depth, interval, mean, var, vis, aw, is_ref, depth_range):
+        """dist_decoder.py:109-140 (is_ref=True, the render path): depth (rfn,qn,rn,dn), interval (1|rfn,qn,rn,dn),
+        mean/var (rfn,qn,rn,dn,2), vis/aw (rfn,qn,rn,dn,1), depth_range (rfn,2) -> alpha, visibility, hit_prob (rfn,qn,rn,dn)."""
+        if not is_ref:
+            raise NotImplementedError("compute_prob(is_ref=False) belongs to the training-only self hit probability")
+        _lib.require_cuda(depth, interval, mean, var, aw)
+        lib = _lib.load()
+        shape = depth.shape
+        rfn, dn = shape[0], shape[-1]
+        n = depth[0].numel()
+        f = lambda t, c: t.detach().float().expand(*shape, c).reshape(rfn, n, c).contiguous()
+        d = depth.detach().float().reshape(rfn, n).contiguous()
+        per_view = interval.shape[0] == rfn and rfn > 1
+        iv = interval.detach().float().expand(rfn if per_view else 1, *shape[1:]).reshape(-1).contiguous()
+        m2, v2, a1 = f(mean, 2), f(var, 2), f(aw, 1)
+        vs = f(vis, 1) if (self.cfg["use_vis"] and vis is not None) else None
+        rng = depth_range.detach().float().contiguous().to(d.device)
+        outs = [torch.empty(rfn, n, device=d.device) for _ in range(3)]
+        with torch.cuda.device(d.device):
+            rc = lib.pgrf_compute_prob_fwd(_lib.ptr(d), _lib.ptr(iv), int(per_view), _lib.ptr(m2), _lib.ptr(v2), _lib.ptr(vs),
+                                           _lib.ptr(a1), _lib.ptr(rng), rfn, n, dn, *[_lib.ptr(o) for o in outs],
+                                           _lib.stream_ptr())
+        _lib.check(rc, "pgrf_compute_prob_fwd")
+        return tuple(o.reshape(shape) for o in outs)
+
 
 class _RayAttention(nn.Module):
     def __init__(self):
@@ -105,6 +146,103 @@ class DefaultAggregationNet(nn.Module):
         dim = self.cfg["neuray_dim"]
         self.agg_impl = IBRNetWithNeuRay(dim, in_feat_ch=32, n_samples=self.cfg["sample_num"])
         self.prob_embed = nn.Sequential(nn.Linear(2 + 32, dim), nn.Identity(), nn.Linear(dim, dim))
+
+    def _run(self, prj_dict, que_dir):
+        rfn, qn, rn, dn, _ = prj_dict["hit_prob"].shape
+        if dn != self.cfg["sample_num"]:
+            raise RuntimeError(f"The size of tensor a ({dn}) must match the size of tensor b "
+                               f"({self.cfg['sample_num']}) at non-singleton dimension 1")   # ibrnet.py:358
+        n = qn * rn * dn
+        dev = prj_dict["hit_prob"].device
+        prj = torch.zeros(rfn, n, 6, device=dev)
+        prj[..., 2] = 1.0
+        prj[..., 3:6] = _rows(prj_dict["dir"], rfn, n, 3)
+        feat = torch.cat([_rows(prj_dict["ray_feats"], rfn, n, 32), _rows(prj_dict["rgb"], rfn, n, 3),
+                          _rows(prj_dict["img_feats"], rfn, n, 32)], -1).contiguous()
+        alpha = prj_dict["alpha"] if "alpha" in prj_dict else torch.zeros_like(prj_dict["vis"])
+        prob = torch.cat([_rows(alpha, rfn, n, 1), _rows(prj_dict["vis"], rfn, n, 1), _rows(prj_dict["hit_prob"], rfn, n, 1)],
+                         -1).contiguous()
+        qd = que_dir.detach().float().reshape(n, 3).contiguous()
+        blob = _module_blob(self, "agg_net.", self, self.cfg["sample_num"])
+        out = _module_pass(blob, rfn, qn * rn, dn, False, 0.05, prj=prj, feat=feat, prob=prob, que_dir=qd)
+        return out, (qn, rn, dn)
+
+    def forward(self, prj_dict, que_dir):
+        """aggregate_net.py:41-89: prj_dict of (rfn,qn,rn,dn,*) tensors (ray_feats, hit_prob, vis, rgb, dir, img_feats),
+        que_dir (qn,rn,dn,3) -> density (qn,rn,dn), colors (qn,rn,dn,3)."""
+        out, (qn, rn, dn) = self._run(prj_dict, que_dir)
+        return out["density"].reshape(qn, rn, dn), out["colors"].reshape(qn, rn, dn, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# module-level API of the reference (dist decoder / aggregation net evaluated on a caller-provided prj_dict):
+# the fp32 kernels of the fused path with their producers switched off (pgrf_render_args.prj_in / feat_in / prob_in)
+# ------------------------------------------------------------------------------------------------
+
+def _module_blob(module, prefix, cache_owner, n_samples=64):
+    """fp32 blob holding only `module`'s parameters under the reference prefix (`dist_decoder.` / `agg_net.`)."""
+    params = list(module.parameters())
+    dev = params[0].device
+    key = (str(dev), tuple((p.data_ptr(), p._version) for p in params))
+    hit = getattr(cache_owner, "_mod_blob", None)
+    if hit is None or hit[0] != key:
+        state = {prefix + k: v for k, v in module.state_dict().items()}
+        cache_owner._mod_blob = (key, pack_blob(state, False, n_samples, dev, allow_missing=True))
+    return cache_owner._mod_blob[1]
+
+
+def _rows(t, rfn, n, c):
+    return t.detach().float().reshape(rfn, n, c).contiguous()
+
+
+def _module_pass(blob, rfn, rn, dn, use_vis, bias_val, *, prj, feat, prob=None, que_dir=None, interval=None, ref_range=None,
+                 stage_mask=7, want_dec=False, want_prob=False):
+    """One pgrf_render_pass_fwd / pgrf_agg_mlp_fwd call on per-row inputs. prj (rfn,n,6), feat (rfn,n,67), prob (rfn,n,3),
+    que_dir (n,3), interval (n); n = rn*dn. Returns a dict of outputs."""
+    lib = _lib.load()
+    dev = feat.device
+    _lib.require_cuda(prj, feat, prob, que_dir, interval)
+    n = rn * dn
+    if not (1 <= rfn <= 4) or not (3 <= dn <= 128):
+        raise _lib.PanoGRFError(f"module-level kernels need 1..4 views and 3..128 samples per ray (got rfn={rfn}, dn={dn})")
+    a = _lib.RenderArgs()
+    a.dataset, a.H, a.W = 0, 2, 2
+    a.rfn, a.rn, a.dn = rfn, rn, dn
+    a.use_vis, a.bias_val = int(bool(use_vis)), float(bias_val)
+    a.img_h = a.img_w = a.if_h = a.if_w = a.rf_h = a.rf_w = 2
+    a.que_near, a.que_far = 1.0, 2.0
+    e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    if que_dir is None:
+        que_dir = torch.zeros(n, 3, device=dev)
+    if interval is None and prob is None:
+        interval = torch.zeros(n, device=dev)
+    if ref_range is None:
+        ref_range = torch.tensor([[1.0, 2.0]], device=dev).repeat(rfn, 1)
+    ref_range = ref_range.detach().float().contiguous().to(dev)
+    a.prj_in, a.feat_in, a.que_dir_in = _lib.ptr(prj), _lib.ptr(feat), _lib.ptr(que_dir)
+    a.prob_in, a.interval_in, a.ref_depth_range = _lib.ptr(prob), _lib.ptr(interval), _lib.ptr(ref_range)
+    a.weights = _lib.ptr(blob)
+    f1n, f2n = ctypes.c_longlong(), ctypes.c_longlong()
+    _lib.check(lib.pgrf_render_workspace(rfn, n, ctypes.byref(f1n), ctypes.byref(f2n)), "pgrf_render_workspace")
+    f1, f2 = e(f1n.value), e(f2n.value)
+    a.f1, a.f2 = _lib.ptr(f1), _lib.ptr(f2)
+    out = {"pixel_colors": e(rn, 3), "hit_prob": e(rn, dn), "density": e(rn, dn), "colors": e(rn, dn, 3)}
+    a.pixel_colors, a.hit_prob = _lib.ptr(out["pixel_colors"]), _lib.ptr(out["hit_prob"])
+    a.density, a.colors = _lib.ptr(out["density"]), _lib.ptr(out["colors"])
+    if want_dec:
+        out["dec"] = e(rfn, n, 6)
+        a.dec_dbg = _lib.ptr(out["dec"])
+    if want_prob:
+        out["prob"] = e(rfn, n, 3)
+        a.prob_dbg = _lib.ptr(out["prob"])
+    a.stage_mask = stage_mask
+    with torch.cuda.device(dev):
+        if stage_mask == 7 and prob is not None:
+            rc = lib.pgrf_agg_mlp_fwd(ctypes.byref(a), _lib.stream_ptr())
+        else:
+            rc = lib.pgrf_render_pass_fwd(ctypes.byref(a), _lib.stream_ptr())
+    _lib.check(rc, "pgrf_render_pass_fwd")
+    return out
 
 
 name2dist_decoder = {"mixture_logistics": MixtureLogisticsDistDecoder}
@@ -541,6 +679,44 @@ class NeuralRayBaseRenderer(nn.Module):
             rc = lib.pgrf_render_view_fwd(ctypes.byref(va), _lib.stream_ptr())
         _lib.check(rc, "pgrf_render_view_fwd")
         del keep
+
+    # ---- module-level entry points of the reference renderer ----------------------------------------
+    def predict_proj_ray_prob(self, prj_dict, ref_imgs_info, que_dists, is_fine):
+        """renderer.py:120-136: dist decoder on prj_dict['ray_feats'] + compute_prob -> prj_dict['alpha'|'vis'|'hit_prob']."""
+        rfn, qn, rn, dn, _ = prj_dict["pts"].shape
+        n = qn * rn * dn
+        dec = self.fine_dist_decoder if is_fine else self.dist_decoder
+        dev = prj_dict["ray_feats"].device
+        prj = torch.cat([_rows(prj_dict["pts"], rfn, n, 2), _rows(prj_dict["depth"], rfn, n, 1),
+                         torch.zeros(rfn, n, 3, device=dev)], -1).contiguous()
+        feat = torch.zeros(rfn, n, 67, device=dev)
+        feat[..., :32] = _rows(prj_dict["ray_feats"], rfn, n, 32)
+        interval = que_dists.detach().float().reshape(n).contiguous()
+        # the reference always evaluates self.dist_decoder.compute_prob, i.e. the COARSE cfg's use_vis (renderer.py:129)
+        out = _module_pass(_module_blob(dec, "dist_decoder.", dec), rfn, qn * rn, dn, self.dist_decoder.cfg["use_vis"],
+                           dec.cfg["bias_val"], prj=prj, feat=feat, interval=interval, ref_range=ref_imgs_info["depth_range"],
+                           stage_mask=1, want_prob=True)["prob"]
+        prj_dict["alpha"] = out[..., 0].reshape(rfn, qn, rn, dn, 1)
+        prj_dict["vis"] = out[..., 1].reshape(rfn, qn, rn, dn, 1)
+        prj_dict["hit_prob"] = out[..., 2].reshape(rfn, qn, rn, dn, 1)
+        return prj_dict
+
+    def get_img_feats(self, ref_imgs_info, prj_dict):
+        """renderer.py:180-188."""
+        from .render_ops import interpolate_feature_map
+        rfn, _, h, w = ref_imgs_info["imgs"].shape
+        rfn, qn, rn, dn, _ = prj_dict["pts"].shape
+        feats = interpolate_feature_map(ref_imgs_info["img_feats"], prj_dict["pts"].reshape(rfn, qn * rn * dn, 2), h, w)
+        prj_dict["img_feats"] = feats.reshape(rfn, qn, rn, dn, -1)
+        return prj_dict
+
+    def network_rendering(self, prj_dict, que_dir, is_fine):
+        """renderer.py:210-219: aggregation net + alpha compositing -> hit_prob (qn,rn,dn), colors (qn,rn,dn,3),
+        pixel_colors (qn,rn,3), density (qn,rn,dn)."""
+        net = self.fine_agg_net if is_fine else self.agg_net
+        out, (qn, rn, dn) = net._run(prj_dict, que_dir)
+        return (out["hit_prob"].reshape(qn, rn, dn), out["colors"].reshape(qn, rn, dn, 3),
+                out["pixel_colors"].reshape(qn, rn, 3), out["density"].reshape(qn, rn, dn))
 
     def render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, is_fine, is_perspec=False):
         """network/renderer.py:223-317 for explicit per-ray sample depths (qn=1,rn,dn)."""

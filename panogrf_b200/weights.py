@@ -20,10 +20,12 @@ def posenc_table(d_hid, n_samples):
     return torch.from_numpy(table).float()
 
 
-def pack_blob(state, fine, n_samples, device):
+def pack_blob(state, fine, n_samples, device, allow_missing=False):
     """state: mapping name -> tensor (a state_dict). Returns a (blob_floats,) fp32 tensor on `device`.
 
     `n_samples` is the length of the aggregation net's positional table (its cfg `sample_num`).
+    `allow_missing`: layers absent from `state` stay zero (a stand-alone dist decoder or aggregation net whose
+    counterpart is not evaluated: module-level API of panogrf_b200.renderer).
     """
     lib = _lib.load()
     dd = "fine_dist_decoder" if fine else "dist_decoder"
@@ -33,13 +35,17 @@ def pack_blob(state, fine, n_samples, device):
         key = name.replace("{dd}", dd).replace("{agg}", agg)
         if key.endswith("ray_attention.qkv"):
             base = key[:-len(".qkv")]
+            if allow_missing and base + ".w_qs.weight" not in state:
+                continue
             w = torch.cat([state[base + ".w_qs.weight"], state[base + ".w_ks.weight"], state[base + ".w_vs.weight"]], 0)
             b = None
         elif key.endswith("ray_attention.fc"):
+            if allow_missing and key + ".weight" not in state:
+                continue
             w, b = state[key + ".weight"], None
         else:
             if key + ".weight" not in state:
-                if ".vis_decoder." in key:           # use_vis == False: decoder absent, slots stay zero
+                if ".vis_decoder." in key or allow_missing:   # use_vis == False: decoder absent, slots stay zero
                     continue
                 raise KeyError(f"missing parameter {key}.weight")
             w = state[key + ".weight"]
@@ -54,8 +60,9 @@ def pack_blob(state, fine, n_samples, device):
             blob[b_off:b_off + N] = b.detach().float().cpu()
     ln_off, pe_off, max_samples = _lib.weight_aux_offsets()
     lnk = agg + ".agg_impl.ray_attention.layer_norm"
-    blob[ln_off:ln_off + 16] = state[lnk + ".weight"].detach().float().cpu()
-    blob[ln_off + 16:ln_off + 32] = state[lnk + ".bias"].detach().float().cpu()
+    if lnk + ".weight" in state or not allow_missing:
+        blob[ln_off:ln_off + 16] = state[lnk + ".weight"].detach().float().cpu()
+        blob[ln_off + 16:ln_off + 32] = state[lnk + ".bias"].detach().float().cpu()
     if n_samples > max_samples:
         raise _lib.PanoGRFError(f"sample_num={n_samples} exceeds the kernel limit {max_samples}")
     blob[pe_off:pe_off + n_samples * 16] = posenc_table(16, n_samples).reshape(-1)

@@ -1,0 +1,104 @@
+"""GPU: the reference's MODULE-level API (dist decoder, aggregation net, network_rendering, predict_proj_ray_prob, get_img_feats,
+interpolate_feature_map, depth2points_spherical) evaluated by the CUDA kernels on a caller-provided prj_dict, vs the oracle."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import cases  # noqa: E402
+from util import assert_close, load_golden  # noqa: E402
+from test_oracle_render import split_golden  # noqa: E402
+from test_render_gpu import build_renderer, cuda_dict  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["render_m3d_vis_nodisp", "render_replica", "render_m3d_2src"]
+
+
+def _oracle_pass(name):
+    from oracle import render as R
+    cfg, _, _ = cases.make_render_inputs(name)
+    que, ref, W, _ = split_golden(load_golden(name))
+    rn = que["coords"].shape[1]
+    depth = R.sample_depth(cfg["min_depth"], cfg["max_depth"], rn, cfg["depth_sample_num"], cfg["use_disp"])
+    out = R.render_by_depth(cfg, W, que, ref, depth, False, return_prj=True)
+    return cfg, que, ref, W, depth, out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_functional_geometry_ops(name):
+    from oracle import render as R
+    from panogrf_b200 import render_ops as rops
+    cfg, que, ref, W, depth, out = _oracle_pass(name)
+    spt = types.SimpleNamespace(dataset=cfg["dataset_name"], height=cfg["height"], width=cfg["width"])
+    pts_o, dir_o = R.depth2points_spherical(cfg["dataset_name"], cfg["height"], cfg["width"], que["c2w"], que["coords"], depth)
+    pts, dirs = rops.depth2points_spherical(cuda_dict(que), depth.cuda(), spt)
+    assert_close(pts, pts_o, rtol=1e-5, atol=1e-5, what="que_pts")
+    assert_close(dirs, dir_o, rtol=1e-5, atol=1e-6, what="que_dir")
+    rfn, _, h, w = ref["imgs"].shape
+    pix = out["prj"]["pts"].reshape(rfn, -1, 2)
+    for key in ("ray_feats", "img_feats", "imgs"):
+        got = rops.interpolate_feature_map(ref[key].cuda(), pix.cuda(), h, w)
+        assert_close(got, R.bilinear_border(ref[key], pix, h, w), rtol=1e-4, atol=1e-4, what=key)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_dist_decoder_module(name):
+    from oracle import render as R
+    cfg, que, ref, W, depth, out = _oracle_pass(name)
+    net = build_renderer(cfg, W)
+    prj = out["prj"]
+    use_vis = cfg["dist_decoder_cfg"].get("use_vis", True)
+    mean_o, var_o, vis_o, aw_o = R.dist_decoder_forward(W, "dist_decoder", prj["ray_feats"], use_vis)
+    mean, var, vis, aw = net.dist_decoder(prj["ray_feats"].cuda())
+    assert_close(mean, mean_o, rtol=1e-4, atol=1e-5, what="mean")
+    assert_close(var, var_o, rtol=1e-4, atol=1e-5, what="var")
+    assert_close(aw, aw_o, rtol=1e-4, atol=1e-5, what="aw")
+    assert (vis is None) == (vis_o is None)
+    if vis is not None:
+        assert_close(vis, vis_o, rtol=1e-4, atol=1e-5, what="vis")
+    # compute_prob on the ORACLE's decoder outputs: same inputs on both sides
+    c = lambda t: None if t is None else t.cuda()
+    a, v, h = net.dist_decoder.compute_prob(prj["depth"].squeeze(-1).cuda(), out["dists"].unsqueeze(0).cuda(), c(mean_o), c(var_o),
+                                            c(vis_o), c(aw_o), True, ref["depth_range"].cuda())
+    a_o, v_o, h_o = R.compute_prob_ref(prj["depth"].squeeze(-1), out["dists"].unsqueeze(0), mean_o, var_o, vis_o, aw_o,
+                                       ref["depth_range"], use_vis)
+    assert_close(v, v_o, rtol=1e-4, atol=1e-5, what="visibility")
+    assert_close(h, h_o, rtol=1e-4, atol=1e-5, what="hit_prob")
+    assert_close(a, a_o, rtol=1e-4, atol=2e-3, what="alpha")       # log of a ratio of differences: ill-conditioned near 0
+    with pytest.raises(NotImplementedError):
+        net.dist_decoder.compute_prob(prj["depth"].squeeze(-1).cuda(), out["dists"].unsqueeze(0).cuda(), c(mean_o), c(var_o),
+                                      c(vis_o), c(aw_o), False, ref["depth_range"].cuda())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_predict_prob_agg_net_and_network_rendering(name):
+    cfg, que, ref, W, depth, out = _oracle_pass(name)
+    net = build_renderer(cfg, W)
+    prj_o = out["prj"]
+    # 1. predict_proj_ray_prob + get_img_feats from the geometric part of the dict
+    prj = {k: prj_o[k].cuda() for k in ("pts", "depth", "dir", "ray_feats", "rgb")}
+    prj = net.predict_proj_ray_prob(prj, cuda_dict(ref), out["dists"].cuda(), False)
+    prj = net.get_img_feats(cuda_dict(ref), prj)
+    assert_close(prj["vis"], prj_o["vis"], rtol=1e-4, atol=1e-5, what="vis")
+    assert_close(prj["hit_prob"], prj_o["hit_prob"], rtol=1e-4, atol=1e-5, what="hit_prob")
+    assert_close(prj["alpha"], prj_o["alpha"], rtol=1e-4, atol=2e-3, what="alpha")
+    assert_close(prj["img_feats"], prj_o["img_feats"], rtol=1e-4, atol=1e-4, what="img_feats")
+    # 2. the aggregation network on the ORACLE's dict (identical inputs)
+    prj_in = {k: v.cuda() for k, v in prj_o.items()}
+    density, colors = net.agg_net(prj_in, out["que_dir"].cuda())
+    assert density.shape == out["density_nr"].shape and colors.shape == out["colors_nr"].shape
+    assert_close(density, out["density_nr"], rtol=1e-4, atol=1e-4, what="density")
+    assert_close(colors, out["colors_nr"], rtol=1e-4, atol=1e-4, what="colors")
+    # 3. network_rendering
+    hit, col, pix, den = net.network_rendering(prj_in, out["que_dir"].cuda(), False)
+    assert_close(hit, out["hit_prob_nr"], rtol=1e-4, atol=1e-5, what="hit_prob_nr")
+    assert_close(pix, out["pixel_colors_nr"], rtol=1e-4, atol=1e-4, what="pixel_colors_nr")
+    assert_close(den, out["density_nr"], rtol=1e-4, atol=1e-4, what="density_nr")
+    # the positional table is tied to sample_num like in the reference (ibrnet.py:358)
+    bad = {k: v[:, :, :, :-1] for k, v in prj_in.items()}
+    with pytest.raises(RuntimeError):
+        net.agg_net(bad, out["que_dir"][:, :, :-1].cuda())
