@@ -447,6 +447,8 @@ def render_by_depth(cfg, W, que, ref, depth, is_fine, return_prj=False):
     hit, pixel_colors, render_depth = composite(density, colors, depth)
     out = {"pixel_colors_nr": pixel_colors, "hit_prob_nr": hit, "colors_nr": colors, "density_nr": density,
            "render_depth": render_depth}
+    if cfg.get("render_uncert", False):                                   # renderer.py:299-301
+        out["render_uncert"] = ((depth - render_depth.unsqueeze(-1)).pow(2) * hit).sum(-1) + 1e-5
     if return_prj:
         out["prj"] = prj
         out["que_dir"] = que_dir
@@ -468,6 +470,14 @@ def render_rays(cfg, W, que, ref, keep_hit_prob=False):
         else:
             fdepth = torch.sort(fine, -1)[0]
         fout = render_by_depth(cfg, W, que, ref, fdepth, not cfg.get("one_mlp", False))
+        if cfg.get("render_c2f_all", False):                              # renderer.py:484-521: coarse + fine samples together
+            z, idx = torch.cat([depth, fdepth], 2).sort()
+            col = torch.gather(torch.cat([out["colors_nr"], fout["colors_nr"]], 2), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 3))
+            den = torch.gather(torch.cat([out["density_nr"], fout["density_nr"]], 2), 2, idx)
+            hit, pix, rdepth = composite(den, col, z)
+            fout.update({"pixel_colors_nr": pix, "hit_prob_nr": hit, "colors_nr": col, "density_nr": den, "render_depth": rdepth})
+            if cfg.get("render_uncert", False):
+                fout["render_uncert"] = ((z - rdepth.unsqueeze(-1)).pow(2) * hit).sum(-1) + 1e-5
         fout["que_depth"] = fdepth
         for k, v in fout.items():
             out[k + "_fine"] = v

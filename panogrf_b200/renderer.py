@@ -74,6 +74,18 @@ class MixtureLogisticsDistDecoder(nn.Module):
         vis = out[:, 4:5].reshape(*lead, 1) if self.cfg["use_vis"] else None
         return mean, var, vis, out[:, 5:6].reshape(*lead, 1)
 
+    def predict_mean(self, prj_ray_feats):
+        """dist_decoder.py:146-148."""
+        return self.forward(prj_ray_feats)[0]
+
+    def predict_aw(self, prj_ray_feats):
+        """dist_decoder.py:150-151."""
+        return self.forward(prj_ray_feats)[3]
+
+    def decode_alpha_value(self, alpha_value):
+        """dist_decoder.py:142-144."""
+        return torch.sigmoid(alpha_value)
+
     def compute_prob(self, depth, interval, mean, var, vis, aw, is_ref, depth_range):
         """dist_decoder.py:109-140 (is_ref=True, the render path): depth (rfn,qn,rn,dn), interval (1|rfn,qn,rn,dn),
         mean/var (rfn,qn,rn,dn,2), vis/aw (rfn,qn,rn,dn,1), depth_range (rfn,2) -> alpha, visibility, hit_prob (rfn,qn,rn,dn)."""
@@ -484,8 +496,9 @@ class NeuralRayBaseRenderer(nn.Module):
         dev = coords2.device
         dn = int(cfg["depth_sample_num"])
         hier = bool(cfg["use_hierarchical_sampling"])
+        own = _outs is None
         if _outs is None:
-            _outs = self._alloc_outputs(rn, dev, keep_hit_prob or hier, ctx['rfn'])
+            _outs = self._alloc_outputs(rn, dev, keep_hit_prob or hier or self._needs_post(), ctx['rfn'])
             _r0 = 0
         depth_table = coarse_depth_table(cfg, dn, cfg["use_disp"]).to(dev)
         coarse = {k: v for k, v in _outs.items() if not k.endswith("_fine")}
@@ -496,7 +509,42 @@ class NeuralRayBaseRenderer(nn.Module):
                        "hit_prob_nr" in fine)
             if "que_depth_fine" in _outs:
                 _outs["que_depth_fine"][0, _r0:_r0 + rn] = fine_depth
+        if own:
+            self._post(_outs, depth_table, True)
         return _outs
+
+    def _needs_post(self):
+        return bool(self.cfg.get("render_uncert")) or bool(self.cfg.get("render_c2f_all") and self.cfg["use_hierarchical_sampling"])
+
+    def _post(self, outs, depth_table, keep_hit_prob):
+        """Optional outputs assembled from the per-sample results: `render_c2f_all` re-composites the coarse and the
+        fine samples together (renderer.py:484-521), `render_uncert` is the depth variance under hit_prob (:299-301)."""
+        cfg = self.cfg
+        if not self._needs_post():
+            return outs
+        from .render_ops import composite
+        z_c = depth_table.view(1, 1, -1).expand_as(outs["hit_prob_nr"])
+        unc = lambda z, d, h: ((z - d.unsqueeze(-1)).pow(2) * h).sum(-1) + 1e-5
+        if cfg.get("render_uncert"):
+            if "render_depth" not in outs:
+                raise KeyError("render_depth")                       # the reference reads outputs['render_depth'] (:300)
+            outs["render_uncert"] = unc(z_c, outs["render_depth"], outs["hit_prob_nr"])
+        if cfg["use_hierarchical_sampling"]:
+            z_f = outs["que_depth_fine"]
+            if cfg.get("render_c2f_all"):
+                z_f, idx = torch.cat([z_c, z_f], 2).sort()
+                col = torch.gather(torch.cat([outs["colors_nr"], outs["colors_nr_fine"]], 2), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 3))
+                den = torch.gather(torch.cat([outs["density_nr"], outs["density_nr_fine"]], 2), 2, idx)
+                hit, pix, rdepth = composite(den, col, z_f)
+                outs.update({"pixel_colors_nr_fine": pix, "hit_prob_nr_fine": hit, "colors_nr_fine": col, "density_nr_fine": den})
+                if "render_depth_fine" in outs:
+                    outs["render_depth_fine"] = rdepth
+            if cfg.get("render_uncert"):
+                outs["render_uncert_fine"] = unc(z_f, outs["render_depth_fine"], outs["hit_prob_nr_fine"])
+        if not keep_hit_prob:
+            for k in ("hit_prob_nr", "hit_prob_nr_fine", "que_depth_fine"):
+                outs.pop(k, None)
+        return outs
 
     def _alloc_outputs(self, rn, dev, keep_hit_prob, rfn):
         cfg = self.cfg
@@ -543,8 +591,14 @@ class NeuralRayBaseRenderer(nn.Module):
         coords = que_imgs_info["coords"]
         assert coords.shape[0] == 1
         rn = coords.shape[1]
-        outs = self._alloc_outputs(rn, coords.device, keep_hit_prob, ctx['rfn'])
+        outs = self._alloc_outputs(rn, coords.device, keep_hit_prob or self._needs_post(), ctx['rfn'])
         self._render_view(ctx, coords[0].float().contiguous(), outs)
+        if self._needs_post():
+            dn = int(self.cfg["depth_sample_num"])
+            table = self._cached_table(("coarse", dn, bool(self.cfg["use_disp"]), float(self.cfg["min_depth"]),
+                                        float(self.cfg["max_depth"])), coords.device,
+                                       lambda: coarse_depth_table(self.cfg, dn, self.cfg["use_disp"]))
+            self._post(outs, table, keep_hit_prob)
         return outs
 
     def _render_diner(self, que_imgs_info, ref_imgs_info, keep_hit_prob=False):
@@ -744,4 +798,57 @@ class NeuralRayBaseRenderer(nn.Module):
         return self.render(que, ref, "eval" not in data, is_perspec)
 
 
-name2network = {"neuray_base": NeuralRayBaseRenderer}
+class NeuralRayGenRenderer(NeuralRayBaseRenderer):
+    """network/renderer.py:688-786.  The initialisation network (cost-volume MVS + CNNs, `name2init_net`) is outside the
+    hot path: attach it as `self.init_net` (any callable with the reference's signature
+    `init_net(ref_imgs_info, src_imgs_info, is_train) -> {'ray_feats', 'mvs_depth'[, 'mvs_uncert']}`), or pass
+    `ref_imgs_info` that already holds 'ray_feats'."""
+    gen_default_cfg = {"init_net_type": "depth", "init_net_cfg": {}, "use_depth_loss": False, "depth_loss_coords_num": 8192}
+
+    def __init__(self, cfg):
+        super().__init__({**self.gen_default_cfg, **cfg})
+        self.init_net = None
+
+    def render_call(self, que_imgs_info, ref_imgs_info, is_train, src_imgs_info=None, is_perspec=False):
+        if self.init_net is not None:
+            ret = self.init_net(ref_imgs_info, src_imgs_info, is_train)
+            ref_imgs_info["ray_feats"] = ret["ray_feats"]
+            ref_imgs_info["mvs_depth"] = ret["mvs_depth"]
+            if self.cfg.get("uncert_tune"):
+                ref_imgs_info["mvs_uncert"] = ret["mvs_uncert"]
+        elif "ray_feats" not in ref_imgs_info:
+            raise _lib.PanoGRFError("NeuralRayGenRenderer: attach init_net or pass pre-computed ref_imgs_info['ray_feats']")
+        if self.cfg.get("backface_culling") and "mvs_normal" not in ref_imgs_info:
+            raise _lib.PanoGRFError("backface_culling needs ref_imgs_info['mvs_normal'] (depth2normal is outside the hot path)")
+        return self.render(que_imgs_info, ref_imgs_info, is_train, is_perspec)
+
+    def gen_depth_loss_coords(self, h, w, device):
+        coords = torch.stack(torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij"), -1).reshape(-1, 2).to(device)
+        return coords[torch.randperm(coords.shape[0])[:self.cfg["depth_loss_coords_num"]]]
+
+    def predict_mean_for_depth_loss(self, ref_imgs_info):
+        """renderer.py:730-775: mixture means of the (fine) dist decoder at random source pixels."""
+        from .render_ops import interpolate_feature_map
+        ray_feats, imgs = ref_imgs_info["ray_feats"], ref_imgs_info["imgs"]
+        rfn, _, h, w = imgs.shape
+        coords = self.gen_depth_loss_coords(h, w, imgs.device).unsqueeze(0).repeat(rfn, 1, 1)
+        feats = interpolate_feature_map(ray_feats, coords.float(), h, w)
+        mean = self.dist_decoder.predict_mean(feats)
+        out = {"depth_mean": mean[..., 0], "depth_coords": coords, "depth_mean_2": mean[..., 1]}
+        if self.cfg["use_hierarchical_sampling"] and not self.cfg.get("one_mlp"):
+            fmean = self.fine_dist_decoder.predict_mean(feats)
+            out["depth_mean_fine"], out["depth_mean_fine_2"] = fmean[..., 0], fmean[..., 1]
+        return out
+
+    def forward(self, data, is_perspec=False):
+        ref = dict(data["ref_imgs_info"])
+        que = dict(data["que_imgs_info"])
+        is_train = "eval" not in data
+        src = dict(data["src_imgs_info"]) if "src_imgs_info" in data else None
+        outs = self.render_call(que, ref, is_train, src, is_perspec=is_perspec)
+        if (self.cfg["use_depth_loss"] and "true_depth" in ref) or (not is_train):
+            outs.update(self.predict_mean_for_depth_loss(ref))
+        return outs
+
+
+name2network = {"neuray_base": NeuralRayBaseRenderer, "neuray_gen": NeuralRayGenRenderer}

@@ -102,6 +102,8 @@ RENDER_CASES = {
     "render_residential": dict(cfg=dict(dataset="residential"), rfn=2, n_rays=64),
     "render_replica": dict(cfg=dict(dataset="replica_test"), rfn=3, n_rays=64),
     "render_coffee": dict(cfg=dict(dataset="CoffeeArea", hierarchical=False), rfn=2, n_rays=64),
+    # optional outputs: depth variance (renderer.py:299-301) and the coarse+fine re-compositing of render_c2f_all (:484-521)
+    "render_m3d_c2f_all": dict(cfg=dict(render_uncert=True, render_c2f_all=True), rfn=2, n_rays=48),
 }
 
 

@@ -102,3 +102,38 @@ def test_predict_prob_agg_net_and_network_rendering(name):
     bad = {k: v[:, :, :, :-1] for k, v in prj_in.items()}
     with pytest.raises(RuntimeError):
         net.agg_net(bad, out["que_dir"][:, :, :-1].cuda())
+
+
+def test_gen_renderer_forward_and_registry():
+    """NeuralRayGenRenderer.forward(data) (renderer.py:777-786): init_net hook, render, depth-mean outputs in eval."""
+    import panogrf_b200 as pg
+    from oracle import render as R
+    name = "render_m3d_2src"
+    cfg, _, _ = cases.make_render_inputs(name)
+    que, ref, W, gold = split_golden(load_golden(name))
+    assert pg.name2network["neuray_gen"] is pg.NeuralRayGenRenderer
+    net = pg.NeuralRayGenRenderer({**cfg, "depth_loss_coords_num": 256}).cuda().eval()
+    net.load_state_dict(W, strict=True)
+    ref_c = cuda_dict(ref)
+    ray_feats = ref_c.pop("ray_feats")
+    calls = []
+
+    def init_net(ref_imgs_info, src_imgs_info, is_train):          # stands in for the (out-of-scope) CNN init net
+        calls.append((src_imgs_info is not None, is_train))
+        return {"ray_feats": ray_feats, "mvs_depth": torch.ones(2, 1, 8, 16, device="cuda")}
+
+    with pytest.raises(pg._lib.PanoGRFError):
+        net({"que_imgs_info": cuda_dict(que), "ref_imgs_info": dict(ref_c), "eval": True})
+    net.init_net = init_net
+    out = net({"que_imgs_info": cuda_dict(que), "ref_imgs_info": dict(ref_c), "src_imgs_info": {}, "eval": True})
+    assert calls == [(True, False)]
+    assert_close(out["pixel_colors_nr_fine"], gold["pixel_colors_nr_fine"].float(), rtol=1e-4, atol=5e-5, what="gen/pixel_colors_nr_fine")
+    assert out["depth_mean"].shape == (2, 256) and out["depth_coords"].shape == (2, 256, 2)
+    # depth_mean == first mixture mean of the coarse decoder at those source pixels
+    h, w = ref["imgs"].shape[-2:]
+    feats = R.bilinear_border(ref["ray_feats"], out["depth_coords"].float().cpu(), h, w)
+    mean_o = R.dist_decoder_forward(W, "dist_decoder", feats, cfg["dist_decoder_cfg"].get("use_vis", True))[0]
+    assert_close(out["depth_mean"], mean_o[..., 0], rtol=1e-4, atol=1e-5, what="gen/depth_mean")
+    assert_close(out["depth_mean_fine_2"],
+                 R.dist_decoder_forward(W, "fine_dist_decoder", feats, cfg["fine_dist_decoder_cfg"].get("use_vis", True))[0][..., 1],
+                 rtol=1e-4, atol=1e-5, what="gen/depth_mean_fine_2")
