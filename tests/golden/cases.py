@@ -104,6 +104,8 @@ RENDER_CASES = {
     "render_coffee": dict(cfg=dict(dataset="CoffeeArea", hierarchical=False), rfn=2, n_rays=64),
     # optional outputs: depth variance (renderer.py:299-301) and the coarse+fine re-compositing of render_c2f_all (:484-521)
     "render_m3d_c2f_all": dict(cfg=dict(render_uncert=True, render_c2f_all=True), rfn=2, n_rays=48),
+    # one source view: ibrnet.py:359-360 masks every attention key (uniform weights); ragged sizes (37 rays, 24 samples)
+    "render_m3d_1src": dict(cfg=dict(sample_num=24, use_vis=True), rfn=1, n_rays=37),
 }
 
 
