@@ -60,11 +60,10 @@ __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128
 // stages executed once per tile by only 8 warps, so instruction-cache footprint matters more than unrolling. ----
 // dst chunks [0,nchunks) = bf16( act(acc + bias) )
 // acc[16] (+bias) -> activation, as 8 packed fp32 pairs (FADD2 / FMUL2: one issue slot per two elements)
-__device__ __forceinline__ void act_pairs(float (&v)[16], const float* __restrict__ bias, int act) {
-  const float4* b4 = reinterpret_cast<const float4*>(bias);
+__device__ __forceinline__ void act_pairs(float (&v)[16], const float4 (&bb)[4], int act) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 b = b4[i];
+    const float4 b = bb[i];
     const float2 lo = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
     const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
     v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
@@ -85,9 +84,12 @@ static __device__ __noinline__ void epi_act_store(uint32_t taddr, const float* _
   // two chunks (16 accumulator columns) per TMEM round trip; nchunks is even for every caller
 #pragma unroll 1
   for (int c = 0; c < nchunks; c += 2) {
+    float4 bb[4];   // issued before the TMEM load: the tcgen05.ld / wait::ld asm is a compiler barrier for shared-memory loads
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bb[i] = reinterpret_cast<const float4*>(bias + 8 * c)[i];
     float v[16];
     umma::ld16(taddr + 8 * c, v);
-    act_pairs(v, bias + 8 * c, act);
+    act_pairs(v, bb, act);
     umma::store_chunk(dst, ROWS, c, m, v);
     umma::store_chunk(dst, ROWS, c + 1, m, v + 8);
   }
@@ -102,9 +104,12 @@ static __device__ __noinline__ void epi_act_gemv(uint32_t taddr, const float* __
   for (int j = 0; j < NOUT; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int c = 0; c < nchunks; c += 2) {
+    float4 bb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bb[i] = reinterpret_cast<const float4*>(bias + 8 * c)[i];
     float v[16];
     umma::ld16(taddr + 8 * c, v);
-    act_pairs(v, bias + 8 * c, act);
+    act_pairs(v, bb, act);
     if (dst) {
       umma::store_chunk(dst, ROWS, c, m, v);
       umma::store_chunk(dst, ROWS, c + 1, m, v + 8);
