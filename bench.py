@@ -358,8 +358,12 @@ def time_stages(torch, net, que_d, ref_d, flush):
     kernels = {k: {"ms": round(v, 4), "tflops": round(flops[k] / v / 1e9, 2), "rays": rn} for k, v in res.items()}
     top = max(res, key=res.get)
     peak = peaks["bf16_sustained"] or peaks["bf16_tflops"]
+    # DRAM bytes per ray of the two bf16 kernels from the committed ncu capture (profiles/r1_final_ncu_summary.md: 16 384-ray launch,
+    # dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch; None for the fp32 kernels (not captured this round)
+    ncu_dram_per_ray = {"render_mlp_bf16_kernel": (0.006649e9 + 0.233480e9) / 16384, "render_rays_bf16_kernel": (0.285318e9 + 0.019544e9) / 16384}
+    traffic = ncu_dram_per_ray[top] * rn if top in ncu_dram_per_ray else None
     roof = {"kernel": top, "bound": "tensor", "achieved": flops[top] / res[top] / 1e9, "peak": peak, "unit": "TFLOP/s",
-            "frac": flops[top] / res[top] / 1e9 / peak, "traffic": None,
+            "frac": flops[top] / res[top] / 1e9 / peak, "traffic": traffic,
             "note": (f"algorithmic (unpadded) MLP FLOPs of the kernel / its CUDA-event time, against the {peaks['src']} bf16 "
                      "tensor peak (sustained); " + ("tcgen05 bf16 path" if net.mlp_dtype == "bf16" else
                                                    "fp32 SIMT parity path, fp32 FMA peak of B200 is ~74 TFLOP/s"))}
