@@ -453,7 +453,8 @@ def time_project_gather(torch, que_d, ref_d, flush, peaks):
     return {"workload": f"{rn} rays x {dn} samples x {RFN} views -> pts,depth,dir,ray_feats,rgb,img_feats (292 B/row)",
             "rows_per_s": rows / ms * 1e3, "ms": ms,
             "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "bytes_per_row": 292}}
+                         "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": (0.056696e9 + 0.554805e9) * rn / 16384,   # ncu, 16 384-ray capture scaled
+                         "bytes_per_row": 292}}
 
 
 def time_cost_volume(torch, pg, flush, peaks):
@@ -508,7 +509,7 @@ def time_cost_volume(torch, pg, flush, peaks):
             "timing": f"median of groups of {REPS} back-to-back calls, 256 MiB L2 flush before each group",
             "voxels_per_s": vox / ms * 1e3, "ms": ms,
             "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": None,
+                         "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": 0.066685e9 + 1.016099e9,   # ncu, profiles/r1_final_ncu_summary.md
                          "bytes_per_voxel": alg / vox, "peak_src": peaks["src"]},
             "channels_last": {"ms": ms_cl, "voxels_per_s": vox / ms_cl * 1e3, "frac": alg / ms_cl / 1e6 / peaks["hbm_gbs"]},
             "backward": {"ms": ms_bwd, "voxels_per_s": vox / ms_bwd * 1e3, "frac": alg / ms_bwd / 1e6 / peaks["hbm_gbs"],
