@@ -33,6 +33,27 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tbase = tmem_base;
+  if (swap_lbo_sbo == 2) {
+    // variant 2: A operand in TMEM columns [128, 128 + K/2): every thread writes its own row with tcgen05.st
+    const uint32_t a_lane = tbase + ((uint32_t)(warp * 32) << 16) + 128;
+    for (int k = 0; k < K; k += 16) {
+      uint32_t r[8];
+      for (int i = 0; i < 8; ++i) r[i] = umma::pack2(A[(size_t)tid * K + k + 2 * i], A[(size_t)tid * K + k + 2 * i + 1]);
+      umma::st8(a_lane + (k >> 1), r);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (tid == 0) {
+      const uint32_t idesc = umma::instr_desc_bf16(128, N);
+      for (int k = 0; k < K; k += 16) {
+        const uint64_t bd = umma::smem_desc(umma::smem_addr(Ws) + (k >> 3) * N * 16, N * 16, 128);
+        umma::mma_bf16_ts(tbase, tbase + 128 + (k >> 1), bd, idesc, k > 0);
+      }
+      umma::commit(&bar);
+    }
+  } else
   if (tid == 0) {
     if (!swap_lbo_sbo) {
       umma::gemm_issue(tbase, As, 128, Ws, N, N, K);
