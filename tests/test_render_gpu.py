@@ -232,3 +232,50 @@ def test_bf16_full_view_end_to_end():
         err = (a[k].float().cpu() - e).abs()
         assert float(err.mean()) < 5e-3 * float(e.abs().max()), (k, float(err.mean()))
         assert float(err.max()) < 1e-1 * float(e.abs().max()), (k, float(err.max()))
+
+
+@pytest.mark.parametrize("rfn", [2, 4])
+def test_production_shapes_max_samples(rfn):
+    """The bench's sample counts at the kernel limits: 64 coarse + 64 fine samples merged (fine pass dn = 128 = the
+    maximum), 2 and 4 source views (64- and 32-sample tiles), ragged ray count, against the oracle; fp32 1e-4, bf16 1e-2."""
+    import panogrf_b200 as pg
+    cfg = cases.render_cfg(height=64, width=128, hierarchical=True, fine_use_all=True, use_vis=True)
+    cfg.pop("sample_num")
+    cfg.update(depth_sample_num=64, fine_depth_sample_num=64, agg_net_cfg={"sample_num": 64}, fine_agg_net_cfg={"sample_num": 128})
+    gen = torch.Generator().manual_seed(100 + rfn)
+    torch.manual_seed(100 + rfn)
+    net = pg.NeuralRayBaseRenderer(cfg)
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            if n_.endswith("bias"):
+                p_.copy_(torch.randn(p_.shape, generator=gen) * 0.1)
+    W = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    h, w = 64, 128
+    imgs = cases.smooth(torch.rand(rfn, h, w, 3, generator=gen), 1).permute(0, 3, 1, 2).contiguous()
+    rots = cases.small_rotations(gen, 1, rfn, 6.0)[0]
+    trans = torch.randn(rfn, 3, generator=gen) * 0.3
+    ref = {"imgs": imgs, "w2c": torch.cat([rots, trans[:, :, None]], -1).contiguous(),
+           "depth_range": torch.tensor([[0.5, 15.0]]).repeat(rfn, 1),
+           "ray_feats": cases.smooth(torch.randn(rfn, h // 4, w // 4, 32, generator=gen), 1).permute(0, 3, 1, 2).contiguous(),
+           "img_feats": cases.smooth(torch.randn(rfn, h // 2, w // 2, 32, generator=gen), 1).permute(0, 3, 1, 2).contiguous()}
+    perm = torch.randperm(h * w, generator=gen)[:45]
+    coords = torch.stack([(perm % w).float(), (perm // w).float()], -1)[None]
+    que = {"coords": coords, "c2w": torch.eye(4)[None, :3], "depth_range": torch.tensor([[0.5, 15.0]])}
+    o = orender.render_rays(cfg, W, que, ref, keep_hit_prob=True)
+    assert o["hit_prob_nr_fine"].shape == (1, 45, 128)
+    net = net.cuda().eval()
+    out = net.render(cuda_dict(que), cuda_dict(ref), False, keep_hit_prob=True)
+    for k in ("pixel_colors_nr", "render_depth", "hit_prob_nr", "density_nr", "pixel_colors_nr_fine", "render_depth_fine",
+              "que_depth_fine", "hit_prob_nr_fine", "density_nr_fine", "colors_nr_fine"):
+        # inverse-CDF resampling divides by the cdf increment of a bin: in a nearly empty bin a 1e-7 difference of the coarse
+        # hit_prob moves a fine sample by a few 1e-4 (and its per-sample outputs with it); one sample in a thousand may do so
+        frac = 2e-3 if k in ("que_depth_fine", "hit_prob_nr_fine", "density_nr_fine", "colors_nr_fine") else 0.0
+        assert_close(out[k], o[k], rtol=1e-4, atol=1e-4, max_bad_frac=frac, what=f"max-samples rfn={rfn} fp32 {k}")
+    net16 = build_renderer({**cfg, "mlp_dtype": "bf16"}, W)
+    out16 = net16.render(cuda_dict(que), cuda_dict(ref), False, keep_hit_prob=True)
+    _close_bf16(out16["pixel_colors_nr"], o["pixel_colors_nr"], f"rfn={rfn} bf16 pixel_colors_nr", 1e-2)
+    _close_bf16(out16["render_depth"], o["render_depth"], f"rfn={rfn} bf16 render_depth", 1e-2)
+    _close_bf16(out16["hit_prob_nr"], o["hit_prob_nr"], f"rfn={rfn} bf16 hit_prob_nr", 3e-2)
+    # the fine pass resamples from the (bf16) coarse hit_prob: smooth maps keep the composited result within 3 % of range
+    _close_bf16(out16["pixel_colors_nr_fine"], o["pixel_colors_nr_fine"], f"rfn={rfn} bf16 pixel_colors_nr_fine", 3e-2)
+    assert out16["hit_prob_nr_fine"].shape == (1, 45, 128) and bool(torch.isfinite(out16["colors_nr_fine"]).all())
