@@ -92,29 +92,37 @@ __device__ __forceinline__ void gemm_smem(const float* __restrict__ A, int lda, 
     const int n0 = (t / ntm) * CT + TN * g;
     if (n0 >= N) continue;  // ragged last column tile (N multiple of TN but not of CT)
     float acc[4][TN];
+    // accumulators as packed fp32 pairs over two neighbouring output columns: FFMA2 performs the same two fused
+    // multiply-adds (bit-identical results) in one issue slot
+    float2 acc2[4][TN / 2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < TN / 2; ++j) acc2[i][j] = make_float2(0.f, 0.f);
     const float* a_ptr = A + m0;
     const float* w_ptr = Wt + n0;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(a_ptr + k * lda);
-      float w[TN];
+      float2 w2[TN / 2];
 #pragma unroll
       for (int j4 = 0; j4 < TN / 4; ++j4) {
         const float4 wv = *reinterpret_cast<const float4*>(w_ptr + k * ldw + 4 * j4);
-        w[4 * j4] = wv.x; w[4 * j4 + 1] = wv.y; w[4 * j4 + 2] = wv.z; w[4 * j4 + 3] = wv.w;
+        w2[2 * j4] = make_float2(wv.x, wv.y); w2[2 * j4 + 1] = make_float2(wv.z, wv.w);
       }
+      const float2 ax = make_float2(a.x, a.x), ay = make_float2(a.y, a.y), az = make_float2(a.z, a.z), aw = make_float2(a.w, a.w);
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        acc[0][j] = fmaf(a.x, w[j], acc[0][j]);
-        acc[1][j] = fmaf(a.y, w[j], acc[1][j]);
-        acc[2][j] = fmaf(a.z, w[j], acc[2][j]);
-        acc[3][j] = fmaf(a.w, w[j], acc[3][j]);
+      for (int j = 0; j < TN / 2; ++j) {
+        acc2[0][j] = ffma2(ax, w2[j], acc2[0][j]);
+        acc2[1][j] = ffma2(ay, w2[j], acc2[1][j]);
+        acc2[2][j] = ffma2(az, w2[j], acc2[2][j]);
+        acc2[3][j] = ffma2(aw, w2[j], acc2[3][j]);
       }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TN / 2; ++j) { acc[i][2 * j] = acc2[i][j].x; acc[i][2 * j + 1] = acc2[i][j].y; }
     float rs[4] = {1.f, 1.f, 1.f, 1.f};
     if (ROW_SCALE) {
       const float4 r = *reinterpret_cast<const float4*>(row_scale + m0);
