@@ -302,7 +302,7 @@ def main():
 
 
 def rays_per_launch(net):
-    return int(net.rays_per_launch or (131072 if net.mlp_dtype == "bf16" else 4096))
+    return int(net.rays_per_launch or (131072 if net.mlp_dtype == "bf16" else 32768))
 
 
 def time_stages(torch, net, que_d, ref_d, flush):

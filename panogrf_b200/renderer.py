@@ -312,7 +312,7 @@ class NeuralRayBaseRenderer(nn.Module):
     }
     #: rays per kernel launch (the reference's ray_batch_num only bounds ITS activation memory; here it bounds the
     #: inter-kernel workspaces).  None = 131072 for the bf16 path (only the 272 B/sample F2 tiles exist; larger launches
-    #: amortise the per-CTA weight load and the tail), 4096 for the fp32 path (F1 tiles: 38.9 KB per 64 samples).
+    #: amortise the per-CTA weight load and the tail), 32768 for the fp32 path (F1 tiles: 38.9 KB per 64 samples, 1.3 GB of workspace).
     rays_per_launch = None
 
     def __init__(self, cfg):
@@ -642,7 +642,7 @@ class NeuralRayBaseRenderer(nn.Module):
         fdn = int(cfg["fine_depth_sample_num"])
         fine_total = fdn + (N if cfg["fine_depth_use_all"] else 0)
         fine = alloc(fine_total) if c2f else None
-        rpl = self.rays_per_launch or (131072 if self.mlp_dtype == "bf16" else 4096)
+        rpl = self.rays_per_launch or (131072 if self.mlp_dtype == "bf16" else 32768)
         d2 = depth[0]
         for r0 in range(0, rn, int(rpl)):
             n = min(int(rpl), rn - r0)
@@ -679,7 +679,7 @@ class NeuralRayBaseRenderer(nn.Module):
             if agg.cfg["sample_num"] != n:
                 raise RuntimeError(f"The size of tensor a ({n}) must match the size of tensor b "
                                    f"({agg.cfg['sample_num']}) at non-singleton dimension 1")   # ibrnet.py:358
-        rpl = self.rays_per_launch or (131072 if self.mlp_dtype == "bf16" else 4096)
+        rpl = self.rays_per_launch or (131072 if self.mlp_dtype == "bf16" else 32768)
         chunk = max(1, min(int(rpl), rn))
         va = _lib.RenderViewArgs()
         a = va.pass_
