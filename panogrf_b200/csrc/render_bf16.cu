@@ -54,6 +54,8 @@ constexpr int SM16_WG = (kW16Sec0Bytes + 127) & ~127;
 constexpr int SM16_BAR = SM16_WG + kWG * WG_BYTES;
 constexpr int SM16_BYTES = SM16_BAR + 64;
 
+// softplus for the bf16 path: log(1 + e^x) through lg2.approx (absolute error ~1e-7; the fp32 path keeps log1pf)
+__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + fast_exp(x)); }
 __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 
 // ---- epilogues (thread = row m).  Kept out of line and rolled: the kernel is a long straight-line sequence of
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     {
       float o2[2];
       epi_act_gemv<2>(tq + 0, Bias + B16(M_MEAN1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_MEAN2), 32, o2);
-      mean[0] = softplusf(o2[0] + Wsm[SMB(M_MEAN2)]); mean[1] = softplusf(o2[1] + Wsm[SMB(M_MEAN2) + 1]);
+      mean[0] = softplus_fast(o2[0] + Wsm[SMB(M_MEAN2)]); mean[1] = softplus_fast(o2[1] + Wsm[SMB(M_MEAN2) + 1]);
       epi_act_store(tq + 32, Bias + B16(M_VAR0), P + P_HDB, m, 4, ACT_ELU);
     }
     STAGE_BEGIN()
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     {
       float o2[2];
       epi_act_gemv<2>(tq + 0, Bias + B16(M_VAR1), nullptr, m, 4, ACT_ELU, Wsm + SMW(M_VAR2), 32, o2);
-      var[0] = softplusf(o2[0] + Wsm[SMB(M_VAR2)]) + a.bias_val; var[1] = softplusf(o2[1] + Wsm[SMB(M_VAR2) + 1]) + a.bias_val;
+      var[0] = softplus_fast(o2[0] + Wsm[SMB(M_VAR2)]) + a.bias_val; var[1] = softplus_fast(o2[1] + Wsm[SMB(M_VAR2) + 1]) + a.bias_val;
       epi_act_store(tq + 32, Bias + B16(M_AW0), E + E_HDA, m, 4, ACT_ELU);
     }
     STAGE_BEGIN()
@@ -408,8 +410,9 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       float visibility = 0.f, hp = 0.f;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        float cdf0 = 0.5f + 0.5f * tanhf((nearp - mean[j]) * var[j]);
-        float cdf1 = 0.5f + 0.5f * tanhf((farp - mean[j]) * var[j]);
+        // 0.5 + 0.5 tanh(x) == sigmoid(2x): one ex2 + one rcp (~3e-7 relative) instead of two libm tanhf
+        float cdf0 = sigmoidf(2.f * ((nearp - mean[j]) * var[j]));
+        float cdf1 = sigmoidf(2.f * ((farp - mean[j]) * var[j]));
         if (a.use_vis) { cdf0 *= visd; cdf1 *= visd; }
         visibility += (1.f - cdf0) * mix[j];
         hp += (cdf1 - cdf0) * mix[j];
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
         float den = 0.f, r = 0.f, gg = 0.f, b = 0.f;
 #pragma unroll
         for (int vv = 0; vv < V; ++vv) {
-            const float e = expf(SF[SF_LOGIT * ROWS + vv * T + m] - mx);
+            const float e = fast_exp(SF[SF_LOGIT * ROWS + vv * T + m] - mx);
             den += e;
             r += SF[SF_R * ROWS + vv * T + m] * e; gg += SF[SF_G * ROWS + vv * T + m] * e; b += SF[SF_B * ROWS + vv * T + m] * e;
         }
