@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
 
   __shared__ int s_tile[kWG];
   int static_tile = blockIdx.x * kWG + wg;
+  // per-thread constants of the whole launch (the view of a row never changes: v = m / T)
+  const float inv_wm1 = 1.f / (float)(a.img_w - 1), inv_hm1 = 1.f / (float)(a.img_h - 1);
+  const float q_nn = -1.f / a.que_near, q_inv = 1.f / (-1.f / a.que_far - q_nn);
+  const float r_nn = -1.f / __ldg(a.ref_depth_range + 2 * v), r_inv = 1.f / (-1.f / __ldg(a.ref_depth_range + 2 * v + 1) - r_nn);
 #pragma unroll 1
   while (true) {
     // dynamic tile scheduler (one atomic per 128-row tile) when the caller provides a counter, else static striding
@@ -278,12 +282,12 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     const int ray = (int)(g / a.dn), s = (int)(g % a.dn);
 
     // ------------------------------------------------------------ geometry (thread = row)
-    const RowGeom rg = row_geometry(a, v, g);
+    const RowGeom rg = row_geometry<true>(a, v, g);
     {
-      Footprint f = border_footprint(rg.px, rg.py, a.img_h, a.img_w, a.rf_h, a.rf_w);
+      Footprint f = border_footprint_r(rg.px, rg.py, inv_wm1, inv_hm1, a.rf_h == a.img_h && a.rf_w == a.img_w, a.rf_h, a.rf_w);
       FootRec r1; r1.off = v * a.rf_h * a.rf_w + f.off; r1.dxy = f.dx | (f.dy << 1); r1.tx = f.tx; r1.ty = f.ty;
       FP[m] = r1;
-      f = border_footprint(rg.px, rg.py, a.img_h, a.img_w, a.if_h, a.if_w);
+      f = border_footprint_r(rg.px, rg.py, inv_wm1, inv_hm1, a.if_h == a.img_h && a.if_w == a.img_w, a.if_h, a.if_w);
       r1.off = v * a.if_h * a.if_w + f.off; r1.dxy = f.dx | (f.dy << 1); r1.tx = f.tx; r1.ty = f.ty;
       FP[ROWS + m] = r1;
     }
@@ -300,20 +304,20 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // own-row colour taps (fp32, kept in registers for the final blend)
     float rgb_in[3];
     {
-      const Footprint f = border_footprint(rg.px, rg.py, a.img_h, a.img_w, a.img_h, a.img_w);
+      const Footprint f = border_footprint_r(rg.px, rg.py, inv_wm1, inv_hm1, true, a.img_h, a.img_w);
       const float4 c = tap4(reinterpret_cast<const float4*>(a.imgs_cl) + (size_t)v * a.img_h * a.img_w + f.off, f, 1, a.img_w);
       rgb_in[0] = c.x; rgb_in[1] = c.y; rgb_in[2] = c.z;
     }
     // sampling interval of this sample along its ray (depth2inv_dists) and the view's normalised depth
     float d_prev, d_s, dv;
     {
+      // normalised inverse depth (-1/d - nn) / (ff - nn) with the range constants hoisted and one MUFU.RCP per depth
       const float* dp = a.depth + (size_t)ray * a.depth_ray_stride;
-      const float i_s = inv_norm(__ldg(dp + s), a.que_near, a.que_far);
-      d_s = (s + 1 < a.dn) ? inv_norm(__ldg(dp + s + 1), a.que_near, a.que_far) - i_s : 1e6f;
+      const float i_s = (-fast_rcp(__ldg(dp + s)) - q_nn) * q_inv;
+      d_s = (s + 1 < a.dn) ? (-fast_rcp(__ldg(dp + s + 1)) - q_nn) * q_inv - i_s : 1e6f;
       d_prev = d_s;
-      if (s > 0) d_prev = i_s - inv_norm(__ldg(dp + s - 1), a.que_near, a.que_far);
-      const float rnear = __ldg(a.ref_depth_range + 2 * v), rfar = __ldg(a.ref_depth_range + 2 * v + 1);
-      dv = inv_norm(fmaxf(rg.pdepth, 1e-5f), rnear, rfar);
+      if (s > 0) d_prev = i_s - (-fast_rcp(__ldg(dp + s - 1)) - q_nn) * q_inv;
+      dv = (-fast_rcp(fmaxf(rg.pdepth, 1e-5f)) - r_nn) * r_inv;
     }
     wg_sync(wg);
 

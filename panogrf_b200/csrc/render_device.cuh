@@ -340,6 +340,32 @@ __device__ __forceinline__ Footprint border_footprint(float px, float py, int h,
   return f;
 }
 
+// same footprint with the two divisions by (w-1), (h-1) replaced by multiplications with reciprocals the caller hoisted
+// (bf16 path only: positions differ from the reference's by ~1 ulp)
+__device__ __forceinline__ Footprint border_footprint_r(float px, float py, float inv_wm1, float inv_hm1, bool align, int fh, int fw) {
+  const float xn = px * inv_wm1 * 2.f - 1.f;
+  const float yn = py * inv_hm1 * 2.f - 1.f;
+  float ix, iy;
+  if (align) {
+    ix = ((xn + 1.f) * 0.5f) * (float)(fw - 1);
+    iy = ((yn + 1.f) * 0.5f) * (float)(fh - 1);
+  } else {
+    ix = ((xn + 1.f) * (float)fw - 1.f) * 0.5f;
+    iy = ((yn + 1.f) * (float)fh - 1.f) * 0.5f;
+  }
+  ix = fminf(fmaxf(ix, 0.f), (float)(fw - 1));
+  iy = fminf(fmaxf(iy, 0.f), (float)(fh - 1));
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  Footprint f;
+  const int xi = (int)x0, yi = (int)y0;
+  f.tx = ix - x0;
+  f.ty = iy - y0;
+  f.dx = (xi + 1 < fw) ? 1 : 0;
+  f.dy = (yi + 1 < fh) ? 1 : 0;
+  f.off = yi * fw + xi;
+  return f;
+}
+
 // ---- shared by the fp32 and the bf16 render kernels ----
 __device__ __forceinline__ float4 tap4(const float4* __restrict__ base, const Footprint& f, int stride_x, int stride_y) {
   // ATen order: nw, ne, sw, se
@@ -364,6 +390,7 @@ struct RowGeom {
   float dir[3];
   float dirdiff[4];
 };
+template <bool FAST = false>   // FAST (bf16 path): the two normalisations use rsqrt.approx instead of sqrt + 3 IEEE divisions each
 __device__ __forceinline__ RowGeom row_geometry(const pgrf_render_args& a, int v, long long g) {
   const int ray = (int)(g / a.dn), s = (int)(g % a.dn);
   const float cx = __ldg(a.coords + 2 * (size_t)ray), cy = __ldg(a.coords + 2 * (size_t)ray + 1);
@@ -376,8 +403,14 @@ __device__ __forceinline__ RowGeom row_geometry(const pgrf_render_args& a, int v
   const float rdy = c[4] * dx + c[5] * dy + c[6] * dz;
   const float rdz = c[8] * dx + c[9] * dy + c[10] * dz;
   const float p0 = c[3] + rdx * depth, p1 = c[7] + rdy * depth, p2 = c[11] + rdz * depth;
-  const float rn = sqrtf(rdx * rdx + rdy * rdy + rdz * rdz);
-  const float q0 = -rdx / rn, q1 = -rdy / rn, q2 = -rdz / rn;   // que_dir
+  float q0, q1, q2;   // que_dir
+  if (FAST) {
+    const float ir = rsqrtf(rdx * rdx + rdy * rdy + rdz * rdz);
+    q0 = -rdx * ir; q1 = -rdy * ir; q2 = -rdz * ir;
+  } else {
+    const float rn = sqrtf(rdx * rdx + rdy * rdy + rdz * rdz);
+    q0 = -rdx / rn; q1 = -rdy / rn; q2 = -rdz / rn;
+  }
   const float* w = a.ref_w2c + 12 * v;
   const float pc0 = w[0] * p0 + w[1] * p1 + w[2] * p2 + w[3];
   const float pc1 = w[4] * p0 + w[5] * p1 + w[6] * p2 + w[7];
@@ -389,8 +422,13 @@ __device__ __forceinline__ RowGeom row_geometry(const pgrf_render_args& a, int v
   const float cam1 = -(w[1] * w[3] + w[5] * w[7] + w[9] * w[11]);
   const float cam2 = -(w[2] * w[3] + w[6] * w[7] + w[10] * w[11]);
   const float e0 = p0 - cam0, e1 = p1 - cam1, e2 = p2 - cam2;
-  const float en = fmaxf(sqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e-5f);
-  r.dir[0] = -e0 / en; r.dir[1] = -e1 / en; r.dir[2] = -e2 / en;
+  if (FAST) {
+    const float ie = fminf(rsqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e5f);     // == 1 / max(|e|, 1e-5)
+    r.dir[0] = -e0 * ie; r.dir[1] = -e1 * ie; r.dir[2] = -e2 * ie;
+  } else {
+    const float en = fmaxf(sqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e-5f);
+    r.dir[0] = -e0 / en; r.dir[1] = -e1 / en; r.dir[2] = -e2 / en;
+  }
   r.dirdiff[0] = r.dir[0] - q0; r.dirdiff[1] = r.dir[1] - q1; r.dirdiff[2] = r.dir[2] - q2;
   r.dirdiff[3] = r.dir[0] * q0 + r.dir[1] * q1 + r.dir[2] * q2;
   return r;

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rows_kernel(const RenderPa
           r.dirdiff[0] = r.dir[0] - q0; r.dirdiff[1] = r.dir[1] - q1; r.dirdiff[2] = r.dir[2] - q2;
           r.dirdiff[3] = r.dir[0] * q0 + r.dir[1] * q1 + r.dir[2] * q2;
         } else {
-          r = row_geometry(a, v, g);
+          r = row_geometry<false>(a, v, g);
         }
         SC[SC_PX * LD + m] = r.px; SC[SC_PY * LD + m] = r.py; SC[SC_PDEPTH * LD + m] = r.pdepth;
 #pragma unroll
