@@ -225,14 +225,20 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // -------------------------------------------------------------------------------------------------
 
 // pixel (x,y) -> unit direction in the camera frame (ray_utils.py:4-16, spt_utils.py:37-127)
+template <bool FAST = false>   // FAST (bf16 path, m3d convention): reciprocal multiplies, __sincosf, rsqrt normalisation
 __device__ __forceinline__ void equi_unit_dir(int dataset, float x, float y, int H, int W, float& dx, float& dy, float& dz) {
   const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
   float theta, phi;
   switch (dataset) {
     case PGRF_DS_M3D:
       x = fminf(fmaxf(x, 0.f), wm1); y = fminf(fmaxf(y, 0.f), hm1);
-      theta = x / wm1 * 2.f * PGRF_PI_F - PGRF_HALF_PI_F;
-      phi = y / hm1 * PGRF_PI_F;
+      if (FAST) {
+        theta = x * (2.f * PGRF_PI_F / wm1) - PGRF_HALF_PI_F;
+        phi = y * (PGRF_PI_F / hm1);
+      } else {
+        theta = x / wm1 * 2.f * PGRF_PI_F - PGRF_HALF_PI_F;
+        phi = y / hm1 * PGRF_PI_F;
+      }
       break;
     case PGRF_DS_REPLICA_TEST:
       theta = x * 2.f * PGRF_PI_F / wm1 - PGRF_PI_F;
@@ -250,16 +256,26 @@ __device__ __forceinline__ void equi_unit_dir(int dataset, float x, float y, int
       break;
   }
   float st, ct, sp, cp;
-  sincosf(theta, &st, &ct);
-  sincosf(phi, &sp, &cp);
+  if (FAST && dataset == PGRF_DS_M3D) {   // |theta| <= 3pi/2, phi in [0, pi]: MUFU sin/cos, ~1e-6 absolute
+    __sincosf(theta, &st, &ct);
+    __sincosf(phi, &sp, &cp);
+  } else {
+    sincosf(theta, &st, &ct);
+    sincosf(phi, &sp, &cp);
+  }
   switch (dataset) {
     case PGRF_DS_M3D:          dx = sp * ct; dy = cp;  dz = sp * st; break;
     case PGRF_DS_REPLICA_TEST: dx = st * cp; dy = -sp; dz = ct * cp; break;
     case PGRF_DS_RESIDENTIAL:  dx = ct * cp; dy = sp;  dz = st * cp; break;
     default:                   dx = sp * ct; dy = sp * st; dz = cp;  break;
   }
-  const float n = sqrtf(dx * dx + dy * dy + dz * dz);
-  dx /= n; dy /= n; dz /= n;
+  if (FAST) {
+    const float in = rsqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= in; dy *= in; dz *= in;
+  } else {
+    const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx /= n; dy /= n; dz /= n;
+  }
 }
 
 // torch.remainder(a, b) for b > 0
@@ -270,12 +286,21 @@ __device__ __forceinline__ float py_mod(float a, float b) {
 }
 
 // camera-frame point -> (radius, pixel x, pixel y) (ray_utils.py:18-22, spt_utils.py:129-199)
+template <bool FAST = false>   // FAST (bf16 path, m3d convention): one MUFU.RCP, wrap by a compare, constant scales as multiplies
 __device__ __forceinline__ void cam_to_equi(int dataset, float cx, float cy, float cz, int H, int W, float& radius, float& px, float& py) {
   const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
   radius = sqrtf(cx * cx + cy * cy + cz * cz);
   switch (dataset) {
     case PGRF_DS_M3D: {
       float theta = atan2f(cz, cx);
+      if (FAST) {
+        const float phi = acosf(cy * fast_rcp(radius + 1e-5f));
+        theta += PGRF_HALF_PI_F;                       // in (-pi/2, 3pi/2]: python's % 2pi is one conditional add
+        if (theta < 0.f) theta += PGRF_TWO_PI_F;
+        px = theta * (wm1 / PGRF_TWO_PI_F);
+        py = phi * (hm1 / PGRF_PI_F);
+        break;
+      }
       const float phi = acosf(cy / (radius + 1e-5f));
       theta = py_mod(theta + PGRF_HALF_PI_F, PGRF_TWO_PI_F);
       px = theta / PGRF_TWO_PI_F * wm1;
@@ -397,7 +422,7 @@ __device__ __forceinline__ RowGeom row_geometry(const pgrf_render_args& a, int v
   const float depth = __ldg(a.depth + (size_t)ray * a.depth_ray_stride + s);
   float dx, dy, dz;
   // `.long()` truncation of the pixel coordinate (render_ops.py:96-97)
-  equi_unit_dir(a.dataset, (float)(long long)cx, (float)(long long)cy, a.H, a.W, dx, dy, dz);
+  equi_unit_dir<FAST>(a.dataset, (float)(long long)cx, (float)(long long)cy, a.H, a.W, dx, dy, dz);
   const float* c = a.que_c2w;  // (3,4) row-major
   const float rdx = c[0] * dx + c[1] * dy + c[2] * dz;
   const float rdy = c[4] * dx + c[5] * dy + c[6] * dz;
@@ -416,7 +441,7 @@ __device__ __forceinline__ RowGeom row_geometry(const pgrf_render_args& a, int v
   const float pc1 = w[4] * p0 + w[5] * p1 + w[6] * p2 + w[7];
   const float pc2 = w[8] * p0 + w[9] * p1 + w[10] * p2 + w[11];
   RowGeom r;
-  cam_to_equi(a.dataset, pc0, pc1, pc2, a.H, a.W, r.pdepth, r.px, r.py);
+  cam_to_equi<FAST>(a.dataset, pc0, pc1, pc2, a.H, a.W, r.pdepth, r.px, r.py);
   // camera centre -R^T t (render_ops.py:204), direction from the point to the source camera
   const float cam0 = -(w[0] * w[3] + w[4] * w[7] + w[8] * w[11]);
   const float cam1 = -(w[1] * w[3] + w[5] * w[7] + w[9] * w[11]);
