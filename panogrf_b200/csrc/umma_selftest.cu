@@ -33,6 +33,40 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tbase = tmem_base;
+  if (swap_lbo_sbo >= 4) {
+    // diagnostic: ONE M = 64 MMA on rows 0..63, accumulator at lane offset (variant - 4) * 16; dump every lane.
+    // Measured on B200 (tools/umma_m64_probe.py): rows 16q..16q+15 land in lanes 32q + (offset & 16) + 0..15 — every warp's lane
+    // quadrant holds 16 rows, so two M = 64 MMAs interleave INSIDE each warp and cannot serve as two independent pipelines.
+    if (tid < 128) {   // clear the accumulator columns first (zeros via tcgen05.st)
+      uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < N; c += 8) umma::st8(tbase + ((uint32_t)(warp * 32) << 16) + c, z);
+      umma::wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (tid == 0) {
+      const uint32_t idesc = umma::instr_desc_bf16(64, N);
+      for (int k = 0; k < K; k += 16) {
+        const uint64_t ad = umma::smem_desc(umma::smem_addr(As) + (k >> 3) * 128 * 16, 128 * 16, 128);
+        const uint64_t bd = umma::smem_desc(umma::smem_addr(Ws) + (k >> 3) * N * 16, N * 16, 128);
+        umma::mma_bf16(tbase + ((uint32_t)((swap_lbo_sbo - 4) * 16) << 16), ad, bd, idesc, k > 0);
+      }
+      umma::commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    const uint32_t lb = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int n0 = 0; n0 < N; n0 += 16) {
+      float v[16];
+      umma::ld16(lb + n0, v);
+      for (int i = 0; i < 16; ++i) out[(size_t)tid * N + n0 + i] = v[i];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, 256);
+    return;
+  }
   if (swap_lbo_sbo == 2) {
     // variant 2: A operand in TMEM columns [128, 128 + K/2): every thread writes its own row with tcgen05.st
     const uint32_t a_lane = tbase + ((uint32_t)(warp * 32) << 16) + 128;
