@@ -303,12 +303,24 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
       const float* dp = a.depth + (size_t)ray * a.depth_ray_stride;
       for (int s = lane; s < dn; s += 32) alpha[s] = 1.f - fast_exp(-sigma[s]);
       __syncwarp();
-      if (lane == 0) {  // sequential fp32 cumprod (stated accumulation order)
-        float trans = 1.f;
-        for (int s = 0; s < dn; ++s) {
-          hit[s] = alpha[s] * trans;
-          trans = trans * (1.f - alpha[s] + 1e-10f);
+      {   // transmittance = exclusive prefix product of (1 - alpha + 1e-10): warp scan over contiguous per-lane segments
+          // (the fp32 parity path keeps the sequential order; here only the association of the products differs)
+        const int epl = (dn + 31) >> 5;                    // <= 4 elements per lane
+        const int b0 = lane * epl;
+        float loc[4], p = 1.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          loc[e] = p;
+          if (e < epl && b0 + e < dn) p *= 1.f - alpha[b0 + e] + 1e-10f;
         }
+        float incl = p;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl *= t; }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < epl && b0 + e < dn) hit[b0 + e] = alpha[b0 + e] * (excl * loc[e]);
       }
       __syncwarp();
       float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
@@ -342,15 +354,27 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
           if (inv) { d1 = (-1.f / d1 - nn) / (ff - nn); d0 = (-1.f / d0 - nn) / (ff - nn); }
           center[s] = (s == 0 || s == dn) ? d1 : (d1 + d0) / 2.f;
         }
-        float tot = 0.f;
-        if (lane == 0) for (int s = 0; s < dn; ++s) tot += hit[s] + 1e-5f;     // sequential normaliser
-        tot = __shfl_sync(0xffffffffu, tot, 0);
-        for (int s = lane; s < dn; s += 32) cdf[s + 1] = (hit[s] + 1e-5f) / tot; // pdf, in parallel (IEEE division)
-        __syncwarp();
-        if (lane == 0) {                                                         // sequential cumsum
-          float c = 0.f;
-          cdf[0] = 0.f;
-          for (int s = 0; s < dn; ++s) { c += cdf[s + 1]; cdf[s + 1] = c; }
+        {   // pdf = (hit + 1e-5) / sum, cdf = inclusive prefix sum: warp reduce + warp scan over per-lane segments
+          const int epl = (dn + 31) >> 5;
+          const int b0 = lane * epl;
+          float w[4], part = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { w[e] = (e < epl && b0 + e < dn) ? hit[b0 + e] + 1e-5f : 0.f; part += w[e]; }
+          float tot = part;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+          const float itot = 1.f / tot;
+          float run = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { w[e] *= itot; run += w[e]; w[e] = run; }   // inclusive inside the lane
+          float incl = run;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+          float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+          if (lane == 0) { excl = 0.f; cdf[0] = 0.f; }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e < epl && b0 + e < dn) cdf[b0 + e + 1] = excl + w[e];
         }
         __syncwarp();
         const int fdn = a.fine_dn;
@@ -375,6 +399,12 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
           total_out = fdn + dn;
         }
         __syncwarp();
+        bool sorted = !a.fine_use_all;                 // inverse-CDF samples of increasing u are almost always already ordered
+        if (sorted)
+          for (int k = lane; k + 1 < total_out; k += 32) sorted = sorted && (fine[k] <= fine[k + 1]);
+        if (__all_sync(0xffffffffu, sorted)) {
+          for (int k = lane; k < total_out; k += 32) a.fine_depth[(size_t)ray * total_out + k] = fine[k];
+        } else
         for (int k = lane; k < total_out; k += 32) {   // rank sort (value-only result == torch.sort)
           const float x = fine[k];
           int rank = 0;
