@@ -91,6 +91,18 @@ static __device__ __noinline__ void epi_act_store(uint32_t taddr, const float* _
     for (int i = 0; i < 4; ++i) bb[i] = reinterpret_cast<const float4*>(bias + 8 * c)[i];
     float v[16];
     umma::ld16(taddr + 8 * c, v);
+    if (act == ACT_ELU) {
+      uint32_t q[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b = bb[i];
+        q[2 * i] = elu_pack(fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y)));
+        q[2 * i + 1] = elu_pack(fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w)));
+      }
+      *reinterpret_cast<uint4*>(dst + ((size_t)c * ROWS + m) * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+      *reinterpret_cast<uint4*>(dst + ((size_t)(c + 1) * ROWS + m) * 16) = make_uint4(q[4], q[5], q[6], q[7]);
+      continue;
+    }
     act_pairs(v, bb, act);
     umma::store_chunk(dst, ROWS, c, m, v);
     umma::store_chunk(dst, ROWS, c + 1, m, v + 8);

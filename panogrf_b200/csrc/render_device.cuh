@@ -2,6 +2,7 @@
 // for every Linear layer of the fp32 parity path, TMA (cp.async.bulk) helpers, and the ERP geometry
 // of the renderer (network/spt_utils.py, network/render_ops.py).
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "render_layout.cuh"
 
@@ -55,6 +56,15 @@ __device__ __forceinline__ float2 elu_pair(float2 v) {
   const float2 t = fmul2(v, make_float2(1.4426950408889634f, 1.4426950408889634f));
   const float2 r = fadd2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(-1.f, -1.f));
   return make_float2(v.x > 0.f ? v.x : r.x, v.y > 0.f ? v.y : r.y);
+}
+// bf16x2 ELU of a biased fp32 pair: the select runs on the PACKED values (max(v, min(exp(v)-1, 0)) with HMNMX2); rounding is
+// monotonic and sign preserving, so this equals rounding the fp32 ELU
+__device__ __forceinline__ uint32_t elu_pack(float2 v) {
+  const float2 t = fmul2(v, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 r = fadd2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(-1.f, -1.f));
+  const __nv_bfloat162 V = __floats2bfloat162_rn(v.x, v.y), R = __floats2bfloat162_rn(r.x, r.y);
+  const __nv_bfloat162 o = __hmax2(V, __hmin2(R, __floats2bfloat162_rn(0.f, 0.f)));
+  return *reinterpret_cast<const uint32_t*>(&o);
 }
 __device__ __forceinline__ float elu1(float x) { return fmaxf(x, 0.f) + fminf(fast_exp(x) - 1.f, 0.f); }
 __device__ __forceinline__ float sigmoidf(float x) { return fast_rcp(1.f + fast_exp(-x)); }

@@ -57,13 +57,11 @@ static __device__ __noinline__ void epi_elu_store(uint32_t taddr, const float* _
   for (int c = 0; c < nchunks; c += 2) {
     float v[16];
     umma::ld16(taddr + 8 * c, v);
+    uint32_t q[8];
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      const float2 r = elu_pair(fadd2(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2*>(bias + 8 * c + i)));
-      v[i] = r.x; v[i + 1] = r.y;
-    }
-    umma::store_chunk(dst, RROWS, c, m, v);
-    umma::store_chunk(dst, RROWS, c + 1, m, v + 8);
+    for (int i = 0; i < 16; i += 2) q[i >> 1] = elu_pack(fadd2(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2*>(bias + 8 * c + i)));
+    *reinterpret_cast<uint4*>(dst + ((size_t)c * RROWS + m) * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<uint4*>(dst + ((size_t)(c + 1) * RROWS + m) * 16) = make_uint4(q[4], q[5], q[6], q[7]);
   }
 }
 
