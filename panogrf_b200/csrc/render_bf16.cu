@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     long long g = (long long)tile * T + t;
     const bool row_valid = (m < M) && (g < p.total);
     if (g >= p.total) g = p.total - 1;
-    const int ray = (int)(g / a.dn), s = (int)(g % a.dn);
+    const int ray = (int)((unsigned)g / (unsigned)a.dn), s = (int)((unsigned)g - (unsigned)ray * (unsigned)a.dn);   // total < 2^31
 
     // ------------------------------------------------------------ geometry (thread = row)
     const RowGeom rg = row_geometry<true>(a, v, g);
@@ -632,6 +632,7 @@ namespace pgrf {
 static_assert(SM16_BYTES + 1024 <= 227 * 1024, "fused MLP kernel shared memory");
 int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long total, int n_tiles, int sms, cudaStream_t st) {
   PGRF_REQUIRE(a.weights16 != nullptr, "render: bf16 path needs weights16");
+  PGRF_REQUIRE(total < (1ll << 31), "render: rn * dn = %lld samples per launch exceed 2^31 (lower rays_per_launch)", total);
   PGRF_REQUIRE(((uintptr_t)a.weights16 & 15) == 0, "render: weights16 must be 16-byte aligned");
   Render16Params p;
   p.a = a; p.V = V; p.T = T; p.M = V * T; p.total = total; p.n_tiles = n_tiles;

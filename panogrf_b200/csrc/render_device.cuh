@@ -427,7 +427,12 @@ struct RowGeom {
 };
 template <bool FAST = false>   // FAST (bf16 path): the two normalisations use rsqrt.approx instead of sqrt + 3 IEEE divisions each
 __device__ __forceinline__ RowGeom row_geometry(const pgrf_render_args& a, int v, long long g) {
-  const int ray = (int)(g / a.dn), s = (int)(g % a.dn);
+  int ray, s;
+  if (FAST) {   // bf16 path: sample indices of one launch fit 32 bits (checked by the launcher): no 64-bit division
+    ray = (int)((unsigned)g / (unsigned)a.dn); s = (int)((unsigned)g - (unsigned)ray * (unsigned)a.dn);
+  } else {
+    ray = (int)(g / a.dn); s = (int)(g % a.dn);
+  }
   const float cx = __ldg(a.coords + 2 * (size_t)ray), cy = __ldg(a.coords + 2 * (size_t)ray + 1);
   const float depth = __ldg(a.depth + (size_t)ray * a.depth_ray_stride + s);
   float dx, dy, dz;

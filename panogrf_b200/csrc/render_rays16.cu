@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
     const long long g0 = (long long)tile * Mv;
     long long g = g0 + min(m, Mv - 1);
     if (g >= p.total) g = p.total - 1;
-    const int sidx = (int)(g % dn);                       // sample index inside its ray
+    const int sidx = (int)((unsigned)g % (unsigned)dn);    // sample index inside its ray (total < 2^31, checked by the MLP launcher)
     // ---- pooled features of this sample (F2 tile [kF2][T]) -> A operand (bf16), colours -> smem
     {
       const float* f2 = a.f2 + (size_t)(g >> p.log2T) * kF2 * T + (g & (T - 1));
