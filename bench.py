@@ -288,7 +288,7 @@ def main():
         }
         line.update(kern.get("roofline_objects", {}))
         line["kernels"] = kern.get("kernels")
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # the CPU baseline is an N=1 measurement (rank 0, all host cores)
             v, t = oracle_rays_per_s(8192)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"8192 random rays of the view, oracle/render.py torch-CPU fp32, {t:.1f} s"}
