@@ -296,6 +296,16 @@ PGRF_API int pgrf_interpolate_feature_map_fwd(const float* feats, int rfn, int C
 PGRF_API int pgrf_depth2points_fwd(const float* coords, const float* depth, int depth_ray_stride, const float* c2w, int dataset,
                                    int H, int W, long long rn, int dn, float* pts, float* dir, void* stream);
 
+/* Backward of pgrf_composite_fwd (the reference: autograd through cumprod / exp): upstream gradients g_hit_prob (rn,dn),
+ * g_pixel_colors (rn,3), g_render_depth (rn) (each optional) -> grad w.r.t. density (or alpha, whichever was the input) (rn,dn)
+ * and colors (rn,dn,3; optional) */
+PGRF_API int pgrf_composite_bwd(const float* density, const float* alpha, const float* colors, const float* depth, int depth_ray_stride,
+                                int rn, int dn, const float* g_hit_prob, const float* g_pixel_colors, const float* g_render_depth,
+                                float* grad_density_or_alpha, float* grad_colors, void* stream);
+/* Backward of pgrf_interpolate_feature_map_fwd w.r.t. the map: grad_feats (rfn,C,fh,fw) is ACCUMULATED into (zero it first) */
+PGRF_API int pgrf_interpolate_feature_map_bwd(const float* grad_out, int rfn, int C, int fh, int fw, const float* pix, long long pn,
+                                              int h, int w, float* grad_feats, void* stream);
+
 /* Weight blob layout: one entry per (slice of a) Linear layer of [fine_]dist_decoder / [fine_]agg_net.
  * name uses "{dd}" / "{agg}" placeholders; the weight slice [N, k_begin:k_begin+K] is stored
  * transposed (k-major) with rows padded to Npad at w_offset, the bias (Npad) at b_offset. */

@@ -127,3 +127,122 @@ extern "C" int pgrf_depth2points_fwd(const float* coords, const float* depth, in
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Backward passes of the two cheap differentiable stages (the reference gets them from autograd):
+//   composite_bwd            — d/d(density|alpha), d/d(colors) of hit_prob / pixel_colors / render_depth
+//   interpolate_feature_map_bwd — d/d(feats) of the bilinear border gather (scatter-add of the 4 tap weights)
+// ------------------------------------------------------------------------------------------------
+namespace pgrf {
+
+// one warp per ray.  h_s = a_s T_s, T_s = prod_{j<s} x_j, x_j = 1 - a_j + 1e-10:
+//   dL/da_s = G_s T_s - (sum_{k>s} G_k h_k) / x_s,   G_s = g_hit[s] + <g_pix, c_s> + g_depth z_s
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const float* __restrict__ density, const float* __restrict__ alpha_in,
+                                                            const float* __restrict__ colors, const float* __restrict__ depth,
+                                                            int depth_ray_stride, const float* __restrict__ g_hit,
+                                                            const float* __restrict__ g_pix, const float* __restrict__ g_depth,
+                                                            float* __restrict__ grad_in, float* __restrict__ grad_colors, int rn, int dn) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* alpha = sm + warp * 4 * dn;
+  float* trans = alpha + dn;
+  float* gh = trans + dn;      // G_s * h_s, then its exclusive suffix sum
+  float* G = gh + dn;
+  for (long long ray = (long long)blockIdx.x * 8 + warp; ray < rn; ray += (long long)gridDim.x * 8) {
+    for (int s = lane; s < dn; s += 32)
+      alpha[s] = alpha_in ? __ldg(alpha_in + ray * dn + s) : 1.f - expf(-fmaxf(__ldg(density + ray * dn + s), 0.f));
+    __syncwarp();
+    if (lane == 0) {
+      float t = 1.f;
+      for (int s = 0; s < dn; ++s) { trans[s] = t; t = t * (1.f - alpha[s] + 1e-10f); }
+    }
+    __syncwarp();
+    const float gp0 = g_pix ? __ldg(g_pix + ray * 3) : 0.f, gp1 = g_pix ? __ldg(g_pix + ray * 3 + 1) : 0.f,
+                gp2 = g_pix ? __ldg(g_pix + ray * 3 + 2) : 0.f;
+    const float gd = g_depth ? __ldg(g_depth + ray) : 0.f;
+    for (int s = lane; s < dn; s += 32) {
+      float g = g_hit ? __ldg(g_hit + ray * dn + s) : 0.f;
+      const float h = alpha[s] * trans[s];
+      if (colors && g_pix) {
+        const float* c = colors + (ray * dn + s) * 3;
+        g += gp0 * __ldg(c) + gp1 * __ldg(c + 1) + gp2 * __ldg(c + 2);
+        if (grad_colors) {
+          float* gc = grad_colors + (ray * dn + s) * 3;
+          gc[0] = gp0 * h; gc[1] = gp1 * h; gc[2] = gp2 * h;
+        }
+      } else if (grad_colors) {
+        float* gc = grad_colors + (ray * dn + s) * 3;
+        gc[0] = gc[1] = gc[2] = 0.f;
+      }
+      if (depth && g_depth) g += gd * __ldg(depth + ray * depth_ray_stride + s);
+      G[s] = g;
+      gh[s] = g * h;
+    }
+    __syncwarp();
+    if (lane == 0) {   // exclusive suffix sum
+      float acc = 0.f;
+      for (int s = dn - 1; s >= 0; --s) { const float v = gh[s]; gh[s] = acc; acc += v; }
+    }
+    __syncwarp();
+    for (int s = lane; s < dn; s += 32) {
+      const float x = 1.f - alpha[s] + 1e-10f;
+      float ga = G[s] * trans[s] - gh[s] / x;
+      if (!alpha_in) {
+        const float sg = __ldg(density + ray * dn + s);
+        ga = sg > 0.f ? ga * expf(-sg) : 0.f;
+      }
+      grad_in[ray * dn + s] = ga;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) interpolate_bwd_kernel(const float* __restrict__ grad_out, int rfn, int C, int fh, int fw,
+                                                              const float* __restrict__ pix, long long pn, int h, int w,
+                                                              float* __restrict__ grad_feats) {
+  const size_t plane = (size_t)fh * fw;
+  const long long total = (long long)rfn * pn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i / pn);
+    const Footprint f = border_footprint(__ldg(pix + 2 * i), __ldg(pix + 2 * i + 1), h, w, fh, fw);
+    const float tx1 = 1.f - f.tx, ty1 = 1.f - f.ty;
+    const float wnw = tx1 * ty1, wne = f.tx * ty1, wsw = tx1 * f.ty, wse = f.tx * f.ty;
+    float* base = grad_feats + (size_t)v * C * plane + f.off;
+    for (int c = 0; c < C; ++c) {
+      const float g = __ldg(grad_out + (size_t)i * C + c);
+      float* m = base + c * plane;
+      atomicAdd(m, g * wnw);
+      if (f.dx) atomicAdd(m + 1, g * wne);
+      if (f.dy) atomicAdd(m + fw, g * wsw);
+      if (f.dx && f.dy) atomicAdd(m + fw + 1, g * wse);
+    }
+  }
+}
+
+}  // namespace pgrf
+
+extern "C" int pgrf_composite_bwd(const float* density, const float* alpha, const float* colors, const float* depth, int depth_ray_stride,
+                                  int rn, int dn, const float* g_hit_prob, const float* g_pixel_colors, const float* g_render_depth,
+                                  float* grad_density_or_alpha, float* grad_colors, void* stream) {
+  PGRF_REQUIRE((density != nullptr) != (alpha != nullptr), "composite_bwd: pass exactly one of density / alpha");
+  PGRF_REQUIRE(grad_density_or_alpha != nullptr, "composite_bwd: null pointer argument");
+  PGRF_REQUIRE(rn >= 1 && dn >= 1 && dn <= 1024, "composite_bwd: rn=%d dn=%d", rn, dn);
+  const int grid = (rn + 7) / 8 < 148 * 8 ? (rn + 7) / 8 : 148 * 8;
+  const size_t smem = 8 * 4 * (size_t)dn * sizeof(float);
+  if (smem > 48 * 1024) PGRF_CUDA(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  composite_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(density, alpha, colors, depth, depth_ray_stride, g_hit_prob, g_pixel_colors,
+                                                                g_render_depth, grad_density_or_alpha, grad_colors, rn, dn);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_interpolate_feature_map_bwd(const float* grad_out, int rfn, int C, int fh, int fw, const float* pix, long long pn, int h,
+                                                int w, float* grad_feats, void* stream) {
+  PGRF_REQUIRE(grad_out && pix && grad_feats, "interpolate_feature_map_bwd: null pointer argument");
+  PGRF_REQUIRE(rfn >= 1 && C >= 1 && fh >= 1 && fw >= 1 && pn >= 1 && h >= 2 && w >= 2, "interpolate_feature_map_bwd: bad sizes");
+  interpolate_bwd_kernel<<<grid_for((long long)rfn * pn), 256, 0, (cudaStream_t)stream>>>(grad_out, rfn, C, fh, fw, pix, pn, h, w, grad_feats);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}

@@ -45,34 +45,66 @@ def depth2inv_dists(depth, depth_range):
     return torch.cat([inv[..., 1:] - inv[..., :-1], torch.full_like(inv[..., :1], 1e6)], -1)
 
 
+class _CompositeFn(torch.autograd.Function):
+    """pgrf_composite_fwd / pgrf_composite_bwd.  `x` is the density (from_density) or the alpha values; colors / depth may be
+    None.  Gradients flow to x and colors (the sample depths carry none on this path)."""
+
+    @staticmethod
+    def forward(ctx, x, colors, depth, from_density):
+        lib = _lib.load()
+        rn, dn = x.shape
+        hit = torch.empty_like(x)
+        pix = torch.empty(rn, 3, device=x.device) if colors is not None else None
+        rd = torch.empty(rn, device=x.device) if depth is not None else None
+        with torch.cuda.device(x.device):
+            rc = lib.pgrf_composite_fwd(_lib.ptr(x) if from_density else None, None if from_density else _lib.ptr(x), _lib.ptr(colors),
+                                        _lib.ptr(depth), dn if depth is not None else 0, rn, dn, _lib.ptr(hit), _lib.ptr(pix),
+                                        _lib.ptr(rd), _lib.stream_ptr())
+        _lib.check(rc, "pgrf_composite_fwd")
+        ctx.from_density = from_density
+        ctx.has = (colors is not None, depth is not None)
+        ctx.save_for_backward(x, colors if colors is not None else x.new_empty(0), depth if depth is not None else x.new_empty(0))
+        outs = [hit]
+        outs.append(pix if pix is not None else x.new_empty(0))
+        outs.append(rd if rd is not None else x.new_empty(0))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_hit, g_pix, g_rd):
+        lib = _lib.load()
+        x, colors, depth = ctx.saved_tensors
+        has_c, has_d = ctx.has
+        rn, dn = x.shape
+        gx = torch.empty_like(x)
+        gc = torch.empty_like(colors) if has_c else None
+        f = lambda t: None if t is None else t.contiguous().float()
+        g_hit, g_pix, g_rd = f(g_hit), f(g_pix) if has_c else None, f(g_rd) if has_d else None
+        with torch.cuda.device(x.device):
+            rc = lib.pgrf_composite_bwd(_lib.ptr(x) if ctx.from_density else None, None if ctx.from_density else _lib.ptr(x),
+                                        _lib.ptr(colors) if has_c else None, _lib.ptr(depth) if has_d else None, dn if has_d else 0,
+                                        rn, dn, _lib.ptr(g_hit), _lib.ptr(g_pix), _lib.ptr(g_rd), _lib.ptr(gx), _lib.ptr(gc),
+                                        _lib.stream_ptr())
+        _lib.check(rc, "pgrf_composite_bwd")
+        return gx, gc, None, None
+
+
 def alpha_values2hit_prob(alpha_values):
-    """render_ops.py:145-153: (...,dn) -> (...,dn); sequential fp32 cumprod (the stated accumulation order)."""
+    """render_ops.py:145-153: (...,dn) -> (...,dn); sequential fp32 cumprod (the stated accumulation order); differentiable."""
     _lib.require_cuda(alpha_values)
-    lib = _lib.load()
     shape = alpha_values.shape
     a = _f32(alpha_values).reshape(-1, shape[-1])
-    out = torch.empty_like(a)
-    with torch.cuda.device(a.device):
-        rc = lib.pgrf_composite_fwd(None, _lib.ptr(a), None, None, 0, a.shape[0], a.shape[1], _lib.ptr(out), None, None,
-                                    _lib.stream_ptr())
-    _lib.check(rc, "pgrf_composite_fwd")
-    return out.reshape(shape)
+    hit, _, _ = _CompositeFn.apply(a, None, None, False)
+    return hit.reshape(shape)
 
 
 def composite(density, colors, depth):
     """network_rendering's tail (renderer.py:214-218) + render_depth (:302-304): density (qn,rn,dn), colors (qn,rn,dn,3),
-    depth (qn,rn,dn) -> hit_prob (qn,rn,dn), pixel_colors (qn,rn,3), render_depth (qn,rn)."""
+    depth (qn,rn,dn) -> hit_prob (qn,rn,dn), pixel_colors (qn,rn,3), render_depth (qn,rn).  Differentiable w.r.t. density and
+    colors (pgrf_composite_bwd)."""
     _lib.require_cuda(density, colors, depth)
-    lib = _lib.load()
     qn, rn, dn = density.shape
-    d, c, z = _f32(density).reshape(-1, dn), _f32(colors).reshape(-1, dn, 3), _f32(depth).reshape(-1, dn)
-    hit = torch.empty_like(d)
-    pix = torch.empty(d.shape[0], 3, device=d.device)
-    rd = torch.empty(d.shape[0], device=d.device)
-    with torch.cuda.device(d.device):
-        rc = lib.pgrf_composite_fwd(_lib.ptr(d), None, _lib.ptr(c), _lib.ptr(z), dn, d.shape[0], dn, _lib.ptr(hit), _lib.ptr(pix),
-                                    _lib.ptr(rd), _lib.stream_ptr())
-    _lib.check(rc, "pgrf_composite_fwd")
+    d, c, z = _f32(density).reshape(-1, dn), _f32(colors).reshape(-1, dn, 3), _f32(depth).detach().reshape(-1, dn)
+    hit, pix, rd = _CompositeFn.apply(d, c, z, True)
     return hit.reshape(qn, rn, dn), pix.reshape(qn, rn, 3), rd.reshape(qn, rn)
 
 
@@ -134,22 +166,45 @@ def project_points_dict(ref_imgs_info, que_pts, spt_utils, with_img_feats=True):
     return {k: v.reshape(rfn, qn, rn, dn, -1) for k, v in out.items()}
 
 
+class _InterpolateFn(torch.autograd.Function):
+    """pgrf_interpolate_feature_map_fwd / _bwd (gradient w.r.t. the map; pixel coordinates carry none on this path)."""
+
+    @staticmethod
+    def forward(ctx, feats, pix, h, w):
+        lib = _lib.load()
+        rfn, f, fh, fw = feats.shape
+        pn = pix.shape[1]
+        out = torch.empty(rfn, pn, f, device=feats.device, dtype=torch.float32)
+        with torch.cuda.device(feats.device):
+            rc = lib.pgrf_interpolate_feature_map_fwd(_lib.ptr(feats), rfn, f, fh, fw, _lib.ptr(pix), pn, h, w, _lib.ptr(out),
+                                                      _lib.stream_ptr())
+        _lib.check(rc, "pgrf_interpolate_feature_map_fwd")
+        ctx.save_for_backward(pix)
+        ctx.meta = (rfn, f, fh, fw, pn, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (pix,) = ctx.saved_tensors
+        rfn, f, fh, fw, pn, h, w = ctx.meta
+        g = g.contiguous().float()
+        gf = torch.zeros(rfn, f, fh, fw, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            rc = lib.pgrf_interpolate_feature_map_bwd(_lib.ptr(g), rfn, f, fh, fw, _lib.ptr(pix), pn, h, w, _lib.ptr(gf), _lib.stream_ptr())
+        _lib.check(rc, "pgrf_interpolate_feature_map_bwd")
+        return gf, None, None, None
+
+
 def interpolate_feature_map(ray_feats, coords, h, w, border_type="border"):
     """render_ops.py:126-143: ray_feats (rfn,f,fh,fw), coords (rfn,pn,2) in (h,w) pixel units -> (rfn,pn,f); bilinear,
-    border padding, align_corners only when the map is at full resolution."""
+    border padding, align_corners only when the map is at full resolution.  Differentiable w.r.t. ray_feats."""
     if border_type != "border":
         raise NotImplementedError("only border padding is used on the render path")
     _lib.require_cuda(ray_feats, coords)
-    lib = _lib.load()
-    rfn, f, fh, fw = ray_feats.shape
+    rfn = ray_feats.shape[0]
     pn = coords.shape[1]
-    feats, pix = _f32(ray_feats), _f32(coords).reshape(rfn, pn, 2)
-    out = torch.empty(rfn, pn, f, device=feats.device, dtype=torch.float32)
-    with torch.cuda.device(feats.device):
-        rc = lib.pgrf_interpolate_feature_map_fwd(_lib.ptr(feats), rfn, f, fh, fw, _lib.ptr(pix), pn, int(h), int(w), _lib.ptr(out),
-                                                  _lib.stream_ptr())
-    _lib.check(rc, "pgrf_interpolate_feature_map_fwd")
-    return out
+    return _InterpolateFn.apply(_f32(ray_feats), _f32(coords).detach().reshape(rfn, pn, 2), int(h), int(w))
 
 
 def depth2points_spherical(que_imgs_info, que_depth, spt_utils):

@@ -86,3 +86,61 @@ def test_depth_hypotheses_bit_exact():
     expect = ocv.mono_guided_hypotheses(mu, ks, 0.5, 0.1, 10.0, 59)
     assert got.shape == (2, 64, 24, 40)
     assert torch.equal(got, expect), "hypothesis values / order differ"
+
+
+# ---- backward passes of the cheap differentiable stages -----------------------------------------------------
+
+def test_composite_backward_matches_torch_autograd():
+    """d/d(density), d/d(colors) of (hit_prob, pixel_colors, render_depth) vs torch autograd on the reference formulas in fp64."""
+    from panogrf_b200 import render_ops as rops
+    gen = torch.Generator().manual_seed(3)
+    qn, rn, dn = 1, 70, 48
+    density = (torch.randn(qn, rn, dn, generator=gen) * 2).requires_grad_(True)        # ~half negative: relu branch
+    colors = torch.rand(qn, rn, dn, 3, generator=gen).requires_grad_(True)
+    depth = torch.sort(torch.rand(qn, rn, dn, generator=gen) * 10 + 0.5, -1)[0]
+    wh, wp, wd = torch.randn(qn, rn, dn, generator=gen), torch.randn(qn, rn, 3, generator=gen), torch.randn(qn, rn, generator=gen)
+
+    def ref(d, c, z):
+        alpha = 1.0 - torch.exp(-torch.relu(d))
+        T = torch.cumprod(torch.cat([torch.ones_like(alpha[..., :1]), 1 - alpha + 1e-10], -1), -1)[..., :-1]
+        hit = alpha * T
+        return hit, (hit[..., None] * c).sum(2), (hit * z).sum(-1)
+
+    d64, c64 = density.detach().double().requires_grad_(True), colors.detach().double().requires_grad_(True)
+    h, p, r = ref(d64, c64, depth.double())
+    ((h * wh).sum() + (p * wp).sum() + (r * wd).sum()).backward()
+    dc, cc = density.detach().cuda().requires_grad_(True), colors.detach().cuda().requires_grad_(True)
+    h2, p2, r2 = rops.composite(dc, cc, depth.cuda())
+    ((h2 * wh.cuda()).sum() + (p2 * wp.cuda()).sum() + (r2 * wd.cuda()).sum()).backward()
+    assert_close(h2, h.float(), rtol=1e-5, atol=1e-6, what="hit")
+    assert_close(dc.grad, d64.grad.float(), rtol=1e-4, atol=1e-5, what="grad density")
+    assert_close(cc.grad, c64.grad.float(), rtol=1e-4, atol=1e-6, what="grad colors")
+    # alpha-input form (alpha_values2hit_prob)
+    a64 = torch.rand(5, 33, generator=gen).double().requires_grad_(True)
+    T = torch.cumprod(torch.cat([torch.ones_like(a64[..., :1]), 1 - a64 + 1e-10], -1), -1)[..., :-1]
+    w = torch.randn(5, 33, generator=gen)
+    ((a64 * T) * w).sum().backward()
+    ac = a64.detach().float().cuda().requires_grad_(True)
+    (rops.alpha_values2hit_prob(ac) * w.cuda()).sum().backward()
+    assert_close(ac.grad, a64.grad.float(), rtol=1e-4, atol=1e-5, what="grad alpha")
+
+
+@pytest.mark.parametrize("scale", [1, 4])
+def test_interpolate_feature_map_backward_matches_torch_autograd(scale):
+    """d/d(feats) of the bilinear border gather vs torch autograd through F.grid_sample (the reference's own op)."""
+    import torch.nn.functional as F
+    from panogrf_b200 import render_ops as rops
+    gen = torch.Generator().manual_seed(5 + scale)
+    rfn, f, h, w, pn = 2, 7, 32, 64, 500
+    feats = torch.randn(rfn, f, h // scale, w // scale, generator=gen)
+    pix = torch.stack([torch.rand(rfn, pn, generator=gen) * (w + 3) - 2, torch.rand(rfn, pn, generator=gen) * (h + 3) - 2], -1)
+    wgt = torch.randn(rfn, pn, f, generator=gen)
+    f64 = feats.double().requires_grad_(True)
+    grid = torch.stack([pix[..., 0] / (w - 1) * 2 - 1, pix[..., 1] / (h - 1) * 2 - 1], -1).unsqueeze(1).double()
+    ref = F.grid_sample(f64, grid, mode="bilinear", padding_mode="border", align_corners=(scale == 1)).squeeze(2).permute(0, 2, 1)
+    (ref * wgt.double()).sum().backward()
+    fc = feats.cuda().requires_grad_(True)
+    out = rops.interpolate_feature_map(fc, pix.cuda(), h, w)
+    (out * wgt.cuda()).sum().backward()
+    assert_close(out, ref.float(), rtol=1e-4, atol=1e-5, what="fwd")
+    assert_close(fc.grad, f64.grad.float(), rtol=1e-4, atol=1e-4, what="grad feats")
