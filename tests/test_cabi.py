@@ -56,3 +56,40 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(PanoGRFError):
         calculate_cost_volume_erp({"dataset_name": "m3d", "contain_dnet": False}, torch.zeros(1, 2, 8, 16, 8),
                                   torch.ones(3), torch.zeros(1, 2, 3), torch.eye(3).expand(1, 2, 3, 3))
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """ctypes mirrors of pgrf_render_args / pgrf_render_view_args / pgrf_diner_args have the size and field offsets the C
+    compiler gives the header's structs (a silent mismatch would shift every pointer after the first wrong field)."""
+    import ctypes
+    import re
+    import shutil
+    import subprocess
+    from panogrf_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "panogrf_b200.h")
+    structs = {"pgrf_render_args": _lib.RenderArgs, "pgrf_render_view_args": _lib.RenderViewArgs, "pgrf_diner_args": _lib.DinerArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{header}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            cfield = "pass" if fname == "pass_" else fname
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {cfield}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c11", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for m in re.finditer(r"(\w+) (\w+) (\d+)", out):
+        cname, fname, val = m.group(1), m.group(2), int(m.group(3))
+        cls = structs[cname]
+        if fname == "size":
+            assert ctypes.sizeof(cls) == val, (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, fname).offset == val, (cname, fname, getattr(cls, fname).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
