@@ -336,6 +336,7 @@ class NeuralRayBaseRenderer(nn.Module):
         self.image_encoder = None    # optional user-supplied encoders (out of scope, see module docstring)
         self.vis_encoder = None
         self._blob_cache = {}
+        self._param_lists = {}
         self._ws = {}
         self._cl_cache = {}
         self._tables = {}
@@ -345,10 +346,23 @@ class NeuralRayBaseRenderer(nn.Module):
             raise _lib.PanoGRFError(f"mlp_dtype must be 'fp32' or 'bf16', got {self.mlp_dtype!r}")
 
     # ---- weights --------------------------------------------------------------------------------
+    def _param_key(self, fine, device):
+        """Cheap identity of the hot-path parameters of one net pair: (storage pointer, in-place version) of every tensor.
+        The parameter LIST is collected once (module traversal costs ~0.25 ms per call, as much as 3 % of a 64-row shard);
+        in-place updates, load_state_dict and .to()/.cuda() are seen through version / pointer; after REPLACING a Parameter
+        object call invalidate_weight_cache()."""
+        lst = self._param_lists.get(fine)
+        if lst is None:
+            pre = ("fine_dist_decoder.", "fine_agg_net.") if fine else ("dist_decoder.", "agg_net.")
+            lst = self._param_lists[fine] = [p for n, p in self.named_parameters() if n.startswith(pre)]
+        return (fine, str(device), tuple((p.data_ptr(), p._version) for p in lst))
+
+    def invalidate_weight_cache(self):
+        self._param_lists.clear()
+        self._blob_cache.clear()
+
     def _blob(self, fine, device):
-        params = [p for n, p in self.named_parameters()
-                  if n.startswith(("fine_dist_decoder.", "fine_agg_net.") if fine else ("dist_decoder.", "agg_net."))]
-        key = (fine, str(device), tuple((p.data_ptr(), p._version) for p in params))
+        key = self._param_key(fine, device)
         hit = self._blob_cache.get(fine)
         if hit is None or hit[0] != key:
             agg = self.fine_agg_net if fine else self.agg_net
@@ -357,9 +371,7 @@ class NeuralRayBaseRenderer(nn.Module):
         return self._blob_cache[fine][1]
 
     def _blob16(self, fine, device):
-        params = [p for n, p in self.named_parameters()
-                  if n.startswith(("fine_dist_decoder.", "fine_agg_net.") if fine else ("dist_decoder.", "agg_net."))]
-        key = (fine, str(device), tuple((p.data_ptr(), p._version) for p in params))
+        key = self._param_key(fine, device)
         hit = self._blob_cache.get(("w16", fine))
         if hit is None or hit[0] != key:
             self._blob_cache[("w16", fine)] = (key, pack_blob16(self.state_dict(), fine, device))
