@@ -337,6 +337,7 @@ class NeuralRayBaseRenderer(nn.Module):
         self.vis_encoder = None
         self._blob_cache = {}
         self._param_lists = {}
+        self._key_memo = None          # per-call memo of _param_key (set by _render_view)
         self._ws = {}
         self._cl_cache = {}
         self._tables = {}
@@ -351,11 +352,17 @@ class NeuralRayBaseRenderer(nn.Module):
         The parameter LIST is collected once (module traversal costs ~0.25 ms per call, as much as 3 % of a 64-row shard);
         in-place updates, load_state_dict and .to()/.cuda() are seen through version / pointer; after REPLACING a Parameter
         object call invalidate_weight_cache()."""
+        memo = self._key_memo
+        if memo is not None and (fine, str(device)) in memo:
+            return memo[(fine, str(device))]
         lst = self._param_lists.get(fine)
         if lst is None:
             pre = ("fine_dist_decoder.", "fine_agg_net.") if fine else ("dist_decoder.", "agg_net.")
             lst = self._param_lists[fine] = [p for n, p in self.named_parameters() if n.startswith(pre)]
-        return (fine, str(device), tuple((p.data_ptr(), p._version) for p in lst))
+        key = (fine, str(device), tuple((p.data_ptr(), p._version) for p in lst))
+        if memo is not None:
+            memo[(fine, str(device))] = key
+        return key
 
     def invalidate_weight_cache(self):
         self._param_lists.clear()
@@ -468,6 +475,14 @@ class NeuralRayBaseRenderer(nn.Module):
             self._cl_cache[name] = (key, (float(v[0, 0]), float(v[0, 1])), t)
         return self._cl_cache[name][1]
 
+    def _const_mask(self, value, rn, dev):
+        """(1,rn) bool mask of one value as an expanded view of a cached scalar (the ERP path's ray_mask is a constant,
+        renderer.py:289-293): no fill kernel per call."""
+        k = ("mask", value, str(dev))
+        if k not in self._tables:
+            self._tables[k] = torch.full((1, 1), value, device=dev)
+        return self._tables[k].expand(1, rn)
+
     def _cached_table(self, key, dev, make):
         k = (key, str(dev))
         if k not in self._tables:
@@ -568,7 +583,7 @@ class NeuralRayBaseRenderer(nn.Module):
         if cfg["use_ray_mask"]:
             # every projection is "valid" in the ERP path: mask of ones (renderer.py:289-293)
             views_ok = rfn >= cfg["ray_mask_view_num"]
-            outs["ray_mask"] = torch.full((1, rn), bool(views_ok and dn > cfg["ray_mask_point_num"]), device=dev)
+            outs["ray_mask"] = self._const_mask(bool(views_ok and dn > cfg["ray_mask_point_num"]), rn, dev)
         if cfg["render_depth"]:
             outs["render_depth"] = e(1, rn)
         if cfg["use_hierarchical_sampling"]:
@@ -579,7 +594,7 @@ class NeuralRayBaseRenderer(nn.Module):
                 outs["hit_prob_nr_fine"] = e(1, rn, fdn)
                 outs["que_depth_fine"] = e(1, rn, fdn)
             if cfg["use_ray_mask"]:
-                outs["ray_mask_fine"] = torch.full((1, rn), bool(views_ok and fdn > cfg["ray_mask_point_num"]), device=dev)
+                outs["ray_mask_fine"] = self._const_mask(bool(views_ok and fdn > cfg["ray_mask_point_num"]), rn, dev)
             if cfg["render_depth"]:
                 outs["render_depth_fine"] = e(1, rn)
         return outs
@@ -676,6 +691,15 @@ class NeuralRayBaseRenderer(nn.Module):
     def _render_view(self, ctx, coords2, outs):
         """One C-ABI call for the whole view: pgrf_render_view_fwd runs the ray-batch loop and the
         coarse -> fine hand-off (network/renderer.py:647-683, 600-631) on the current stream."""
+        cfg, lib = self.cfg, _lib.load()
+        dev = coords2.device
+        self._key_memo = {}
+        try:
+            return self._render_view_impl(ctx, coords2, outs)
+        finally:
+            self._key_memo = None
+
+    def _render_view_impl(self, ctx, coords2, outs):
         cfg, lib = self.cfg, _lib.load()
         dev = coords2.device
         rn = coords2.shape[0]
