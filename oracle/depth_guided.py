@@ -127,6 +127,17 @@ def render_rays_diner(cfg, W, que, ref, fill_rand, gauss=None):
     depth = diner_sample_placement(cfg, que, ref, fill_rand, gauss)
     d_out = R.render_by_depth(cfg, W, que, ref, depth, False)
     d_out["que_depth"] = depth
+    if cfg.get("N_uniform", 0) > 0 and cfg.get("one_mlp", False):       # merge_uniform_diner, renderer.py:526-565
+        rn = que["coords"].shape[1]
+        udepth = R.sample_depth(cfg["min_depth"], cfg["max_depth"], rn, cfg["depth_sample_num"], use_disp=True)
+        u_out = R.render_by_depth(cfg, W, que, ref, udepth, False)
+        z, idx = torch.cat([depth, udepth], 2).sort()
+        col = torch.gather(torch.cat([d_out["colors_nr"], u_out["colors_nr"]], 2), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 3))
+        den = torch.gather(torch.cat([d_out["density_nr"], u_out["density_nr"]], 2), 2, idx)
+        hit, pix, rdepth = R.composite(den, col, z)
+        d_out.update({"pixel_colors_nr": pix, "hit_prob_nr": hit, "colors_nr": col, "density_nr": den, "render_depth": rdepth})
+        if cfg.get("render_uncert", False):
+            d_out["render_uncert"] = ((z - rdepth.unsqueeze(-1)).pow(2) * hit).sum(-1) + 1e-5
     if cfg.get("c2f", False):
         fine = R.sample_fine_depth(depth, d_out["hit_prob_nr"], que["depth_range"], cfg.get("fine_depth_sample_num", 64),
                                    cfg["use_disp"])

@@ -637,8 +637,10 @@ class NeuralRayBaseRenderer(nn.Module):
         when present, else drawn on the device."""
         from .render_ops import depth_guided_placement
         cfg = self.cfg
-        if cfg.get("N_uniform", 0) > 0:
-            raise NotImplementedError("merge_uniform_diner (cfg N_uniform > 0) is not part of the accelerated path")
+        merge_uniform = cfg.get("N_uniform", 0) > 0 and bool(cfg.get("one_mlp", False))   # else the uniform pass is dead code (:526-528)
+        if merge_uniform and cfg.get("c2f", False):
+            raise NotImplementedError("N_uniform + one_mlp + c2f: the reference hands mismatched depth / hit_prob shapes to "
+                                      "sample_fine_depth (renderer.py:586-589)")
         for k in ("mvs_depth", "mvs_uncert"):
             if k not in ref_imgs_info:
                 raise _lib.PanoGRFError(f"diner_depth_guided_sampling needs ref_imgs_info[{k!r}]")
@@ -656,7 +658,7 @@ class NeuralRayBaseRenderer(nn.Module):
 
         def alloc(n):
             o = {"pixel_colors_nr": e(1, rn, 3), "colors_nr": e(1, rn, n, 3), "density_nr": e(1, rn, n)}
-            if keep_hit_prob or c2f:
+            if keep_hit_prob or c2f or cfg.get("render_uncert"):
                 o["hit_prob_nr"] = e(1, rn, n)
             if cfg["use_ray_mask"]:
                 ok = rfn >= cfg["ray_mask_view_num"] and n > cfg["ray_mask_point_num"]
@@ -677,9 +679,37 @@ class NeuralRayBaseRenderer(nn.Module):
             if c2f:
                 self._pass(ctx, coords2[r0:r0 + n], fd, fine_total, not cfg.get("one_mlp", False), False, fine, r0,
                            "hit_prob_nr" in fine)
-                if keep_hit_prob:
+                if keep_hit_prob or cfg.get("render_uncert"):
                     fine.setdefault("que_depth", e(1, rn, fine_total))[0, r0:r0 + n] = fd
         coarse["que_depth"] = depth
+        if merge_uniform:
+            # merge_uniform_diner (renderer.py:526-565): a uniform-in-disparity pass of the same (coarse) networks, merged with the
+            # depth-guided samples by depth and composited again
+            from .render_ops import composite
+            dn_u = int(cfg["depth_sample_num"])
+            table = self._cached_table(("coarse", dn_u, True, float(cfg["min_depth"]), float(cfg["max_depth"])), dev,
+                                       lambda: coarse_depth_table(cfg, dn_u, True))
+            uni = {"pixel_colors_nr": e(1, rn, 3), "colors_nr": e(1, rn, dn_u, 3), "density_nr": e(1, rn, dn_u)}
+            if cfg["render_depth"]:
+                uni["render_depth"] = e(1, rn)
+            for r0 in range(0, rn, int(rpl)):
+                n = min(int(rpl), rn - r0)
+                self._pass(ctx, coords2[r0:r0 + n], table, 0, False, False, uni, r0, False)
+            z, idx = torch.cat([depth, table.view(1, 1, -1).expand(1, rn, -1)], 2).sort()
+            col = torch.gather(torch.cat([coarse["colors_nr"], uni["colors_nr"]], 2), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 3))
+            den = torch.gather(torch.cat([coarse["density_nr"], uni["density_nr"]], 2), 2, idx)
+            hit, pix, rdepth = composite(den, col, z)
+            coarse.update({"pixel_colors_nr": pix, "hit_prob_nr": hit, "colors_nr": col, "density_nr": den})
+            if cfg["render_depth"]:
+                coarse["render_depth"] = rdepth
+            if cfg.get("render_uncert"):
+                coarse["render_uncert"] = ((z - rdepth.unsqueeze(-1)).pow(2) * hit).sum(-1) + 1e-5
+        elif cfg.get("render_uncert"):
+            if "render_depth" not in coarse:
+                raise KeyError("render_depth")
+            coarse["render_uncert"] = ((depth - coarse["render_depth"].unsqueeze(-1)).pow(2) * coarse["hit_prob_nr"]).sum(-1) + 1e-5
+        if c2f and cfg.get("render_uncert"):
+            fine["render_uncert"] = ((fine["que_depth"] - fine["render_depth"].unsqueeze(-1)).pow(2) * fine["hit_prob_nr"]).sum(-1) + 1e-5
         if not (keep_hit_prob or not c2f):
             coarse.pop("hit_prob_nr", None)
         if c2f:

@@ -160,6 +160,9 @@ DINER_CASES = {
     "diner_dense_c2f": dict(cfg=dict(n_candidates=600, n_samples=16, n_gaussian=0, contain_uniform=False, c2f=True,
                                      max_depth=4.0, sample_num=16, diner_sigma=0.03, hierarchical=True), rfn=3, n_rays=48, map_scale=2,
                             radius=2.0),
+    # N_uniform + one_mlp: an extra uniform pass is merged with the depth-guided samples and re-composited (renderer.py:526-565)
+    "diner_merge_uniform": dict(cfg=dict(n_candidates=500, n_samples=16, n_gaussian=2, contain_uniform=False, N_uniform=16, one_mlp=True,
+                                         max_depth=6.0, sample_num=16, render_uncert=True), rfn=2, n_rays=40, map_scale=1, radius=2.5),
 }
 
 
