@@ -313,13 +313,19 @@ PGRF_API int pgrf_weight_blob_floats(void);
 PGRF_API int pgrf_weight_num_layers(void);
 PGRF_API int pgrf_weight_layer_info(int i, char* name, int name_cap, int* K, int* N, int* Npad, int* has_bias,
                                     int* k_begin, int* w_offset, int* b_offset);
-/* bf16 tensor-core blob: layer i stored as [Kpad/8][Npad][8] bf16 at w_offset_bytes, fp32 bias [Npad] at b_offset_bytes;
+/* bf16 tensor-core blob: layer i stored as [Kpad/8][Npad][8] bf16 at w_offset_bytes, its bias at b_offset_bytes (see layer_info2);
  * kmap[Kpad] / nmap[Npad] give the reference input / output feature of every padded slot (-1 = zero) */
 PGRF_API int pgrf_w16_blob_bytes(void);
 PGRF_API int pgrf_w16_num_layers(void);
 PGRF_API int pgrf_w16_layer_info(int i, char* name, int name_cap, int* Kpad, int* Npad, int* w_offset_bytes, int* b_offset_bytes,
                                  int* kmap, int* nmap, int* is_small);
 /* is_small = 1: tiny output layer kept as fp32 W[N][K] row-major at w_offset_bytes and bias[N] at b_offset_bytes (Kpad = K, Npad = N) */
+/* kmap values: >= 0 reference input feature, -1 zero column, -2 / -3 the layer's bias as a bf16 (hi, lo) pair (bias_kind 2).
+ * bias_kind: 0 = fp32 [Npad] at b_offset_bytes, 1 = bf16 chunk [Npad][8] = (hi, lo, 0 x6) at b_offset_bytes (B operand of a
+ * K-step against a constant ones chunk), 2 = inside the weight (kmap -2 / -3; b_offset_bytes = -1), 3 = none.
+ * in_ln2: store the weights multiplied by ln 2; out_log2e: store weights and bias multiplied by log2(e) (the kernel evaluates
+ * the ELU between two such layers on pre-scaled values). */
+PGRF_API int pgrf_w16_layer_info2(int i, int* bias_kind, int* in_ln2, int* out_log2e);
 /* layer-norm (weight 16, bias 16) offset, positional table offset ([max_samples][16]) */
 PGRF_API int pgrf_weight_aux_offsets(int* layer_norm_offset, int* posenc_offset, int* max_samples);
 

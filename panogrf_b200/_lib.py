@@ -55,6 +55,11 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # experiment knobs: PGRF_DEBUG="key=value,key=value" -> pgrf_debug_set (tuning only, never changes results)
+    for kv in filter(None, os.environ.get("PGRF_DEBUG", "").split(",")):
+        k, v = kv.split("=")
+        if lib.pgrf_debug_set(k.encode(), int(v)) != PGRF_OK:
+            raise PanoGRFError(f"PGRF_DEBUG: {lib.pgrf_last_error().decode()}")
     return lib
 
 
@@ -167,7 +172,10 @@ SIGNATURES.update({
     "pgrf_w16_blob_bytes": (_I, []),
     "pgrf_w16_num_layers": (_I, []),
     "pgrf_w16_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI, _PI]),
+    "pgrf_w16_layer_info2": (_I, [_I, _PI, _PI, _PI]),
 })
+
+BIAS_F32, BIAS_CHUNK, BIAS_INLINE, BIAS_NONE = 0, 1, 2, 3
 
 
 def weight_layers():
@@ -190,7 +198,8 @@ def weight_aux_offsets():
 
 
 def w16_layers():
-    """[(name, Kpad, Npad, w_offset_bytes, b_offset_bytes, kmap, nmap, is_small)] of the bf16 tensor-core blob."""
+    """[(name, Kpad, Npad, w_offset_bytes, b_offset_bytes, kmap, nmap, is_small, bias_kind, in_ln2, out_log2e)] of the bf16
+    tensor-core blob (kmap: -1 = zero column, -2 / -3 = bias_hi / bias_lo column)."""
     lib = load()
     out = []
     for i in range(lib.pgrf_w16_num_layers()):
@@ -200,6 +209,8 @@ def w16_layers():
         nmap = (_I * 64)()
         check(lib.pgrf_w16_layer_info(i, name, 128, ctypes.byref(kp), ctypes.byref(np_), ctypes.byref(wo), ctypes.byref(bo),
                                       kmap, nmap, ctypes.byref(small)), "pgrf_w16_layer_info")
+        bk, il, ol = _I(), _I(), _I()
+        check(lib.pgrf_w16_layer_info2(i, ctypes.byref(bk), ctypes.byref(il), ctypes.byref(ol)), "pgrf_w16_layer_info2")
         out.append((name.value.decode(), kp.value, np_.value, wo.value, bo.value, list(kmap[:kp.value]), list(nmap[:np_.value]),
-                    bool(small.value)))
+                    bool(small.value), bk.value, bool(il.value), bool(ol.value)))
     return out

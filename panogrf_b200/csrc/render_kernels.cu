@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "render_device.cuh"
+#include "render_layout16.cuh"
 
 // Layout offsets must be constant-evaluated: kLayers is a host constexpr table and may not be indexed at run time
 // in device code.
@@ -708,7 +709,7 @@ static int num_sms() {
 }  // namespace pgrf
 
 namespace pgrf {
-int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long total, int n_tiles, int sms, cudaStream_t st);
+int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long total, int n_tiles, int Mv, int sms, cudaStream_t st);
 int launch_render_rays_bf16(const pgrf_render_args& a, int V, int T, long long total, int sms, cudaStream_t st);
 }
 using namespace pgrf;
@@ -736,6 +737,9 @@ extern "C" int pgrf_render_workspace(int rfn, long long n_samples, long long* f1
   const long long tiles = (n_samples + T - 1) / T;
   *f1_floats = tiles * kF1 * kTileRows;
   *f2_floats = tiles * kF2 * T;
+  // bf16 path: operand tiles of the rays kernel (<= 128 samples each, > 64 used) + one float4 per sample
+  const long long f2_bf16 = ((n_samples / 65 + 2) * kF2TileBytes + n_samples * 16 + 3) / 4;
+  if (f2_bf16 > *f2_floats) *f2_floats = f2_bf16;
   return PGRF_OK;
 }
 
@@ -786,12 +790,14 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
   const int mask = a.stage_mask ? a.stage_mask : 7;
   if (a.mlp_bf16) {
     if (a.sched) PGRF_CUDA(cudaMemsetAsync(a.sched, 0, 2 * sizeof(int), st));
+    const int T16 = tile_samples16(a.rfn);
+    const int Mv = (a.dn >= kTileRows ? 1 : kTileRows / a.dn) * a.dn;     // samples per tile of the rays kernel (whole rays)
     if (mask & 3) {
-      const int rc = launch_render_mlp_bf16(a, p.V, p.T, p.total, p.n_tiles, sms, st);
+      const int rc = launch_render_mlp_bf16(a, p.V, T16, p.total, (int)((p.total + T16 - 1) / T16), Mv, sms, st);
       if (rc != PGRF_OK) return rc;
     }
     if (mask & 4) {
-      const int rc = launch_render_rays_bf16(a, p.V, p.T, p.total, sms, st);
+      const int rc = launch_render_rays_bf16(a, p.V, T16, p.total, sms, st);
       if (rc != PGRF_OK) return rc;
     }
     return PGRF_OK;

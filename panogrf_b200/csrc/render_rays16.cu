@@ -43,7 +43,7 @@ constexpr int SMR_W32 = (kSec1Bytes + 15) & ~15;
 constexpr int SMR_PE = SMR_W32 + ((kR3W32 * 4 + 15) & ~15);
 constexpr int SMR_WG = (SMR_PE + kMaxSamplesPerRay * 16 * 4 + 127) & ~127;
 constexpr int SMR_BAR = SMR_WG + kWGr * R_WG_BYTES;
-constexpr int SMR_BYTES = SMR_BAR + 64;
+constexpr int SMR_BYTES = SMR_BAR + 128;
 
 __device__ __forceinline__ void wgr_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 __device__ __forceinline__ float warp_sum16(float v) {
@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
   float* RV = reinterpret_cast<float*>(G + R_RV);
   float* RGB = reinterpret_cast<float*>(G + R_RGB);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMR_BAR) + wg;
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(smem + SMR_BAR) + kWGr + wg;     // completion of the tile's bulk copy
+  const unsigned char* f2_op = reinterpret_cast<const unsigned char*>(a.f2);    // bf16 operand tiles written by the MLP kernel
 
   {
     constexpr int sec1 = sec16_begin(1);
@@ -124,14 +126,16 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
     for (int i = tid; i < a.dn * 16; i += kThreadsR) PE[i] = __ldg(a.weights + kPosencOffset + i);
   }
   if (tid < 32) umma::tmem_alloc(&tmem_base_s, 256);
-  if (m == 0) mbar_init(bar, 1);
+  if (m == 0) { mbar_init(bar, 1); mbar_init(tbar, 1); }
+  // chunk 9 of the A operand (K columns 72..79 of geometry_fc.0) is never written by a tile: zero it once
+  *reinterpret_cast<uint4*>(G + R_A + ((size_t)9 * RROWS + m) * 16) = make_uint4(0u, 0u, 0u, 0u);
   umma::fence_smem_to_async();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base_s + wg * 64;
   const uint32_t tq = tb + ((uint32_t)(wq * 32) << 16);
-  uint32_t phase = 0;
+  uint32_t phase = 0, tphase = 0;
   constexpr int ln_rel = section_floats(2) - kR3W32Begin;
   const float* LNW = W32 + ln_rel;
   const float* LNB = LNW + 16;
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
   const int dn = a.dn, V = p.V, T = p.T;
   const int rpt = p.rays_per_tile;
   const int Mv = rpt * dn;
+  const float4* f2_rgb = reinterpret_cast<const float4*>(f2_op + (size_t)p.n_tiles * kF2TileBytes);
 
   __shared__ int s_tile[kWGr];
   __shared__ float4 s_kn[kWGr][4];
@@ -159,22 +164,17 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
     long long g = g0 + min(m, Mv - 1);
     if (g >= p.total) g = p.total - 1;
     const int sidx = (int)((unsigned)g % (unsigned)dn);    // sample index inside its ray (total < 2^31, checked by the MLP launcher)
-    // ---- pooled features of this sample (F2 tile [kF2][T]) -> A operand (bf16), colours -> smem
-    {
-      const float* f2 = a.f2 + (size_t)(g >> p.log2T) * kF2 * T + (g & (T - 1));
-      // all 68 loads of this sample are issued before the first use (HBM-streamed tile: the pass is latency bound on them)
-      float v[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] = __ldcs(f2 + (size_t)i * T);
-      const float wm = __ldcs(f2 + (size_t)64 * T);
-      const float c0 = __ldcs(f2 + (size_t)F2_RGB * T), c1 = __ldcs(f2 + (size_t)(F2_RGB + 1) * T), c2 = __ldcs(f2 + (size_t)(F2_RGB + 2) * T);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) umma::store_chunk(G + R_A, RROWS, c, m, v + 8 * c);
-      float tail[8] = {wm, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      umma::store_chunk(G + R_A, RROWS, 8, m, tail);
-      *reinterpret_cast<uint4*>(G + R_A + ((size_t)9 * RROWS + m) * 16) = make_uint4(0u, 0u, 0u, 0u);
-      RGB[m] = c0; RGB[RROWS + m] = c1; RGB[2 * RROWS + m] = c2;
+    // ---- pooled features of the tile: the MLP kernel wrote them as a ready bf16 A operand (9 k-chunks x 128 rows); ONE bulk copy
+    //      (TMA) brings the tile in while the threads fetch their sample's blended colour
+    if (m == 0) {
+      mbar_expect_tx(tbar, kF2TileBytes);
+      bulk_g2s(G + R_A, f2_op + (size_t)tile * kF2TileBytes, kF2TileBytes, tbar);
     }
+    {
+      const float4 c = __ldcs(f2_rgb + g);
+      RGB[m] = c.x; RGB[RROWS + m] = c.y; RGB[2 * RROWS + m] = c.z;
+    }
+    mbar_wait(tbar, tphase); tphase ^= 1;
     // ---- geometry_fc 65 -> 64 -> 16 (+ positional code)
     RSTAGE_BEGIN() umma::gemm_issue(tb, G + R_A, RROWS, Wb + W16(M_GEO0), 64, 64, 80); RSTAGE_END()
     epi_elu_store(tq, Bias + B16(M_GEO0), G + R_A, m, 8);       // H64 overwrites A: its MMA is complete
@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
         kn2[h] = kv[4 * h] * kv[4 * h] + kv[4 * h + 1] * kv[4 * h + 1] + kv[4 * h + 2] * kv[4 * h + 2] + kv[4 * h + 3] * kv[4 * h + 3];
       }
       // largest key norm of the tile, per head: |q||k|max bounds every score, so the softmax needs no separate max pass
+      if (m >= Mv || g0 + m >= p.total) { kn2[0] = 0.f; kn2[1] = 0.f; kn2[2] = 0.f; kn2[3] = 0.f; }   // rows without a sample
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
 #pragma unroll
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) render_rays_bf16_kernel(const Ra
         }
       }
     }
+    umma::fence_smem_to_async();
     wgr_sync(wg);
   }
   umma::fence_before_sync();

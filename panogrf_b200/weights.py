@@ -69,14 +69,26 @@ def pack_blob(state, fine, n_samples, device, allow_missing=False):
     return blob.to(device)
 
 
+def _bf16_hi_lo(x):
+    """fp32 vector -> (hi, lo) fp32 tensors holding bf16-representable values with hi + lo ~= x to ~2^-17 relative."""
+    hi = x.to(torch.bfloat16).float()
+    lo = (x - hi).to(torch.bfloat16).float()
+    return hi, lo
+
+
 def pack_blob16(state, fine, device):
     """bf16 tensor-core blob (csrc/render_layout16.cuh): per layer the padded / permuted weight as a tcgen05 B
-    operand [Kpad/8][Npad][8] bf16, then the fp32 biases.  Returns a uint8 tensor of pgrf_w16_blob_bytes() bytes."""
+    operand [Kpad/8][Npad][8] bf16.  Section 0 (fused MLP kernel): the bias is a bf16 (hi, lo) pair, either in its own
+    [Npad][8] chunk or in two spare K columns of the layer (kmap -2 / -3); layers flagged `out_log2e` are stored
+    multiplied by log2(e) (weights and bias), layers flagged `in_ln2` have their weights multiplied by ln 2 (the
+    producing ELU is evaluated on pre-scaled values).  Section 1 (rays kernel): fp32 biases.
+    Returns a uint8 tensor of pgrf_w16_blob_bytes() bytes."""
     lib = _lib.load()
     dd = "fine_dist_decoder" if fine else "dist_decoder"
     agg = "fine_agg_net" if fine else "agg_net"
+    LOG2E, LN2 = 1.4426950408889634, 0.6931471805599453
     blob = torch.zeros(lib.pgrf_w16_blob_bytes(), dtype=torch.uint8)
-    for name, Kpad, Npad, w_off, b_off, kmap, nmap, is_small in _lib.w16_layers():
+    for name, Kpad, Npad, w_off, b_off, kmap, nmap, is_small, bias_kind, in_ln2, out_log2e in _lib.w16_layers():
         key = name.replace("{dd}", dd).replace("{agg}", agg)
         if key.endswith("ray_attention.qkv"):
             base = key[:-len(".qkv")]
@@ -89,10 +101,17 @@ def pack_blob16(state, fine, device):
                 raise KeyError(f"missing parameter {key}.weight")
             w = state[key + ".weight"].detach().float().cpu()
             b = state.get(key + ".bias")
+        if b is not None:
+            b = b.detach().float().cpu()
+        scale = (LN2 if in_ln2 else 1.0) * (LOG2E if out_log2e else 1.0)
+        if scale != 1.0:
+            w = (w.double() * scale).float()
+        if out_log2e and b is not None:
+            b = (b.double() * LOG2E).float()
         if is_small:      # fp32 W[N][K] row-major + bias[N], evaluated as a register GEMV in the previous epilogue
             blob[w_off:w_off + Kpad * Npad * 4] = w[:Npad, :Kpad].contiguous().view(torch.uint8).reshape(-1)
             if b is not None:
-                blob[b_off:b_off + Npad * 4] = b.detach().float().cpu().contiguous().view(torch.uint8).reshape(-1)
+                blob[b_off:b_off + Npad * 4] = b.contiguous().view(torch.uint8).reshape(-1)
             continue
         km = torch.tensor(kmap)
         nm = torch.tensor(nmap)
@@ -100,11 +119,22 @@ def pack_blob16(state, fine, device):
         rows = torch.nonzero(nm >= 0).flatten()
         cols = torch.nonzero(km >= 0).flatten()
         wp[rows[:, None], cols[None, :]] = w[nm[rows][:, None], km[cols][None, :]]
+        bp = torch.zeros(Npad)
+        if b is not None:
+            bp[rows] = b[nm[rows]]
+        if bias_kind == _lib.BIAS_INLINE:     # two spare K columns carry (bias_hi, bias_lo); the kernel writes ones there
+            hi, lo = _bf16_hi_lo(bp)
+            wp[:, int(torch.nonzero(km == -2).flatten()[0])] = hi
+            wp[:, int(torch.nonzero(km == -3).flatten()[0])] = lo
         # B operand: element (n, k) at [(k/8)][n][k%8]
         op = wp.reshape(Npad, Kpad // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
         blob[w_off:w_off + Kpad * Npad * 2] = op.view(torch.uint8).reshape(-1)
-        bp = torch.zeros(Npad)
-        if b is not None:
-            bp[rows] = b.detach().float().cpu()[nm[rows]]
-        blob[b_off:b_off + Npad * 4] = bp.view(torch.uint8).reshape(-1)
+        if bias_kind == _lib.BIAS_CHUNK:      # [Npad][8] bf16 = (hi, lo, 0 x6): B operand of the "ones" K-step
+            hi, lo = _bf16_hi_lo(bp)
+            ch = torch.zeros(Npad, 8)
+            ch[:, 0] = hi
+            ch[:, 1] = lo
+            blob[b_off:b_off + Npad * 16] = ch.to(torch.bfloat16).view(torch.uint8).reshape(-1)
+        elif bias_kind == _lib.BIAS_F32:
+            blob[b_off:b_off + Npad * 4] = bp.view(torch.uint8).reshape(-1)
     return blob.to(device)

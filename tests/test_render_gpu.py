@@ -169,13 +169,30 @@ def test_errors():
 # bf16 tensor-core MLP path (tcgen05): north-star tolerance rtol 1e-2
 # ------------------------------------------------------------------------------------------------
 
-def _close_bf16(actual, expected, what, frac_of_max):
-    """|a-e| <= 1e-2*|e| + frac_of_max*max|e|.  Operands of every Linear layer are rounded to bf16 (unit
-    roundoff 2^-8 = 3.9e-3) and the random-init, un-normalised network chains ~12 such layers, so per-sample
-    quantities carry up to ~3 % of the tensor's dynamic range in the worst element (typically < 1 %); the
-    composited pixel colours / depths (sums over 64 samples) stay within 1 %."""
+# Natural scale of every output: colours, probabilities and alphas live in [0, 1]; depths in the 0.5 .. 15 m sampling range.
+DEPTH_SCALE = 14.5
+BF16_ATOL = 5e-3      # of the natural scale: 0.5 % of full-scale colour (1.3 / 255), 7 cm of depth
+
+
+def _close_bf16(actual, expected, what, scale=1.0, atol=BF16_ATOL, max_bad_frac=0.0):
+    """north-star bf16 tolerance: |a-e| <= 1e-2*|e| + atol*scale.
+
+    `scale` is the NATURAL scale of the quantity (1 for colours / hit probabilities, the depth range for depths), not the largest
+    value that happens to occur in the test case.  The operands of every Linear layer are rounded to bf16 (unit roundoff 2^-9 =
+    2e-3) and the random-init network chains ~12 such layers; measured on the goldens (tools/bf16_error_stats.py, B200):
+    composited colour error <= 3.4e-3, depth error <= 4.1 cm, hit_prob error <= 3.5e-3 in the worst element, ~1e-3 / 1 cm / 5e-4 on
+    average.  `density` has no natural scale (pre-activation of alpha): its tolerance is relative to max|e| (callers pass it)."""
     e = torch.as_tensor(expected).float().cpu()
-    assert_close(actual, e, rtol=1e-2, atol=frac_of_max * float(e.abs().max()), what=what)
+    assert_close(actual, e, rtol=1e-2, atol=atol * scale, max_bad_frac=max_bad_frac, what=what)
+
+
+def _check_bf16_pass(out, gold, name, suffix=""):
+    _close_bf16(out["pixel_colors_nr"], gold["pixel_colors_nr" + suffix], f"{name}/pixel_colors_nr{suffix}")
+    _close_bf16(out["render_depth"], gold["render_depth" + suffix], f"{name}/render_depth{suffix}", scale=DEPTH_SCALE)
+    _close_bf16(out["hit_prob_nr"], gold["hit_prob_nr" + suffix], f"{name}/hit_prob_nr{suffix}")
+    _close_bf16(out["colors_nr"], gold["colors_nr" + suffix], f"{name}/colors_nr{suffix}")
+    d = gold["density_nr" + suffix]
+    _close_bf16(out["density_nr"], d, f"{name}/density_nr{suffix}", scale=float(d.abs().max()), atol=2.5e-2)
 
 
 @pytest.mark.parametrize("name", list(cases.RENDER_CASES))
@@ -186,10 +203,7 @@ def test_bf16_coarse_pass_matches_reference_golden(name):
     net = build_renderer(cfg, W)
     out = net.render_impl(cuda_dict(que), cuda_dict(ref), False, keep_hit_prob=True)
     torch.cuda.synchronize()
-    _close_bf16(out["pixel_colors_nr"], gold["pixel_colors_nr"], f"{name}/pixel_colors_nr", 1e-2)
-    _close_bf16(out["render_depth"], gold["render_depth"], f"{name}/render_depth", 1e-2)
-    for k in ("hit_prob_nr", "colors_nr", "density_nr"):
-        _close_bf16(out[k], gold[k], f"{name}/{k}", 3e-2)
+    _check_bf16_pass(out, gold, name)
 
 
 @pytest.mark.parametrize("name", ["render_m3d_2src", "render_m3d_vis_nodisp", "render_replica", "render_m3d_4src_all"])
@@ -203,10 +217,7 @@ def test_bf16_fine_pass_on_reference_sample_positions(name):
     net = build_renderer({**cfg, "mlp_dtype": "bf16"}, W)
     out = net.render_by_depth(fdepth.cuda(), cuda_dict(que), cuda_dict(ref), False, True)
     torch.cuda.synchronize()
-    _close_bf16(out["pixel_colors_nr"], o["pixel_colors_nr_fine"], f"{name}/fine rgb", 1e-2)
-    _close_bf16(out["render_depth"], o["render_depth_fine"], f"{name}/fine depth", 1e-2)
-    for k in ("hit_prob_nr", "density_nr", "colors_nr"):
-        _close_bf16(out[k], o[k + "_fine"], f"{name}/fine {k}", 3e-2)
+    _check_bf16_pass(out, o, name, "_fine")
 
 
 def test_bf16_full_view_end_to_end():
@@ -225,13 +236,18 @@ def test_bf16_full_view_end_to_end():
     a = build_renderer({**cfg, "mlp_dtype": "bf16"}, W).render(cuda_dict(que), cuda_dict(ref2), False)
     b = build_renderer(cfg, W).render(cuda_dict(que), cuda_dict(ref2), False)
     torch.cuda.synchronize()
-    for k in ("pixel_colors_nr", "pixel_colors_nr_fine", "render_depth", "render_depth_fine"):
+    # coarse pass: same sample positions in both paths -> the plain bf16 tolerance
+    _close_bf16(a["pixel_colors_nr"], b["pixel_colors_nr"], "view/pixel_colors_nr")
+    _close_bf16(a["render_depth"], b["render_depth"], "view/render_depth", scale=DEPTH_SCALE)
+    # fine pass: the inverse-CDF resampling is discontinuous in the coarse hit_prob (a 1e-3 change moves a sample across an
+    # occlusion boundary of the scene), so single pixels may land on a different surface: bound the distribution —
+    # mean within 2e-3 of the natural scale, 99 % of the pixels within the bf16 tolerance, none off by more than 10 % of scale
+    for k, scale in (("pixel_colors_nr_fine", 1.0), ("render_depth_fine", DEPTH_SCALE)):
         e = b[k].float().cpu()
-        # mean error well below 1e-2 of the range; worst pixel within 1e-1 (the fine pass resamples from the bf16
-        # hit_prob, and render_depth = sum(hit * depth) spans 0.5 .. 15 m)
         err = (a[k].float().cpu() - e).abs()
-        assert float(err.mean()) < 5e-3 * float(e.abs().max()), (k, float(err.mean()))
-        assert float(err.max()) < 1e-1 * float(e.abs().max()), (k, float(err.max()))
+        assert float(err.mean()) < 2e-3 * scale, (k, float(err.mean()))
+        _close_bf16(a[k], e, "view/" + k, scale=scale, max_bad_frac=1e-2)
+        assert float(err.max()) < 1e-1 * scale, (k, float(err.max()))
 
 
 @pytest.mark.parametrize("rfn", [2, 4])
@@ -273,9 +289,9 @@ def test_production_shapes_max_samples(rfn):
         assert_close(out[k], o[k], rtol=1e-4, atol=1e-4, max_bad_frac=frac, what=f"max-samples rfn={rfn} fp32 {k}")
     net16 = build_renderer({**cfg, "mlp_dtype": "bf16"}, W)
     out16 = net16.render(cuda_dict(que), cuda_dict(ref), False, keep_hit_prob=True)
-    _close_bf16(out16["pixel_colors_nr"], o["pixel_colors_nr"], f"rfn={rfn} bf16 pixel_colors_nr", 1e-2)
-    _close_bf16(out16["render_depth"], o["render_depth"], f"rfn={rfn} bf16 render_depth", 1e-2)
-    _close_bf16(out16["hit_prob_nr"], o["hit_prob_nr"], f"rfn={rfn} bf16 hit_prob_nr", 3e-2)
-    # the fine pass resamples from the (bf16) coarse hit_prob: smooth maps keep the composited result within 3 % of range
-    _close_bf16(out16["pixel_colors_nr_fine"], o["pixel_colors_nr_fine"], f"rfn={rfn} bf16 pixel_colors_nr_fine", 3e-2)
+    _close_bf16(out16["pixel_colors_nr"], o["pixel_colors_nr"], f"rfn={rfn} bf16 pixel_colors_nr")
+    _close_bf16(out16["render_depth"], o["render_depth"], f"rfn={rfn} bf16 render_depth", scale=DEPTH_SCALE)
+    _close_bf16(out16["hit_prob_nr"], o["hit_prob_nr"], f"rfn={rfn} bf16 hit_prob_nr")
+    # the fine pass resamples from the (bf16) coarse hit_prob: smooth maps keep the composited colour within 1 % of full scale
+    _close_bf16(out16["pixel_colors_nr_fine"], o["pixel_colors_nr_fine"], f"rfn={rfn} bf16 pixel_colors_nr_fine", atol=1e-2)
     assert out16["hit_prob_nr_fine"].shape == (1, 45, 128) and bool(torch.isfinite(out16["colors_nr_fine"]).all())
