@@ -16,6 +16,8 @@
 //            cost vs. the reference feature held in registers, accumulation over source views
 //   epilogue: channels-last -> direct 128-bit streaming stores (512 B contiguous per warp store);
 //             planar (B,D,C,H,W)/(B,C,D,H,W)/group-mean -> conflict-free smem transpose, 128-B row stores
+#include <cuda.h>
+
 #include "cost_volume.cuh"
 
 namespace pgrf {
@@ -60,6 +62,10 @@ __global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_kernel(const CvP
     const int px = x_warp + j * PPS + pp;
     ref[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (px < p.W) ref[j] = ldg4(img4 + (size_t)p.ref_idx * view_f4 + ((size_t)y * p.W + px) * CG + cg);
+  }
+  if (p.cost_type == PGRF_COST_ABS_DIFF) {     // |warped - ref| = |warped + (-ref)|: keep the negated feature
+#pragma unroll
+    for (int j = 0; j < NSUB; ++j) ref[j] = make_float4(-ref[j].x, -ref[j].y, -ref[j].z, -ref[j].w);
   }
 
   const float4* lane_base = img4 + cg;
@@ -131,21 +137,9 @@ __global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_kernel(const CvP
         }
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
-          const float tx1 = 1.f - tx[jj], ty1 = 1.f - ty[jj];   // exact: == (x0+1)-ix, (y0+1)-iy
-          const float wnw = tx1 * ty1, wne = tx[jj] * ty1, wsw = tx1 * ty[jj], wse = tx[jj] * ty[jj];
-          const float4 nw = t[jj][0], ne = t[jj][1], sw = t[jj][2], se = t[jj][3];
-          const float4 rf = ref[j0 + jj];
-          float4 val;   // ATen's accumulation order: nw, ne, sw, se
-          val.x = nw.x * wnw; val.y = nw.y * wnw; val.z = nw.z * wnw; val.w = nw.w * wnw;
-          val.x = fmaf(ne.x, wne, val.x); val.y = fmaf(ne.y, wne, val.y); val.z = fmaf(ne.z, wne, val.z); val.w = fmaf(ne.w, wne, val.w);
-          val.x = fmaf(sw.x, wsw, val.x); val.y = fmaf(sw.y, wsw, val.y); val.z = fmaf(sw.z, wsw, val.z); val.w = fmaf(sw.w, wsw, val.w);
-          val.x = fmaf(se.x, wse, val.x); val.y = fmaf(se.y, wse, val.y); val.z = fmaf(se.z, wse, val.z); val.w = fmaf(se.w, wse, val.w);
-          if (p.cost_type == PGRF_COST_ABS_DIFF) {
-            val.x = fabsf(val.x - rf.x); val.y = fabsf(val.y - rf.y); val.z = fabsf(val.z - rf.z); val.w = fabsf(val.w - rf.w);
-          } else if (p.cost_type == PGRF_COST_DOT) {
-            val.x *= rf.x; val.y *= rf.y; val.z *= rf.z; val.w *= rf.w;
-          }
-          if (!SINGLE && use_div) { val.x = val.x / p.divisor; val.y = val.y / p.divisor; val.z = val.z / p.divisor; val.w = val.w / p.divisor; }
+          float4 val = blend_cost(t[jj][0], t[jj][1], t[jj][2], t[jj][3], tx[jj], ty[jj], ref[j0 + jj], p.cost_type);
+          if (SINGLE) { acc[jj] = val; continue; }          // one swept view, no divisor: the sum is the term itself
+          if (use_div) { val.x = val.x / p.divisor; val.y = val.y / p.divisor; val.z = val.z / p.divisor; val.w = val.w / p.divisor; }
           acc[jj].x += val.x; acc[jj].y += val.y; acc[jj].z += val.z; acc[jj].w += val.w;
         }
       }
@@ -188,8 +182,203 @@ __global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_kernel(const CvP
   if (bad) atomicOr(p.err, 1);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Planar layouts, C = 32, W % 128 == 0: the output leaves through the TMA engine (tensor-map store) instead of the LSU.
+// The L1TEX data stage is this kernel's limiter (profiles/r1_final_ncu_summary.md: 89 % busy, DRAM 39 %): per voxel column it
+// serves 4 x 128 B of bilinear taps, and in the version above another 32 STS + 32 LDS + 32 STG wavefronts for the
+// (pixel, channel) -> (channel, pixel) transposition.  Here
+//   * the gather keeps its lane = (pixel pp, channel group cg) mapping (a quarter-warp of a 128-bit load = one 128-byte line);
+//     a 4x4 register transpose over the lanes pp = 0..3 of a channel group (4 SHFL) turns "4 channels of 1 pixel" into
+//     "1 channel of 4 pixels";
+//   * one STS.128 per sub-iteration writes it into the warp's own [32 rows][32 pixels] tile, row = pp * 8 + cg (channel
+//     4 cg + pp), in the 128-byte swizzle of the tensor map (16-byte chunk index XOR row % 8 = cg): conflict-free;
+//   * one lane hands the whole 4 KB tile to the TMA engine (cp.async.bulk.tensor.5d): the output is described as
+//     (pixel, cg, pp, depth, batch) with channel = 4 cg + pp split over two dimensions, box 32 x 8 x 4 x 1 x 1, so the row
+//     permutation costs nothing; double-buffered over the depth loop — warp-local, no CTA barrier.
+// Measured dead ends: 512-byte cp.async.bulk row copies (2.1 M requests per volume: 0.62 ms, request bound); pixel-fastest
+// lane mapping for an un-permuted tile (every quarter-warp of a tap load then touches 4 lines instead of 1: 0.55 ms).
+// L1TEX wavefronts per voxel column: 128 (taps) + 32 (STS.128) instead of 128 + 96.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kCvWarpTileBytes = 32 * 32 * 4;           // one warp's [32 channels][32 pixels] fp32 tile
+
+template <bool SINGLE, int JBT, int MINB>
+__global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_planar_tma_kernel(const CvParams p, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int CG = 8, PPS = 4, NSUB = 8;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ float s_A[kMaxSrc][12];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = p.W / kCvThreads;
+  const int y = blockIdx.x / tiles_x;
+  const int x_warp = (blockIdx.x % tiles_x) * kCvThreads + warp * 32;
+  const int b = blockIdx.z;
+  const int d_begin = blockIdx.y * p.d_chunk;
+  const int d_end = min(p.D, d_begin + p.d_chunk);
+
+  unsigned char* tiles = smem_raw + (size_t)warp * 2 * kCvWarpTileBytes;                 // this warp's two tiles (1024 B aligned)
+  TapRec* rec = reinterpret_cast<TapRec*>(smem_raw + (size_t)kCvWarps * 2 * kCvWarpTileBytes) + warp * (p.n_src * 32);
+
+  if (threadIdx.x < p.n_src) relative_pose(p, b, threadIdx.x, s_A[threadIdx.x]);
+  __syncthreads();
+
+  const int x = x_warp + lane;
+  float rx, ry, rz;
+  pixel_ray(p, x, y, rx, ry, rz);
+
+  const int pp = lane >> 3, cg = lane & 7;
+  const size_t view_f4 = (size_t)p.H * p.W * CG;
+  const float4* img4 = reinterpret_cast<const float4*>(p.images) + (size_t)b * p.S * view_f4;
+  float4 ref[NSUB];
+#pragma unroll
+  for (int j = 0; j < NSUB; ++j)
+    ref[j] = ldg4(img4 + (size_t)p.ref_idx * view_f4 + ((size_t)y * p.W + x_warp + j * PPS + pp) * CG + cg);
+  if (p.cost_type == PGRF_COST_ABS_DIFF) {     // |warped - ref| = |warped + (-ref)|: keep the negated feature
+#pragma unroll
+    for (int j = 0; j < NSUB; ++j) ref[j] = make_float4(-ref[j].x, -ref[j].y, -ref[j].z, -ref[j].w);
+  }
+
+  const float4* lane_base = img4 + cg;
+  const int row_f4 = p.W * CG;
+  const bool use_div = p.divisor != 0.f;
+  const float hax = s_A[0][0] * rx + s_A[0][1] * ry + s_A[0][2] * rz;
+  const float hay = s_A[0][3] * rx + s_A[0][4] * ry + s_A[0][5] * rz;
+  const float haz = s_A[0][6] * rx + s_A[0][7] * ry + s_A[0][8] * rz;
+  const float hbx = s_A[0][9], hby = s_A[0][10], hbz = s_A[0][11];
+  const size_t plane = (size_t)p.H * p.W;
+  bool bad = false;
+  // after the 4x4 transpose this lane holds channel 4cg + pp of pixels 4j .. 4j+3: tile row pp*8 + cg, 16-byte chunk j ^ cg
+  const int crow = pp * 8 + cg;
+  uint64_t l2_evict_first;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_evict_first));
+  const int pix0 = y * p.W + x_warp;                     // coordinate 0 of the warp's box
+
+  for (int d = d_begin; d < d_end; ++d) {
+    unsigned char* tile = tiles + ((d - d_begin) & 1) * kCvWarpTileBytes;
+    // the store issued two depths ago read this buffer: at most the most recent one may still be reading
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    // ---------------- phase A: one lane per pixel ----------------
+    float depth;
+    if (p.depth_volume) depth = __ldg(p.depth_volume + ((size_t)b * p.D + d) * plane + (size_t)y * p.W + x);
+    else depth = __ldg(p.depths + d);
+    for (int s = 0; s < (SINGLE ? 1 : p.n_src); ++s) {
+      float cx, cy, cz;
+      if (SINGLE) {
+        cx = fmaf(depth, hax, hbx); cy = fmaf(depth, hay, hby); cz = fmaf(depth, haz, hbz);
+      } else {
+        const float* A = s_A[s];
+        const float ax = A[0] * rx + A[1] * ry + A[2] * rz;
+        const float ay = A[3] * rx + A[4] * ry + A[5] * rz;
+        const float az = A[6] * rx + A[7] * ry + A[8] * rz;
+        cx = fmaf(depth, ax, A[9]); cy = fmaf(depth, ay, A[10]); cz = fmaf(depth, az, A[11]);
+      }
+      float u, v;
+      point_uv(p.dataset, cx, cy, cz, u, v);
+      if (!(u >= -1.f && u <= 1.f && v >= -1.f && v <= 1.f)) bad = true;
+      const float ix = ((u + 1.f) / 2.f) * (float)(p.W - 1);
+      const float iy = ((v + 1.f) / 2.f) * (float)(p.H - 1);
+      float x0f = floorf(ix), y0f = floorf(iy);
+      x0f = fminf(fmaxf(x0f, 0.f), (float)(p.W - 2));   // NaN -> 0
+      y0f = fminf(fmaxf(y0f, 0.f), (float)(p.H - 2));
+      TapRec r;
+      r.tx = ix - x0f;
+      r.ty = iy - y0f;
+      r.off4 = ((int)y0f * p.W + (int)x0f) * CG;
+      r.pad = 0;
+      rec[s * 32 + lane] = r;
+    }
+    __syncwarp();
+
+    // ---------------- phase B: one lane per (pixel, float4 of channels) ----------------
+    constexpr int JB = JBT;
+#pragma unroll
+    for (int j0 = 0; j0 < NSUB; j0 += JB) {
+      float4 acc[JB];
+#pragma unroll
+      for (int jj = 0; jj < JB; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < (SINGLE ? 1 : p.n_src); ++s) {
+        const float4* vbase = lane_base + (size_t)p.src_views[s] * view_f4;
+        float4 t[JB][4];
+        float tx[JB], ty[JB];
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+          const TapRec r = rec[s * 32 + (j0 + jj) * PPS + pp];
+          const float4* row0 = vbase + r.off4;
+          const float4* row1 = row0 + row_f4;
+          t[jj][0] = ldg4(row0); t[jj][1] = ldg4(row0 + CG); t[jj][2] = ldg4(row1); t[jj][3] = ldg4(row1 + CG);
+          tx[jj] = r.tx; ty[jj] = r.ty;
+        }
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+          float4 val = blend_cost(t[jj][0], t[jj][1], t[jj][2], t[jj][3], tx[jj], ty[jj], ref[j0 + jj], p.cost_type);
+          if (SINGLE) { acc[jj] = val; continue; }          // one swept view, no divisor: the sum is the term itself
+          if (use_div) { val.x = val.x / p.divisor; val.y = val.y / p.divisor; val.z = val.z / p.divisor; val.w = val.w / p.divisor; }
+          acc[jj].x += val.x; acc[jj].y += val.y; acc[jj].z += val.z; acc[jj].w += val.w;
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < JB; ++jj) {
+        // 4x4 transpose over the lanes pp = 0..3 of one channel group: (4 channels of pixel pp) -> (channel pp of 4 pixels)
+        float4 v = acc[jj];
+        {
+          const bool odd = pp & 1;
+          const float s0 = odd ? v.x : v.y, s1 = odd ? v.z : v.w;
+          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
+          v = odd ? make_float4(r0, v.y, r1, v.w) : make_float4(v.x, r0, v.z, r1);
+        }
+        {
+          const bool up = pp & 2;
+          const float s0 = up ? v.x : v.z, s1 = up ? v.y : v.w;
+          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+          v = up ? make_float4(r0, r1, v.z, v.w) : make_float4(v.x, v.y, r0, r1);
+        }
+        *reinterpret_cast<float4*>(tile + crow * 128 + (((j0 + jj) ^ (crow & 7)) << 4)) = v;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      // evict-first: the volume is written once and never re-read here; without the hint the stores push the feature maps out
+      // of L2 (ncu: DRAM reads 67 MB -> 161 MB, long_scoreboard on the tap loads)
+      asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4, %5}], [%6], %7;" ::"l"(&tmap),
+                   "r"(pix0), "r"(0), "r"(0), "r"(d), "r"(b), "r"((uint32_t)__cvta_generic_to_shared(tile)), "l"(l2_evict_first)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (bad) atomicOr(p.err, 1);
+}
+
+// tensor map of the planar output as (pixel = y*W + x, cg, pp, depth, batch) with channel = 4 cg + pp; box 32 x 8 x 4 x 1 x 1,
+// 128-byte swizzle
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_out_tensor_map(const CvParams& p, CUtensorMap* tm) {
+  static PFN_encodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PGRF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PGRF_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cost_volume: cuTensorMapEncodeTiled unavailable");
+    encode = (PFN_encodeTiled)fn;
+  }
+  const cuuint64_t dims[5] = {(cuuint64_t)p.H * p.W, 8, 4, (cuuint64_t)p.D, (cuuint64_t)p.B};
+  const cuuint64_t strides[4] = {(cuuint64_t)p.sC * 16, (cuuint64_t)p.sC * 4, (cuuint64_t)p.sD * 4, (cuuint64_t)p.sB * 4};   // bytes, dims 1..4
+  const cuuint32_t box[5] = {32, 8, 4, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PGRF_REQUIRE(r == CUDA_SUCCESS, "cost_volume: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return PGRF_OK;
+}
+
 int g_cv_jb = 0;      // gathers batched per lane (4*JB 128-bit loads in flight); 0 = measured default per layout
 int g_cv_dchunk = 0;  // 0 = heuristic
+int g_cv_pad_smem = 0;
+int g_cv_tma = 0;     // 1 = planar layouts (C = 32, W % 128 == 0) leave through the TMA engine; measured 2 % slower than the LSU path
+                      // on B200 although it takes L1TEX from 89 % to 69 %: opt-in (debug knob cv_tma)
 int g_cv_minb = 0;    // __launch_bounds__ min blocks per SM: 0 = default (5 blocks = 20 warps/SM), 1 = uncapped registers
 
 template <int C>
@@ -200,6 +389,7 @@ static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
   const bool planar = layout != PGRF_CV_BDHWC;
   size_t smem = (size_t)kCvWarps * p.n_src * 32 * sizeof(TapRec);
   if (planar) smem += (size_t)kCvWarps * C * 33 * sizeof(float);
+  smem += (size_t)g_cv_pad_smem;       // experiment knob: shrink the L1 carve-out without touching the kernel
   const bool single = p.n_src == 1 && p.divisor == 0.f;
 #define PGRF_CV_LAUNCH1(PL, SG, J, MB)                                                                                \
   do {                                                                                                                \
@@ -212,6 +402,27 @@ static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
     else PGRF_CV_LAUNCH1(PL, SG, J, 5);                                                                               \
   } while (0)
   const int jb = g_cv_jb ? g_cv_jb : 2;   // B200 sweep (tools/time_cost_volume.py): 8 gathers in flight per lane, <= 102 registers
+  if (planar && C == 32 && p.groups == 0 && p.W % kCvThreads == 0 && g_cv_tma) {
+    // planar store through the TMA engine (see cost_volume_planar_tma_kernel)
+    const size_t smem_t = (size_t)kCvWarps * 2 * kCvWarpTileBytes + (size_t)kCvWarps * p.n_src * 32 * sizeof(TapRec);
+    CUtensorMap tmap;
+    const int trc = make_out_tensor_map(p, &tmap);
+    if (trc != PGRF_OK) return trc;
+#define PGRF_CV_TMA(SG, J, MB)                                                                                        \
+  do {                                                                                                                \
+    PGRF_CUDA(cudaFuncSetAttribute(cost_volume_planar_tma_kernel<SG, J, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+    cost_volume_planar_tma_kernel<SG, J, MB><<<grid, kCvThreads, smem_t, st>>>(p, tmap);                              \
+  } while (0)
+    if (!single) PGRF_CV_TMA(false, 2, 5);
+    else if (jb == 4) PGRF_CV_TMA(true, 4, 4);
+    else if (g_cv_minb == 6) PGRF_CV_TMA(true, 2, 6);
+    else if (g_cv_minb == 4) PGRF_CV_TMA(true, 2, 4);
+    else PGRF_CV_TMA(true, 2, 5);
+#undef PGRF_CV_TMA
+    count_launch();
+    PGRF_CUDA(cudaGetLastError());
+    return PGRF_OK;
+  }
   if (planar) {
     if (!single) PGRF_CV_LAUNCH(true, false, 2);
     else if (jb == 4) PGRF_CV_LAUNCH(true, true, 4);
@@ -239,6 +450,8 @@ extern "C" int pgrf_debug_set(const char* key, int value) {
   if (!strcmp(key, "cv_jb")) { g_cv_jb = value; return PGRF_OK; }
   if (!strcmp(key, "cv_dchunk")) { g_cv_dchunk = value; return PGRF_OK; }
   if (!strcmp(key, "cv_minb")) { g_cv_minb = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_tma")) { g_cv_tma = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_pad_smem")) { g_cv_pad_smem = value; return PGRF_OK; }
   set_error("pgrf_debug_set: unknown key %s", key);
   return PGRF_EINVAL;
 }

@@ -119,6 +119,29 @@ __device__ __forceinline__ void point_uv(int dataset, float cx, float cy, float 
   v = 2.f * vv * kInvPi - 1.f;
 }
 
+// Bilinear blend of one 2x2 footprint (ATen's accumulation order nw, ne, sw, se) of 4 channels and the matching cost against the
+// reference feature (`rf` holds -reference for abs_diff, so the difference is one packed add).  Packed fp32 pairs: mul/fma.rn.f32x2 perform the same IEEE operations as the scalar chain
+// (bit-identical results) in half the issue slots — the sweep is issue bound (ncu: time proportional to executed instructions).
+__device__ __forceinline__ float4 blend_cost(const float4& nw, const float4& ne, const float4& sw, const float4& se, float tx, float ty,
+                                             const float4& rf, int cost_type) {
+  const float tx1 = 1.f - tx, ty1 = 1.f - ty;   // exact: == (x0+1)-ix, (y0+1)-iy
+  const float2 wn = fmul2(make_float2(tx1, tx), make_float2(ty1, ty1));     // (wnw, wne)
+  const float2 ws = fmul2(make_float2(tx1, tx), make_float2(ty, ty));       // (wsw, wse)
+  const float2 w0 = make_float2(wn.x, wn.x), w1 = make_float2(wn.y, wn.y), w2 = make_float2(ws.x, ws.x), w3 = make_float2(ws.y, ws.y);
+  float2 lo = fmul2(make_float2(nw.x, nw.y), w0), hi = fmul2(make_float2(nw.z, nw.w), w0);
+  lo = ffma2(make_float2(ne.x, ne.y), w1, lo); hi = ffma2(make_float2(ne.z, ne.w), w1, hi);
+  lo = ffma2(make_float2(sw.x, sw.y), w2, lo); hi = ffma2(make_float2(sw.z, sw.w), w2, hi);
+  lo = ffma2(make_float2(se.x, se.y), w3, lo); hi = ffma2(make_float2(se.z, se.w), w3, hi);
+  if (cost_type == PGRF_COST_ABS_DIFF) {
+    lo = fadd2(lo, make_float2(rf.x, rf.y)); hi = fadd2(hi, make_float2(rf.z, rf.w));
+    return make_float4(fabsf(lo.x), fabsf(lo.y), fabsf(hi.x), fabsf(hi.y));
+  }
+  if (cost_type == PGRF_COST_DOT) {
+    lo = fmul2(lo, make_float2(rf.x, rf.y)); hi = fmul2(hi, make_float2(rf.z, rf.w));
+  }
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // Relative pose of swept view `slot` w.r.t. the reference view, in fp64, rounded once to fp32:
 // dst[0..8] = A = R_s * R_ref^-1 (row-major), dst[9..11] = b = t_s - A t_ref   (spherical_cost_volume.py:139-150)
 __device__ __forceinline__ void relative_pose(const CvParams& p, int b, int slot, float* dst) {

@@ -12,7 +12,65 @@ import torch
 
 from . import _lib
 
-_CHECK_UV = True   # the reference asserts uv in [-1,1] after every depth (:191); we check one flag per call
+#: How the reference's `assert uv in [-1, 1]` (one host sync per depth, :191) is honoured:
+#:   "deferred" (default)  the kernel ORs a device flag; the flag travels to pinned host memory asynchronously and is looked at
+#:                         — without ever blocking the stream — at the next cost-volume call or at `check_pending()`; a violation
+#:                         raises the reference's AssertionError there (asynchronous error reporting, like CUDA's own);
+#:   "sync"                read the flag back before returning (one host sync per call);
+#:   "off"                 never look at it.
+UV_CHECK = "deferred"
+_CHECK_UV = True          # legacy switch (False == "off")
+_RING = 256
+
+
+class _UvChecks:
+    """Per-device ring of device flags + pinned host mirrors + events: deferred, non-blocking range assertion."""
+
+    def __init__(self):
+        self.dev = {}
+
+    def slot(self, device):
+        st = self.dev.get(device)
+        if st is None:
+            st = self.dev[device] = {"flags": torch.zeros(_RING, device=device, dtype=torch.int32),
+                                     "host": torch.zeros(_RING, dtype=torch.int32).pin_memory(), "next": 0, "pending": []}
+        if len(st["pending"]) >= _RING - 1:
+            self.drain(device, block=True)
+        i = st["next"]
+        st["next"] = (i + 1) % _RING
+        return st, i
+
+    def queue(self, st, i):
+        st["host"][i:i + 1].copy_(st["flags"][i:i + 1], non_blocking=True)
+        st["flags"][i:i + 1].zero_()                       # stream-ordered after the copy: the slot is clean when reused
+        ev = torch.cuda.Event()
+        ev.record()
+        st["pending"].append((ev, i))
+
+    def drain(self, device=None, block=False):
+        for d, st in self.dev.items():
+            if device is not None and d != device:
+                continue
+            keep, bad = [], False
+            for ev, i in st["pending"]:
+                if block:
+                    ev.synchronize()
+                if ev.query():
+                    bad = bad or int(st["host"][i]) != 0
+                else:
+                    keep.append((ev, i))
+            st["pending"] = keep
+            if bad:
+                raise AssertionError("Wrong UV mapping, UV must be in [-1, 1]!")
+
+
+_uv = _UvChecks()
+
+
+def check_pending(block=True):
+    """Look at the deferred uv-range flags of earlier cost-volume calls (block=True waits for them first); raises the
+    reference's AssertionError if any call produced a uv outside [-1, 1]."""
+    _uv.drain(None, block)
 
 
 class _SweepFn(torch.autograd.Function):
@@ -32,7 +90,13 @@ class _SweepFn(torch.autograd.Function):
             store = torch.empty((B, D, H, W, OC), device=dev, dtype=torch.float32)
         else:
             store = torch.empty((B, OC, D, H, W), device=dev, dtype=torch.float32)
-        err = torch.zeros(1, device=dev, dtype=torch.int32)
+        mode = UV_CHECK if _CHECK_UV else "off"
+        if mode == "deferred":
+            _uv.drain(dev, block=False)                    # raise for an EARLIER call whose flag has arrived
+            st, slot = _uv.slot(dev)
+            err = st["flags"][slot:slot + 1]
+        else:
+            err = torch.zeros(1, device=dev, dtype=torch.int32)
         views = (ctypes.c_int * len(meta["src_views"]))(*meta["src_views"])
         with torch.cuda.device(dev):
             rc = lib.pgrf_cost_volume_fwd(
@@ -41,7 +105,9 @@ class _SweepFn(torch.autograd.Function):
                 meta["dataset"], meta["cost"], _lib.CV_LAYOUT_IDS[out_layout], groups,
                 _lib.ptr(store), _lib.ptr(err), _lib.stream_ptr())
         _lib.check(rc, "pgrf_cost_volume_fwd")
-        if _CHECK_UV and int(err.item()) != 0:
+        if mode == "deferred":
+            _uv.queue(st, slot)
+        elif mode == "sync" and int(err.item()) != 0:
             raise AssertionError("Wrong UV mapping, UV must be in [-1, 1]!")
         ctx.meta = meta
         ctx.save_for_backward(images, depth_t, rots, trans)

@@ -164,9 +164,25 @@ def test_uv_range_assert_and_errors():
     images = torch.randn(1, 2, 8, 32, 8, device="cuda")
     rots = torch.eye(3, device="cuda").expand(1, 2, 3, 3).contiguous()
     trans = torch.zeros(1, 2, 3, device="cuda")
-    # depth 0 with identical poses -> radius 0 -> NaN uv -> the reference's assert (:191) fires
+    from panogrf_b200 import spherical_cost_volume as scv
+    # depth 0 with identical poses -> radius 0 -> NaN uv -> the reference's assert (:191) fires.
+    # default ("deferred"): the call itself never blocks; the flag is looked at by check_pending() or by the next call
+    scv.check_pending()
+    pg.calculate_cost_volume_erp(args, images, torch.zeros(2, device="cuda"), trans, rots)
     with pytest.raises(AssertionError, match="Wrong UV mapping"):
-        pg.calculate_cost_volume_erp(args, images, torch.zeros(2, device="cuda"), trans, rots)
+        scv.check_pending()
+    scv.check_pending()                                   # reported once
+    pg.calculate_cost_volume_erp(args, images, torch.zeros(2, device="cuda"), trans, rots)
+    torch.cuda.synchronize()
+    with pytest.raises(AssertionError, match="Wrong UV mapping"):
+        pg.calculate_cost_volume_erp(args, images, torch.ones(2, device="cuda"), trans, rots)   # the NEXT call raises
+    scv.check_pending()
+    try:                                                  # "sync": the reference's behaviour, one host sync per call
+        scv.UV_CHECK = "sync"
+        with pytest.raises(AssertionError, match="Wrong UV mapping"):
+            pg.calculate_cost_volume_erp(args, images, torch.zeros(2, device="cuda"), trans, rots)
+    finally:
+        scv.UV_CHECK = "deferred"
     with pytest.raises(ValueError):
         pg.calculate_cost_volume_erp(args, images, torch.ones(2, device="cuda"), trans, rots, cost_type="ssd")
     with pytest.raises(Exception):
@@ -269,3 +285,33 @@ def test_backward_full_size_properties():
     out2.sum().backward()
     g2 = images2.grad
     assert abs(float(g2[:, 0].double().sum()) + float(g2[:, 1].double().sum())) <= 1e-3 * float(g2[:, 1].double().abs().sum())
+
+
+@pytest.mark.parametrize("layout", ["bdchw", "bcdhw"])
+@pytest.mark.parametrize("mv", [False, True])
+def test_planar_tma_store_path_is_bit_identical(layout, mv):
+    """W % 128 == 0, C = 32: the planar layouts can leave through the TMA engine (register transpose + swizzled warp tile +
+    cp.async.bulk.tensor.5d, csrc/cost_volume.cu: cost_volume_planar_tma_kernel; opt-in, debug knob cv_tma).  Same arithmetic as
+    the LSU path -> identical bits,
+    incl. per-pixel depth volumes, a ragged last depth chunk and the multi-view mean."""
+    import panogrf_b200 as pg
+    from panogrf_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, S, H, W, C, D = 2, (4 if mv else 2), 16, 256, 32, 11
+    images = torch.randn(B, S, H, W, C, device="cuda", generator=g)
+    rots = cases.small_rotations(torch.Generator().manual_seed(1), B, S, 4.0).cuda()
+    trans = (torch.randn(B, S, 3, generator=torch.Generator().manual_seed(2)) * 0.3).cuda()
+    dvol = (0.5 + 8.0 * torch.rand(B, D, H, W, device="cuda", generator=g)).sort(dim=1).values
+    args = {"dataset_name": "m3d", "contain_dnet": True, "mono_uncertainty": False}
+    fn = pg.calculate_cost_volume_erp_multiview if mv else pg.calculate_cost_volume_erp
+    outs = {}
+    for tma in (1, 0):
+        _lib.check(lib.pgrf_debug_set(b"cv_tma", tma), "pgrf_debug_set")
+        try:
+            outs[tma] = fn(args, images, None, trans, rots, depth_volume=dvol, out_layout=layout).contiguous()
+            torch.cuda.synchronize()
+        finally:
+            lib.pgrf_debug_set(b"cv_tma", 0)
+    assert torch.equal(outs[1], outs[0])
+    assert float(outs[1].abs().sum()) > 0
