@@ -695,15 +695,17 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
   }
 }
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cached[dev & 63];
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
   }
-  return g_num_sms;
+  return n;
 }
 
 }  // namespace pgrf
@@ -782,12 +784,16 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
   cudaStream_t st = (cudaStream_t)stream;
   const int sms = num_sms();
   const size_t s1 = R1_FLOATS * sizeof(float), s2 = R2_FLOATS * sizeof(float), s3 = R3_FLOATS * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    PGRF_CUDA(cudaFuncSetAttribute(render_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-    PGRF_CUDA(cudaFuncSetAttribute(render_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-    PGRF_CUDA(cudaFuncSetAttribute(render_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
-    attr_done = true;
+  {   // the > 48 KB dynamic shared memory opt-in is a per-device function attribute
+    static bool attr_done[64] = {};
+    int dev = 0;
+    PGRF_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+      PGRF_CUDA(cudaFuncSetAttribute(render_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+      PGRF_CUDA(cudaFuncSetAttribute(render_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+      PGRF_CUDA(cudaFuncSetAttribute(render_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
+      attr_done[dev & 63] = true;
+    }
   }
   const int mask = a.stage_mask ? a.stage_mask : 7;
   if (a.mlp_bf16) {

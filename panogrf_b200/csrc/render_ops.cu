@@ -280,9 +280,12 @@ extern "C" int pgrf_composite_fwd(const float* density, const float* alpha, cons
                                   int depth_ray_stride, int rn, int dn, float* hit_prob, float* pixel_colors,
                                   float* render_depth, void* stream) {
   PGRF_REQUIRE((density != nullptr) != (alpha != nullptr), "composite: pass exactly one of density / alpha");
-  PGRF_REQUIRE(rn >= 1 && dn >= 1 && dn <= 4096, "composite: rn=%d dn=%d", rn, dn);
+  // 8 rays per CTA x 2 vectors of dn floats in shared memory: opt in above 48 KB, reject what no SM can hold (227 KB)
+  const size_t smem = 8 * 2 * (size_t)dn * sizeof(float);
+  PGRF_REQUIRE(rn >= 1 && dn >= 1 && smem <= 200 * 1024, "composite: rn=%d dn=%d (dn <= 3200)", rn, dn);
+  if (smem > 48 * 1024) PGRF_CUDA(cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (rn + 7) / 8 < 148 * 8 ? (rn + 7) / 8 : 148 * 8;
-  composite_kernel<<<grid, 256, 8 * 2 * dn * sizeof(float), (cudaStream_t)stream>>>(density, alpha, colors, depth, depth_ray_stride,
+  composite_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(density, alpha, colors, depth, depth_ray_stride,
                                                                                  hit_prob, pixel_colors, render_depth, rn, dn);
   count_launch();
   PGRF_CUDA(cudaGetLastError());

@@ -309,10 +309,12 @@ int launch_render_rays_bf16(const pgrf_render_args& a, int V, int T, long long t
   while ((1 << p.log2T) < T) ++p.log2T;
   p.rays_per_tile = a.dn >= RROWS ? 1 : RROWS / a.dn;
   p.n_tiles = (a.rn + p.rays_per_tile - 1) / p.rays_per_tile;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};   // per-device function attribute
+  int dev = 0;
+  PGRF_CUDA(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
     PGRF_CUDA(cudaFuncSetAttribute(render_rays_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMR_BYTES));
-    attr_done = true;
+    attr_done[dev & 63] = true;
   }
   const int grid = min((p.n_tiles + kWGr - 1) / kWGr, sms);
   render_rays_bf16_kernel<<<grid, kThreadsR, SMR_BYTES, st>>>(p);

@@ -7,7 +7,7 @@ import math
 import torch
 
 from . import _lib
-from .renderer import coarse_depth_table, fine_u_table, to_channels_last
+from .renderer import coarse_depth_table, fine_u_table, tensor_version, to_channels_last
 
 
 def _f32(t):
@@ -19,7 +19,10 @@ _CL_CACHE = {}
 
 def _channels_last_cached(name, t, pad_to=None):
     """NCHW -> channels-last copy, reused while the caller keeps passing the same unmodified tensor."""
-    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+    ver = tensor_version(t)
+    if ver is None:
+        return to_channels_last(t, pad_to)                  # untracked (inference-mode) tensor: never cached
+    key = (t.data_ptr(), ver, tuple(t.shape), str(t.device))
     hit = _CL_CACHE.get(name)
     if hit is None or hit[0] != key:
         _CL_CACHE[name] = (key, to_channels_last(t, pad_to), t)

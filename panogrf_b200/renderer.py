@@ -293,11 +293,29 @@ def fine_u_table(fdn):
 
 
 def to_channels_last(x, pad_to=None):
-    """(N,C,H,W) -> contiguous (N,H,W,C[+pad])."""
-    x = x.float().permute(0, 2, 3, 1)
-    if pad_to is not None and x.shape[-1] < pad_to:
-        x = torch.cat([x, x.new_zeros(*x.shape[:-1], pad_to - x.shape[-1])], -1)
-    return x.contiguous()
+    """(N,C,H,W) -> contiguous (N,H,W,C[+pad]) with the library's tiled transpose kernel (pgrf_nchw_to_nhwc: one launch per map,
+    coalesced on both sides; the torch permute + cat + contiguous chain it replaces cost 19 ms for the three maps of a
+    512x1024 view)."""
+    x = x.detach()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    _lib.require_cuda(x)
+    n, c, h, w = x.shape
+    cpad = max(c, int(pad_to or 0))
+    out = torch.empty((n, h, w, cpad), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().pgrf_nchw_to_nhwc(_lib.ptr(x), _lib.ptr(out), n, c, h, w, cpad, _lib.stream_ptr())
+    _lib.check(rc, "pgrf_nchw_to_nhwc")
+    return out
+
+
+def tensor_version(t):
+    """In-place version counter of a tensor, or None when it is not tracked (tensors created under torch.inference_mode):
+    such tensors are never cached."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
 
 
 class NeuralRayBaseRenderer(nn.Module):
@@ -314,6 +332,10 @@ class NeuralRayBaseRenderer(nn.Module):
     #: inter-kernel workspaces).  None = 131072 for the bf16 path (only the 272 B/sample F2 tiles exist; larger launches
     #: amortise the per-CTA weight load and the tail), 32768 for the fp32 path (F1 tiles: 38.9 KB per 64 samples, 1.3 GB of workspace).
     rays_per_launch = None
+    #: reuse the channels-last copies of the source maps while the caller passes the same, unmodified tensors (keyed on storage
+    #: pointer + in-place version).  Writes through `.data` do not bump the version: set False (or call invalidate_map_cache())
+    #: if the maps are updated that way.
+    cache_maps = True
 
     def __init__(self, cfg):
         super().__init__()
@@ -365,8 +387,14 @@ class NeuralRayBaseRenderer(nn.Module):
         return key
 
     def invalidate_weight_cache(self):
+        """Drop the packed weight blobs.  REQUIRED after updating parameters through `.data` (p.data.copy_, EMA updates,
+        nn.init.*(p.data)): such writes do not bump the version counter the cache key uses.  Optimizer steps, load_state_dict
+        and .to()/.cuda() are detected automatically."""
         self._param_lists.clear()
         self._blob_cache.clear()
+
+    def invalidate_map_cache(self):
+        self._cl_cache.clear()
 
     def _blob(self, fine, device):
         key = self._param_key(fine, device)
@@ -468,9 +496,10 @@ class NeuralRayBaseRenderer(nn.Module):
 
     def _cached_scalars(self, name, t):
         """(near, far) of a (1,2) depth_range tensor as python floats without a device sync on every call."""
-        key = (t.data_ptr(), t._version, str(t.device))
+        ver = tensor_version(t)
+        key = (t.data_ptr(), ver, str(t.device))
         hit = self._cl_cache.get(name)
-        if hit is None or hit[0] != key:
+        if ver is None or hit is None or hit[0] != key:
             v = t.detach().float().cpu()
             self._cl_cache[name] = (key, (float(v[0, 0]), float(v[0, 1])), t)
         return self._cl_cache[name][1]
@@ -489,8 +518,14 @@ class NeuralRayBaseRenderer(nn.Module):
             self._tables[k] = make().to(dev)
         return self._tables[k]
 
+    @staticmethod
+    def _ws_key(dev):
+        """Workspaces (inter-kernel tiles, tile counters) are per device AND per stream: two renders enqueued on different
+        streams of one device must not share them."""
+        return (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+
     def _sched(self, dev):
-        ws = self._ws.setdefault(str(dev), {})
+        ws = self._ws.setdefault(self._ws_key(dev), {})
         if ws.get("sched") is None:
             ws["sched"] = torch.zeros(4, device=dev, dtype=torch.int32)
         return ws["sched"]
@@ -498,7 +533,10 @@ class NeuralRayBaseRenderer(nn.Module):
     def _cached_cl(self, name, t, pad_to):
         """Channels-last copy of a source map, reused while the caller keeps passing the same (unmodified) tensor —
         the source panoramas do not change between the query poses of a video render (render.py:249-291)."""
-        key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+        ver = tensor_version(t)
+        if ver is None or not self.cache_maps:
+            return to_channels_last(t, pad_to)              # untracked (inference-mode) tensor or caching switched off
+        key = (t.data_ptr(), ver, tuple(t.shape), str(t.device))
         hit = self._cl_cache.get(name)
         if hit is None or hit[0] != key:
             self._cl_cache[name] = (key, to_channels_last(t, pad_to), t)      # keep `t` alive so data_ptr stays unique
@@ -538,7 +576,30 @@ class NeuralRayBaseRenderer(nn.Module):
                 _outs["que_depth_fine"][0, _r0:_r0 + rn] = fine_depth
         if own:
             self._post(_outs, depth_table, True)
+            self._add_gt(_outs, que_imgs_info, self._gt_suffixes())
         return _outs
+
+    def _add_gt(self, outs, que_imgs_info, suffixes=("",)):
+        """`pixel_colors_gt[_fine]` (+ `polar_weights`) of the reference's output dict (renderer.py:278-286, 398-405): the
+        query image sampled at the ray coordinates, interpolate_feats(align_corners=True).  network/metrics.py reads them."""
+        if "imgs" not in que_imgs_info and "cube_imgs" not in que_imgs_info:
+            return outs
+        from .render_ops import interpolate_feature_map
+        src = que_imgs_info["imgs"] if "imgs" in que_imgs_info else que_imgs_info["cube_imgs"]
+        coords = que_imgs_info["coords"]
+        gt = interpolate_feature_map(src, coords, src.shape[2], src.shape[3])          # full resolution -> align_corners=True
+        pw = None
+        if "imgs" in que_imgs_info and self.cfg.get("use_polar_weighted_loss"):
+            m = que_imgs_info["polar_weights"]
+            pw = interpolate_feature_map(m, coords, m.shape[2], m.shape[3])
+        for sfx in suffixes:
+            outs["pixel_colors_gt" + sfx] = gt
+            if pw is not None:
+                outs["polar_weights" + sfx] = pw
+        return outs
+
+    def _gt_suffixes(self):
+        return ("", "_fine") if self.cfg["use_hierarchical_sampling"] else ("",)
 
     def _needs_post(self):
         return bool(self.cfg.get("render_uncert")) or bool(self.cfg.get("render_c2f_all") and self.cfg["use_hierarchical_sampling"])
@@ -626,6 +687,7 @@ class NeuralRayBaseRenderer(nn.Module):
                                         float(self.cfg["max_depth"])), coords.device,
                                        lambda: coarse_depth_table(self.cfg, dn, self.cfg["use_disp"]))
             self._post(outs, table, keep_hit_prob)
+        self._add_gt(outs, que_imgs_info, self._gt_suffixes())
         return outs
 
     def _render_diner(self, que_imgs_info, ref_imgs_info, keep_hit_prob=False):
@@ -769,7 +831,7 @@ class NeuralRayBaseRenderer(nn.Module):
         f1n, f2n = ctypes.c_longlong(), ctypes.c_longlong()
         _lib.check(lib.pgrf_render_workspace(a.rfn, chunk * max(dn, fine_total), ctypes.byref(f1n), ctypes.byref(f2n)),
                    "pgrf_render_workspace")
-        ws = self._ws.setdefault(str(dev), {})
+        ws = self._ws.setdefault(self._ws_key(dev), {})
         if self.mlp_dtype == "bf16":
             f1n.value = 4                      # the fused tensor-core kernel has no F1 inter-kernel tiles
         for key, n in (("f1", f1n.value), ("f2", f2n.value), ("fine", chunk * max(fine_total, 1))):
@@ -856,7 +918,7 @@ class NeuralRayBaseRenderer(nn.Module):
             outs["ray_mask"] = torch.full((1, rn), bool(ok), device=dev)
         if not self.cfg["render_depth"]:
             outs.pop("render_depth")
-        return outs
+        return self._add_gt(outs, que_imgs_info)
 
     def forward(self, data, is_perspec=False):
         que = dict(data["que_imgs_info"])

@@ -137,3 +137,28 @@ def test_gen_renderer_forward_and_registry():
     assert_close(out["depth_mean_fine_2"],
                  R.dist_decoder_forward(W, "fine_dist_decoder", feats, cfg["fine_dist_decoder_cfg"].get("use_vis", True))[0][..., 1],
                  rtol=1e-4, atol=1e-5, what="gen/depth_mean_fine_2")
+
+
+def test_render_emits_pixel_colors_gt_like_the_reference():
+    """renderer.py:278-286 / 398-405: whenever the query carries its image, the output dict has `pixel_colors_gt[_fine]`
+    (interpolate_feats(imgs, coords, align_corners=True)); network/metrics.py reads it.  Also: maps created under
+    torch.inference_mode (no version counter) must not crash the map cache."""
+    import torch.nn.functional as F
+    import panogrf_b200 as pg
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import cases
+    cfg, que, ref = cases.make_render_inputs("render_m3d_2src")
+    net = pg.NeuralRayBaseRenderer(cfg).cuda().eval()
+    gen = torch.Generator().manual_seed(3)
+    h, w = int(cfg["height"]), int(cfg["width"])
+    qimg = torch.rand(1, 3, h, w, generator=gen)
+    que = {**{k: v.cuda() for k, v in que.items()}, "imgs": qimg.cuda()}
+    with torch.inference_mode():
+        ref_c = {k: (v.cuda() * 1.0) for k, v in ref.items()}        # inference tensors: `_version` raises on them
+    out = net.render(que, ref_c, False)
+    c = que["coords"].cpu()
+    grid = torch.stack([c[..., 0] / (w - 1) * 2 - 1, c[..., 1] / (h - 1) * 2 - 1], -1)[:, None]
+    want = F.grid_sample(qimg, grid, mode="bilinear", padding_mode="border", align_corners=True)[:, :, 0].permute(0, 2, 1)
+    for k in ("pixel_colors_gt", "pixel_colors_gt_fine"):
+        assert k in out and float((out[k].cpu() - want).abs().max()) < 1e-5
+    assert bool(torch.isfinite(out["pixel_colors_nr_fine"]).all())
