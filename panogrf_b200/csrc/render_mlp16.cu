@@ -191,41 +191,58 @@ __device__ __forceinline__ float4 tap4_rec(const float4* __restrict__ base, cons
 }
 
 // ---- MMA issue (ONE thread).  All operands K-major, no swizzle, SBO = 128 B; a K = 16 step reads the two 8-element chunks at
-// `addr` and `addr + lbo` — an odd trailing chunk is paired with the shared zero chunk by choosing lbo = zero - addr. ----
+// `addr` and `addr + lbo` — an odd trailing chunk is paired with the shared zero chunk by choosing lbo = zero - addr.
+// The issuing thread is the critical path of every stage, so a descriptor costs ONE add: its low word is
+//   (addr >> 4) | (lbo >> 4) << 16  =  per-buffer base (computed once per kernel) + compile-time immediate,
+// with two bases per buffer: `n` for chunk pairs inside the buffer (constant lbo) and `z` for a chunk paired with the zero chunk
+// (lbo = zero - addr, i.e. base16 + ((z16 - base16) << 16), immediate off16 - (off16 << 16)). ----
 struct Issuer {
-  uint32_t sW, sZ, sO;   // shared-memory byte addresses: weight section, zero chunk, ones chunk
-  __device__ __forceinline__ void ss(uint32_t d, uint32_t a, uint32_t a_lbo, uint32_t b, uint32_t b_lbo, int N, uint32_t acc) const {
-    umma::mma_bf16(d, umma::smem_desc(a, a_lbo, 128), umma::smem_desc(b, b_lbo, 128), umma::instr_desc_bf16(128, N), acc);
+  uint32_t wn, wz;        // weight section
+  uint32_t xn, xz, yn, yz;   // the warpgroup's X / Y operand regions
+  uint32_t ones_lo;       // A = [ones | zero]
+  static constexpr uint64_t kHi = (uint64_t)0x4008 << 32;     // SBO = 128 B, descriptor version 1, no swizzle
+  __device__ __forceinline__ void init(uint32_t sW, uint32_t sX, uint32_t sY, uint32_t sO, uint32_t sZ) {
+    const uint32_t z16 = sZ >> 4;
+    wn = sW >> 4; wz = wn + ((z16 - wn) << 16);
+    xn = sX >> 4; xz = xn + ((z16 - xn) << 16);
+    yn = sY >> 4; yz = yn + ((z16 - yn) << 16);
+    ones_lo = (sO >> 4) + ((z16 - (sO >> 4)) << 16);
   }
-  __device__ __forceinline__ void ts(uint32_t d, uint32_t a_tmem, uint32_t b, uint32_t b_lbo, int N, uint32_t acc) const {
-    umma::mma_bf16_ts(d, a_tmem, umma::smem_desc(b, b_lbo, 128), umma::instr_desc_bf16(128, N), acc);
+  static __device__ __forceinline__ constexpr uint32_t imm_n(uint32_t off, uint32_t pitch) { return (off >> 4) | ((pitch >> 4) << 16); }
+  static __device__ __forceinline__ constexpr uint32_t imm_z(uint32_t off) { return (off >> 4) - ((off >> 4) << 16); }
+  __device__ __forceinline__ void ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, int N, uint32_t acc) const {
+    umma::mma_bf16(d, kHi | a_lo, kHi | b_lo, umma::instr_desc_bf16(128, N), acc);
   }
-  // A = NCH consecutive chunks of a shared-memory operand starting at `a` (row pitch 128), B = chunks [kc0, kc0 + NCH) of layer
-  // weights at `w` with Npad = N rows
-  template <int NCH>
-  __device__ __forceinline__ void smem_chunks(uint32_t d, uint32_t a, uint32_t w, int kc0, int N, uint32_t acc_first) const {
+  __device__ __forceinline__ void ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, int N, uint32_t acc) const {
+    umma::mma_bf16_ts(d, a_tmem, kHi | b_lo, umma::instr_desc_bf16(128, N), acc);
+  }
+  // A = NCH consecutive chunks of the X (AX = true) or Y operand region starting at byte offset `a_off`, B = chunks
+  // [kc0, kc0 + NCH) of the layer at byte offset `w_off` of the weight section (Npad = N rows)
+  template <int NCH, bool AX>
+  __device__ __forceinline__ void smem_chunks(uint32_t d, uint32_t a_off, uint32_t w_off, int kc0, int N, uint32_t acc_first) const {
     const uint32_t wp = (uint32_t)N * 16;
+    const uint32_t an = AX ? xn : yn, az = AX ? xz : yz;
 #pragma unroll
     for (int c = 0; c < NCH; c += 2) {
-      const uint32_t aa = a + c * CH, bb = w + (kc0 + c) * wp;
-      if (c + 1 < NCH) ss(d, aa, CH, bb, wp, N, (c > 0) ? 1u : acc_first);
-      else ss(d, aa, sZ - aa, bb, sZ - bb, N, (c > 0) ? 1u : acc_first);
+      const uint32_t ao = a_off + c * CH, bo = w_off + (kc0 + c) * wp;
+      if (c + 1 < NCH) ss(d, an + imm_n(ao, CH), wn + imm_n(bo, wp), N, (c > 0) ? 1u : acc_first);
+      else ss(d, az + imm_z(ao), wz + imm_z(bo), N, (c > 0) ? 1u : acc_first);
     }
   }
   // A = NCH chunks held in tensor memory (4 columns per chunk) starting at column address `a_tmem`
   template <int NCH>
-  __device__ __forceinline__ void tmem_chunks(uint32_t d, uint32_t a_tmem, uint32_t w, int kc0, int N, uint32_t acc_first) const {
+  __device__ __forceinline__ void tmem_chunks(uint32_t d, uint32_t a_tmem, uint32_t w_off, int kc0, int N, uint32_t acc_first) const {
     static_assert(NCH % 2 == 0, "tensor-memory operands are written in whole K = 16 steps");
     const uint32_t wp = (uint32_t)N * 16;
 #pragma unroll
-    for (int c = 0; c < NCH; c += 2) ts(d, a_tmem + 4 * c, w + (kc0 + c) * wp, wp, N, (c > 0) ? 1u : acc_first);
+    for (int c = 0; c < NCH; c += 2) ts(d, a_tmem + 4 * c, wn + imm_n(w_off + (kc0 + c) * wp, wp), N, (c > 0) ? 1u : acc_first);
   }
   // tensor-memory operand whose SECOND chunk is absent (K = 8 real columns): B pairs the weight chunk with the zero chunk
-  __device__ __forceinline__ void tmem_half(uint32_t d, uint32_t a_tmem, uint32_t w, int N, uint32_t acc) const {
-    ts(d, a_tmem, w, sZ - w, N, acc);
+  __device__ __forceinline__ void tmem_half(uint32_t d, uint32_t a_tmem, uint32_t w_off, int N, uint32_t acc) const {
+    ts(d, a_tmem, wz + imm_z(w_off), N, acc);
   }
   // + bias: A = [ones | zero], B = [bias chunk | zero]
-  __device__ __forceinline__ void bias(uint32_t d, uint32_t bchunk, int N) const { ss(d, sO, sZ - sO, bchunk, sZ - bchunk, N, 1u); }
+  __device__ __forceinline__ void bias(uint32_t d, uint32_t b_off, int N) const { ss(d, ones_lo, wz + imm_z(b_off), N, 1u); }
 };
 
 // weighted mean / variance over the V views of sample t (fused_mean_variance, ibrnet.py:112-116) of the 40-wide
@@ -321,8 +338,9 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
   const uint32_t tq = tb + ((uint32_t)(wq * 32) << 16);       // + this warp's lane quadrant
   uint32_t phase = 0;
   Issuer is;
-  is.sW = umma::smem_addr(Wb); is.sZ = umma::smem_addr(smem + SM16_ZERO); is.sO = umma::smem_addr(smem + SM16_ONES);
-  const uint32_t sX = umma::smem_addr(X), sY = umma::smem_addr(Y);
+  is.init(__shfl_sync(0xffffffffu, umma::smem_addr(Wb), 0), __shfl_sync(0xffffffffu, umma::smem_addr(X), 0),
+          __shfl_sync(0xffffffffu, umma::smem_addr(Y), 0), __shfl_sync(0xffffffffu, umma::smem_addr(smem + SM16_ONES), 0),
+          __shfl_sync(0xffffffffu, umma::smem_addr(smem + SM16_ZERO), 0));
 
   const int T = p.T, M = p.M;
   const int v = min(m / T, V - 1), t = m % T;
@@ -360,6 +378,9 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       static_tile += gridDim.x * kWG;
     }
     if (tile >= p.n_tiles) break;
+    // keep the descriptor bases opaque per tile: otherwise the compiler hoists all ~140 "base + immediate" sums out of the tile
+    // loop and spills them (they cost one add each where they are used)
+    asm volatile("" : "+r"(is.wn), "+r"(is.wz), "+r"(is.xn), "+r"(is.xz), "+r"(is.yn), "+r"(is.yz), "+r"(is.ones_lo));
     long long g = (long long)tile * T + t;
     const bool row_valid = (m < M) && (g < p.total);
     if (g >= p.total) g = p.total - 1;
@@ -400,7 +421,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // ------------------------------------------------------------ stage 0: ray_dir_fc.0 (runs under the gathers)
     SYNC_TMEM()      // also publishes the footprint records to the warpgroup
     ISSUE_BEGIN()
-      is.tmem_half(tb + C_RD0, tb + T_RDIN, is.sW + W16(M_RD0), 16, 0u);
+      is.tmem_half(tb + C_RD0, tb + T_RDIN, W16(M_RD0), 16, 0u);
     ISSUE_END()
 
     // ------------------------------------------------------------ cooperative gathers (lane = (row, float4 group))
@@ -432,9 +453,9 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // ------------------------------------------------------------ stage 1: mean_decoder.0, var_decoder.0, ray_dir_fc.2
     SYNC_BOTH()
     ISSUE_BEGIN()
-      is.smem_chunks<4>(tb + C_MEAN0, sX, is.sW + W16(M_MEAN0), 0, 32, 0u); is.bias(tb + C_MEAN0, is.sW + BC16(M_MEAN0), 32);
-      is.smem_chunks<4>(tb + C_VAR0, sX, is.sW + W16(M_VAR0), 0, 32, 0u);   is.bias(tb + C_VAR0, is.sW + BC16(M_VAR0), 32);
-      is.tmem_chunks<2>(tb + C_RD1, tb + T_HRD, is.sW + W16(M_RD1), 0, 48, 0u); is.bias(tb + C_RD1, is.sW + BC16(M_RD1), 48);
+      is.smem_chunks<4, true>(tb + C_MEAN0, 0, W16(M_MEAN0), 0, 32, 0u); is.bias(tb + C_MEAN0, BC16(M_MEAN0), 32);
+      is.smem_chunks<4, true>(tb + C_VAR0, 0, W16(M_VAR0), 0, 32, 0u);   is.bias(tb + C_VAR0, BC16(M_VAR0), 32);
+      is.tmem_chunks<2>(tb + C_RD1, tb + T_HRD, W16(M_RD1), 0, 48, 0u); is.bias(tb + C_RD1, BC16(M_RD1), 48);
     ISSUE_END()
     WAIT_MMA()
     epi_elu2p_tmem(tq, C_MEAN0, T_H0);
@@ -462,37 +483,49 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // ------------------------------------------------------------ stage 2: mean_decoder.2, var_decoder.2, aw_decoder.0
     SYNC_BOTH()
     ISSUE_BEGIN()
-      is.tmem_chunks<4>(tb + C_MEAN1, tb + T_H0, is.sW + W16(M_MEAN1), 0, 32, 0u); is.bias(tb + C_MEAN1, is.sW + BC16(M_MEAN1), 32);
-      is.tmem_chunks<4>(tb + C_VAR1, tb + T_H1, is.sW + W16(M_VAR1), 0, 32, 0u);   is.bias(tb + C_VAR1, is.sW + BC16(M_VAR1), 32);
-      is.smem_chunks<4>(tb + C_AW0, sX, is.sW + W16(M_AW0), 0, 32, 0u);            is.bias(tb + C_AW0, is.sW + BC16(M_AW0), 32);
+      is.tmem_chunks<4>(tb + C_MEAN1, tb + T_H0, W16(M_MEAN1), 0, 32, 0u); is.bias(tb + C_MEAN1, BC16(M_MEAN1), 32);
+      is.tmem_chunks<4>(tb + C_VAR1, tb + T_H1, W16(M_VAR1), 0, 32, 0u);   is.bias(tb + C_VAR1, BC16(M_VAR1), 32);
+      is.smem_chunks<4, true>(tb + C_AW0, 0, W16(M_AW0), 0, 32, 0u);            is.bias(tb + C_AW0, BC16(M_AW0), 32);
     ISSUE_END()
     WAIT_MMA()
     float mean[2], var[2], aw, visd = 1.f;
+    // aw_decoder.0's hidden first: it is the only input of stage 3, whose MMAs then run under the two output-layer epilogues below
+    epi_elu2p_tmem(tq, C_AW0, T_H2);
+    // ------------------------------------------------------------ stage 3: aw_decoder.2 (+ vis_decoder.0)
+    SYNC_TMEM()
+    // without the vis decoder the accumulator takes aw_decoder.0's columns (just consumed): mean/var accumulators stay readable
+    const int c_aw1 = a.use_vis ? C_AW1 : C_AW0;
+    if (!a.use_vis) {
+      ISSUE_BEGIN()
+        is.tmem_chunks<4>(tb + C_AW0, tb + T_H2, W16(M_AW1), 0, 32, 0u); is.bias(tb + C_AW0, BC16(M_AW1), 32);
+      ISSUE_END()
+    }
     {
       float o2[2];
       epi_elu2p_gemv<2>(tq, C_MEAN1, Wsm + SMW(M_MEAN2), o2);
       mean[0] = softplus_fast(o2[0] + Wsm[SMB(M_MEAN2)]); mean[1] = softplus_fast(o2[1] + Wsm[SMB(M_MEAN2) + 1]);
       epi_elu2p_gemv<2>(tq, C_VAR1, Wsm + SMW(M_VAR2), o2);
       var[0] = softplus_fast(o2[0] + Wsm[SMB(M_VAR2)]) + a.bias_val; var[1] = softplus_fast(o2[1] + Wsm[SMB(M_VAR2) + 1]) + a.bias_val;
-      epi_elu2p_tmem(tq, C_AW0, T_H2);
     }
-    // ------------------------------------------------------------ stage 3: aw_decoder.2 (+ vis_decoder.0)
-    SYNC_TMEM()
-    ISSUE_BEGIN()
-      is.tmem_chunks<4>(tb + C_AW1, tb + T_H2, is.sW + W16(M_AW1), 0, 32, 0u); is.bias(tb + C_AW1, is.sW + BC16(M_AW1), 32);
-      if (a.use_vis) { is.smem_chunks<4>(tb + C_VIS0, sX, is.sW + W16(M_VIS0), 0, 32, 0u); is.bias(tb + C_VIS0, is.sW + BC16(M_VIS0), 32); }
-    ISSUE_END()
+    if (a.use_vis) {
+      umma::fence_before_sync();
+      wg_sync(wg);                 // every thread has read the mean / var accumulators that stage 3 overwrites
+      ISSUE_BEGIN()
+        is.tmem_chunks<4>(tb + C_AW1, tb + T_H2, W16(M_AW1), 0, 32, 0u); is.bias(tb + C_AW1, BC16(M_AW1), 32);
+        is.smem_chunks<4, true>(tb + C_VIS0, 0, W16(M_VIS0), 0, 32, 0u); is.bias(tb + C_VIS0, BC16(M_VIS0), 32);
+      ISSUE_END()
+    }
     WAIT_MMA()
     {
       float o1[1];
-      epi_elu2p_gemv<1>(tq, C_AW1, Wsm + SMW(M_AW2), o1);
+      epi_elu2p_gemv<1>(tq, c_aw1, Wsm + SMW(M_AW2), o1);
       aw = sigmoidf(o1[0] + Wsm[SMB(M_AW2)]);
     }
     if (a.use_vis) {   // 4th decoder
       epi_elu2p_tmem(tq, C_VIS0, T_H3);
       SYNC_TMEM()
       ISSUE_BEGIN()
-        is.tmem_chunks<4>(tb + C_VIS1, tb + T_H3, is.sW + W16(M_VIS1), 0, 32, 0u); is.bias(tb + C_VIS1, is.sW + BC16(M_VIS1), 32);
+        is.tmem_chunks<4>(tb + C_VIS1, tb + T_H3, W16(M_VIS1), 0, 32, 0u); is.bias(tb + C_VIS1, BC16(M_VIS1), 32);
       ISSUE_END()
       WAIT_MMA()
       float o1[1];
@@ -526,8 +559,8 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // ------------------------------------------------------------ prob_embed 34 -> 32 (ReLU) -> 32
     SYNC_TMEM()
     ISSUE_BEGIN()
-      is.smem_chunks<4>(tb + C_PE0, sX, is.sW + W16(M_PE0), 0, 32, 0u);
-      is.tmem_half(tb + C_PE0, tb + T_HVT, is.sW + W16(M_PE0) + 4 * 32 * 16, 32, 1u);
+      is.smem_chunks<4, true>(tb + C_PE0, 0, W16(M_PE0), 0, 32, 0u);
+      is.tmem_half(tb + C_PE0, tb + T_HVT, W16(M_PE0) + 4 * 32 * 16, 32, 1u);
     ISSUE_END()
     WAIT_MMA()
     {
@@ -540,7 +573,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     }
     SYNC_TMEM()
     ISSUE_BEGIN()
-      is.tmem_chunks<4>(tb + C_PE1, tb + T_HPE, is.sW + W16(M_PE1), 0, 32, 0u); is.bias(tb + C_PE1, is.sW + BC16(M_PE1), 32);
+      is.tmem_chunks<4>(tb + C_PE1, tb + T_HPE, W16(M_PE1), 0, 32, 0u); is.bias(tb + C_PE1, BC16(M_PE1), 32);
     ISSUE_END()
     WAIT_MMA()
     {   // prob_embedding (no activation) -> tensor memory: operand of base_fc.0 and neuray_fc.0
@@ -555,10 +588,10 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // then the pooled K-blocks in two accumulating slices (uniform weights first: they do not need neuray_fc)
     SYNC_TMEM()
     ISSUE_BEGIN()
-      is.tmem_chunks<4>(tb + C_NF0, tb + T_PEMB, is.sW + W16(M_NF0), 0, 16, 0u); is.bias(tb + C_NF0, is.sW + BC16(M_NF0), 16);
-      is.smem_chunks<5>(tb + C_BASE0, sY, is.sW + W16(M_BASE0), 20, 64, 0u);
-      is.tmem_chunks<4>(tb + C_BASE0, tb + T_PEMB, is.sW + W16(M_BASE0), 25, 64, 1u);
-      is.bias(tb + C_BASE0, is.sW + BC16(M_BASE0), 64);
+      is.tmem_chunks<4>(tb + C_NF0, tb + T_PEMB, W16(M_NF0), 0, 16, 0u); is.bias(tb + C_NF0, BC16(M_NF0), 16);
+      is.smem_chunks<5, false>(tb + C_BASE0, 0, W16(M_BASE0), 20, 64, 0u);
+      is.tmem_chunks<4>(tb + C_BASE0, tb + T_PEMB, W16(M_BASE0), 25, 64, 1u);
+      is.bias(tb + C_BASE0, BC16(M_BASE0), 64);
     ISSUE_END()
     float w0n[V];
 #pragma unroll
@@ -575,8 +608,8 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     }
     SYNC_SMEM()
     ISSUE_BEGIN()
-      is.smem_chunks<5>(tb + C_BASE0, sX, is.sW + W16(M_BASE0), 10, 64, 1u);              // mean1 (uniform)
-      is.smem_chunks<5>(tb + C_BASE0, sX + 5 * CH, is.sW + W16(M_BASE0), 15, 64, 1u);     // var1
+      is.smem_chunks<5, true>(tb + C_BASE0, 0, W16(M_BASE0), 10, 64, 1u);              // mean1 (uniform)
+      is.smem_chunks<5, true>(tb + C_BASE0, 5 * CH, W16(M_BASE0), 15, 64, 1u);     // var1
     ISSUE_END()
 #pragma unroll
     for (int vv = 0; vv < V; ++vv) w0n[vv] = SF[SF_W0 * ROWS + vv * T + t] * wgt;
@@ -584,8 +617,8 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     pool_views<V>(Y, X, t, T, vrow, w0n);
     SYNC_SMEM()
     ISSUE_BEGIN()
-      is.smem_chunks<5>(tb + C_BASE0, sX, is.sW + W16(M_BASE0), 0, 64, 1u);               // mean0 (neuray-weighted)
-      is.smem_chunks<5>(tb + C_BASE0, sX + 5 * CH, is.sW + W16(M_BASE0), 5, 64, 1u);      // var0
+      is.smem_chunks<5, true>(tb + C_BASE0, 0, W16(M_BASE0), 0, 64, 1u);               // mean0 (neuray-weighted)
+      is.smem_chunks<5, true>(tb + C_BASE0, 5 * CH, W16(M_BASE0), 5, 64, 1u);      // var0
     ISSUE_END()
     WAIT_MMA()
     epi_elu2p_tmem(tq, C_BASE0, T_H64);
@@ -594,7 +627,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // ------------------------------------------------------------ base_fc.2 -> x (fp32, registers)
     SYNC_TMEM()
     ISSUE_BEGIN()
-      is.tmem_chunks<8>(tb + C_BASE1, tb + T_H64, is.sW + W16(M_BASE1), 0, 32, 0u); is.bias(tb + C_BASE1, is.sW + BC16(M_BASE1), 32);
+      is.tmem_chunks<8>(tb + C_BASE1, tb + T_H64, W16(M_BASE1), 0, 32, 0u); is.bias(tb + C_BASE1, BC16(M_BASE1), 32);
     ISSUE_END()
     WAIT_MMA()
     float x[32];
@@ -613,40 +646,44 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // ------------------------------------------------------------ vis_fc(x * weight) 32 -> 32 -> 33
     SYNC_TMEM()
     ISSUE_BEGIN()
-      is.tmem_chunks<4>(tb + C_VFC0, tb + T_HV, is.sW + W16(M_VFC0), 0, 32, 0u); is.bias(tb + C_VFC0, is.sW + BC16(M_VFC0), 32);
+      is.tmem_chunks<4>(tb + C_VFC0, tb + T_HV, W16(M_VFC0), 0, 32, 0u); is.bias(tb + C_VFC0, BC16(M_VFC0), 32);
     ISSUE_END()
     WAIT_MMA()
     epi_elu2p_tmem(tq, C_VFC0, T_HV2);
     SYNC_TMEM()
     ISSUE_BEGIN()
-      is.tmem_chunks<4>(tb + C_VFC1, tb + T_HV2, is.sW + W16(M_VFC1), 0, 48, 0u); is.bias(tb + C_VFC1, is.sW + BC16(M_VFC1), 48);
+      is.tmem_chunks<4>(tb + C_VFC1, tb + T_HV2, W16(M_VFC1), 0, 48, 0u); is.bias(tb + C_VFC1, BC16(M_VFC1), 48);
     ISSUE_END()
     WAIT_MMA()
     {
       float vr, vr1;
       umma::ld2(tq + C_VFC1 + 32, vr, vr1);
       const float vis1 = sigmoidf(elu_plain1(vr));   // vis = sigmoid(vis) * mask
-      float r[32];
-      ld32f(tq + C_VFC1, r);
-      uint32_t h[16], hx[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float2 xv = fadd2(make_float2(x[2 * i], x[2 * i + 1]), elu_plain2(r[2 * i], r[2 * i + 1]));   // x = x + x_res
-        x[2 * i] = xv.x; x[2 * i + 1] = xv.y;
-        XF[(2 * i) * ROWS + m] = xv.x;
-        XF[(2 * i + 1) * ROWS + m] = xv.y;
-        const float2 sv = fmul2(xv, make_float2(vis1, vis1));
-        h[i] = umma::pack2(sv.x, sv.y);
-        hx[i] = umma::pack2(xv.x, xv.y);
+      for (int half = 0; half < 2; ++half) {       // two halves of 16 columns: x[32] stays live, keep the rest of the working set small
+        float r[16];
+        umma::ld16(tq + C_VFC1 + 16 * half, r);
+        uint32_t h[8], hx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = 16 * half + 2 * i;
+          const float2 xv = fadd2(make_float2(x[k], x[k + 1]), elu_plain2(r[2 * i], r[2 * i + 1]));   // x = x + x_res
+          x[k] = xv.x; x[k + 1] = xv.y;
+          XF[k * ROWS + m] = xv.x;
+          XF[(k + 1) * ROWS + m] = xv.y;
+          const float2 sv = fmul2(xv, make_float2(vis1, vis1));
+          h[i] = umma::pack2(sv.x, sv.y);
+          hx[i] = umma::pack2(xv.x, xv.y);
+        }
+        umma::st8(tq + T_HVP + 8 * half, h);
+        umma::st8(tq + T_RGX + 8 * half, hx);
       }
-      st16(tq + T_HVP, h);
-      st16(tq + T_RGX, hx);
     }
     // ------------------------------------------------------------ vis_fc2(x * vis) 32 -> 32 -> 1 and the x K-block of rgb_fc.0
     SYNC_TMEM()
     ISSUE_BEGIN()
-      is.tmem_chunks<4>(tb + C_V2, tb + T_HVP, is.sW + W16(M_V2_0), 0, 32, 0u); is.bias(tb + C_V2, is.sW + BC16(M_V2_0), 32);
-      is.tmem_chunks<4>(tb + C_RGB0, tb + T_RGX, is.sW + W16(M_RGB0), 0, 16, 0u);
+      is.tmem_chunks<4>(tb + C_V2, tb + T_HVP, W16(M_V2_0), 0, 32, 0u); is.bias(tb + C_V2, BC16(M_V2_0), 32);
+      is.tmem_chunks<4>(tb + C_RGB0, tb + T_RGX, W16(M_RGB0), 0, 16, 0u);
     ISSUE_END()
     WAIT_MMA()
     {
@@ -663,7 +700,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     // ------------------------------------------------------------ rgb_fc.0 tail, overlapped with view pooling #2
     SYNC_TMEM()      // also publishes XF and SF_VIS2 to the warpgroup (generic reads: no proxy fence)
     ISSUE_BEGIN()
-      is.tmem_half(tb + C_RGB0, tb + T_RGT, is.sW + W16(M_RGB0) + 4 * 16 * 16, 16, 1u);
+      is.tmem_half(tb + C_RGB0, tb + T_RGT, W16(M_RGB0) + 4 * 16 * 16, 16, 1u);
     ISSUE_END()
     if (vrow < V) {   // weights = vis / (sum + 1e-8), mean / var of x over views, mean of weights -> the rays kernel's A operand
       const long long gs = (long long)tile * T + t;
