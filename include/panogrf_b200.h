@@ -169,6 +169,9 @@ typedef struct pgrf_render_args {
   const float* interval_in;    /* (rn*dn) que_dists of depth2inv_dists (render_ops.py:110-122); `depth` may then be NULL
                                   (no render_depth / fine sampling) */
   float* dec_dbg;              /* optional OUTPUT (rfn, rn*dn, 6): mean[2], var[2], vis, aw of the dist decoder */
+  /* ablation switches of DefaultAggregationNet (network/aggregate_net.py:60-62, 79-81) */
+  int wo_geometry;             /* agg_net_cfg.wo_geometry: prob_embedding = 0 */
+  int wo_appearance;           /* agg_net_cfg.wo_appearance: [rgb, img_feats] of every view = 0 (the blended colours are then 0) */
 } pgrf_render_args;
 /* Module-level entry ("agg_mlp_fwd"): the aggregation network + ray transformer + compositing on
  * caller-provided per-row inputs (prj_in, feat_in, prob_in, que_dir_in required).  fp32. */
@@ -230,6 +233,17 @@ PGRF_API int pgrf_fine_sample_fwd(const float* depth, int depth_ray_stride, cons
  * with the reference's own ops so they are bit-identical). */
 PGRF_API int pgrf_depth_hypotheses_fwd(const float* ref_mu, int B, int h, int w, const float* k_sigma, int n_mono,
                                        const float* linear, int n_linear, float min_depth, float max_depth, float* out, void* stream);
+/* every variant of the builder (pipeline3_model.py:717-733, 774-815):
+ *   mono list  clamp(ref_mu + s * k_i): mono_mode 0 = k_table holds float32(k_i * fixed_sigma); 1 = s = max(ref_sigma, basic_sigma)
+ *              (mono_uncertainty, :731); 2 = (ref_sigma * k_i) * relaxation (:729); n_mono <= 16, 0 = none (n_samples == 0)
+ *   centres    centers_mode 0 = table `centers` (n_centers; linear :802 or inverse-linear :804, built by the host with the reference's
+ *              torch ops); 1 = per-pixel `revise_range` with `fixed_dist` (:784-799); 2 = none (`wo_hdh`)
+ *   sort_out   1: per-pixel ascending merge (:815); 0: mono list in k order (the `wo_hdh` branch does not sort)
+ * out (B, n_mono + n_centers, h, w). */
+PGRF_API int pgrf_depth_hypotheses2_fwd(const float* ref_mu, const float* ref_sigma, int B, int h, int w, const float* k_table,
+                                        int n_mono, int mono_mode, float basic_sigma, float relaxation, const float* centers,
+                                        int n_centers, int centers_mode, float fixed_dist, float min_depth, float max_depth,
+                                        int sort_out, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Depth-prior sample placement ("diner" branch of render_impl, network/renderer.py:570-600, :318-355):
@@ -280,6 +294,13 @@ PGRF_API int pgrf_project_gather_diner_fwd(const float* pts, long long pn, const
                                            const float* mvs_depth, const float* mvs_uncert, const float* mvs_normal, int map_h,
                                            int map_w, int img_h, int img_w, float* out_pix, float* out_depth, float* out_mu,
                                            float* out_uncert, float* out_normal, void* stream);
+
+/* depth2normal (network/orig_diner_depth2normal.py:7-110): prior normals of the depth-guided placement (cfg backface_culling):
+ * mvs_depth (N,1,H,W) at the ERP size of the spherical convention -> normal (N,3,H,W); zero rows above / below, longitude wrap,
+ * the reference's hole "cleaning" (lookup shifted away from neighbours whose x coordinate is 0), zero normal where depth == 0.
+ * raw_ws: N*H*W*3 floats, off_ws: N*H*W*2 bytes of workspace. */
+PGRF_API int pgrf_depth2normal_fwd(const float* mvs_depth, int N, int H, int W, int dataset, float* raw_ws, signed char* off_ws,
+                                   float* out_normal, void* stream);
 
 /* MixtureLogisticsDistDecoder.compute_prob (dist_decoder.py:113-140) with get_near_far_points(is_ref=True) (:6-51):
  * depth (rfn,n), interval (n) shared by all views or (rfn,n) when interval_per_view, mean/var (rfn,n,2), vis (rfn,n) or NULL

@@ -229,6 +229,46 @@ def mono_guided_hypotheses(ref_mu, k_list, fixed_sigma, min_depth, max_depth, n_
     return torch.sort(vol, dim=1)[0]
 
 
+def depth_hypotheses(args, ref_gmms, k_list, cost_volume_channels, contain_dnet=True):
+    """pipeline3_model.py:717-733, 774-821 restated (every switch).  Pinned by tests/golden/hyp_*.npz, which are produced by
+    executing the reference's own source lines (tests/golden/make_golden_hypotheses.py).  Returns (depth_volume, d_centers)."""
+    lo, hi = args["min_depth"], args["max_depth"]
+    n_samples = len(k_list)
+    if not contain_dnet:
+        n = cost_volume_channels
+        return None, (torch.linspace(lo, hi, n) if args["use_depth_sampling"] else 1.0 / torch.linspace(1 / lo, 1 / hi, n))
+    ref_mu = ref_gmms[:, :1]
+    vol = None
+    if n_samples > 0:
+        if args["mono_uncertainty"] or args.get("mono_uncert_tune"):
+            ref_sigma = ref_gmms[:, 1:]
+            if args.get("relaxation_factor") in args:          # sic (:726): the value looked up as a key
+                mono = [torch.clamp(ref_mu + ref_sigma * float(k) * args["relaxation_factor"], min=lo, max=hi) for k in k_list]
+            else:
+                mono = [torch.clamp(ref_mu + torch.clamp(ref_sigma, min=args["basic_sigma"]) * float(k), min=lo, max=hi) for k in k_list]
+        else:
+            mono = [torch.clamp(ref_mu + float(k) * args["fixed_sigma"], min=lo, max=hi) for k in k_list]
+        vol = torch.cat(mono, 1)
+    if args["wo_hdh"]:
+        return vol, None
+    n = cost_volume_channels - n_samples
+    B, _, H, W = ref_mu.shape
+    if args["use_depth_sampling"]:
+        if args["revise_range"]:
+            d_min = torch.clamp(ref_mu - args["fixed_dist"], min=lo)
+            d_max = torch.clamp(ref_mu + args["fixed_dist"], max=hi)
+            interval = (d_max - d_min) / (n - 1)
+            cen = torch.cat([d_min, d_min + interval * torch.arange(0, n - 1).reshape(1, n - 1, 1, 1)], 1)
+        else:
+            cen = torch.linspace(lo, hi, n).reshape(1, n, 1, 1)
+    else:
+        cen = 1.0 / torch.linspace(1 / lo, 1 / hi, n).reshape(1, n, 1, 1)
+    if not args["revise_range"]:
+        cen = cen.repeat(B, 1, H, W)
+    vol = cen if vol is None else torch.cat([vol, cen], 1)
+    return torch.sort(vol, dim=1)[0], cen
+
+
 def magnet_k_list(n_samples=5, sampling_range=3):
     """pipeline3_model.py:537-545 without scipy: midpoints of equal-probability normal quantiles."""
     from statistics import NormalDist

@@ -152,3 +152,31 @@ def render_rays_diner(cfg, W, que, ref, fill_rand, gauss=None):
             out[k + "_fine"] = v
         return out
     return {k + "_fine": v for k, v in d_out.items()}
+
+
+def depth2normal(dataset, dmap):
+    """network/orig_diner_depth2normal.py:7-110 restated: normals of the back-projected depth map by central differences over the
+    panorama (zero rows above / below, longitude wrap left / right), then the reference's "cleaning": where the x coordinate of a
+    neighbouring point is exactly 0 (a hole or the zero padding) the normal is replaced by the RAW normal of the pixel one step to
+    the opposite side, and pixels without depth get a zero normal.  dmap (N,1,H,W) -> (N,3,H,W).  Pinned by
+    tests/golden/normal_*.npz (produced by the reference)."""
+    from .render import equi_to_unit_dirs
+    N, _, H, W = dmap.shape
+    pts = equi_to_unit_dirs(dataset, H, W).unsqueeze(0) * dmap.view(N, H, W, 1)          # (N,H,W,3)
+    zero = torch.zeros(N, 1, W, 3)
+    down = torch.cat([pts[:, 1:], zero], 1)
+    up = torch.cat([zero, pts[:, :-1]], 1)
+    right = torch.roll(pts, -1, 2)
+    left = torch.roll(pts, 1, 2)
+    vdiff, hdiff = down - up, right - left
+    normal = torch.linalg.cross(vdiff, hdiff, dim=-1)
+    normal = normal / torch.norm(normal, p=2, dim=-1, keepdim=True)
+    off_y = (up[..., 0] == 0).long() - (down[..., 0] == 0).long()
+    off_x = (left[..., 0] == 0).long() - (right[..., 0] == 0).long()
+    ys = (torch.arange(H).view(1, H, 1) + off_y).clamp(0, H - 1)
+    xs = (torch.arange(W).view(1, 1, W) + off_x).clamp(0, W - 1)
+    moved = (off_y != 0) | (off_x != 0)
+    n_idx = torch.arange(N).view(N, 1, 1).expand(N, H, W)
+    cleaned = torch.where(moved.unsqueeze(-1), normal[n_idx, ys, xs], normal)
+    cleaned = torch.where((dmap[:, 0] == 0).unsqueeze(-1), torch.zeros_like(cleaned), cleaned)
+    return cleaned.permute(0, 3, 1, 2)

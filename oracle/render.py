@@ -374,18 +374,22 @@ def ibrnet_forward(W, p, rgb_feat, neuray_feat, ray_diff, mask, n_samples):
     return torch.cat([rgb_out, sigma_out], dim=-1)
 
 
-def agg_net_forward(W, p, prj, que_dir, n_samples):
+def agg_net_forward(W, p, prj, que_dir, n_samples, wo_geometry=False, wo_appearance=False):
     """DefaultAggregationNet.forward (aggregate_net.py:41-89). Returns density (qn,rn,dn), colors (qn,rn,dn,3)."""
     hit = (prj["hit_prob"] - 0.5) * 2
     vis = (prj["vis"] - 0.5) * 2
     rfn, qn, rn, dn, _ = hit.shape
     emb = torch.cat([prj["ray_feats"], hit, vis], -1)
     emb = _lin(W, p + ".prob_embed.2", F.relu(_lin(W, p + ".prob_embed.0", emb)))
+    if wo_geometry:                                                       # aggregate_net.py:60-62
+        emb = torch.zeros_like(emb)
     dir_diff = prj["dir"] - que_dir.unsqueeze(0)
     dir_dot = torch.sum(prj["dir"] * que_dir.unsqueeze(0), -1, keepdim=True)
     dir_diff = torch.cat([dir_diff, dir_dot], -1).reshape(rfn, qn * rn, dn, -1).permute(1, 2, 0, 3)
     mask = torch.ones(qn * rn, dn, rfn, 1)
     img = torch.cat([prj["rgb"], prj["img_feats"]], -1).reshape(rfn, qn * rn, dn, -1).permute(1, 2, 0, 3)
+    if wo_appearance:                                                     # aggregate_net.py:79-81
+        img = torch.zeros_like(img)
     emb = emb.reshape(rfn, qn * rn, dn, -1).permute(1, 2, 0, 3)
     outs = ibrnet_forward(W, p + ".agg_impl", img, emb, dir_diff, mask, n_samples)
     return outs[..., 3].reshape(qn, rn, dn), outs[..., :3].reshape(qn, rn, dn, 3)
@@ -443,7 +447,10 @@ def render_by_depth(cfg, W, que, ref, depth, is_fine, return_prj=False):
     prj["img_feats"] = bilinear_border(ref["img_feats"], pix, ih, iw).reshape(rfn, qn, rn, dn, -1)
     agg = "fine_agg_net" if is_fine else "agg_net"
     n_samples = agg_sample_num(cfg, is_fine)
-    density, colors = agg_net_forward(W, agg, prj, que_dir, n_samples)
+    sub = cfg.get("fine_agg_net_cfg" if is_fine else "agg_net_cfg") or {}     # renderer.py:67-78 copies the top-level switches
+    density, colors = agg_net_forward(W, agg, prj, que_dir, n_samples,
+                                      bool(cfg.get("wo_geometry", sub.get("wo_geometry", False))),
+                                      bool(cfg.get("wo_appearance", sub.get("wo_appearance", False))))
     hit, pixel_colors, render_depth = composite(density, colors, depth)
     out = {"pixel_colors_nr": pixel_colors, "hit_prob_nr": hit, "colors_nr": colors, "density_nr": density,
            "render_depth": render_depth}

@@ -115,6 +115,7 @@ class RenderArgs(ctypes.Structure):
         ("fine_inds", _P), ("prob_dbg", _P), ("prj_dbg", _P), ("feat_dbg", _P),
         ("stage_mask", _I), ("mlp_bf16", _I), ("sched", _P), ("weights16", _P),
         ("prj_in", _P), ("feat_in", _P), ("prob_in", _P), ("que_dir_in", _P), ("interval_in", _P), ("dec_dbg", _P),
+        ("wo_geometry", _I), ("wo_appearance", _I),
     ]
 
 
@@ -155,6 +156,7 @@ SIGNATURES.update({
     "pgrf_interpolate_feature_map_fwd": (_I, [_P, _I, _I, _I, _I, _P, ctypes.c_longlong, _I, _I, _P, _P]),
     "pgrf_composite_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pgrf_interpolate_feature_map_bwd": (_I, [_P, _I, _I, _I, _I, _P, ctypes.c_longlong, _I, _I, _P, _P]),
+    "pgrf_depth2normal_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "pgrf_depth2points_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, ctypes.c_longlong, _I, _P, _P, _P]),
     "pgrf_render_workspace": (_I, [_I, ctypes.c_longlong, _PLL, _PLL]),
     "pgrf_render_view_fwd": (_I, [ctypes.POINTER(RenderViewArgs), _P]),
@@ -165,6 +167,7 @@ SIGNATURES.update({
     "pgrf_composite_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "pgrf_fine_sample_fwd": (_I, [_P, _I, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pgrf_depth_hypotheses_fwd": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _F, _F, _P, _P]),
+    "pgrf_depth_hypotheses2_fwd": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _P, _I, _I, _F, _F, _F, _I, _P, _P]),
     "pgrf_weight_blob_floats": (_I, []),
     "pgrf_weight_num_layers": (_I, []),
     "pgrf_weight_layer_info": (_I, [_I, ctypes.c_char_p, _I, _PI, _PI, _PI, _PI, _PI, _PI, _PI]),

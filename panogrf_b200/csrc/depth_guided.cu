@@ -268,6 +268,54 @@ __global__ void __launch_bounds__(256) project_gather_diner_kernel(const float* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// depth2normal (network/orig_diner_depth2normal.py:7-110): prior normals for `backface_culling`.
+// Pass 1 (thread = pixel): back-project the 4-neighbourhood (zero rows above / below the panorama, longitude wrap), cross product
+// of the vertical and horizontal central differences, normalise; record the reference's "cleaning" offset (a neighbour whose x
+// coordinate is exactly 0 pushes the lookup one pixel to the opposite side).  Pass 2: gather the RAW normal at the offset pixel,
+// zero where the depth is 0, write (N,3,H,W).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) depth2normal_raw_kernel(const float* __restrict__ dmap, int N, int H, int W, int dataset,
+                                                               float* __restrict__ raw, signed char* __restrict__ offs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * H * W) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H);
+  const float* d = dmap + (i / ((long long)H * W)) * H * W;
+  auto point = [&](int yy, int xx, float (&o)[3]) {
+    if (yy < 0 || yy >= H) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; return; }
+    float dx, dy, dz;
+    equi_unit_dir<false>(dataset, (float)xx, (float)yy, H, W, dx, dy, dz);
+    const float dd = __ldg(d + (size_t)yy * W + xx);
+    o[0] = __fmul_rn(dx, dd); o[1] = __fmul_rn(dy, dd); o[2] = __fmul_rn(dz, dd);
+  };
+  float dn[3], up[3], rt[3], lf[3];
+  point(y + 1, x, dn); point(y - 1, x, up);
+  point(y, x + 1 == W ? 0 : x + 1, rt); point(y, x == 0 ? W - 1 : x - 1, lf);
+  float v[3], h[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { v[k] = __fsub_rn(dn[k], up[k]); h[k] = __fsub_rn(rt[k], lf[k]); }
+  float n[3] = {__fsub_rn(__fmul_rn(v[1], h[2]), __fmul_rn(v[2], h[1])), __fsub_rn(__fmul_rn(v[2], h[0]), __fmul_rn(v[0], h[2])),
+                __fsub_rn(__fmul_rn(v[0], h[1]), __fmul_rn(v[1], h[0]))};
+  const float len = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(n[0], n[0]), __fmul_rn(n[1], n[1])), __fmul_rn(n[2], n[2])));
+  raw[3 * i] = __fdiv_rn(n[0], len); raw[3 * i + 1] = __fdiv_rn(n[1], len); raw[3 * i + 2] = __fdiv_rn(n[2], len);
+  offs[2 * i] = (signed char)((up[0] == 0.f ? 1 : 0) - (dn[0] == 0.f ? 1 : 0));
+  offs[2 * i + 1] = (signed char)((lf[0] == 0.f ? 1 : 0) - (rt[0] == 0.f ? 1 : 0));
+}
+__global__ void __launch_bounds__(256) depth2normal_clean_kernel(const float* __restrict__ dmap, const float* __restrict__ raw,
+                                                                 const signed char* __restrict__ offs, int N, int H, int W,
+                                                                 float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * H * W) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H);
+  const long long n = i / ((long long)H * W);
+  const int yy = min(max(y + offs[2 * i], 0), H - 1), xx = min(max(x + offs[2 * i + 1], 0), W - 1);
+  const long long j = (n * H + yy) * W + xx;
+  const bool hole = __ldg(dmap + i) == 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[((n * 3 + k) * H + y) * W + x] = hole ? 0.f : raw[3 * j + k];
+}
+
 }  // namespace pgrf
 
 using namespace pgrf;
@@ -322,6 +370,20 @@ extern "C" int pgrf_project_gather_diner_fwd(const float* pts, long long pn, con
                                                                     map_h, map_w, img_h, img_w, out_pix, out_depth, out_mu, out_uncert,
                                                                     out_normal);
   count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+
+extern "C" int pgrf_depth2normal_fwd(const float* mvs_depth, int N, int H, int W, int dataset, float* raw_ws, signed char* off_ws,
+                                     float* out_normal, void* stream) {
+  PGRF_REQUIRE(mvs_depth && raw_ws && off_ws && out_normal, "depth2normal: null pointer argument");
+  PGRF_REQUIRE(N >= 1 && H >= 2 && W >= 2 && dataset >= 0 && dataset <= 3, "depth2normal: bad arguments N=%d H=%d W=%d", N, H, W);
+  const long long total = (long long)N * H * W;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  depth2normal_raw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mvs_depth, N, H, W, dataset, raw_ws, off_ws);
+  depth2normal_clean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mvs_depth, raw_ws, off_ws, N, H, W, out_normal);
+  count_launch(2);
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
 }

@@ -268,13 +268,22 @@ __global__ void __launch_bounds__(kThreads, 1) render_rows_kernel(const RenderPa
       IN[33 * LD + m] = (vis - 0.5f) * 2.f;
     }
     __syncthreads();
+    if (a.wo_appearance) {   // aggregate_net.py:79-81: [rgb, img_feats] = 0 (raw colours included: ibrnet takes rgb_in from them)
+      for (int it = tid; it < 35 * LD; it += kThreads) OUT[it] = 0.f;
+      for (int it = tid; it < 3 * LD; it += kThreads) OUT[F1_RGBRAW * LD + it] = 0.f;
+      __syncthreads();
+    }
 
     // ---------------- prob_embed 34 -> 32 (ReLU) -> 32, straight into the output block ----------------
+    if (a.wo_geometry) {     // aggregate_net.py:60-62: prob_embedding = 0
+      for (int it = tid; it < 32 * LD; it += kThreads) OUT[F1_NEURAY * LD + it] = 0.f;
+    } else {
     gemm_smem<4, ACT_RELU, false, false>(IN, LD, 34, W + WOFF(L_PE0), 32, W + BOFF(L_PE0), H1, LD, Mp, 32,
                                          nullptr, nullptr, 1, 0, warp, lane, kWarps);
     __syncthreads();
     gemm_smem<4, ACT_NONE, false, false>(H1, LD, 32, W + WOFF(L_PE1), 32, W + BOFF(L_PE1), OUT + F1_NEURAY * LD, LD,
                                          Mp, 32, nullptr, nullptr, 1, 0, warp, lane, kWarps);
+    }
     __syncthreads();
 
     // ---------------- neuray_fc (threads 0..127) and ray_dir_fc (threads 128..255) ----------------

@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       const Footprint f = border_footprint_r(rg.px, rg.py, inv_wm1, inv_hm1, true, a.img_h, a.img_w);
       const float4 c = tap4(reinterpret_cast<const float4*>(a.imgs_cl) + (size_t)v * a.img_h * a.img_w + f.off, f, 1, a.img_w);
       rgb_in[0] = c.x; rgb_in[1] = c.y; rgb_in[2] = c.z;
+      if (a.wo_appearance) { rgb_in[0] = 0.f; rgb_in[1] = 0.f; rgb_in[2] = 0.f; }      // aggregate_net.py:79-81
     }
     // sampling interval of this sample along its ray (depth2inv_dists) and the view's normalised depth
     float d_prev, d_s, dv;
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       q.x = umma::pack2(rf.x, rf.y); q.y = umma::pack2(rf.z, rf.w);
       *reinterpret_cast<uint2*>(X + ((size_t)(cg >> 1) * ROWS + r) * 16 + (cg & 1) * 8) = q;
       q.x = umma::pack2(imf.x, imf.y); q.y = umma::pack2(imf.z, imf.w);
+      if (a.wo_appearance) q = make_uint2(0u, 0u);
       *reinterpret_cast<uint2*>(Y + ((size_t)(cg >> 1) * ROWS + r) * 16 + (cg & 1) * 8) = q;
     }
     WAIT_MMA()
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       ld32f(tq + C_PE1, y);
       uint32_t h[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) h[i] = umma::pack2(y[2 * i], y[2 * i + 1]);
+      for (int i = 0; i < 16; ++i) h[i] = a.wo_geometry ? 0u : umma::pack2(y[2 * i], y[2 * i + 1]);   // aggregate_net.py:60-62
       st16(tq + T_PEMB, h);
     }
     // ------------------------------------------------------------ base_fc.0 = per-row K-blocks [rgb_feat' | prob_embedding] + bias,

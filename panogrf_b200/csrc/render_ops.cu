@@ -35,18 +35,29 @@ struct PgParams {
   int rfn, dataset, H, W, img_h, img_w, if_h, if_w, rf_h, rf_w;
 };
 
+template <bool PACKED = true>
 __device__ __forceinline__ float4 blend4(const float4* __restrict__ base, int sx, int sy, float tx, float ty) {
   const float4 nw = ldg4(base), ne = ldg4(base + sx), sw = ldg4(base + sy), se = ldg4(base + sy + sx);
   const float tx1 = 1.f - tx, ty1 = 1.f - ty;
   const float wnw = tx1 * ty1, wne = tx * ty1, wsw = tx1 * ty, wse = tx * ty;
-  float4 o;
-  o.x = nw.x * wnw; o.y = nw.y * wnw; o.z = nw.z * wnw; o.w = nw.w * wnw;
-  o.x = fmaf(ne.x, wne, o.x); o.y = fmaf(ne.y, wne, o.y); o.z = fmaf(ne.z, wne, o.z); o.w = fmaf(ne.w, wne, o.w);
-  o.x = fmaf(sw.x, wsw, o.x); o.y = fmaf(sw.y, wsw, o.y); o.z = fmaf(sw.z, wsw, o.z); o.w = fmaf(sw.w, wsw, o.w);
-  o.x = fmaf(se.x, wse, o.x); o.y = fmaf(se.y, wse, o.y); o.z = fmaf(se.z, wse, o.z); o.w = fmaf(se.w, wse, o.w);
-  return o;
+  if (!PACKED) {
+    float4 o;
+    o.x = nw.x * wnw; o.y = nw.y * wnw; o.z = nw.z * wnw; o.w = nw.w * wnw;
+    o.x = fmaf(ne.x, wne, o.x); o.y = fmaf(ne.y, wne, o.y); o.z = fmaf(ne.z, wne, o.z); o.w = fmaf(ne.w, wne, o.w);
+    o.x = fmaf(sw.x, wsw, o.x); o.y = fmaf(sw.y, wsw, o.y); o.z = fmaf(sw.z, wsw, o.z); o.w = fmaf(sw.w, wsw, o.w);
+    o.x = fmaf(se.x, wse, o.x); o.y = fmaf(se.y, wse, o.y); o.z = fmaf(se.z, wse, o.z); o.w = fmaf(se.w, wse, o.w);
+    return o;
+  }
+  // ATen's order (nw, ne, sw, se) on packed fp32 pairs: the same IEEE mul / fma per channel, half the issue slots
+  const float2 w0 = make_float2(wnw, wnw), w1 = make_float2(wne, wne), w2 = make_float2(wsw, wsw), w3 = make_float2(wse, wse);
+  float2 lo = fmul2(make_float2(nw.x, nw.y), w0), hi = fmul2(make_float2(nw.z, nw.w), w0);
+  lo = ffma2(make_float2(ne.x, ne.y), w1, lo); hi = ffma2(make_float2(ne.z, ne.w), w1, hi);
+  lo = ffma2(make_float2(sw.x, sw.y), w2, lo); hi = ffma2(make_float2(sw.z, sw.w), w2, hi);
+  lo = ffma2(make_float2(se.x, se.y), w3, lo); hi = ffma2(make_float2(se.z, se.w), w3, hi);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
+template <bool PACKED, int UNR>
 __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgParams p) {
   __shared__ PgRec rec[kPgThreads];
   const int tid = threadIdx.x;
@@ -75,7 +86,7 @@ __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgPara
         const float e0 = x - cam0, e1 = y - cam1, e2 = z - cam2;
         const float en = fmaxf(sqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e-5f);
         const size_t row = (size_t)v * p.pn + pi;
-        p.out_pix[2 * row] = px; p.out_pix[2 * row + 1] = py;
+        __stcs(reinterpret_cast<float2*>(p.out_pix) + row, make_float2(px, py));
         p.out_depth[row] = radius;
         p.out_dir[3 * row] = -e0 / en; p.out_dir[3 * row + 1] = -e1 / en; p.out_dir[3 * row + 2] = -e2 / en;
         Footprint f = border_footprint(px, py, p.img_h, p.img_w, p.rf_h, p.rf_w);
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgPara
     __syncthreads();
     // ---- phase 2: lane = (row, float4 channel group): 8 lanes fetch one 128-byte texel line per tap and write one
     //      128-byte output row (coalesced both ways)
-#pragma unroll 2
+#pragma unroll UNR
     for (int it = tid; it < rows * 8; it += kPgThreads) {
       const int rrow = it >> 3, cg = it & 7;
       const int v = rrow / kPgPoints;
@@ -102,11 +113,11 @@ __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgPara
       if (pi >= p.pn) continue;
       const PgRec r = rec[rrow];
       const size_t row = (size_t)v * p.pn + pi;
-      const float4 a = blend4(reinterpret_cast<const float4*>(p.ray_feats_cl) + (size_t)r.off_rf * 8 + cg, (r.dxy & 1) * 8,
+      const float4 a = blend4<PACKED>(reinterpret_cast<const float4*>(p.ray_feats_cl) + (size_t)r.off_rf * 8 + cg, (r.dxy & 1) * 8,
                               ((r.dxy >> 1) & 1) * p.rf_w * 8, r.tx_rf, r.ty_rf);
       __stcs(reinterpret_cast<float4*>(p.out_rf) + row * 8 + cg, a);
       if (p.out_if) {
-        const float4 b = blend4(reinterpret_cast<const float4*>(p.img_feats_cl) + (size_t)r.off_if * 8 + cg, ((r.dxy >> 2) & 1) * 8,
+        const float4 b = blend4<PACKED>(reinterpret_cast<const float4*>(p.img_feats_cl) + (size_t)r.off_if * 8 + cg, ((r.dxy >> 2) & 1) * 8,
                                 ((r.dxy >> 3) & 1) * p.if_w * 8, r.tx_if, r.ty_if);
         __stcs(reinterpret_cast<float4*>(p.out_if) + row * 8 + cg, b);
       }
@@ -225,25 +236,77 @@ __global__ void __launch_bounds__(256) fine_sample_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// a5: depth hypotheses.  thread = pixel; merge of two ascending lists (clamped mono-guided, linear) = the sort.
+// a5: depth hypotheses (pipeline3_model.py:717-733, 774-815).  thread = pixel.
+//   mono-guided list: clamp(mu + s * k_i, min, max), i < n_mono, with
+//       mode 0  s * k_i = k_table[i]                      ("fixed_sigma": the host passes float32(k_i * fixed_sigma))
+//       mode 1  s = max(sigma, basic_sigma), product rounded, then added   (mono_uncertainty, :731)
+//       mode 2  (sigma * k_i) * relaxation_factor                          (:729)
+//   centres: mode 0 a table shared by all pixels (linear :802 / inverse-linear :804, built by the host with the reference's torch
+//       ops), mode 1 per-pixel `revise_range` (:784-799: [d_min, d_min + interval * j], j < n-1, interval = (d_max - d_min) / (n-1)),
+//       mode 2 none (`wo_hdh`).
+//   output = the two ascending lists merged (== torch.sort of their concatenation, values only); with `sort_out` = 0 (wo_hdh) the
+//   mono list is written in k order, as the reference leaves it.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) depth_hypotheses_kernel(const float* __restrict__ ref_mu, const float* __restrict__ k_sigma,
-                                                               int n_mono, const float* __restrict__ linear, int n_lin,
-                                                               float min_d, float max_d, long long hw, long long total_px,
+constexpr int kMaxMono = 16;
+__global__ void __launch_bounds__(256) depth_hypotheses_kernel(const float* __restrict__ ref_mu, const float* __restrict__ ref_sigma,
+                                                               const float* __restrict__ k_table, int n_mono, int mono_mode,
+                                                               float basic_sigma, float relax, const float* __restrict__ centers,
+                                                               int n_cen, int cen_mode, float fixed_dist, float min_d, float max_d,
+                                                               int sort_out, long long hw, long long total_px,
                                                                float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total_px) return;
   const long long b = i / hw, px = i % hw;
   const float mu = __ldg(ref_mu + i);
-  const int D = n_mono + n_lin;
+  const int D = n_mono + (cen_mode == 2 ? 0 : n_cen);
   float* o = out + b * D * hw + px;
-  // mono list ascending in k (k_sigma ascending): clamp keeps the order
+  float mono[kMaxMono];
+  const float sg = ref_sigma ? __ldg(ref_sigma + i) : 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxMono; ++j) {
+    if (j >= n_mono) { mono[j] = INFINITY; continue; }
+    const float k = __ldg(k_table + j);
+    float add;
+    if (mono_mode == 0) add = k;
+    else if (mono_mode == 1) add = __fmul_rn(fmaxf(sg, basic_sigma), k);
+    else add = __fmul_rn(__fmul_rn(sg, k), relax);
+    mono[j] = fminf(fmaxf(__fadd_rn(mu, add), min_d), max_d);
+  }
+  if (!sort_out) {
+    for (int j = 0; j < n_mono; ++j) o[(long long)j * hw] = mono[j];
+    return;
+  }
+  // ascending k and a positive sigma give an ascending list; a predicted sigma may be negative (mode 2): insertion sort
+#pragma unroll
+  for (int a2 = 1; a2 < kMaxMono; ++a2) {
+#pragma unroll
+    for (int c = a2; c > 0; --c) {
+      const float lo = fminf(mono[c - 1], mono[c]), hi = fmaxf(mono[c - 1], mono[c]);
+      mono[c - 1] = lo; mono[c] = hi;
+    }
+  }
+  float dmin = 0.f, interval = 0.f;
+  if (cen_mode == 1) {
+    dmin = fmaxf(__fsub_rn(mu, fixed_dist), min_d);
+    const float dmax = fminf(__fadd_rn(mu, fixed_dist), max_d);
+    interval = __fdiv_rn(__fsub_rn(dmax, dmin), (float)(n_cen - 1));
+  }
+  auto centre = [&](int j) -> float {
+    if (cen_mode == 0) return __ldg(centers + j);
+    return j == 0 ? dmin : __fadd_rn(dmin, __fmul_rn(interval, (float)(j - 1)));
+  };
   int im = 0, il = 0;
+  const int n_lin = cen_mode == 2 ? 0 : n_cen;
+  float vm = mono[0];
   for (int d = 0; d < D; ++d) {
-    const float vm = im < n_mono ? fminf(fmaxf(mu + __ldg(k_sigma + im), min_d), max_d) : INFINITY;
-    const float vl = il < n_lin ? __ldg(linear + il) : INFINITY;
+    const float vl = il < n_lin ? centre(il) : INFINITY;
     float v;
-    if (vm <= vl) { v = vm; ++im; } else { v = vl; ++il; }
+    if (vm <= vl) {
+      v = vm; ++im;
+      vm = INFINITY;
+#pragma unroll
+      for (int j = 1; j < kMaxMono; ++j) if (j == im) vm = mono[j];
+    } else { v = vl; ++il; }
     o[(long long)d * hw] = v;
   }
 }
@@ -251,6 +314,7 @@ __global__ void __launch_bounds__(256) depth_hypotheses_kernel(const float* __re
 }  // namespace pgrf
 
 using namespace pgrf;
+namespace pgrf { int g_pg_variant = 3; int g_pg_grid = 48; }   // B200 sweep (tools/time_pg_variants.py): 8 gathers in flight per lane, 48 CTAs per SM-slot
 
 extern "C" int pgrf_project_gather_fwd(const float* pts, long long pn, const float* w2c, int rfn, int dataset, int H, int W,
                                        const float* imgs_cl, int img_h, int img_w, const float* img_feats_cl, int if_h, int if_w,
@@ -269,8 +333,14 @@ extern "C" int pgrf_project_gather_fwd(const float* pts, long long pn, const flo
   p.if_h = if_h; p.if_w = if_w; p.rf_h = rf_h; p.rf_w = rf_w;
   const int pts_per_tile = kPgThreads / rfn;
   const long long tiles = (pn + pts_per_tile - 1) / pts_per_tile;
-  const int grid = (int)(tiles < 148 * 16 ? tiles : 148 * 16);
-  project_gather_kernel<<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p);
+  const int grid = (int)(tiles < 148 * g_pg_grid ? tiles : 148 * g_pg_grid);
+  switch (g_pg_variant) {
+    case 0: project_gather_kernel<false, 2><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
+    case 1: project_gather_kernel<true, 2><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
+    case 2: project_gather_kernel<true, 4><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
+    case 3: project_gather_kernel<false, 4><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
+    default: project_gather_kernel<false, 8><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
+  }
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
@@ -308,15 +378,28 @@ extern "C" int pgrf_fine_sample_fwd(const float* depth, int depth_ray_stride, co
   return PGRF_OK;
 }
 
-extern "C" int pgrf_depth_hypotheses_fwd(const float* ref_mu, int B, int h, int w, const float* k_sigma, int n_mono,
-                                         const float* linear, int n_linear, float min_depth, float max_depth, float* out,
-                                         void* stream) {
-  PGRF_REQUIRE(ref_mu && k_sigma && linear && out, "depth_hypotheses: null pointer argument");
-  PGRF_REQUIRE(B >= 1 && h >= 1 && w >= 1 && n_mono >= 0 && n_linear >= 0 && n_mono + n_linear >= 1, "depth_hypotheses: bad sizes");
+extern "C" int pgrf_depth_hypotheses2_fwd(const float* ref_mu, const float* ref_sigma, int B, int h, int w, const float* k_table,
+                                          int n_mono, int mono_mode, float basic_sigma, float relaxation, const float* centers,
+                                          int n_centers, int centers_mode, float fixed_dist, float min_depth, float max_depth,
+                                          int sort_out, float* out, void* stream) {
+  PGRF_REQUIRE(ref_mu && out && (n_mono == 0 || k_table), "depth_hypotheses: null pointer argument");
+  PGRF_REQUIRE(B >= 1 && h >= 1 && w >= 1 && n_mono >= 0 && n_mono <= kMaxMono && n_centers >= 0, "depth_hypotheses: bad sizes");
+  PGRF_REQUIRE(mono_mode >= 0 && mono_mode <= 2 && (mono_mode == 0 || ref_sigma || n_mono == 0), "depth_hypotheses: sigma modes need ref_sigma");
+  PGRF_REQUIRE(centers_mode >= 0 && centers_mode <= 2 && (centers_mode != 0 || centers || n_centers == 0) &&
+                   (centers_mode != 1 || n_centers >= 2), "depth_hypotheses: bad centres");
+  PGRF_REQUIRE(n_mono + (centers_mode == 2 ? 0 : n_centers) >= 1, "depth_hypotheses: empty output");
   const long long hw = (long long)h * w, total = hw * B;
-  depth_hypotheses_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ref_mu, k_sigma, n_mono, linear, n_linear,
-                                                                                            min_depth, max_depth, hw, total, out);
+  depth_hypotheses_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      ref_mu, ref_sigma, k_table, n_mono, mono_mode, basic_sigma, relaxation, centers, n_centers, centers_mode, fixed_dist, min_depth,
+      max_depth, sort_out, hw, total, out);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
+}
+
+extern "C" int pgrf_depth_hypotheses_fwd(const float* ref_mu, int B, int h, int w, const float* k_sigma, int n_mono, const float* linear,
+                                         int n_linear, float min_depth, float max_depth, float* out, void* stream) {
+  PGRF_REQUIRE(ref_mu && k_sigma && linear && out, "depth_hypotheses: null pointer argument");
+  return pgrf_depth_hypotheses2_fwd(ref_mu, nullptr, B, h, w, k_sigma, n_mono, 0, 0.f, 1.f, linear, n_linear, 0, 0.f, min_depth, max_depth, 1,
+                                    out, stream);
 }

@@ -234,6 +234,27 @@ def depth2points_spherical(que_imgs_info, que_depth, spt_utils):
     return pts, dirs
 
 
+def depth2normal(ref_imgs_info, spt_utils):
+    """network/orig_diner_depth2normal.py:7-110: ref_imgs_info['mvs_depth'] (N,1,H,W) -> normals (N,3,H,W) by central
+    differences of the back-projected panorama (the renderer fills ref_imgs_info['mvs_normal'] with it, renderer.py:714)."""
+    dmap = ref_imgs_info["mvs_depth"]
+    _lib.require_cuda(dmap)
+    name = spt_utils.dataset
+    if name not in _lib.DATASET_IDS:
+        raise Exception(f"unknown dataset {name!r}")
+    N, _, H, W = dmap.shape
+    d = _f32(dmap)
+    dev = d.device
+    raw = torch.empty(N, H, W, 3, device=dev)
+    offs = torch.empty(N, H, W, 2, device=dev, dtype=torch.int8)
+    out = torch.empty(N, 3, H, W, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pgrf_depth2normal_fwd(_lib.ptr(d), N, H, W, _lib.DATASET_IDS[name], _lib.ptr(raw), _lib.ptr(offs),
+                                               _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "pgrf_depth2normal_fwd")
+    return out
+
+
 def mono_guided_hypotheses(ref_mu, k_list, fixed_sigma, min_depth, max_depth, n_linear):
     """Depth hypotheses of the MVS net (pipeline3_model.py:723-733, 774-815): clamp(ref_mu + k*sigma) for k in k_list,
     concatenated with linspace(min,max,n_linear) and sorted per pixel.  ref_mu (B,1,h,w) -> (B,len(k_list)+n_linear,h,w)."""
@@ -249,6 +270,66 @@ def mono_guided_hypotheses(ref_mu, k_list, fixed_sigma, min_depth, max_depth, n_
                                            float(min_depth), float(max_depth), _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "pgrf_depth_hypotheses_fwd")
     return out
+
+
+def magnet_k_list(n_samples=5, sampling_range=3):
+    """pipeline3_model.py:537-545 (`depth_sampling`): midpoints of equal-probability normal quantiles covering
+    +-sampling_range sigma.  fp64, without scipy: statistics.NormalDist().inv_cdf agrees with scipy's norm.ppf to 1e-15."""
+    import math
+    from statistics import NormalDist
+    p_total = math.erf(sampling_range / math.sqrt(2))
+    ps = [(1 - p_total) / 2 + (i / n_samples) * p_total for i in range(n_samples + 1)]
+    ks = [NormalDist().inv_cdf(p) for p in ps]
+    return [(a + b) / 2 for a, b in zip(ks[1:], ks[:-1])]
+
+
+def depth_hypotheses(args, ref_gmms, k_list, cost_volume_channels, contain_dnet=True):
+    """The MVS net's hypothesis builder with every switch of the reference (pipeline3_model.py:717-733, 774-821).
+
+    args keys read: min_depth, max_depth, mono_uncertainty, mono_uncert_tune, fixed_sigma, basic_sigma, relaxation_factor, wo_hdh,
+    use_depth_sampling, revise_range, fixed_dist.  `k_list` = magnet_k_list(MAGNET_num_samples, MAGNET_sampling_range) ([] when
+    n_samples == 0).  Returns (depth_volume (B,D,h,w) or None, d_centers): with `contain_dnet` the per-pixel sorted volume (and the
+    centres the reference keeps alongside), else (None, 1-D centres) exactly as the reference passes them to the cost volume."""
+    lib = _lib.load()
+    lo, hi = args["min_depth"], args["max_depth"]
+    n_samples = len(k_list)
+    if not contain_dnet:
+        n = int(cost_volume_channels)
+        cen = torch.linspace(lo, hi, n) if args["use_depth_sampling"] else 1.0 / torch.linspace(1 / lo, 1 / hi, n)
+        return None, cen.to(ref_gmms.device if ref_gmms is not None else "cpu")
+    _lib.require_cuda(ref_gmms)
+    dev = ref_gmms.device
+    B, _, h, w = ref_gmms.shape
+    mu = _f32(ref_gmms[:, :1])
+    use_sigma = bool(args["mono_uncertainty"] or args.get("mono_uncert_tune"))
+    sigma = _f32(ref_gmms[:, 1:2]) if (use_sigma and n_samples > 0) else None
+    mono_mode, ks = 0, None
+    if n_samples > 0:
+        if use_sigma:
+            # the reference tests `args["relaxation_factor"] in self.args` — the VALUE as a key (:726) — kept as written
+            mono_mode = 2 if args.get("relaxation_factor") in args else 1
+            ks = torch.tensor([float(k) for k in k_list], dtype=torch.float32, device=dev)
+        else:
+            ks = torch.tensor([float(k) * float(args["fixed_sigma"]) for k in k_list], dtype=torch.float32, device=dev)
+    wo_hdh = bool(args["wo_hdh"])
+    n_cen = int(cost_volume_channels) - n_samples
+    cen_mode, cen, d_centers = 2, None, None
+    if not wo_hdh:
+        if args["use_depth_sampling"] and args["revise_range"]:
+            cen_mode = 1
+        else:
+            cen_mode = 0
+            cen = (torch.linspace(lo, hi, n_cen) if args["use_depth_sampling"] else 1.0 / torch.linspace(1 / lo, 1 / hi, n_cen)).to(dev)
+            d_centers = cen.reshape(1, n_cen, 1, 1)
+    D = n_samples + (0 if wo_hdh else n_cen)
+    out = torch.empty(B, D, h, w, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pgrf_depth_hypotheses2_fwd(_lib.ptr(mu), _lib.ptr(sigma), B, h, w, _lib.ptr(ks), n_samples, mono_mode,
+                                            float(args.get("basic_sigma", 0.0)), float(args.get("relaxation_factor", 1.0)),
+                                            _lib.ptr(cen), n_cen, cen_mode, float(args.get("fixed_dist", 0.0)), float(lo), float(hi),
+                                            0 if wo_hdh else 1, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "pgrf_depth_hypotheses2_fwd")
+    return out, d_centers
 
 
 # ------------------------------------------------------------------------------------------------

@@ -152,9 +152,6 @@ class DefaultAggregationNet(nn.Module):
         self.cfg = {**self.default_cfg, **cfg}
         if self.cfg.get("level") in [-1]:
             raise _lib.PanoGRFError("level=-1 (16-channel image features) is not supported")
-        for k in ("wo_geometry", "wo_appearance"):
-            if self.cfg.get(k):
-                raise _lib.PanoGRFError(f"ablation switch {k} is not supported by the fused kernels")
         dim = self.cfg["neuray_dim"]
         self.agg_impl = IBRNetWithNeuRay(dim, in_feat_ch=32, n_samples=self.cfg["sample_num"])
         self.prob_embed = nn.Sequential(nn.Linear(2 + 32, dim), nn.Identity(), nn.Linear(dim, dim))
@@ -466,6 +463,7 @@ class NeuralRayBaseRenderer(nn.Module):
             if ctx.get(k) is not None:
                 setattr(a, k, _lib.ptr(ctx[k]))
         a.stage_mask = int(ctx.get("stage_mask", 0))
+        a.wo_geometry, a.wo_appearance = int(bool(agg.cfg.get("wo_geometry"))), int(bool(agg.cfg.get("wo_appearance")))
         with torch.cuda.device(dev):
             rc = lib.pgrf_render_pass_fwd(ctypes.byref(a), _lib.stream_ptr())
         _lib.check(rc, "pgrf_render_pass_fwd")
@@ -946,8 +944,13 @@ class NeuralRayGenRenderer(NeuralRayBaseRenderer):
                 ref_imgs_info["mvs_uncert"] = ret["mvs_uncert"]
         elif "ray_feats" not in ref_imgs_info:
             raise _lib.PanoGRFError("NeuralRayGenRenderer: attach init_net or pass pre-computed ref_imgs_info['ray_feats']")
-        if self.cfg.get("backface_culling") and "mvs_normal" not in ref_imgs_info:
-            raise _lib.PanoGRFError("backface_culling needs ref_imgs_info['mvs_normal'] (depth2normal is outside the hot path)")
+        if self.cfg.get("backface_culling"):          # renderer.py:713-714
+            import types
+            from .render_ops import depth2normal
+            if "mvs_depth" not in ref_imgs_info:
+                raise _lib.PanoGRFError("backface_culling needs ref_imgs_info['mvs_depth'] (depth2normal input)")
+            ref_imgs_info["mvs_normal"] = depth2normal(ref_imgs_info, types.SimpleNamespace(
+                dataset=self.cfg["dataset_name"], height=int(self.cfg["height"]), width=int(self.cfg["width"])))
         return self.render(que_imgs_info, ref_imgs_info, is_train, is_perspec)
 
     def gen_depth_loss_coords(self, h, w, device):

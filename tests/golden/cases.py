@@ -106,6 +106,9 @@ RENDER_CASES = {
     "render_m3d_c2f_all": dict(cfg=dict(render_uncert=True, render_c2f_all=True), rfn=2, n_rays=48),
     # one source view: ibrnet.py:359-360 masks every attention key (uniform weights); ragged sizes (37 rays, 24 samples)
     "render_m3d_1src": dict(cfg=dict(sample_num=24, use_vis=True), rfn=1, n_rays=37),
+    # ablation switches of DefaultAggregationNet (aggregate_net.py:60-62, 79-81)
+    "render_m3d_wo_geometry": dict(cfg=dict(wo_geometry=True), rfn=2, n_rays=40),
+    "render_m3d_wo_appearance": dict(cfg=dict(wo_appearance=True), rfn=3, n_rays=40),
 }
 
 
@@ -214,3 +217,53 @@ def make_diner_inputs(name, seed=0):
     fill_rand = torch.rand(rn, cfg["n_samples"], generator=gen)
     gauss = torch.randn(rn, max(cfg["n_gaussian"], 1), generator=gen)[:, :cfg["n_gaussian"]]
     return cfg, que, ref, fill_rand, gauss
+
+
+# ------------------------------------------------------------------------------------------------
+# depth-hypothesis builder (pipeline3_model.py:537-545, 717-733, 774-821)
+# ------------------------------------------------------------------------------------------------
+_HYP_ARGS = {"min_depth": 0.1, "max_depth": 10.0, "mono_uncertainty": False, "mono_uncert_tune": False, "fixed_sigma": 0.5,
+             "basic_sigma": 0.05, "relaxation_factor": 1.0, "wo_hdh": False, "use_depth_sampling": True, "revise_range": False,
+             "fixed_dist": 1.5}
+HYP_CASES = {
+    # name: (args overrides, n_samples, cost_volume_channels, contain_dnet)
+    "hyp_fixed_sigma_linear": ({}, 5, 64, True),
+    "hyp_mono_uncert_basic_sigma": ({"mono_uncertainty": True}, 5, 64, True),
+    "hyp_inverse_linear": ({"use_depth_sampling": False}, 5, 32, True),
+    "hyp_revise_range": ({"revise_range": True}, 5, 24, True),
+    "hyp_wo_hdh": ({"wo_hdh": True}, 5, 64, True),
+    "hyp_no_mono_samples": ({}, 0, 16, True),
+    "hyp_scalar_linear": ({}, 0, 48, False),
+    "hyp_scalar_inverse": ({"use_depth_sampling": False}, 0, 48, False),
+}
+
+
+def make_hyp_inputs(name):
+    over, n_samples, channels, contain_dnet = HYP_CASES[name]
+    g = torch.Generator().manual_seed(900 + sorted(HYP_CASES).index(name))
+    B, h, w = 2, 6, 11
+    mu = 0.3 + 9.5 * torch.rand(B, 1, h, w, generator=g)          # a few pixels clamp at both ends
+    sigma = 0.6 * torch.rand(B, 1, h, w, generator=g)             # some below basic_sigma
+    return {"args": {**_HYP_ARGS, **over}, "n_samples": n_samples, "sampling_range": 3, "cost_volume_channels": channels,
+            "contain_dnet": contain_dnet, "ref_gmms": torch.cat([mu, sigma], 1)}
+
+
+# ------------------------------------------------------------------------------------------------
+# depth2normal (network/orig_diner_depth2normal.py) — prior normals of the depth-guided placement (backface_culling)
+# ------------------------------------------------------------------------------------------------
+NORMAL_CASES = {
+    # name: (dataset, h, w, fraction of zero-depth holes)
+    "normal_m3d": ("m3d", 16, 32, 0.0),
+    "normal_m3d_holes": ("m3d", 12, 24, 0.08),
+    "normal_residential": ("residential", 10, 20, 0.03),
+}
+
+
+def make_normal_inputs(name):
+    ds, h, w, holes = NORMAL_CASES[name]
+    g = torch.Generator().manual_seed(700 + sorted(NORMAL_CASES).index(name))
+    d = smooth(1.0 + 4.0 * torch.rand(2, h, w, 1, generator=g), 1).permute(0, 3, 1, 2).contiguous()
+    if holes > 0:
+        d = d * (torch.rand(2, 1, h, w, generator=g) > holes)
+    cfg = {"dataset_name": ds, "batch_size": 1, "height": h, "width": w}
+    return cfg, d

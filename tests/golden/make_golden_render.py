@@ -41,8 +41,10 @@ def hot_weights(net):
     return {k: v.detach().clone() for k, v in net.state_dict().items() if k.startswith(cases.RENDER_WEIGHT_PREFIXES)}
 
 
-def gen_render():
+def gen_render(only=None):
     for name in cases.RENDER_CASES:
+        if only and name not in only:
+            continue
         cfg, que, ref = cases.make_render_inputs(name)
         net = build_reference_renderer(cfg, seed=sum(map(ord, name)))
         with torch.no_grad():
@@ -62,4 +64,4 @@ def gen_render():
 
 
 if __name__ == "__main__":
-    gen_render()
+    gen_render(sys.argv[1:] or None)      # optional: names of the cases to (re)generate

@@ -128,3 +128,17 @@ def test_diner_random_tables_default_and_validation():
         depth_guided_placement(bad, _cuda(que), _cuda(ref))
     with pytest.raises(_lib.PanoGRFError):
         depth_guided_placement(cfg, que, ref)          # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("name", list(cases.NORMAL_CASES))
+def test_depth2normal_matches_reference(name):
+    """f3: depth2normal (network/orig_diner_depth2normal.py) on the GPU == the reference's output: same NaN pattern (degenerate
+    cross products the reference leaves as NaN), values within 1e-5 (unit vectors; the pixel -> ray trig differs by 1 ulp)."""
+    import types
+    from panogrf_b200 import render_ops as rops
+    ds, h, w, _ = cases.NORMAL_CASES[name]
+    g = load_golden(name)
+    got = rops.depth2normal({"mvs_depth": g["mvs_depth"].cuda()}, types.SimpleNamespace(dataset=ds, height=h, width=w)).cpu()
+    want = g["normal"]
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert float((torch.nan_to_num(got) - torch.nan_to_num(want)).abs().max()) < 1e-5

@@ -82,3 +82,22 @@ def test_oracle_gradient_matches_reference_autograd(name):
     gold = load_golden(name + "_bwd")
     assert abs(float(w.double().sum()) - float(gold["weight_sum"])) < 1e-6
     assert_close(images.grad, gold["grad_images"], rtol=1e-4, atol=1e-4, max_bad_frac=2e-3, what=name)
+
+
+@pytest.mark.parametrize("name", list(cases.HYP_CASES))
+def test_hypothesis_builder_oracle_matches_reference_lines(name):
+    """a5: the restated builder equals the outputs of the reference's own statements (pipeline3_model.py:717-733, 774-821,
+    executed by tests/golden/make_golden_hypotheses.py) bit for bit; the k list agrees with scipy's (fp64)."""
+    case = cases.make_hyp_inputs(name)
+    g = load_golden(name)
+    k_ref = g["k_list"].double()
+    k_list = ocv.magnet_k_list(case["n_samples"], case["sampling_range"]) if case["n_samples"] > 0 else []
+    assert len(k_list) == k_ref.numel() and all(abs(a - float(b)) < 1e-13 for a, b in zip(k_list, k_ref))
+    vol, cen = ocv.depth_hypotheses(case["args"], g["ref_gmms"], [float(k) for k in k_ref], case["cost_volume_channels"],
+                                    case["contain_dnet"])
+    if "depth_volume" in g:
+        assert torch.equal(vol, g["depth_volume"])
+    else:
+        assert vol is None
+    if "d_centers" in g and not case["args"]["wo_hdh"]:
+        assert torch.equal(cen.reshape(g["d_centers"].shape) if cen.dim() == 1 else cen.expand_as(g["d_centers"]) if case["args"]["revise_range"] else cen, g["d_centers"])

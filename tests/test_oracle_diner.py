@@ -48,3 +48,14 @@ def test_placement_statistics():
     assert z.shape == (1, que["coords"].shape[1], cfg["n_samples"])
     assert bool((z[..., 1:] >= z[..., :-1]).all())
     assert float(z.min()) >= cfg["min_depth"] and float(z.max()) <= cfg["max_depth"]
+
+
+@pytest.mark.parametrize("name", list(cases.NORMAL_CASES))
+def test_depth2normal_oracle_matches_reference(name):
+    """f3: depth2normal (network/orig_diner_depth2normal.py) restated == the reference's output (NaNs where the reference has them)."""
+    from oracle import depth_guided as odg
+    g = load_golden(name)
+    got = odg.depth2normal(cases.NORMAL_CASES[name][0], g["mvs_depth"])
+    want = g["normal"]
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert float((torch.nan_to_num(got) - torch.nan_to_num(want)).abs().max()) < 2e-6

@@ -144,3 +144,20 @@ def test_interpolate_feature_map_backward_matches_torch_autograd(scale):
     (out * wgt.cuda()).sum().backward()
     assert_close(out, ref.float(), rtol=1e-4, atol=1e-5, what="fwd")
     assert_close(fc.grad, f64.grad.float(), rtol=1e-4, atol=1e-4, what="grad feats")
+
+
+@pytest.mark.parametrize("name", list(cases.HYP_CASES))
+def test_depth_hypotheses_every_variant_bit_exact(name):
+    """a5 with every switch of the reference (fixed_sigma / mono_uncertainty + basic_sigma, linear / inverse-linear / revise_range
+    centres, wo_hdh, n_samples = 0, scalar hypotheses): the CUDA builder equals the outputs of the reference's own source lines
+    (tests/golden/make_golden_hypotheses.py) bit for bit — bin order of the sweep depends on it."""
+    from panogrf_b200 import render_ops as rops
+    case = cases.make_hyp_inputs(name)
+    g = load_golden(name)
+    k_list = rops.magnet_k_list(case["n_samples"], case["sampling_range"]) if case["n_samples"] > 0 else []
+    assert all(abs(a - float(b)) < 1e-13 for a, b in zip(k_list, g["k_list"].double()))
+    vol, cen = rops.depth_hypotheses(case["args"], g["ref_gmms"].cuda(), k_list, case["cost_volume_channels"], case["contain_dnet"])
+    if "depth_volume" in g:
+        assert torch.equal(vol.cpu(), g["depth_volume"]), float((vol.cpu() - g["depth_volume"]).abs().max())
+    else:
+        assert vol is None and torch.equal(cen.cpu(), g["d_centers"])
