@@ -172,6 +172,10 @@ typedef struct pgrf_render_args {
   /* ablation switches of DefaultAggregationNet (network/aggregate_net.py:60-62, 79-81) */
   int wo_geometry;             /* agg_net_cfg.wo_geometry: prob_embedding = 0 */
   int wo_appearance;           /* agg_net_cfg.wo_appearance: [rgb, img_feats] of every view = 0 (the blended colours are then 0) */
+  /* perspective / cube query rays (is_perspec, network/render_ops.py:37-74): optional (rn,3) WORLD-space ray directions
+   * (unnormalised, the reference's `directions`) replacing the ERP pixel -> ray table; the origin stays que_c2w[:,3] (= -R^T t);
+   * `coords` is then unused (may be NULL) */
+  const float* ray_dirs;
 } pgrf_render_args;
 /* Module-level entry ("agg_mlp_fwd"): the aggregation network + ray transformer + compositing on
  * caller-provided per-row inputs (prj_in, feat_in, prob_in, que_dir_in required).  fp32. */

@@ -210,6 +210,21 @@ def depth2points_spherical(dataset, height, width, c2w, coords, depth):
     return pts, que_dir.unsqueeze(2).repeat(1, 1, depth.shape[2], 1)
 
 
+def depth2points_perspec(coords, poses, Ks, depth):
+    """coords2rays + depth2points_perspec (render_ops.py:37-74): pinhole query rays.  coords (qn,rn,2), poses (qn,3,4) world->camera,
+    Ks (qn,3,3), depth (qn,rn,dn) -> pts, dir (qn,rn,dn,3); directions are not normalised before the points are formed."""
+    rot = poses[:, :, :3].unsqueeze(1).permute(0, 1, 3, 2)
+    trans = -rot @ poses[:, :, 3:].unsqueeze(1)
+    qn, rn, _ = coords.shape
+    centers = trans.repeat(1, rn, 1, 1).squeeze(-1)
+    hom = torch.cat([coords, torch.ones([qn, rn, 1], dtype=torch.float32)], 2)
+    cam_xyz = rot @ (torch.inverse(Ks).unsqueeze(1) @ hom.unsqueeze(3)) + trans
+    directions = cam_xyz.squeeze(3) - centers
+    pts = centers.unsqueeze(2) + directions.unsqueeze(2) * depth.unsqueeze(3)
+    que_dir = -directions / torch.norm(directions, dim=2, keepdim=True)
+    return pts, que_dir.unsqueeze(2).repeat(1, 1, depth.shape[2], 1)
+
+
 def project_points(dataset, height, width, w2c, pts):
     """project_points_ref_views (render_ops.py:158-230). w2c (rfn,3,4), pts (pn,3) ->
     pixel (rfn,pn,2), depth (rfn,pn), dir (rfn,pn,3)."""
@@ -422,11 +437,14 @@ def agg_sample_num(cfg, is_fine):
     return sub.get("sample_num", 64)
 
 
-def render_by_depth(cfg, W, que, ref, depth, is_fine, return_prj=False):
+def render_by_depth(cfg, W, que, ref, depth, is_fine, return_prj=False, is_perspec=False):
     """renderer.py:223-317 (eval, non-debug). `ref` holds imgs, w2c, depth_range, ray_feats, img_feats."""
     ds, h, w = cfg["dataset_name"], cfg["height"], cfg["width"]
     dists = depth2inv_dists(depth, que["depth_range"])
-    pts, que_dir = depth2points_spherical(ds, h, w, que["c2w"], que["coords"], depth)
+    if is_perspec:                                                        # renderer.py:231-232
+        pts, que_dir = depth2points_perspec(que["coords"], que["poses"], que["Ks"], depth)
+    else:
+        pts, que_dir = depth2points_spherical(ds, h, w, que["c2w"], que["coords"], depth)
     qn, rn, dn, _ = pts.shape
     rfn, _, ih, iw = ref["imgs"].shape
     pix, pdepth, pdir = project_points(ds, h, w, ref["w2c"], pts.reshape(qn * rn * dn, 3))
@@ -463,11 +481,11 @@ def render_by_depth(cfg, W, que, ref, depth, is_fine, return_prj=False):
     return out
 
 
-def render_rays(cfg, W, que, ref, keep_hit_prob=False):
+def render_rays(cfg, W, que, ref, keep_hit_prob=False, is_perspec=False):
     """render_impl (renderer.py:567-633), default (non-diner) eval branch, one ray batch."""
     rn = que["coords"].shape[1]
     depth = sample_depth(cfg["min_depth"], cfg["max_depth"], rn, cfg.get("depth_sample_num", 64), cfg["use_disp"])
-    out = render_by_depth(cfg, W, que, ref, depth, False)
+    out = render_by_depth(cfg, W, que, ref, depth, False, is_perspec=is_perspec)
     out["que_depth"] = depth
     if cfg.get("use_hierarchical_sampling", False):
         fine = sample_fine_depth(depth, out["hit_prob_nr"], que["depth_range"], cfg.get("fine_depth_sample_num", 64),
@@ -476,7 +494,7 @@ def render_rays(cfg, W, que, ref, keep_hit_prob=False):
             fdepth = torch.sort(torch.cat([depth, fine], -1), -1)[0]
         else:
             fdepth = torch.sort(fine, -1)[0]
-        fout = render_by_depth(cfg, W, que, ref, fdepth, not cfg.get("one_mlp", False))
+        fout = render_by_depth(cfg, W, que, ref, fdepth, not cfg.get("one_mlp", False), is_perspec=is_perspec)
         if cfg.get("render_c2f_all", False):                              # renderer.py:484-521: coarse + fine samples together
             z, idx = torch.cat([depth, fdepth], 2).sort()
             col = torch.gather(torch.cat([out["colors_nr"], fout["colors_nr"]], 2), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 3))

@@ -115,7 +115,7 @@ class RenderArgs(ctypes.Structure):
         ("fine_inds", _P), ("prob_dbg", _P), ("prj_dbg", _P), ("feat_dbg", _P),
         ("stage_mask", _I), ("mlp_bf16", _I), ("sched", _P), ("weights16", _P),
         ("prj_in", _P), ("feat_in", _P), ("prob_in", _P), ("que_dir_in", _P), ("interval_in", _P), ("dec_dbg", _P),
-        ("wo_geometry", _I), ("wo_appearance", _I),
+        ("wo_geometry", _I), ("wo_appearance", _I), ("ray_dirs", _P),
     ]
 
 

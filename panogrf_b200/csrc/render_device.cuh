@@ -410,15 +410,20 @@ __device__ __forceinline__ RowGeom row_geometry(const pgrf_render_args& a, int v
   } else {
     ray = (int)(g / a.dn); s = (int)(g % a.dn);
   }
-  const float cx = __ldg(a.coords + 2 * (size_t)ray), cy = __ldg(a.coords + 2 * (size_t)ray + 1);
   const float depth = __ldg(a.depth + (size_t)ray * a.depth_ray_stride + s);
-  float dx, dy, dz;
-  // `.long()` truncation of the pixel coordinate (render_ops.py:96-97)
-  equi_unit_dir<FAST>(a.dataset, (float)(long long)cx, (float)(long long)cy, a.H, a.W, dx, dy, dz);
   const float* c = a.que_c2w;  // (3,4) row-major
-  const float rdx = c[0] * dx + c[1] * dy + c[2] * dz;
-  const float rdy = c[4] * dx + c[5] * dy + c[6] * dz;
-  const float rdz = c[8] * dx + c[9] * dy + c[10] * dz;
+  float rdx, rdy, rdz;
+  if (a.ray_dirs) {   // perspective / cube rays: the caller's world-space directions (render_ops.py:37-74)
+    rdx = __ldg(a.ray_dirs + 3 * (size_t)ray); rdy = __ldg(a.ray_dirs + 3 * (size_t)ray + 1); rdz = __ldg(a.ray_dirs + 3 * (size_t)ray + 2);
+  } else {
+    const float cx = __ldg(a.coords + 2 * (size_t)ray), cy = __ldg(a.coords + 2 * (size_t)ray + 1);
+    float dx, dy, dz;
+    // `.long()` truncation of the pixel coordinate (render_ops.py:96-97)
+    equi_unit_dir<FAST>(a.dataset, (float)(long long)cx, (float)(long long)cy, a.H, a.W, dx, dy, dz);
+    rdx = c[0] * dx + c[1] * dy + c[2] * dz;
+    rdy = c[4] * dx + c[5] * dy + c[6] * dz;
+    rdz = c[8] * dx + c[9] * dy + c[10] * dz;
+  }
   const float p0 = c[3] + rdx * depth, p1 = c[7] + rdy * depth, p2 = c[11] + rdz * depth;
   float q0, q1, q2;   // que_dir
   if (FAST) {

@@ -769,7 +769,7 @@ extern "C" int pgrf_render_pass_fwd(const pgrf_render_args* args, void* stream) 
   PGRF_REQUIRE(!(dict_in || a.dec_dbg) || !a.mlp_bf16, "render: prj_in / feat_in / prob_in / dec_dbg exist on the fp32 path only");
   PGRF_REQUIRE(!a.prj_in || (a.que_dir_in && (a.interval_in || a.prob_in || a.depth)),
                "render: prj_in needs que_dir_in and interval_in (or depth, or prob_in)");
-  PGRF_REQUIRE(a.prj_in || (a.coords && a.que_c2w && a.ref_w2c), "render: null pointer argument (coords / que_c2w / ref_w2c)");
+  PGRF_REQUIRE(a.prj_in || ((a.coords || a.ray_dirs) && a.que_c2w && a.ref_w2c), "render: null pointer argument (coords / que_c2w / ref_w2c)");
   PGRF_REQUIRE(a.feat_in || (a.imgs_cl && a.img_feats_cl && a.ray_feats_cl), "render: null pointer argument (source maps)");
   PGRF_REQUIRE(a.depth || (a.prj_in && (a.interval_in || a.prob_in) && !a.render_depth && !a.fine_depth),
                "render: depth may only be omitted with prj_in + interval_in/prob_in and without render_depth / fine sampling");

@@ -59,7 +59,8 @@ extern "C" int pgrf_render_view_fwd(const pgrf_render_view_args* va, void* strea
     const int n = base.rn - r0 < va->rays_per_launch ? base.rn - r0 : va->rays_per_launch;
     pgrf_render_args c = base;
     c.rn = n;
-    c.coords = base.coords + 2 * (size_t)r0;
+    c.coords = base.coords ? base.coords + 2 * (size_t)r0 : nullptr;
+    c.ray_dirs = base.ray_dirs ? base.ray_dirs + 3 * (size_t)r0 : nullptr;
     c.depth = base.depth + (size_t)r0 * base.depth_ray_stride;
     c.pixel_colors = base.pixel_colors + 3 * (size_t)r0;
     if (base.render_depth) c.render_depth = base.render_depth + r0;

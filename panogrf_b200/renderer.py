@@ -306,6 +306,24 @@ def to_channels_last(x, pad_to=None):
     return out
 
 
+def perspective_ray_dirs(que_imgs_info):
+    """coords2rays (network/render_ops.py:37-59) for ONE query view: pixel coords (1,rn,2) + world->camera `poses` (1,3,4) + `Ks`
+    (1,3,3) -> (c2w (3,4), directions (rn,3)) with the reference's op order (K^-1 @ [x,y,1], rotate + translate, subtract the
+    centre).  The directions are NOT normalised, exactly like the reference's."""
+    coords, poses, Ks = que_imgs_info["coords"].float(), que_imgs_info["poses"].float(), que_imgs_info["Ks"].float()
+    assert poses.shape[0] == 1, "que_imgs_info poses.shape[0]=1"
+    rot = poses[:, :, :3].unsqueeze(1).permute(0, 1, 3, 2)
+    trans = -rot @ poses[:, :, 3:].unsqueeze(1)
+    rfn, rn, _ = coords.shape
+    centers = trans.repeat(1, rn, 1, 1).squeeze(-1)
+    hom = torch.cat([coords, torch.ones([rfn, rn, 1], dtype=torch.float32, device=coords.device)], 2)
+    cam_xyz = torch.inverse(Ks).unsqueeze(1) @ hom.unsqueeze(3)
+    cam_xyz = rot @ cam_xyz + trans
+    directions = cam_xyz.squeeze(3) - centers
+    c2w = torch.cat([rot[0, 0], trans[0, 0]], 1)                      # (3,4): [R^T | -R^T t]
+    return c2w.contiguous(), directions[0].contiguous()
+
+
 def tensor_version(t):
     """In-place version counter of a tensor, or None when it is not tracked (tensors created under torch.inference_mode):
     such tensors are never cached."""
@@ -427,6 +445,8 @@ class NeuralRayBaseRenderer(nn.Module):
         a.use_vis = int(bool(self.dist_decoder.cfg["use_vis"]))
         a.bias_val = float((self.fine_dist_decoder if fine_net else self.dist_decoder).cfg["bias_val"])
         a.coords, a.depth, a.depth_ray_stride = _lib.ptr(coords), _lib.ptr(depth), depth_stride
+        if ctx.get("ray_dirs") is not None:
+            a.ray_dirs = _lib.ptr(ctx["ray_dirs"][r0:r0 + rn])
         a.que_c2w, a.que_near, a.que_far = _lib.ptr(ctx["c2w"]), ctx["que_near"], ctx["que_far"]
         a.ref_w2c, a.ref_depth_range = _lib.ptr(ctx["w2c"]), _lib.ptr(ctx["ref_range"])
         a.imgs_cl, a.img_h, a.img_w = _lib.ptr(ctx["imgs"]), ctx["imgs"].shape[1], ctx["imgs"].shape[2]
@@ -469,11 +489,18 @@ class NeuralRayBaseRenderer(nn.Module):
         _lib.check(rc, "pgrf_render_pass_fwd")
         return fine_depth
 
-    def _context(self, que_imgs_info, ref_imgs_info):
+    def _context(self, que_imgs_info, ref_imgs_info, is_perspec=False):
+        ctx = self._context_erp(que_imgs_info, ref_imgs_info, is_perspec)
+        if is_perspec:      # perspective / cube query rays (render_ops.py:61-74): explicit world-space directions
+            c2w, dirs = perspective_ray_dirs(que_imgs_info)
+            ctx["c2w"], ctx["ray_dirs"] = c2w.to(ctx["w2c"].device), dirs.to(ctx["w2c"].device)
+        return ctx
+
+    def _context_erp(self, que_imgs_info, ref_imgs_info, is_perspec=False):
         imgs = ref_imgs_info["imgs"]
         _lib.require_cuda(imgs, ref_imgs_info["ray_feats"], ref_imgs_info["img_feats"], que_imgs_info["coords"])
         dev = imgs.device
-        c2w = que_imgs_info["c2w"]
+        c2w = que_imgs_info["c2w"] if not is_perspec else que_imgs_info["poses"]
         assert c2w.shape[0] == 1, "que_imgs_info c2w.shape[0]=1"                 # render_ops.py:89
         if ref_imgs_info["ray_feats"].shape[1] != 32 or ref_imgs_info["img_feats"].shape[1] != 32:
             raise _lib.PanoGRFError("ray_feats / img_feats must have 32 channels")
@@ -546,12 +573,12 @@ class NeuralRayBaseRenderer(nn.Module):
         """network/renderer.py:567-633 (default, non-diner branch) for the rays in que_imgs_info['coords']."""
         if is_train:
             raise NotImplementedError("panogrf_b200 renderer: only the eval path (is_train=False) is implemented")
-        if is_perspec:
-            raise NotImplementedError("perspective (cube) query rays are outside the ERP hot path")
         cfg = self.cfg
         if cfg.get("diner_depth_guided_sampling", False):
+            if is_perspec:
+                raise NotImplementedError("depth-guided placement is implemented for ERP query rays only")
             return self._render_diner(que_imgs_info, ref_imgs_info, keep_hit_prob=True)
-        ctx = _ctx or self._context(que_imgs_info, ref_imgs_info)
+        ctx = _ctx or self._context(que_imgs_info, ref_imgs_info, is_perspec)
         coords = que_imgs_info["coords"]
         assert coords.shape[0] == 1
         coords2 = coords[0].float().contiguous()
@@ -672,8 +699,10 @@ class NeuralRayBaseRenderer(nn.Module):
             ref_imgs_info["img_feats"] = feats
             ref_imgs_info["ray_feats"] = self.vis_encoder(ref_imgs_info["ray_feats"], feats)
         if self.cfg.get("diner_depth_guided_sampling", False):
+            if is_perspec:
+                raise NotImplementedError("depth-guided placement is implemented for ERP query rays only")
             return self._render_diner(que_imgs_info, ref_imgs_info, keep_hit_prob)
-        ctx = self._context(que_imgs_info, ref_imgs_info)
+        ctx = self._context(que_imgs_info, ref_imgs_info, is_perspec)
         coords = que_imgs_info["coords"]
         assert coords.shape[0] == 1
         rn = coords.shape[1]
@@ -817,6 +846,10 @@ class NeuralRayBaseRenderer(nn.Module):
         depth_table = self._cached_table(("coarse", dn, bool(cfg["use_disp"]), float(cfg["min_depth"]), float(cfg["max_depth"])),
                                          dev, lambda: coarse_depth_table(cfg, dn, cfg["use_disp"]))
         a.coords, a.depth, a.depth_ray_stride = _lib.ptr(coords2), _lib.ptr(depth_table), 0
+        if ctx.get("ray_dirs") is not None:
+            a.ray_dirs = _lib.ptr(ctx["ray_dirs"])
+        a.wo_geometry = int(bool(self.agg_net.cfg.get("wo_geometry")))
+        a.wo_appearance = int(bool(self.agg_net.cfg.get("wo_appearance")))
         a.que_c2w, a.que_near, a.que_far = _lib.ptr(ctx["c2w"]), ctx["que_near"], ctx["que_far"]
         a.ref_w2c, a.ref_depth_range = _lib.ptr(ctx["w2c"]), _lib.ptr(ctx["ref_range"])
         a.imgs_cl, a.img_h, a.img_w = _lib.ptr(ctx["imgs"]), ctx["imgs"].shape[1], ctx["imgs"].shape[2]
@@ -900,9 +933,9 @@ class NeuralRayBaseRenderer(nn.Module):
 
     def render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, is_fine, is_perspec=False):
         """network/renderer.py:223-317 for explicit per-ray sample depths (qn=1,rn,dn)."""
-        if is_train or is_perspec:
-            raise NotImplementedError("only the eval ERP path is implemented")
-        ctx = self._context(que_imgs_info, ref_imgs_info)
+        if is_train:
+            raise NotImplementedError("only the eval path is implemented")
+        ctx = self._context(que_imgs_info, ref_imgs_info, is_perspec)
         coords2 = que_imgs_info["coords"][0].float().contiguous()
         rn, dn = coords2.shape[0], que_depth.shape[-1]
         dev = coords2.device

@@ -148,6 +148,22 @@ def make_render_inputs(name, seed=0):
     return cfg, que, ref
 
 
+# perspective (pinhole) query rays, renderer.render_impl(..., is_perspec=True): render_ops.py:37-74
+PERSPEC_CASES = {"render_m3d_perspec": dict(base="render_m3d_2src", img_hw=(24, 32), focal=20.0, n_rays=50)}
+
+
+def make_perspec_inputs(name):
+    c = PERSPEC_CASES[name]
+    cfg, que, ref = make_render_inputs(c["base"])
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    ph, pw = c["img_hw"]
+    perm = torch.randperm(ph * pw, generator=gen)[:c["n_rays"]]
+    coords = torch.stack([(perm % pw).float() + 0.25, (perm // pw).float() + 0.5], -1)[None]      # non-integer pixel centres
+    K = torch.tensor([[c["focal"], 0.0, pw / 2.0], [0.0, c["focal"] * 1.1, ph / 2.0], [0.0, 0.0, 1.0]])[None]
+    que = {"coords": coords, "poses": que["w2c"].clone(), "Ks": K, "depth_range": que["depth_range"]}
+    return cfg, que, ref
+
+
 RENDER_WEIGHT_PREFIXES = ("dist_decoder.", "fine_dist_decoder.", "agg_net.", "fine_agg_net.")
 
 

@@ -63,5 +63,27 @@ def gen_render(only=None):
         print(name, {k: tuple(v.shape) for k, v in out.items()})
 
 
+def gen_perspec(only=None):
+    for name in cases.PERSPEC_CASES:
+        if only and name not in only:
+            continue
+        cfg, que, ref = cases.make_perspec_inputs(name)
+        net = build_reference_renderer(cfg, seed=sum(map(ord, name)))
+        with torch.no_grad():
+            out = net.render_impl(dict(que), dict(ref), False, is_perspec=True)
+        blob = {}
+        for k, v in que.items():
+            blob["que." + k] = v.numpy()
+        for k, v in ref.items():
+            blob["ref." + k] = v.numpy()
+        for k, v in hot_weights(net).items():
+            blob["w." + k] = v.numpy()
+        for k, v in out.items():
+            blob["out." + k] = v.float().numpy() if v.dtype != torch.bool else v.numpy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        print(name, {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    gen_render(sys.argv[1:] or None)      # optional: names of the cases to (re)generate
+    gen_render(sys.argv[1:] or None)
+    gen_perspec(sys.argv[1:] or None)      # optional: names of the cases to (re)generate

@@ -162,3 +162,23 @@ def test_render_emits_pixel_colors_gt_like_the_reference():
     for k in ("pixel_colors_gt", "pixel_colors_gt_fine"):
         assert k in out and float((out[k].cpu() - want).abs().max()) < 1e-5
     assert bool(torch.isfinite(out["pixel_colors_nr_fine"]).all())
+
+
+def test_pose_loop_driver_renders_views():
+    """f4: the reference's render script loop (render.py:249-291) around the fused renderer: build_render_imgs_info per pose,
+    `renderer(data)`, uint8 image + normalised depth back; the first view equals a direct render() of the same pose."""
+    import numpy as np
+    import panogrf_b200 as pg
+    from panogrf_b200 import driver
+    cfg, que, ref = cases.make_render_inputs("render_m3d_2src")
+    h, w = int(cfg["height"]), int(cfg["width"])
+    net = pg.NeuralRayBaseRenderer(cfg).cuda().eval()
+    poses = [que["w2c"][0].numpy().astype(np.float64), np.concatenate([np.eye(3), [[0.1], [0.0], [0.2]]], 1)]
+    imgs, depths = driver.render_poses(net, ref, poses, [(h, w)] * 2, [(0.5, 15.0)] * 2)
+    assert len(imgs) == 2 and imgs[0].shape == (h, w, 3) and imgs[0].dtype == np.uint8 and depths[1].shape == (h, w)
+    q0 = driver.to_cuda(driver.imgs_info_to_torch(driver.build_render_imgs_info(poses[0], (h, w), (0.5, 15.0))))
+    direct = net.render(q0, {k: v.cuda() for k, v in ref.items()}, False)["pixel_colors_nr_fine"].cpu().numpy().reshape(h, w, 3)
+    assert np.array_equal(imgs[0], driver.color_map_backward(direct))
+    m = driver.WSPSNR()
+    a = torch.from_numpy(imgs[0].astype(np.float32) / 255)[None]
+    assert float(m.ws_psnr(a, a + 0.01)[0]) > 39.0

@@ -59,3 +59,13 @@ def test_sample_depth_and_dists_shapes():
     assert float(dist[0, 0, -1]) == 1e6 and bool((dist[..., :-1] > 0).all())
     d2 = orender.sample_depth(0.5, 15.0, 3, 8, False)
     assert torch.allclose(d2[0, 0], torch.linspace(0.5, 15.0, 8))
+
+
+def test_oracle_perspective_rays_match_reference_golden():
+    """is_perspec (render_ops.py:37-74): pinhole query rays through the same renderer."""
+    name = "render_m3d_perspec"
+    cfg, _, _ = cases.make_perspec_inputs(name)
+    que, ref, W, gold = split_golden(load_golden(name))
+    out = orender.render_rays(cfg, W, que, ref, keep_hit_prob=True, is_perspec=True)
+    for k in ("pixel_colors_nr", "render_depth", "hit_prob_nr", "pixel_colors_nr_fine", "render_depth_fine"):
+        assert_close(out[k], gold[k], rtol=1e-4, atol=2e-5, what=f"{name}/{k}")

@@ -352,3 +352,22 @@ def test_bf16_tensor_core_attention_rays_kernel(variant):
             d = o["density_nr"]
             _close_bf16(out["density_nr"], d, f"{variant} tc={tc} density_nr", scale=float(d.abs().max()), atol=2.5e-2)
     assert bool(torch.isfinite(outs[1]["density_nr"]).all())
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_perspective_query_rays_match_reference_golden(dtype):
+    """is_perspec=True (network/render_ops.py:37-74): pinhole query rays (K, pose) instead of the ERP table — the kernels take the
+    world-space directions from the caller (pgrf_render_args.ray_dirs); golden from the reference's render_impl(is_perspec=True).
+    Both entry points: render_impl (per-pass calls) and render (whole-view C call)."""
+    name = "render_m3d_perspec"
+    cfg, _, _ = cases.make_perspec_inputs(name)
+    que, ref, W, gold = split_golden(load_golden(name))
+    net = build_renderer({**cfg, "mlp_dtype": dtype}, W)
+    for call in ("render_impl", "render"):
+        out = getattr(net, call)(cuda_dict(que), cuda_dict(ref), False, is_perspec=True)
+        torch.cuda.synchronize()
+        for k, scale in (("pixel_colors_nr", 1.0), ("render_depth", DEPTH_SCALE), ("pixel_colors_nr_fine", 1.0), ("render_depth_fine", DEPTH_SCALE)):
+            if dtype == "fp32":
+                assert_close(out[k], gold[k], rtol=1e-4, atol=5e-5, what=f"{call}/{k}")
+            elif not k.endswith("_fine"):
+                _close_bf16(out[k], gold[k], f"{call}/{k}", scale=scale)
