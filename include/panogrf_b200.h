@@ -306,6 +306,32 @@ PGRF_API int pgrf_project_gather_diner_fwd(const float* pts, long long pn, const
 PGRF_API int pgrf_depth2normal_fwd(const float* mvs_depth, int N, int H, int W, int dataset, float* raw_ws, signed char* off_ws,
                                    float* out_normal, void* stream);
 
+/* Equirectangular -> cubemap resampling of the MVS input path: replaces Equirec2Cube.run (UniFuse datasets/util.py:74-100) as called
+ * by e2c_process (network/omni_mvsnet/pipeline3_model.py:262-283; scipy map_coordinates order 1, mode 'wrap', on the CPU).
+ * equ (n_img,H,W,C) channels-last panoramas; coor_x / coor_y (face_w, 6*face_w) the reference's sampling coordinates (float32, built by
+ * the host with the reference's numpy expressions); cube (n_img, face_w, 6*face_w, C) in [F R B L U D] order. */
+PGRF_API int pgrf_e2c_fwd(const float* equ, int n_img, int H, int W, int C, const float* coor_x, const float* coor_y, int face_w,
+                          float* cube, void* stream);
+
+/* 3-D cost regulariser: the Conv3DBlockv2 / UNet2 stack (models/common_blocks.py:187-242, 366-503) applied to the cost
+ * volume by network/omni_mvsnet/pipeline3_model.py:847-855.  Activations are bf16 CHANNELS-LAST (B,D,H,W,C) with C padded to a
+ * multiple of 16; weights are packed by the host (panogrf_b200/regulariser.py: pack_conv) per (output-channel tile, tap, channel chunk).
+ *  - pgrf_conv3d_to_bf16_cl: fp32 (B,C,D,H,W) with arbitrary ELEMENT strides (so every cost-volume layout feeds it without a copy)
+ *    -> bf16 channels-last with Cpad channels (zeros above C);
+ *  - pgrf_conv3d_igemm_fwd: Conv3d(k=3) over WrapPadding3D(1) (zeros along D and H, wrap along W) + bias (+ LeakyReLU 0.01 if act) of
+ *    the channel concatenation [xa (Ca) | xb (Cb, may be NULL/0)] -> y (Cout channels); tcgen05 implicit GEMM;
+ *  - pgrf_conv3d_cout1_fwd: the same convolution with ONE output channel, fp32 output (B,D,H,W); input either the bf16 pair or a
+ *    single-channel fp32 volume xf; w is fp32 [27][Cin] (tap-major);
+ *  - pgrf_avgpool3d2_fwd: AvgPool3d(2); pgrf_upsample3d2_fwd: F.interpolate(scale_factor=2, mode='trilinear') (align_corners False). */
+PGRF_API int pgrf_conv3d_to_bf16_cl(const float* x, long long sb, long long sc, long long sd, long long sh, long long sw, int B, int C,
+                                    int D, int H, int W, int Cpad, void* y, void* stream);
+PGRF_API int pgrf_conv3d_igemm_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, int Cout,
+                                   int B, int D, int H, int W, int act, void* stream);
+PGRF_API int pgrf_conv3d_cout1_fwd(const void* xa, int Ca, const void* xb, int Cb, const float* xf, const float* w, float bias, int B,
+                                   int D, int H, int W, int act, float* out, void* stream);
+PGRF_API int pgrf_avgpool3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream);
+PGRF_API int pgrf_upsample3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream);
+
 /* MixtureLogisticsDistDecoder.compute_prob (dist_decoder.py:113-140) with get_near_far_points(is_ref=True) (:6-51):
  * depth (rfn,n), interval (n) shared by all views or (rfn,n) when interval_per_view, mean/var (rfn,n,2), vis (rfn,n) or NULL
  * (use_vis=False), aw (rfn,n), depth_range (rfn,2); n = rays*dn -> alpha, visibility, hit_prob (rfn,n) */

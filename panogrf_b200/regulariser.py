@@ -1,0 +1,188 @@
+"""3-D cost regulariser (`unet3d`) on the B200 tensor cores — SURVEY.md 8 f1.
+
+Mirrors what the reference builds in models/test_models.py:81-146 (initialize_cost_volume_network: a UNet2 of Conv3DBlockv2 with
+WrapPadding3D, LeakyReLU, AvgPool3d(2), trilinear x2 upsampling) and applies at network/omni_mvsnet/pipeline3_model.py:847-855
+(`self.unet3d(cost_volume)`): same constructor meaning (`size`, `num_layer`), same parameter names
+(`encoders.{i}.conv{1,2}.{weight,bias}`, `decoders.{i}.conv{1,2}.*`) so a reference state_dict loads with `load_state_dict`, and the
+same module construction order so that a seeded construction draws the same initial weights as the reference's.
+
+The forward pass runs through the C ABI only (csrc/conv3d.cu): activations bf16 channels-last, 3x3x3 convolutions as tcgen05
+implicit GEMMs with the wrap/zero padding folded into the operand gather, fp32 accumulation, bias + LeakyReLU in the epilogue, the
+U-Net's concatenations as a second operand pointer.  Inference only (the MVS depth network is frozen at render time,
+pipeline3_model.py:647).
+"""
+import torch
+from torch import nn
+
+from . import _lib
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def chunk_size(ca, cb):
+    """Channels per pipeline stage: <= 64, divides both inputs of a concatenation (csrc/conv3d.cu pgrf_conv3d_igemm_fwd)."""
+    kc = min(ca + cb, 64)
+    while ca % kc or cb % kc:
+        kc //= 2
+    return kc
+
+
+def pack_conv(weight, bias, ca, cb, ca_pad, cb_pad):
+    """(Co, ca+cb, 3,3,3) conv weights -> the kernel's operand blocks [n_tiles][27][n_cc][KC/8][NT][8] bf16 (+ padded fp32 bias).
+
+    Input channel ci sits at position ci (first input) or ca_pad + ci - ca (second input) of the padded K axis."""
+    co = weight.shape[0]
+    co_pad = _pad16(co)
+    nt = min(128, co_pad)
+    assert co_pad % nt == 0, f"C_out={co} unsupported"
+    kpad = ca_pad + cb_pad
+    kc = chunk_size(ca_pad, cb_pad)
+    w = weight.detach().float().reshape(co, ca + cb, 27).permute(0, 2, 1)            # (co, tap, ci), tap = kd*9 + kh*3 + kw
+    wp = torch.zeros((co_pad, 27, kpad), device=w.device, dtype=torch.float32)
+    wp[:co, :, :ca] = w[:, :, :ca]
+    if cb:
+        wp[:co, :, ca_pad:ca_pad + cb] = w[:, :, ca:]
+    wp = wp.reshape(co_pad // nt, nt, 27, kpad // kc, kc // 8, 8).permute(0, 2, 3, 4, 1, 5)
+    bp = torch.zeros(co_pad, device=w.device, dtype=torch.float32)
+    bp[:co] = bias.detach().float()
+    return wp.contiguous().to(torch.bfloat16), bp
+
+
+def pack_conv_cout1(weight, ca, cb, ca_pad, cb_pad):
+    """(1, ca+cb, 3,3,3) -> fp32 [27][ca_pad+cb_pad] for the single-output-channel kernel."""
+    w = weight.detach().float().reshape(ca + cb, 27).t()
+    wp = torch.zeros((27, ca_pad + cb_pad), device=w.device, dtype=torch.float32)
+    wp[:, :ca] = w[:, :ca]
+    if cb:
+        wp[:, ca_pad:ca_pad + cb] = w[:, ca:]
+    return wp.contiguous()
+
+
+class _Block(nn.Module):
+    """Parameter holder with Conv3DBlockv2's names (models/common_blocks.py:366-445)."""
+
+    def __init__(self, cin, cout, pool):
+        super().__init__()
+        self.conv1 = nn.Conv3d(cin, cout, kernel_size=(3, 3, 3), padding=0)
+        self.conv2 = nn.Conv3d(cout, cout, kernel_size=(3, 3, 3), padding=0)
+        self.pool = pool
+
+
+class CostRegulariser3D(nn.Module):
+    """`unet3d` of the reference: (B, 2^(size+1), D, H, W) cost volume -> (B, 1, D, H, W) regularised cost."""
+
+    def __init__(self, size=4, num_layer=3):
+        super().__init__()
+        # construction order == models/test_models.py:113-146: the first decoder is created before the encoders
+        enc, dec = [], [_Block(2 ** (size + 3), 1, False)]
+        for i in range(num_layer):
+            ch = 2 ** (i + size + 1)
+            enc.append(_Block(ch, 2 * ch, True))
+            if i > 0:
+                dec.append(_Block(4 * ch, ch, False))
+        enc.append(_Block(2 ** (num_layer + size + 1), 2 ** (num_layer + size + 2), False))
+        self.encoders = nn.ModuleList(enc)
+        self.decoders = nn.ModuleList(dec)
+        self.in_channels = 2 ** (size + 1)
+        self._packed = {}
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    # ---- weights ----------------------------------------------------------------------------------------------------------------
+    def _pack(self, conv, ca, cb, ca_pad, cb_pad):
+        key = id(conv)
+        ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), str(conv.weight.device), ca, cb)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            if conv.weight.shape[0] == 1:
+                hit = (ver, pack_conv_cout1(conv.weight, ca, cb, ca_pad, cb_pad), float(conv.bias.detach().float().item()))
+            else:
+                hit = (ver,) + pack_conv(conv.weight, conv.bias, ca, cb, ca_pad, cb_pad)
+            self._packed[key] = hit
+        return hit[1], hit[2]
+
+    # ---- kernels ----------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _conv(lib, st, xa, ca_pad, xb, cb_pad, wpk, bias, co_pad, dims):
+        B, D, H, W = dims
+        y = torch.empty((B, D, H, W, co_pad), device=xa.device, dtype=torch.bfloat16)
+        _lib.check(lib.pgrf_conv3d_igemm_fwd(_lib.ptr(xa), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad, _lib.ptr(wpk),
+                                             _lib.ptr(bias), _lib.ptr(y), co_pad, B, D, H, W, 1, st), "pgrf_conv3d_igemm_fwd")
+        return y
+
+    def _block(self, lib, st, blk, xa, ca, xb, cb, dims):
+        """pad-conv1-lrelu-pad-conv2-lrelu of one block on [xa | xb]; returns the un-pooled bf16 activation and its channel count."""
+        ca_pad, cb_pad = xa.shape[-1], (xb.shape[-1] if xb is not None else 0)
+        co = blk.conv1.weight.shape[0]
+        w1, b1 = self._pack(blk.conv1, ca, cb, ca_pad, cb_pad)
+        t = self._conv(lib, st, xa, ca_pad, xb, cb_pad, w1, b1, _pad16(co), dims)
+        w2, b2 = self._pack(blk.conv2, co, 0, _pad16(co), 0)
+        return self._conv(lib, st, t, _pad16(co), None, 0, w2, b2, _pad16(co), dims), co
+
+    def forward(self, cost_volume):
+        """cost_volume (B, C, D, H, W) fp32 CUDA tensor with ANY strides (the permuted views the sweep returns are consumed in place)."""
+        _lib.require_cuda(cost_volume)
+        lib = _lib.load()
+        x = cost_volume.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        B, C, D, H, W = x.shape
+        n_enc = len(self.encoders)
+        f = 2 ** (n_enc - 1)
+        if C != self.in_channels:
+            raise RuntimeError(f"unet3d expects {self.in_channels} input channels, got {C}")       # the reference's conv would raise
+        if D % f or H % f or W % f:
+            raise RuntimeError(f"unet3d: D, H, W must be multiples of {f} (got {D}, {H}, {W}); the reference's skip concatenation fails "
+                               "on other sizes")
+        dev = x.device
+        if next(self.parameters()).device != dev:
+            raise RuntimeError("CostRegulariser3D parameters and input are on different devices; call .to(device) first")
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr()
+            cpad = _pad16(C)
+            a = torch.empty((B, D, H, W, cpad), device=dev, dtype=torch.bfloat16)
+            sb, sc, sd, sh, sw = x.stride()
+            _lib.check(lib.pgrf_conv3d_to_bf16_cl(_lib.ptr(x), sb, sc, sd, sh, sw, B, C, D, H, W, cpad, _lib.ptr(a), st),
+                       "pgrf_conv3d_to_bf16_cl")
+            dims = (B, D, H, W)
+            skips = []
+            ch = C
+            for i, blk in enumerate(self.encoders):
+                u, ch = self._block(lib, st, blk, a, ch, None, 0, dims)
+                skips.append((u, ch, dims))
+                if blk.pool:
+                    b_, d_, h_, w_ = dims
+                    a = torch.empty((b_, d_ // 2, h_ // 2, w_ // 2, u.shape[-1]), device=dev, dtype=torch.bfloat16)
+                    _lib.check(lib.pgrf_avgpool3d2_fwd(_lib.ptr(u), b_, d_, h_, w_, u.shape[-1], _lib.ptr(a), st), "pgrf_avgpool3d2_fwd")
+                    dims = (b_, d_ // 2, h_ // 2, w_ // 2)
+                else:
+                    a = u
+            n_dec = len(self.decoders)
+            for i in range(n_dec - 1, -1, -1):
+                b_, d_, h_, w_ = dims
+                up = torch.empty((b_, 2 * d_, 2 * h_, 2 * w_, a.shape[-1]), device=dev, dtype=torch.bfloat16)
+                _lib.check(lib.pgrf_upsample3d2_fwd(_lib.ptr(a), b_, d_, h_, w_, a.shape[-1], _lib.ptr(up), st), "pgrf_upsample3d2_fwd")
+                dims = (b_, 2 * d_, 2 * h_, 2 * w_)
+                if i == n_dec - 1:
+                    xb, cb = None, 0
+                else:
+                    xb, cb, sdims = skips[i]
+                    assert sdims == dims
+                blk = self.decoders[i]
+                if blk.conv1.weight.shape[0] > 1:
+                    a, ch = self._block(lib, st, blk, up, ch, xb, cb, dims)
+                    continue
+                # last decoder: (ch + cb) -> 1 -> 1, fp32
+                ca_pad, cb_pad = up.shape[-1], (xb.shape[-1] if xb is not None else 0)
+                w1, b1 = self._pack(blk.conv1, ch, cb, ca_pad, cb_pad)
+                t = torch.empty(dims, device=dev, dtype=torch.float32)
+                _lib.check(lib.pgrf_conv3d_cout1_fwd(_lib.ptr(up), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad, None,
+                                                     _lib.ptr(w1), b1, *dims, 1, _lib.ptr(t), st), "pgrf_conv3d_cout1_fwd")
+                w2, b2 = self._pack(blk.conv2, 1, 0, 1, 0)
+                out = torch.empty(dims, device=dev, dtype=torch.float32)
+                _lib.check(lib.pgrf_conv3d_cout1_fwd(None, 0, None, 0, _lib.ptr(t), _lib.ptr(w2), b2, *dims, 1, _lib.ptr(out), st),
+                           "pgrf_conv3d_cout1_fwd")
+                return out.unsqueeze(1)
+        raise RuntimeError("unet3d: the first decoder must have one output channel (models/test_models.py:113)")

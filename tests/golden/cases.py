@@ -283,3 +283,39 @@ def make_normal_inputs(name):
         d = d * (torch.rand(2, 1, h, w, generator=g) > holes)
     cfg = {"dataset_name": ds, "batch_size": 1, "height": h, "width": w}
     return cfg, d
+
+
+# ------------------------------------------------------------------------------------------------
+# equirect -> cubemap (UniFuse util.py Equirec2Cube, pipeline3_model.py:262-283 e2c_process)
+# ------------------------------------------------------------------------------------------------
+E2C_CASES = {"e2c_32x64_f16": (32, 64, 16), "e2c_24x48_f9": (24, 48, 9), "e2c_64x128_f32": (64, 128, 32)}
+
+
+def make_e2c_input(name):
+    import numpy as np
+    h, w, _ = E2C_CASES[name]
+    g = torch.Generator().manual_seed(500 + sorted(E2C_CASES).index(name))
+    return torch.rand(h, w, 3, generator=g).numpy().astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# 3-D cost regulariser `unet3d` (models/test_models.py:81-146, common_blocks.py:187-242, 366-503)
+# ------------------------------------------------------------------------------------------------
+UNET3D_CASES = {
+    # name: (size, input shape (B, 2^(size+1), D, H, W)); D, H, W divisible by 8 (three poolings)
+    "unet3d_s1": (1, (1, 4, 8, 8, 16)),
+    "unet3d_s2": (2, (2, 8, 8, 16, 16)),
+}
+
+
+UNET3D_STORE_WEIGHTS = {"unet3d_s1": True, "unet3d_s2": False}
+
+
+def unet3d_seed(name):
+    return sum(map(ord, name))
+
+
+def make_unet3d_input(name):
+    size, shape = UNET3D_CASES[name]
+    g = torch.Generator().manual_seed(300 + sorted(UNET3D_CASES).index(name))
+    return torch.rand(*shape, generator=g) * 2.0      # abs-diff costs are non-negative
