@@ -318,15 +318,19 @@ PGRF_API int pgrf_e2c_fwd(const float* equ, int n_img, int H, int W, int C, cons
  * multiple of 16; weights are packed by the host (panogrf_b200/regulariser.py: pack_conv) per (output-channel tile, tap, channel chunk).
  *  - pgrf_conv3d_to_bf16_cl: fp32 (B,C,D,H,W) with arbitrary ELEMENT strides (so every cost-volume layout feeds it without a copy)
  *    -> bf16 channels-last with Cpad channels (zeros above C);
- *  - pgrf_conv3d_igemm_fwd: Conv3d(k=3) over WrapPadding3D(1) (zeros along D and H, wrap along W) + bias (+ LeakyReLU 0.01 if act) of
- *    the channel concatenation [xa (Ca) | xb (Cb, may be NULL/0)] -> y (Cout channels); tcgen05 implicit GEMM;
- *  - pgrf_conv3d_cout1_fwd: the same convolution with ONE output channel, fp32 output (B,D,H,W); input either the bf16 pair or a
+ *  - pgrf_conv3d_fwd: Conv3d(k=3) over WrapPadding3D(1) (zeros along D and H, wrap along W) + bias (+ LeakyReLU 0.01 if act) of
+ *    the channel concatenation [xa (Ca) | xb (Cb, may be NULL/0)]; tcgen05 implicit GEMM.  Exactly one output: y = bf16 channels-last
+ *    with Cout channels, or yf = the first cout_real (of Cout padded) channels as fp32 planar (B,cout_real,D,H,W) — the
+ *    single-channel head of the last decoder keeps fp32.  Layers whose grid cannot fill the GPU split K over the tap rows and need
+ *    ws: pgrf_conv3d_workspace gives the number of floats (0 = none) for the same arguments;
+ *  - pgrf_conv3d_cout1_fwd: the same convolution with ONE output channel on the fp32 pipes (SIMT), fp32 output (B,D,H,W); input either the bf16 pair or a
  *    single-channel fp32 volume xf; w is fp32 [27][Cin] (tap-major);
  *  - pgrf_avgpool3d2_fwd: AvgPool3d(2); pgrf_upsample3d2_fwd: F.interpolate(scale_factor=2, mode='trilinear') (align_corners False). */
 PGRF_API int pgrf_conv3d_to_bf16_cl(const float* x, long long sb, long long sc, long long sd, long long sh, long long sw, int B, int C,
                                     int D, int H, int W, int Cpad, void* y, void* stream);
-PGRF_API int pgrf_conv3d_igemm_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, int Cout,
-                                   int B, int D, int H, int W, int act, void* stream);
+PGRF_API int pgrf_conv3d_workspace(int Ca, int Cb, int Cout, int B, int D, int H, int W, long long* ws_floats);
+PGRF_API int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
+                             int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, void* stream);
 PGRF_API int pgrf_conv3d_cout1_fwd(const void* xa, int Ca, const void* xb, int Cb, const float* xf, const float* w, float bias, int B,
                                    int D, int H, int W, int act, float* out, void* stream);
 PGRF_API int pgrf_avgpool3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream);

@@ -1,16 +1,18 @@
 // 3-D cost regulariser: the Conv3DBlockv2 / UNet2 stack of models/common_blocks.py:187-242, 366-503 as consumed by
 // network/omni_mvsnet/pipeline3_model.py:847-855, on the 5th-generation tensor cores.
 //
-//   conv3d_igemm_kernel  3x3x3 convolution (+ bias + LeakyReLU 0.01) as an implicit GEMM on tcgen05:
-//        M = 128 output voxels per CTA (thread <-> voxel <-> TMEM lane), N = a tile of output channels (16..128, fp32 accumulators in
-//        tensor memory), K = 27 taps x input channels, walked in stages of one (tap, <=64-channel chunk).
-//        A operand: activations are bf16 CHANNELS-LAST (B,D,H,W,C), so a voxel's channel chunk of one tap is one contiguous run:
-//        each thread gathers its row with 128-bit loads — WrapPadding3D (common_blocks.py:448-503: zeros along depth / height, wrap
-//        along width) is folded into the gather — and writes it k-chunk-major into the stage buffer.  B operand: the layer's weights
-//        pre-packed per (n-tile, tap, chunk) as a ready k-chunk-major block, fetched by ONE bulk copy (TMA) per stage.  3-stage ring,
-//        completion through tcgen05.commit -> mbarrier; the gather of stage i+1 overlaps the MMAs of stage i.  A second input pointer
-//        makes the U-Net's torch.cat((upsampled, skip), 1) free.
-//   conv3d_cout1_kernel  the two single-output-channel layers of the last decoder (128 -> 1, 1 -> 1): fp32 SIMT, fp32 output.
+//   conv3d_igemm_kernel / conv3d_igemm_row_kernel
+//        3x3x3 convolution (+ bias + LeakyReLU 0.01) as an implicit GEMM on tcgen05: M = 128 output voxels per CTA (voxel <-> TMEM
+//        lane), N = a tile of output channels (16..128, fp32 accumulators in tensor memory), K = 27 taps x input channels, walked in
+//        pipeline stages of one tap (per-tap variant) or one (kd, kh) tap row = three taps (row variant) of a <=64-channel chunk.
+//        A operand: activations are bf16 CHANNELS-LAST (B,D,H,W,C), so a voxel's channel chunk is one contiguous run: eight gather
+//        warps copy the runs with 16-byte cp.async straight into the k-chunk-major stage buffer — WrapPadding3D (common_blocks.py:
+//        448-503: zeros along depth / height, wrap along width) is folded into the addresses / zero-fill — and hand completion to the
+//        stage's mbarrier (cp.async.mbarrier.arrive), so nobody waits for its own loads.  B operand: the layer's weights pre-packed
+//        per (n-tile, tap, chunk) as ready k-chunk-major blocks, one bulk copy (TMA) each.  A ninth warp issues the MMAs and commits
+//        them to the stage's `free` barrier.  A second input pointer makes the U-Net's torch.cat((upsampled, skip), 1) free; layers
+//        whose grid cannot fill the GPU split K over the nine tap rows (conv3d_reduce_kernel sums the partial volumes).
+//   conv3d_cout1_kernel  single-output-channel layer on the fp32 pipes (the 1 -> 1 head of the last decoder), fp32 output.
 //   avgpool / trilinear  AvgPool3d(2) and the x2 trilinear upsampling (align_corners=False) of UNet2.forward on bf16 channels-last.
 // Numerics: bf16 operands, fp32 accumulation and activation (the reference's cuDNN convolutions run in TF32 on the same GPUs).
 #include <cuda_bf16.h>
@@ -20,114 +22,323 @@
 
 namespace pgrf {
 
-constexpr int kConvStages = 3;
-constexpr int kConvRows = 128;
+constexpr int kConvRows = 128;          // output voxels per CTA == TMEM lanes
+constexpr int kGatherThreads = 256;     // 8 gather / epilogue warps
+constexpr int kConvThreads = 288;       // + 1 MMA-issuing warp
+constexpr int kConvPad = 64;            // bytes appended to each k-chunk plane of the A stage (conflict-free 16-byte writes)
 
 struct ConvParams {
   const __nv_bfloat16* xa; int Ca;     // first input, channels-last, channel count (multiple of 16)
   const __nv_bfloat16* xb; int Cb;     // second input of a concatenation (or null / 0)
   const unsigned char* wpk;            // packed weights [n_tiles][27][n_cc][KC/8][NT][8] bf16
   const float* bias;                   // [Cout] (padded)
-  __nv_bfloat16* y; int Cout;          // output, channels-last, Cout (multiple of 16)
+  __nv_bfloat16* y; int Cout;          // bf16 channels-last output with Cout (multiple of 16) channels, or
+  float* yf; int cout_real;            // fp32 planar (B, cout_real, D, H, W) output of the first cout_real channels
   int B, D, H, W, KC, n_cc, act;
   long long n_vox;
+  int splits;                          // split-K over the 9 (kd, kh) tap rows: blockIdx.z accumulates 9/splits of them into
+  float* ws;                           // fp32 partial sums [splits][n_vox][Cout] (bias / activation applied by the reduction)
 };
 
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// mbarrier arrive triggered by the completion of all cp.async operations this thread issued before it (counts as one arrival)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Epilogue of both variants, 8 warps: warp w reads TMEM lanes 32 (w % 4).. (its quadrant) and the column half w / 4 of the tile.
+// + bias, LeakyReLU; bf16 16-byte channel runs, fp32 planar for the first cout_real channels, or raw split-K partial sums.
 template <int NT>
-__global__ void __launch_bounds__(kConvRows, 2) conv3d_igemm_kernel(const ConvParams p) {
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tb, int nt, int warp, int lane) {
+  constexpr int kHalf = NT >= 32 ? NT / 2 : NT;
+  const int q = warp & 3, h = warp >> 2;
+  if (NT < 32 && h) return;
+  const long long v = (long long)blockIdx.x * kConvRows + q * 32 + lane;
+  const bool row_ok = v < p.n_vox;
+  const uint32_t tq = tb + ((uint32_t)(q * 32) << 16) + h * kHalf;
+  const int cbase = nt * NT + h * kHalf;
+  const float* bias = p.bias + cbase;
+  const long long DHW = (long long)p.D * p.H * p.W;
+#pragma unroll
+  for (int c = 0; c < kHalf; c += 16) {
+    float a[16];
+    umma::ld16(tq + c, a);                                            // warp-collective: only the stores are predicated
+    if (p.splits > 1) {                                               // raw partial sums; conv3d_reduce_kernel finishes the layer
+      if (row_ok) {
+        float4* dst = reinterpret_cast<float4*>(p.ws + ((size_t)blockIdx.z * p.n_vox + v) * p.Cout + cbase + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+      }
+      continue;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      a[i] += __ldg(bias + c + i);
+      if (p.act) a[i] = a[i] > 0.f ? a[i] : 0.01f * a[i];
+    }
+    if (!row_ok) continue;
+    if (p.yf) {
+      const long long bi = v / DHW, rem = v - bi * DHW;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (cbase + c + i < p.cout_real) p.yf[(bi * p.cout_real + cbase + c + i) * DHW + rem] = a[i];
+    } else {
+      __nv_bfloat16* dst = p.y + (size_t)v * p.Cout + cbase + c;
+      reinterpret_cast<uint4*>(dst)[0] = make_uint4(umma::pack2(a[0], a[1]), umma::pack2(a[2], a[3]), umma::pack2(a[4], a[5]), umma::pack2(a[6], a[7]));
+      reinterpret_cast<uint4*>(dst)[1] = make_uint4(umma::pack2(a[8], a[9]), umma::pack2(a[10], a[11]), umma::pack2(a[12], a[13]), umma::pack2(a[14], a[15]));
+    }
+  }
+}
+
+// The MMA warp's loop, shared by both variants: one thread waits for a full stage, issues TAPS x KC/16 MMAs, commits to `free`.
+template <int NT, int S, int TAPS>
+__device__ __forceinline__ void conv_mma_loop(uint32_t tb, const unsigned char* As, int a_bytes, int a_pitch16, const unsigned char* Bs,
+                                              int b_bytes, int KC, int n_it, uint64_t* bar_full, uint64_t* bar_free, uint64_t* bar_done) {
+  int s = 0;
+  uint32_t ph = 0;
+#pragma unroll 1
+  for (int it = 0; it < n_it; ++it) {
+    mbar_wait(&bar_full[s], ph);
+    umma::fence_smem_to_async();          // cp.async wrote the stage through the generic proxy; the MMA reads through the async one
+    umma::fence_after_sync();
+#pragma unroll
+    for (int kw = 0; kw < TAPS; ++kw)
+      umma::gemm_issue(tb, As + s * a_bytes + kw * 16, a_pitch16, Bs + (s * TAPS + kw) * b_bytes, NT, NT, KC, it > 0 || kw > 0);
+    umma::commit(&bar_free[s]);
+    if (++s == S) { s = 0; ph ^= 1u; }
+  }
+  umma::commit(bar_done);
+}
+
+// Per-tap variant (any W).  Gather mapping: `kch` consecutive lanes copy one voxel's contiguous channel run (a warp request touches
+// 32/kch lines), each thread serving rows row0 + i * row_step, i < kch/2.  Per row: bit (kd*3+kh) = that tap row lies inside the
+// volume (zeros along depth / height otherwise), bits 9 / 10 = the voxel sits in the first / last column (wrap along width).
+template <int NT, int S>
+__global__ void __launch_bounds__(kConvThreads) conv3d_igemm_kernel(const ConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) uint64_t bar_full[kConvStages], bar_free[kConvStages], bar_done;
+  __shared__ __align__(8) uint64_t bar_full[S], bar_free[S], bar_done;
   const int r = threadIdx.x, warp = r >> 5;
-  const int a_bytes = p.KC * kConvRows * 2, b_bytes = p.KC * NT * 2;
+  const uint32_t a_pitch = kConvRows * 16 + kConvPad;       // bytes between k-chunk planes
+  const int kch = p.KC >> 3;                                // 16-byte chunks per row and stage (2, 4 or 8)
+  const int a_bytes = kch * a_pitch, b_bytes = p.KC * NT * 2;
   unsigned char* As = smem;
-  unsigned char* Bs = smem + kConvStages * a_bytes;
-  if (warp == 0) umma::tmem_alloc(&tmem_base_s, NT < 32 ? 32 : NT);
+  unsigned char* Bs = smem + S * a_bytes;
+  constexpr uint32_t kCols = NT < 32 ? 32 : NT;
+  if (warp == 8) umma::tmem_alloc(&tmem_base_s, kCols);
   if (r == 0) {
-    for (int s = 0; s < kConvStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_free[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], kGatherThreads + 1); mbar_init(&bar_free[s], 1); }
     mbar_init(&bar_done, 1);
   }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base_s;
-
-  // this thread's output voxel
-  const long long v = (long long)blockIdx.x * kConvRows + r;
-  const bool row_ok = v < p.n_vox;
-  long long t = row_ok ? v : 0;
-  const int x = (int)(t % p.W); t /= p.W;
-  const int y = (int)(t % p.H); t /= p.H;
-  const int d = (int)(t % p.D);
-  const int b = (int)(t / p.D);
   const int nt = blockIdx.y;
-  const unsigned char* wt = p.wpk + (size_t)nt * 27 * p.n_cc * b_bytes;
-  const int n_it = 27 * p.n_cc;
-  const int kch = p.KC >> 3;                         // 16-byte chunks per row and stage
+  const int n_taps = 27 / p.splits, tap0 = blockIdx.z * n_taps;       // this CTA's share of the taps
 
+  if (warp == 8) {
+    if (r == kGatherThreads)
+      conv_mma_loop<NT, S, 1>(tb, As, a_bytes, (int)(a_pitch >> 4), Bs, b_bytes, p.KC, n_taps * p.n_cc, bar_full, bar_free, &bar_done);
+  } else {
+    const int lanes_shift = kch == 8 ? 3 : (kch == 4 ? 2 : 1);
+    const int my_chunk = r & (kch - 1), row0 = r >> lanes_shift, row_step = kGatherThreads >> lanes_shift, n_rows = kch >> 1;
+    const long long vbase = (long long)blockIdx.x * kConvRows + row0;
+    const long long HW = (long long)p.H * p.W;
+    uint32_t rowinfo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rowinfo[i] = 0;
+      const long long vv = vbase + i * row_step;
+      if (i < n_rows && vv < p.n_vox) {
+        long long t = vv;
+        const int x = (int)(t % p.W); t /= p.W;
+        const int y = (int)(t % p.H); t /= p.H;
+        const int d = (int)(t % p.D);
+        uint32_t m = 0;
+        for (int kd = 0; kd < 3; ++kd)
+          for (int kh = 0; kh < 3; ++kh)
+            if (d + kd - 1 >= 0 && d + kd - 1 < p.D && y + kh - 1 >= 0 && y + kh - 1 < p.H) m |= 1u << (kd * 3 + kh);
+        rowinfo[i] = m | (x == 0 ? 512u : 0u) | (x == p.W - 1 ? 1024u : 0u);
+      }
+    }
+    const uint32_t adst0 = smem_u32(As) + my_chunk * a_pitch + row0 * 16;
+    const uint32_t dst_step = row_step * 16;
+    const unsigned char* wt = p.wpk + ((size_t)nt * 27 + tap0) * p.n_cc * b_bytes;
+    int s = 0;
+    uint32_t ph = 1;                                                    // parity of the `free` phase that precedes the first use
 #pragma unroll 1
-  for (int it = 0; it < n_it; ++it) {
-    const int s = it % kConvStages, use = it / kConvStages;
-    if (it >= kConvStages) mbar_wait(&bar_free[s], (use - 1) & 1);      // the MMAs that read this stage have completed
-    if (r == 0) {
-      mbar_expect_tx(&bar_full[s], b_bytes);
-      bulk_g2s(Bs + s * b_bytes, wt + (size_t)it * b_bytes, b_bytes, &bar_full[s]);
-    }
-    const int tap = it / p.n_cc, cc = it - tap * p.n_cc;
-    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-    const int dd = d + kd - 1, yy = y + kh - 1;
-    int xx = x + kw - 1;
-    xx = xx < 0 ? xx + p.W : (xx >= p.W ? xx - p.W : xx);             // wrap along width
-    const bool ok = row_ok && dd >= 0 && dd < p.D && yy >= 0 && yy < p.H;   // zeros along depth / height
-    const int c0 = cc * p.KC;
-    const __nv_bfloat16* src;
-    if (c0 < p.Ca) src = p.xa + ((((size_t)b * p.D + dd) * p.H + yy) * p.W + xx) * p.Ca + c0;
-    else src = p.xb + ((((size_t)b * p.D + dd) * p.H + yy) * p.W + xx) * p.Cb + (c0 - p.Ca);
-    unsigned char* arow = As + s * a_bytes + (size_t)r * 16;
-#pragma unroll 4
-    for (int j = 0; j < kch; ++j) {
-      uint4 q = make_uint4(0u, 0u, 0u, 0u);
-      if (ok) q = __ldg(reinterpret_cast<const uint4*>(src) + j);
-      *reinterpret_cast<uint4*>(arow + (size_t)j * kConvRows * 16) = q;
-    }
-    umma::fence_smem_to_async();
-    __syncthreads();
-    if (r == 0) {
-      mbar_wait(&bar_full[s], use & 1);
-      umma::fence_after_sync();
-      umma::gemm_issue(tb, As + s * a_bytes, kConvRows, Bs + s * b_bytes, NT, NT, p.KC, it > 0);
-      umma::commit(&bar_free[s]);
-    }
-  }
-  if (r == 0) umma::commit(&bar_done);
-  mbar_wait(&bar_done, 0);
-  umma::fence_after_sync();
-
-  // epilogue: + bias, LeakyReLU, bf16, 16-byte channel runs (the TMEM loads are warp-collective: only the stores are predicated)
-  {
-    const uint32_t tq = tb + ((uint32_t)(warp * 32) << 16);
-    __nv_bfloat16* dst = p.y + (size_t)(row_ok ? v : 0) * p.Cout + (size_t)nt * NT;
-    const float* bias = p.bias + nt * NT;
+    for (int tap = tap0; tap < tap0 + n_taps; ++tap) {
+      const int krow = tap / 3, kw = tap - krow * 3 - 1;                // krow = kd*3 + kh
+      const long long tap_off = (long long)(krow / 3 - 1) * HW + (long long)(krow % 3 - 1) * p.W + kw;
+      const uint32_t wrap_bit = kw < 0 ? 512u : (kw > 0 ? 1024u : 0u);
+      const long long wrap_off = kw < 0 ? p.W : -p.W;
+      long long nv[4];
+      uint32_t nb[4];
 #pragma unroll
-    for (int c = 0; c < NT; c += 16) {
-      float a[16];
-      umma::ld16(tq + c, a);
-      uint32_t q[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float u0 = a[2 * i] + __ldg(bias + c + 2 * i), u1 = a[2 * i + 1] + __ldg(bias + c + 2 * i + 1);
-        if (p.act) { u0 = u0 > 0.f ? u0 : 0.01f * u0; u1 = u1 > 0.f ? u1 : 0.01f * u1; }
-        q[i] = umma::pack2(u0, u1);
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = (rowinfo[i] >> krow) & 1u;
+        nb[i] = ok ? 16u : 0u;
+        nv[i] = ok ? vbase + i * row_step + tap_off + ((rowinfo[i] & wrap_bit) ? wrap_off : 0) : 0;
       }
-      if (row_ok) {
-        reinterpret_cast<uint4*>(dst + c)[0] = make_uint4(q[0], q[1], q[2], q[3]);
-        reinterpret_cast<uint4*>(dst + c)[1] = make_uint4(q[4], q[5], q[6], q[7]);
+      const __nv_bfloat16* src = p.xa + my_chunk * 8;
+      int cs = p.Ca, c_left = p.Ca;
+#pragma unroll 1
+      for (int cc = 0; cc < p.n_cc; ++cc) {
+        if (c_left == 0) { src = p.xb + my_chunk * 8; cs = p.Cb; c_left = p.Cb; }      // second input of the concatenation
+        mbar_wait(&bar_free[s], ph);                                    // the MMAs that read this stage have completed
+        if (r == 0) {
+          mbar_expect_tx(&bar_full[s], b_bytes);
+          bulk_g2s(Bs + s * b_bytes, wt, b_bytes, &bar_full[s]);
+        }
+        wt += b_bytes;
+        const uint32_t adst = adst0 + s * a_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < n_rows) cp_async16(adst + i * dst_step, src + (size_t)nv[i] * cs, nb[i]);
+        cp_async_arrive(&bar_full[s]);      // arrives when this thread's copies of the stage have landed; up to S stages in flight
+        src += p.KC;
+        c_left -= p.KC;
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
+    mbar_wait(&bar_done, 0);
+    umma::fence_after_sync();
+    conv_epilogue<NT>(p, tb, nt, warp, r & 31);
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tb, NT < 32 ? 32 : NT);
+  if (warp == 8) umma::tmem_dealloc(tb, kCols);
+}
+
+// Row variant (W % 128 == 0: every tile is a run of 128 voxels inside ONE image row).  A pipeline stage holds that run of one
+// (kd, kh) neighbour row plus its two wrap-around halo voxels — 130 operand rows — and serves all three kw taps: in the un-swizzled
+// k-chunk-major layout operand rows are 16 bytes apart, so tap kw is the same buffer with the descriptor start advanced by kw rows.
+// One gather (and one third of the copy instructions / L1TEX traffic) feeds three taps of MMAs.
+constexpr int kRowA = kConvRows + 2;
+constexpr int kRowPitch = kRowA * 16 + 32;        // bytes between k-chunk planes
+
+template <int NT, int S>
+__global__ void __launch_bounds__(kConvThreads) conv3d_igemm_row_kernel(const ConvParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar_full[S], bar_free[S], bar_done;
+  const int r = threadIdx.x, warp = r >> 5;
+  const int kch = p.KC >> 3;
+  const int a_bytes = kch * kRowPitch, b_bytes = p.KC * NT * 2;
+  unsigned char* As = smem;
+  unsigned char* Bs = smem + S * a_bytes;
+  constexpr uint32_t kCols = NT < 32 ? 32 : NT;
+  if (warp == 8) umma::tmem_alloc(&tmem_base_s, kCols);
+  if (r == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], kGatherThreads + 1); mbar_init(&bar_free[s], 1); }
+    mbar_init(&bar_done, 1);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = tmem_base_s;
+  const int nt = blockIdx.y;
+  const int n_krow = 9 / p.splits, krow0 = blockIdx.z * n_krow;
+
+  if (warp == 8) {
+    if (r == kGatherThreads)
+      conv_mma_loop<NT, S, 3>(tb, As, a_bytes, kRowPitch >> 4, Bs, b_bytes, p.KC, n_krow * p.n_cc, bar_full, bar_free, &bar_done);
+  } else {
+    const int lanes_shift = kch == 8 ? 3 : (kch == 4 ? 2 : 1);
+    const int my_chunk = r & (kch - 1), row0 = r >> lanes_shift, row_step = kGatherThreads >> lanes_shift, n_rows = kch >> 1;
+    // the tile: voxels [v0, v0 + 128) of image row (b, d, y), starting at column x0
+    const long long v0 = (long long)blockIdx.x * kConvRows;
+    const long long HW = (long long)p.H * p.W;
+    long long t = v0;
+    const int x0 = (int)(t % p.W); t /= p.W;
+    const int y = (int)(t % p.H); t /= p.H;
+    const int d = (int)(t % p.D);
+    // halo voxels (wrap along width): threads [0, kch) copy the left one (operand row 0), [kch, 2 kch) the right one (row 129)
+    const bool halo = r < 2 * kch;
+    const long long halo_off = r < kch ? (x0 == 0 ? (long long)p.W - 1 : -1) : (x0 + kConvRows == p.W ? (long long)kConvRows - p.W : kConvRows);
+    const int hc = r < kch ? r : r - kch;
+    const uint32_t hdst0 = smem_u32(As) + hc * kRowPitch + (r < kch ? 0 : kRowA - 1) * 16;
+    const uint32_t adst0 = smem_u32(As) + my_chunk * kRowPitch + (row0 + 1) * 16;
+    const uint32_t dst_step = row_step * 16;
+    const size_t wtap = (size_t)p.n_cc * b_bytes;                        // distance between the weight blocks of two taps
+    const unsigned char* wt = p.wpk + ((size_t)nt * 27 + krow0 * 3) * wtap;
+    int s = 0;
+    uint32_t ph = 1;
+#pragma unroll 1
+    for (int krow = krow0; krow < krow0 + n_krow; ++krow) {              // krow = kd*3 + kh
+      const int dd = d + krow / 3 - 1, yy = y + krow % 3 - 1;
+      const bool ok = dd >= 0 && dd < p.D && yy >= 0 && yy < p.H;        // zeros along depth / height (uniform over the tile)
+      const uint32_t nbytes = ok ? 16u : 0u;
+      const long long nv0 = ok ? v0 + (long long)(krow / 3 - 1) * HW + (long long)(krow % 3 - 1) * p.W : 0;
+      const long long nvr = ok ? nv0 + row0 : 0, nvh = ok ? nv0 + halo_off : 0;
+      const long long rstep = ok ? row_step : 0;
+      const __nv_bfloat16* src = p.xa;
+      int cs = p.Ca, c_left = p.Ca;
+#pragma unroll 1
+      for (int cc = 0; cc < p.n_cc; ++cc) {
+        if (c_left == 0) { src = p.xb; cs = p.Cb; c_left = p.Cb; }
+        mbar_wait(&bar_free[s], ph);
+        if (r == 0) {
+          mbar_expect_tx(&bar_full[s], 3 * b_bytes);
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) bulk_g2s(Bs + (s * 3 + kw) * b_bytes, wt + kw * wtap, b_bytes, &bar_full[s]);
+        }
+        wt += b_bytes;
+        const uint32_t adst = adst0 + s * a_bytes;
+        const __nv_bfloat16* rsrc = src + (size_t)nvr * cs + my_chunk * 8;
+        const size_t sstep = (size_t)rstep * cs;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < n_rows) cp_async16(adst + i * dst_step, rsrc + i * sstep, nbytes);
+        if (halo) cp_async16(hdst0 + s * a_bytes, src + (size_t)nvh * cs + hc * 8, nbytes);
+        cp_async_arrive(&bar_full[s]);
+        src += p.KC;
+        c_left -= p.KC;
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+      wt += 2 * wtap;                                                     // next tap row: skip the two taps already consumed
+    }
+    mbar_wait(&bar_done, 0);
+    umma::fence_after_sync();
+    conv_epilogue<NT>(p, tb, nt, warp, r & 31);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) umma::tmem_dealloc(tb, kCols);
+}
+
+// split-K reduction: sum of the partial volumes + bias + LeakyReLU -> bf16 channels-last (or fp32 planar); thread = (voxel, 8 channels)
+__global__ void __launch_bounds__(256) conv3d_reduce_kernel(const ConvParams p) {
+  const int C8 = p.Cout / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_vox * C8) return;
+  const long long v = i / C8;
+  const int c = (int)(i - v * C8) * 8;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = __ldg(p.bias + c + k);
+  for (int z = 0; z < p.splits; ++z) {
+    const float4* src = reinterpret_cast<const float4*>(p.ws + ((size_t)z * p.n_vox + v) * p.Cout + c);
+    const float4 q0 = __ldcs(src), q1 = __ldcs(src + 1);
+    a[0] += q0.x; a[1] += q0.y; a[2] += q0.z; a[3] += q0.w; a[4] += q1.x; a[5] += q1.y; a[6] += q1.z; a[7] += q1.w;
+  }
+  if (p.act) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = a[k] > 0.f ? a[k] : 0.01f * a[k];
+  }
+  if (p.yf) {
+    const long long DHW = (long long)p.D * p.H * p.W;
+    const long long bi = v / DHW, rem = v - bi * DHW;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c + k < p.cout_real) p.yf[(bi * p.cout_real + c + k) * DHW + rem] = a[k];
+  } else {
+    *reinterpret_cast<uint4*>(p.y + (size_t)v * p.Cout + c) =
+        make_uint4(umma::pack2(a[0], a[1]), umma::pack2(a[2], a[3]), umma::pack2(a[4], a[5]), umma::pack2(a[6], a[7]));
+  }
 }
 
 // single output channel (last decoder): fp32 SIMT.  in: bf16 channels-last (two concatenated inputs) or fp32 single channel
@@ -260,6 +471,12 @@ __global__ void __launch_bounds__(256) to_bf16_cl_kernel(const float* __restrict
 
 using namespace pgrf;
 
+namespace pgrf {
+int g_conv_stages = 0;   // pipeline depth of the conv3d kernels (pgrf_debug_set "conv_stages": 0 = automatic, else 3..6)
+int g_conv_row = 1;      // use the row variant when W % 128 == 0 (pgrf_debug_set "conv_row")
+int g_conv_splits = 0;   // split-K factor (pgrf_debug_set "conv_splits": 0 = automatic, else 1, 3 or 9)
+}
+
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 extern "C" int pgrf_conv3d_to_bf16_cl(const float* x, long long sb, long long sc, long long sd, long long sh, long long sw, int B, int C,
@@ -272,36 +489,111 @@ extern "C" int pgrf_conv3d_to_bf16_cl(const float* x, long long sb, long long sc
   return PGRF_OK;
 }
 
-extern "C" int pgrf_conv3d_igemm_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, int Cout,
-                                     int B, int D, int H, int W, int act, void* stream) {
-  PGRF_REQUIRE(xa && wpk && bias && y, "conv3d: null pointer argument");
-  PGRF_REQUIRE(Ca >= 16 && Ca % 16 == 0 && Cb % 16 == 0 && (Cb == 0 || xb) && Cout >= 16 && Cout % 16 == 0, "conv3d: channel counts must "
-               "be multiples of 16 (Ca=%d Cb=%d Cout=%d)", Ca, Cb, Cout);
-  ConvParams p;
-  p.xa = (const __nv_bfloat16*)xa; p.Ca = Ca; p.xb = (const __nv_bfloat16*)xb; p.Cb = Cb;
-  p.wpk = (const unsigned char*)wpk; p.bias = bias; p.y = (__nv_bfloat16*)y; p.Cout = Cout;
-  p.B = B; p.D = D; p.H = H; p.W = W; p.act = act;
+struct ConvPlan {
+  int KC, n_cc, NT, row, S, splits;
+  size_t smem;
+  dim3 grid;
+  long long ws_floats;
+};
+
+// tile / pipeline / split-K choice of one layer (shared by the launcher and the workspace query)
+static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, ConvPlan& pl) {
+  PGRF_REQUIRE(Ca >= 16 && Ca % 16 == 0 && Cb >= 0 && Cb % 16 == 0 && Cout >= 16 && Cout % 16 == 0, "conv3d: channel counts must be "
+               "multiples of 16 (Ca=%d Cb=%d Cout=%d)", Ca, Cb, Cout);
+  PGRF_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 2, "conv3d: bad volume %dx%dx%dx%d", B, D, H, W);
   const int Cin = Ca + Cb;
   int KC = Cin < 64 ? Cin : 64;
   while (Ca % KC || Cb % KC) KC >>= 1;           // a stage never straddles the two inputs of a concatenation
   PGRF_REQUIRE(KC >= 16, "conv3d: no common chunk size for Ca=%d Cb=%d", Ca, Cb);
-  p.KC = KC; p.n_cc = Cin / KC;
+  pl.KC = KC; pl.n_cc = Cin / KC;
+  pl.NT = Cout >= 128 ? 128 : Cout;
+  PGRF_REQUIRE(pl.NT == 16 || pl.NT == 32 || pl.NT == 64 || pl.NT == 128, "conv3d: Cout=%d unsupported", Cout);
+  PGRF_REQUIRE(Cout % pl.NT == 0, "conv3d: Cout=%d not a multiple of the channel tile", Cout);
+  const long long n_vox = (long long)B * D * H * W;
+  pl.grid = dim3(blocks_for(n_vox, kConvRows), (unsigned)(Cout / pl.NT), 1);
+  const long long n_cta = (long long)pl.grid.x * pl.grid.y;
+  pl.row = g_conv_row && W % kConvRows == 0;
+  const size_t stage = pl.row ? (size_t)(KC / 8) * kRowPitch + 3 * (size_t)KC * pl.NT * 2            // [130-row operand | three taps of weights]
+                              : (size_t)(KC / 8) * (kConvRows * 16 + kConvPad) + (size_t)KC * pl.NT * 2;
+  // split-K over the nine (kd, kh) tap rows when the (voxel tile x channel tile) grid cannot fill the GPU (2 CTAs per SM assumed)
+  pl.splits = 1;
+  if (g_conv_splits > 0) pl.splits = g_conv_splits;
+  else if (n_cta < 444) pl.splits = n_cta * 3 >= 740 ? 3 : 9;
+  PGRF_REQUIRE(pl.splits == 1 || pl.splits == 3 || pl.splits == 9, "conv3d: splits=%d (1, 3 or 9)", pl.splits);
+  // pipeline depth: as many stages as keep two CTAs on an SM (one CTA's epilogue hides behind the other's main loop), at least 2 / 3
+  const int s_min = pl.row ? 2 : 3, s_max = pl.row ? 4 : 6;
+  int S = (int)((113 * 1024) / stage);
+  S = S < s_min ? s_min : (S > s_max ? s_max : S);
+  if (!pl.row && S == 5) S = 4;
+  if (g_conv_stages) S = g_conv_stages < s_min ? s_min : (g_conv_stages > s_max ? s_max : g_conv_stages);
+  if (!pl.row && S == 5) S = 6;
+  pl.S = S;
+  pl.smem = S * stage;
+  PGRF_REQUIRE(pl.smem <= 227 * 1024, "conv3d: %zu bytes of shared memory", pl.smem);
+  pl.grid.z = pl.splits;
+  pl.ws_floats = pl.splits > 1 ? (long long)pl.splits * n_vox * Cout : 0;
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_conv3d_workspace(int Ca, int Cb, int Cout, int B, int D, int H, int W, long long* ws_floats) {
+  PGRF_REQUIRE(ws_floats, "conv3d_workspace: null pointer argument");
+  ConvPlan pl;
+  const int rc = conv3d_plan(Ca, Cb, Cout, B, D, H, W, pl);
+  if (rc != PGRF_OK) return rc;
+  *ws_floats = pl.ws_floats;
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
+                               int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, void* stream) {
+  PGRF_REQUIRE(xa && wpk && bias && ((y != nullptr) != (yf != nullptr)), "conv3d: null pointer argument (exactly one of y / yf)");
+  PGRF_REQUIRE(Cb == 0 || xb, "conv3d: Cb=%d without a second input", Cb);
+  PGRF_REQUIRE(!yf || (cout_real >= 1 && cout_real <= Cout), "conv3d: cout_real=%d outside [1, %d]", cout_real, Cout);
+  ConvPlan pl;
+  const int rc = conv3d_plan(Ca, Cb, Cout, B, D, H, W, pl);
+  if (rc != PGRF_OK) return rc;
+  PGRF_REQUIRE(pl.ws_floats == 0 || (ws && ws_floats >= pl.ws_floats), "conv3d: workspace of %lld floats needed (pgrf_conv3d_workspace), "
+               "%lld given", pl.ws_floats, ws ? ws_floats : 0LL);
+  ConvParams p;
+  p.xa = (const __nv_bfloat16*)xa; p.Ca = Ca; p.xb = (const __nv_bfloat16*)xb; p.Cb = Cb;
+  p.wpk = (const unsigned char*)wpk; p.bias = bias; p.y = (__nv_bfloat16*)y; p.Cout = Cout; p.yf = yf; p.cout_real = cout_real;
+  p.B = B; p.D = D; p.H = H; p.W = W; p.act = act; p.KC = pl.KC; p.n_cc = pl.n_cc;
   p.n_vox = (long long)B * D * H * W;
-  const int NT = Cout >= 128 ? 128 : Cout;
-  PGRF_REQUIRE(NT == 16 || NT == 32 || NT == 64 || NT == 128, "conv3d: Cout=%d unsupported", Cout);
-  PGRF_REQUIRE(Cout % NT == 0, "conv3d: Cout=%d not a multiple of the channel tile", Cout);
-  dim3 grid(blocks_for(p.n_vox, kConvRows), (unsigned)(Cout / NT));
-  const size_t smem = (size_t)kConvStages * (KC * kConvRows * 2 + KC * NT * 2);
+  p.splits = pl.splits; p.ws = ws;
   cudaStream_t st = (cudaStream_t)stream;
-#define PGRF_CONV(N)                                                                                                   \
-  case N:                                                                                                              \
-    PGRF_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    conv3d_igemm_kernel<N><<<grid, kConvRows, smem, st>>>(p);                                                          \
+  const dim3 grid = pl.grid;
+  const size_t smem = pl.smem;
+  const int S = pl.S;
+#define PGRF_CONV(K, N, SS)                                                                                \
+  {                                                                                                        \
+    PGRF_CUDA(cudaFuncSetAttribute(K<N, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    K<N, SS><<<grid, kConvThreads, smem, st>>>(p);                                                         \
+  }
+  if (pl.row) {
+#define PGRF_CONV_S(N)                                                                                     \
+  case N:                                                                                                  \
+    if (S == 2) PGRF_CONV(conv3d_igemm_row_kernel, N, 2) else if (S == 3) PGRF_CONV(conv3d_igemm_row_kernel, N, 3) \
+    else PGRF_CONV(conv3d_igemm_row_kernel, N, 4)                                                          \
     break;
-  switch (NT) { PGRF_CONV(16) PGRF_CONV(32) PGRF_CONV(64) PGRF_CONV(128) }
+    switch (pl.NT) { PGRF_CONV_S(16) PGRF_CONV_S(32) PGRF_CONV_S(64) PGRF_CONV_S(128) }
+#undef PGRF_CONV_S
+  } else {
+#define PGRF_CONV_S(N)                                                                                     \
+  case N:                                                                                                  \
+    if (S == 3) PGRF_CONV(conv3d_igemm_kernel, N, 3) else if (S == 4) PGRF_CONV(conv3d_igemm_kernel, N, 4) \
+    else PGRF_CONV(conv3d_igemm_kernel, N, 6)                                                              \
+    break;
+    switch (pl.NT) { PGRF_CONV_S(16) PGRF_CONV_S(32) PGRF_CONV_S(64) PGRF_CONV_S(128) }
+#undef PGRF_CONV_S
+  }
 #undef PGRF_CONV
   count_launch();
   PGRF_CUDA(cudaGetLastError());
+  if (pl.splits > 1) {
+    conv3d_reduce_kernel<<<blocks_for(p.n_vox * (Cout / 8), 256), 256, 0, st>>>(p);
+    count_launch();
+    PGRF_CUDA(cudaGetLastError());
+  }
   return PGRF_OK;
 }
 

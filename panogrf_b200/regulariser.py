@@ -11,6 +11,8 @@ implicit GEMMs with the wrap/zero padding folded into the operand gather, fp32 a
 U-Net's concatenations as a second operand pointer.  Inference only (the MVS depth network is frozen at render time,
 pipeline3_model.py:647).
 """
+import ctypes
+
 import torch
 from torch import nn
 
@@ -22,7 +24,7 @@ def _pad16(c):
 
 
 def chunk_size(ca, cb):
-    """Channels per pipeline stage: <= 64, divides both inputs of a concatenation (csrc/conv3d.cu pgrf_conv3d_igemm_fwd)."""
+    """Channels per pipeline stage: <= 64, divides both inputs of a concatenation (csrc/conv3d.cu conv3d_plan)."""
     kc = min(ca + cb, 64)
     while ca % kc or cb % kc:
         kc //= 2
@@ -60,6 +62,32 @@ def pack_conv_cout1(weight, ca, cb, ca_pad, cb_pad):
     return wp.contiguous()
 
 
+def conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels=0, ws_cache=None, lib=None, st=None):
+    """One Conv3d(3x3x3) + WrapPadding3D + bias + LeakyReLU layer on [xa | xb] (bf16 channels-last, packed weights from `pack_conv`).
+    Returns bf16 channels-last (B,D,H,W,co_pad), or fp32 (B,f32_channels,D,H,W) when f32_channels > 0."""
+    lib = lib or _lib.load()
+    st = _lib.stream_ptr() if st is None else st
+    B, D, H, W = dims
+    ca_pad, cb_pad = xa.shape[-1], (xb.shape[-1] if xb is not None else 0)
+    need = ctypes.c_longlong(0)
+    _lib.check(lib.pgrf_conv3d_workspace(ca_pad, cb_pad, co_pad, B, D, H, W, ctypes.byref(need)), "pgrf_conv3d_workspace")
+    ws = None
+    if need.value:
+        ws = ws_cache.get(xa.device) if ws_cache is not None else None
+        if ws is None or ws.numel() < need.value:
+            ws = torch.empty(need.value, device=xa.device, dtype=torch.float32)
+            if ws_cache is not None:
+                ws_cache[xa.device] = ws
+    if f32_channels:
+        y = torch.empty((B, f32_channels, D, H, W), device=xa.device, dtype=torch.float32)
+    else:
+        y = torch.empty((B, D, H, W, co_pad), device=xa.device, dtype=torch.bfloat16)
+    _lib.check(lib.pgrf_conv3d_fwd(_lib.ptr(xa), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad, _lib.ptr(wpk), _lib.ptr(bias),
+                                   None if f32_channels else _lib.ptr(y), _lib.ptr(y) if f32_channels else None, f32_channels, co_pad,
+                                   B, D, H, W, 1, _lib.ptr(ws) if ws is not None else None, need.value, st), "pgrf_conv3d_fwd")
+    return y
+
+
 class _Block(nn.Module):
     """Parameter holder with Conv3DBlockv2's names (models/common_blocks.py:366-445)."""
 
@@ -87,16 +115,17 @@ class CostRegulariser3D(nn.Module):
         self.decoders = nn.ModuleList(dec)
         self.in_channels = 2 ** (size + 1)
         self._packed = {}
+        self._ws_cache = {}          # split-K workspace per device (stream-ordered reuse)
         for p in self.parameters():
             p.requires_grad_(False)
 
     # ---- weights ----------------------------------------------------------------------------------------------------------------
-    def _pack(self, conv, ca, cb, ca_pad, cb_pad):
+    def _pack(self, conv, ca, cb, ca_pad, cb_pad, simt=False):
         key = id(conv)
-        ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), str(conv.weight.device), ca, cb)
+        ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), str(conv.weight.device), ca, cb, simt)
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
-            if conv.weight.shape[0] == 1:
+            if simt:
                 hit = (ver, pack_conv_cout1(conv.weight, ca, cb, ca_pad, cb_pad), float(conv.bias.detach().float().item()))
             else:
                 hit = (ver,) + pack_conv(conv.weight, conv.bias, ca, cb, ca_pad, cb_pad)
@@ -104,13 +133,8 @@ class CostRegulariser3D(nn.Module):
         return hit[1], hit[2]
 
     # ---- kernels ----------------------------------------------------------------------------------------------------------------
-    @staticmethod
-    def _conv(lib, st, xa, ca_pad, xb, cb_pad, wpk, bias, co_pad, dims):
-        B, D, H, W = dims
-        y = torch.empty((B, D, H, W, co_pad), device=xa.device, dtype=torch.bfloat16)
-        _lib.check(lib.pgrf_conv3d_igemm_fwd(_lib.ptr(xa), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad, _lib.ptr(wpk),
-                                             _lib.ptr(bias), _lib.ptr(y), co_pad, B, D, H, W, 1, st), "pgrf_conv3d_igemm_fwd")
-        return y
+    def _conv(self, lib, st, xa, ca_pad, xb, cb_pad, wpk, bias, co_pad, dims, f32_channels=0):
+        return conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels, self._ws_cache, lib, st)
 
     def _block(self, lib, st, blk, xa, ca, xb, cb, dims):
         """pad-conv1-lrelu-pad-conv2-lrelu of one block on [xa | xb]; returns the un-pooled bf16 activation and its channel count."""
@@ -174,13 +198,11 @@ class CostRegulariser3D(nn.Module):
                 if blk.conv1.weight.shape[0] > 1:
                     a, ch = self._block(lib, st, blk, up, ch, xb, cb, dims)
                     continue
-                # last decoder: (ch + cb) -> 1 -> 1, fp32
+                # last decoder: (ch + cb) -> 1 on the tensor cores (one 16-channel tile, fp32 output), then 1 -> 1 on the fp32 pipes
                 ca_pad, cb_pad = up.shape[-1], (xb.shape[-1] if xb is not None else 0)
                 w1, b1 = self._pack(blk.conv1, ch, cb, ca_pad, cb_pad)
-                t = torch.empty(dims, device=dev, dtype=torch.float32)
-                _lib.check(lib.pgrf_conv3d_cout1_fwd(_lib.ptr(up), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad, None,
-                                                     _lib.ptr(w1), b1, *dims, 1, _lib.ptr(t), st), "pgrf_conv3d_cout1_fwd")
-                w2, b2 = self._pack(blk.conv2, 1, 0, 1, 0)
+                t = self._conv(lib, st, up, ca_pad, xb, cb_pad, w1, b1, 16, dims, f32_channels=1)
+                w2, b2 = self._pack(blk.conv2, 1, 0, 1, 0, simt=True)
                 out = torch.empty(dims, device=dev, dtype=torch.float32)
                 _lib.check(lib.pgrf_conv3d_cout1_fwd(None, 0, None, 0, _lib.ptr(t), _lib.ptr(w2), b2, *dims, 1, _lib.ptr(out), st),
                            "pgrf_conv3d_cout1_fwd")

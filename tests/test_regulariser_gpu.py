@@ -54,7 +54,10 @@ def test_unet3d_matches_reference_golden(name):
 
 @pytest.mark.parametrize("ca,cb,co,dims", [(16, 0, 16, (1, 4, 8, 16)), (32, 0, 64, (2, 4, 6, 10)), (64, 64, 64, (1, 4, 8, 8)),
                                            (128, 0, 256, (1, 2, 4, 8)), (256, 0, 128, (1, 2, 5, 7)), (4, 0, 8, (1, 3, 5, 9)),
-                                           (48, 16, 32, (1, 2, 4, 8))])
+                                           (48, 16, 32, (1, 2, 4, 8)),
+                                           # W % 128 == 0: the row variant (one gather serves the three kw taps)
+                                           (32, 0, 64, (1, 3, 3, 128)), (64, 64, 16, (2, 2, 2, 256)), (128, 0, 128, (1, 2, 2, 128)),
+                                           (16, 0, 32, (1, 2, 3, 128))])
 def test_conv3d_layer_vs_oracle_block(ca, cb, co, dims):
     from panogrf_b200 import _lib
     from panogrf_b200 import regulariser as reg
@@ -68,9 +71,7 @@ def test_conv3d_layer_vs_oracle_block(ca, cb, co, dims):
     ca_pad, cb_pad, co_pad = reg._pad16(ca), reg._pad16(cb) if cb else 0, reg._pad16(co)
     a_cl, b_cl = _cl(xa, ca_pad), (_cl(xb, cb_pad) if cb else None)
     wpk, bp = reg.pack_conv(w, b, ca, cb, ca_pad, cb_pad)
-    y = torch.empty((B, D, H, W, co_pad), device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.pgrf_conv3d_igemm_fwd(_lib.ptr(a_cl), ca_pad, _lib.ptr(b_cl) if cb else None, cb_pad, _lib.ptr(wpk), _lib.ptr(bp),
-                                         _lib.ptr(y), co_pad, B, D, H, W, 1, _lib.stream_ptr()), "conv3d")
+    y = reg.conv3d(a_cl, b_cl, wpk, bp, co_pad, (B, D, H, W))
     torch.cuda.synchronize()
     xin = torch.cat([xa] + ([xb] if cb else []), 1).to(torch.bfloat16).float().cpu()
     ref = F.leaky_relu(F.conv3d(oreg.wrap_pad3d(xin), w.to(torch.bfloat16).float().cpu(), b.cpu()), 0.01)
@@ -121,6 +122,33 @@ def test_cout1_pool_upsample_convert_vs_torch():
                                          1, _lib.ptr(o), st), "cout1 fp32")
     ref2 = F.leaky_relu(F.conv3d(oreg.wrap_pad3d(ref[:, None]), w2.cpu(), torch.tensor([-0.5])), 0.01)[:, 0]
     assert torch.allclose(o.cpu(), ref2, rtol=1e-4, atol=1e-5)
+
+
+def test_row_variant_equals_per_tap_variant():
+    """Same layer through both kernels (debug switch): identical operands and accumulation order per tap -> equal results."""
+    from panogrf_b200 import _lib
+    from panogrf_b200 import regulariser as reg
+    lib = _lib.load()
+    torch.manual_seed(11)
+    B, D, H, W, ca, co = 1, 4, 4, 128, 64, 64
+    a = _cl(torch.randn(B, ca, D, H, W, device="cuda"), ca)
+    wpk, bp = reg.pack_conv(torch.randn(co, ca, 3, 3, 3, device="cuda") / 40, torch.randn(co, device="cuda"), ca, 0, ca, 0)
+    outs = {}
+    try:
+        for row in (1, 0):
+            for splits in (1, 3, 9):
+                _lib.check(lib.pgrf_debug_set(b"conv_row", row), "debug_set")
+                _lib.check(lib.pgrf_debug_set(b"conv_splits", splits), "debug_set")
+                outs[row, splits] = reg.conv3d(a, None, wpk, bp, co, (B, D, H, W))
+    finally:
+        lib.pgrf_debug_set(b"conv_row", 1)
+        lib.pgrf_debug_set(b"conv_splits", 0)
+    for splits in (1, 3, 9):
+        assert torch.equal(outs[1, splits], outs[0, splits])
+    # split-K changes the fp32 summation order of the 9 tap rows: equal to bf16 rounding, not bitwise
+    ref = outs[1, 1].float()
+    for splits in (3, 9):
+        assert float((outs[1, splits].float() - ref).abs().max()) <= 2 ** -7 * float(ref.abs().max())
 
 
 def test_unet3d_rejects_bad_shapes():
