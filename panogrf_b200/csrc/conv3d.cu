@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_kernel(const ConvPa
     const unsigned char* wt = p.wpk + ((size_t)nt * 27 + tap0) * p.n_cc * b_bytes;
     int s = 0;
     uint32_t ph = 1;                                                    // parity of the `free` phase that precedes the first use
+    uint32_t adst = adst0;
 #pragma unroll 1
     for (int tap = tap0; tap < tap0 + n_taps; ++tap) {
       const int krow = tap / 3, kw = tap - krow * 3 - 1;                // krow = kd*3 + kh
@@ -183,25 +184,28 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_kernel(const ConvPa
         nb[i] = ok ? 16u : 0u;
         nv[i] = ok ? vbase + i * row_step + tap_off + ((rowinfo[i] & wrap_bit) ? wrap_off : 0) : 0;
       }
-      const __nv_bfloat16* src = p.xa + my_chunk * 8;
-      int cs = p.Ca, c_left = p.Ca;
 #pragma unroll 1
-      for (int cc = 0; cc < p.n_cc; ++cc) {
-        if (c_left == 0) { src = p.xb + my_chunk * 8; cs = p.Cb; c_left = p.Cb; }      // second input of the concatenation
-        mbar_wait(&bar_free[s], ph);                                    // the MMAs that read this stage have completed
-        if (r == 0) {
-          mbar_expect_tx(&bar_full[s], b_bytes);
-          bulk_g2s(Bs + s * b_bytes, wt, b_bytes, &bar_full[s]);
-        }
-        wt += b_bytes;
-        const uint32_t adst = adst0 + s * a_bytes;
+      for (int inp = 0; inp < 2; ++inp) {                               // the two inputs of the concatenation
+        const int cs = inp ? p.Cb : p.Ca;
+        if (cs == 0) continue;
+        const __nv_bfloat16* rp[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < n_rows) cp_async16(adst + i * dst_step, src + (size_t)nv[i] * cs, nb[i]);
-        cp_async_arrive(&bar_full[s]);      // arrives when this thread's copies of the stage have landed; up to S stages in flight
-        src += p.KC;
-        c_left -= p.KC;
-        if (++s == S) { s = 0; ph ^= 1u; }
+        for (int i = 0; i < 4; ++i) rp[i] = (inp ? p.xb : p.xa) + (size_t)nv[i] * cs + my_chunk * 8;
+#pragma unroll 1
+        for (int c = 0; c < cs; c += p.KC) {
+          mbar_wait(&bar_free[s], ph);                                  // the MMAs that read this stage have completed
+          if (r == 0) {
+            mbar_expect_tx(&bar_full[s], b_bytes);
+            bulk_g2s(Bs + s * b_bytes, wt, b_bytes, &bar_full[s]);
+          }
+          wt += b_bytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < n_rows) { cp_async16(adst + i * dst_step, rp[i], nb[i]); rp[i] += p.KC; }
+          cp_async_arrive(&bar_full[s]);    // arrives when this thread's copies of the stage have landed; up to S stages in flight
+          adst += a_bytes;
+          if (++s == S) { s = 0; ph ^= 1u; adst = adst0; }
+        }
       }
     }
     mbar_wait(&bar_done, 0);
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_row_kernel(const Co
     const size_t wtap = (size_t)p.n_cc * b_bytes;                        // distance between the weight blocks of two taps
     const unsigned char* wt = p.wpk + ((size_t)nt * 27 + krow0 * 3) * wtap;
     int s = 0;
-    uint32_t ph = 1;
+    uint32_t ph = 1, adst = adst0, hdst = hdst0;
 #pragma unroll 1
     for (int krow = krow0; krow < krow0 + n_krow; ++krow) {              // krow = kd*3 + kh
       const int dd = d + krow / 3 - 1, yy = y + krow % 3 - 1;
@@ -275,29 +279,33 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_row_kernel(const Co
       const long long nv0 = ok ? v0 + (long long)(krow / 3 - 1) * HW + (long long)(krow % 3 - 1) * p.W : 0;
       const long long nvr = ok ? nv0 + row0 : 0, nvh = ok ? nv0 + halo_off : 0;
       const long long rstep = ok ? row_step : 0;
-      const __nv_bfloat16* src = p.xa;
-      int cs = p.Ca, c_left = p.Ca;
 #pragma unroll 1
-      for (int cc = 0; cc < p.n_cc; ++cc) {
-        if (c_left == 0) { src = p.xb; cs = p.Cb; c_left = p.Cb; }
-        mbar_wait(&bar_free[s], ph);
-        if (r == 0) {
-          mbar_expect_tx(&bar_full[s], 3 * b_bytes);
+      for (int inp = 0; inp < 2; ++inp) {                                 // the two inputs of the concatenation
+        const int cs = inp ? p.Cb : p.Ca;
+        if (cs == 0) continue;
+        const __nv_bfloat16* base = inp ? p.xb : p.xa;
+        const __nv_bfloat16* rp[4];
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) bulk_g2s(Bs + (s * 3 + kw) * b_bytes, wt + kw * wtap, b_bytes, &bar_full[s]);
+        for (int i = 0; i < 4; ++i) rp[i] = base + (size_t)(nvr + i * rstep) * cs + my_chunk * 8;
+        const __nv_bfloat16* hp = base + (size_t)nvh * cs + hc * 8;
+#pragma unroll 1
+        for (int c = 0; c < cs; c += p.KC) {
+          mbar_wait(&bar_free[s], ph);
+          if (r == 0) {
+            mbar_expect_tx(&bar_full[s], 3 * b_bytes);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) bulk_g2s(Bs + (s * 3 + kw) * b_bytes, wt + kw * wtap, b_bytes, &bar_full[s]);
+          }
+          wt += b_bytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < n_rows) { cp_async16(adst + i * dst_step, rp[i], nbytes); rp[i] += p.KC; }
+          if (halo) { cp_async16(hdst, hp, nbytes); hp += p.KC; }
+          cp_async_arrive(&bar_full[s]);
+          adst += a_bytes;
+          hdst += a_bytes;
+          if (++s == S) { s = 0; ph ^= 1u; adst = adst0; hdst = hdst0; }
         }
-        wt += b_bytes;
-        const uint32_t adst = adst0 + s * a_bytes;
-        const __nv_bfloat16* rsrc = src + (size_t)nvr * cs + my_chunk * 8;
-        const size_t sstep = (size_t)rstep * cs;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < n_rows) cp_async16(adst + i * dst_step, rsrc + i * sstep, nbytes);
-        if (halo) cp_async16(hdst0 + s * a_bytes, src + (size_t)nvh * cs + hc * 8, nbytes);
-        cp_async_arrive(&bar_full[s]);
-        src += p.KC;
-        c_left -= p.KC;
-        if (++s == S) { s = 0; ph ^= 1u; }
       }
       wt += 2 * wtap;                                                     // next tap row: skip the two taps already consumed
     }
@@ -474,6 +482,8 @@ using namespace pgrf;
 namespace pgrf {
 int g_conv_stages = 0;   // pipeline depth of the conv3d kernels (pgrf_debug_set "conv_stages": 0 = automatic, else 3..6)
 int g_conv_row = 1;      // use the row variant when W % 128 == 0 (pgrf_debug_set "conv_row")
+int g_conv_kc = 64;       // channels per pipeline stage (pgrf_debug_set "conv_kc": 64, 32 or 16)
+int g_conv_smem_kb = 56;  // shared-memory budget per CTA that sizes the pipeline (pgrf_debug_set "conv_smem_kb")
 int g_conv_splits = 0;   // split-K factor (pgrf_debug_set "conv_splits": 0 = automatic, else 1, 3 or 9)
 }
 
@@ -502,7 +512,7 @@ static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, Con
                "multiples of 16 (Ca=%d Cb=%d Cout=%d)", Ca, Cb, Cout);
   PGRF_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 2, "conv3d: bad volume %dx%dx%dx%d", B, D, H, W);
   const int Cin = Ca + Cb;
-  int KC = Cin < 64 ? Cin : 64;
+  int KC = Cin < g_conv_kc ? Cin : g_conv_kc;
   while (Ca % KC || Cb % KC) KC >>= 1;           // a stage never straddles the two inputs of a concatenation
   PGRF_REQUIRE(KC >= 16, "conv3d: no common chunk size for Ca=%d Cb=%d", Ca, Cb);
   pl.KC = KC; pl.n_cc = Cin / KC;
@@ -522,7 +532,7 @@ static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, Con
   PGRF_REQUIRE(pl.splits == 1 || pl.splits == 3 || pl.splits == 9, "conv3d: splits=%d (1, 3 or 9)", pl.splits);
   // pipeline depth: as many stages as keep two CTAs on an SM (one CTA's epilogue hides behind the other's main loop), at least 2 / 3
   const int s_min = pl.row ? 2 : 3, s_max = pl.row ? 4 : 6;
-  int S = (int)((113 * 1024) / stage);
+  int S = (int)(((size_t)g_conv_smem_kb * 1024) / stage);
   S = S < s_min ? s_min : (S > s_max ? s_max : S);
   if (!pl.row && S == 5) S = 4;
   if (g_conv_stages) S = g_conv_stages < s_min ? s_min : (g_conv_stages > s_max ? s_max : g_conv_stages);

@@ -28,6 +28,47 @@ def unet_flops(size, D, H, W, B=1):
     return tot, layers
 
 
+def torch_unet3d(net, x):
+    """The same network through torch's library convolutions (cuDNN), as the reference runs it: wrap padding by concatenation,
+    F.conv3d, F.avg_pool3d, F.interpolate — the library baseline the tensor-core kernels are compared with."""
+    import torch.nn.functional as F
+
+    def pad(t):
+        t = F.pad(t, (0, 0, 1, 1, 1, 1))
+        return torch.cat([t[..., -1:], t, t[..., :1]], -1)
+
+    def block(blk, t):
+        for conv in (blk.conv1, blk.conv2):
+            t = F.leaky_relu(F.conv3d(pad(t), conv.weight.to(t.dtype), conv.bias.to(t.dtype)), 0.01)
+        return t
+
+    skips = []
+    for blk in net.encoders:
+        u = block(blk, x)
+        skips.append(u)
+        x = F.avg_pool3d(u, 2) if blk.pool else u
+    n_dec = len(net.decoders)
+    for i in range(n_dec - 1, -1, -1):
+        x = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+        if i < n_dec - 1:
+            x = torch.cat((x, skips[i]), 1)
+        x = block(net.decoders[i], x)
+    return x
+
+
+def time_fn(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(n):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / n
+
+
 if __name__ == "__main__":
     D, H, W = (int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (64, 64, 128)
     torch.manual_seed(0)
@@ -48,3 +89,12 @@ if __name__ == "__main__":
     fl, layers = unet_flops(4, D, H, W)
     print(f"unet3d size=4 on 1x32x{D}x{H}x{W}: {ms:.3f} ms, {fl / 1e9:.1f} GFLOP -> {fl / ms / 1e9:.1f} TFLOP/s, "
           f"{(_lib.launch_count() - l0) // n} launches, finite={bool(torch.isfinite(y).all())}")
+    if os.environ.get("PGRF_TIME_TORCH", "1") != "0":
+        with torch.no_grad():
+            ref = torch_unet3d(net, x)
+            err = float((y - ref).abs().max() / ref.abs().max())
+            t32 = time_fn(lambda: torch_unet3d(net, x), 5)
+            xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+            t16 = time_fn(lambda: torch_unet3d(net, xb), 5)
+        print(f"library baseline (torch/cuDNN, same network): fp32 (TF32 convolutions, the reference's default) {t32:.3f} ms, "
+              f"bf16 channels_last_3d {t16:.3f} ms; ours vs fp32 library output: max err {err:.2e} of range")
