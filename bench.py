@@ -409,6 +409,7 @@ def main():
         line["project_gather"] = time_project_gather(torch, que_d, ref_d, flush, peaks)
         line["depth_guided"] = time_depth_guided(torch, que_d, ref_d)
         line["configs"] = time_other_configs(torch, pg, dev, flush, peaks, not args.no_cpu_baseline)
+        line["mvs_stages"] = time_mvs_stages(torch, dev, flush, peaks)
     elif rank == 0:
         kern = time_stages(torch, net, que_d, ref_d, flush)
         line.update(kern.get("roofline_objects", {}))
@@ -625,7 +626,7 @@ def time_project_gather(torch, que_d, ref_d, flush, peaks):
     return {"workload": f"{rn} rays x {dn} samples x {RFN} views -> pts,depth,dir,ray_feats,rgb,img_feats (292 B/row)",
             "rows_per_s": rows / ms * 1e3, "ms": ms,
             "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": tr["dram_bytes_per_ray"] * rn if tr else None,
+                         "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "traffic": tr["dram_bytes_per_launch"] if tr else None,
                          "traffic_src": (tr or {}).get("src"), "bytes_per_row": 292}}
 
 
@@ -785,6 +786,65 @@ def time_other_configs(torch, pg, dev, flush, peaks, with_oracle):
     res["c5_cost_volume_1024x2048_D192"] = {"ms": ms, "voxels_per_s": vox / ms * 1e3,
                                             "frac_of_hbm": vox * (C * 4 + 4 + 8.0 * C / D) / ms / 1e6 / peaks["hbm_gbs"]}
     del images, dvol
+    torch.cuda.empty_cache()
+    return res
+
+
+def time_mvs_stages(torch, dev, flush, peaks):
+    """SURVEY 8 (f) rows next to the hot path: the 3-D cost regulariser (`unet3d`, size 4: 32 -> ... -> 512 channels) on a
+    1x32x64x64x128 cost volume, the same network through torch's library convolutions (what the reference runs), and the
+    equirect -> cubemap resampling that replaces the reference's scipy CPU hop."""
+    import torch.nn.functional as F
+    from panogrf_b200 import e2c as pe2c
+    from panogrf_b200 import regulariser as reg
+    res = {}
+    torch.manual_seed(0)
+    D, H, W = 64, 64, 128
+    net = reg.CostRegulariser3D(4).to(dev)
+    x = torch.rand(1, 32, D, H, W, device=dev)
+    ms = _median_ms(torch, flush, lambda: net(x), n=5)
+    flops = 0
+    for blocks in (net.encoders, net.decoders):          # level i works on the volume pooled i times (the last encoder is not pooled)
+        for i, blk in enumerate(blocks):
+            for conv in (blk.conv1, blk.conv2):
+                flops += 2 * 27 * conv.weight.shape[0] * conv.weight.shape[1] * (D * H * W // 8 ** i)
+
+    def pad(t):
+        t = F.pad(t, (0, 0, 1, 1, 1, 1))
+        return torch.cat([t[..., -1:], t, t[..., :1]], -1)
+
+    def lib_unet(t):
+        def block(blk, t):
+            for conv in (blk.conv1, blk.conv2):
+                t = F.leaky_relu(F.conv3d(pad(t), conv.weight, conv.bias), 0.01)
+            return t
+        skips = []
+        for blk in net.encoders:
+            u = block(blk, t)
+            skips.append(u)
+            t = F.avg_pool3d(u, 2) if blk.pool else u
+        n_dec = len(net.decoders)
+        for i in range(n_dec - 1, -1, -1):
+            t = F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=False)
+            if i < n_dec - 1:
+                t = torch.cat((t, skips[i]), 1)
+            t = block(net.decoders[i], t)
+        return t
+
+    with torch.no_grad():
+        ms_lib = _median_ms(torch, flush, lambda: lib_unet(x), n=3)
+        ref = lib_unet(x)
+        err = float((net(x) - ref).abs().max() / ref.abs().max())
+    res["unet3d_1x32x64x64x128"] = {
+        "ms": ms, "gflop": flops / 1e9, "tflops": flops / ms / 1e9, "frac_of_bf16_peak": flops / ms / 1e9 / peaks["bf16_tflops"],
+        "library_ms": ms_lib, "library": "the same network through torch/cuDNN fp32 (TF32) convolutions, as the reference runs it",
+        "max_err_vs_library_of_range": err, "dtype": "bf16 operands, fp32 accumulate"}
+    del net, x, ref
+    # equirect -> cubemap: 3 panoramas 512x1024x3 -> 256-pixel faces
+    conv = pe2c.Equirec2Cube(512, 1024, 256)
+    pano = torch.rand(3, 512, 1024, 3, device=dev)
+    ms = _median_ms(torch, flush, lambda: conv.run(pano), n=5)
+    res["e2c_3x512x1024_to_256"] = {"ms": ms, "mpix_per_s": 3 * 6 * 256 * 256 / ms / 1e3}
     torch.cuda.empty_cache()
     return res
 

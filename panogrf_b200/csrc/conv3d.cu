@@ -25,7 +25,10 @@ namespace pgrf {
 constexpr int kConvRows = 128;          // output voxels per CTA == TMEM lanes
 constexpr int kGatherThreads = 256;     // 8 gather / epilogue warps
 constexpr int kConvThreads = 288;       // + 1 MMA-issuing warp
-constexpr int kConvPad = 64;            // bytes appended to each k-chunk plane of the A stage (conflict-free 16-byte writes)
+// Bytes appended to each k-chunk plane of the A stage.  The gather writes 16 bytes per lane with 8 consecutive lanes = the 8 k-chunks
+// of one row, i.e. one quarter-warp phase hits 8 planes at the same row offset: a plane pitch of 16 (mod 128) bytes spreads them over
+// all 32 banks (ncu: the LSU shared-memory wavefronts were the busiest unit, 80 % of peak, with a 4-way conflict per phase).
+constexpr int kConvPad = 16;
 
 struct ConvParams {
   const __nv_bfloat16* xa; int Ca;     // first input, channels-last, channel count (multiple of 16)
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_kernel(const ConvPa
 // k-chunk-major layout operand rows are 16 bytes apart, so tap kw is the same buffer with the descriptor start advanced by kw rows.
 // One gather (and one third of the copy instructions / L1TEX traffic) feeds three taps of MMAs.
 constexpr int kRowA = kConvRows + 2;
-constexpr int kRowPitch = kRowA * 16 + 32;        // bytes between k-chunk planes
+constexpr int kRowPitch = kRowA * 16 + 112;       // bytes between k-chunk planes: 16 (mod 128), see kConvPad
 
 template <int NT, int S>
 __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_row_kernel(const ConvParams p) {
