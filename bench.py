@@ -158,11 +158,14 @@ def ncu_traffic():
 # CPU oracle (cpu_baseline leg, parity check and --impl reference)
 # --------------------------------------------------------------------------------------------------
 
-def oracle_run(n_rays, cfg=None, rfn=RFN, h=H, w=W, repeats=1, warm=0, seed_rays=1):
+def oracle_run(n_rays, cfg=None, rfn=RFN, h=H, w=W, repeats=1, warm=0, seed_rays=1, device=None):
     """oracle/render.py on `n_rays` random rays of the view (ray batches of 2048 like the reference's loop, renderer.py:647-683),
-    all host cores.  Returns (rays/s, seconds, outputs incl. the resampled fine depths, ray ids, weights)."""
+    all host cores.  Returns (rays/s, seconds, outputs incl. the resampled fine depths, ray ids, weights).
+    `device="cuda"` runs the same op sequence as eager PyTorch on the GPU (the reference's execution model on this hardware)."""
     import torch
     from oracle import render as orender
+    if device is not None:
+        return _oracle_run_on(torch, orender, device, n_rays, cfg, rfn, h, w, repeats, warm, seed_rays)
     from panogrf_b200.renderer import NeuralRayBaseRenderer
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
@@ -189,6 +192,40 @@ def oracle_run(n_rays, cfg=None, rfn=RFN, h=H, w=W, repeats=1, warm=0, seed_rays
             if i >= warm:
                 times.append(time.perf_counter() - t0)
     return n_rays / min(times), min(times), out, idx, Wd
+
+
+def _oracle_run_on(torch, orender, device, n_rays, cfg, rfn, h, w, repeats, warm, seed_rays):
+    """Eager-PyTorch-on-GPU baseline: the oracle's op sequence with every tensor on `device`, torch's own scans, CUDA-synchronised
+    wall clock.  A baseline, never a checker (the parity legs use the CPU run with the stated scan order)."""
+    from panogrf_b200.renderer import NeuralRayBaseRenderer
+    torch.manual_seed(0)
+    cfg = dict(cfg or cfg_dict(h, w))
+    Wd = {k: v.detach().to(device) for k, v in NeuralRayBaseRenderer(cfg).state_dict().items()}
+    que, ref = make_inputs(torch, None, h, w, rfn)
+    que = {k: v.to(device) for k, v in que.items()}
+    ref = {k: v.to(device) for k, v in ref.items()}
+    g = torch.Generator().manual_seed(seed_rays)
+    coords = que["coords"][:, torch.randperm(h * w, generator=g)[:n_rays].to(device)]
+    ocfg = dict(cfg)
+    ocfg["sample_num"] = DN
+    times = []
+    orender.TORCH_SCANS = True
+    try:
+        with torch.no_grad(), torch.device(device):
+            for i in range(warm + repeats):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for r0 in range(0, n_rays, 2048):
+                    q = dict(que)
+                    q["coords"] = coords[:, r0:r0 + 2048]
+                    out = orender.render_rays(ocfg, Wd, q, ref)
+                torch.cuda.synchronize()
+                if i >= warm:
+                    times.append(time.perf_counter() - t0)
+    finally:
+        orender.TORCH_SCANS = False
+    assert torch.isfinite(out["pixel_colors_nr_fine"]).all()
+    return n_rays / min(times), min(times), None, None, None
 
 
 def oracle_rays_per_s(n_rays, repeats=1, warm=0):
@@ -406,6 +443,15 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"8192 random rays of the view, oracle/render.py torch-CPU fp32, {t:.1f} s"}
             line["parity"] = parity_check(torch, pg, dev, o, idx, Wd, cfg_dict())
+            try:
+                gv, gt, _, _, _ = oracle_run(32768, repeats=1, warm=1, device=dev)
+                line["eager_torch_gpu"] = {
+                    "value": gv, "unit": "rays/s", "sample": f"32768 random rays of the view in ray batches of 2048, {gt:.2f} s",
+                    "what": "the oracle's op sequence (the reference's eager PyTorch execution model: ~10^3 small launches per ray "
+                            "batch, torch.cumsum/cumprod, fp32) on the same B200 — the same-hardware comparison; a port, not the "
+                            "reference itself"}
+            except Exception as exc:                                   # a baseline must never fail the bench
+                line["eager_torch_gpu"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         line["project_gather"] = time_project_gather(torch, que_d, ref_d, flush, peaks)
         line["depth_guided"] = time_depth_guided(torch, que_d, ref_d)
         line["configs"] = time_other_configs(torch, pg, dev, flush, peaks, not args.no_cpu_baseline)

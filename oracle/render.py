@@ -132,10 +132,17 @@ def depth2inv_dists(depth, depth_range):
     return torch.cat([dists, torch.full([*depth.shape[:-1], 1], 1e6, dtype=torch.float32)], -1)
 
 
+#: bench.py's eager-GPU baseline sets this: use torch.cumsum / torch.cumprod (one launch each, as the reference does,
+#: render_ops.py:152,438-439) instead of the stated sequential order (64 python iterations).  Never set by the parity checks.
+TORCH_SCANS = False
+
+
 def seq_cumsum(x):
     """Sequential left-to-right fp32 cumulative sum over the last dim — the STATED accumulation order
     of this build.  torch.cumsum accumulates in fp64 on the CPU and with a parallel scan
     on CUDA, so neither is a fixed fp32 order; the CUDA kernels reproduce exactly this loop."""
+    if TORCH_SCANS:
+        return torch.cumsum(x, -1)
     out = torch.empty_like(x)
     acc = torch.zeros_like(x[..., 0])
     for i in range(x.shape[-1]):
@@ -146,6 +153,8 @@ def seq_cumsum(x):
 
 def seq_cumprod(x):
     """Sequential left-to-right fp32 cumulative product over the last dim (see seq_cumsum)."""
+    if TORCH_SCANS:
+        return torch.cumprod(x, -1)
     out = torch.empty_like(x)
     acc = torch.ones_like(x[..., 0])
     for i in range(x.shape[-1]):
@@ -331,7 +340,7 @@ def posenc_table(d_hid, n_samples):
     table = pos / np.power(10000, 2 * (j // 2) / d_hid)
     table[:, 0::2] = np.sin(table[:, 0::2])
     table[:, 1::2] = np.cos(table[:, 1::2])
-    return torch.from_numpy(table).float().unsqueeze(0)
+    return torch.from_numpy(table).float().unsqueeze(0).to(torch.empty(0).device)     # follows `with torch.device(...)`
 
 
 def _mean_var(x, weight):

@@ -1,7 +1,7 @@
 // Depth-prior sample placement of the render path ("diner" branch, network/renderer.py:570-600 and :318-355):
 //   project_points_dict_diner                     network/render_ops.py:260-290
 //   sample_depthguided / fill_up_uniform_samples  network/original_depth_guided_sample.py:45-297 / 333-366
-// One CTA per ray walks the ray's candidate depths (typically 1000): project into every source panorama, gather the
+// One WARP per ray (4 independent rays per CTA, no block-wide barrier anywhere) walks the ray's candidate depths (typically 1000): project into every source panorama, gather the
 // MVS depth / variance / normal priors (bilinear, border padding), surface likelihood = max over views, compact the
 // few candidates with non-zero likelihood, keep the most likely ones (shared-memory bitonic sort only when more survive
 // than there are slots), draw the Gaussian samples, fill empty slots, append the uniform samples, sort, write.
@@ -10,7 +10,8 @@
 
 namespace pgrf {
 
-constexpr int kDgThreads = 128;
+constexpr int kDgWarps = 4;                // rays per CTA (one warp each)
+constexpr int kDgThreads = 32 * kDgWarps;
 constexpr int kDgMaxCand = 4096;
 constexpr int kDgMaxOut = 512;
 
@@ -38,10 +39,10 @@ __device__ __forceinline__ float surface_likelihood(const pgrf_diner_args& a, fl
 }
 
 template <typename T, typename Less>
-__device__ __forceinline__ void bitonic_sort(T* a, int n, Less less) {   // n = power of two, all threads of the CTA
+__device__ __forceinline__ void bitonic_sort(T* a, int n, Less less, int lane) {   // n = power of two, one warp, `a` in shared memory
   for (int k = 2; k <= n; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      for (int i = lane; i < n; i += 32) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const bool up = (i & k) == 0;
@@ -49,38 +50,34 @@ __device__ __forceinline__ void bitonic_sort(T* a, int n, Less less) {   // n = 
           if (less(y, x) == up) { a[i] = y; a[ixj] = x; }
         }
       }
-      __syncthreads();
+      __syncwarp();
     }
 }
 
-__device__ __forceinline__ float block_sum(float v, float* scratch) {   // scratch: 4 floats
+__device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  return scratch[0] + scratch[1] + scratch[2] + scratch[3];
+  return v;
 }
 
 __device__ __forceinline__ int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_diner_args a, int nc_pad, int nc_pow2) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm);                 // [nc_pow2]
-  float* lik = reinterpret_cast<float*>(keys + nc_pow2);                                 // [nc_pad]
-  float* opq = lik + nc_pad;                                                             // [nc_pad] (n_gaussian > 0)
-  float* z = opq + nc_pad;                                                               // [out_pow2]
-  __shared__ int s_count;
-  __shared__ float s_red[4];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x & 31, warp = threadIdx.x >> 5;                             // tid = lane: the warp owns the ray
   const int nc = a.n_candidates, ns = a.n_samples, ng = a.n_gaussian, nu = a.n_uniform;
   const int keep = ns - ng;
   const int n_out = ns + nu;
   const int out_pow2 = next_pow2(n_out), ns_pow2 = next_pow2(ns);
   const bool from_dict = a.prj_mu != nullptr;
+  // per-warp shared memory: keys [nc_pow2] | lik (later the opacity weights, in place) [nc_pad] | z [out_pow2]
+  const size_t warp_bytes = (size_t)nc_pow2 * 8 + (size_t)nc_pad * 4 + (size_t)out_pow2 * 4;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm + warp * warp_bytes);
+  float* lik = reinterpret_cast<float*>(keys + nc_pow2);
+  float* opq = lik;
+  float* z = lik + nc_pad;
 
-  for (long long ray = blockIdx.x; ray < a.rn; ray += gridDim.x) {
-    if (tid == 0) s_count = 0;
-    __syncthreads();
+  for (long long ray = (long long)blockIdx.x * kDgWarps + warp; ray < a.rn; ray += (long long)gridDim.x * kDgWarps) {
+    int count = 0;                                                                       // survivors so far (warp-uniform)
     const float* cand = a.cand_depth + ray * a.cand_ray_stride;
     // ---- ray in world space (render_ops.py:76-106)
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
@@ -98,8 +95,10 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
     }
     const size_t map_px = (size_t)a.map_h * a.map_w;
     // ---- phase 1: likelihood of every candidate, max over views; survivors are compacted as sortable keys
-    for (int i = tid; i < nc; i += kDgThreads) {
+    for (int i0 = 0; i0 < nc; i0 += 32) {
+      const int i = i0 + tid;
       float best = 0.f;
+      if (i < nc) {
       if (from_dict) {
         const float* qd = a.que_dir + ((size_t)ray * nc + i) * 3;
         const float q0 = -__ldg(qd), q1 = -__ldg(qd + 1), q2 = -__ldg(qd + 2);
@@ -128,7 +127,7 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
           cam_to_equi(a.dataset, pc0, pc1, pc2, a.H, a.W, pd, px, py);
           const Footprint f = border_footprint(px, py, a.img_h, a.img_w, a.map_h, a.map_w);
           const float mu = tap1(a.mvs_depth + v * map_px, f, a.map_w);
-          if (!(fabsf(mu - pd) < a.depth_diff_max)) continue;            // the common case: far from the prior surface
+          if (!(fabsf(mu - pd) < a.depth_diff_max)) continue;            // the common case: far from the prior surface (view loop)
           const float uncert = tap1(a.mvs_uncert + v * map_px, f, a.map_w);
           float cosv = 0.f;
           if (a.include_norm) {
@@ -143,26 +142,29 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
       }
       lik[i] = best;
       if (a.likelihood) a.likelihood[(size_t)ray * nc + i] = best;
+      }
+      // survivors are compacted in candidate order (ballot prefix): deterministic, no atomics
+      const unsigned alive = __ballot_sync(0xffffffffu, best > 0.f);
       if (best > 0.f) {
         // descending key order = descending likelihood, ties: lower candidate index first (stable descending sort)
-        const int pos = atomicAdd(&s_count, 1);
+        const int pos = count + __popc(alive & ((1u << tid) - 1u));
         keys[pos] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)i);
       }
+      count += __popc(alive);
     }
-    __syncthreads();
-    const int count = s_count;
+    __syncwarp();
     // ---- phase 2: more survivors than slots -> order them
     if (count > keep) {
       const int P = next_pow2(count);
-      for (int i = count + tid; i < P; i += kDgThreads) keys[i] = 0ull;
-      __syncthreads();
-      bitonic_sort(keys, P, [](unsigned long long x, unsigned long long y) { return x > y; });
+      for (int i = count + tid; i < P; i += 32) keys[i] = 0ull;
+      __syncwarp();
+      bitonic_sort(keys, P, [](unsigned long long x, unsigned long long y) { return x > y; }, tid);
     }
     // ---- phase 3: Gaussian samples around the occlusion-aware mean (original_depth_guided_sample.py:199-202,257-275)
     float g_mean = 0.f, g_std = 0.f;
     bool g_on = false;
     if (ng > 0) {
-      if (tid < 32) {
+      {
         float T = 1.f;                                                    // prod_{j<i} (1 - lik_j), sequential fp32
         for (int c0 = 0; c0 < nc; c0 += 32) {
           const int i = c0 + tid;
@@ -179,26 +181,26 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
           if (i < nc) opq[i] = mine;
         }
       }
-      __syncthreads();
+      __syncwarp();
       float part = 0.f;
-      for (int i = tid; i < nc; i += kDgThreads) part += opq[i];
-      const float S = block_sum(part, s_red);
+      for (int i = tid; i < nc; i += 32) part += opq[i];
+      const float S = warp_sum(part);
       g_on = S != 0.f;
       if (g_on) {
         part = 0.f;
-        for (int i = tid; i < nc; i += kDgThreads) part += __ldg(cand + i) * (opq[i] / S);
-        g_mean = block_sum(part, s_red);
+        for (int i = tid; i < nc; i += 32) part += __ldg(cand + i) * (opq[i] / S);
+        g_mean = warp_sum(part);
         part = 0.f;
-        for (int i = tid; i < nc; i += kDgThreads) {
+        for (int i = tid; i < nc; i += 32) {
           const float d = __ldg(cand + i) - g_mean;
           part += d * d * (opq[i] / S);
         }
-        g_std = sqrtf(block_sum(part, s_red));
+        g_std = sqrtf(warp_sum(part));
       }
     }
     // ---- phase 4: slots = [most likely candidates | Gaussian samples], 0 = empty
     const int n_sel = count < keep ? count : keep;
-    for (int s = tid; s < ns_pow2; s += kDgThreads) {
+    for (int s = tid; s < ns_pow2; s += 32) {
       float v = __int_as_float(0x7f800000);
       if (s < n_sel) {
         const unsigned idx = 0xFFFFFFFFu - (unsigned)(keys[s] & 0xFFFFFFFFull);
@@ -210,28 +212,28 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
       }
       z[s] = v;
     }
-    __syncthreads();
-    bitonic_sort(z, ns_pow2, [](float x, float y) { return x < y; });
+    __syncwarp();
+    bitonic_sort(z, ns_pow2, [](float x, float y) { return x < y; }, tid);
     // ---- fill_up_uniform_samples (original_depth_guided_sample.py:333-366)
     int mine = 0;
-    for (int s = tid; s < ns; s += kDgThreads) mine += (z[s] == 0.f) ? 1 : 0;
-    const float n_miss_f = block_sum((float)mine, s_red);
+    for (int s = tid; s < ns; s += 32) mine += (z[s] == 0.f) ? 1 : 0;
+    const float n_miss_f = warp_sum((float)mine);
     if (n_miss_f > 0.f) {
       const float step = (a.max_depth - a.min_depth) / n_miss_f;
-      for (int s = tid; s < ns; s += kDgThreads)
+      for (int s = tid; s < ns; s += 32)
         if (z[s] == 0.f) {
           float zf = __fadd_rn(a.min_depth, __fmul_rn((float)s, step));
           zf = __fadd_rn(zf, __fmul_rn(__ldg(a.fill_rand + ray * ns + s), step));
           z[s] = zf;
         }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- optional uniform samples (renderer.py:346-349), final sort
-    for (int s = ns + tid; s < out_pow2; s += kDgThreads) z[s] = (s < n_out) ? __ldg(a.uniform_depth + (s - ns)) : __int_as_float(0x7f800000);
-    __syncthreads();
-    bitonic_sort(z, out_pow2, [](float x, float y) { return x < y; });
-    for (int s = tid; s < n_out; s += kDgThreads) a.out_depth[ray * n_out + s] = z[s];
-    __syncthreads();
+    for (int s = ns + tid; s < out_pow2; s += 32) z[s] = (s < n_out) ? __ldg(a.uniform_depth + (s - ns)) : __int_as_float(0x7f800000);
+    __syncwarp();
+    bitonic_sort(z, out_pow2, [](float x, float y) { return x < y; }, tid);
+    for (int s = tid; s < n_out; s += 32) a.out_depth[ray * n_out + s] = z[s];
+    __syncwarp();
   }
 }
 
@@ -345,10 +347,11 @@ extern "C" int pgrf_depth_guided_sample_fwd(const pgrf_diner_args* args, void* s
   const int nc_pad = (a.n_candidates + 3) & ~3;
   int nc_pow2 = 1; while (nc_pow2 < a.n_candidates) nc_pow2 <<= 1;
   int out_pow2 = 1; while (out_pow2 < a.n_samples + a.n_uniform) out_pow2 <<= 1;
-  const size_t smem = (size_t)nc_pow2 * 8 + (size_t)nc_pad * 8 + (size_t)out_pow2 * 4;
+  const size_t smem = kDgWarps * ((size_t)nc_pow2 * 8 + (size_t)nc_pad * 4 + (size_t)out_pow2 * 4);
+  PGRF_REQUIRE(smem <= 227 * 1024, "depth_guided_sample: %zu bytes of shared memory", smem);
   if (smem > 48 * 1024) PGRF_CUDA(cudaFuncSetAttribute(depth_guided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long max_grid = 148LL * 12;
-  const int grid = (int)(a.rn < max_grid ? a.rn : max_grid);
+  const long long max_grid = 148LL * 16, want = (a.rn + kDgWarps - 1) / kDgWarps;
+  const int grid = (int)(want < max_grid ? want : max_grid);
   depth_guided_kernel<<<grid, kDgThreads, smem, (cudaStream_t)stream>>>(a, nc_pad, nc_pow2);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
