@@ -335,6 +335,15 @@ PGRF_API int pgrf_conv3d_cout1_fwd(const void* xa, int Ca, const void* xb, int C
                                    int D, int H, int W, int act, float* out, void* stream);
 PGRF_API int pgrf_avgpool3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream);
 PGRF_API int pgrf_upsample3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream);
+/* 2-D heads after the regulariser (models/test_models.py:147-205, pipeline3_model.py:866-905).  A (B,1,H,W,C) volume is a 2-D feature
+ * map: pgrf_conv3d_fwd with D == 1 is Conv2d(3x3) over WrapPadding (zeros along H, wrap along W; common_blocks.py:258-293) and walks
+ * only the three kd == 1 tap rows.  pgrf_upsample2d2_fwd: F.interpolate(scale_factor=2, 'bilinear', align_corners=False) on bf16
+ * channels-last (Upscale, common_blocks.py:245-256).  pgrf_channel_dot_upsample_fwd: decoders1 = 1x1 convolution over the C channels
+ * of a strided fp32 (B,C,H,W) map (+ bias), bilinear x`scale` upsampling and the depth rectification (0 none, 1 clamp(min=0),
+ * 2 1/(clamp(min=0)+1e-10)) -> (B, H*scale, W*scale) fp32. */
+PGRF_API int pgrf_upsample2d2_fwd(const void* x, int B, int H, int W, int C, void* y, void* stream);
+PGRF_API int pgrf_channel_dot_upsample_fwd(const float* x, long long sb, long long sc, long long sh, long long sw, int B, int C, int H,
+                                           int W, const float* w, float bias, int scale, int rectify, float* out, void* stream);
 
 /* MixtureLogisticsDistDecoder.compute_prob (dist_decoder.py:113-140) with get_near_far_points(is_ref=True) (:6-51):
  * depth (rfn,n), interval (n) shared by all views or (rfn,n) when interval_per_view, mean/var (rfn,n,2), vis (rfn,n) or NULL

@@ -45,3 +45,34 @@ def unet3d(W, x, n_enc=4):
         x = torch.cat((x, skips[i]), dim=1)
         x, _ = conv_block(W, f"decoders.{i}", x, pool=False)
     return x
+
+
+# ---- 2-D heads after the regulariser (models/test_models.py:147-205, pipeline3_model.py:866-905) -----------------------------------
+def wrap_pad2d(x):
+    """WrapPadding (common_blocks.py:258-293): zeros along height, wrap along width."""
+    x = F.pad(x, (0, 0, 1, 1))
+    return torch.cat([x[..., -1:], x, x[..., :1]], -1)
+
+
+def rectify(x, out_type):
+    """pipeline3_model.py:875-879: disparity -> depth, or clamp."""
+    return 1.0 / (torch.clamp(x, min=0) + 1e-10) if out_type == "disparity" else torch.clamp(x, min=0)
+
+
+def decoders1(W, cost_reg, out_type):
+    """ConvBlock(kernel 1, no norm / activation) + x4 bilinear + rectification -> raw (B,4H,4W,1), depth (B,4H,4W,1)"""
+    y = F.conv2d(cost_reg, W["decoders1.conv.weight"], W["decoders1.conv.bias"])
+    raw = F.interpolate(y, scale_factor=4, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    return raw, rectify(raw, out_type)
+
+
+def decoders2(W, feats):
+    """three ConvBlock2 (common_blocks.py:96-184): [x2 bilinear] pad-conv-lrelu-pad-conv-lrelu; the last one without upscale / activation"""
+    for i, (up, act) in enumerate(((True, True), (True, True), (False, False))):
+        if up:
+            feats = F.interpolate(feats, scale_factor=2, mode="bilinear", align_corners=False)
+        for k in ("conv1", "conv2"):
+            feats = F.conv2d(wrap_pad2d(feats), W[f"decoders2.{i}.{k}.weight"], W[f"decoders2.{i}.{k}.bias"])
+            if act:
+                feats = F.leaky_relu(feats, 0.01)
+    return feats

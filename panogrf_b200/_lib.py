@@ -164,6 +164,9 @@ SIGNATURES.update({
     "pgrf_conv3d_cout1_fwd": (_I, [_P, _I, _P, _I, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P]),
     "pgrf_avgpool3d2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "pgrf_upsample3d2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "pgrf_upsample2d2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "pgrf_channel_dot_upsample_fwd": (_I, [_P, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _I, _I, _I, _I,
+                                           _P, _F, _I, _I, _P, _P]),
     "pgrf_depth2points_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, ctypes.c_longlong, _I, _P, _P, _P]),
     "pgrf_render_workspace": (_I, [_I, ctypes.c_longlong, _PLL, _PLL]),
     "pgrf_render_view_fwd": (_I, [ctypes.POINTER(RenderViewArgs), _P]),

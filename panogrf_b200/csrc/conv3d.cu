@@ -41,6 +41,8 @@ struct ConvParams {
   long long n_vox;
   int splits;                          // split-K over the 9 (kd, kh) tap rows: blockIdx.z accumulates 9/splits of them into
   float* ws;                           // fp32 partial sums [splits][n_vox][Cout] (bias / activation applied by the reduction)
+  int krow_lo, krow_cnt;               // (kd, kh) tap rows walked: all 9, or rows 3..5 when D == 1 (a 2-D convolution: the kd != 1
+                                       // taps only ever see the zero padding)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_kernel(const ConvPa
   umma::fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const int nt = blockIdx.y;
-  const int n_taps = 27 / p.splits, tap0 = blockIdx.z * n_taps;       // this CTA's share of the taps
+  const int n_taps = p.krow_cnt * 3 / p.splits, tap0 = p.krow_lo * 3 + blockIdx.z * n_taps;       // this CTA's share of the taps
 
   if (warp == 8) {
     if (r == kGatherThreads)
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_row_kernel(const Co
   umma::fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const int nt = blockIdx.y;
-  const int n_krow = 9 / p.splits, krow0 = blockIdx.z * n_krow;
+  const int n_krow = p.krow_cnt / p.splits, krow0 = p.krow_lo + blockIdx.z * n_krow;
 
   if (warp == 8) {
     if (r == kGatherThreads)
@@ -429,8 +431,8 @@ __device__ __forceinline__ void up_src(int o, int n, int& i0, int& i1, float& l)
   l = s - (float)i0;
 }
 __global__ void __launch_bounds__(256) upsample3d2_kernel(const __nv_bfloat16* __restrict__ x, int B, int D, int H, int W, int C,
-                                                          __nv_bfloat16* __restrict__ y) {
-  const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W, C8 = C / 8;
+                                                          int scale_d, __nv_bfloat16* __restrict__ y) {
+  const int Do = scale_d * D, Ho = 2 * H, Wo = 2 * W, C8 = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * Do * Ho * Wo * C8) return;
   long long t = i;
@@ -441,7 +443,8 @@ __global__ void __launch_bounds__(256) upsample3d2_kernel(const __nv_bfloat16* _
   const int b = (int)(t / Do);
   int d0, d1, y0, y1, x0, x1;
   float ld, ly, lx;
-  up_src(dO, D, d0, d1, ld); up_src(yo, H, y0, y1, ly); up_src(xo, W, x0, x1, lx);
+  if (scale_d == 2) up_src(dO, D, d0, d1, ld); else { d0 = d1 = dO; ld = 0.f; }      // scale_d == 1: bilinear (2-D feature maps)
+  up_src(yo, H, y0, y1, ly); up_src(xo, W, x0, x1, lx);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int k = 0; k < 8; ++k) {
     const int dd = (k & 4) ? d1 : d0, yy = (k & 2) ? y1 : y0, xx = (k & 1) ? x1 : x0;
@@ -478,6 +481,39 @@ __global__ void __launch_bounds__(256) to_bf16_cl_kernel(const float* __restrict
   reinterpret_cast<uint4*>(y + i / C8 * Cpad)[c8] = o;
 }
 
+// decoders1 of the MVS head (models/test_models.py:147-158, pipeline3_model.py:866-879): 1x1 convolution over the depth axis of the
+// regularised cost (C = D channels -> 1) followed by F.interpolate(scale_factor, 'bilinear', align_corners=False) and the depth
+// rectification (1: clamp(min=0), 2: 1 / (clamp(min=0) + 1e-10)).  The 1x1 convolution commutes with the (linear) interpolation, so
+// each output pixel blends its four source pixels' dot products; thread = output pixel.  fp32 throughout.
+__global__ void __launch_bounds__(256) channel_dot_upsample_kernel(const float* __restrict__ x, long long sb, long long sc, long long sh,
+                                                                   long long sw, int B, int C, int H, int W, const float* __restrict__ w,
+                                                                   float bias, int scale, int rectify, float* __restrict__ out) {
+  const int Ho = H * scale, Wo = W * scale;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Ho * Wo) return;
+  const int xo = (int)(i % Wo), yo = (int)((i / Wo) % Ho), b = (int)(i / ((long long)Wo * Ho));
+  const float inv = 1.f / (float)scale;
+  float sy = ((float)yo + 0.5f) * inv - 0.5f, sx = ((float)xo + 0.5f) * inv - 0.5f;      // ATen area_pixel_compute_source_index
+  sy = sy < 0.f ? 0.f : sy; sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float* p00 = x + b * sb + y0 * sh + x0 * sw;
+  const float* p01 = x + b * sb + y0 * sh + x1 * sw;
+  const float* p10 = x + b * sb + y1 * sh + x0 * sw;
+  const float* p11 = x + b * sb + y1 * sh + x1 * sw;
+  float a00 = bias, a01 = bias, a10 = bias, a11 = bias;
+  for (int c = 0; c < C; ++c) {
+    const float wc = __ldg(w + c);
+    a00 = fmaf(wc, __ldg(p00 + c * sc), a00); a01 = fmaf(wc, __ldg(p01 + c * sc), a01);
+    a10 = fmaf(wc, __ldg(p10 + c * sc), a10); a11 = fmaf(wc, __ldg(p11 + c * sc), a11);
+  }
+  float v = (1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11);
+  if (rectify) v = fmaxf(v, 0.f);
+  if (rectify == 2) v = 1.0f / (v + 1e-10f);
+  out[i] = v;
+}
+
 }  // namespace pgrf
 
 using namespace pgrf;
@@ -503,7 +539,7 @@ extern "C" int pgrf_conv3d_to_bf16_cl(const float* x, long long sb, long long sc
 }
 
 struct ConvPlan {
-  int KC, n_cc, NT, row, S, splits;
+  int KC, n_cc, NT, row, S, splits, krow_lo, krow_cnt;
   size_t smem;
   dim3 grid;
   long long ws_floats;
@@ -529,10 +565,13 @@ static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, Con
   const size_t stage = pl.row ? (size_t)(KC / 8) * kRowPitch + 3 * (size_t)KC * pl.NT * 2            // [130-row operand | three taps of weights]
                               : (size_t)(KC / 8) * (kConvRows * 16 + kConvPad) + (size_t)KC * pl.NT * 2;
   // split-K over the nine (kd, kh) tap rows when the (voxel tile x channel tile) grid cannot fill the GPU (2 CTAs per SM assumed)
+  pl.krow_lo = D == 1 ? 3 : 0;                   // D == 1: a 2-D convolution, only the kd == 1 tap rows can see data
+  pl.krow_cnt = D == 1 ? 3 : 9;
   pl.splits = 1;
   if (g_conv_splits > 0) pl.splits = g_conv_splits;
   else if (n_cta < 444) pl.splits = n_cta * 3 >= 740 ? 3 : 9;
   PGRF_REQUIRE(pl.splits == 1 || pl.splits == 3 || pl.splits == 9, "conv3d: splits=%d (1, 3 or 9)", pl.splits);
+  if (pl.splits > pl.krow_cnt) pl.splits = pl.krow_cnt;
   // pipeline depth: as many stages as keep two CTAs on an SM (one CTA's epilogue hides behind the other's main loop), at least 2 / 3
   const int s_min = pl.row ? 2 : 3, s_max = pl.row ? 4 : 6;
   int S = (int)(((size_t)g_conv_smem_kb * 1024) / stage);
@@ -572,7 +611,7 @@ extern "C" int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, c
   p.wpk = (const unsigned char*)wpk; p.bias = bias; p.y = (__nv_bfloat16*)y; p.Cout = Cout; p.yf = yf; p.cout_real = cout_real;
   p.B = B; p.D = D; p.H = H; p.W = W; p.act = act; p.KC = pl.KC; p.n_cc = pl.n_cc;
   p.n_vox = (long long)B * D * H * W;
-  p.splits = pl.splits; p.ws = ws;
+  p.splits = pl.splits; p.ws = ws; p.krow_lo = pl.krow_lo; p.krow_cnt = pl.krow_cnt;
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid = pl.grid;
   const size_t smem = pl.smem;
@@ -630,10 +669,30 @@ extern "C" int pgrf_avgpool3d2_fwd(const void* x, int B, int D, int H, int W, in
   return PGRF_OK;
 }
 
+extern "C" int pgrf_upsample2d2_fwd(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+  PGRF_REQUIRE(x && y && C % 8 == 0, "upsample2d: C %% 8 == 0");
+  const long long n = (long long)B * (2 * H) * (2 * W) * (C / 8);
+  upsample3d2_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, 1, H, W, C, 1, (__nv_bfloat16*)y);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_channel_dot_upsample_fwd(const float* x, long long sb, long long sc, long long sh, long long sw, int B, int C, int H,
+                                             int W, const float* w, float bias, int scale, int rectify, float* out, void* stream) {
+  PGRF_REQUIRE(x && w && out && B >= 1 && C >= 1 && H >= 1 && W >= 1 && scale >= 1, "channel_dot_upsample: bad arguments");
+  PGRF_REQUIRE(rectify >= 0 && rectify <= 2, "channel_dot_upsample: rectify=%d (0 none, 1 depth, 2 disparity)", rectify);
+  const long long n = (long long)B * H * scale * W * scale;
+  channel_dot_upsample_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, sb, sc, sh, sw, B, C, H, W, w, bias, scale, rectify, out);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
 extern "C" int pgrf_upsample3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream) {
   PGRF_REQUIRE(x && y && C % 8 == 0, "upsample3d: C %% 8 == 0");
   const long long n = (long long)B * (2 * D) * (2 * H) * (2 * W) * (C / 8);
-  upsample3d2_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, D, H, W, C, (__nv_bfloat16*)y);
+  upsample3d2_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, D, H, W, C, 2, (__nv_bfloat16*)y);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;

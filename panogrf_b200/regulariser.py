@@ -62,7 +62,7 @@ def pack_conv_cout1(weight, ca, cb, ca_pad, cb_pad):
     return wp.contiguous()
 
 
-def conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels=0, ws_cache=None, lib=None, st=None):
+def conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels=0, ws_cache=None, lib=None, st=None, act=True):
     """One Conv3d(3x3x3) + WrapPadding3D + bias + LeakyReLU layer on [xa | xb] (bf16 channels-last, packed weights from `pack_conv`).
     Returns bf16 channels-last (B,D,H,W,co_pad), or fp32 (B,f32_channels,D,H,W) when f32_channels > 0."""
     lib = lib or _lib.load()
@@ -84,7 +84,8 @@ def conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels=0, ws_cache=None, lib=N
         y = torch.empty((B, D, H, W, co_pad), device=xa.device, dtype=torch.bfloat16)
     _lib.check(lib.pgrf_conv3d_fwd(_lib.ptr(xa), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad, _lib.ptr(wpk), _lib.ptr(bias),
                                    None if f32_channels else _lib.ptr(y), _lib.ptr(y) if f32_channels else None, f32_channels, co_pad,
-                                   B, D, H, W, 1, _lib.ptr(ws) if ws is not None else None, need.value, st), "pgrf_conv3d_fwd")
+                                   B, D, H, W, 1 if act else 0, _lib.ptr(ws) if ws is not None else None, need.value, st),
+               "pgrf_conv3d_fwd")
     return y
 
 
@@ -208,3 +209,104 @@ class CostRegulariser3D(nn.Module):
                            "pgrf_conv3d_cout1_fwd")
                 return out.unsqueeze(1)
         raise RuntimeError("unet3d: the first decoder must have one output channel (models/test_models.py:113)")
+
+
+class _Block2D(nn.Module):
+    """Parameter holder with ConvBlock2's names (models/common_blocks.py:96-184)."""
+
+    def __init__(self, cin, cout, upscale, act):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, kernel_size=3, padding=0)
+        self.conv2 = nn.Conv2d(cout, cout, kernel_size=3, padding=0)
+        self.upscale, self.act = upscale, act
+
+
+class _Conv1x1(nn.Module):
+    """Parameter holder with ConvBlock's name `conv` (models/common_blocks.py:10-94)."""
+
+    def __init__(self, cin):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, 1, kernel_size=1)
+
+
+class CostDecoders2D(nn.Module):
+    """`decoders1` / `decoders2` of the reference's MVS network (models/test_models.py:147-205), applied as in
+    network/omni_mvsnet/pipeline3_model.py:866-905: `depth_d1(cost_reg)` = 1x1 convolution over the depth axis + x4 bilinear +
+    rectification; `forward(image_features)` = the three ConvBlock2 of the mono-stereo fusion (x2 bilinear, WrapPadding, 3x3
+    convolutions on the tensor cores as D == 1 volumes) -> (B, 1, 4H, 4W) fp32.  `out_channels` = 1 (no `mvs_uncertainty` head)."""
+
+    def __init__(self, size=4, cost_volume_channels=64, wo_mono_feat=False, with_sin=False):
+        super().__init__()
+        self.decoders1 = _Conv1x1(cost_volume_channels)
+        in_dim = cost_volume_channels + (0 if wo_mono_feat else 2 ** (size + 1)) + (1 if with_sin else 0)
+        self.decoders2 = nn.ModuleList([_Block2D(in_dim, 2 ** (size + 1), True, True), _Block2D(2 ** (size + 1), 2 ** size, True, True),
+                                        _Block2D(2 ** size, 1, False, False)])
+        self._packed = {}
+        self._ws_cache = {}
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def _pack(self, conv, ca_pad, simt=False):
+        ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), str(conv.weight.device), ca_pad, simt)
+        hit = self._packed.get(id(conv))
+        if hit is None or hit[0] != ver:
+            co, ci = conv.weight.shape[:2]
+            w3 = torch.zeros((co, ci, 3, 3, 3), device=conv.weight.device, dtype=torch.float32)
+            w3[:, :, 1] = conv.weight.detach().float()                 # a 2-D kernel is the kd == 1 slice of a 3-D one
+            if simt:
+                hit = (ver, pack_conv_cout1(w3, ci, 0, ca_pad, 0), float(conv.bias.detach().float().item()))
+            else:
+                hit = (ver,) + pack_conv(w3, conv.bias, ci, 0, ca_pad, 0)
+            self._packed[id(conv)] = hit
+        return hit[1], hit[2]
+
+    def depth_d1(self, cost_reg, out_type="depth"):
+        """cost_reg (B, D, H, W) fp32, any strides (e.g. `unet3d(x)[:, 0]`) -> raw or rectified (B, 4H, 4W, 1)
+        (`out_type` in {"raw", "depth", "disparity"}; pipeline3_model.py:866-879)."""
+        _lib.require_cuda(cost_reg)
+        lib = _lib.load()
+        x = cost_reg.detach().float()
+        B, C, H, W = x.shape
+        conv = self.decoders1.conv
+        if C != conv.weight.shape[1]:
+            raise RuntimeError(f"decoders1 expects {conv.weight.shape[1]} channels, got {C}")
+        w = conv.weight.detach().float().reshape(-1).contiguous()
+        out = torch.empty((B, 4 * H, 4 * W, 1), device=x.device, dtype=torch.float32)
+        mode = {"raw": 0, "depth": 1, "disparity": 2}[out_type]
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pgrf_channel_dot_upsample_fwd(_lib.ptr(x), *x.stride(), B, C, H, W, _lib.ptr(w), float(conv.bias.item()), 4, mode,
+                                                         _lib.ptr(out), _lib.stream_ptr()), "pgrf_channel_dot_upsample_fwd")
+        return out
+
+    def forward(self, image_features):
+        """image_features (B, C, H, W) fp32 = cat(regularised cost, mono features) -> (B, 1, 4H, 4W) fp32 (pipeline3_model.py:902-905)."""
+        _lib.require_cuda(image_features)
+        lib = _lib.load()
+        x = image_features.detach().float()
+        B, C, H, W = x.shape
+        if C != self.decoders2[0].conv1.weight.shape[1]:
+            raise RuntimeError(f"decoders2 expects {self.decoders2[0].conv1.weight.shape[1]} channels, got {C}")
+        dev = x.device
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr()
+            cpad = _pad16(C)
+            a = torch.empty((B, 1, H, W, cpad), device=dev, dtype=torch.bfloat16)
+            sb, sc, sh, sw = x.stride()
+            _lib.check(lib.pgrf_conv3d_to_bf16_cl(_lib.ptr(x), sb, sc, 0, sh, sw, B, C, 1, H, W, cpad, _lib.ptr(a), st), "pgrf_conv3d_to_bf16_cl")
+            for blk in self.decoders2[:2]:
+                up = torch.empty((B, 1, 2 * H, 2 * W, a.shape[-1]), device=dev, dtype=torch.bfloat16)
+                _lib.check(lib.pgrf_upsample2d2_fwd(_lib.ptr(a), B, H, W, a.shape[-1], _lib.ptr(up), st), "pgrf_upsample2d2_fwd")
+                H, W = 2 * H, 2 * W
+                co_pad = _pad16(blk.conv1.weight.shape[0])
+                w1, b1 = self._pack(blk.conv1, up.shape[-1])
+                t = conv3d(up, None, w1, b1, co_pad, (B, 1, H, W), 0, self._ws_cache, lib, st)
+                w2, b2 = self._pack(blk.conv2, co_pad)
+                a = conv3d(t, None, w2, b2, co_pad, (B, 1, H, W), 0, self._ws_cache, lib, st)
+            blk = self.decoders2[2]                                     # 2^size -> 1 -> 1, no activation, fp32
+            w1, b1 = self._pack(blk.conv1, a.shape[-1])
+            t = conv3d(a, None, w1, b1, 16, (B, 1, H, W), 1, self._ws_cache, lib, st, act=False)           # (B,1,1,H,W) fp32
+            w2, b2 = self._pack(blk.conv2, 1, simt=True)
+            out = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+            _lib.check(lib.pgrf_conv3d_cout1_fwd(None, 0, None, 0, _lib.ptr(t), _lib.ptr(w2), b2, B, 1, H, W, 0, _lib.ptr(out), st),
+                       "pgrf_conv3d_cout1_fwd")
+        return out

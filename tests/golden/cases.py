@@ -319,3 +319,22 @@ def make_unet3d_input(name):
     size, shape = UNET3D_CASES[name]
     g = torch.Generator().manual_seed(300 + sorted(UNET3D_CASES).index(name))
     return torch.rand(*shape, generator=g) * 2.0      # abs-diff costs are non-negative
+
+
+# ------------------------------------------------------------------------------------------------
+# 2-D heads after the regulariser: decoders1 / decoders2 (models/test_models.py:147-205, pipeline3_model.py:866-905)
+# ------------------------------------------------------------------------------------------------
+DEC2D_CASES = {
+    # name: (size, cost_volume_channels = D, (B, H, W), out_type)
+    "dec2d_s1": (1, 8, (2, 8, 16), "depth"),
+    "dec2d_s2": (2, 16, (1, 8, 32), "disparity"),        # 4x upscaled width = 128: the row variant of the convolution kernel
+}
+
+
+def make_dec2d_inputs(name):
+    """regularised cost (B, D, H, W) as unet3d returns it ((B,1,D,H,W)[:, 0]) and the mono feature map (B, 2^(size+1), H, W)"""
+    size, D, (B, H, W), _ = DEC2D_CASES[name]
+    g = torch.Generator().manual_seed(400 + sorted(DEC2D_CASES).index(name))
+    cost_reg = torch.randn(B, 1, D, H, W, generator=g)[:, 0]
+    mono = torch.randn(B, 2 ** (size + 1), H, W, generator=g)
+    return cost_reg, mono

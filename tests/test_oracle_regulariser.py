@@ -65,3 +65,24 @@ def test_pack_conv_layout(co, ca, cb):
     assert torch.equal(dense[:co, :, :ca], ref[:, :, :ca])
     assert torch.equal(dense[:co, :, ca_pad:ca_pad + cb], ref[:, :, ca:])
     assert float(dense[co:].abs().sum()) == 0 and float(dense[:, :, ca:ca_pad].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("name", list(cases.DEC2D_CASES))
+def test_decoders_oracle_matches_reference_classes(name):
+    g = load_golden(name)
+    W = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
+    out_type = cases.DEC2D_CASES[name][3]
+    raw, depth_d1 = oreg.decoders1(W, g["cost_reg"], out_type)
+    assert torch.allclose(raw, g["raw_d1"], rtol=1e-5, atol=1e-6) and torch.allclose(depth_d1, g["depth_d1"], rtol=1e-4, atol=1e-6)
+    feats = oreg.decoders2(W, torch.cat((g["cost_reg"], g["mono"]), 1))
+    assert torch.allclose(feats, g["feats"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(oreg.rectify(feats[:, :1], out_type).permute(0, 2, 3, 1), g["depth"], rtol=1e-4, atol=1e-6)
+
+
+def test_decoders_container_has_the_reference_parameter_names():
+    g = load_golden("dec2d_s1")
+    W = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
+    size, D, _, _ = cases.DEC2D_CASES["dec2d_s1"]
+    net = reg.CostDecoders2D(size, D)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in W.items()}
+    net.load_state_dict(W)

@@ -158,3 +158,27 @@ def test_unet3d_rejects_bad_shapes():
         net(torch.zeros(1, 4, 8, 8, 12, device="cuda"))       # W not a multiple of 8
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 8, 8, 8, 16, device="cuda"))       # wrong channel count
+
+
+@pytest.mark.parametrize("name", list(cases.DEC2D_CASES))
+def test_decoders_2d_match_reference_golden(name):
+    """decoders1 (fp32: 1x1 convolution + x4 bilinear + rectification) and decoders2 (bf16 tensor-core 3x3 convolutions as D == 1
+    volumes, bilinear x2 upscaling) against outputs of the reference's ConvBlock / ConvBlock2 classes."""
+    from panogrf_b200 import regulariser as reg
+    g = load_golden(name)
+    W = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
+    size, D, _, out_type = cases.DEC2D_CASES[name]
+    net = reg.CostDecoders2D(size, D)
+    net.load_state_dict(W)
+    net = net.cuda()
+    # decoders1 on the strided view unet3d returns ((B,1,D,H,W)[:, 0])
+    cost5 = g["cost_reg"].cuda()[:, None]
+    raw = net.depth_d1(cost5[:, 0], "raw").cpu()
+    assert torch.allclose(raw, g["raw_d1"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(net.depth_d1(cost5[:, 0], out_type).cpu(), g["depth_d1"], rtol=1e-3, atol=1e-5)
+    feats = net(torch.cat((g["cost_reg"], g["mono"]), 1).cuda()).cpu()
+    assert feats.shape == g["feats"].shape
+    scale = float(g["feats"].abs().max())
+    err = float((feats - g["feats"]).abs().max())
+    print(f"{name}: decoders2 max err {err:.3e} of range {scale:.3e} ({err / scale:.2e})")
+    assert err <= UNET_TOL * scale
