@@ -713,6 +713,12 @@ def time_cost_volume(torch, pg, flush, peaks, light=False):
     ms_cl = _median_ms(torch, flush, lambda: pg.calculate_cost_volume_erp(args, images, depths, trans, rots, out_layout="bdhwc"),
                        n=7, reps=REPS, warm=2)
     res["channels_last"] = {"ms": ms_cl, "voxels_per_s": vox / ms_cl * 1e3, "frac": alg / ms_cl / 1e6 / peaks["hbm_gbs"]}
+    ms_16 = _median_ms(torch, flush, lambda: pg.calculate_cost_volume_erp(args, images, depths, trans, rots, out_layout="bdhwc_bf16"),
+                       n=7, reps=REPS, warm=2)
+    alg16 = alg - vox * C * 2                      # the volume itself is 2 bytes per channel
+    res["channels_last_bf16"] = {"ms": ms_16, "voxels_per_s": vox / ms_16 * 1e3, "frac": alg16 / ms_16 / 1e6 / peaks["hbm_gbs"],
+                                 "bytes_per_voxel": alg16 / vox,
+                                 "note": "the layout the tensor-core regulariser consumes in place (no fp32 volume, no conversion pass)"}
     # backward: d/d(images) of the same volume (reads the 1.07 GB upstream gradient once, vector atomics into 2 maps)
     img_g = images.clone().requires_grad_(True)
     out = pg.calculate_cost_volume_erp(args, img_g, depths, trans, rots, out_layout="bdhwc")
@@ -881,6 +887,20 @@ def time_mvs_stages(torch, dev, flush, peaks):
         ms_lib = _median_ms(torch, flush, lambda: lib_unet(x), n=3)
         ref = lib_unet(x)
         err = float((net(x) - ref).abs().max() / ref.abs().max())
+    # sweep -> regulariser as one pipeline: 64x128 feature maps, D = 64 hypotheses -> the same 1x32x64x64x128 volume
+    from panogrf_b200 import calculate_cost_volume_erp as pg_cv
+    from panogrf_b200 import spherical_cost_volume as scv
+    imgs, rots, trans = _cv_inputs(torch, dev, 1, H, W, 32, seed=9)
+    depths = torch.linspace(0.5, 15.0, D, device=dev)
+    cv_args = {"dataset_name": "m3d", "contain_dnet": False, "mono_uncertainty": False}
+    pipe16 = lambda: net(pg_cv(cv_args, imgs, depths, trans, rots, out_layout="bdhwc_bf16").permute(0, 4, 1, 2, 3))
+    pipe32 = lambda: net(pg_cv(cv_args, imgs, depths, trans, rots).permute(0, 4, 1, 2, 3))
+    ms_p16 = _median_ms(torch, flush, pipe16, n=5)
+    ms_p32 = _median_ms(torch, flush, pipe32, n=5)
+    scv.check_pending()
+    res["sweep_plus_unet3d"] = {"ms_bf16_volume": ms_p16, "ms_fp32_reference_layout_volume": ms_p32,
+                                "note": "calculate_cost_volume_erp -> unet3d; bf16 channels-last volume consumed in place vs the "
+                                        "reference (B,D,C,H,W) fp32 volume + conversion pass"}
     res["unet3d_1x32x64x64x128"] = {
         "ms": ms, "gflop": flops / 1e9, "tflops": flops / ms / 1e9, "frac_of_bf16_peak": flops / ms / 1e9 / peaks["bf16_tflops"],
         "library_ms": ms_lib, "library": "the same network through torch/cuDNN fp32 (TF32) convolutions, as the reference runs it",

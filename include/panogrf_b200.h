@@ -51,6 +51,8 @@ extern "C" {
 #define PGRF_CV_BDHWC 1   /* channels-last contiguous (B,D,H,W,C)                                   */
 #define PGRF_CV_BCDHW 2   /* what the 3-D regulariser consumes (pipeline3_model.py:847); with        */
                           /* groups>0 this is the group-wise mean (B,G,D,H,W) (pipeline3_model.py:849-853) */
+#define PGRF_CV_BDHWC_BF16 3 /* channels-last (B,D,H,W,C) stored as bf16 (`out` points to 2-byte elements, C % 16 == 0): the */
+                          /* operand layout of pgrf_conv3d_fwd — the regulariser consumes the sweep without a conversion pass */
 
 PGRF_API const char* pgrf_last_error(void);
 PGRF_API int pgrf_version(void);

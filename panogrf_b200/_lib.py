@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libpanogrf_b200.so")
 
 DATASET_IDS = {"m3d": 0, "replica_test": 1, "residential": 2, "CoffeeArea": 3}
 COST_IDS = {"abs_diff": 0, "dot": 1, "none": 2}
-CV_LAYOUT_IDS = {"bdchw": 0, "bdhwc": 1, "bcdhw": 2}
+CV_LAYOUT_IDS = {"bdchw": 0, "bdhwc": 1, "bcdhw": 2, "bdhwc_bf16": 3}
 
 PGRF_OK, PGRF_EINVAL, PGRF_ECUDA, PGRF_ERANGE = 0, -1, -2, -3
 

@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_kernel(const CvP
     // Sub-iterations are processed JB at a time with ALL their gathers issued before the first use, so a
     // lane keeps 4*JB independent 128-bit loads in flight (the kernel is latency bound on these L1/L2 hits).
     constexpr int JB = (NSUB >= JBT) ? JBT : NSUB;
-    float4* out_cl = reinterpret_cast<float4*>(p.out) + ((((size_t)b * p.D + d) * p.H + y) * p.W + x_warp) * CG + lane;
+    const size_t cl_idx = ((((size_t)b * p.D + d) * p.H + y) * p.W + x_warp) * CG + lane;      // 4-channel group index of this lane
+    float4* out_cl = reinterpret_cast<float4*>(p.out) + cl_idx;
+    uint2* out_cl16 = reinterpret_cast<uint2*>(p.out) + cl_idx;                                // bf16 channels-last variant
 #pragma unroll
     for (int j0 = 0; j0 < NSUB; j0 += JB) {
       float4 acc[JB];
@@ -148,7 +150,16 @@ __global__ void __launch_bounds__(kCvThreads, MINB) cost_volume_kernel(const CvP
         const int pi = (j0 + jj) * PPS + pp;
         if (!PLANAR) {
           // lane (pp,cg) of sub-iteration j writes float4 index j*32 + lane of the warp's 32*CG contiguous float4
-          if (x_warp + pi < p.W) stcs4(out_cl + (j0 + jj) * 32, acc[jj]);
+          if (x_warp + pi < p.W) {
+            if (p.out_bf16) {   // what the tensor-core regulariser consumes: half the bytes, no conversion pass
+              uint2 q;
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(acc[jj].y), "f"(acc[jj].x));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(acc[jj].w), "f"(acc[jj].z));
+              __stcs(out_cl16 + (j0 + jj) * 32, q);
+            } else {
+              stcs4(out_cl + (j0 + jj) * 32, acc[jj]);
+            }
+          }
         } else {
           // tile[c][pixel] with row pitch 33: bank = (4cg + k + 4j + pp) mod 32 -> conflict-free
           tile[(cg * 4 + 0) * 33 + pi] = acc[jj].x;
@@ -467,6 +478,7 @@ namespace pgrf {
 int cv_fill_params(CvParams& p, const float* images, int B, int S, int H, int W, int C, const float* depths, const float* depth_volume,
                    int D, const float* rots, const float* trans, int ref_idx, const int* src_views, int n_src, float divisor,
                    int dataset, int cost_type) {
+  p.out_bf16 = 0;
   PGRF_REQUIRE(images && rots && trans && src_views, "cost_volume: null pointer argument");
   PGRF_REQUIRE(depths || depth_volume, "cost_volume: need depths or depth_volume");
   PGRF_REQUIRE(B > 0 && S > 0 && H > 1 && W > 1 && D > 0, "cost_volume: bad shape B=%d S=%d H=%d W=%d D=%d", B, S, H, W, D);
@@ -504,7 +516,8 @@ extern "C" int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, in
                                     int dataset, int cost_type, int layout, int groups,
                                     float* out, int* err_flag, void* stream) {
   PGRF_REQUIRE(out && err_flag, "cost_volume: null pointer argument");
-  PGRF_REQUIRE(layout >= 0 && layout <= 2, "cost_volume: unknown layout %d", layout);
+  PGRF_REQUIRE(layout >= 0 && layout <= 3, "cost_volume: unknown layout %d", layout);
+  PGRF_REQUIRE(layout != PGRF_CV_BDHWC_BF16 || C % 16 == 0, "cost_volume: the bf16 channels-last layout needs C %% 16 == 0 (C=%d)", C);
   PGRF_REQUIRE(groups == 0 || (layout == PGRF_CV_BCDHW && groups > 0 && C % groups == 0),
                "cost_volume: groups=%d needs layout BCDHW and C %% groups == 0", groups);
   PGRF_REQUIRE(((uintptr_t)out & 15) == 0, "cost_volume: images/out must be 16-byte aligned");
@@ -513,6 +526,8 @@ extern "C" int pgrf_cost_volume_fwd(const float* images, int B, int S, int H, in
                                  dataset, cost_type);
   if (frc != PGRF_OK) return frc;
   p.out = out; p.err = err_flag;
+  p.out_bf16 = layout == PGRF_CV_BDHWC_BF16;
+  if (p.out_bf16) layout = PGRF_CV_BDHWC;
   p.groups = groups;
   p.OC = groups > 0 ? groups : C;
   const long long HW = (long long)H * W;

@@ -22,6 +22,7 @@ struct CvParams {
   float divisor;
   int dataset, cost_type, groups, OC;
   int d_chunk;
+  int out_bf16;            // channels-last output stored as bf16 (PGRF_CV_BDHWC_BF16)
   long long sB, sD, sC;  // planar strides in elements
   float ang0, ang1, ang2, ang3;  // per-dataset pixel->angle constants (see host side)
 };

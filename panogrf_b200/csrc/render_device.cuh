@@ -155,19 +155,22 @@ __device__ __forceinline__ void row_layer(const float* __restrict__ A, int lda, 
 template <int K, int N, int NP>
 __device__ __forceinline__ void reg_layer(const float (&in)[K], const float* __restrict__ Wt,
                                           const float* __restrict__ bias, float (&out)[NP]) {
+  // packed fp32 pairs over neighbouring output columns: the same IEEE fma per element (bit-identical), half the issue slots
+  float2 acc[NP / 2];
 #pragma unroll
-  for (int n = 0; n < NP; ++n) out[n] = bias ? bias[n] : 0.f;
+  for (int n = 0; n < NP / 2; ++n) acc[n] = bias ? make_float2(bias[2 * n], bias[2 * n + 1]) : make_float2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
+    const float2 xk = make_float2(in[k], in[k]);
 #pragma unroll
     for (int n4 = 0; n4 < NP / 4; ++n4) {
       const float4 w = *reinterpret_cast<const float4*>(Wt + k * NP + 4 * n4);
-      out[4 * n4] = fmaf(in[k], w.x, out[4 * n4]);
-      out[4 * n4 + 1] = fmaf(in[k], w.y, out[4 * n4 + 1]);
-      out[4 * n4 + 2] = fmaf(in[k], w.z, out[4 * n4 + 2]);
-      out[4 * n4 + 3] = fmaf(in[k], w.w, out[4 * n4 + 3]);
+      acc[2 * n4] = ffma2(xk, make_float2(w.x, w.y), acc[2 * n4]);
+      acc[2 * n4 + 1] = ffma2(xk, make_float2(w.z, w.w), acc[2 * n4 + 1]);
     }
   }
+#pragma unroll
+  for (int n = 0; n < NP / 2; ++n) { out[2 * n] = acc[n].x; out[2 * n + 1] = acc[n].y; }
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -151,9 +151,12 @@ class CostRegulariser3D(nn.Module):
         _lib.require_cuda(cost_volume)
         lib = _lib.load()
         x = cost_volume.detach()
-        if x.dtype != torch.float32:
-            x = x.float()
         B, C, D, H, W = x.shape
+        # bf16 channels-last storage (what calculate_cost_volume_erp(out_layout="bdhwc_bf16").permute(0, 4, 1, 2, 3) is): consumed in place
+        direct = (x.dtype == torch.bfloat16 and C % 16 == 0 and x.stride() == (D * H * W * C, 1, H * W * C, W * C, C)
+                  and x.data_ptr() % 16 == 0)
+        if not direct and x.dtype != torch.float32:
+            x = x.float()
         n_enc = len(self.encoders)
         f = 2 ** (n_enc - 1)
         if C != self.in_channels:
@@ -166,11 +169,14 @@ class CostRegulariser3D(nn.Module):
             raise RuntimeError("CostRegulariser3D parameters and input are on different devices; call .to(device) first")
         with torch.cuda.device(dev):
             st = _lib.stream_ptr()
-            cpad = _pad16(C)
-            a = torch.empty((B, D, H, W, cpad), device=dev, dtype=torch.bfloat16)
-            sb, sc, sd, sh, sw = x.stride()
-            _lib.check(lib.pgrf_conv3d_to_bf16_cl(_lib.ptr(x), sb, sc, sd, sh, sw, B, C, D, H, W, cpad, _lib.ptr(a), st),
-                       "pgrf_conv3d_to_bf16_cl")
+            if direct:
+                a = x.permute(0, 2, 3, 4, 1)                      # the (B,D,H,W,C) storage itself
+            else:
+                cpad = _pad16(C)
+                a = torch.empty((B, D, H, W, cpad), device=dev, dtype=torch.bfloat16)
+                sb, sc, sd, sh, sw = x.stride()
+                _lib.check(lib.pgrf_conv3d_to_bf16_cl(_lib.ptr(x), sb, sc, sd, sh, sw, B, C, D, H, W, cpad, _lib.ptr(a), st),
+                           "pgrf_conv3d_to_bf16_cl")
             dims = (B, D, H, W)
             skips = []
             ch = C

@@ -88,6 +88,8 @@ class _SweepFn(torch.autograd.Function):
             store = torch.empty((B, D, OC, H, W), device=dev, dtype=torch.float32)
         elif out_layout == "bdhwc":
             store = torch.empty((B, D, H, W, OC), device=dev, dtype=torch.float32)
+        elif out_layout == "bdhwc_bf16":
+            store = torch.empty((B, D, H, W, OC), device=dev, dtype=torch.bfloat16)
         else:
             store = torch.empty((B, OC, D, H, W), device=dev, dtype=torch.float32)
         mode = UV_CHECK if _CHECK_UV else "off"
@@ -120,6 +122,9 @@ class _SweepFn(torch.autograd.Function):
         lib = _lib.load()
         B, S, H, W, C = images.shape
         groups, out_layout, D = meta["groups"], meta["out_layout"], meta["D"]
+        if out_layout == "bdhwc_bf16":
+            raise RuntimeError("the bf16 channels-last cost volume feeds the inference-only tensor-core regulariser; use an fp32 layout "
+                               "for training")
         g = grad_store.float()
         if groups > 0:                                             # (B,G,D,H,W): mean over C/G channels
             cpg = C // groups
@@ -185,7 +190,8 @@ def calculate_cost_volume_erp(args, images, depths, trans, rots, depth_volume=No
 
     `ref_gmms`, `nghbr_gmms`, `thres`, `direction` are accepted and ignored exactly like the
     reference.  Extensions (keyword-only in spirit): `out_layout` picks the physical layout
-    ("bdchw" = the reference's strides, "bdhwc" channels-last, "bcdhw" the regulariser's), and
+    ("bdchw" = the reference's strides, "bdhwc" channels-last, "bcdhw" the regulariser's, "bdhwc_bf16" = channels-last
+    bf16, the operand layout of `regulariser.CostRegulariser3D`, which then consumes `cv.permute(0, 4, 1, 2, 3)` in place), and
     `groups>0` fuses the group-wise mean of pipeline3_model.py:849-853, returning (B,G,D,H,W).
     """
     if groups > 0:

@@ -315,3 +315,28 @@ def test_planar_tma_store_path_is_bit_identical(layout, mv):
             lib.pgrf_debug_set(b"cv_tma", 0)
     assert torch.equal(outs[1], outs[0])
     assert float(outs[1].abs().sum()) > 0
+
+
+def test_bf16_channels_last_layout_and_regulariser_pipeline():
+    """out_layout="bdhwc_bf16": the sweep stores exactly bf16(round-to-nearest) of its fp32 channels-last result, and the tensor-core
+    regulariser consumes that storage in place with the same result as the fp32 volume + its own conversion pass."""
+    import panogrf_b200 as pg
+    from panogrf_b200 import regulariser as reg
+    torch.manual_seed(3)
+    B, H, W, C, D = 1, 16, 32, 16, 8
+    images = torch.randn(B, 2, H, W, C, device="cuda")
+    rots = torch.eye(3, device="cuda").expand(B, 2, 3, 3).contiguous()
+    trans = torch.zeros(B, 2, 3, device="cuda")
+    trans[:, 0, 0] = 0.3
+    depths = torch.linspace(0.6, 9.0, D, device="cuda")
+    args = {"dataset_name": "m3d", "contain_dnet": False, "mono_uncertainty": False}
+    cv32 = pg.calculate_cost_volume_erp(args, images, depths, trans, rots, out_layout="bdhwc")
+    cv16 = pg.calculate_cost_volume_erp(args, images, depths, trans, rots, out_layout="bdhwc_bf16")
+    assert cv16.dtype == torch.bfloat16 and cv16.shape == cv32.shape and cv16.is_contiguous()
+    assert torch.equal(cv16, cv32.to(torch.bfloat16))
+    net = reg.CostRegulariser3D(3).cuda()                      # 2^(3+1) = 16 input channels
+    y32 = net(cv32.permute(0, 4, 1, 2, 3))                     # fp32 view -> conversion kernel -> convolutions
+    y16 = net(cv16.permute(0, 4, 1, 2, 3))                     # bf16 storage consumed in place
+    assert torch.equal(y16, y32)
+    with pytest.raises(Exception):
+        pg.calculate_cost_volume_erp(args, images[..., :8].contiguous(), depths, trans, rots, out_layout="bdhwc_bf16")   # C % 16
