@@ -357,6 +357,7 @@ def main():
     ref_d = {k: v.to(dev) for k, v in ref.items()}
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     full = torch.empty(N_RAYS, 4, device=dev) if world > 1 else None
+    sync_token = torch.zeros(1, device=dev)
 
     def step(ref_maps=ref_d):
         out = net.render(que_d, ref_maps, False)
@@ -375,6 +376,10 @@ def main():
         times = []
         for _ in range(steps):
             flush.zero_()                                        # L2 flush between timed iterations
+            if world > 1:
+                # device-side rendezvous: every rank's stream starts the step together, so the step's own collective does not
+                # absorb the host-side skew between the 8 python processes (it would be charged to the earliest rank)
+                dist.all_reduce(sync_token)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -590,7 +595,10 @@ def time_e2e(torch, dist, net, cfg, rank, world, dev, steps, full):
             one()
         dist.barrier()
         times = []
+        token = torch.zeros(1, device=dev)
         for _ in range(steps):
+            dist.all_reduce(token)                       # ranks start the step together (see `timed`)
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
             one()
             times.append(time.perf_counter() - t0)

@@ -333,6 +333,14 @@ PGRF_API int pgrf_conv3d_to_bf16_cl(const float* x, long long sb, long long sc, 
 PGRF_API int pgrf_conv3d_workspace(int Ca, int Cb, int Cout, int B, int D, int H, int W, long long* ws_floats);
 PGRF_API int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
                              int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, void* stream);
+/* A 3x3x3 convolution with ONE output channel over many input channels (the 128 -> 1 head of the last decoder) in two steps that read
+ * every voxel's channels once instead of once per tap row: pgrf_conv3d_pointwise_fwd = 1x1x1 convolution through the tensor-core
+ * pipeline (only the centre tap of the packed weights is walked; here with the 27 taps as output channels, fp32 planar
+ * (B,27,D,H,W) output), then pgrf_conv3d_tapsum_fwd = out[v] = act(bias + sum_tap z[tap][neighbour(v, tap)]) (zeros along D / H,
+ * wrap along W). */
+PGRF_API int pgrf_conv3d_pointwise_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y,
+                                       float* yf, int cout_real, int Cout, int B, int D, int H, int W, int act, void* stream);
+PGRF_API int pgrf_conv3d_tapsum_fwd(const float* z, float bias, int B, int D, int H, int W, int act, float* out, void* stream);
 PGRF_API int pgrf_conv3d_cout1_fwd(const void* xa, int Ca, const void* xb, int Cb, const float* xf, const float* w, float bias, int B,
                                    int D, int H, int W, int act, float* out, void* stream);
 PGRF_API int pgrf_avgpool3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream);

@@ -41,6 +41,8 @@ struct ConvParams {
   long long n_vox;
   int splits;                          // split-K over the 9 (kd, kh) tap rows: blockIdx.z accumulates 9/splits of them into
   float* ws;                           // fp32 partial sums [splits][n_vox][Cout] (bias / activation applied by the reduction)
+  int tap_lo, tap_cnt;                 // taps walked by the per-tap variant (= 3 * the tap rows below, or the centre tap alone for a
+                                       // pointwise / 1x1x1 convolution)
   int krow_lo, krow_cnt;               // (kd, kh) tap rows walked: all 9, or rows 3..5 when D == 1 (a 2-D convolution: the kd != 1
                                        // taps only ever see the zero padding)
 };
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_kernel(const ConvPa
   umma::fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const int nt = blockIdx.y;
-  const int n_taps = p.krow_cnt * 3 / p.splits, tap0 = p.krow_lo * 3 + blockIdx.z * n_taps;       // this CTA's share of the taps
+  const int n_taps = p.tap_cnt / p.splits, tap0 = p.tap_lo + blockIdx.z * n_taps;       // this CTA's share of the taps
 
   if (warp == 8) {
     if (r == kGatherThreads)
@@ -354,6 +356,40 @@ __global__ void __launch_bounds__(256) conv3d_reduce_kernel(const ConvParams p) 
   }
 }
 
+// Single-output-channel 3x3x3 convolution over MANY input channels, second half.  The layer  out[v] = b + sum_tap sum_c w[tap][c]
+// x[nbr(v, tap)][c]  is evaluated as  z[tap][u] = sum_c w[tap][c] x[u][c]  (a pointwise GEMM with the 27 taps as output channels:
+// every voxel's channels are read ONCE instead of once per tap row) followed by this 27-tap stencil over the scalar planes:
+// out[v] = act(b + sum_tap z[tap][nbr(v, tap)]), zeros along depth / height, wrap along width (WrapPadding3D).  z is fp32 planar
+// (B, 27, D, H, W): a warp reads 128 contiguous bytes per tap.
+__global__ void __launch_bounds__(256) conv3d_tapsum_kernel(const float* __restrict__ z, float bias, int B, int D, int H, int W, int act,
+                                                            float* __restrict__ out) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W, DHW = HW * D;
+  if (v >= (long long)B * DHW) return;
+  long long t = v;
+  const int x = (int)(t % W); t /= W;
+  const int y = (int)(t % H); t /= H;
+  const int d = (int)(t % D);
+  const long long b = t / D;
+  const float* zb = z + b * 27 * DHW;
+  const int xm = x == 0 ? W - 1 : x - 1, xp = x == W - 1 ? 0 : x + 1;
+  float acc = bias;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd) {
+    const int dd = d + kd - 1;
+    if (dd < 0 || dd >= D) continue;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yy = y + kh - 1;
+      if (yy < 0 || yy >= H) continue;
+      const float* row = zb + (long long)(kd * 9 + kh * 3) * DHW + (long long)dd * HW + (long long)yy * W;
+      acc += __ldg(row + xm) + __ldg(row + DHW + x) + __ldg(row + 2 * DHW + xp);
+    }
+  }
+  if (act) acc = acc > 0.f ? acc : 0.01f * acc;
+  out[v] = acc;
+}
+
 // single output channel (last decoder): fp32 SIMT.  in: bf16 channels-last (two concatenated inputs) or fp32 single channel
 __global__ void __launch_bounds__(256) conv3d_cout1_kernel(const __nv_bfloat16* __restrict__ xa, int Ca, const __nv_bfloat16* __restrict__ xb,
                                                            int Cb, const float* __restrict__ xf, const float* __restrict__ w /* [27][Cin] */,
@@ -546,7 +582,7 @@ struct ConvPlan {
 };
 
 // tile / pipeline / split-K choice of one layer (shared by the launcher and the workspace query)
-static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, ConvPlan& pl) {
+static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, bool pointwise, ConvPlan& pl) {
   PGRF_REQUIRE(Ca >= 16 && Ca % 16 == 0 && Cb >= 0 && Cb % 16 == 0 && Cout >= 16 && Cout % 16 == 0, "conv3d: channel counts must be "
                "multiples of 16 (Ca=%d Cb=%d Cout=%d)", Ca, Cb, Cout);
   PGRF_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 2, "conv3d: bad volume %dx%dx%dx%d", B, D, H, W);
@@ -561,7 +597,7 @@ static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, Con
   const long long n_vox = (long long)B * D * H * W;
   pl.grid = dim3(blocks_for(n_vox, kConvRows), (unsigned)(Cout / pl.NT), 1);
   const long long n_cta = (long long)pl.grid.x * pl.grid.y;
-  pl.row = g_conv_row && W % kConvRows == 0;
+  pl.row = g_conv_row && W % kConvRows == 0 && !pointwise;
   const size_t stage = pl.row ? (size_t)(KC / 8) * kRowPitch + 3 * (size_t)KC * pl.NT * 2            // [130-row operand | three taps of weights]
                               : (size_t)(KC / 8) * (kConvRows * 16 + kConvPad) + (size_t)KC * pl.NT * 2;
   // split-K over the nine (kd, kh) tap rows when the (voxel tile x channel tile) grid cannot fill the GPU (2 CTAs per SM assumed)
@@ -572,6 +608,7 @@ static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, Con
   else if (n_cta < 444) pl.splits = n_cta * 3 >= 740 ? 3 : 9;
   PGRF_REQUIRE(pl.splits == 1 || pl.splits == 3 || pl.splits == 9, "conv3d: splits=%d (1, 3 or 9)", pl.splits);
   if (pl.splits > pl.krow_cnt) pl.splits = pl.krow_cnt;
+  if (pointwise) pl.splits = 1;
   // pipeline depth: as many stages as keep two CTAs on an SM (one CTA's epilogue hides behind the other's main loop), at least 2 / 3
   const int s_min = pl.row ? 2 : 3, s_max = pl.row ? 4 : 6;
   int S = (int)(((size_t)g_conv_smem_kb * 1024) / stage);
@@ -590,19 +627,20 @@ static int conv3d_plan(int Ca, int Cb, int Cout, int B, int D, int H, int W, Con
 extern "C" int pgrf_conv3d_workspace(int Ca, int Cb, int Cout, int B, int D, int H, int W, long long* ws_floats) {
   PGRF_REQUIRE(ws_floats, "conv3d_workspace: null pointer argument");
   ConvPlan pl;
-  const int rc = conv3d_plan(Ca, Cb, Cout, B, D, H, W, pl);
+  const int rc = conv3d_plan(Ca, Cb, Cout, B, D, H, W, false, pl);
   if (rc != PGRF_OK) return rc;
   *ws_floats = pl.ws_floats;
   return PGRF_OK;
 }
 
-extern "C" int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
-                               int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, void* stream) {
+static int conv3d_launch(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
+                         int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, bool pointwise,
+                         void* stream) {
   PGRF_REQUIRE(xa && wpk && bias && ((y != nullptr) != (yf != nullptr)), "conv3d: null pointer argument (exactly one of y / yf)");
   PGRF_REQUIRE(Cb == 0 || xb, "conv3d: Cb=%d without a second input", Cb);
   PGRF_REQUIRE(!yf || (cout_real >= 1 && cout_real <= Cout), "conv3d: cout_real=%d outside [1, %d]", cout_real, Cout);
   ConvPlan pl;
-  const int rc = conv3d_plan(Ca, Cb, Cout, B, D, H, W, pl);
+  const int rc = conv3d_plan(Ca, Cb, Cout, B, D, H, W, pointwise, pl);
   if (rc != PGRF_OK) return rc;
   PGRF_REQUIRE(pl.ws_floats == 0 || (ws && ws_floats >= pl.ws_floats), "conv3d: workspace of %lld floats needed (pgrf_conv3d_workspace), "
                "%lld given", pl.ws_floats, ws ? ws_floats : 0LL);
@@ -612,6 +650,8 @@ extern "C" int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, c
   p.B = B; p.D = D; p.H = H; p.W = W; p.act = act; p.KC = pl.KC; p.n_cc = pl.n_cc;
   p.n_vox = (long long)B * D * H * W;
   p.splits = pl.splits; p.ws = ws; p.krow_lo = pl.krow_lo; p.krow_cnt = pl.krow_cnt;
+  p.tap_lo = pointwise ? 13 : 3 * pl.krow_lo;          // 13 = (kd, kh, kw) = (1, 1, 1)
+  p.tap_cnt = pointwise ? 1 : 3 * pl.krow_cnt;
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid = pl.grid;
   const size_t smem = pl.smem;
@@ -646,6 +686,26 @@ extern "C" int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, c
     count_launch();
     PGRF_CUDA(cudaGetLastError());
   }
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
+                               int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, void* stream) {
+  return conv3d_launch(xa, Ca, xb, Cb, wpk, bias, y, yf, cout_real, Cout, B, D, H, W, act, ws, ws_floats, false, stream);
+}
+
+// Pointwise (1x1x1) convolution through the same pipeline: only the centre tap of the packed weights is walked.
+extern "C" int pgrf_conv3d_pointwise_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y,
+                                         float* yf, int cout_real, int Cout, int B, int D, int H, int W, int act, void* stream) {
+  return conv3d_launch(xa, Ca, xb, Cb, wpk, bias, y, yf, cout_real, Cout, B, D, H, W, act, nullptr, 0, true, stream);
+}
+
+extern "C" int pgrf_conv3d_tapsum_fwd(const float* z, float bias, int B, int D, int H, int W, int act, float* out, void* stream) {
+  PGRF_REQUIRE(z && out && B >= 1 && D >= 1 && H >= 1 && W >= 2, "conv3d_tapsum: bad arguments");
+  const long long n = (long long)B * D * H * W;
+  conv3d_tapsum_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, bias, B, D, H, W, act, out);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
 }
 

@@ -73,11 +73,12 @@ def conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels=0, ws_cache=None, lib=N
     _lib.check(lib.pgrf_conv3d_workspace(ca_pad, cb_pad, co_pad, B, D, H, W, ctypes.byref(need)), "pgrf_conv3d_workspace")
     ws = None
     if need.value:
-        ws = ws_cache.get(xa.device) if ws_cache is not None else None
+        key = (xa.device, getattr(st, "value", st))             # stream-ordered reuse: one buffer per (device, stream)
+        ws = ws_cache.get(key) if ws_cache is not None else None
         if ws is None or ws.numel() < need.value:
             ws = torch.empty(need.value, device=xa.device, dtype=torch.float32)
             if ws_cache is not None:
-                ws_cache[xa.device] = ws
+                ws_cache[key] = ws
     if f32_channels:
         y = torch.empty((B, f32_channels, D, H, W), device=xa.device, dtype=torch.float32)
     else:
@@ -121,6 +122,11 @@ class CostRegulariser3D(nn.Module):
             p.requires_grad_(False)
 
     # ---- weights ----------------------------------------------------------------------------------------------------------------
+    def invalidate_weight_cache(self):
+        """Drop the packed operands.  REQUIRED after writing parameters through `.data` (such writes do not bump the version counter
+        the cache key uses); optimizer steps, load_state_dict and .to()/.cuda() are detected automatically."""
+        self._packed.clear()
+
     def _pack(self, conv, ca, cb, ca_pad, cb_pad, simt=False):
         key = id(conv)
         ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), str(conv.weight.device), ca, cb, simt)
@@ -132,6 +138,19 @@ class CostRegulariser3D(nn.Module):
                 hit = (ver,) + pack_conv(conv.weight, conv.bias, ca, cb, ca_pad, cb_pad)
             self._packed[key] = hit
         return hit[1], hit[2]
+
+    def _pack_head(self, conv, ca, cb, ca_pad, cb_pad):
+        """(1, ca+cb, 3,3,3) head -> pointwise weights with the 27 taps as output channels (centre tap of a (32, ca+cb, 3,3,3) kernel)"""
+        ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), str(conv.weight.device), ca, cb, "head")
+        hit = self._packed.get(id(conv))
+        if hit is None or hit[0] != ver:
+            w = conv.weight.detach().float()
+            wz = torch.zeros((32, ca + cb, 3, 3, 3), device=w.device, dtype=torch.float32)
+            wz[:27, :, 1, 1, 1] = w[0].reshape(ca + cb, 27).t()
+            wpk, bz = pack_conv(wz, torch.zeros(32, device=w.device), ca, cb, ca_pad, cb_pad)
+            hit = (ver, wpk, bz, float(conv.bias.detach().float().item()))
+            self._packed[id(conv)] = hit
+        return hit[1], hit[2], hit[3]
 
     # ---- kernels ----------------------------------------------------------------------------------------------------------------
     def _conv(self, lib, st, xa, ca_pad, xb, cb_pad, wpk, bias, co_pad, dims, f32_channels=0):
@@ -205,10 +224,17 @@ class CostRegulariser3D(nn.Module):
                 if blk.conv1.weight.shape[0] > 1:
                     a, ch = self._block(lib, st, blk, up, ch, xb, cb, dims)
                     continue
-                # last decoder: (ch + cb) -> 1 on the tensor cores (one 16-channel tile, fp32 output), then 1 -> 1 on the fp32 pipes
+                # last decoder, conv1: (ch + cb) -> 1.  Evaluated as a pointwise GEMM with the 27 taps as output channels (every voxel's
+                # channels are read once, not once per tap row) + a 27-tap stencil over the fp32 scalar planes; then 1 -> 1 on the
+                # fp32 pipes
                 ca_pad, cb_pad = up.shape[-1], (xb.shape[-1] if xb is not None else 0)
-                w1, b1 = self._pack(blk.conv1, ch, cb, ca_pad, cb_pad)
-                t = self._conv(lib, st, up, ca_pad, xb, cb_pad, w1, b1, 16, dims, f32_channels=1)
+                wz, bz, b1 = self._pack_head(blk.conv1, ch, cb, ca_pad, cb_pad)
+                z = torch.empty((dims[0], 27) + tuple(dims[1:]), device=dev, dtype=torch.float32)
+                _lib.check(lib.pgrf_conv3d_pointwise_fwd(_lib.ptr(up), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad,
+                                                         _lib.ptr(wz), _lib.ptr(bz), None, _lib.ptr(z), 27, 32, *dims, 0, st),
+                           "pgrf_conv3d_pointwise_fwd")
+                t = torch.empty(dims, device=dev, dtype=torch.float32)
+                _lib.check(lib.pgrf_conv3d_tapsum_fwd(_lib.ptr(z), b1, *dims, 1, _lib.ptr(t), st), "pgrf_conv3d_tapsum_fwd")
                 w2, b2 = self._pack(blk.conv2, 1, 0, 1, 0, simt=True)
                 out = torch.empty(dims, device=dev, dtype=torch.float32)
                 _lib.check(lib.pgrf_conv3d_cout1_fwd(None, 0, None, 0, _lib.ptr(t), _lib.ptr(w2), b2, *dims, 1, _lib.ptr(out), st),
