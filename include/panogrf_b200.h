@@ -341,6 +341,9 @@ PGRF_API int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, con
 PGRF_API int pgrf_conv3d_pointwise_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y,
                                        float* yf, int cout_real, int Cout, int B, int D, int H, int W, int act, void* stream);
 PGRF_API int pgrf_conv3d_tapsum_fwd(const float* z, float bias, int B, int D, int H, int W, int act, float* out, void* stream);
+/* 1 -> 1 channel 3x3x3 convolution of an fp32 scalar volume (B,D,H,W); w27_host = the 27 taps (kd, kh, kw order) in HOST memory. */
+PGRF_API int pgrf_conv3d_scalar_fwd(const float* x, const float* w27_host, float bias, int B, int D, int H, int W, int act, float* out,
+                                    void* stream);
 PGRF_API int pgrf_conv3d_cout1_fwd(const void* xa, int Ca, const void* xb, int Cb, const float* xf, const float* w, float bias, int B,
                                    int D, int H, int W, int act, float* out, void* stream);
 PGRF_API int pgrf_avgpool3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream);

@@ -163,6 +163,7 @@ SIGNATURES.update({
     "pgrf_conv3d_fwd": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, ctypes.c_longlong, _P]),
     "pgrf_conv3d_pointwise_fwd": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pgrf_conv3d_tapsum_fwd": (_I, [_P, _F, _I, _I, _I, _I, _I, _P, _P]),
+    "pgrf_conv3d_scalar_fwd": (_I, [_P, _P, _F, _I, _I, _I, _I, _I, _P, _P]),
     "pgrf_conv3d_cout1_fwd": (_I, [_P, _I, _P, _I, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P]),
     "pgrf_avgpool3d2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "pgrf_upsample3d2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),

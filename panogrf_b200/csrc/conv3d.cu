@@ -363,10 +363,10 @@ __global__ void __launch_bounds__(256) conv3d_reduce_kernel(const ConvParams p) 
 // (B, 27, D, H, W): a warp reads 128 contiguous bytes per tap.
 __global__ void __launch_bounds__(256) conv3d_tapsum_kernel(const float* __restrict__ z, float bias, int B, int D, int H, int W, int act,
                                                             float* __restrict__ out) {
-  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
   const long long HW = (long long)H * W, DHW = HW * D;
-  if (v >= (long long)B * DHW) return;
-  long long t = v;
+  if (v >= (unsigned)B * (unsigned)DHW) return;
+  unsigned t = v;
   const int x = (int)(t % W); t /= W;
   const int y = (int)(t % H); t /= H;
   const int d = (int)(t % D);
@@ -384,6 +384,39 @@ __global__ void __launch_bounds__(256) conv3d_tapsum_kernel(const float* __restr
       if (yy < 0 || yy >= H) continue;
       const float* row = zb + (long long)(kd * 9 + kh * 3) * DHW + (long long)dd * HW + (long long)yy * W;
       acc += __ldg(row + xm) + __ldg(row + DHW + x) + __ldg(row + 2 * DHW + xp);
+    }
+  }
+  if (act) acc = acc > 0.f ? acc : 0.01f * acc;
+  out[v] = acc;
+}
+
+// 1 -> 1 channel 3x3x3 convolution on an fp32 scalar volume (conv2 of the last decoder): 27-tap weighted stencil, thread = voxel
+struct Taps27 { float w[27]; };
+__global__ void __launch_bounds__(256) conv3d_scalar_kernel(const float* __restrict__ xin, const Taps27 taps, float bias, int B, int D, int H,
+                                                            int W, int act, float* __restrict__ out) {
+  const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W, DHW = HW * D;
+  if (v >= (unsigned)B * (unsigned)DHW) return;
+  unsigned t = v;
+  const int x = (int)(t % W); t /= W;
+  const int y = (int)(t % H); t /= H;
+  const int d = (int)(t % D);
+  const float* xb = xin + (t / D) * DHW;
+  const int xm = x == 0 ? W - 1 : x - 1, xp = x == W - 1 ? 0 : x + 1;
+  float acc = bias;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd) {
+    const int dd = d + kd - 1;
+    if (dd < 0 || dd >= D) continue;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yy = y + kh - 1;
+      if (yy < 0 || yy >= H) continue;
+      const float* row = xb + (long long)dd * HW + (long long)yy * W;
+      const float* w = taps.w + kd * 9 + kh * 3;
+      acc = fmaf(w[0], __ldg(row + xm), acc);
+      acc = fmaf(w[1], __ldg(row + x), acc);
+      acc = fmaf(w[2], __ldg(row + xp), acc);
     }
   }
   if (act) acc = acc > 0.f ? acc : 0.01f * acc;
@@ -436,15 +469,16 @@ __global__ void __launch_bounds__(256) conv3d_cout1_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) avgpool3d2_kernel(const __nv_bfloat16* __restrict__ x, int B, int D, int H, int W, int C,
                                                          __nv_bfloat16* __restrict__ y) {
   const int Do = D / 2, Ho = H / 2, Wo = W / 2, C8 = C / 8;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * Do * Ho * Wo * C8) return;
-  long long t = i;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)B * Do * Ho * Wo * C8) return;
+  unsigned t = i;
   const int c8 = (int)(t % C8); t /= C8;
   const int xo = (int)(t % Wo); t /= Wo;
   const int yo = (int)(t % Ho); t /= Ho;
   const int dO = (int)(t % Do);
   const int b = (int)(t / Do);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int dd = 2 * dO + (k >> 2), yy = 2 * yo + ((k >> 1) & 1), xx = 2 * xo + (k & 1);
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + ((((size_t)b * D + dd) * H + yy) * W + xx) * C) + c8);
@@ -455,7 +489,7 @@ __global__ void __launch_bounds__(256) avgpool3d2_kernel(const __nv_bfloat16* __
   uint4 o;
   o.x = umma::pack2(acc[0] * 0.125f, acc[1] * 0.125f); o.y = umma::pack2(acc[2] * 0.125f, acc[3] * 0.125f);
   o.z = umma::pack2(acc[4] * 0.125f, acc[5] * 0.125f); o.w = umma::pack2(acc[6] * 0.125f, acc[7] * 0.125f);
-  reinterpret_cast<uint4*>(y + i / C8 * C)[c8] = o;
+  reinterpret_cast<uint4*>(y + (size_t)(i / C8) * C)[c8] = o;
 }
 
 // x2 trilinear upsampling, align_corners=False (ATen area_pixel_compute_source_index): thread = (output voxel, 8-channel chunk)
@@ -469,9 +503,9 @@ __device__ __forceinline__ void up_src(int o, int n, int& i0, int& i1, float& l)
 __global__ void __launch_bounds__(256) upsample3d2_kernel(const __nv_bfloat16* __restrict__ x, int B, int D, int H, int W, int C,
                                                           int scale_d, __nv_bfloat16* __restrict__ y) {
   const int Do = scale_d * D, Ho = 2 * H, Wo = 2 * W, C8 = C / 8;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * Do * Ho * Wo * C8) return;
-  long long t = i;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;          // 32-bit index math (the launcher checks the range): the
+  if (i >= (unsigned)B * Do * Ho * Wo * C8) return;                 // 64-bit divisions were most of this kernel's instructions
+  unsigned t = i;
   const int c8 = (int)(t % C8); t /= C8;
   const int xo = (int)(t % Wo); t /= Wo;
   const int yo = (int)(t % Ho); t /= Ho;
@@ -482,17 +516,22 @@ __global__ void __launch_bounds__(256) upsample3d2_kernel(const __nv_bfloat16* _
   if (scale_d == 2) up_src(dO, D, d0, d1, ld); else { d0 = d1 = dO; ld = 0.f; }      // scale_d == 1: bilinear (2-D feature maps)
   up_src(yo, H, y0, y1, ly); up_src(xo, W, x0, x1, lx);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint4 q[8];                                                        // all eight corner loads in flight before the first use
+#pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int dd = (k & 4) ? d1 : d0, yy = (k & 2) ? y1 : y0, xx = (k & 1) ? x1 : x0;
+    q[k] = __ldg(reinterpret_cast<const uint4*>(x + ((((size_t)b * D + dd) * H + yy) * W + xx) * C) + c8);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
     const float wgt = ((k & 4) ? ld : 1.f - ld) * ((k & 2) ? ly : 1.f - ly) * ((k & 1) ? lx : 1.f - lx);
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + ((((size_t)b * D + dd) * H + yy) * W + xx) * C) + c8);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q[k]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] = fmaf(wgt, f.x, acc[2 * j]); acc[2 * j + 1] = fmaf(wgt, f.y, acc[2 * j + 1]); }
   }
   uint4 o;
   o.x = umma::pack2(acc[0], acc[1]); o.y = umma::pack2(acc[2], acc[3]); o.z = umma::pack2(acc[4], acc[5]); o.w = umma::pack2(acc[6], acc[7]);
-  reinterpret_cast<uint4*>(y + i / C8 * C)[c8] = o;
+  reinterpret_cast<uint4*>(y + (size_t)(i / C8) * C)[c8] = o;
 }
 
 // fp32 (B,C,D,H,W) with arbitrary element strides -> bf16 channels-last (B,D,H,W,Cpad), zero padded channels
@@ -500,9 +539,9 @@ __global__ void __launch_bounds__(256) to_bf16_cl_kernel(const float* __restrict
                                                          long long sw, int B, int C, int D, int H, int W, int Cpad,
                                                          __nv_bfloat16* __restrict__ y) {
   const int C8 = Cpad / 8;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * D * H * W * C8) return;
-  long long t = i;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)B * D * H * W * C8) return;
+  unsigned t = i;
   const int c8 = (int)(t % C8); t /= C8;
   const int xx = (int)(t % W); t /= W;
   const int yy = (int)(t % H); t /= H;
@@ -514,7 +553,7 @@ __global__ void __launch_bounds__(256) to_bf16_cl_kernel(const float* __restrict
   for (int k = 0; k < 8; ++k) { const int c = 8 * c8 + k; v[k] = c < C ? __ldg(src + c * sc) : 0.f; }
   uint4 o;
   o.x = umma::pack2(v[0], v[1]); o.y = umma::pack2(v[2], v[3]); o.z = umma::pack2(v[4], v[5]); o.w = umma::pack2(v[6], v[7]);
-  reinterpret_cast<uint4*>(y + i / C8 * Cpad)[c8] = o;
+  reinterpret_cast<uint4*>(y + (size_t)(i / C8) * Cpad)[c8] = o;
 }
 
 // decoders1 of the MVS head (models/test_models.py:147-158, pipeline3_model.py:866-879): 1x1 convolution over the depth axis of the
@@ -563,11 +602,14 @@ int g_conv_splits = 0;   // split-K factor (pgrf_debug_set "conv_splits": 0 = au
 }
 
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+// the element-wise kernels decode their thread index with 32-bit arithmetic
+#define PGRF_REQUIRE_32BIT(n, what) PGRF_REQUIRE((n) < 4294967040LL, what ": %lld work items exceed the 32-bit index range", (long long)(n))
 
 extern "C" int pgrf_conv3d_to_bf16_cl(const float* x, long long sb, long long sc, long long sd, long long sh, long long sw, int B, int C,
                                       int D, int H, int W, int Cpad, void* y, void* stream) {
   PGRF_REQUIRE(x && y && B >= 1 && C >= 1 && Cpad >= C && Cpad % 8 == 0, "conv3d_to_bf16_cl: bad arguments");
   const long long n = (long long)B * D * H * W * (Cpad / 8);
+  PGRF_REQUIRE_32BIT(n, "conv3d_to_bf16_cl");
   to_bf16_cl_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, sb, sc, sd, sh, sw, B, C, D, H, W, Cpad, (__nv_bfloat16*)y);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
@@ -703,7 +745,21 @@ extern "C" int pgrf_conv3d_pointwise_fwd(const void* xa, int Ca, const void* xb,
 extern "C" int pgrf_conv3d_tapsum_fwd(const float* z, float bias, int B, int D, int H, int W, int act, float* out, void* stream) {
   PGRF_REQUIRE(z && out && B >= 1 && D >= 1 && H >= 1 && W >= 2, "conv3d_tapsum: bad arguments");
   const long long n = (long long)B * D * H * W;
+  PGRF_REQUIRE_32BIT(n, "conv3d_tapsum");
   conv3d_tapsum_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, bias, B, D, H, W, act, out);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_conv3d_scalar_fwd(const float* x, const float* w27_host, float bias, int B, int D, int H, int W, int act, float* out,
+                                      void* stream) {
+  PGRF_REQUIRE(x && w27_host && out && B >= 1 && D >= 1 && H >= 1 && W >= 2, "conv3d_scalar: bad arguments");
+  Taps27 taps;
+  for (int i = 0; i < 27; ++i) taps.w[i] = w27_host[i];
+  const long long n = (long long)B * D * H * W;
+  PGRF_REQUIRE_32BIT(n, "conv3d_scalar");
+  conv3d_scalar_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, taps, bias, B, D, H, W, act, out);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
@@ -723,6 +779,7 @@ extern "C" int pgrf_conv3d_cout1_fwd(const void* xa, int Ca, const void* xb, int
 extern "C" int pgrf_avgpool3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream) {
   PGRF_REQUIRE(x && y && D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "avgpool3d: sizes must be even, C %% 8 == 0");
   const long long n = (long long)B * (D / 2) * (H / 2) * (W / 2) * (C / 8);
+  PGRF_REQUIRE_32BIT(n, "avgpool3d");
   avgpool3d2_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, D, H, W, C, (__nv_bfloat16*)y);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
@@ -732,6 +789,7 @@ extern "C" int pgrf_avgpool3d2_fwd(const void* x, int B, int D, int H, int W, in
 extern "C" int pgrf_upsample2d2_fwd(const void* x, int B, int H, int W, int C, void* y, void* stream) {
   PGRF_REQUIRE(x && y && C % 8 == 0, "upsample2d: C %% 8 == 0");
   const long long n = (long long)B * (2 * H) * (2 * W) * (C / 8);
+  PGRF_REQUIRE_32BIT(n, "upsample2d");
   upsample3d2_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, 1, H, W, C, 1, (__nv_bfloat16*)y);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
@@ -752,6 +810,7 @@ extern "C" int pgrf_channel_dot_upsample_fwd(const float* x, long long sb, long 
 extern "C" int pgrf_upsample3d2_fwd(const void* x, int B, int D, int H, int W, int C, void* y, void* stream) {
   PGRF_REQUIRE(x && y && C % 8 == 0, "upsample3d: C %% 8 == 0");
   const long long n = (long long)B * (2 * D) * (2 * H) * (2 * W) * (C / 8);
+  PGRF_REQUIRE_32BIT(n, "upsample3d");
   upsample3d2_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, D, H, W, C, 2, (__nv_bfloat16*)y);
   count_launch();
   PGRF_CUDA(cudaGetLastError());

@@ -139,6 +139,16 @@ class CostRegulariser3D(nn.Module):
             self._packed[key] = hit
         return hit[1], hit[2]
 
+    def _pack_scalar(self, conv):
+        """(1, 1, 3,3,3) -> 27 host floats (passed by value to the stencil kernel) + bias"""
+        ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), str(conv.weight.device), "scalar")
+        hit = self._packed.get(id(conv))
+        if hit is None or hit[0] != ver:
+            w = (ctypes.c_float * 27)(*conv.weight.detach().float().reshape(-1).cpu().tolist())
+            hit = (ver, w, float(conv.bias.detach().float().item()))
+            self._packed[id(conv)] = hit
+        return hit[1], hit[2]
+
     def _pack_head(self, conv, ca, cb, ca_pad, cb_pad):
         """(1, ca+cb, 3,3,3) head -> pointwise weights with the 27 taps as output channels (centre tap of a (32, ca+cb, 3,3,3) kernel)"""
         ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), str(conv.weight.device), ca, cb, "head")
@@ -235,10 +245,9 @@ class CostRegulariser3D(nn.Module):
                            "pgrf_conv3d_pointwise_fwd")
                 t = torch.empty(dims, device=dev, dtype=torch.float32)
                 _lib.check(lib.pgrf_conv3d_tapsum_fwd(_lib.ptr(z), b1, *dims, 1, _lib.ptr(t), st), "pgrf_conv3d_tapsum_fwd")
-                w2, b2 = self._pack(blk.conv2, 1, 0, 1, 0, simt=True)
+                w2, b2 = self._pack_scalar(blk.conv2)
                 out = torch.empty(dims, device=dev, dtype=torch.float32)
-                _lib.check(lib.pgrf_conv3d_cout1_fwd(None, 0, None, 0, _lib.ptr(t), _lib.ptr(w2), b2, *dims, 1, _lib.ptr(out), st),
-                           "pgrf_conv3d_cout1_fwd")
+                _lib.check(lib.pgrf_conv3d_scalar_fwd(_lib.ptr(t), w2, b2, *dims, 1, _lib.ptr(out), st), "pgrf_conv3d_scalar_fwd")
                 return out.unsqueeze(1)
         raise RuntimeError("unet3d: the first decoder must have one output channel (models/test_models.py:113)")
 
