@@ -55,26 +55,29 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Epilogue of both variants, 8 warps: warp w reads TMEM lanes 32 (w % 4).. (its quadrant) and the column half w / 4 of the tile.
 // + bias, LeakyReLU; bf16 16-byte channel runs, fp32 planar for the first cout_real channels, or raw split-K partial sums.
-template <int NT>
-__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tb, int nt, int warp, int lane) {
-  constexpr int kHalf = NT >= 32 ? NT / 2 : NT;
-  const int q = warp & 3, h = warp >> 2;
-  if (NT < 32 && h) return;
-  const long long v = (long long)blockIdx.x * kConvRows + q * 32 + lane;
+// `cols` columns starting at column `c0` of the tile's accumulator (TMEM address `tacc`), lane quadrant q, voxel tile vt, split z
+template <int NT, int COLS>
+__device__ __forceinline__ void conv_epilogue_cols(const ConvParams& p, uint32_t tacc, int vt, int nt, int z, int q, int lane, int c0) {
+  const long long v = (long long)vt * kConvRows + q * 32 + lane;
   const bool row_ok = v < p.n_vox;
-  const uint32_t tq = tb + ((uint32_t)(q * 32) << 16) + h * kHalf;
-  const int cbase = nt * NT + h * kHalf;
+  const uint32_t tq = tacc + ((uint32_t)(q * 32) << 16) + c0;
+  const int cbase = nt * NT + c0;
   const float* bias = p.bias + cbase;
   const long long DHW = (long long)p.D * p.H * p.W;
+  constexpr int kHalf = COLS;
 #pragma unroll
   for (int c = 0; c < kHalf; c += 16) {
     float a[16];
     umma::ld16(tq + c, a);                                            // warp-collective: only the stores are predicated
     if (p.splits > 1) {                                               // raw partial sums; conv3d_reduce_kernel finishes the layer
       if (row_ok) {
-        float4* dst = reinterpret_cast<float4*>(p.ws + ((size_t)blockIdx.z * p.n_vox + v) * p.Cout + cbase + c);
+        float4* dst = reinterpret_cast<float4*>(p.ws + ((size_t)z * p.n_vox + v) * p.Cout + cbase + c);
 #pragma unroll
         for (int i = 0; i < 4; ++i) dst[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
       }
@@ -97,6 +100,14 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tb, 
       reinterpret_cast<uint4*>(dst)[1] = make_uint4(umma::pack2(a[8], a[9]), umma::pack2(a[10], a[11]), umma::pack2(a[12], a[13]), umma::pack2(a[14], a[15]));
     }
   }
+}
+
+template <int NT>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tb, int nt, int warp, int lane) {
+  constexpr int kHalf = NT >= 32 ? NT / 2 : NT;
+  const int q = warp & 3, h = warp >> 2;
+  if (NT < 32 && h) return;
+  conv_epilogue_cols<NT, kHalf>(p, tb, blockIdx.x, nt, blockIdx.z, q, lane, h * kHalf);
 }
 
 // The MMA warp's loop, shared by both variants: one thread waits for a full stage, issues TAPS x KC/16 MMAs, commits to `free`.
@@ -319,6 +330,187 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_row_kernel(const Co
     mbar_wait(&bar_done, 0);
     umma::fence_after_sync();
     conv_epilogue<NT>(p, tb, nt, warp, r & 31);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) umma::tmem_dealloc(tb, kCols);
+}
+
+// ---- persistent variant ---------------------------------------------------------------------------------------------------------
+// One CTA per SM slot walks work items (voxel tile, channel tile, split).  13 warps: 0-7 gather (the stage ring runs on across work
+// items, so the copies of the next tile are in flight while the current one drains), 8 issues the MMAs into one of TWO accumulators
+// in tensor memory, 9-12 are the epilogue of the other accumulator: the pipeline never drains between tiles.
+constexpr int kPersistThreads = 416;
+
+template <int NT, int S, bool ROW>
+__global__ void __launch_bounds__(kPersistThreads) conv3d_persist_kernel(const ConvParams p, int n_vt) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar_full[S], bar_free[S], acc_full[2], acc_empty[2];
+  constexpr int TAPS = ROW ? 3 : 1;
+  const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
+  const uint32_t a_pitch = ROW ? kRowPitch : kConvRows * 16 + kConvPad;
+  const int kch = p.KC >> 3;
+  const int a_bytes = kch * a_pitch, b_bytes = p.KC * NT * 2;
+  unsigned char* As = smem;
+  unsigned char* Bs = smem + S * a_bytes;
+  constexpr uint32_t kCols = 2 * NT < 32 ? 32 : 2 * NT;
+  if (warp == 8) umma::tmem_alloc(&tmem_base_s, kCols);
+  if (r == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], kGatherThreads + 1); mbar_init(&bar_free[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = tmem_base_s;
+  const int n_nt = p.Cout / NT;
+  const int total = n_vt * n_nt * p.splits;
+  const int units = (ROW ? p.krow_cnt : p.tap_cnt) / p.splits;          // tap rows (ROW) or taps per work item
+  const int n_st = units * p.n_cc;                                      // pipeline stages per work item
+
+  if (warp < 8) {
+    // ================= gather warps =================
+    const int lanes_shift = kch == 8 ? 3 : (kch == 4 ? 2 : 1);
+    const int my_chunk = r & (kch - 1), row0 = r >> lanes_shift, row_step = kGatherThreads >> lanes_shift, n_rows = kch >> 1;
+    const long long HW = (long long)p.H * p.W;
+    const uint32_t dst_step = row_step * 16;
+    const uint32_t adst0 = smem_u32(As) + my_chunk * a_pitch + (row0 + (ROW ? 1 : 0)) * 16;
+    const bool halo = ROW && r < 2 * kch;
+    const int hc = r < kch ? r : r - kch;
+    const uint32_t hdst0 = smem_u32(As) + hc * a_pitch + (r < kch ? 0 : kRowA - 1) * 16;
+    const size_t wtap = (size_t)p.n_cc * b_bytes;                       // distance between the weight blocks of two taps
+    int s = 0;
+    uint32_t ph = 1, adst = adst0, hdst = hdst0;
+#pragma unroll 1
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int vt = w % n_vt, rest = w / n_vt, nt = rest % n_nt, z = rest / n_nt;
+      const long long v0 = (long long)vt * kConvRows;
+      const unsigned char* wt = p.wpk + ((size_t)nt * 27 + (ROW ? (p.krow_lo + z * units) * 3 : p.tap_lo + z * units)) * wtap;
+      // per-tile coordinates: ROW -> (x0, y, d) of the run; per-tap -> validity / wrap bits of this thread's rows
+      int x0 = 0, ty = 0, td = 0;
+      uint32_t rowinfo[4] = {0u, 0u, 0u, 0u};
+      long long halo_off = 0;
+      if (ROW) {
+        long long t = v0;
+        x0 = (int)(t % p.W); t /= p.W;
+        ty = (int)(t % p.H); t /= p.H;
+        td = (int)(t % p.D);
+        halo_off = r < kch ? (x0 == 0 ? (long long)p.W - 1 : -1) : (x0 + kConvRows == p.W ? (long long)kConvRows - p.W : kConvRows);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long vv = v0 + row0 + i * row_step;
+          if (i < n_rows && vv < p.n_vox) {
+            long long t = vv;
+            const int x = (int)(t % p.W); t /= p.W;
+            const int y = (int)(t % p.H); t /= p.H;
+            const int d = (int)(t % p.D);
+            uint32_t m = 0;
+            for (int kd = 0; kd < 3; ++kd)
+              for (int kh = 0; kh < 3; ++kh)
+                if (d + kd - 1 >= 0 && d + kd - 1 < p.D && y + kh - 1 >= 0 && y + kh - 1 < p.H) m |= 1u << (kd * 3 + kh);
+            rowinfo[i] = m | (x == 0 ? 512u : 0u) | (x == p.W - 1 ? 1024u : 0u);
+          }
+        }
+      }
+#pragma unroll 1
+      for (int u = 0; u < units; ++u) {
+        // source rows of this tap row (ROW) / tap
+        long long nv[4], nvh = 0;
+        uint32_t nb[4];
+        if (ROW) {
+          const int krow = p.krow_lo + z * units + u;
+          const int dd = td + krow / 3 - 1, yy = ty + krow % 3 - 1;
+          const bool ok = dd >= 0 && dd < p.D && yy >= 0 && yy < p.H;
+          const long long nv0 = ok ? v0 + (long long)(krow / 3 - 1) * HW + (long long)(krow % 3 - 1) * p.W : 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { nb[i] = ok ? 16u : 0u; nv[i] = ok ? nv0 + row0 + i * row_step : 0; }
+          nvh = ok ? nv0 + halo_off : 0;
+        } else {
+          const int tap = p.tap_lo + z * units + u;
+          const int krow = tap / 3, kw = tap - krow * 3 - 1;
+          const long long tap_off = (long long)(krow / 3 - 1) * HW + (long long)(krow % 3 - 1) * p.W + kw;
+          const uint32_t wrap_bit = kw < 0 ? 512u : (kw > 0 ? 1024u : 0u);
+          const long long wrap_off = kw < 0 ? p.W : -p.W;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = (rowinfo[i] >> krow) & 1u;
+            nb[i] = ok ? 16u : 0u;
+            nv[i] = ok ? v0 + row0 + i * row_step + tap_off + ((rowinfo[i] & wrap_bit) ? wrap_off : 0) : 0;
+          }
+        }
+#pragma unroll 1
+        for (int inp = 0; inp < 2; ++inp) {                             // the two inputs of the concatenation
+          const int cs = inp ? p.Cb : p.Ca;
+          if (cs == 0) continue;
+          const __nv_bfloat16* base = inp ? p.xb : p.xa;
+          const __nv_bfloat16* rp[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rp[i] = base + (size_t)nv[i] * cs + my_chunk * 8;
+          const __nv_bfloat16* hp = base + (size_t)nvh * cs + hc * 8;
+#pragma unroll 1
+          for (int c = 0; c < cs; c += p.KC) {
+            mbar_wait(&bar_free[s], ph);                                // the MMAs that read this stage have completed
+            if (r == 0) {
+              mbar_expect_tx(&bar_full[s], TAPS * b_bytes);
+#pragma unroll
+              for (int kw = 0; kw < TAPS; ++kw) bulk_g2s(Bs + (s * TAPS + kw) * b_bytes, wt + kw * wtap, b_bytes, &bar_full[s]);
+            }
+            wt += b_bytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < n_rows) { cp_async16(adst + i * dst_step, rp[i], nb[i]); rp[i] += p.KC; }
+            if (halo) { cp_async16(hdst, hp, nb[0]); hp += p.KC; }
+            cp_async_arrive(&bar_full[s]);
+            adst += a_bytes;
+            hdst += a_bytes;
+            if (++s == S) { s = 0; ph ^= 1u; adst = adst0; hdst = hdst0; }
+          }
+        }
+        if (ROW) wt += 2 * wtap;                                        // next tap row: skip the two taps already consumed
+      }
+    }
+  } else if (warp == 8) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+#pragma unroll 1
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int ab = it & 1;
+        mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);                 // the epilogue has drained this accumulator
+        umma::fence_after_sync();
+        const uint32_t tacc = tb + ab * NT;
+#pragma unroll 1
+        for (int st = 0; st < n_st; ++st) {
+          mbar_wait(&bar_full[s], ph);
+          umma::fence_smem_to_async();
+          umma::fence_after_sync();
+#pragma unroll
+          for (int kw = 0; kw < TAPS; ++kw)
+            umma::gemm_issue(tacc, As + s * a_bytes + kw * 16, (int)(a_pitch >> 4), Bs + (s * TAPS + kw) * b_bytes, NT, NT, p.KC,
+                             st > 0 || kw > 0);
+          umma::commit(&bar_free[s]);
+          if (++s == S) { s = 0; ph ^= 1u; }
+        }
+        umma::commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    // ================= epilogue warps (TMEM lane quadrant = warp % 4) =================
+    const int q = warp & 3;
+    int it = 0;
+#pragma unroll 1
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int vt = w % n_vt, rest = w / n_vt, nt = rest % n_nt, z = rest / n_nt;
+      const int ab = it & 1;
+      mbar_wait(&acc_full[ab], (it >> 1) & 1);
+      umma::fence_after_sync();
+      conv_epilogue_cols<NT, NT>(p, tb + ab * NT, vt, nt, z, q, lane, 0);
+      umma::fence_before_sync();
+      mbar_arrive(&acc_empty[ab]);
+    }
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -598,6 +790,8 @@ int g_conv_stages = 0;   // pipeline depth of the conv3d kernels (pgrf_debug_set
 int g_conv_row = 1;      // use the row variant when W % 128 == 0 (pgrf_debug_set "conv_row")
 int g_conv_kc = 64;       // channels per pipeline stage (pgrf_debug_set "conv_kc": 64, 32 or 16)
 int g_conv_smem_kb = 56;  // shared-memory budget per CTA that sizes the pipeline (pgrf_debug_set "conv_smem_kb")
+int g_conv_persist = 1;      // persistent CTAs with double-buffered accumulators (pgrf_debug_set "conv_persist")
+int g_conv_persist_kb = 100; // their shared-memory budget per CTA (pgrf_debug_set "conv_persist_kb")
 int g_conv_splits = 0;   // split-K factor (pgrf_debug_set "conv_splits": 0 = automatic, else 1, 3 or 9)
 }
 
@@ -698,6 +892,34 @@ static int conv3d_launch(const void* xa, int Ca, const void* xb, int Cb, const v
   const dim3 grid = pl.grid;
   const size_t smem = pl.smem;
   const int S = pl.S;
+  if (g_conv_persist) {
+    // persistent CTAs: pipeline depth from the shared-memory budget (two CTAs per SM by default), grid = the SM slots
+    const size_t stage = pl.smem / pl.S;
+    int Sp = (int)(((size_t)g_conv_persist_kb * 1024) / stage);
+    Sp = Sp < 2 ? 2 : (Sp > 6 ? 6 : Sp);
+    if (Sp == 5) Sp = 4;
+    const size_t smem_p = Sp * stage;
+    PGRF_REQUIRE(smem_p <= 227 * 1024, "conv3d: %zu bytes of shared memory", smem_p);
+    int per_sm = (int)((227 * 1024) / (smem_p + 2048));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+    const int n_vt = (int)grid.x;
+    const long long total = (long long)grid.x * grid.y * grid.z;
+    const unsigned gp = (unsigned)(total < 148LL * per_sm ? total : 148LL * per_sm);
+#define PGRF_CONVP(N, SS, R)                                                                                                 \
+  {                                                                                                                          \
+    PGRF_CUDA(cudaFuncSetAttribute(conv3d_persist_kernel<N, SS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
+    conv3d_persist_kernel<N, SS, R><<<gp, kPersistThreads, smem_p, st>>>(p, n_vt);                                           \
+  }
+#define PGRF_CONVP_S(N, R)                                                                     \
+  case N:                                                                                      \
+    if (Sp == 2) PGRF_CONVP(N, 2, R) else if (Sp == 3) PGRF_CONVP(N, 3, R)                       \
+    else if (Sp == 4) PGRF_CONVP(N, 4, R) else PGRF_CONVP(N, 6, R)                               \
+    break;
+    if (pl.row) { switch (pl.NT) { PGRF_CONVP_S(16, true) PGRF_CONVP_S(32, true) PGRF_CONVP_S(64, true) PGRF_CONVP_S(128, true) } }
+    else { switch (pl.NT) { PGRF_CONVP_S(16, false) PGRF_CONVP_S(32, false) PGRF_CONVP_S(64, false) PGRF_CONVP_S(128, false) } }
+#undef PGRF_CONVP_S
+#undef PGRF_CONVP
+  } else {
 #define PGRF_CONV(K, N, SS)                                                                                \
   {                                                                                                        \
     PGRF_CUDA(cudaFuncSetAttribute(K<N, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
@@ -721,6 +943,7 @@ static int conv3d_launch(const void* xa, int Ca, const void* xb, int Cb, const v
 #undef PGRF_CONV_S
   }
 #undef PGRF_CONV
+  }
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   if (pl.splits > 1) {

@@ -454,7 +454,7 @@ static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
 
 using namespace pgrf;
 
-namespace pgrf { extern int g_mlp_wait_mode; extern int g_rays_tc; extern int g_pg_variant; extern int g_pg_grid; extern int g_conv_stages; extern int g_conv_row; extern int g_conv_splits; extern int g_conv_kc; extern int g_conv_smem_kb; }
+namespace pgrf { extern int g_mlp_wait_mode; extern int g_rays_tc; extern int g_pg_variant; extern int g_pg_grid; extern int g_conv_stages; extern int g_conv_row; extern int g_conv_splits; extern int g_conv_kc; extern int g_conv_smem_kb; extern int g_conv_persist; extern int g_conv_persist_kb; }
 extern "C" int pgrf_debug_set(const char* key, int value) {
   if (!strcmp(key, "mlp_wait_mode")) { pgrf::g_mlp_wait_mode = value; return PGRF_OK; }
   if (!strcmp(key, "rays_tc")) { pgrf::g_rays_tc = value; return PGRF_OK; }
@@ -463,6 +463,8 @@ extern "C" int pgrf_debug_set(const char* key, int value) {
   if (!strcmp(key, "conv_stages")) { pgrf::g_conv_stages = value <= 0 ? 0 : (value < 2 ? 2 : (value > 6 ? 6 : value)); return PGRF_OK; }
   if (!strcmp(key, "conv_kc")) { pgrf::g_conv_kc = value >= 64 ? 64 : (value >= 32 ? 32 : 16); return PGRF_OK; }
   if (!strcmp(key, "conv_smem_kb")) { pgrf::g_conv_smem_kb = value; return PGRF_OK; }
+  if (!strcmp(key, "conv_persist")) { pgrf::g_conv_persist = value; return PGRF_OK; }
+  if (!strcmp(key, "conv_persist_kb")) { pgrf::g_conv_persist_kb = value; return PGRF_OK; }
   if (!strcmp(key, "conv_splits")) { pgrf::g_conv_splits = value; return PGRF_OK; }
   if (!strcmp(key, "conv_row")) { pgrf::g_conv_row = value; return PGRF_OK; }
   if (!strcmp(key, "cv_jb")) { g_cv_jb = value; return PGRF_OK; }

@@ -145,6 +145,17 @@ def test_row_variant_equals_per_tap_variant():
         lib.pgrf_debug_set(b"conv_splits", 0)
     for splits in (1, 3, 9):
         assert torch.equal(outs[1, splits], outs[0, splits])
+    # the non-persistent kernels (one CTA per tile) accumulate in the same order: bit-identical
+    try:
+        _lib.check(lib.pgrf_debug_set(b"conv_persist", 0), "debug_set")
+        for row in (1, 0):
+            _lib.check(lib.pgrf_debug_set(b"conv_row", row), "debug_set")
+            _lib.check(lib.pgrf_debug_set(b"conv_splits", 1), "debug_set")
+            assert torch.equal(reg.conv3d(a, None, wpk, bp, co, (B, D, H, W)), outs[1, 1])
+    finally:
+        lib.pgrf_debug_set(b"conv_persist", 1)
+        lib.pgrf_debug_set(b"conv_row", 1)
+        lib.pgrf_debug_set(b"conv_splits", 0)
     # split-K changes the fp32 summation order of the 9 tap rows: equal to bf16 rounding, not bitwise
     ref = outs[1, 1].float()
     for splits in (3, 9):
