@@ -55,6 +55,17 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// wait with back-off: the epilogue warps of the persistent kernel idle for a whole tile; a tight try_wait loop would take issue slots
+// from the gather warps (ncu: ALU was the busiest pipe at 55 %, mostly spin loops)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -505,7 +516,7 @@ __global__ void __launch_bounds__(kPersistThreads) conv3d_persist_kernel(const C
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const int vt = w % n_vt, rest = w / n_vt, nt = rest % n_nt, z = rest / n_nt;
       const int ab = it & 1;
-      mbar_wait(&acc_full[ab], (it >> 1) & 1);
+      mbar_wait_backoff(&acc_full[ab], (it >> 1) & 1);
       umma::fence_after_sync();
       conv_epilogue_cols<NT, NT>(p, tb + ab * NT, vt, nt, z, q, lane, 0);
       umma::fence_before_sync();
