@@ -107,9 +107,12 @@ __device__ __forceinline__ uint32_t pack_relu2(float lo, float hi) {
 }
 // y = log2e * x (pre-scaled accumulator incl. bias) -> bf16x2 of log2e * ELU(x) = max(y, min(log2e * 2^y - log2e, 0))
 __device__ __forceinline__ uint32_t elu2p_pack(float y0, float y1) {
-  const float2 g = ffma2(make_float2(ex2_approx(y0), ex2_approx(y1)), make_float2(kLog2e, kLog2e), make_float2(-kLog2e, -kLog2e));
-  const __nv_bfloat162 Y = __floats2bfloat162_rn(y0, y1), G = __floats2bfloat162_rn(g.x, g.y);
-  const __nv_bfloat162 o = __hmax2(Y, __hmin2(G, __floats2bfloat162_rn(0.f, 0.f)));
+  // ELU'(y) = relu(y) + min(g, 0) = relu(y) - relu(-g) with -g = log2e - log2e * 2^y.  Both relus are free in the packing conversion
+  // (cvt.rn.relu.bf16x2.f32) and exactly one of the two terms is non-zero, so the packed subtraction is exact:
+  // 2 MUFU + FFMA2 + 2 F2FP + HADD2 per pair (was 2 F2FP + 2 HMNMX2 after the FFMA2)
+  const float2 ng = ffma2(make_float2(ex2_approx(y0), ex2_approx(y1)), make_float2(-kLog2e, -kLog2e), make_float2(kLog2e, kLog2e));
+  const uint32_t yr = pack_relu2(y0, y1), r = pack_relu2(ng.x, ng.y);
+  const __nv_bfloat162 o = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&yr), *reinterpret_cast<const __nv_bfloat162*>(&r));
   return *reinterpret_cast<const uint32_t*>(&o);
 }
 // same in fp32 (the value feeds a register GEMV): log2e * ELU(x)
