@@ -364,6 +364,11 @@ PGRF_API int pgrf_channel_dot_upsample_fwd(const float* x, long long sb, long lo
 PGRF_API int pgrf_compute_prob_fwd(const float* depth, const float* interval, int interval_per_view, const float* mean,
                                    const float* var, const float* vis, const float* aw, const float* depth_range, int rfn,
                                    long long n, int dn, float* alpha, float* visibility, float* hit_prob, void* stream);
+/* compute_prob with is_ref=False (dist_decoder.py:37-45,109-140): the query rays' own hit probability (training: depth loss).  depth,
+ * interval (qn,n); mean / var (qn,n,2), vis (qn,n) or NULL, aw (qn,n) already broadcast over the dn samples of a ray; depth_range (qn,2). */
+PGRF_API int pgrf_compute_prob_que_fwd(const float* depth, const float* interval, const float* mean, const float* var, const float* vis,
+                                       const float* aw, const float* depth_range, int qn, long long n, int dn, float* alpha,
+                                       float* visibility, float* hit_prob, void* stream);
 /* interpolate_feature_map (render_ops.py:126-143 -> ops.py:32-52): feats (rfn,C,fh,fw) NCHW, pix (rfn,pn,2) in full-res
  * (h,w) pixel units -> out (rfn,pn,C); bilinear, padding 'border', align_corners = (fh==h && fw==w) */
 PGRF_API int pgrf_interpolate_feature_map_fwd(const float* feats, int rfn, int C, int fh, int fw, const float* pix, long long pn,

@@ -333,6 +333,31 @@ def compute_prob_ref(depth, interval, mean, var, vis, aw, depth_range, use_vis):
     return alpha, visibility, hit_prob
 
 
+def compute_prob_que(depth, interval, mean, var, vis, aw, depth_range, use_vis):
+    """dist_decoder.py:109-140 with is_ref=False (the query rays' own depth distribution, training only): depth, interval (qn,rn,dn),
+    mean / var (qn,rn,1|dn,2), vis / aw (qn,rn,1|dn,1), depth_range (qn,2).  Near / far are the midpoints between consecutive
+    normalised inverse depths (dist_decoder.py:37-45)."""
+    near_q = -1 / depth_range[:, 0][:, None, None]
+    far_q = -1 / depth_range[:, 1][:, None, None]
+    d = -1 / torch.clamp(depth, min=1e-5)
+    d = (d - near_q) / (far_q - near_q)
+    half = interval / 2
+    first = d[..., 0] - half[..., 0]
+    last = d[..., -1] + half[..., -1]
+    ext = torch.cat([first[..., None], (d[..., :-1] + d[..., 1:]) / 2, last[..., None]], -1)
+    near, far = ext[..., :-1, None], ext[..., 1:, None]
+    mix = torch.cat([aw, 1 - aw], -1)
+    cdf0 = 0.5 + 0.5 * torch.tanh((near - mean) * var)
+    cdf1 = 0.5 + 0.5 * torch.tanh((far - mean) * var)
+    if use_vis:
+        cdf0, cdf1 = cdf0 * vis, cdf1 * vis
+    visibility = torch.sum((1 - cdf0) * mix, -1)
+    hit_prob = torch.sum((cdf1 - cdf0) * mix, -1)
+    eps = 1e-5
+    alpha = torch.log(hit_prob / (visibility - hit_prob + eps) + eps)
+    return alpha, visibility, hit_prob
+
+
 def posenc_table(d_hid, n_samples):
     """ibrnet.py:305-313 (fp64 numpy table cast to fp32)."""
     pos = np.arange(n_samples)[:, None].astype(np.float64)

@@ -152,6 +152,7 @@ SIGNATURES.update({
                                            _P, _P, _P, _P, _P, _P]),
     "pgrf_render_pass_fwd": (_I, [ctypes.POINTER(RenderArgs), _P]),
     "pgrf_agg_mlp_fwd": (_I, [ctypes.POINTER(RenderArgs), _P]),
+    "pgrf_compute_prob_que_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, ctypes.c_longlong, _I, _P, _P, _P, _P]),
     "pgrf_compute_prob_fwd": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, ctypes.c_longlong, _I, _P, _P, _P, _P]),
     "pgrf_interpolate_feature_map_fwd": (_I, [_P, _I, _I, _I, _I, _P, ctypes.c_longlong, _I, _I, _P, _P]),
     "pgrf_composite_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(256) compute_prob_kernel(const float* __restri
                                                            long long interval_view_stride, const float* __restrict__ mean,
                                                            const float* __restrict__ var, const float* __restrict__ vis,
                                                            const float* __restrict__ aw, const float* __restrict__ depth_range,
-                                                           int rfn, long long n, int dn, float* __restrict__ alpha,
+                                                           int rfn, long long n, int dn, int is_ref, float* __restrict__ alpha,
                                                            float* __restrict__ visibility, float* __restrict__ hit_prob) {
   const long long total = (long long)rfn * n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -23,7 +23,13 @@ __global__ void __launch_bounds__(256) compute_prob_kernel(const float* __restri
     const float d_prev = s > 0 ? __ldg(iv + g - 1) : d_s;
     const float rnear = __ldg(depth_range + 2 * v), rfar = __ldg(depth_range + 2 * v + 1);
     const float dv = inv_norm(fmaxf(__ldg(depth + i), 1e-5f), rnear, rfar);
-    const float nearp = dv - d_prev / 2.f, farp = dv + d_s / 2.f;
+    float nearp = dv - d_prev / 2.f, farp = dv + d_s / 2.f;
+    if (!is_ref) {
+      // the rays' own distribution (dist_decoder.py:37-45): bin edges are the midpoints between consecutive normalised inverse depths,
+      // half an interval beyond the first / last sample
+      nearp = s > 0 ? (inv_norm(fmaxf(__ldg(depth + i - 1), 1e-5f), rnear, rfar) + dv) / 2.f : dv - d_s / 2.f;
+      farp = s + 1 < dn ? (dv + inv_norm(fmaxf(__ldg(depth + i + 1), 1e-5f), rnear, rfar)) / 2.f : dv + d_s / 2.f;
+    }
     const float a = __ldg(aw + i);
     const float mix[2] = {a, 1.f - a};
     float vsum = 0.f, hp = 0.f;
@@ -101,7 +107,19 @@ extern "C" int pgrf_compute_prob_fwd(const float* depth, const float* interval, 
   PGRF_REQUIRE(depth && interval && mean && var && aw && depth_range && alpha && visibility && hit_prob, "compute_prob: null pointer argument");
   PGRF_REQUIRE(rfn >= 1 && n >= 1 && dn >= 1 && n % dn == 0, "compute_prob: rfn=%d n=%lld dn=%d (n must be a multiple of dn)", rfn, n, dn);
   compute_prob_kernel<<<grid_for((long long)rfn * n), 256, 0, (cudaStream_t)stream>>>(depth, interval, interval_per_view ? n : 0, mean, var, vis,
-                                                                                    aw, depth_range, rfn, n, dn, alpha, visibility, hit_prob);
+                                                                                    aw, depth_range, rfn, n, dn, 1, alpha, visibility, hit_prob);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_compute_prob_que_fwd(const float* depth, const float* interval, const float* mean, const float* var, const float* vis,
+                                         const float* aw, const float* depth_range, int qn, long long n, int dn, float* alpha,
+                                         float* visibility, float* hit_prob, void* stream) {
+  PGRF_REQUIRE(depth && interval && mean && var && aw && depth_range && alpha && visibility && hit_prob, "compute_prob_que: null pointer argument");
+  PGRF_REQUIRE(qn >= 1 && n >= 1 && dn >= 1 && n % dn == 0, "compute_prob_que: qn=%d n=%lld dn=%d (n must be a multiple of dn)", qn, n, dn);
+  compute_prob_kernel<<<grid_for((long long)qn * n), 256, 0, (cudaStream_t)stream>>>(depth, interval, n, mean, var, vis, aw, depth_range, qn, n, dn,
+                                                                                   0, alpha, visibility, hit_prob);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;

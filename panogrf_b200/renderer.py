@@ -87,12 +87,29 @@ class MixtureLogisticsDistDecoder(nn.Module):
         return torch.sigmoid(alpha_value)
 
     def compute_prob(self, depth, interval, mean, var, vis, aw, is_ref, depth_range):
-        """dist_decoder.py:109-140 (is_ref=True, the render path): depth (rfn,qn,rn,dn), interval (1|rfn,qn,rn,dn),
-        mean/var (rfn,qn,rn,dn,2), vis/aw (rfn,qn,rn,dn,1), depth_range (rfn,2) -> alpha, visibility, hit_prob (rfn,qn,rn,dn)."""
-        if not is_ref:
-            raise NotImplementedError("compute_prob(is_ref=False) belongs to the training-only self hit probability")
+        """dist_decoder.py:109-140.  is_ref=True (the render path): depth (rfn,qn,rn,dn), interval (1|rfn,qn,rn,dn),
+        mean/var (rfn,qn,rn,dn,2), vis/aw (rfn,qn,rn,dn,1), depth_range (rfn,2) -> alpha, visibility, hit_prob (rfn,qn,rn,dn).
+        is_ref=False (the query rays' own distribution, used by the training losses): depth, interval (qn,rn,dn), mean/var
+        (qn,rn,1|dn,2), vis/aw (qn,rn,1|dn,1), depth_range (qn,2) -> (qn,rn,dn)."""
         _lib.require_cuda(depth, interval, mean, var, aw)
         lib = _lib.load()
+        if not is_ref:
+            # the query rays' own distribution: depth, interval (qn,rn,dn); mean / var (qn,rn,1|dn,2); vis / aw (qn,rn,1|dn,1)
+            shape = depth.shape
+            qn, dn = shape[0], shape[-1]
+            n = depth[0].numel()
+            fq = lambda t, c: t.detach().float().expand(*shape, c).reshape(qn, n, c).contiguous()
+            d = depth.detach().float().reshape(qn, n).contiguous()
+            iv = interval.detach().float().expand(*shape).reshape(qn, n).contiguous()
+            m2, v2, a1 = fq(mean, 2), fq(var, 2), fq(aw, 1)
+            vs = fq(vis, 1) if (self.cfg["use_vis"] and vis is not None) else None
+            rng = depth_range.detach().float().contiguous().to(d.device)
+            outs = [torch.empty(qn, n, device=d.device) for _ in range(3)]
+            with torch.cuda.device(d.device):
+                rc = lib.pgrf_compute_prob_que_fwd(_lib.ptr(d), _lib.ptr(iv), _lib.ptr(m2), _lib.ptr(v2), _lib.ptr(vs), _lib.ptr(a1),
+                                                   _lib.ptr(rng), qn, n, dn, *[_lib.ptr(o) for o in outs], _lib.stream_ptr())
+            _lib.check(rc, "pgrf_compute_prob_que_fwd")
+            return tuple(o.reshape(shape) for o in outs)
         shape = depth.shape
         rfn, dn = shape[0], shape[-1]
         n = depth[0].numel()

@@ -69,9 +69,22 @@ def test_dist_decoder_module(name):
     assert_close(v, v_o, rtol=1e-4, atol=1e-5, what="visibility")
     assert_close(h, h_o, rtol=1e-4, atol=1e-5, what="hit_prob")
     assert_close(a, a_o, rtol=1e-4, atol=2e-3, what="alpha")       # log of a ratio of differences: ill-conditioned near 0
-    with pytest.raises(NotImplementedError):
-        net.dist_decoder.compute_prob(prj["depth"].squeeze(-1).cuda(), out["dists"].unsqueeze(0).cuda(), c(mean_o), c(var_o),
-                                      c(vis_o), c(aw_o), False, ref["depth_range"].cuda())
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_compute_prob_is_ref_false_matches_reference_golden(tag):
+    """the query rays' own hit probability (is_ref=False, training losses): golden produced by the reference class"""
+    import panogrf_b200 as pg
+    g = load_golden("prob_que")
+    c = {k[2:]: v for k, v in g.items() if k.startswith(tag + ".")}
+    cfg, _, _ = cases.make_render_inputs("render_m3d_2src")
+    uv = bool(c["use_vis"])
+    net = pg.NeuralRayBaseRenderer({**cfg, "dist_decoder_cfg": {"use_vis": uv}, "fine_dist_decoder_cfg": {"use_vis": uv}}).cuda()
+    d = lambda k: c[k].cuda()
+    a, v, h = net.dist_decoder.compute_prob(d("depth"), d("interval"), d("mean"), d("var"), d("vis"), d("aw"), False, d("depth_range"))
+    assert_close(v, c["visibility"], rtol=1e-4, atol=1e-5, what="visibility")
+    assert_close(h, c["hit_prob"], rtol=1e-4, atol=1e-5, what="hit_prob")
+    assert_close(a, c["alpha"], rtol=1e-4, atol=2e-3, what="alpha")
 
 
 @pytest.mark.parametrize("name", CASES)

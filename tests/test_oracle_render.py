@@ -94,3 +94,14 @@ def test_oracle_perspective_rays_match_reference_golden():
     out = orender.render_rays(cfg, W, que, ref, keep_hit_prob=True, is_perspec=True)
     for k in ("pixel_colors_nr", "render_depth", "hit_prob_nr", "pixel_colors_nr_fine", "render_depth_fine"):
         assert_close(out[k], gold[k], rtol=1e-4, atol=2e-5, what=f"{name}/{k}")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_oracle_compute_prob_is_ref_false_matches_reference_golden(tag):
+    """the query rays' own hit probability (dist_decoder.py:37-45,109-140, is_ref=False): per-ray and per-sample distributions"""
+    g = load_golden("prob_que")
+    c = {k[2:]: v for k, v in g.items() if k.startswith(tag + ".")}
+    a, v, h = orender.compute_prob_que(c["depth"], c["interval"], c["mean"], c["var"], c["vis"], c["aw"], c["depth_range"],
+                                       bool(c["use_vis"]))
+    for got, key in ((a, "alpha"), (v, "visibility"), (h, "hit_prob")):
+        assert_close(got, c[key], rtol=1e-5, atol=1e-6, what=f"prob_que/{tag}/{key}")
