@@ -644,7 +644,8 @@ class NeuralRayBaseRenderer(nn.Module):
         return ("", "_fine") if self.cfg["use_hierarchical_sampling"] else ("",)
 
     def _needs_post(self):
-        return bool(self.cfg.get("render_uncert")) or bool(self.cfg.get("render_c2f_all") and self.cfg["use_hierarchical_sampling"])
+        return (bool(self.cfg.get("render_uncert")) or bool(self.cfg.get("perpoint_loss"))
+                or bool(self.cfg.get("render_c2f_all") and self.cfg["use_hierarchical_sampling"]))
 
     def _post(self, outs, depth_table, keep_hit_prob):
         """Optional outputs assembled from the per-sample results: `render_c2f_all` re-composites the coarse and the
@@ -671,6 +672,10 @@ class NeuralRayBaseRenderer(nn.Module):
                     outs["render_depth_fine"] = rdepth
             if cfg.get("render_uncert"):
                 outs["render_uncert_fine"] = unc(z_f, outs["render_depth_fine"], outs["hit_prob_nr_fine"])
+        if cfg.get("perpoint_loss"):                                  # per-sample weights and depths for the losses (renderer.py:314-316)
+            outs["render_weights"], outs["render_dvals"] = outs["hit_prob_nr"], z_c
+            if cfg["use_hierarchical_sampling"]:
+                outs["render_weights_fine"], outs["render_dvals_fine"] = outs["hit_prob_nr_fine"], z_f
         if not keep_hit_prob:
             for k in ("hit_prob_nr", "hit_prob_nr_fine", "que_depth_fine"):
                 outs.pop(k, None)

@@ -148,6 +148,22 @@ def test_render_full_view_chunking_and_properties():
     assert_close(a["render_depth_fine"][:, idx.cuda()], o["render_depth_fine"], rtol=1e-4, atol=5e-5, what="view/depth")
 
 
+def test_perpoint_loss_outputs():
+    """cfg['perpoint_loss'] (renderer.py:314-316): per-sample weights and depths of both passes next to the composited outputs"""
+    name = "render_m3d_2src"
+    cfg, _, _ = cases.make_render_inputs(name)
+    g = load_golden(name)
+    que, ref, W, gold = split_golden(g)
+    net = build_renderer({**cfg, "perpoint_loss": True}, W)
+    out = net.render(cuda_dict(que), cuda_dict(ref), False)
+    expect = orender.render_rays(cfg, W, que, ref, keep_hit_prob=True)
+    assert_close(out["render_weights"], expect["hit_prob_nr"], rtol=1e-4, atol=2e-5, what="render_weights")
+    assert_close(out["render_weights_fine"], expect["hit_prob_nr_fine"], rtol=1e-4, atol=2e-4, max_bad_frac=2e-3, what="render_weights_fine")
+    assert_close(out["render_dvals_fine"], expect["que_depth_fine"], rtol=1e-4, atol=1e-4, max_bad_frac=2e-3, what="render_dvals_fine")
+    assert out["render_dvals"].shape == out["render_weights"].shape
+    assert "hit_prob_nr" not in out
+
+
 def test_errors():
     import panogrf_b200 as pg
     cfg = cases.render_cfg()
