@@ -93,3 +93,28 @@ def test_struct_layouts_match_the_header(tmp_path):
             assert getattr(cls, fname).offset == val, (cname, fname, getattr(cls, fname).offset, val)
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+
+
+def test_conv3d_plan_and_validation_without_gpu(lib):
+    """The tile / split-K plan of the regulariser's convolution is host code: workspace sizes and argument checks on a CPU box."""
+    import ctypes
+    from panogrf_b200 import _lib
+    need = ctypes.c_longlong(-1)
+    # a coarse U-Net level (8 voxel tiles x 4 channel tiles = 32 CTAs) splits K over all nine tap rows: 9 partial volumes
+    assert lib.pgrf_conv3d_workspace(512, 0, 512, 1, 8, 8, 16, ctypes.byref(need)) == _lib.PGRF_OK
+    assert need.value == 9 * 1024 * 512
+    # a full-resolution level fills the GPU by itself: no workspace
+    assert lib.pgrf_conv3d_workspace(64, 0, 64, 1, 64, 64, 128, ctypes.byref(need)) == _lib.PGRF_OK and need.value == 0
+    # D == 1 is a 2-D convolution: only the three kd == 1 tap rows exist, so at most 3 splits
+    assert lib.pgrf_conv3d_workspace(32, 0, 32, 1, 1, 32, 64, ctypes.byref(need)) == _lib.PGRF_OK
+    assert need.value == 3 * 2048 * 32
+    # channel counts must be multiples of 16; a concatenation needs a common chunk size
+    assert lib.pgrf_conv3d_workspace(24, 0, 32, 1, 8, 8, 16, ctypes.byref(need)) == _lib.PGRF_EINVAL
+    assert b"multiples of 16" in lib.pgrf_last_error()
+    dummy = ctypes.c_void_p(256)
+    rc = lib.pgrf_conv3d_fwd(dummy, 32, None, 16, dummy, dummy, dummy, None, 0, 32, 1, 8, 8, 16, 1, None, 0, None)
+    assert rc == _lib.PGRF_EINVAL and b"second input" in lib.pgrf_last_error()
+    rc = lib.pgrf_conv3d_fwd(dummy, 512, None, 0, dummy, dummy, dummy, None, 0, 512, 1, 8, 8, 16, 1, None, 0, None)
+    assert rc == _lib.PGRF_EINVAL and b"workspace" in lib.pgrf_last_error()
+    rc = lib.pgrf_conv3d_fwd(dummy, 32, None, 0, dummy, dummy, dummy, dummy, 1, 32, 1, 8, 8, 16, 1, None, 0, None)
+    assert rc == _lib.PGRF_EINVAL and b"exactly one of y / yf" in lib.pgrf_last_error()
