@@ -305,10 +305,11 @@ UNET3D_CASES = {
     # name: (size, input shape (B, 2^(size+1), D, H, W)); D, H, W divisible by 8 (three poolings)
     "unet3d_s1": (1, (1, 4, 8, 8, 16)),
     "unet3d_s2": (2, (2, 8, 8, 16, 16)),
+    "unet3d_s3": (1, (1, 4, 8, 16, 128)),      # W = 128: the row variant of the convolution kernel on the full-resolution levels
 }
 
 
-UNET3D_STORE_WEIGHTS = {"unet3d_s1": True, "unet3d_s2": False}
+UNET3D_STORE_WEIGHTS = {"unet3d_s1": True, "unet3d_s2": False, "unet3d_s3": False}
 
 
 def unet3d_seed(name):
