@@ -967,6 +967,15 @@ def time_mvs_stages(torch, dev, flush, peaks):
         "library_ms": ms_lib, "library": "the same network through torch/cuDNN fp32 (TF32) convolutions, as the reference runs it",
         "max_err_vs_library_of_range": err, "dtype": "bf16 operands, fp32 accumulate"}
     del net, x, ref
+    # DefaultVisEncoder on the 1/4-resolution maps of the benched view (2 source panoramas: 32 + 32 channels at 128x256)
+    from panogrf_b200.vis_encoder import DefaultVisEncoder
+    venc = DefaultVisEncoder({"use_wrap_padding": True}).to(dev)
+    rf, imf = torch.randn(2, 32, 128, 256, device=dev), torch.randn(2, 32, 128, 256, device=dev)
+    ms = _median_ms(torch, flush, lambda: venc(rf, imf), n=5)
+    vflops = 2 * 2 * 128 * 256 * (9 * 64 * 32 + 4 * 9 * 32 * 32 + 32 * 32)
+    res["vis_encoder_2x32x128x256"] = {"ms": ms, "gflop": vflops / 1e9, "tflops": vflops / ms / 1e9,
+                                       "note": "6 tensor-core convolutions + 4 instance norms, 14 launches; bf16 activations"}
+    del venc, rf, imf
     # equirect -> cubemap: 3 panoramas 512x1024x3 -> 256-pixel faces
     conv = pe2c.Equirec2Cube(512, 1024, 256)
     pano = torch.rand(3, 512, 1024, 3, device=dev)

@@ -333,6 +333,18 @@ PGRF_API int pgrf_conv3d_to_bf16_cl(const float* x, long long sb, long long sc, 
 PGRF_API int pgrf_conv3d_workspace(int Ca, int Cb, int Cout, int B, int D, int H, int W, long long* ws_floats);
 PGRF_API int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
                              int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, void* stream);
+/* pgrf_conv3d_fwd with an optional residual input `res` (bf16 channels-last, the shape of y; added after bias / activation:
+ * ResidualBlock, network/ops.py:61-115) and the choice of the width padding: wrap = 1 WrapPadding, 0 zeros on every side. */
+PGRF_API int pgrf_conv3d_ex_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
+                                int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats,
+                                const void* res, int wrap, void* stream);
+/* DefaultVisEncoder (network/vis_encoder.py:6-33) around the convolutions: pgrf_feats_to_bf16_cl = cat(F.interpolate(img_feats, (h,w),
+ * 'bilinear'), ray_feats) of two fp32 NCHW maps -> bf16 channels-last (N,h,w,Ci+Cr); pgrf_instnorm_relu_fwd = nn.InstanceNorm2d
+ * (affine, biased variance, eps) + ReLU on a bf16 channels-last map (N,HW,C); stats_ws: 2*N*C doubles. */
+PGRF_API int pgrf_feats_to_bf16_cl(const float* img, int Ci, int hi, int wi, const float* ray, int Cr, int N, int h, int w, void* out,
+                                   void* stream);
+PGRF_API int pgrf_instnorm_relu_fwd(const void* x, int N, int HW, int C, const float* gamma, const float* beta, float eps, double* stats_ws,
+                                    void* y, void* stream);
 /* A 3x3x3 convolution with ONE output channel over many input channels (the 128 -> 1 head of the last decoder) in two steps that read
  * every voxel's channels once instead of once per tap row: pgrf_conv3d_pointwise_fwd = 1x1x1 convolution through the tensor-core
  * pipeline (only the centre tap of the packed weights is walked; here with the 27 taps as output channels, fp32 planar

@@ -41,6 +41,8 @@ struct ConvParams {
   long long n_vox;
   int splits;                          // split-K over the 9 (kd, kh) tap rows: blockIdx.z accumulates 9/splits of them into
   float* ws;                           // fp32 partial sums [splits][n_vox][Cout] (bias / activation applied by the reduction)
+  const __nv_bfloat16* res;            // optional residual (same shape as y) added after bias / activation (ResidualBlock, ops.py:61-115)
+  int wrap;                            // 1: wrap along width (WrapPadding), 0: zeros on every side (plain zero padding)
   int tap_lo, tap_cnt;                 // taps walked by the per-tap variant (= 3 * the tap rows below, or the centre tap alone for a
                                        // pointwise / 1x1x1 convolution)
   int krow_lo, krow_cnt;               // (kd, kh) tap rows walked: all 9, or rows 3..5 when D == 1 (a 2-D convolution: the kd != 1
@@ -106,6 +108,16 @@ __device__ __forceinline__ void conv_epilogue_cols(const ConvParams& p, uint32_t
       for (int i = 0; i < 16; ++i)
         if (cbase + c + i < p.cout_real) p.yf[(bi * p.cout_real + cbase + c + i) * DHW + rem] = a[i];
     } else {
+      if (p.res) {
+        const uint4* rs = reinterpret_cast<const uint4*>(p.res + (size_t)v * p.Cout + cbase + c);
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          const uint4 q4 = __ldg(rs + hq);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); a[8 * hq + 2 * j] += f.x; a[8 * hq + 2 * j + 1] += f.y; }
+        }
+      }
       __nv_bfloat16* dst = p.y + (size_t)v * p.Cout + cbase + c;
       reinterpret_cast<uint4*>(dst)[0] = make_uint4(umma::pack2(a[0], a[1]), umma::pack2(a[2], a[3]), umma::pack2(a[4], a[5]), umma::pack2(a[6], a[7]));
       reinterpret_cast<uint4*>(dst)[1] = make_uint4(umma::pack2(a[8], a[9]), umma::pack2(a[10], a[11]), umma::pack2(a[12], a[13]), umma::pack2(a[14], a[15]));
@@ -209,7 +221,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_kernel(const ConvPa
       uint32_t nb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const bool ok = (rowinfo[i] >> krow) & 1u;
+        const bool ok = ((rowinfo[i] >> krow) & 1u) && (p.wrap || !(rowinfo[i] & wrap_bit));
         nb[i] = ok ? 16u : 0u;
         nv[i] = ok ? vbase + i * row_step + tap_off + ((rowinfo[i] & wrap_bit) ? wrap_off : 0) : 0;
       }
@@ -293,6 +305,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_row_kernel(const Co
     const bool halo = r < 2 * kch;
     const long long halo_off = r < kch ? (x0 == 0 ? (long long)p.W - 1 : -1) : (x0 + kConvRows == p.W ? (long long)kConvRows - p.W : kConvRows);
     const int hc = r < kch ? r : r - kch;
+    const bool halo_zero = !p.wrap && (r < kch ? x0 == 0 : x0 + kConvRows == p.W);      // zero padding: no neighbour across the seam
     const uint32_t hdst0 = smem_u32(As) + hc * kRowPitch + (r < kch ? 0 : kRowA - 1) * 16;
     const uint32_t adst0 = smem_u32(As) + my_chunk * kRowPitch + (row0 + 1) * 16;
     const uint32_t dst_step = row_step * 16;
@@ -329,7 +342,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_row_kernel(const Co
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (i < n_rows) { cp_async16(adst + i * dst_step, rp[i], nbytes); rp[i] += p.KC; }
-          if (halo) { cp_async16(hdst, hp, nbytes); hp += p.KC; }
+          if (halo) { cp_async16(hdst, hp, halo_zero ? 0u : nbytes); hp += p.KC; }
           cp_async_arrive(&bar_full[s]);
           adst += a_bytes;
           hdst += a_bytes;
@@ -402,12 +415,14 @@ __global__ void __launch_bounds__(kPersistThreads) conv3d_persist_kernel(const C
       int x0 = 0, ty = 0, td = 0;
       uint32_t rowinfo[4] = {0u, 0u, 0u, 0u};
       long long halo_off = 0;
+      bool halo_zero = false;
       if (ROW) {
         long long t = v0;
         x0 = (int)(t % p.W); t /= p.W;
         ty = (int)(t % p.H); t /= p.H;
         td = (int)(t % p.D);
         halo_off = r < kch ? (x0 == 0 ? (long long)p.W - 1 : -1) : (x0 + kConvRows == p.W ? (long long)kConvRows - p.W : kConvRows);
+        halo_zero = !p.wrap && (r < kch ? x0 == 0 : x0 + kConvRows == p.W);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -446,7 +461,7 @@ __global__ void __launch_bounds__(kPersistThreads) conv3d_persist_kernel(const C
           const long long wrap_off = kw < 0 ? p.W : -p.W;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const bool ok = (rowinfo[i] >> krow) & 1u;
+            const bool ok = ((rowinfo[i] >> krow) & 1u) && (p.wrap || !(rowinfo[i] & wrap_bit));
             nb[i] = ok ? 16u : 0u;
             nv[i] = ok ? v0 + row0 + i * row_step + tap_off + ((rowinfo[i] & wrap_bit) ? wrap_off : 0) : 0;
           }
@@ -472,7 +487,7 @@ __global__ void __launch_bounds__(kPersistThreads) conv3d_persist_kernel(const C
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               if (i < n_rows) { cp_async16(adst + i * dst_step, rp[i], nb[i]); rp[i] += p.KC; }
-            if (halo) { cp_async16(hdst, hp, nb[0]); hp += p.KC; }
+            if (halo) { cp_async16(hdst, hp, halo_zero ? 0u : nb[0]); hp += p.KC; }
             cp_async_arrive(&bar_full[s]);
             adst += a_bytes;
             hdst += a_bytes;
@@ -554,6 +569,12 @@ __global__ void __launch_bounds__(256) conv3d_reduce_kernel(const ConvParams p) 
     for (int k = 0; k < 8; ++k)
       if (c + k < p.cout_real) p.yf[(bi * p.cout_real + c + k) * DHW + rem] = a[k];
   } else {
+    if (p.res) {
+      const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)v * p.Cout + c));
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); a[2 * j] += f.x; a[2 * j + 1] += f.y; }
+    }
     *reinterpret_cast<uint4*>(p.y + (size_t)v * p.Cout + c) =
         make_uint4(umma::pack2(a[0], a[1]), umma::pack2(a[2], a[3]), umma::pack2(a[4], a[5]), umma::pack2(a[6], a[7]));
   }
@@ -882,7 +903,7 @@ extern "C" int pgrf_conv3d_workspace(int Ca, int Cb, int Cout, int B, int D, int
 
 static int conv3d_launch(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
                          int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, bool pointwise,
-                         void* stream) {
+                         const void* res, int wrap, void* stream) {
   PGRF_REQUIRE(xa && wpk && bias && ((y != nullptr) != (yf != nullptr)), "conv3d: null pointer argument (exactly one of y / yf)");
   PGRF_REQUIRE(Cb == 0 || xb, "conv3d: Cb=%d without a second input", Cb);
   PGRF_REQUIRE(!yf || (cout_real >= 1 && cout_real <= Cout), "conv3d: cout_real=%d outside [1, %d]", cout_real, Cout);
@@ -896,6 +917,8 @@ static int conv3d_launch(const void* xa, int Ca, const void* xb, int Cb, const v
   p.wpk = (const unsigned char*)wpk; p.bias = bias; p.y = (__nv_bfloat16*)y; p.Cout = Cout; p.yf = yf; p.cout_real = cout_real;
   p.B = B; p.D = D; p.H = H; p.W = W; p.act = act; p.KC = pl.KC; p.n_cc = pl.n_cc;
   p.n_vox = (long long)B * D * H * W;
+  PGRF_REQUIRE(!res || y, "conv3d: a residual needs the bf16 channels-last output");
+  p.res = (const __nv_bfloat16*)res; p.wrap = wrap ? 1 : 0;
   p.splits = pl.splits; p.ws = ws; p.krow_lo = pl.krow_lo; p.krow_cnt = pl.krow_cnt;
   p.tap_lo = pointwise ? 13 : 3 * pl.krow_lo;          // 13 = (kd, kh, kw) = (1, 1, 1)
   p.tap_cnt = pointwise ? 1 : 3 * pl.krow_cnt;
@@ -967,13 +990,20 @@ static int conv3d_launch(const void* xa, int Ca, const void* xb, int Cb, const v
 
 extern "C" int pgrf_conv3d_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
                                int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats, void* stream) {
-  return conv3d_launch(xa, Ca, xb, Cb, wpk, bias, y, yf, cout_real, Cout, B, D, H, W, act, ws, ws_floats, false, stream);
+  return conv3d_launch(xa, Ca, xb, Cb, wpk, bias, y, yf, cout_real, Cout, B, D, H, W, act, ws, ws_floats, false, nullptr, 1, stream);
+}
+
+// same with an optional residual input and the choice of the width padding (wrap / zeros)
+extern "C" int pgrf_conv3d_ex_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y, float* yf,
+                                  int cout_real, int Cout, int B, int D, int H, int W, int act, float* ws, long long ws_floats,
+                                  const void* res, int wrap, void* stream) {
+  return conv3d_launch(xa, Ca, xb, Cb, wpk, bias, y, yf, cout_real, Cout, B, D, H, W, act, ws, ws_floats, false, res, wrap, stream);
 }
 
 // Pointwise (1x1x1) convolution through the same pipeline: only the centre tap of the packed weights is walked.
 extern "C" int pgrf_conv3d_pointwise_fwd(const void* xa, int Ca, const void* xb, int Cb, const void* wpk, const float* bias, void* y,
                                          float* yf, int cout_real, int Cout, int B, int D, int H, int W, int act, void* stream) {
-  return conv3d_launch(xa, Ca, xb, Cb, wpk, bias, y, yf, cout_real, Cout, B, D, H, W, act, nullptr, 0, true, stream);
+  return conv3d_launch(xa, Ca, xb, Cb, wpk, bias, y, yf, cout_real, Cout, B, D, H, W, act, nullptr, 0, true, nullptr, 1, stream);
 }
 
 extern "C" int pgrf_conv3d_tapsum_fwd(const float* z, float bias, int B, int D, int H, int W, int act, float* out, void* stream) {

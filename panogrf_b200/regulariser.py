@@ -62,9 +62,10 @@ def pack_conv_cout1(weight, ca, cb, ca_pad, cb_pad):
     return wp.contiguous()
 
 
-def conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels=0, ws_cache=None, lib=None, st=None, act=True):
+def conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels=0, ws_cache=None, lib=None, st=None, act=True, res=None, wrap=True):
     """One Conv3d(3x3x3) + WrapPadding3D + bias + LeakyReLU layer on [xa | xb] (bf16 channels-last, packed weights from `pack_conv`).
-    Returns bf16 channels-last (B,D,H,W,co_pad), or fp32 (B,f32_channels,D,H,W) when f32_channels > 0."""
+    Returns bf16 channels-last (B,D,H,W,co_pad), or fp32 (B,f32_channels,D,H,W) when f32_channels > 0.  `res`: bf16 channels-last
+    residual added after bias / activation; `wrap=False`: zeros instead of the wrap along the width."""
     lib = lib or _lib.load()
     st = _lib.stream_ptr() if st is None else st
     B, D, H, W = dims
@@ -83,10 +84,10 @@ def conv3d(xa, xb, wpk, bias, co_pad, dims, f32_channels=0, ws_cache=None, lib=N
         y = torch.empty((B, f32_channels, D, H, W), device=xa.device, dtype=torch.float32)
     else:
         y = torch.empty((B, D, H, W, co_pad), device=xa.device, dtype=torch.bfloat16)
-    _lib.check(lib.pgrf_conv3d_fwd(_lib.ptr(xa), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad, _lib.ptr(wpk), _lib.ptr(bias),
-                                   None if f32_channels else _lib.ptr(y), _lib.ptr(y) if f32_channels else None, f32_channels, co_pad,
-                                   B, D, H, W, 1 if act else 0, _lib.ptr(ws) if ws is not None else None, need.value, st),
-               "pgrf_conv3d_fwd")
+    _lib.check(lib.pgrf_conv3d_ex_fwd(_lib.ptr(xa), ca_pad, _lib.ptr(xb) if xb is not None else None, cb_pad, _lib.ptr(wpk), _lib.ptr(bias),
+                                      None if f32_channels else _lib.ptr(y), _lib.ptr(y) if f32_channels else None, f32_channels, co_pad,
+                                      B, D, H, W, 1 if act else 0, _lib.ptr(ws) if ws is not None else None, need.value,
+                                      _lib.ptr(res) if res is not None else None, 1 if wrap else 0, st), "pgrf_conv3d_ex_fwd")
     return y
 
 

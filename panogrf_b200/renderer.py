@@ -7,9 +7,11 @@ parameters (`[fine_]dist_decoder.*`, `[fine_]agg_net.*`), so a reference checkpo
 (network/renderer.py:223-317, 435-524, 567-633, 635-686) is replaced by three persistent sm_100a
 kernels per pass (csrc/render_kernels.cu) reached through the C ABI.
 
-Out of scope here (SURVEY.md §8f "next"): the per-call CNN encoders (`image_encoder`,
-`vis_encoder`, `init_net`).  `render()` therefore takes `ref_imgs_info['img_feats']` and the already
-vis-encoded `ref_imgs_info['ray_feats']`, or runs user-supplied encoder callables if attached.
+The per-call CNN encoders (SURVEY.md §8f "next"): `render()` takes `ref_imgs_info['img_feats']` and the already
+vis-encoded `ref_imgs_info['ray_feats']`, or — when `ref_imgs_info` has no `img_feats` — runs the attached encoders like
+network/renderer.py:639-642: `net.vis_encoder = panogrf_b200.vis_encoder.DefaultVisEncoder(cfg)` is the tensor-core drop-in
+(its parameters then appear as `vis_encoder.*`, the reference's names); `image_encoder` (ResUNetLight) and `init_net` stay
+user-supplied callables.
 Only the eval path (`is_train=False`, deterministic sampling, no autograd) is implemented.
 """
 import ctypes

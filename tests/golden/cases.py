@@ -339,3 +339,20 @@ def make_dec2d_inputs(name):
     cost_reg = torch.randn(B, 1, D, H, W, generator=g)[:, 0]
     mono = torch.randn(B, 2 ** (size + 1), H, W, generator=g)
     return cost_reg, mono
+
+
+# ------------------------------------------------------------------------------------------------
+# DefaultVisEncoder (network/vis_encoder.py:6-33)
+# ------------------------------------------------------------------------------------------------
+VISENC_CASES = {
+    # name: (use_wrap_padding, n views, ray_feats (h, w), img_feats (hi, wi))
+    "visenc_wrap": (True, 2, (16, 32), (16, 32)),
+    "visenc_wrap_resize": (True, 1, (8, 128), (16, 256)),      # W = 128: row variant of the convolution; img_feats resized
+    "visenc_zero": (False, 2, (12, 24), (24, 48)),
+}
+
+
+def make_visenc_inputs(name):
+    _, n, (h, w), (hi, wi) = VISENC_CASES[name]
+    g = torch.Generator().manual_seed(500 + sorted(VISENC_CASES).index(name))
+    return torch.randn(n, 32, h, w, generator=g), torch.randn(n, 32, hi, wi, generator=g)
