@@ -39,3 +39,24 @@ def vis_encoder(W, ray_feats, img_feats, wrap=True):
         t = F.conv2d(_pad(t, wrap), W[p + f"{i[3]}.weight"])
         x = x + t
     return F.conv2d(x, W["out_conv.3.weight"])
+
+
+def conv_stack(W, prefix, x, n_blocks, wrap=True):
+    """`conv3x3 -> n x ResidualBlock -> conv1x1` (network/init_net.py:540-574) with the reference's state_dict names under `prefix`."""
+    c0 = f"{prefix}.0.1.weight" if wrap else f"{prefix}.0.weight"
+    x = F.conv2d(_pad(x, wrap), W[c0])
+    i = (0, 3, 4, 7) if wrap else (0, 2, 3, 5)
+    for blk in range(1, n_blocks + 1):
+        p = f"{prefix}.{blk}.conv."
+        t = _inorm_relu(x, W[p + f"{i[0]}.weight"], W[p + f"{i[0]}.bias"])
+        t = F.conv2d(_pad(t, wrap), W[p + f"{i[1]}.weight"])
+        t = _inorm_relu(t, W[p + f"{i[2]}.weight"], W[p + f"{i[2]}.bias"])
+        t = F.conv2d(_pad(t, wrap), W[p + f"{i[3]}.weight"])
+        x = x + t
+    return F.conv2d(x, W[f"{prefix}.{n_blocks + 1}.weight"])
+
+
+def init_net_convs(W, ref_feats, depth, wrap=True):
+    """network/init_net.py:629-636: depth_feats = depth_conv(depth); ray_feats = out_conv(cat(ref_feats, depth_feats))"""
+    depth_feats = conv_stack(W, "depth_conv", depth, 1, wrap)
+    return conv_stack(W, "out_conv", torch.cat([ref_feats, depth_feats], 1), 1, wrap)

@@ -356,3 +356,17 @@ def make_visenc_inputs(name):
     _, n, (h, w), (hi, wi) = VISENC_CASES[name]
     g = torch.Generator().manual_seed(500 + sorted(VISENC_CASES).index(name))
     return torch.randn(n, 32, h, w, generator=g), torch.randn(n, 32, hi, wi, generator=g)
+
+
+# CostVolumeInitNet's convolution stacks (network/init_net.py:540-574, 606-636)
+INITCONV_CASES = {
+    # name: (use_wrap_padding, n views, (h, w))
+    "initconv_wrap": (True, 2, (16, 32)),
+    "initconv_zero": (False, 1, (12, 128)),
+}
+
+
+def make_initconv_inputs(name):
+    _, n, (h, w) = INITCONV_CASES[name]
+    g = torch.Generator().manual_seed(600 + sorted(INITCONV_CASES).index(name))
+    return torch.randn(n, 32, h, w, generator=g), 0.5 + 9.0 * torch.rand(n, 1, h, w, generator=g)

@@ -29,3 +29,16 @@ def test_container_has_the_reference_parameter_names(name):
     net = DefaultVisEncoder({"use_wrap_padding": cases.VISENC_CASES[name][0]})
     assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in W.items()}
     net.load_state_dict(W)
+
+
+@pytest.mark.parametrize("name", list(cases.INITCONV_CASES))
+def test_init_net_convs_oracle_and_container(name):
+    from panogrf_b200.vis_encoder import CostVolumeInitConvs
+    g = load_golden(name)
+    W = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
+    wrap = cases.INITCONV_CASES[name][0]
+    out = ovis.init_net_convs(W, g["ref_feats"], g["depth"], wrap)
+    assert float((out - g["ray_feats"]).abs().max()) <= 1e-5 * max(1.0, float(g["ray_feats"].abs().max()))
+    net = CostVolumeInitConvs({"use_wrap_padding": wrap})
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in W.items()}
+    net.load_state_dict(W)

@@ -82,3 +82,20 @@ def test_renderer_runs_the_attached_vis_encoder():
     ref_out = net.render(q, r2, False)
     assert torch.equal(out["pixel_colors_nr_fine"], ref_out["pixel_colors_nr_fine"])
     assert torch.isfinite(out["pixel_colors_nr_fine"]).all()
+
+
+@pytest.mark.parametrize("name", list(cases.INITCONV_CASES))
+def test_init_net_convs_match_reference_golden(name):
+    """CostVolumeInitNet's depth_conv / out_conv stacks (init_net.py:540-574, 629-636) vs the reference's own layers"""
+    from panogrf_b200.vis_encoder import CostVolumeInitConvs
+    g = load_golden(name)
+    W = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
+    net = CostVolumeInitConvs({"use_wrap_padding": cases.INITCONV_CASES[name][0]})
+    net.load_state_dict(W)
+    net = net.cuda()
+    out = net(g["ref_feats"].cuda(), g["depth"].cuda()).cpu()
+    scale = float(g["ray_feats"].abs().max())
+    err = float((out - g["ray_feats"]).abs().max())
+    rms = float((out - g["ray_feats"]).pow(2).mean().sqrt())
+    print(f"{name}: max err {err:.3e}, rms {rms:.3e} of range {scale:.3e} ({err / scale:.2e})")
+    assert err <= VISENC_TOL * scale and rms <= 3e-3 * scale
