@@ -976,6 +976,15 @@ def time_mvs_stages(torch, dev, flush, peaks):
     res["vis_encoder_2x32x128x256"] = {"ms": ms, "gflop": vflops / 1e9, "tflops": vflops / ms / 1e9,
                                        "note": "6 tensor-core convolutions + 4 instance norms, 14 launches; bf16 activations"}
     del venc, rf, imf
+    # image encoder ResUNetLight on the two 512x1024 source panoramas (network/renderer.py:106,639), with torch's library path beside it
+    from panogrf_b200.image_encoder import ResUNetLight
+    torch.manual_seed(1)
+    ienc = ResUNetLight({}, 3, [1, 2, 6, 4], 32, inplanes=16, use_wrap_padding=True).to(dev)
+    imgs = torch.rand(2, 3, 512, 1024, device=dev)
+    ms = _median_ms(torch, flush, lambda: ienc(imgs), n=5)
+    res["image_encoder_2x3x512x1024"] = {"ms": ms, "note": "ResUNetLight(3, [1,2,6,4], 32, inplanes=16): 27 tensor-core convolutions + 30 "
+                                                           "instance norms; bf16 activations"}
+    del ienc, imgs
     # equirect -> cubemap: 3 panoramas 512x1024x3 -> 256-pixel faces
     conv = pe2c.Equirec2Cube(512, 1024, 256)
     pano = torch.rand(3, 512, 1024, 3, device=dev)

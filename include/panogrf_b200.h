@@ -345,6 +345,17 @@ PGRF_API int pgrf_feats_to_bf16_cl(const float* img, int Ci, int hi, int wi, con
                                    void* stream);
 PGRF_API int pgrf_instnorm_relu_fwd(const void* x, int N, int HW, int C, const float* gamma, const float* beta, float eps, double* stats_ws,
                                     void* y, void* stream);
+/* Parts of the image encoder ResUNetLight (network/ops.py:126-455): pgrf_instnorm_act_fwd = act(InstanceNorm2d(x) [+ res]) with act
+ * 0 none / 1 ReLU / 2 ELU (BasicBlock: relu(bn2(conv2) + identity); conv module: elu(bn(conv))), C up to 256;
+ * pgrf_patch7x7_s2_fwd = the 7x7xCin input patch (WrapPadding(3) or zeros, stride 2) of every output pixel of conv1 as a bf16
+ * channels-last row (k = c*49 + ky*7 + kx, padded to Kpad), which turns the 7x7 convolution into a pointwise GEMM;
+ * pgrf_subsample2_fwd = y[yo][xo] = x[2yo][2xo] (stride 2 of a stride-1 result / input of a 1x1 stride-2 convolution);
+ * pgrf_upsample2d2_ac_fwd = F.interpolate(scale_factor=2, 'bilinear', align_corners=True) (upconv).  All on bf16 channels-last. */
+PGRF_API int pgrf_instnorm_act_fwd(const void* x, int N, int HW, int C, const float* gamma, const float* beta, float eps, double* stats_ws,
+                                   const void* res, int act, void* y, void* stream);
+PGRF_API int pgrf_patch7x7_s2_fwd(const float* x, int N, int Cin, int H, int W, int Kpad, int wrap, void* out, void* stream);
+PGRF_API int pgrf_subsample2_fwd(const void* x, int N, int h, int w, int C, void* y, void* stream);
+PGRF_API int pgrf_upsample2d2_ac_fwd(const void* x, int N, int h, int w, int C, void* y, void* stream);
 /* A 3x3x3 convolution with ONE output channel over many input channels (the 128 -> 1 head of the last decoder) in two steps that read
  * every voxel's channels once instead of once per tap row: pgrf_conv3d_pointwise_fwd = 1x1x1 convolution through the tensor-core
  * pipeline (only the centre tap of the packed weights is walked; here with the 27 taps as output channels, fp32 planar

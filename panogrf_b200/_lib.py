@@ -165,6 +165,10 @@ SIGNATURES.update({
     "pgrf_conv3d_ex_fwd": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, ctypes.c_longlong, _P, _I, _P]),
     "pgrf_feats_to_bf16_cl": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
     "pgrf_instnorm_relu_fwd": (_I, [_P, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
+    "pgrf_instnorm_act_fwd": (_I, [_P, _I, _I, _I, _P, _P, _F, _P, _P, _I, _P, _P]),
+    "pgrf_patch7x7_s2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "pgrf_subsample2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "pgrf_upsample2d2_ac_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "pgrf_conv3d_pointwise_fwd": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pgrf_conv3d_tapsum_fwd": (_I, [_P, _F, _I, _I, _I, _I, _I, _P, _P]),
     "pgrf_conv3d_scalar_fwd": (_I, [_P, _P, _F, _I, _I, _I, _I, _I, _P, _P]),

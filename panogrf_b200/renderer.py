@@ -10,8 +10,9 @@ kernels per pass (csrc/render_kernels.cu) reached through the C ABI.
 The per-call CNN encoders (SURVEY.md §8f "next"): `render()` takes `ref_imgs_info['img_feats']` and the already
 vis-encoded `ref_imgs_info['ray_feats']`, or — when `ref_imgs_info` has no `img_feats` — runs the attached encoders like
 network/renderer.py:639-642: `net.vis_encoder = panogrf_b200.vis_encoder.DefaultVisEncoder(cfg)` is the tensor-core drop-in
-(its parameters then appear as `vis_encoder.*`, the reference's names); `image_encoder` (ResUNetLight) and `init_net` stay
-user-supplied callables.
+(its parameters then appear as `vis_encoder.*`, the reference's names), `net.image_encoder =
+panogrf_b200.image_encoder.ResUNetLight(cfg, 3, [1, 2, 6, 4], 32, inplanes=16, use_wrap_padding=...)` the image encoder;
+`init_net` (mono / MVS depth networks) stays a user-supplied callable.
 Only the eval path (`is_train=False`, deterministic sampling, no autograd) is implemented.
 """
 import ctypes

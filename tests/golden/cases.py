@@ -370,3 +370,17 @@ def make_initconv_inputs(name):
     _, n, (h, w) = INITCONV_CASES[name]
     g = torch.Generator().manual_seed(600 + sorted(INITCONV_CASES).index(name))
     return torch.randn(n, 32, h, w, generator=g), 0.5 + 9.0 * torch.rand(n, 1, h, w, generator=g)
+
+
+# image encoder ResUNetLight (network/ops.py:235-455, built as in network/renderer.py:106)
+RESUNET_CASES = {
+    # name: (use_wrap_padding, n views, (H, W)); H, W multiples of 16
+    "resunet_wrap": (True, 2, (32, 64)),
+    "resunet_zero": (False, 1, (48, 32)),
+}
+
+
+def make_resunet_input(name):
+    _, n, (h, w) = RESUNET_CASES[name]
+    g = torch.Generator().manual_seed(700 + sorted(RESUNET_CASES).index(name))
+    return torch.rand(n, 3, h, w, generator=g)
