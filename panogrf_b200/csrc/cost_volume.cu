@@ -454,7 +454,7 @@ static int launch_c(const CvParams& p, int layout, cudaStream_t st) {
 
 using namespace pgrf;
 
-namespace pgrf { extern int g_mlp_wait_mode; extern int g_rays_tc; extern int g_pg_variant; extern int g_pg_grid; extern int g_conv_stages; extern int g_conv_row; extern int g_conv_splits; extern int g_conv_kc; extern int g_conv_smem_kb; extern int g_conv_persist; extern int g_conv_persist_kb; }
+namespace pgrf { extern int g_mlp_wait_mode; extern int g_rays_tc; extern int g_pg_variant; extern int g_pg_grid; extern int g_conv_stages; extern int g_conv_row; extern int g_conv_splits; extern int g_conv_kc; extern int g_conv_smem_kb; extern int g_conv_persist; extern int g_conv_persist_kb; extern int g_cv_bwd_variant; extern int g_cv_bwd_run; extern int g_cv_bwd_chunks; extern int g_cv_bwd_nored; extern int g_cv_bwd_minb; extern int g_dg_prefilter; extern int g_dg_regsort; }
 extern "C" int pgrf_debug_set(const char* key, int value) {
   if (!strcmp(key, "mlp_wait_mode")) { pgrf::g_mlp_wait_mode = value; return PGRF_OK; }
   if (!strcmp(key, "rays_tc")) { pgrf::g_rays_tc = value; return PGRF_OK; }
@@ -467,6 +467,13 @@ extern "C" int pgrf_debug_set(const char* key, int value) {
   if (!strcmp(key, "conv_persist_kb")) { pgrf::g_conv_persist_kb = value; return PGRF_OK; }
   if (!strcmp(key, "conv_splits")) { pgrf::g_conv_splits = value; return PGRF_OK; }
   if (!strcmp(key, "conv_row")) { pgrf::g_conv_row = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_bwd_variant")) { pgrf::g_cv_bwd_variant = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_bwd_minb")) { pgrf::g_cv_bwd_minb = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_bwd_nored")) { pgrf::g_cv_bwd_nored = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_bwd_chunks")) { pgrf::g_cv_bwd_chunks = value; return PGRF_OK; }
+  if (!strcmp(key, "cv_bwd_run")) { pgrf::g_cv_bwd_run = value; return PGRF_OK; }
+  if (!strcmp(key, "dg_regsort")) { pgrf::g_dg_regsort = value; return PGRF_OK; }
+  if (!strcmp(key, "dg_prefilter")) { pgrf::g_dg_prefilter = value; return PGRF_OK; }
   if (!strcmp(key, "cv_jb")) { g_cv_jb = value; return PGRF_OK; }
   if (!strcmp(key, "cv_dchunk")) { g_cv_dchunk = value; return PGRF_OK; }
   if (!strcmp(key, "cv_minb")) { g_cv_minb = value; return PGRF_OK; }

@@ -14,6 +14,10 @@ constexpr int kDgWarps = 4;                // rays per CTA (one warp each)
 constexpr int kDgThreads = 32 * kDgWarps;
 constexpr int kDgMaxCand = 4096;
 constexpr int kDgMaxOut = 512;
+constexpr int kDgQueue = 256;             // (candidate, view) pairs waiting for the exact evaluation, per warp
+
+int g_dg_regsort = 1;     // 0 = final sorts in shared memory for every size (debug knob dg_regsort)
+int g_dg_prefilter = 1;   // 0 = exact projection for every (candidate, view) pair (debug knob dg_prefilter)
 
 __device__ __forceinline__ float tap1(const float* __restrict__ m, const Footprint& f, int fw) {
   const float nw = __ldg(m + f.off), ne = __ldg(m + f.off + f.dx);
@@ -38,6 +42,91 @@ __device__ __forceinline__ float surface_likelihood(const pgrf_diner_args& a, fl
   return 0.5f * fabsf(erff(x1) - erff(x0));
 }
 
+// ---- conservative pre-filter of phase 1 (m3d convention) --------------------------------------------------------------------
+// A (candidate, view) pair contributes only when |mu - pd| < depth_diff_max, mu = the bilinear prior depth at the projected
+// pixel.  The exact projection (atan2f / acosf / IEEE divisions, ~380 instructions) is what the oracle is compared with bit for
+// bit, and it is needed for the handful of candidates next to the prior surface only.  The filter projects with polynomial
+// atan / acos (|error| < 2e-6 rad, checked in tests/test_diner_gpu.py through the bit-exact results) and is SOUND: when the
+// approximate map coordinate is further than `eps` (4x the error bound + the fp32 rounding of the coordinate chain) from a
+// texel boundary, the exact footprint covers the same four texels, the exact mu is a convex combination of them, and
+// pd outside [min - thr, max + thr] (with slack for rounding) proves the pair contributes 0.  Everything else — next to a
+// texel boundary, next to the prior surface, NaNs — is queued and evaluated exactly.
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+struct DgFilter {
+  float sx, bx, sy, by;        // angle -> map coordinate
+  float eps_x, eps_y, eps_ys;  // safety margins in texels (eps_ys scales with 1/sin(phi): conditioning of acos)
+  float xmax, ymax;
+};
+__device__ __forceinline__ DgFilter dg_filter(const pgrf_diner_args& a) {
+  DgFilter f;
+  const bool align = (a.map_h == a.img_h && a.map_w == a.img_w);
+  const float fw = (float)a.map_w, fh = (float)a.map_h;
+  f.sx = (align ? fw - 1.f : fw) * (1.f / PGRF_TWO_PI_F);
+  f.sy = (align ? fh - 1.f : fh) * (1.f / PGRF_PI_F);
+  f.bx = f.by = align ? 0.f : -0.5f;
+  f.eps_x = fw * 2.5e-6f;
+  f.eps_y = fh * 3.6e-6f;
+  f.eps_ys = fh * (8e-7f / PGRF_PI_F);
+  f.xmax = fw - 1.f;
+  f.ymax = fh - 1.f;
+  return f;
+}
+// c = camera-frame point (approximate: A + B t), dpos = bound of its distance to the exactly computed point
+__device__ __forceinline__ bool dg_certainly_far(const DgFilter& f, const float* __restrict__ dmap, int fw, float thr, float c0, float c1,
+                                                 float c2, float dpos) {
+  const float r2 = c0 * c0 + c1 * c1 + c2 * c2;
+  const float rpd = fast_rsqrt(r2);                 // r2 == 0 -> NaN below -> queued
+  const float pd = r2 * rpd;
+  // theta = atan2(c2, c0) + pi/2 wrapped to [0, 2pi)
+  const float ax = fabsf(c0), az = fabsf(c2);
+  const float rmx = fast_rcp(fmaxf(ax, az));
+  const float q = fminf(ax, az) * rmx;
+  const float s = q * q;
+  float t = fmaf(s, 0.00782548263669014f, -0.03689862787723541f);
+  t = fmaf(t, s, 0.08374155312776566f);
+  t = fmaf(t, s, -0.13480405509471893f);
+  t = fmaf(t, s, 0.19879871606826782f);
+  t = fmaf(t, s, -0.3332637548446655f);
+  t = fmaf(t, s, 0.9999993443489075f);
+  t *= q;
+  if (az > ax) t = PGRF_HALF_PI_F - t;
+  if (c0 < 0.f) t = PGRF_PI_F - t;
+  if (c2 < 0.f) t = -t;
+  t += PGRF_HALF_PI_F;
+  if (t < 0.f) t += PGRF_TWO_PI_F;
+  // phi = acos(c1 / (pd + 1e-5))
+  const float xq = c1 * fast_rcp(pd + 1e-5f);
+  const float aq = fabsf(xq), om = 1.f - aq;
+  float ph = fmaf(aq, 0.002251368248835206f, -0.011012386530637741f);
+  ph = fmaf(ph, aq, 0.02674933150410652f);
+  ph = fmaf(ph, aq, -0.048724401742219925f);
+  ph = fmaf(ph, aq, 0.08873733133077621f);
+  ph = fmaf(ph, aq, -0.21458369493484497f);
+  ph = fmaf(ph, aq, 1.5707961320877075f);
+  const float rs = fast_rsqrt(om);                 // om <= 0 -> inf / NaN: the margin below is not finite and the pair is queued
+  ph *= om * rs;
+  if (xq < 0.f) ph = PGRF_PI_F - ph;
+  float ix = fmaf(t, f.sx, f.bx), iy = fmaf(ph, f.sy, f.by);
+  ix = fminf(fmaxf(ix, 0.f), f.xmax);
+  iy = fminf(fmaxf(iy, 0.f), f.ymax);
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  const float tx = ix - x0, ty = iy - y0;
+  // margins: approximation + rounding (constant part), position uncertainty dpos seen under the angle's lever arm,
+  // conditioning of acos (1 / sin(phi) = rs * rsqrt(1 + |x|))
+  const float ex = fmaf(f.sx * dpos, rmx, f.eps_x);
+  const float ey = fmaf(fmaf(2.f * f.sy * dpos, rpd, f.eps_ys), rs * fast_rsqrt(1.f + aq), f.eps_y);
+  if (!(fminf(fminf(tx, 1.f - tx) - ex, fminf(ty, 1.f - ty) - ey) > 0.f)) return false;   // also catches NaN
+  const int idx = (int)y0 * fw + (int)x0;      // tx, ty > 0 here: the east / south neighbours are inside the map
+  const float nw = __ldg(dmap + idx), ne = __ldg(dmap + idx + 1), sw = __ldg(dmap + idx + fw), se = __ldg(dmap + idx + fw + 1);
+  const float lo = fminf(fminf(nw, ne), fminf(sw, se)), hi = fmaxf(fmaxf(nw, ne), fmaxf(sw, se));
+  const float slack = fmaf(1e-5f, pd + 2.f * fmaxf(fabsf(lo), fabsf(hi)), fmaf(2.f, dpos, thr * 1.00001f));   // thr + rounding slack
+  return (pd - hi > slack) || (lo - pd > slack);      // false on NaN texels
+}
+
 template <typename T, typename Less>
 __device__ __forceinline__ void bitonic_sort(T* a, int n, Less less, int lane) {   // n = power of two, one warp, `a` in shared memory
   for (int k = 2; k <= n; k <<= 1)
@@ -54,6 +143,38 @@ __device__ __forceinline__ void bitonic_sort(T* a, int n, Less less, int lane) {
     }
 }
 
+// Ascending bitonic sort of 32*E floats held one column per lane (element index = r*32 + lane): compare-exchange partners
+// 32 or more apart live in the same lane, closer ones are one shuffle away.  Same exchange rule as bitonic_sort above.
+template <int E>
+__device__ __forceinline__ void warp_sort_regs(float (&x)[E], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          if ((r ^ jr) > r) {
+            const bool up = (((r << 5) | lane) & k) == 0;
+            const float lo = x[r], hi = x[r ^ jr];
+            if ((hi < lo) == up) { x[r] = hi; x[r ^ jr] = lo; }
+          }
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const bool up = (((r << 5) | lane) & k) == 0;
+          const float mine = x[r], other = __shfl_xor_sync(0xffffffffu, mine, j);
+          const bool take = lower ? ((other < mine) == up) : ((mine < other) == up);
+          x[r] = take ? other : mine;
+        }
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -61,7 +182,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
-__global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_diner_args a, int nc_pad, int nc_pow2) {
+// E > 0: the two final sorts run in registers (32*E >= n_samples + n_uniform slots); E == 0: in shared memory
+template <int E>
+__global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_diner_args a, int nc_pad, int nc_pow2, int g_prefilter_on) {
   extern __shared__ __align__(16) unsigned char dsm[];
   const int tid = threadIdx.x & 31, warp = threadIdx.x >> 5;                             // tid = lane: the warp owns the ray
   const int nc = a.n_candidates, ns = a.n_samples, ng = a.n_gaussian, nu = a.n_uniform;
@@ -70,11 +193,14 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
   const int out_pow2 = next_pow2(n_out), ns_pow2 = next_pow2(ns);
   const bool from_dict = a.prj_mu != nullptr;
   // per-warp shared memory: keys [nc_pow2] | lik (later the opacity weights, in place) [nc_pad] | z [out_pow2]
-  const size_t warp_bytes = (size_t)nc_pow2 * 8 + (size_t)nc_pad * 4 + (size_t)out_pow2 * 4;
+  const size_t warp_bytes = (size_t)nc_pow2 * 8 + (size_t)nc_pad * 4 + (size_t)out_pow2 * 4 + kDgQueue * 4;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm + warp * warp_bytes);
   float* lik = reinterpret_cast<float*>(keys + nc_pow2);
   float* opq = lik;
   float* z = lik + nc_pad;
+  int* queue = reinterpret_cast<int*>(z + out_pow2);
+  const bool prefilter = !from_dict && a.dataset == PGRF_DS_M3D && g_prefilter_on;
+  const DgFilter flt = dg_filter(a);
 
   for (long long ray = (long long)blockIdx.x * kDgWarps + warp; ray < a.rn; ray += (long long)gridDim.x * kDgWarps) {
     int count = 0;                                                                       // survivors so far (warp-uniform)
@@ -94,6 +220,91 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
       u0 = r0 / rn; u1 = r1 / rn; u2 = r2 / rn;             // = -que_dir (original_depth_guided_sample.py:112-114)
     }
     const size_t map_px = (size_t)a.map_h * a.map_w;
+    // exact likelihood of candidate i in view v (the code path the oracle is compared with)
+    auto exact_lik = [&](int i, int v) -> float {
+      const float t = __ldg(cand + i);
+      const float p0 = o0 + r0 * t, p1 = o1 + r1 * t, p2 = o2 + r2 * t;
+      const float* w = a.ref_w2c + 12 * v;
+      const float pc0 = w[0] * p0 + w[1] * p1 + w[2] * p2 + w[3];
+      const float pc1 = w[4] * p0 + w[5] * p1 + w[6] * p2 + w[7];
+      const float pc2 = w[8] * p0 + w[9] * p1 + w[10] * p2 + w[11];
+      float pd, px, py;
+      cam_to_equi(a.dataset, pc0, pc1, pc2, a.H, a.W, pd, px, py);
+      const Footprint f = border_footprint(px, py, a.img_h, a.img_w, a.map_h, a.map_w);
+      const float mu = tap1(a.mvs_depth + v * map_px, f, a.map_w);
+      if (!(fabsf(mu - pd) < a.depth_diff_max)) return 0.f;            // the common case: far from the prior surface
+      const float uncert = tap1(a.mvs_uncert + v * map_px, f, a.map_w);
+      float cosv = 0.f;
+      if (a.include_norm) {
+        const float d0 = w[0] * u0 + w[1] * u1 + w[2] * u2;
+        const float d1 = w[4] * u0 + w[5] * u1 + w[6] * u2;
+        const float d2 = w[8] * u0 + w[9] * u1 + w[10] * u2;
+        const float* nm = a.mvs_normal + (size_t)v * 3 * map_px;
+        cosv = d0 * tap1(nm, f, a.map_w) + d1 * tap1(nm + map_px, f, a.map_w) + d2 * tap1(nm + 2 * map_px, f, a.map_w);
+      }
+      return surface_likelihood(a, mu, uncert, pd, cosv);
+    };
+    if (prefilter) {
+      // ---- phase 1 (filtered): reject with the approximate projection, queue the rest, evaluate the queue exactly
+      for (int i = tid; i < nc; i += 32) lik[i] = 0.f;
+      int n_q = 0;                                                                        // warp-uniform
+      auto drain = [&]() {
+        __syncwarp();
+        for (int e = tid; e < n_q; e += 32) {
+          const int code = queue[e];
+          const float l = exact_lik(code & 0xFFFF, code >> 16);
+          if (l > 0.f) atomicMax(reinterpret_cast<unsigned*>(lik) + (code & 0xFFFF), __float_as_uint(l));   // l > 0: bit order = value order
+        }
+        __syncwarp();
+        n_q = 0;
+      };
+      for (int v = 0; v < a.rfn; ++v) {
+        // camera-frame point of candidate depth t: (W o + T) + (W r) t, with a bound of its distance to the exact evaluation
+        // (8 ulp of the largest intermediate magnitude of either evaluation order)
+        const float* w = a.ref_w2c + 12 * v;
+        const float A0 = w[0] * o0 + w[1] * o1 + w[2] * o2 + w[3], B0 = w[0] * r0 + w[1] * r1 + w[2] * r2;
+        const float A1 = w[4] * o0 + w[5] * o1 + w[6] * o2 + w[7], B1 = w[4] * r0 + w[5] * r1 + w[6] * r2;
+        const float A2 = w[8] * o0 + w[9] * o1 + w[10] * o2 + w[11], B2 = w[8] * r0 + w[9] * r1 + w[10] * r2;
+        const float on = fabsf(o0) + fabsf(o1) + fabsf(o2), rnm = fabsf(r0) + fabsf(r1) + fabsf(r2);
+        float magA = 0.f, magB = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float wr = fmaxf(fmaxf(fabsf(w[4 * k]), fabsf(w[4 * k + 1])), fabsf(w[4 * k + 2]));
+          magA = fmaxf(magA, wr * on + fabsf(w[4 * k + 3]));
+          magB = fmaxf(magB, wr * rnm);
+        }
+        magA *= 1e-6f; magB *= 1e-6f;
+        const float* dmap = a.mvs_depth + v * map_px;
+        const float* cp = cand + tid;
+        for (int i0 = 0; i0 < nc; i0 += 32, cp += 32) {
+          const int i = i0 + tid;
+          bool need = false;
+          if (i < nc) {
+            const float t = __ldg(cp);
+            need = !dg_certainly_far(flt, dmap, a.map_w, a.depth_diff_max, fmaf(B0, t, A0), fmaf(B1, t, A1), fmaf(B2, t, A2),
+                                     fmaf(magB, fabsf(t), magA));
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, need);
+          if (m) {
+            if (n_q + __popc(m) > kDgQueue) drain();
+            if (need) queue[n_q + __popc(m & ((1u << tid) - 1u))] = i | (v << 16);
+            n_q += __popc(m);
+          }
+        }
+      }
+      drain();
+      for (int i0 = 0; i0 < nc; i0 += 32) {
+        const int i = i0 + tid;
+        const float best = i < nc ? lik[i] : 0.f;
+        if (i < nc && a.likelihood) a.likelihood[(size_t)ray * nc + i] = best;
+        const unsigned alive = __ballot_sync(0xffffffffu, best > 0.f);
+        if (best > 0.f) {
+          const int pos = count + __popc(alive & ((1u << tid) - 1u));
+          keys[pos] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)i);
+        }
+        count += __popc(alive);
+      }
+    } else
     // ---- phase 1: likelihood of every candidate, max over views; survivors are compacted as sortable keys
     for (int i0 = 0; i0 < nc; i0 += 32) {
       const int i = i0 + tid;
@@ -116,29 +327,7 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
           best = fmaxf(best, surface_likelihood(a, __ldg(a.prj_mu + row), __ldg(a.prj_uncert + row), __ldg(a.prj_depth + row), cosv));
         }
       } else {
-        const float t = __ldg(cand + i);
-        const float p0 = o0 + r0 * t, p1 = o1 + r1 * t, p2 = o2 + r2 * t;
-        for (int v = 0; v < a.rfn; ++v) {
-          const float* w = a.ref_w2c + 12 * v;
-          const float pc0 = w[0] * p0 + w[1] * p1 + w[2] * p2 + w[3];
-          const float pc1 = w[4] * p0 + w[5] * p1 + w[6] * p2 + w[7];
-          const float pc2 = w[8] * p0 + w[9] * p1 + w[10] * p2 + w[11];
-          float pd, px, py;
-          cam_to_equi(a.dataset, pc0, pc1, pc2, a.H, a.W, pd, px, py);
-          const Footprint f = border_footprint(px, py, a.img_h, a.img_w, a.map_h, a.map_w);
-          const float mu = tap1(a.mvs_depth + v * map_px, f, a.map_w);
-          if (!(fabsf(mu - pd) < a.depth_diff_max)) continue;            // the common case: far from the prior surface (view loop)
-          const float uncert = tap1(a.mvs_uncert + v * map_px, f, a.map_w);
-          float cosv = 0.f;
-          if (a.include_norm) {
-            const float d0 = w[0] * u0 + w[1] * u1 + w[2] * u2;
-            const float d1 = w[4] * u0 + w[5] * u1 + w[6] * u2;
-            const float d2 = w[8] * u0 + w[9] * u1 + w[10] * u2;
-            const float* nm = a.mvs_normal + (size_t)v * 3 * map_px;
-            cosv = d0 * tap1(nm, f, a.map_w) + d1 * tap1(nm + map_px, f, a.map_w) + d2 * tap1(nm + 2 * map_px, f, a.map_w);
-          }
-          best = fmaxf(best, surface_likelihood(a, mu, uncert, pd, cosv));
-        }
+        for (int v = 0; v < a.rfn; ++v) best = fmaxf(best, exact_lik(i, v));
       }
       lik[i] = best;
       if (a.likelihood) a.likelihood[(size_t)ray * nc + i] = best;
@@ -188,30 +377,61 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
       g_on = S != 0.f;
       if (g_on) {
         part = 0.f;
-        for (int i = tid; i < nc; i += 32) part += __ldg(cand + i) * (opq[i] / S);
+        // entries with zero opacity add +-0 to a partial sum: skipping them is bit-identical and saves the division
+        for (int i = tid; i < nc; i += 32) { const float o = opq[i]; if (o != 0.f) part += __ldg(cand + i) * (o / S); }
         g_mean = warp_sum(part);
         part = 0.f;
         for (int i = tid; i < nc; i += 32) {
+          const float o = opq[i];
+          if (o == 0.f) continue;
           const float d = __ldg(cand + i) - g_mean;
-          part += d * d * (opq[i] / S);
+          part += d * d * (o / S);
         }
         g_std = sqrtf(warp_sum(part));
       }
     }
     // ---- phase 4: slots = [most likely candidates | Gaussian samples], 0 = empty
     const int n_sel = count < keep ? count : keep;
-    for (int s = tid; s < ns_pow2; s += 32) {
-      float v = __int_as_float(0x7f800000);
-      if (s < n_sel) {
-        const unsigned idx = 0xFFFFFFFFu - (unsigned)(keys[s] & 0xFFFFFFFFull);
-        v = __ldg(cand + idx);
-      } else if (s < keep) {
-        v = 0.f;
-      } else if (s < ns) {
-        v = g_on ? __fadd_rn(__fmul_rn(__ldg(a.gauss + ray * ng + (s - keep)), g_std), g_mean) : 0.f;
+    auto slot_value = [&](int s) -> float {
+      if (s < n_sel) return __ldg(cand + (0xFFFFFFFFu - (unsigned)(keys[s] & 0xFFFFFFFFull)));
+      if (s < keep) return 0.f;
+      if (s < ns) return g_on ? __fadd_rn(__fmul_rn(__ldg(a.gauss + ray * ng + (s - keep)), g_std), g_mean) : 0.f;
+      return __int_as_float(0x7f800000);
+    };
+    if constexpr (E > 0) {
+      float x[E];
+#pragma unroll
+      for (int r = 0; r < E; ++r) x[r] = slot_value(r * 32 + tid);
+      warp_sort_regs<E>(x, tid);
+      // ---- fill_up_uniform_samples (original_depth_guided_sample.py:333-366)
+      int mine = 0;
+#pragma unroll
+      for (int r = 0; r < E; ++r) mine += (r * 32 + tid < ns && x[r] == 0.f) ? 1 : 0;
+      const float n_miss_f = warp_sum((float)mine);
+      if (n_miss_f > 0.f) {
+        const float step = (a.max_depth - a.min_depth) / n_miss_f;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const int s = r * 32 + tid;
+          if (s < ns && x[r] == 0.f) {
+            float zf = __fadd_rn(a.min_depth, __fmul_rn((float)s, step));
+            x[r] = __fadd_rn(zf, __fmul_rn(__ldg(a.fill_rand + ray * ns + s), step));
+          }
+        }
       }
-      z[s] = v;
-    }
+      // ---- optional uniform samples (renderer.py:346-349), final sort
+#pragma unroll
+      for (int r = 0; r < E; ++r) {
+        const int s = r * 32 + tid;
+        if (s >= ns) x[r] = (s < n_out) ? __ldg(a.uniform_depth + (s - ns)) : __int_as_float(0x7f800000);
+      }
+      warp_sort_regs<E>(x, tid);
+#pragma unroll
+      for (int r = 0; r < E; ++r)
+        if (r * 32 + tid < n_out) a.out_depth[ray * n_out + r * 32 + tid] = x[r];
+      __syncwarp();
+    } else {
+    for (int s = tid; s < ns_pow2; s += 32) z[s] = slot_value(s);
     __syncwarp();
     bitonic_sort(z, ns_pow2, [](float x, float y) { return x < y; }, tid);
     // ---- fill_up_uniform_samples (original_depth_guided_sample.py:333-366)
@@ -234,6 +454,7 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
     bitonic_sort(z, out_pow2, [](float x, float y) { return x < y; }, tid);
     for (int s = tid; s < n_out; s += 32) a.out_depth[ray * n_out + s] = z[s];
     __syncwarp();
+    }
   }
 }
 
@@ -347,12 +568,21 @@ extern "C" int pgrf_depth_guided_sample_fwd(const pgrf_diner_args* args, void* s
   const int nc_pad = (a.n_candidates + 3) & ~3;
   int nc_pow2 = 1; while (nc_pow2 < a.n_candidates) nc_pow2 <<= 1;
   int out_pow2 = 1; while (out_pow2 < a.n_samples + a.n_uniform) out_pow2 <<= 1;
-  const size_t smem = kDgWarps * ((size_t)nc_pow2 * 8 + (size_t)nc_pad * 4 + (size_t)out_pow2 * 4);
+  const size_t smem = kDgWarps * ((size_t)nc_pow2 * 8 + (size_t)nc_pad * 4 + (size_t)out_pow2 * 4 + kDgQueue * 4);
   PGRF_REQUIRE(smem <= 227 * 1024, "depth_guided_sample: %zu bytes of shared memory", smem);
-  if (smem > 48 * 1024) PGRF_CUDA(cudaFuncSetAttribute(depth_guided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long max_grid = 148LL * 16, want = (a.rn + kDgWarps - 1) / kDgWarps;
   const int grid = (int)(want < max_grid ? want : max_grid);
-  depth_guided_kernel<<<grid, kDgThreads, smem, (cudaStream_t)stream>>>(a, nc_pad, nc_pow2);
+  const int E = (g_dg_regsort && out_pow2 <= 128) ? (out_pow2 <= 32 ? 1 : out_pow2 / 32) : 0;
+#define PGRF_DG_LAUNCH(EE)                                                                                                            \
+  do {                                                                                                                                \
+    if (smem > 48 * 1024) PGRF_CUDA(cudaFuncSetAttribute(depth_guided_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    depth_guided_kernel<EE><<<grid, kDgThreads, smem, (cudaStream_t)stream>>>(a, nc_pad, nc_pow2, g_dg_prefilter);                     \
+  } while (0)
+  if (E == 1) PGRF_DG_LAUNCH(1);
+  else if (E == 2) PGRF_DG_LAUNCH(2);
+  else if (E == 4) PGRF_DG_LAUNCH(4);
+  else PGRF_DG_LAUNCH(0);
+#undef PGRF_DG_LAUNCH
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;

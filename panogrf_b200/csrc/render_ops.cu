@@ -57,9 +57,12 @@ __device__ __forceinline__ float4 blend4(const float4* __restrict__ base, int sx
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-template <bool PACKED, int UNR>
+// STAGE: the 12-byte-per-row outputs (unit direction, colour) leave through shared memory as fully coalesced 4-byte stores instead of
+// three stride-12 scalar stores per row (each of those touches three 128-byte lines per warp).
+template <bool PACKED, int UNR, bool STAGE = false>
 __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgParams p) {
   __shared__ PgRec rec[kPgThreads];
+  __shared__ float s_dir[STAGE ? 3 * kPgThreads : 1], s_rgb[STAGE ? 3 * kPgThreads : 1];
   const int tid = threadIdx.x;
   const int kPgPoints = kPgThreads / p.rfn;                // points per tile: all 256 threads own a (view, point) row
   const int rows = kPgPoints * p.rfn;
@@ -88,7 +91,8 @@ __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgPara
         const size_t row = (size_t)v * p.pn + pi;
         __stcs(reinterpret_cast<float2*>(p.out_pix) + row, make_float2(px, py));
         p.out_depth[row] = radius;
-        p.out_dir[3 * row] = -e0 / en; p.out_dir[3 * row + 1] = -e1 / en; p.out_dir[3 * row + 2] = -e2 / en;
+        if (STAGE) { s_dir[3 * tid] = -e0 / en; s_dir[3 * tid + 1] = -e1 / en; s_dir[3 * tid + 2] = -e2 / en; }
+        else { p.out_dir[3 * row] = -e0 / en; p.out_dir[3 * row + 1] = -e1 / en; p.out_dir[3 * row + 2] = -e2 / en; }
         Footprint f = border_footprint(px, py, p.img_h, p.img_w, p.rf_h, p.rf_w);
         r.off_rf = v * p.rf_h * p.rf_w + f.off; r.dxy |= f.dx | (f.dy << 1); r.tx_rf = f.tx; r.ty_rf = f.ty;
         f = border_footprint(px, py, p.img_h, p.img_w, p.if_h, p.if_w);
@@ -98,11 +102,23 @@ __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgPara
         // colours: one 16-byte tap each, done by the row's own thread
         const float4 c = blend4(reinterpret_cast<const float4*>(p.imgs_cl) + r.off_im, (r.dxy >> 4) & 1, ((r.dxy >> 5) & 1) * p.img_w,
                                 r.tx_im, r.ty_im);
-        p.out_rgb[3 * row] = c.x; p.out_rgb[3 * row + 1] = c.y; p.out_rgb[3 * row + 2] = c.z;
+        if (STAGE) { s_rgb[3 * tid] = c.x; s_rgb[3 * tid + 1] = c.y; s_rgb[3 * tid + 2] = c.z; }
+        else { p.out_rgb[3 * row] = c.x; p.out_rgb[3 * row + 1] = c.y; p.out_rgb[3 * row + 2] = c.z; }
       }
       rec[tid] = r;
     }
     __syncthreads();
+    if (STAGE) {
+      const long long left = p.pn - p0;
+      const int n3 = 3 * (int)(left < kPgPoints ? left : kPgPoints);
+      for (int v = 0; v < p.rfn; ++v) {
+        const size_t base = 3 * ((size_t)v * p.pn + p0);
+        for (int j = tid; j < n3; j += kPgThreads) {
+          __stcs(p.out_dir + base + j, s_dir[3 * v * kPgPoints + j]);
+          __stcs(p.out_rgb + base + j, s_rgb[3 * v * kPgPoints + j]);
+        }
+      }
+    }
     // ---- phase 2: lane = (row, float4 channel group): 8 lanes fetch one 128-byte texel line per tap and write one
     //      128-byte output row (coalesced both ways)
 #pragma unroll UNR
@@ -314,7 +330,7 @@ __global__ void __launch_bounds__(256) depth_hypotheses_kernel(const float* __re
 }  // namespace pgrf
 
 using namespace pgrf;
-namespace pgrf { int g_pg_variant = 3; int g_pg_grid = 48; }   // B200 sweep (tools/time_pg_variants.py): 8 gathers in flight per lane, 48 CTAs per SM-slot
+namespace pgrf { int g_pg_variant = 5; int g_pg_grid = 64; }   // B200 sweep (tools/time_pg_variants.py): staged 12-byte outputs, 8 gathers in flight per lane, 64 CTAs per SM-slot
 
 extern "C" int pgrf_project_gather_fwd(const float* pts, long long pn, const float* w2c, int rfn, int dataset, int H, int W,
                                        const float* imgs_cl, int img_h, int img_w, const float* img_feats_cl, int if_h, int if_w,
@@ -339,7 +355,9 @@ extern "C" int pgrf_project_gather_fwd(const float* pts, long long pn, const flo
     case 1: project_gather_kernel<true, 2><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
     case 2: project_gather_kernel<true, 4><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
     case 3: project_gather_kernel<false, 4><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
-    default: project_gather_kernel<false, 8><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
+    case 4: project_gather_kernel<false, 8><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
+    case 5: project_gather_kernel<false, 4, true><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
+    default: project_gather_kernel<true, 4, true><<<grid, kPgThreads, 0, (cudaStream_t)stream>>>(p); break;
   }
   count_launch();
   PGRF_CUDA(cudaGetLastError());

@@ -340,3 +340,29 @@ def test_bf16_channels_last_layout_and_regulariser_pipeline():
     assert torch.equal(y16, y32)
     with pytest.raises(Exception):
         pg.calculate_cost_volume_erp(args, images[..., :8].contiguous(), depths, trans, rots, out_layout="bdhwc_bf16")   # C % 16
+
+
+@pytest.mark.parametrize("C", [32, 64])
+def test_backward_run_merged_variant_agrees(C):
+    """The opt-in run-merged backward kernel (debug knob cv_bwd_variant = 1) against the default kernel: same gradient up to the
+    summation order of the float atomics."""
+    from panogrf_b200 import _lib, spherical_cost_volume as scv
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    B, S, H, W, D = 1, 2, 32, 96, 12                      # W is not a multiple of the CTA tile: ragged runs
+    images = torch.randn(B, S, H, W, C, generator=g).cuda().requires_grad_(True)
+    rots = torch.eye(3).expand(B, S, 3, 3).contiguous().cuda()
+    trans = torch.zeros(B, S, 3)
+    trans[:, 0, 2], trans[:, 1, 0] = 0.4, -0.3
+    depths = torch.linspace(0.3, 8, D).cuda()
+    args = {"dataset_name": "m3d", "contain_dnet": False, "mono_uncertainty": False}
+    out = scv.calculate_cost_volume_erp(args, images, depths, trans.cuda(), rots)
+    gout = torch.randn(out.shape, generator=g).cuda()
+    grads = []
+    try:
+        for variant in (0, 1):
+            lib.pgrf_debug_set(b"cv_bwd_variant", variant)
+            grads.append(torch.autograd.grad(out, images, gout, retain_graph=True)[0])
+    finally:
+        lib.pgrf_debug_set(b"cv_bwd_variant", 0)
+    assert_close(grads[1], grads[0], rtol=1e-4, atol=1e-4 * float(grads[0].abs().max()), what=f"run-merged backward C={C}")

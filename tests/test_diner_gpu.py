@@ -142,3 +142,43 @@ def test_depth2normal_matches_reference(name):
     want = g["normal"]
     assert torch.equal(torch.isnan(got), torch.isnan(want))
     assert float((torch.nan_to_num(got) - torch.nan_to_num(want)).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["smooth", "edges", "noise"])
+def test_prefilter_is_exact(kind):
+    """The conservative pre-filter of phase 1 (approximate projection, csrc/depth_guided.cu:dg_certainly_far) must not change a
+    single bit: likelihoods and placed samples with the filter == without it, on priors with smooth surfaces, depth edges and noise."""
+    from panogrf_b200 import _lib
+    from panogrf_b200.render_ops import depth_guided_placement
+    lib = _lib.load()
+    H, W, rfn, rn = 64, 128, 3, 4096
+    cfg = {"dataset_name": "m3d", "height": H, "width": W, "min_depth": 0.5, "max_depth": 15.0, "n_candidates": 1000,
+           "n_samples": 64, "n_gaussian": 15, "backface_culling": True, "contain_uniform": False}
+    g = torch.Generator().manual_seed(3)
+    idx = torch.randperm(H * W, generator=g)[:rn]
+    coords = torch.stack([idx % W, idx // W], -1).float()[None].cuda()
+    w2c = torch.eye(3, 4)[None].repeat(rfn, 1, 1)
+    w2c[0, 2, 3], w2c[1, 2, 3], w2c[2, 0, 3] = 0.5, -0.5, 0.3
+    yy = torch.linspace(0, 3.14159, H)[:, None]
+    xx = torch.linspace(0, 6.28318, W)[None, :]
+    depth = 3.0 + 1.5 * torch.sin(xx * 2) * torch.sin(yy)
+    if kind == "edges":
+        depth = depth + (xx > 3.0).float() * 2.0 + (yy > 1.2).float() * 0.7
+    if kind == "noise":
+        depth = depth + torch.rand(H, W, generator=g)
+    for map_hw in ((H, W), (H // 2, W // 2)):          # align_corners and half-resolution priors
+        d = torch.nn.functional.interpolate(depth[None, None], size=map_hw, mode="bilinear")[0, 0]
+        ref = {"imgs": torch.zeros(rfn, 3, H, W).cuda(), "w2c": w2c.cuda(), "mvs_depth": d[None, None].repeat(rfn, 1, 1, 1).cuda(),
+               "mvs_uncert": torch.full((rfn, 1, *map_hw), 0.02).cuda(), "mvs_normal": torch.randn(rfn, 3, *map_hw, generator=g).cuda()}
+        que = {"coords": coords, "c2w": torch.eye(3, 4)[None].cuda()}
+        fill, ga = torch.rand(rn, 64, generator=g).cuda(), torch.randn(rn, 15, generator=g).cuda()
+        res = []
+        try:
+            for pre in (0, 1):
+                lib.pgrf_debug_set(b"dg_prefilter", pre)
+                res.append(depth_guided_placement(cfg, que, ref, fill, ga, return_likelihood=True))
+        finally:
+            lib.pgrf_debug_set(b"dg_prefilter", 1)
+        assert int((res[0][1] > 0).sum()) > rn          # the scene does hit the prior surfaces
+        assert torch.equal(res[0][1], res[1][1]), f"{kind} {map_hw}: likelihood changed"
+        assert torch.equal(res[0][0], res[1][0]), f"{kind} {map_hw}: placement changed"

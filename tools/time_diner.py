@@ -21,14 +21,26 @@ ref = {"imgs": torch.zeros(rfn, 3, H, W, device=dev), "w2c": w2c.to(dev),
        "mvs_normal": torch.randn(rfn, 3, H, W, generator=g).to(dev)}
 rn = H * W
 fill = torch.rand(rn, 64, device=dev); ga = torch.randn(rn, 15, device=dev)
-for _ in range(2):
-    z = depth_guided_placement(cfg, que, ref, fill, ga)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-e0.record()
-for _ in range(3):
-    z = depth_guided_placement(cfg, que, ref, fill, ga)
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 3
-print(f"depth_guided_placement {rn} rays x 1000 candidates x {rfn} views: {ms:.2f} ms  ({rn * 1000 * rfn / ms / 1e6:.1f} G candidate-views/s)")
-print("finite", bool(torch.isfinite(z).all()), "sorted", bool((z[..., 1:] >= z[..., :-1]).all()))
+from panogrf_b200 import _lib
+lib = _lib.load()
+# a smooth prior (what an MVS network produces) next to the white-noise one above
+yy = torch.linspace(0, 3.14159, H)[:, None]; xx = torch.linspace(0, 6.28318, W)[None, :]
+smooth = (3.0 + 1.5 * torch.sin(xx * 2) * torch.sin(yy) + (xx > 3.0).float() * 2.0)[None, None].repeat(rfn, 1, 1, 1).to(dev)
+outs = {}
+for label, dmap in (("noise", ref["mvs_depth"]), ("smooth", smooth)):
+    ref2 = dict(ref, mvs_depth=dmap)
+    for pre in (0, 1):
+        lib.pgrf_debug_set(b"dg_prefilter", pre)
+        for _ in range(2):
+            z = depth_guided_placement(cfg, que, ref2, fill, ga)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(3):
+            z = depth_guided_placement(cfg, que, ref2, fill, ga)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        outs[(label, pre)] = z
+        print(f"depth_guided_placement[{label}, prefilter={pre}] {rn} rays x 1000 candidates x {rfn} views: {ms:.2f} ms  ({rn * 1000 * rfn / ms / 1e6:.1f} G candidate-views/s)")
+        print("  finite", bool(torch.isfinite(z).all()), "sorted", bool((z[..., 1:] >= z[..., :-1]).all()))
+    print(f"  [{label}] prefilter on == off bit for bit:", bool(torch.equal(outs[(label, 0)], outs[(label, 1)])))
