@@ -858,7 +858,9 @@ def time_depth_guided(torch, que_d, ref_d):
     ms = e0.elapsed_time(e1) / 3
     return {"workload": f"{rn} rays x 1000 candidates x {RFN} views -> 64 samples/ray (49 likelihood + 15 gaussian, fill-up, sort)",
             "ms": ms, "candidate_views_per_s": rn * 1000.0 * RFN / ms * 1e3,
-            "note": "compute bound (atan2/acos/erf per candidate-view); writes only (rn,64) floats"}
+            "note": "instruction bound: a sound approximate projection rejects candidate-views far from the prior surface, the rest "
+                    "(texel-boundary cases, near-surface candidates) is evaluated with the exact atan2/acos/erf path; white-noise prior "
+                    "(worst case for the filter); writes only (rn,64) floats"}
 
 
 def time_other_configs(torch, pg, dev, flush, peaks, with_oracle):

@@ -119,12 +119,14 @@ __device__ __forceinline__ bool dg_certainly_far(const DgFilter& f, const float*
   // conditioning of acos (1 / sin(phi) = rs * rsqrt(1 + |x|))
   const float ex = fmaf(f.sx * dpos, rmx, f.eps_x);
   const float ey = fmaf(fmaf(2.f * f.sy * dpos, rpd, f.eps_ys), rs * fast_rsqrt(1.f + aq), f.eps_y);
-  if (!(fminf(fminf(tx, 1.f - tx) - ex, fminf(ty, 1.f - ty) - ey) > 0.f)) return false;   // also catches NaN
-  const int idx = (int)y0 * fw + (int)x0;      // tx, ty > 0 here: the east / south neighbours are inside the map
+  const bool inside = fminf(fminf(tx, 1.f - tx) - ex, fminf(ty, 1.f - ty) - ey) > 0.f;   // false on NaN: the pair is queued
+  // branch-free: the four texels are read in any case (indices clamped for the read only), so that two candidates' chains interleave
+  const int xi = min((int)x0, (int)f.xmax - 1), yi = min((int)y0, (int)f.ymax - 1);
+  const int idx = max(yi, 0) * fw + max(xi, 0);
   const float nw = __ldg(dmap + idx), ne = __ldg(dmap + idx + 1), sw = __ldg(dmap + idx + fw), se = __ldg(dmap + idx + fw + 1);
   const float lo = fminf(fminf(nw, ne), fminf(sw, se)), hi = fmaxf(fmaxf(nw, ne), fmaxf(sw, se));
   const float slack = fmaf(1e-5f, pd + 2.f * fmaxf(fabsf(lo), fabsf(hi)), fmaf(2.f, dpos, thr * 1.00001f));   // thr + rounding slack
-  return (pd - hi > slack) || (lo - pd > slack);      // false on NaN texels
+  return inside && ((pd - hi > slack) || (lo - pd > slack));      // false on NaN texels
 }
 
 template <typename T, typename Less>
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
   float* opq = lik;
   float* z = lik + nc_pad;
   int* queue = reinterpret_cast<int*>(z + out_pow2);
-  const bool prefilter = !from_dict && a.dataset == PGRF_DS_M3D && g_prefilter_on;
+  const bool prefilter = !from_dict && a.dataset == PGRF_DS_M3D && g_prefilter_on && a.map_h >= 2 && a.map_w >= 2;
   const DgFilter flt = dg_filter(a);
 
   for (long long ray = (long long)blockIdx.x * kDgWarps + warp; ray < a.rn; ray += (long long)gridDim.x * kDgWarps) {
@@ -275,20 +277,27 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
         }
         magA *= 1e-6f; magB *= 1e-6f;
         const float* dmap = a.mvs_depth + v * map_px;
+        // two candidates per lane and iteration: two independent dependency chains for the scheduler
         const float* cp = cand + tid;
-        for (int i0 = 0; i0 < nc; i0 += 32, cp += 32) {
-          const int i = i0 + tid;
-          bool need = false;
-          if (i < nc) {
-            const float t = __ldg(cp);
-            need = !dg_certainly_far(flt, dmap, a.map_w, a.depth_diff_max, fmaf(B0, t, A0), fmaf(B1, t, A1), fmaf(B2, t, A2),
-                                     fmaf(magB, fabsf(t), magA));
+        for (int i0 = 0; i0 < nc; i0 += 64, cp += 64) {
+          const int ia = i0 + tid, ib = ia + 32;
+          bool need_a = false, need_b = false;
+          {
+            const float ta = ia < nc ? __ldg(cp) : 0.f, tb = ib < nc ? __ldg(cp + 32) : 0.f;
+            const bool far_a = dg_certainly_far(flt, dmap, a.map_w, a.depth_diff_max, fmaf(B0, ta, A0), fmaf(B1, ta, A1), fmaf(B2, ta, A2),
+                                                fmaf(magB, fabsf(ta), magA));
+            const bool far_b = dg_certainly_far(flt, dmap, a.map_w, a.depth_diff_max, fmaf(B0, tb, A0), fmaf(B1, tb, A1), fmaf(B2, tb, A2),
+                                                fmaf(magB, fabsf(tb), magA));
+            need_a = ia < nc && !far_a;
+            need_b = ib < nc && !far_b;
           }
-          const unsigned m = __ballot_sync(0xffffffffu, need);
-          if (m) {
-            if (n_q + __popc(m) > kDgQueue) drain();
-            if (need) queue[n_q + __popc(m & ((1u << tid) - 1u))] = i | (v << 16);
-            n_q += __popc(m);
+          const unsigned ma = __ballot_sync(0xffffffffu, need_a), mb = __ballot_sync(0xffffffffu, need_b);
+          if (ma | mb) {
+            if (n_q + __popc(ma) + __popc(mb) > kDgQueue) drain();
+            if (need_a) queue[n_q + __popc(ma & ((1u << tid) - 1u))] = ia | (v << 16);
+            n_q += __popc(ma);
+            if (need_b) queue[n_q + __popc(mb & ((1u << tid) - 1u))] = ib | (v << 16);
+            n_q += __popc(mb);
           }
         }
       }
