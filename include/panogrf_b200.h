@@ -234,6 +234,14 @@ PGRF_API int pgrf_composite_fwd(const float* density, const float* alpha, const 
 PGRF_API int pgrf_fine_sample_fwd(const float* depth, int depth_ray_stride, const float* hit_prob, const float* u_table,
                                   float near_depth, float far_depth, int inv_mode, int rn, int dn, int fine_dn, int sort_out,
                                   int use_all, float* fine_out, int* inds_out, void* stream);
+/* sample_3sigma + sample_pdf (network/sample_utils.py:6-60, det = True) and its use in fine_render_impl (network/renderer.py:438-470).
+ * select = 1: ft (rn, ft_stride >= 3) rows [marker, low, high]; rays with marker >= min_valid get io[ray] = sort(n samples
+ * [++ coarse_depth[ray] (dn) when coarse_depth != NULL]), the other rows of io (rn, n [+ dn]) are left as they are.
+ * select = 0: ft rows [low, high]; io (rn, n) = the unsorted samples of every ray (the functional form).
+ * t_table (n) = linspace(0,1,n), gauss (n-1) = N(0,1) density at linspace(-3,3,n-1), both built by the host with torch. */
+PGRF_API int pgrf_sample_3sigma_fwd(const float* ft, int ft_stride, float min_valid, const float* t_table, const float* gauss, int n,
+                                    float near_depth, float far_depth, const float* coarse_depth, int coarse_ray_stride, int dn,
+                                    int select, int rn, float* io, void* stream);
 /* depth hypotheses of the MVS net (pipeline3_model.py:723-733,774-815): out (B,n_mono+n_linear,h,w) = per-pixel sorted
  * [clamp(ref_mu + k_sigma[i], min, max)] ++ linear[]; k_sigma and linear ascending (device arrays, computed by the host
  * with the reference's own ops so they are bit-identical). */

@@ -201,6 +201,53 @@ def sample_fine_depth(depth, hit_prob, depth_range, sample_num, use_disp=True, r
     return fine
 
 
+def sample_3sigma_tables(n):
+    """Per-call constants of sample_3sigma (sample_utils.py:7,11-12), built with the reference's own torch ops:
+    t = linspace(0,1,n) (bin positions AND the deterministic u of sample_pdf), g = N(0,1) density at linspace(-3,3,n-1)."""
+    t = torch.linspace(0., 1., steps=n)
+    x = torch.linspace(-3., 3., steps=n - 1)
+    g = 1. / math.sqrt(2 * np.pi) * torch.exp(-0.5 * x.pow(2))
+    return t, g
+
+
+def sample_3sigma(low, high, n, near, far, u=None):
+    """sample_utils.py:6-15 + sample_pdf :18-60 with det=True (u = linspace(0,1,n); pass `u` (R,n) for the random branch).
+    low, high (R,) -> (R,n) depths inside [low, high] clamped to [near, far], Gaussian-weighted bins, unsorted like the reference.
+    Accumulation order stated like sample_fine_depth: sequential left-to-right fp32 for the normaliser and the cdf."""
+    t, g = sample_3sigma_tables(n)
+    step = (high - low) / (n - 1)
+    edges = (low.unsqueeze(-1) * (1. - t) + high.unsqueeze(-1) * t).clamp(near, far)
+    factor = (edges[..., 1:] - edges[..., :-1]) / step.unsqueeze(-1)
+    w = factor * g.unsqueeze(0) + 1e-5
+    pdf = w / seq_cumsum(w)[..., -1:]
+    cdf = seq_cumsum(pdf)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    uu = t.expand(list(cdf.shape[:-1]) + [n]).contiguous() if u is None else u.contiguous()
+    inds = torch.searchsorted(cdf, uu, right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
+    cdf_b, cdf_a = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+    bin_b, bin_a = torch.gather(edges, -1, below), torch.gather(edges, -1, above)
+    denom = cdf_a - cdf_b
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    tt = (uu - cdf_b) / denom
+    return bin_b + tt * (bin_a - bin_b)
+
+
+def fine_depth_with_ft_range(fine_depth, coarse_depth, ft_depth_range, min_depth, max_depth, use_all):
+    """fine_render_impl, renderer.py:438-470 (eval): rays whose ft_depth_range[...,0] >= min_depth take sample_3sigma between
+    ft_depth_range[...,1] and [...,2] instead of the inverse-CDF samples; then the sort (with the coarse depths when use_all).
+    fine_depth, coarse_depth (1,rn,dn); ft_depth_range (1,rn,3)."""
+    valid = ft_depth_range[..., 0] >= min_depth
+    z2 = fine_depth.clone()
+    n = coarse_depth.shape[-1]
+    if bool(valid.any()):
+        z2[valid] = sample_3sigma(ft_depth_range[valid][:, 1], ft_depth_range[valid][:, 2], n, min_depth, max_depth)
+    if use_all:
+        return torch.sort(torch.cat([coarse_depth, z2], -1), -1)[0]
+    return torch.sort(z2, -1)[0]
+
+
 # ------------------------------------------------------------------------------------------------
 # geometry: rays, projection, gathers
 # ------------------------------------------------------------------------------------------------
@@ -524,7 +571,10 @@ def render_rays(cfg, W, que, ref, keep_hit_prob=False, is_perspec=False):
     if cfg.get("use_hierarchical_sampling", False):
         fine = sample_fine_depth(depth, out["hit_prob_nr"], que["depth_range"], cfg.get("fine_depth_sample_num", 64),
                                  cfg["use_disp"])
-        if cfg.get("fine_depth_use_all", False):
+        if que.get("ft_depth_range") is not None:                        # renderer.py:438-456: prior-guided samples for valid rays
+            fdepth = fine_depth_with_ft_range(fine, depth, que["ft_depth_range"], cfg["min_depth"], cfg["max_depth"],
+                                              cfg.get("fine_depth_use_all", False))
+        elif cfg.get("fine_depth_use_all", False):
             fdepth = torch.sort(torch.cat([depth, fine], -1), -1)[0]
         else:
             fdepth = torch.sort(fine, -1)[0]
@@ -553,6 +603,8 @@ def render(cfg, W, que, ref, ray_batch_num=None):
     for r0 in range(0, coords.shape[1], ray_batch_num):
         q = dict(que)
         q["coords"] = coords[:, r0:r0 + ray_batch_num]
+        if que.get("ft_depth_range") is not None:
+            q["ft_depth_range"] = que["ft_depth_range"][:, r0:r0 + ray_batch_num]
         o = render_rays(cfg, W, q, ref)
         for k, v in o.items():
             outs.setdefault(k, []).append(v)

@@ -187,6 +187,7 @@ SIGNATURES.update({
                                       _P, _P, _P, _P, _P, _P, _P]),
     "pgrf_composite_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "pgrf_fine_sample_fwd": (_I, [_P, _I, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "pgrf_sample_3sigma_fwd": (_I, [_P, _I, _F, _P, _P, _I, _F, _F, _P, _I, _I, _I, _I, _P, _P]),
     "pgrf_depth_hypotheses_fwd": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _F, _F, _P, _P]),
     "pgrf_depth_hypotheses2_fwd": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _P, _I, _I, _F, _F, _F, _I, _P, _P]),
     "pgrf_weight_blob_floats": (_I, []),

@@ -252,6 +252,74 @@ __global__ void __launch_bounds__(256) fine_sample_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// sample_3sigma + sample_pdf (network/sample_utils.py:6-60, det = True) and the selection / sort of fine_render_impl
+// (network/renderer.py:438-470): one warp per ray.  Rays whose marker ft[ray][0] >= min_valid get n depths between ft[ray][1] and
+// ft[ray][2] (bin edges clamped to [near, far], bins weighted by a unit Gaussian over +-3 sigma, inverse CDF at u = t_table);
+// the others keep the row they have.  t_table = linspace(0,1,n), gauss = 1/sqrt(2 pi) exp(-x^2/2) at linspace(-3,3,n-1): built by the
+// host with the reference's torch ops.  Accumulation order of the normaliser and the cdf: sequential fp32 (the stated order).
+// io (rn, n [+ dn]): with `coarse` the row becomes sort(coarse depths ++ samples), else sort(samples); `select` = 0 writes the
+// unsorted samples of EVERY ray (the functional drop-in).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_3sigma_kernel(const float* __restrict__ ft, int ft_stride, float min_valid,
+                                                            const float* __restrict__ t_table, const float* __restrict__ gauss, int n,
+                                                            float near_d, float far_d, const float* __restrict__ coarse,
+                                                            int coarse_stride, int dn, int select, int rn, float* __restrict__ io) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = n + (coarse ? dn : 0);
+  float* edges = sm + warp * (2 * n + total);
+  float* cdf = edges + n;
+  float* z = cdf + n;
+  for (long long ray = (long long)blockIdx.x * 8 + warp; ray < rn; ray += (long long)gridDim.x * 8) {
+    const float* f = ft + ray * ft_stride;
+    if (select && !(__ldg(f) >= min_valid)) continue;                       // warp-uniform
+    const float low = __ldg(f + (select ? 1 : 0)), high = __ldg(f + (select ? 2 : 1));
+    const float step = (high - low) / (float)(n - 1);
+    for (int s = lane; s < n; s += 32) {
+      const float t = __ldg(t_table + s);
+      const float e = __fadd_rn(__fmul_rn(low, 1.f - t), __fmul_rn(high, t));
+      edges[s] = fminf(fmaxf(e, near_d), far_d);
+    }
+    __syncwarp();
+    for (int s = lane; s < n - 1; s += 32) cdf[s + 1] = __fadd_rn(__fmul_rn((edges[s + 1] - edges[s]) / step, __ldg(gauss + s)), 1e-5f);
+    __syncwarp();
+    if (lane == 0) {
+      float tot = 0.f;
+      for (int s = 1; s < n; ++s) tot += cdf[s];
+      float c = 0.f;
+      cdf[0] = 0.f;
+      for (int s = 1; s < n; ++s) { c += cdf[s] / tot; cdf[s] = c; }
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+      const float u = __ldg(t_table + k);
+      int lo = 0, hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+      const int below = max(lo - 1, 0), above = min(n - 1, lo);
+      const float cb = cdf[below], ca = cdf[above];
+      float denom = ca - cb;
+      if (denom < 1e-5f) denom = 1.f;
+      const float t = (u - cb) / denom;
+      z[k] = __fadd_rn(edges[below], __fmul_rn(t, edges[above] - edges[below]));
+    }
+    if (coarse) for (int s = lane; s < dn; s += 32) z[n + s] = __ldg(coarse + ray * coarse_stride + s);
+    __syncwarp();
+    float* out = io + ray * total;
+    if (select) {
+      for (int k = lane; k < total; k += 32) {
+        const float x = z[k];
+        int rank = 0;
+        for (int j = 0; j < total; ++j) { const float y = z[j]; rank += (y < x || (y == x && j < k)) ? 1 : 0; }
+        out[rank] = x;
+      }
+    } else {
+      for (int k = lane; k < total; k += 32) out[k] = z[k];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // a5: depth hypotheses (pipeline3_model.py:717-733, 774-815).  thread = pixel.
 //   mono-guided list: clamp(mu + s * k_i, min, max), i < n_mono, with
 //       mode 0  s * k_i = k_table[i]                      ("fixed_sigma": the host passes float32(k_i * fixed_sigma))
@@ -391,6 +459,23 @@ extern "C" int pgrf_fine_sample_fwd(const float* depth, int depth_ray_stride, co
   const int grid = (rn + 7) / 8 < 148 * 8 ? (rn + 7) / 8 : 148 * 8;
   fine_sample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(depth, depth_ray_stride, hit_prob, u_table, near_depth, far_depth,
                                                                inv_mode, rn, dn, fine_dn, sort_out, use_all, fine_out, inds_out);
+  count_launch();
+  PGRF_CUDA(cudaGetLastError());
+  return PGRF_OK;
+}
+
+extern "C" int pgrf_sample_3sigma_fwd(const float* ft, int ft_stride, float min_valid, const float* t_table, const float* gauss, int n,
+                                      float near_depth, float far_depth, const float* coarse_depth, int coarse_ray_stride, int dn,
+                                      int select, int rn, float* io, void* stream) {
+  PGRF_REQUIRE(ft && t_table && gauss && io, "sample_3sigma: null pointer argument");
+  PGRF_REQUIRE(rn >= 1 && n >= 2 && n <= 1024 && dn >= 0 && dn <= 1024 && ft_stride >= (select ? 3 : 2), "sample_3sigma: rn=%d n=%d dn=%d", rn, n, dn);
+  PGRF_REQUIRE(select || !coarse_depth, "sample_3sigma: the coarse depths are merged in selection mode only");
+  const size_t smem = 8 * (size_t)(3 * n + (coarse_depth ? dn : 0)) * sizeof(float);
+  PGRF_REQUIRE(smem <= 200 * 1024, "sample_3sigma: n / dn too large for shared memory");
+  if (smem > 48 * 1024) PGRF_CUDA(cudaFuncSetAttribute(sample_3sigma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (rn + 7) / 8 < 148 * 8 ? (rn + 7) / 8 : 148 * 8;
+  sample_3sigma_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(ft, ft_stride, min_valid, t_table, gauss, n, near_depth, far_depth,
+                                                                 coarse_depth, coarse_ray_stride, dn, select, rn, io);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;

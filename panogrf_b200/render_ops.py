@@ -133,6 +133,31 @@ def sample_fine_depth(args, depth, hit_prob, depth_range, sample_num, random_sam
     return (out, inds.reshape(qn, rn, sample_num).long()) if return_indices else out
 
 
+def sample_3sigma_tables(n, device):
+    """Constants of sample_3sigma (sample_utils.py:7,11-12) with the reference's own torch ops: t = linspace(0,1,n) (bin positions and
+    the deterministic u of sample_pdf), g = unit-Gaussian density at linspace(-3,3,n-1)."""
+    t = torch.linspace(0., 1., steps=n)
+    x = torch.linspace(-3., 3., steps=n - 1)
+    g = 1. / math.sqrt(2 * math.pi) * torch.exp(-0.5 * x.pow(2))
+    return t.to(device), g.to(device)
+
+
+def sample_3sigma(low_3sigma, high_3sigma, N, det, near, far):
+    """network/sample_utils.py:6-15 (+ sample_pdf :18-60), deterministic branch: (R,) x2 -> (R,N) depths, unsorted like the reference."""
+    if not det:
+        raise NotImplementedError("sample_3sigma(det=False) draws torch.rand: not part of the render-time path")
+    _lib.require_cuda(low_3sigma, high_3sigma)
+    lib = _lib.load()
+    lh = torch.stack([_f32(low_3sigma).reshape(-1), _f32(high_3sigma).reshape(-1)], -1).contiguous()
+    t, g = sample_3sigma_tables(int(N), lh.device)
+    out = torch.empty(lh.shape[0], int(N), device=lh.device, dtype=torch.float32)
+    with torch.cuda.device(lh.device):
+        rc = lib.pgrf_sample_3sigma_fwd(_lib.ptr(lh), 2, 0.0, _lib.ptr(t), _lib.ptr(g), int(N), float(near), float(far), None, 0, 0, 0,
+                                        lh.shape[0], _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "pgrf_sample_3sigma_fwd")
+    return out.reshape(*low_3sigma.shape, int(N))
+
+
 def project_points_dict(ref_imgs_info, que_pts, spt_utils, with_img_feats=True):
     """render_ops.py:234-257 (+ get_img_feats, renderer.py:180-188, when `img_feats` is present): que_pts (qn,rn,dn,3)
     -> dict of (rfn,qn,rn,dn,*) tensors: dir, pts, depth, ray_feats, rgb[, img_feats].  `spt_utils` only has to expose

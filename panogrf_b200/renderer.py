@@ -17,6 +17,8 @@ Only the eval path (`is_train=False`, deterministic sampling, no autograd) is im
 """
 import ctypes
 
+import math
+
 import torch
 import torch.nn as nn
 
@@ -613,6 +615,8 @@ class NeuralRayBaseRenderer(nn.Module):
         depth_table = coarse_depth_table(cfg, dn, cfg["use_disp"]).to(dev)
         coarse = {k: v for k, v in _outs.items() if not k.endswith("_fine")}
         fine_depth = self._pass(ctx, coords2, depth_table, 0, False, hier, coarse, _r0, "hit_prob_nr" in coarse)
+        if hier and que_imgs_info.get("ft_depth_range") is not None:
+            self._ft_range_samples(que_imgs_info["ft_depth_range"], depth_table, fine_depth)
         if hier:
             fine = {k[:-5]: v for k, v in _outs.items() if k.endswith("_fine")}
             self._pass(ctx, coords2, fine_depth, fine_depth.shape[1], not cfg.get("one_mlp", False), False, fine, _r0,
@@ -623,6 +627,26 @@ class NeuralRayBaseRenderer(nn.Module):
             self._post(_outs, depth_table, True)
             self._add_gt(_outs, que_imgs_info, self._gt_suffixes())
         return _outs
+
+    def _ft_range_samples(self, ft_depth_range, depth_table, fine_depth):
+        """fine_render_impl (network/renderer.py:438-456, eval): rays with a valid depth prior (ft_depth_range[...,0] >= min_depth) take
+        sample_3sigma between ft_depth_range[...,1] and [...,2] (network/sample_utils.py:6-60) instead of the inverse-CDF samples; rows
+        of `fine_depth` (rn, fdn [+ dn]) are rewritten in place, sorted (with the coarse depths when fine_depth_use_all)."""
+        cfg, lib = self.cfg, _lib.load()
+        rn, dev = fine_depth.shape[0], fine_depth.device
+        dn, fdn = int(cfg["depth_sample_num"]), int(cfg["fine_depth_sample_num"])
+        if fdn != dn:      # the reference writes both kinds of rows into empty_like(coarse depth)
+            raise RuntimeError(f"shape mismatch: ft_depth_range needs fine_depth_sample_num ({fdn}) == depth_sample_num ({dn})")
+        ft = ft_depth_range.reshape(-1, ft_depth_range.shape[-1]).float().contiguous()
+        assert ft.shape[0] == rn and ft.shape[1] >= 3, "ft_depth_range must be (1, rn, 3)"
+        t, g = self._cached_table(("3sigma_t", dn), dev, lambda: torch.linspace(0., 1., steps=dn)), \
+            self._cached_table(("3sigma_g", dn), dev, lambda: 1. / math.sqrt(2 * math.pi) * torch.exp(-0.5 * torch.linspace(-3., 3., steps=dn - 1).pow(2)))
+        use_all = bool(cfg["fine_depth_use_all"])
+        with torch.cuda.device(dev):
+            rc = lib.pgrf_sample_3sigma_fwd(_lib.ptr(ft), ft.shape[1], float(cfg["min_depth"]), _lib.ptr(t), _lib.ptr(g), dn,
+                                            float(cfg["min_depth"]), float(cfg["max_depth"]), _lib.ptr(depth_table) if use_all else None, 0,
+                                            dn if use_all else 0, 1, rn, _lib.ptr(fine_depth), _lib.stream_ptr())
+        _lib.check(rc, "pgrf_sample_3sigma_fwd")
 
     def _add_gt(self, outs, que_imgs_info, suffixes=("",)):
         """`pixel_colors_gt[_fine]` (+ `polar_weights`) of the reference's output dict (renderer.py:278-286, 398-405): the
@@ -731,8 +755,19 @@ class NeuralRayBaseRenderer(nn.Module):
         coords = que_imgs_info["coords"]
         assert coords.shape[0] == 1
         rn = coords.shape[1]
+        ft = que_imgs_info.get("ft_depth_range")
+        two_pass = ft is not None and bool(self.cfg["use_hierarchical_sampling"])
         outs = self._alloc_outputs(rn, coords.device, keep_hit_prob or self._needs_post(), ctx['rfn'])
-        self._render_view(ctx, coords[0].float().contiguous(), outs)
+        if two_pass:
+            # per-ray depth priors change the fine samples between the passes (renderer.py:438-456): the ray-batch loop runs here,
+            # two kernel passes per batch with the prior-guided samples written in between
+            step = int(self.cfg.get("fused_ray_batch", 131072))
+            for r0 in range(0, rn, step):
+                q = dict(que_imgs_info)
+                q["coords"], q["ft_depth_range"] = coords[:, r0:r0 + step], ft[:, r0:r0 + step]
+                self.render_impl(q, ref_imgs_info, False, is_perspec, _ctx=ctx, _outs=outs, _r0=r0)
+        else:
+            self._render_view(ctx, coords[0].float().contiguous(), outs)
         if self._needs_post():
             dn = int(self.cfg["depth_sample_num"])
             table = self._cached_table(("coarse", dn, bool(self.cfg["use_disp"]), float(self.cfg["min_depth"]),

@@ -109,6 +109,10 @@ RENDER_CASES = {
     # ablation switches of DefaultAggregationNet (aggregate_net.py:60-62, 79-81)
     "render_m3d_wo_geometry": dict(cfg=dict(wo_geometry=True), rfn=2, n_rays=40),
     "render_m3d_wo_appearance": dict(cfg=dict(wo_appearance=True), rfn=3, n_rays=40),
+    # fine samples of rays with a valid depth prior from sample_3sigma (fine_render_impl, renderer.py:438-456; sample_utils.py:6-60)
+    "render_m3d_ft_range": dict(cfg=dict(), rfn=2, n_rays=56, ft=True),
+    "render_m3d_ft_range_all": dict(cfg=dict(fine_use_all=True, sample_num=32, hierarchical=True), rfn=2, n_rays=40,
+                                    fine_sample_num=16, ft=True),
 }
 
 
@@ -143,6 +147,14 @@ def make_render_inputs(name, seed=0):
     perm = torch.randperm(h * w, generator=gen)[:c["n_rays"]]
     coords = torch.stack([(perm % w).float(), (perm // w).float()], -1)[None]
     que = {"coords": coords, "c2w": c2w, "w2c": que_w2c[None], "depth_range": torch.tensor([[0.5, 15.0]])}
+    if c.get("ft"):
+        # (1,rn,3): [validity marker (>= min_depth: valid), low, high]; a third of the rays have no prior, some intervals stick out
+        # of [min_depth, max_depth] (the clamp of sample_utils.py:9 makes zero-width bins there)
+        n = c["n_rays"]
+        mu = 0.3 + 14.0 * torch.rand(n, generator=gen)
+        half = 0.05 + 1.5 * torch.rand(n, generator=gen)
+        mark = torch.where(torch.rand(n, generator=gen) < 0.33, torch.zeros(n), mu)
+        que["ft_depth_range"] = torch.stack([mark, mu - half, mu + half], -1)[None]
     ref = {"imgs": imgs, "w2c": w2c[:rfn].contiguous(), "depth_range": torch.tensor([[0.5, 15.0]]).repeat(rfn, 1),
            "ray_feats": ray_feats, "img_feats": img_feats}
     return cfg, que, ref

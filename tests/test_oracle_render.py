@@ -105,3 +105,16 @@ def test_oracle_compute_prob_is_ref_false_matches_reference_golden(tag):
                                        bool(c["use_vis"]))
     for got, key in ((a, "alpha"), (v, "visibility"), (h, "hit_prob")):
         assert_close(got, c[key], rtol=1e-5, atol=1e-6, what=f"prob_que/{tag}/{key}")
+
+
+def test_sample_3sigma_matches_reference_golden():
+    """oracle.sample_3sigma (sample_utils.py:6-60, det=True) against outputs of the reference function (tests/golden/make_golden_3sigma.py)."""
+    g = load_golden("sample_3sigma")
+    for tag in "abc":
+        n, near, far = int(g[tag + ".n"]), float(g[tag + ".near"]), float(g[tag + ".far"])
+        z = orender.sample_3sigma(torch.as_tensor(g[tag + ".low"]), torch.as_tensor(g[tag + ".high"]), n, near, far)
+        e = torch.as_tensor(g[tag + ".z"])
+        assert z.shape == e.shape
+        # torch.cumsum vs the stated sequential order: a bin can flip for a u that ties with a cdf entry (same depth to ~1e-5)
+        assert_close(z, e, rtol=1e-5, atol=1e-4, what=f"sample_3sigma/{tag}")
+        assert bool(((z >= near - 1e-6) & (z <= far + 1e-6)).all())

@@ -387,3 +387,24 @@ def test_perspective_query_rays_match_reference_golden(dtype):
                 assert_close(out[k], gold[k], rtol=1e-4, atol=5e-5, what=f"{call}/{k}")
             elif not k.endswith("_fine"):
                 _close_bf16(out[k], gold[k], f"{call}/{k}", scale=scale)
+
+
+@pytest.mark.parametrize("name", ["render_m3d_ft_range", "render_m3d_ft_range_all"])
+def test_ft_depth_range_full_view_path(name):
+    """que_imgs_info['ft_depth_range'] (fine_render_impl, renderer.py:438-456): render() runs the ray-batch loop with the prior-guided
+    samples written between the passes == render_impl on all rays; without any valid prior it equals the plain render."""
+    cfg, _, _ = cases.make_render_inputs(name)
+    que, ref, W, gold = split_golden(load_golden(name))
+    net = build_renderer({**cfg, "fused_ray_batch": 16}, W)          # several ray batches
+    q, r = cuda_dict(que), cuda_dict(ref)
+    full = net.render(dict(q), dict(r), False)
+    for k in ("pixel_colors_nr_fine", "render_depth_fine", "density_nr_fine", "pixel_colors_nr"):
+        assert_close(full[k], gold[k].float(), rtol=1e-4, atol=5e-5, what=f"{name}/render()/{k}")
+    assert not any(k.startswith("hit_prob") for k in full)
+    q0 = dict(q)
+    q0["ft_depth_range"] = torch.zeros_like(q["ft_depth_range"])      # marker 0 < min_depth: no ray has a prior
+    a = net.render(q0, dict(r), False)
+    q1 = {k: v for k, v in q.items() if k != "ft_depth_range"}
+    b = net.render(q1, dict(r), False)
+    for k in ("pixel_colors_nr_fine", "render_depth_fine"):
+        assert_close(a[k], b[k], rtol=1e-5, atol=1e-6, what=f"{name}/no prior/{k}")

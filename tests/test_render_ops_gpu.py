@@ -185,3 +185,18 @@ def test_e2c_matches_reference_class(name):
         pad = np.concatenate([ch, np.roll(ch[[-1]], w // 2, 1), np.roll(ch[[0]], w // 2, 1)], 0)
         want = map_coordinates(pad, [inst.coor_y, inst.coor_x], order=1, mode="wrap")[..., 0]
         assert np.abs(got[0, 1, :, :, c].numpy() - want).max() <= 1.2e-7
+
+
+def test_sample_3sigma_matches_reference_golden():
+    """render_ops.sample_3sigma (pgrf_sample_3sigma_fwd) against the reference function's outputs and the oracle."""
+    from oracle import render as R
+    from panogrf_b200.render_ops import sample_3sigma
+    g = load_golden("sample_3sigma")
+    for tag in "abc":
+        n, near, far = int(g[tag + ".n"]), float(g[tag + ".near"]), float(g[tag + ".far"])
+        low, high = torch.as_tensor(g[tag + ".low"]), torch.as_tensor(g[tag + ".high"])
+        z = sample_3sigma(low.cuda(), high.cuda(), n, True, near, far).cpu()
+        assert_close(z, torch.as_tensor(g[tag + ".z"]), rtol=1e-5, atol=1e-4, what=f"sample_3sigma/{tag} vs reference")
+        assert_close(z, R.sample_3sigma(low, high, n, near, far), rtol=1e-5, atol=2e-5, what=f"sample_3sigma/{tag} vs oracle")
+    with pytest.raises(NotImplementedError):
+        sample_3sigma(low.cuda(), high.cuda(), 8, False, near, far)
