@@ -184,9 +184,27 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
+// Range of every prior depth map, [min, max] per view (NaNs ignored): lets phase 1 drop candidates by their distance to the source
+// camera alone, before any angle is computed.  One CTA per view.
+__global__ void __launch_bounds__(1024) depth_range_kernel(const float* __restrict__ maps, long long px, float* __restrict__ out) {
+  __shared__ float s_lo[32], s_hi[32];
+  const float* m = maps + (size_t)blockIdx.x * px;
+  float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+  for (long long i = threadIdx.x; i < px; i += blockDim.x) { const float v = __ldg(m + i); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+  for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    lo = s_lo[threadIdx.x]; hi = s_hi[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if (threadIdx.x == 0) { out[2 * blockIdx.x] = lo; out[2 * blockIdx.x + 1] = hi; }
+  }
+}
+
 // E > 0: the two final sorts run in registers (32*E >= n_samples + n_uniform slots); E == 0: in shared memory
 template <int E>
-__global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_diner_args a, int nc_pad, int nc_pow2, int g_prefilter_on) {
+__global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_diner_args a, int nc_pad, int nc_pow2, int g_prefilter_on,
+                                                                 const float* __restrict__ prior_range) {
   extern __shared__ __align__(16) unsigned char dsm[];
   const int tid = threadIdx.x & 31, warp = threadIdx.x >> 5;                             // tid = lane: the warp owns the ray
   const int nc = a.n_candidates, ns = a.n_samples, ng = a.n_gaussian, nu = a.n_uniform;
@@ -277,6 +295,11 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
         }
         magA *= 1e-6f; magB *= 1e-6f;
         const float* dmap = a.mvs_depth + v * map_px;
+        // distance-only rejection: |mu - pd| >= thr for every mu of the view when pd is outside [min - thr, max + thr] (with slack for
+        // rounding and the position bound); compared on squared distances.  An all-NaN map gives [+inf, -inf] -> NaN bounds -> nothing is dropped here.
+        const float g_lo = __ldg(prior_range + 2 * v), g_hi = __ldg(prior_range + 2 * v + 1);
+        const float b_hi = fmaf(fabsf(g_hi) + a.depth_diff_max, 1.00002f, g_hi > 0.f ? 0.f : 2.f * g_hi);        // (g_hi + thr) + slack
+        const float b_lo = fmaf(fabsf(g_lo) + a.depth_diff_max, -1.00002f, g_lo > 0.f ? 2.f * g_lo : 0.f);       // (g_lo - thr) - slack
         // two candidates per lane and iteration: two independent dependency chains for the scheduler
         const float* cp = cand + tid;
         for (int i0 = 0; i0 < nc; i0 += 64, cp += 64) {
@@ -284,10 +307,15 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
           bool need_a = false, need_b = false;
           {
             const float ta = ia < nc ? __ldg(cp) : 0.f, tb = ib < nc ? __ldg(cp + 32) : 0.f;
-            const bool far_a = dg_certainly_far(flt, dmap, a.map_w, a.depth_diff_max, fmaf(B0, ta, A0), fmaf(B1, ta, A1), fmaf(B2, ta, A2),
-                                                fmaf(magB, fabsf(ta), magA));
-            const bool far_b = dg_certainly_far(flt, dmap, a.map_w, a.depth_diff_max, fmaf(B0, tb, A0), fmaf(B1, tb, A1), fmaf(B2, tb, A2),
-                                                fmaf(magB, fabsf(tb), magA));
+            const float ca0 = fmaf(B0, ta, A0), ca1 = fmaf(B1, ta, A1), ca2 = fmaf(B2, ta, A2), da = fmaf(magB, fabsf(ta), magA);
+            const float cb0 = fmaf(B0, tb, A0), cb1 = fmaf(B1, tb, A1), cb2 = fmaf(B2, tb, A2), db = fmaf(magB, fabsf(tb), magA);
+            const float ha = fmaf(2.f, da, b_hi), la = fmaf(-2.f, da, b_lo), hb = fmaf(2.f, db, b_hi), lb = fmaf(-2.f, db, b_lo);
+            const float ra = ca0 * ca0 + ca1 * ca1 + ca2 * ca2, rb = cb0 * cb0 + cb1 * cb1 + cb2 * cb2;
+            const bool out_a = ra > ha * ha * 1.000001f || (la > 0.f && ra * 1.000001f < la * la);
+            const bool out_b = rb > hb * hb * 1.000001f || (lb > 0.f && rb * 1.000001f < lb * lb);
+            if (!__any_sync(0xffffffffu, (ia < nc && !out_a) || (ib < nc && !out_b))) continue;   // the whole batch is off the prior's range
+            const bool far_a = out_a || dg_certainly_far(flt, dmap, a.map_w, a.depth_diff_max, ca0, ca1, ca2, da);
+            const bool far_b = out_b || dg_certainly_far(flt, dmap, a.map_w, a.depth_diff_max, cb0, cb1, cb2, db);
             need_a = ia < nc && !far_a;
             need_b = ib < nc && !far_b;
           }
@@ -582,16 +610,25 @@ extern "C" int pgrf_depth_guided_sample_fwd(const pgrf_diner_args* args, void* s
   const long long max_grid = 148LL * 16, want = (a.rn + kDgWarps - 1) / kDgWarps;
   const int grid = (int)(want < max_grid ? want : max_grid);
   const int E = (g_dg_regsort && out_pow2 <= 128) ? (out_pow2 <= 32 ? 1 : out_pow2 / 32) : 0;
+  // range of the prior maps (fused variant only), in stream order
+  float* prior_range = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!a.prj_mu) {
+    PGRF_CUDA(cudaMallocAsync((void**)&prior_range, sizeof(float) * 2 * a.rfn, st));
+    depth_range_kernel<<<a.rfn, 1024, 0, st>>>(a.mvs_depth, (long long)a.map_h * a.map_w, prior_range);
+    count_launch();
+  }
 #define PGRF_DG_LAUNCH(EE)                                                                                                            \
   do {                                                                                                                                \
     if (smem > 48 * 1024) PGRF_CUDA(cudaFuncSetAttribute(depth_guided_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    depth_guided_kernel<EE><<<grid, kDgThreads, smem, (cudaStream_t)stream>>>(a, nc_pad, nc_pow2, g_dg_prefilter);                     \
+    depth_guided_kernel<EE><<<grid, kDgThreads, smem, st>>>(a, nc_pad, nc_pow2, g_dg_prefilter, prior_range);                           \
   } while (0)
   if (E == 1) PGRF_DG_LAUNCH(1);
   else if (E == 2) PGRF_DG_LAUNCH(2);
   else if (E == 4) PGRF_DG_LAUNCH(4);
   else PGRF_DG_LAUNCH(0);
 #undef PGRF_DG_LAUNCH
+  if (prior_range) PGRF_CUDA(cudaFreeAsync(prior_range, st));
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
