@@ -60,7 +60,7 @@ __device__ __forceinline__ float4 blend4(const float4* __restrict__ base, int sx
 // STAGE: the 12-byte-per-row outputs (unit direction, colour) leave through shared memory as fully coalesced 4-byte stores instead of
 // three stride-12 scalar stores per row (each of those touches three 128-byte lines per warp).
 template <bool PACKED, int UNR, bool STAGE = false>
-__global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgParams p) {
+__global__ void __launch_bounds__(kPgThreads, 5) project_gather_kernel(const PgParams p) {
   __shared__ PgRec rec[kPgThreads];
   __shared__ float s_dir[STAGE ? 3 * kPgThreads : 1], s_rgb[STAGE ? 3 * kPgThreads : 1];
   const int tid = threadIdx.x;
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgPara
     const long long p0 = tile * kPgPoints;
     // ---- phase 1: thread = (view, point): w2c, spherical, pixel, direction, three footprints
     if (tid < rows) {
-      const int v = tid / kPgPoints;
-      const long long pi = p0 + (tid % kPgPoints);
+      const int v = (tid >= kPgPoints) + (tid >= 2 * kPgPoints) + (tid >= 3 * kPgPoints);
+      const long long pi = p0 + (tid - v * kPgPoints);
       PgRec r;
       r.dxy = 0; r.off_rf = r.off_if = r.off_im = 0;
       r.tx_rf = r.ty_rf = r.tx_if = r.ty_if = r.tx_im = r.ty_im = 0.f;
@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(kPgThreads) project_gather_kernel(const PgPara
 #pragma unroll UNR
     for (int it = tid; it < rows * 8; it += kPgThreads) {
       const int rrow = it >> 3, cg = it & 7;
-      const int v = rrow / kPgPoints;
-      const long long pi = p0 + (rrow % kPgPoints);
+      // rfn <= 4: the view of a row by comparisons (an integer division by the run-time tile size costs ~35 instructions per lane)
+      const int v = (rrow >= kPgPoints) + (rrow >= 2 * kPgPoints) + (rrow >= 3 * kPgPoints);
+      const long long pi = p0 + (rrow - v * kPgPoints);
       if (pi >= p.pn) continue;
       const PgRec r = rec[rrow];
       const size_t row = (size_t)v * p.pn + pi;

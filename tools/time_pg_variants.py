@@ -11,9 +11,9 @@ flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 for _ in range(20):
     bench.time_project_gather(torch, None, ref_d, flush, bench.measured_peaks())
 for rnd in range(3):
-  for var in (3, 5):
-    for grid in (48, 64, 96):
+  for var in (5,):
+    for grid in (64, 96):
         lib.pgrf_debug_set(b"pg_variant", var); lib.pgrf_debug_set(b"pg_grid", grid)
         r = bench.time_project_gather(torch, None, ref_d, flush, bench.measured_peaks())
         print("round", rnd, "variant", var, "grid", grid, "ms %.4f frac %.4f" % (r["ms"], r["roofline"]["frac"]))
-lib.pgrf_debug_set(b"pg_variant", 3); lib.pgrf_debug_set(b"pg_grid", 48)
+lib.pgrf_debug_set(b"pg_variant", 5); lib.pgrf_debug_set(b"pg_grid", 64)
