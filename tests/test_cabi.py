@@ -47,15 +47,27 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.pgrf_cost_volume_fwd(dummy, 1, 2, 8, 16, 8, dummy, None, 4, dummy, dummy, 1, views, 1, 0.0,
                                   0, 7, 0, 0, dummy, dummy, None)
     assert rc == _lib.PGRF_EINVAL and lib.pgrf_last_error() == b"Unknown cost type"
+    # sample_3sigma: sizes, row stride of the prior table, coarse depths only in selection mode
+    rc = lib.pgrf_sample_3sigma_fwd(dummy, 3, 0.5, dummy, dummy, 1, 0.5, 15.0, None, 0, 0, 1, 8, dummy, None)
+    assert rc == _lib.PGRF_EINVAL and b"n=1" in lib.pgrf_last_error()
+    rc = lib.pgrf_sample_3sigma_fwd(dummy, 2, 0.5, dummy, dummy, 16, 0.5, 15.0, None, 0, 0, 1, 8, dummy, None)
+    assert rc == _lib.PGRF_EINVAL
+    rc = lib.pgrf_sample_3sigma_fwd(dummy, 2, 0.5, dummy, dummy, 16, 0.5, 15.0, dummy, 0, 16, 0, 8, dummy, None)
+    assert rc == _lib.PGRF_EINVAL and b"selection mode" in lib.pgrf_last_error()
+    rc = lib.pgrf_sample_3sigma_fwd(None, 3, 0.5, dummy, dummy, 16, 0.5, 15.0, None, 0, 0, 1, 8, dummy, None)
+    assert rc == _lib.PGRF_EINVAL and b"null pointer" in lib.pgrf_last_error()
 
 
 def test_ops_refuse_cpu_tensors():
     import torch
     from panogrf_b200 import calculate_cost_volume_erp
     from panogrf_b200._lib import PanoGRFError
+    from panogrf_b200.render_ops import sample_3sigma
     with pytest.raises(PanoGRFError):
         calculate_cost_volume_erp({"dataset_name": "m3d", "contain_dnet": False}, torch.zeros(1, 2, 8, 16, 8),
                                   torch.ones(3), torch.zeros(1, 2, 3), torch.eye(3).expand(1, 2, 3, 3))
+    with pytest.raises(PanoGRFError):
+        sample_3sigma(torch.ones(4), 2 * torch.ones(4), 16, True, 0.5, 15.0)
 
 
 def test_struct_layouts_match_the_header(tmp_path):
