@@ -57,3 +57,19 @@ if __name__ == "__main__":
     rms = float((y - ref).pow(2).mean().sqrt() / ref.abs().max())
     print(f"ResUNetLight 2x3x512x1024 -> {tuple(y.shape)}: {ms:.3f} ms ({launches} launches); torch/cuDNN fp32 (TF32): {ms_lib:.3f} ms; "
           f"max err {err:.2e}, rms {rms:.2e} of range")
+    from panogrf_b200.graphs import GraphedForward
+    from panogrf_b200.vis_encoder import DefaultVisEncoder
+    from panogrf_b200 import regulariser as reg
+    g = GraphedForward(net)
+    yg = g(x)
+    print(f"  replayed from a CUDA graph: {time_fn(lambda: g(x), 5):.3f} ms (bit-identical: {bool(torch.equal(yg, y))})")
+    vis = DefaultVisEncoder({"use_wrap_padding": True}).cuda()
+    rf, imf = torch.randn(2, 32, 64, 128, device="cuda"), torch.randn(2, 32, 128, 256, device="cuda")
+    gv = GraphedForward(vis)
+    print(f"DefaultVisEncoder 2 x (32 + 32) x 128x256: eager {time_fn(lambda: vis(rf, imf), 5):.3f} ms, graph {time_fn(lambda: gv(rf, imf), 5):.3f} ms "
+          f"(bit-identical: {bool(torch.equal(gv(rf, imf), vis(rf, imf)))})")
+    unet = reg.CostRegulariser3D(4).cuda()
+    vol = torch.randn(1, 32, 64, 64, 128, device="cuda")
+    gu = GraphedForward(unet)
+    print(f"CostRegulariser3D 1x32x64x64x128: eager {time_fn(lambda: unet(vol), 5):.3f} ms, graph {time_fn(lambda: gu(vol), 5):.3f} ms "
+          f"(bit-identical: {bool(torch.equal(gu(vol), unet(vol)))})")
