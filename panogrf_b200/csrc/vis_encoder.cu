@@ -59,14 +59,24 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const __nv_bfloat16
   const int n = blockIdx.y;
   float s1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (pl < lanes) {
-    for (int p = blockIdx.x * lanes + pl; p < HW; p += gridDim.x * lanes) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)n * HW + p) * C) + c8);
-      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
+    // four independent 16-byte loads in flight per thread (the kernel is a latency chain otherwise); same summation order as a plain loop
+    const int step = gridDim.x * lanes;
+    for (int p0 = blockIdx.x * lanes + pl; p0 < HW; p0 += 4 * step) {
+      uint4 q[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(hh[j]);
-        s1[2 * j] += f.x; s1[2 * j + 1] += f.y;
-        s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]); s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * step;
+        q[u] = p < HW ? __ldg(reinterpret_cast<const uint4*>(x + ((size_t)n * HW + p) * C) + c8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(hh[j]);
+          s1[2 * j] += f.x; s1[2 * j + 1] += f.y;
+          s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]); s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
+        }
       }
     }
   }
@@ -93,36 +103,43 @@ __global__ void __launch_bounds__(256) instnorm_act_kernel(const __nv_bfloat16* 
                                                            const double* __restrict__ stats, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ res,
                                                            int act, __nv_bfloat16* __restrict__ y) {
+  // grid = (blocks over HW * C/8, N): a block stays inside one image, so mean / rstd / gamma / beta of its channels are computed once
+  // per block (one fp64 division + square root per channel instead of one per element) and read from shared memory
+  __shared__ float4 s_par[256];
   const int C8 = C / 8;
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (unsigned)N * HW * C8) return;
-  const int c8 = (int)(i % C8);
-  const int n = (int)(i / ((unsigned)HW * C8));
-  const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(i / C8) * C) + c8);
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
+    const double mean = s1 / HW, var = fmax(s2 / HW - mean * mean, 0.0);
+    s_par[c] = make_float4((float)mean, (float)(1.0 / sqrt(var + (double)eps)), __ldg(gamma + c), __ldg(beta + c));
+  }
+  __syncthreads();
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;          // (pixel, channel chunk) inside the image
+  if (j >= (unsigned)HW * C8) return;
+  const int c8 = (int)(j % C8);
+  const size_t row = (size_t)n * HW + j / C8;
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + row * C) + c8);
   const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
   float v[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(hh[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
   if (res) {
-    const uint4 qr = __ldg(reinterpret_cast<const uint4*>(res + (size_t)(i / C8) * C) + c8);
+    const uint4 qr = __ldg(reinterpret_cast<const uint4*>(res + row * C) + c8);
     const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&qr);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hr[j]); rv[2 * j] = f.x; rv[2 * j + 1] = f.y; }
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(hr[k]); rv[2 * k] = f.x; rv[2 * k + 1] = f.y; }
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int c = 8 * c8 + k;
-    const double s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
-    const double mean = s1 / HW, var = fmax(s2 / HW - mean * mean, 0.0);
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float o = (v[k] - (float)mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) + rv[k];
+    const float4 pr = s_par[8 * c8 + k];
+    float o = (v[k] - pr.x) * pr.y * pr.z + pr.w + rv[k];
     if (act == 1) o = o > 0.f ? o : 0.f;
     else if (act == 2) o = o > 0.f ? o : expm1f(o);
     v[k] = o;
   }
   uint4 o;
   o.x = umma::pack2(v[0], v[1]); o.y = umma::pack2(v[2], v[3]); o.z = umma::pack2(v[4], v[5]); o.w = umma::pack2(v[6], v[7]);
-  reinterpret_cast<uint4*>(y + (size_t)(i / C8) * C)[c8] = o;
+  reinterpret_cast<uint4*>(y + row * C)[c8] = o;
 }
 
 // ---- ResUNetLight parts (network/ops.py:235-455) --------------------------------------------------------------------------------
@@ -243,8 +260,10 @@ static int instnorm_launch(const void* x, int N, int HW, int C, const float* gam
     count_launch();
     PGRF_CUDA(cudaGetLastError());
   }
-  instnorm_act_kernel<<<vblocks(n), 256, 0, st>>>((const __nv_bfloat16*)x, N, HW, C, stats_ws, gamma, beta, eps, (const __nv_bfloat16*)res,
-                                                 act, (__nv_bfloat16*)y);
+  const long long per_image = (long long)HW * (C / 8);
+  PGRF_REQUIRE(N <= 65535, "instnorm: N=%d exceeds the grid's y range", N);
+  instnorm_act_kernel<<<dim3((unsigned)((per_image + 255) / 256), (unsigned)N), 256, 0, st>>>(
+      (const __nv_bfloat16*)x, N, HW, C, stats_ws, gamma, beta, eps, (const __nv_bfloat16*)res, act, (__nv_bfloat16*)y);
   count_launch();
   PGRF_CUDA(cudaGetLastError());
   return PGRF_OK;
