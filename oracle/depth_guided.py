@@ -141,7 +141,10 @@ def render_rays_diner(cfg, W, que, ref, fill_rand, gauss=None):
     if cfg.get("c2f", False):
         fine = R.sample_fine_depth(depth, d_out["hit_prob_nr"], que["depth_range"], cfg.get("fine_depth_sample_num", 64),
                                    cfg["use_disp"])
-        if cfg.get("fine_depth_use_all", False):
+        if que.get("ft_depth_range") is not None:          # fine_render_impl's prior-guided samples also apply here (renderer.py:438-456)
+            fdepth = R.fine_depth_with_ft_range(fine, depth, que["ft_depth_range"], cfg["min_depth"], cfg["max_depth"],
+                                                cfg.get("fine_depth_use_all", False))
+        elif cfg.get("fine_depth_use_all", False):
             fdepth = torch.sort(torch.cat([depth, fine], -1), -1)[0]
         else:
             fdepth = torch.sort(fine, -1)[0]

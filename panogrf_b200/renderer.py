@@ -628,13 +628,14 @@ class NeuralRayBaseRenderer(nn.Module):
             self._add_gt(_outs, que_imgs_info, self._gt_suffixes())
         return _outs
 
-    def _ft_range_samples(self, ft_depth_range, depth_table, fine_depth):
+    def _ft_range_samples(self, ft_depth_range, depth_table, fine_depth, coarse_stride=0, dn=None):
         """fine_render_impl (network/renderer.py:438-456, eval): rays with a valid depth prior (ft_depth_range[...,0] >= min_depth) take
         sample_3sigma between ft_depth_range[...,1] and [...,2] (network/sample_utils.py:6-60) instead of the inverse-CDF samples; rows
-        of `fine_depth` (rn, fdn [+ dn]) are rewritten in place, sorted (with the coarse depths when fine_depth_use_all)."""
+        of `fine_depth` (rn, fdn [+ dn]) are rewritten in place, sorted (with the coarse depths when fine_depth_use_all).  The coarse
+        depths are one shared table (`coarse_stride` 0) or one row per ray (the depth-prior branch)."""
         cfg, lib = self.cfg, _lib.load()
         rn, dev = fine_depth.shape[0], fine_depth.device
-        dn, fdn = int(cfg["depth_sample_num"]), int(cfg["fine_depth_sample_num"])
+        dn, fdn = int(cfg["depth_sample_num"]) if dn is None else int(dn), int(cfg["fine_depth_sample_num"])
         if fdn != dn:      # the reference writes both kinds of rows into empty_like(coarse depth)
             raise RuntimeError(f"shape mismatch: ft_depth_range needs fine_depth_sample_num ({fdn}) == depth_sample_num ({dn})")
         ft = ft_depth_range.reshape(-1, ft_depth_range.shape[-1]).float().contiguous()
@@ -644,8 +645,8 @@ class NeuralRayBaseRenderer(nn.Module):
         use_all = bool(cfg["fine_depth_use_all"])
         with torch.cuda.device(dev):
             rc = lib.pgrf_sample_3sigma_fwd(_lib.ptr(ft), ft.shape[1], float(cfg["min_depth"]), _lib.ptr(t), _lib.ptr(g), dn,
-                                            float(cfg["min_depth"]), float(cfg["max_depth"]), _lib.ptr(depth_table) if use_all else None, 0,
-                                            dn if use_all else 0, 1, rn, _lib.ptr(fine_depth), _lib.stream_ptr())
+                                            float(cfg["min_depth"]), float(cfg["max_depth"]), _lib.ptr(depth_table) if use_all else None,
+                                            int(coarse_stride), dn if use_all else 0, 1, rn, _lib.ptr(fine_depth), _lib.stream_ptr())
         _lib.check(rc, "pgrf_sample_3sigma_fwd")
 
     def _add_gt(self, outs, que_imgs_info, suffixes=("",)):
@@ -825,6 +826,8 @@ class NeuralRayBaseRenderer(nn.Module):
         for r0 in range(0, rn, int(rpl)):
             n = min(int(rpl), rn - r0)
             fd = self._pass(ctx, coords2[r0:r0 + n], d2[r0:r0 + n], N, False, c2f, coarse, r0, "hit_prob_nr" in coarse)
+            if c2f and que_imgs_info.get("ft_depth_range") is not None:
+                self._ft_range_samples(que_imgs_info["ft_depth_range"][:, r0:r0 + n], d2[r0:r0 + n], fd, coarse_stride=N, dn=N)
             if c2f:
                 self._pass(ctx, coords2[r0:r0 + n], fd, fine_total, not cfg.get("one_mlp", False), False, fine, r0,
                            "hit_prob_nr" in fine)

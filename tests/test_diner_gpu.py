@@ -182,3 +182,33 @@ def test_prefilter_is_exact(kind):
         assert int((res[0][1] > 0).sum()) > rn          # the scene does hit the prior surfaces
         assert torch.equal(res[0][1], res[1][1]), f"{kind} {map_hw}: likelihood changed"
         assert torch.equal(res[0][0], res[1][0]), f"{kind} {map_hw}: placement changed"
+
+
+def test_diner_c2f_with_ft_depth_range_matches_oracle():
+    """Depth-prior branch with a real fine pass (c2f) AND per-ray priors for the fine samples (que_imgs_info['ft_depth_range'],
+    fine_render_impl renderer.py:438-456): against the oracle (its parts are pinned by the reference goldens `diner_dense_c2f` and
+    `render_m3d_ft_range`)."""
+    from oracle import depth_guided as odg
+    from panogrf_b200.renderer import NeuralRayBaseRenderer
+    name = "diner_dense_c2f"
+    cfg, que, ref, fill_rand, gauss = cases.make_diner_inputs(name)
+    _, _, W, _ = split_golden(load_golden(name))
+    rn = que["coords"].shape[1]
+    gen = torch.Generator().manual_seed(5)
+    mu = 0.6 + 3.0 * torch.rand(rn, generator=gen)
+    half = 0.05 + 0.5 * torch.rand(rn, generator=gen)
+    mark = torch.where(torch.rand(rn, generator=gen) < 0.4, torch.zeros(rn), mu)
+    que = dict(que, ft_depth_range=torch.stack([mark, mu - half, mu + half], -1)[None])
+    exp = odg.render_rays_diner(cfg, W, que, ref, fill_rand, gauss)
+    net = NeuralRayBaseRenderer({**cfg, "mlp_dtype": "fp32"}).cuda()
+    net.load_state_dict(W, strict=True)
+    q = _cuda(que)
+    q["diner_fill_rand"], q["diner_gauss"] = fill_rand.cuda(), gauss.cuda()
+    out = net.render_impl(q, _cuda(ref), False)
+    ok = _rows_equal(out["que_depth"].cpu(), exp["que_depth"]) & _rows_equal(out["que_depth_fine"].cpu(), exp["que_depth_fine"], atol=1e-4)
+    assert float(ok.float().mean()) >= 1 - 2 / 32
+    valid = (que["ft_depth_range"][0, :, 0] >= cfg["min_depth"])
+    assert int(valid.sum()) > 5 and int((~valid).sum()) > 5
+    for k in ("pixel_colors_nr_fine", "render_depth_fine"):
+        a, e = out[k].cpu()[0][ok], exp[k][0][ok]
+        assert_close(a, e, rtol=1e-4, atol=1e-4 * max(float(e.abs().max()), 1.0), what=f"diner c2f + ft/{k}")
