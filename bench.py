@@ -529,7 +529,7 @@ def main():
 
 
 def rays_per_launch(net):
-    return int(net.rays_per_launch or (131072 if net.mlp_dtype == "bf16" else 32768))
+    return int(net.rays_per_launch or (524288 if net.mlp_dtype == "bf16" else 32768))
 
 
 def _median_ms(torch, flush, fn, n=5, reps=1, warm=1):

@@ -366,8 +366,8 @@ class NeuralRayBaseRenderer(nn.Module):
         "render_depth": False, "render_uncert": False, "debug": False, "use_disp": True,
     }
     #: rays per kernel launch (the reference's ray_batch_num only bounds ITS activation memory; here it bounds the
-    #: inter-kernel workspaces).  None = 131072 for the bf16 path (only the 272 B/sample F2 tiles exist; larger launches
-    #: amortise the per-CTA weight load and the tail), 32768 for the fp32 path (F1 tiles: 38.9 KB per 64 samples, 1.3 GB of workspace).
+    #: inter-kernel workspaces).  None = 524288 for the bf16 path (only the 160 B/sample F2 tiles exist: 5.4 GB at 64 samples; larger
+    #: launches amortise the per-CTA weight load and the tail: 46.63 / 46.41 / 46.27 ms per view at 131072 / 262144 / 524288), 32768 for the fp32 path (F1 tiles: 38.9 KB per 64 samples, 1.3 GB of workspace).
     rays_per_launch = None
     #: reuse the channels-last copies of the source maps while the caller passes the same, unmodified tensors (keyed on storage
     #: pointer + in-place version).  Writes through `.data` do not bump the version: set False (or call invalidate_map_cache())
@@ -762,7 +762,7 @@ class NeuralRayBaseRenderer(nn.Module):
         if two_pass:
             # per-ray depth priors change the fine samples between the passes (renderer.py:438-456): the ray-batch loop runs here,
             # two kernel passes per batch with the prior-guided samples written in between
-            step = int(self.cfg.get("fused_ray_batch", 131072))
+            step = int(self.cfg.get("fused_ray_batch", 524288))
             for r0 in range(0, rn, step):
                 q = dict(que_imgs_info)
                 q["coords"], q["ft_depth_range"] = coords[:, r0:r0 + step], ft[:, r0:r0 + step]
@@ -821,7 +821,7 @@ class NeuralRayBaseRenderer(nn.Module):
         fdn = int(cfg["fine_depth_sample_num"])
         fine_total = fdn + (N if cfg["fine_depth_use_all"] else 0)
         fine = alloc(fine_total) if c2f else None
-        rpl = self.rays_per_launch or (131072 if self.mlp_dtype == "bf16" else 32768)
+        rpl = self.rays_per_launch or (524288 if self.mlp_dtype == "bf16" else 32768)
         d2 = depth[0]
         for r0 in range(0, rn, int(rpl)):
             n = min(int(rpl), rn - r0)
@@ -897,7 +897,7 @@ class NeuralRayBaseRenderer(nn.Module):
             if agg.cfg["sample_num"] != n:
                 raise RuntimeError(f"The size of tensor a ({n}) must match the size of tensor b "
                                    f"({agg.cfg['sample_num']}) at non-singleton dimension 1")   # ibrnet.py:358
-        rpl = self.rays_per_launch or (131072 if self.mlp_dtype == "bf16" else 32768)
+        rpl = self.rays_per_launch or (524288 if self.mlp_dtype == "bf16" else 32768)
         chunk = max(1, min(int(rpl), rn))
         va = _lib.RenderViewArgs()
         a = va.pass_
