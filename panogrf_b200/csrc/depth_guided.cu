@@ -42,7 +42,7 @@ __device__ __forceinline__ float surface_likelihood(const pgrf_diner_args& a, fl
   return 0.5f * fabsf(erff(x1) - erff(x0));
 }
 
-// ---- conservative pre-filter of phase 1 (m3d convention) --------------------------------------------------------------------
+// ---- conservative pre-filter of phase 1 --------------------------------------------------------------------
 // A (candidate, view) pair contributes only when |mu - pd| < depth_diff_max, mu = the bilinear prior depth at the projected
 // pixel.  The exact projection (atan2f / acosf / IEEE divisions, ~380 instructions) is what the oracle is compared with bit for
 // bit, and it is needed for the handful of candidates next to the prior surface only.  The filter projects with polynomial
@@ -60,19 +60,22 @@ struct DgFilter {
   float sx, bx, sy, by;        // angle -> map coordinate
   float eps_x, eps_y, eps_ys;  // safety margins in texels (eps_ys scales with 1/sin(phi): conditioning of acos)
   float xmax, ymax;
+  int dataset;
 };
 __device__ __forceinline__ DgFilter dg_filter(const pgrf_diner_args& a) {
   DgFilter f;
   const bool align = (a.map_h == a.img_h && a.map_w == a.img_w);
   const float fw = (float)a.map_w, fh = (float)a.map_h;
-  f.sx = (align ? fw - 1.f : fw) * (1.f / PGRF_TWO_PI_F);
-  f.sy = (align ? fh - 1.f : fh) * (1.f / PGRF_PI_F);
+  // pixel = angle / (2 pi | pi) * (W-1 | H-1) (cam_to_equi), map coordinate = pixel / (img-1) * (f-1 | f) [- 0.5] (border_footprint)
+  f.sx = (align ? fw - 1.f : fw) * (1.f / PGRF_TWO_PI_F) * ((float)(a.W - 1) / (float)(a.img_w - 1));
+  f.sy = (align ? fh - 1.f : fh) * (1.f / PGRF_PI_F) * ((float)(a.H - 1) / (float)(a.img_h - 1));
   f.bx = f.by = align ? 0.f : -0.5f;
   f.eps_x = fw * 2.5e-6f;
   f.eps_y = fh * 3.6e-6f;
   f.eps_ys = fh * (8e-7f / PGRF_PI_F);
   f.xmax = fw - 1.f;
   f.ymax = fh - 1.f;
+  f.dataset = a.dataset;
   return f;
 }
 // c = camera-frame point (approximate: A + B t), dpos = bound of its distance to the exactly computed point
@@ -81,8 +84,19 @@ __device__ __forceinline__ bool dg_certainly_far(const DgFilter& f, const float*
   const float r2 = c0 * c0 + c1 * c1 + c2 * c2;
   const float rpd = fast_rsqrt(r2);                 // r2 == 0 -> NaN below -> queued
   const float pd = r2 * rpd;
-  // theta = atan2(c2, c0) + pi/2 wrapped to [0, 2pi)
-  const float ax = fabsf(c0), az = fabsf(c2);
+  // the four conventions of cam_to_equi (render_device.cuh) differ in the components that feed atan2 / acos and in how the angle
+  // becomes a pixel: px = t' / (2 pi) * (W - 1), py = phi' / pi * (H - 1) with
+  //   m3d          t = atan2(c2, c0)   t' = wrap(t + pi/2)                  phi' = acos(c1 / (r + 1e-5))
+  //   replica      t = atan2(c0, c2)   t' = t + pi                          phi' = pi - acos(c1 / r)     (= asin + pi/2)
+  //   residential  t = atan2(c2, c0)   t' = t + 3pi/2 (- 2pi if t > pi/2)   phi' = acos(c1 / r)          (= pi/2 - asin)
+  //   CoffeeArea   t = atan2(c1, c0)   t' = 2pi - wrap(t)                   phi' = acos(c2 / r)
+  // a branch taken differently than the exact code moves t' by 2 pi, i.e. the map coordinate from one end of the row to the
+  // other: both ends are within the margin of a texel boundary (or clamped), so such pairs are queued like every boundary case.
+  const int ds = f.dataset;
+  const float num = ds == PGRF_DS_REPLICA_TEST ? c0 : (ds == PGRF_DS_COFFEEAREA ? c1 : c2);
+  const float den = ds == PGRF_DS_REPLICA_TEST ? c2 : c0;
+  const float pc = ds == PGRF_DS_COFFEEAREA ? c2 : c1;
+  const float ax = fabsf(den), az = fabsf(num);
   const float rmx = fast_rcp(fmaxf(ax, az));
   const float q = fminf(ax, az) * rmx;
   const float s = q * q;
@@ -94,12 +108,13 @@ __device__ __forceinline__ bool dg_certainly_far(const DgFilter& f, const float*
   t = fmaf(t, s, 0.9999993443489075f);
   t *= q;
   if (az > ax) t = PGRF_HALF_PI_F - t;
-  if (c0 < 0.f) t = PGRF_PI_F - t;
-  if (c2 < 0.f) t = -t;
-  t += PGRF_HALF_PI_F;
-  if (t < 0.f) t += PGRF_TWO_PI_F;
-  // phi = acos(c1 / (pd + 1e-5))
-  const float xq = c1 * fast_rcp(pd + 1e-5f);
+  if (den < 0.f) t = PGRF_PI_F - t;
+  if (num < 0.f) t = -t;
+  if (ds == PGRF_DS_M3D) { t += PGRF_HALF_PI_F; if (t < 0.f) t += PGRF_TWO_PI_F; }
+  else if (ds == PGRF_DS_REPLICA_TEST) t += PGRF_PI_F;
+  else if (ds == PGRF_DS_RESIDENTIAL) t += (t > PGRF_HALF_PI_F) ? -PGRF_HALF_PI_F : 4.71238898038468985769f;
+  else t = (t < 0.f) ? -t : PGRF_TWO_PI_F - t;
+  const float xq = pc * fast_rcp(pd + (ds == PGRF_DS_M3D ? 1e-5f : 0.f));
   const float aq = fabsf(xq), om = 1.f - aq;
   float ph = fmaf(aq, 0.002251368248835206f, -0.011012386530637741f);
   ph = fmaf(ph, aq, 0.02674933150410652f);
@@ -109,7 +124,7 @@ __device__ __forceinline__ bool dg_certainly_far(const DgFilter& f, const float*
   ph = fmaf(ph, aq, 1.5707961320877075f);
   const float rs = fast_rsqrt(om);                 // om <= 0 -> inf / NaN: the margin below is not finite and the pair is queued
   ph *= om * rs;
-  if (xq < 0.f) ph = PGRF_PI_F - ph;
+  if ((xq < 0.f) != (ds == PGRF_DS_REPLICA_TEST)) ph = PGRF_PI_F - ph;      // replica: phi' = pi - acos
   float ix = fmaf(t, f.sx, f.bx), iy = fmaf(ph, f.sy, f.by);
   ix = fminf(fmaxf(ix, 0.f), f.xmax);
   iy = fminf(fmaxf(iy, 0.f), f.ymax);
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(kDgThreads) depth_guided_kernel(const pgrf_din
   float* opq = lik;
   float* z = lik + nc_pad;
   int* queue = reinterpret_cast<int*>(z + out_pow2);
-  const bool prefilter = !from_dict && a.dataset == PGRF_DS_M3D && g_prefilter_on && a.map_h >= 2 && a.map_w >= 2;
+  const bool prefilter = !from_dict && g_prefilter_on && a.map_h >= 2 && a.map_w >= 2;
   const DgFilter flt = dg_filter(a);
 
   for (long long ray = (long long)blockIdx.x * kDgWarps + warp; ray < a.rn; ray += (long long)gridDim.x * kDgWarps) {

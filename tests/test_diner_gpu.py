@@ -144,21 +144,23 @@ def test_depth2normal_matches_reference(name):
     assert float((torch.nan_to_num(got) - torch.nan_to_num(want)).abs().max()) < 1e-5
 
 
-@pytest.mark.parametrize("kind", ["smooth", "edges", "noise"])
-def test_prefilter_is_exact(kind):
+@pytest.mark.parametrize("kind,dataset", [("smooth", "m3d"), ("edges", "m3d"), ("noise", "m3d"), ("edges", "replica_test"),
+                                          ("edges", "residential"), ("noise", "CoffeeArea"), ("smooth", "CoffeeArea")])
+def test_prefilter_is_exact(kind, dataset):
     """The conservative pre-filter of phase 1 (approximate projection, csrc/depth_guided.cu:dg_certainly_far) must not change a
     single bit: likelihoods and placed samples with the filter == without it, on priors with smooth surfaces, depth edges and noise."""
     from panogrf_b200 import _lib
     from panogrf_b200.render_ops import depth_guided_placement
     lib = _lib.load()
     H, W, rfn, rn = 64, 128, 3, 4096
-    cfg = {"dataset_name": "m3d", "height": H, "width": W, "min_depth": 0.5, "max_depth": 15.0, "n_candidates": 1000,
+    cfg = {"dataset_name": dataset, "height": H, "width": W, "min_depth": 0.5, "max_depth": 15.0, "n_candidates": 1000,
            "n_samples": 64, "n_gaussian": 15, "backface_culling": True, "contain_uniform": False}
     g = torch.Generator().manual_seed(3)
     idx = torch.randperm(H * W, generator=g)[:rn]
     coords = torch.stack([idx % W, idx // W], -1).float()[None].cuda()
     w2c = torch.eye(3, 4)[None].repeat(rfn, 1, 1)
     w2c[0, 2, 3], w2c[1, 2, 3], w2c[2, 0, 3] = 0.5, -0.5, 0.3
+    w2c[2, 1, 3] = 0.2                                   # every axis carries an offset in some view (the conventions permute the axes)
     yy = torch.linspace(0, 3.14159, H)[:, None]
     xx = torch.linspace(0, 6.28318, W)[None, :]
     depth = 3.0 + 1.5 * torch.sin(xx * 2) * torch.sin(yy)

@@ -44,3 +44,23 @@ for label, dmap in (("noise", ref["mvs_depth"]), ("smooth", smooth)):
         print(f"depth_guided_placement[{label}, prefilter={pre}] {rn} rays x 1000 candidates x {rfn} views: {ms:.2f} ms  ({rn * 1000 * rfn / ms / 1e6:.1f} G candidate-views/s)")
         print("  finite", bool(torch.isfinite(z).all()), "sorted", bool((z[..., 1:] >= z[..., :-1]).all()))
     print(f"  [{label}] prefilter on == off bit for bit:", bool(torch.equal(outs[(label, 0)], outs[(label, 1)])))
+
+# the other three pixel conventions (same scene, smooth prior): the filters must stay effective, not only exact
+for ds in ("replica_test", "residential", "CoffeeArea"):
+    cfg2 = dict(cfg, dataset_name=ds)
+    ref2 = dict(ref, mvs_depth=smooth)
+    ts = {}
+    for pre in (0, 1):
+        lib.pgrf_debug_set(b"dg_prefilter", pre)
+        for _ in range(2):
+            z = depth_guided_placement(cfg2, que, ref2, fill, ga)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(3):
+            z = depth_guided_placement(cfg2, que, ref2, fill, ga)
+        e1.record(); torch.cuda.synchronize()
+        ts[pre] = e0.elapsed_time(e1) / 3
+        outs[(ds, pre)] = z
+    print(f"[{ds}] exact {ts[0]:.2f} ms, filtered {ts[1]:.2f} ms, bit-identical: {bool(torch.equal(outs[(ds, 0)], outs[(ds, 1)]))}")
+lib.pgrf_debug_set(b"dg_prefilter", 1)
