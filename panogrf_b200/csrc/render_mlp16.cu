@@ -174,18 +174,28 @@ __device__ __forceinline__ void zero_chunk(unsigned char* dst, int chunk, int m)
   *reinterpret_cast<uint4*>(dst + ((size_t)chunk * ROWS + m) * 16) = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// Footprint record of one row for the cooperative gathers: everything the 8 lanes of a row would otherwise each recompute (neighbour
+// offsets resolved from the border flags, the four bilinear weights) is computed once by the row's own thread.  32 bytes = 2 LDS.128.
 struct __align__(16) FootRec {
   int off;      // texel index of the north-west tap inside the stacked (rfn*h*w) map
-  int dxy;      // bit0: east neighbour inside the map, bit1: south neighbour inside the map
-  float tx, ty;
+  int oe, os;   // float4 offsets of the east / south neighbour (0 when the neighbour is outside the map: its weight is 0 there)
+  int pad;
+  float w0, w1, w2, w3;   // (1-tx)(1-ty), tx(1-ty), (1-tx)ty, tx ty
 };
-__device__ __forceinline__ float4 tap4_rec(const float4* __restrict__ base, const FootRec& f, int stride_x, int stride_y) {
-  const int sx = (f.dxy & 1) ? stride_x : 0, sy = (f.dxy & 2) ? stride_y : 0;
-  const float4 nw = ldg4(base), ne = ldg4(base + sx), sw = ldg4(base + sy), se = ldg4(base + sy + sx);
+__device__ __forceinline__ FootRec make_foot_rec(int view_base, const Footprint& f, int map_w) {
+  FootRec r;
+  r.off = view_base + f.off;
+  r.oe = f.dx ? 8 : 0;
+  r.os = f.dy ? map_w * 8 : 0;
+  r.pad = 0;
   const float tx1 = 1.f - f.tx, ty1 = 1.f - f.ty;
-  const float wnw = tx1 * ty1, wne = f.tx * ty1, wsw = tx1 * f.ty, wse = f.tx * f.ty;
+  r.w0 = tx1 * ty1; r.w1 = f.tx * ty1; r.w2 = tx1 * f.ty; r.w3 = f.tx * f.ty;
+  return r;
+}
+__device__ __forceinline__ float4 tap4_rec(const float4* __restrict__ base, const FootRec& f) {
+  const float4 nw = ldg4(base), ne = ldg4(base + f.oe), sw = ldg4(base + f.os), se = ldg4(base + f.os + f.oe);
   // same products and accumulation order (nw, ne, sw, se) as the scalar form, two channels per instruction
-  const float2 w0 = make_float2(wnw, wnw), w1 = make_float2(wne, wne), w2 = make_float2(wsw, wsw), w3 = make_float2(wse, wse);
+  const float2 w0 = make_float2(f.w0, f.w0), w1 = make_float2(f.w1, f.w1), w2 = make_float2(f.w2, f.w2), w3 = make_float2(f.w3, f.w3);
   float2 lo = fmul2(make_float2(nw.x, nw.y), w0), hi = fmul2(make_float2(nw.z, nw.w), w0);
   lo = ffma2(make_float2(ne.x, ne.y), w1, lo); hi = ffma2(make_float2(ne.z, ne.w), w1, hi);
   lo = ffma2(make_float2(sw.x, sw.y), w2, lo); hi = ffma2(make_float2(sw.z, sw.w), w2, hi);
@@ -296,7 +306,28 @@ struct Render16Params {
   int n_tiles;
   int Mv;                 // samples per tile of the rays kernel (whole rays): rows of one F2 operand tile
   int wait_mode;          // 0: every warp polls the MMA mbarrier; 1: the issuing warp polls, the others wait in a named barrier
+  unsigned dn_magic, dn_shift, mv_magic, mv_shift;   // n / a.dn and n / Mv as multiply-high + shift (fastdiv_gen)
 };
+
+// Unsigned 32-bit division by a launch constant without the ~20-instruction udiv sequence: q = (t + ((n - t) >> 1)) >> shift,
+// t = mulhi(magic, n)  (the "branch-free" form of division by invariant integers; exact for every n < 2^32, d >= 2).
+static void fastdiv_gen(unsigned d, unsigned* magic, unsigned* shift) {
+  int L = 31;
+  while (!((d >> L) & 1u)) --L;                                    // floor(log2 d)
+  if ((d & (d - 1u)) == 0u) { *magic = 0u; *shift = (unsigned)(L - 1); return; }
+  const unsigned long long num = 1ull << (32 + L);
+  unsigned long long m = num / d;
+  const unsigned long long rem = num - m * d;
+  m += m;
+  const unsigned long long twice_rem = rem + rem;
+  if (twice_rem >= d) m += 1;
+  *magic = (unsigned)(m + 1);
+  *shift = (unsigned)L;
+}
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned magic, unsigned shift) {
+  const unsigned t = __umulhi(magic, n);
+  return (t + ((n - t) >> 1)) >> shift;
+}
 
 template <int V>
 __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Render16Params p) {
@@ -315,7 +346,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
   unsigned char* X = smem + SM16_WG + wg * WG_BYTES;
   unsigned char* Y = X + X_BYTES;
   float* SF = reinterpret_cast<float*>(Y + Y_BYTES);
-  FootRec* FP = reinterpret_cast<FootRec*>(SF);   // [2][128] records (dead once the gathers are done)
+  FootRec* FP = reinterpret_cast<FootRec*>(X + 4 * CH);   // [2][128] records of 32 bytes in X chunks 4..7: free between the tile's start and the view pooling
   float* XF = reinterpret_cast<float*>(X);        // x in fp32 [32][128]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM16_BAR) + wg;
   const uint32_t bar_addr = umma::smem_addr(bar);
@@ -387,17 +418,15 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     long long g = (long long)tile * T + t;
     const bool row_valid = (m < M) && (g < p.total);
     if (g >= p.total) g = p.total - 1;
-    const int ray = (int)((unsigned)g / (unsigned)a.dn), s = (int)((unsigned)g - (unsigned)ray * (unsigned)a.dn);   // total < 2^31
+    const int ray = (int)fastdiv((unsigned)g, p.dn_magic, p.dn_shift), s = (int)((unsigned)g - (unsigned)ray * (unsigned)a.dn);   // total < 2^31
 
     // ------------------------------------------------------------ geometry (thread = row)
     const RowGeom rg = row_geometry<true>(a, v, g);
     {
       Footprint f = border_footprint_r(rg.px, rg.py, inv_wm1, inv_hm1, a.rf_h == a.img_h && a.rf_w == a.img_w, a.rf_h, a.rf_w);
-      FootRec r1; r1.off = v * a.rf_h * a.rf_w + f.off; r1.dxy = f.dx | (f.dy << 1); r1.tx = f.tx; r1.ty = f.ty;
-      FP[m] = r1;
+      FP[m] = make_foot_rec(v * a.rf_h * a.rf_w, f, a.rf_w);
       f = border_footprint_r(rg.px, rg.py, inv_wm1, inv_hm1, a.if_h == a.img_h && a.if_w == a.img_w, a.if_h, a.if_w);
-      r1.off = v * a.if_h * a.if_w + f.off; r1.dxy = f.dx | (f.dy << 1); r1.tx = f.tx; r1.ty = f.ty;
-      FP[ROWS + m] = r1;
+      FP[ROWS + m] = make_foot_rec(v * a.if_h * a.if_w, f, a.if_w);
     }
     {   // input of ray_dir_fc.0, one K = 16 step in tensor memory: [dir_diff(4), 1, 1, 0 x10] (the two ones carry the bias)
       const uint32_t h[8] = {umma::pack2(rg.dirdiff[0], rg.dirdiff[1]), umma::pack2(rg.dirdiff[2], rg.dirdiff[3]), 0x3F803F80u, 0u, 0u, 0u, 0u, 0u};
@@ -437,8 +466,8 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
       const FootRec f1 = FP[r], f2 = FP[ROWS + r];
       const float4* b1 = reinterpret_cast<const float4*>(a.ray_feats_cl) + (size_t)f1.off * 8 + cg;
       const float4* b2 = reinterpret_cast<const float4*>(a.img_feats_cl) + (size_t)f2.off * 8 + cg;
-      const float4 rf = tap4_rec(b1, f1, 8, a.rf_w * 8);
-      const float4 imf = tap4_rec(b2, f2, 8, a.if_w * 8);
+      const float4 rf = tap4_rec(b1, f1);
+      const float4 imf = tap4_rec(b2, f2);
       uint2 q;   // 4 channels = half a chunk: chunk cg/2, 8-byte half cg%2
       q.x = umma::pack2(rf.x, rf.y); q.y = umma::pack2(rf.z, rf.w);
       *reinterpret_cast<uint2*>(X + ((size_t)(cg >> 1) * ROWS + r) * 16 + (cg & 1) * 8) = q;
@@ -710,7 +739,7 @@ __global__ void __launch_bounds__(kThreads16, 1) render_mlp_bf16_kernel(const Re
     if (vrow < V) {   // weights = vis / (sum + 1e-8), mean / var of x over views, mean of weights -> the rays kernel's A operand
       const long long gs = (long long)tile * T + t;
       if (gs < p.total) {
-        const unsigned rt = (unsigned)gs / (unsigned)p.Mv, ri = (unsigned)gs - rt * (unsigned)p.Mv;
+        const unsigned rt = fastdiv((unsigned)gs, p.mv_magic, p.mv_shift), ri = (unsigned)gs - rt * (unsigned)p.Mv;
         unsigned char* dst = f2_op + (size_t)rt * kF2TileBytes + (size_t)ri * 16;
         float sum = 0.f;
 #pragma unroll
@@ -834,6 +863,9 @@ int launch_render_mlp_bf16(const pgrf_render_args& a, int V, int T, long long to
   PGRF_REQUIRE(((uintptr_t)a.weights16 & 15) == 0, "render: weights16 must be 16-byte aligned");
   Render16Params p;
   p.a = a; p.V = V; p.T = T; p.M = V * T; p.total = total; p.n_tiles = n_tiles; p.Mv = Mv; p.wait_mode = g_mlp_wait_mode;
+  PGRF_REQUIRE(a.dn >= 2 && Mv >= 2, "render: the bf16 path needs at least 2 samples per ray (dn=%d)", a.dn);
+  fastdiv_gen((unsigned)a.dn, &p.dn_magic, &p.dn_shift);
+  fastdiv_gen((unsigned)Mv, &p.mv_magic, &p.mv_shift);
   const int grid = min((n_tiles + kWG - 1) / kWG, sms);
   int dev = 0;
   PGRF_CUDA(cudaGetDevice(&dev));
