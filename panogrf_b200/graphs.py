@@ -24,9 +24,19 @@ class GraphedForward:
         self._graphs = {}
 
     # ---- bookkeeping -------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _version(t):
+        try:
+            return t._version
+        except RuntimeError:          # tensors created under torch.inference_mode() carry no version counter
+            return None
+
     def _param_state(self):
-        return tuple((p.data_ptr(), p._version) for p in self.module.parameters()) + \
-            tuple((b.data_ptr(), b._version) for b in self.module.buffers())
+        mod = self.module
+        if not hasattr(mod, "parameters"):
+            return ()
+        return tuple((p.data_ptr(), self._version(p)) for p in mod.parameters()) + \
+            tuple((b.data_ptr(), self._version(b)) for b in mod.buffers())
 
     def invalidate(self):
         """Drop every captured graph (call after in-place parameter updates that bypass autograd's version counter)."""
